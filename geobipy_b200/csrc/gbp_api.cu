@@ -1,0 +1,417 @@
+// C-ABI of geobipy_b200 (see include/geobipy_b200.h).  Host side: table construction, device
+// staging, launch configuration.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "gbp_chain.cuh"
+#include "gbp_tables.h"
+
+using namespace gbp;
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+long long g_launches = 0;
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+bool g_ev_valid = false;
+
+int fail(const std::string& m)
+{
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+// device copies of the filter-point table, cached per (device, system)
+struct TableCache {
+    int device = -1;
+    gbp_fdem_system sys;
+    SysHost host;
+    float* d_f32 = nullptr;
+    double* d_f64 = nullptr;
+};
+std::vector<TableCache*> g_cache;
+
+int get_tables(const gbp_fdem_system* sys, TableCache** out)
+{
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (TableCache* c : g_cache)
+        if (c->device == dev && std::memcmp(&c->sys, sys, sizeof(*sys)) == 0) {
+            *out = c;
+            return 0;
+        }
+    TableCache* c = new TableCache();
+    c->device = dev;
+    c->sys = *sys;
+    if (!build_system_tables(*sys, c->host)) {
+        std::string e = c->host.error;
+        delete c;
+        return fail(e);
+    }
+    const size_t n = c->host.tab.size();
+    std::vector<float> f32(n);
+    for (size_t i = 0; i < n; ++i) f32[i] = (float)c->host.tab[i];
+    CK(cudaMalloc(&c->d_f32, n * sizeof(float)));
+    CK(cudaMalloc(&c->d_f64, n * sizeof(double)));
+    CK(cudaMemcpy(c->d_f32, f32.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_f64, c->host.tab.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    g_cache.push_back(c);
+    *out = c;
+    return 0;
+}
+
+int time_begin(cudaStream_t st)
+{
+    if (!g_ev0) {
+        CK(cudaEventCreate(&g_ev0));
+        CK(cudaEventCreate(&g_ev1));
+    }
+    CK(cudaEventRecord(g_ev0, st));
+    return 0;
+}
+int time_end(cudaStream_t st)
+{
+    CK(cudaEventRecord(g_ev1, st));
+    g_ev_valid = true;
+    return 0;
+}
+
+template <typename T> const T* tab_ptr(TableCache* c);
+template <> const float* tab_ptr<float>(TableCache* c) { return c->d_f32; }
+template <> const double* tab_ptr<double>(TableCache* c) { return c->d_f64; }
+
+int sm_count()
+{
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+template <typename T, bool SENS>
+int launch_fdem(TableCache* tc, int B, int l_stride, const int32_t* nl, const double* sig, const double* thk,
+                const double* alt, double* out, double* J, cudaStream_t st)
+{
+    const int threads = 256, wpb = threads / 32;
+    const size_t tab_bytes = ((size_t)TAB_ROWS * tc->host.dev.tab_stride * sizeof(T) + 127) & ~(size_t)127;
+    const size_t per_warp = (2 * KS + GBP_MAXC + (SENS ? GBP_MAXC * KS : 0)) * sizeof(T);
+    const size_t smem = tab_bytes + wpb * per_warp;
+    auto kern = fdem_kernel<T, SENS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int grid = sm_count() * blocks_per_sm;
+    const int need = (B + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (time_begin(st)) return 1;
+    kern<<<grid, threads, smem, st>>>(tc->host.dev, tab_ptr<T>(tc), B, l_stride, nl, sig, thk, alt, out, J);
+    g_launches++;
+    CK(cudaGetLastError());
+    return time_end(st);
+}
+
+template <typename T, int NC>
+int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
+{
+    const size_t tab_bytes = ((size_t)TAB_ROWS * tc->host.dev.tab_stride * sizeof(T) + 127) & ~(size_t)127;
+    const size_t per_warp = sizeof(WarpState<T, NC>);
+    int dev = 0, max_smem = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int warps = (int)(((size_t)max_smem - tab_bytes - 1024) / per_warp);
+    if (warps > 16) warps = 16;
+    const char* env = std::getenv("GBP_WARPS_PER_CTA");
+    if (env && std::atoi(env) > 0 && std::atoi(env) < warps) warps = std::atoi(env);
+    if (warps < 1) return fail("not enough shared memory for one chain");
+    const int threads = warps * 32;
+    const size_t smem = tab_bytes + (size_t)warps * per_warp;
+    auto kern = rjmcmc_kernel<T, NC>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count();
+    const int need = (P.B + warps - 1) / warps;
+    if (grid > need) grid = need;
+    ChainParams Q = P;
+    Q.n_warps_total = grid * warps;
+    // device-side work counter: chains beyond the first wave are claimed dynamically
+    CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (time_begin(st)) return 1;
+    kern<<<grid, threads, smem, st>>>(tc->host.dev, tab_ptr<T>(tc), Q);
+    g_launches++;
+    CK(cudaGetLastError());
+    return time_end(st);
+}
+
+int* g_counter[64] = {nullptr};
+int get_counter(int** out)
+{
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail("device index out of range");
+    if (!g_counter[dev]) CK(cudaMalloc(&g_counter[dev], 256));
+    *out = g_counter[dev];
+    return 0;
+}
+
+int check_options(const gbp_options* o)
+{
+    if (o->max_layers < 1 || o->max_layers > GBP_MAXL) return fail("max_layers must be in [1, 30]");
+    if (o->n_markov_chains < 1) return fail("n_markov_chains must be >= 1");
+    if (o->update_plot_every < 1) return fail("update_plot_every must be >= 1");
+    if (!(o->min_width > 0.0) || !(o->max_edge > o->min_edge) || !(o->min_edge > 0.0))
+        return fail("invalid depth limits");
+    if (!(o->min_width * o->max_layers < o->max_edge))
+        return fail("min_width * max_layers must be < max_edge (RectilinearMesh1D.set_priors)");
+    if (o->n_sigma_bins < 1 || o->n_err_bins < 1) return fail("invalid bin counts");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gbp_version(void) { return "geobipy_b200 0.1.0 (sm_100a)"; }
+const char* gbp_last_error(void) { return g_err.c_str(); }
+
+int gbp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gbp_n_depth(const gbp_options* o)
+{
+    const double stop = 1.1 * o->max_edge, step = 0.5 * o->min_width;
+    return (int)std::ceil(stop / step) - 1;
+}
+
+int gbp_filter_points(const gbp_fdem_system* sys)
+{
+    int n = 0;
+    for (int f = 0; f < sys->n_freq; ++f) {
+        const int t = sys->tid[f];
+        if (t == 1 || t == 9) n += GBP_NJ0;
+        if (t == 1 || t == 3 || t == 7) n += GBP_NJ1;
+    }
+    return n;
+}
+
+// SURVEY.md section 8(d) count convention: per abscissa 17(L+1) + 58(L-1) + 15 + 65 = 75L + 39 flops
+double gbp_flops_per_forward(const gbp_fdem_system* sys, int L)
+{
+    return (double)gbp_filter_points(sys) * (75.0 * (double)L + 39.0);
+}
+
+int64_t gbp_launch_count(void) { return g_launches; }
+
+int gbp_last_kernel_ms(float* ms)
+{
+    if (!g_ev_valid) return fail("no kernel has been timed yet");
+    CK(cudaEventSynchronize(g_ev1));
+    CK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    return 0;
+}
+
+int gbp_fdem_forward(const gbp_fdem_system* sys, int B, int l_stride, const int32_t* d_nlayers, const double* d_sigma,
+                     const double* d_thickness, const double* d_altitude, double* d_out, int precision, void* stream)
+{
+    if (B <= 0) return 0;
+    if (l_stride < 1 || l_stride > GBP_MAXL) return fail("l_stride must be in [1, 30]");
+    TableCache* tc;
+    if (get_tables(sys, &tc)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == GBP_PRECISION_F32)
+        return launch_fdem<float, false>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, nullptr, st);
+    if (precision == GBP_PRECISION_F64)
+        return launch_fdem<double, false>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, nullptr, st);
+    return fail("precision must be 32 or 64");
+}
+
+int gbp_fdem_sensitivity(const gbp_fdem_system* sys, int B, int l_stride, const int32_t* d_nlayers,
+                         const double* d_sigma, const double* d_thickness, const double* d_altitude, double* d_out,
+                         double* d_J, int precision, void* stream)
+{
+    if (B <= 0) return 0;
+    if (l_stride < 1 || l_stride > GBP_MAXL) return fail("l_stride must be in [1, 30]");
+    TableCache* tc;
+    if (get_tables(sys, &tc)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == GBP_PRECISION_F32)
+        return launch_fdem<float, true>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, d_J, st);
+    if (precision == GBP_PRECISION_F64)
+        return launch_fdem<double, true>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, d_J, st);
+    return fail("precision must be 32 or 64");
+}
+
+static int fdem_host(bool sens, const gbp_fdem_system* sys, int B, int l_stride, const int32_t* nlayers,
+                     const double* sigma, const double* thickness, const double* altitude, double* out, double* J,
+                     int precision, int device)
+{
+    if (B <= 0) return 0;
+    for (int b = 0; b < B; ++b)
+        if (nlayers[b] < 1 || nlayers[b] > l_stride) return fail("nlayers out of range");
+    CK(cudaSetDevice(device));
+    const int C = 2 * sys->n_freq;
+    int32_t* d_nl = nullptr;
+    double *d_s = nullptr, *d_t = nullptr, *d_a = nullptr, *d_o = nullptr, *d_J = nullptr;
+    const size_t nm = (size_t)B * l_stride;
+    CK(cudaMalloc(&d_nl, B * sizeof(int32_t)));
+    CK(cudaMalloc(&d_s, nm * sizeof(double)));
+    CK(cudaMalloc(&d_t, nm * sizeof(double)));
+    CK(cudaMalloc(&d_a, B * sizeof(double)));
+    CK(cudaMalloc(&d_o, (size_t)B * C * sizeof(double)));
+    if (sens) CK(cudaMalloc(&d_J, (size_t)B * C * l_stride * sizeof(double)));
+    CK(cudaMemcpy(d_nl, nlayers, B * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_s, sigma, nm * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_t, thickness, nm * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_a, altitude, B * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = sens ? gbp_fdem_sensitivity(sys, B, l_stride, d_nl, d_s, d_t, d_a, d_o, d_J, precision, nullptr)
+                  : gbp_fdem_forward(sys, B, l_stride, d_nl, d_s, d_t, d_a, d_o, precision, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(std::string("kernel: ") + cudaGetErrorString(e));
+    }
+    if (!rc) {
+        CK(cudaMemcpy(out, d_o, (size_t)B * C * sizeof(double), cudaMemcpyDeviceToHost));
+        if (sens) CK(cudaMemcpy(J, d_J, (size_t)B * C * l_stride * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_nl);
+    cudaFree(d_s);
+    cudaFree(d_t);
+    cudaFree(d_a);
+    cudaFree(d_o);
+    cudaFree(d_J);
+    return rc;
+}
+
+int gbp_fdem_forward_host(const gbp_fdem_system* sys, int B, int l_stride, const int32_t* nlayers, const double* sigma,
+                          const double* thickness, const double* altitude, double* out, int precision, int device)
+{
+    return fdem_host(false, sys, B, l_stride, nlayers, sigma, thickness, altitude, out, nullptr, precision, device);
+}
+
+int gbp_fdem_sensitivity_host(const gbp_fdem_system* sys, int B, int l_stride, const int32_t* nlayers,
+                              const double* sigma, const double* thickness, const double* altitude, double* out,
+                              double* J, int precision, int device)
+{
+    return fdem_host(true, sys, B, l_stride, nlayers, sigma, thickness, altitude, out, J, precision, device);
+}
+
+int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, const double* d_data,
+                   const double* d_altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                   const gbp_chain_buffers* d_buf, int precision, void* stream)
+{
+    if (B <= 0) return 0;
+    if (check_options(opt)) return 1;
+    if (!d_buf || !d_buf->scalars) return fail("gbp_chain_buffers.scalars is required");
+    TableCache* tc;
+    if (get_tables(sys, &tc)) return 1;
+    ChainParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.opt = *opt;
+    P.B = B;
+    P.n_depth = gbp_n_depth(opt);
+    P.C = 2 * sys->n_freq;
+    P.data = d_data;
+    P.altitude = d_altitude;
+    P.seed = seed;
+    P.first_index = first_index;
+    P.max_iterations = max_iterations;
+    P.out = *d_buf;
+    if (get_counter(&P.work_counter)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool small = P.C <= 12;
+    if (precision == GBP_PRECISION_F32)
+        return small ? launch_chain<float, 12>(tc, P, st) : launch_chain<float, GBP_MAXC>(tc, P, st);
+    if (precision == GBP_PRECISION_F64)
+        return small ? launch_chain<double, 12>(tc, P, st) : launch_chain<double, GBP_MAXC>(tc, P, st);
+    return fail("precision must be 32 or 64");
+}
+
+int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int B, const double* data,
+                        const double* altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                        const gbp_chain_buffers* h, int precision, int device)
+{
+    if (B <= 0) return 0;
+    if (check_options(opt)) return 1;
+    if (!h || !h->scalars) return fail("gbp_chain_buffers.scalars is required");
+    CK(cudaSetDevice(device));
+    const int C = 2 * sys->n_freq, nd = gbp_n_depth(opt), ml = opt->max_layers;
+    const size_t N2 = 2 * (size_t)opt->n_markov_chains;
+    struct Item {
+        void* const* host;
+        void** dev;
+        size_t bytes;
+    };
+    gbp_chain_buffers d;
+    std::memset(&d, 0, sizeof(d));
+    const Item items[] = {
+        {(void* const*)&h->hitmap, (void**)&d.hitmap, (size_t)B * opt->n_sigma_bins * nd * sizeof(int32_t)},
+        {(void* const*)&h->edges_hist, (void**)&d.edges_hist, (size_t)B * nd * sizeof(int32_t)},
+        {(void* const*)&h->ncells_hist, (void**)&d.ncells_hist, (size_t)B * (ml + 1) * sizeof(int32_t)},
+        {(void* const*)&h->rel_hist, (void**)&d.rel_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
+        {(void* const*)&h->add_hist, (void**)&d.add_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
+        {(void* const*)&h->misfit_trace, (void**)&d.misfit_trace, (size_t)B * N2 * sizeof(double)},
+        {(void* const*)&h->accept_trace, (void**)&d.accept_trace, (size_t)B * N2},
+        {(void* const*)&h->best_sigma, (void**)&d.best_sigma, (size_t)B * ml * sizeof(double)},
+        {(void* const*)&h->best_edges, (void**)&d.best_edges, (size_t)B * (ml + 1) * sizeof(double)},
+        {(void* const*)&h->cur_sigma, (void**)&d.cur_sigma, (size_t)B * ml * sizeof(double)},
+        {(void* const*)&h->cur_edges, (void**)&d.cur_edges, (size_t)B * (ml + 1) * sizeof(double)},
+        {(void* const*)&h->scalars, (void**)&d.scalars, (size_t)B * GBP_NSCALARS * sizeof(double)},
+    };
+    double *d_data = nullptr, *d_alt = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        for (const Item& it : items)
+            if (*it.dev) cudaFree(*it.dev);
+        cudaFree(d_data);
+        cudaFree(d_alt);
+    };
+#define CKC(call)                                                                      \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            cleanup();                                                                 \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+        }                                                                              \
+    } while (0)
+    for (const Item& it : items)
+        if (*it.host) {
+            CKC(cudaMalloc(it.dev, it.bytes));
+            CKC(cudaMemsetAsync(*it.dev, 0, it.bytes, nullptr));
+        }
+    CKC(cudaMalloc(&d_data, (size_t)B * C * sizeof(double)));
+    CKC(cudaMalloc(&d_alt, (size_t)B * sizeof(double)));
+    CKC(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    CKC(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    rc = gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, &d, precision, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(std::string("kernel: ") + cudaGetErrorString(e));
+    }
+    if (!rc)
+        for (const Item& it : items)
+            if (*it.host) CKC(cudaMemcpy(*it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost));
+    cleanup();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// Small complex / warp / RNG helpers for the sm_100a kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gbp {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------- real-type dispatch
+template <typename T> struct rt;
+template <> struct rt<float> {
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    // |x| stays below ~40 rad on this path (|Im(2ut)| <= Re(2ut), and e^-Re is 0 beyond ~88)
+    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+};
+template <> struct rt<double> {
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+};
+
+// ---------------------------------------------------------------- complex
+template <typename T> struct cx {
+    T re, im;
+};
+template <typename T> __device__ __forceinline__ cx<T> mk(T a, T b) { return cx<T>{a, b}; }
+template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> b) { return {a.re + b.re, a.im + b.im}; }
+template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return {a.re - b.re, a.im - b.im}; }
+template <typename T> __device__ __forceinline__ cx<T> operator*(cx<T> a, cx<T> b)
+{
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+template <typename T> __device__ __forceinline__ cx<T> operator*(cx<T> a, T s) { return {a.re * s, a.im * s}; }
+template <typename T> __device__ __forceinline__ cx<T> cinv(cx<T> a)
+{
+    T d = rt<T>::rcp(a.re * a.re + a.im * a.im);
+    return {a.re * d, -a.im * d};
+}
+// sqrt of a + ib with b >= 0 (first-quadrant result)
+template <typename T> __device__ __forceinline__ cx<T> csqrt_q1(T a, T b)
+{
+    T m = rt<T>::sqrt(a * a + b * b);
+    T t = rt<T>::sqrt(T(0.5) * (m + fabs(a)));
+    T o = b * rt<T>::rcp(t + t);
+    return (a >= T(0)) ? cx<T>{t, o} : cx<T>{o, t};
+}
+// exp(z)
+template <typename T> __device__ __forceinline__ cx<T> cexp_(cx<T> z)
+{
+    T e = rt<T>::exp(z.re), s, c;
+    rt<T>::sincos(z.im, &s, &c);
+    return {e * c, e * s};
+}
+
+// ---------------------------------------------------------------- warp reductions
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
+struct Rng {
+    uint32_t seed_lo, seed_hi, snd_lo, snd_hi;
+    unsigned long long block;
+};
+__device__ __forceinline__ void philox_block(const Rng& g, unsigned long long block, uint32_t out[4])
+{
+    uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = g.snd_lo, c3 = g.snd_hi;
+    uint32_t k0 = g.seed_lo, k1 = g.seed_hi;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// one block -> two 53-bit uniforms in [0,1)
+__device__ __forceinline__ void uniforms_at(const Rng& g, unsigned long long block, double* ua, double* ub)
+{
+    uint32_t x[4];
+    philox_block(g, block, x);
+    *ua = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6)) * (1.0 / 9007199254740992.0);
+    *ub = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6)) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double rng_uniform(Rng& g)
+{
+    double a, b;
+    uniforms_at(g, g.block, &a, &b);
+    g.block++;
+    return a;
+}
+// Box-Muller pair of the block at an explicit counter
+__device__ __forceinline__ void normal2_at(const Rng& g, unsigned long long block, double* z0, double* z1)
+{
+    double a, b;
+    uniforms_at(g, block, &a, &b);
+    double r = sqrt(-2.0 * log(1.0 - a));
+    double s, c;
+    sincos(6.283185307179586476925286766559 * b, &s, &c);
+    *z0 = r * c;
+    *z1 = r * s;
+}
+__device__ __forceinline__ double rng_normal(Rng& g)
+{
+    double z0, z1;
+    normal2_at(g, g.block, &z0, &z1);
+    g.block++;
+    return z0;
+}
+
+}  // namespace gbp

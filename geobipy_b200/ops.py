@@ -1,0 +1,247 @@
+"""Batched operators over the C-ABI: FDEM forward / Jacobian and the rjMCMC sampler.
+
+Two calling conventions, as in include/geobipy_b200.h:
+  * numpy arrays  -> the ``*_host`` entry points (copies inside the call);
+  * torch CUDA tensors -> the device entry points, stream-ordered on torch's current stream.
+PyTorch is used for device memory / streams only.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BUFFER_FIELDS, NSCALARS, PRECISION_F32, PRECISION_F64, ChainBuffersC, FdemSystemC, OptionsC)
+
+_ORI = {"x": 0, "y": 1, "z": 2}
+
+
+def make_system_struct(freq, tor, tmom, tx, ty, tz, ror, rmom, rx, ry, rz):
+    """gbp_fdem_system from the columns of an .stm file (FdemSystem.read, FdemSystem.py:146-183)."""
+    n = len(freq)
+    if n < 1 or n > _lib.MAXF:
+        raise ValueError("a system must have 1..%d frequencies" % _lib.MAXF)
+    s = FdemSystemC()
+    s.n_freq = n
+    for i in range(n):
+        to = tor[i] if isinstance(tor[i], (int, np.integer)) else _ORI[str(tor[i]).strip()]
+        ro = ror[i] if isinstance(ror[i], (int, np.integer)) else _ORI[str(ror[i]).strip()]
+        s.tid[i] = 1 + 3 * int(ro) + int(to)  # FdemSystem.tensor_id, FdemSystem.py:199-203
+        s.freq[i], s.tmom[i], s.tx[i], s.ty[i], s.tz[i] = float(freq[i]), float(tmom[i]), float(tx[i]), float(ty[i]), float(tz[i])
+        s.rmom[i], s.rx[i], s.ry[i], s.rz[i] = float(rmom[i]), float(rx[i]), float(ry[i]), float(rz[i])
+    return s
+
+
+def resolve_system_struct():
+    """RESOLVE (documentation_source/source/supplementary/data/resolve.stm)."""
+    return make_system_struct(
+        [380.0, 1776.0, 3345.0, 8171.0, 41020.0, 129550.0], list("zzxzzz"), [1, 1, -1, 1, 1, 1], [0] * 6, [0] * 6,
+        [0] * 6, list("zzxzzz"), [1] * 6, [7.93, 7.91, 9.03, 7.91, 7.91, 7.89], [0] * 6, [0] * 6)
+
+
+_OPTION_DEFAULTS = dict(
+    n_markov_chains=100000, update_plot_every=5000, max_layers=30, solve_parameter=0, solve_gradient=1,
+    solve_relative_error=1, solve_additive_error=1, reset_limit=1, min_edge=0.1, max_edge=200.0, min_width=1.0,
+    p_birth=1.0 / 6.0, p_death=1.0 / 6.0, p_move=1.0 / 6.0, p_none=0.5, factor=10.0, gradient_std=1.5,
+    covariance_scaling=1.0, rel_init=0.05, rel_min=0.001, rel_max=0.5, rel_prop_var=1e-6, add_init=5.0,
+    add_min=3.0, add_max=20.0, add_prop_var=1e-6, n_sigma_bins=250, n_err_bins=99, sigma_bins_nstd=4.0,
+    burn_in_min_iter=5000)
+
+# reference option-file keys -> gbp_options fields (resolve_options; user_parameters.py:40-44)
+_REFERENCE_KEYS = dict(
+    n_markov_chains="n_markov_chains", update_plot_every="update_plot_every",
+    maximum_number_of_layers="max_layers", solve_parameter="solve_parameter", solve_gradient="solve_gradient",
+    solve_relative_error="solve_relative_error", solve_additive_error="solve_additive_error",
+    reset_limit="reset_limit", minimum_depth="min_edge", maximum_depth="max_edge", minimum_thickness="min_width",
+    probability_of_birth="p_birth", probability_of_death="p_death", probability_of_perturb="p_move",
+    probability_of_no_change="p_none", factor="factor", gradient_standard_deviation="gradient_std",
+    covariance_scaling="covariance_scaling", initial_relative_error="rel_init",
+    minimum_relative_error="rel_min", maximum_relative_error="rel_max",
+    relative_error_proposal_variance="rel_prop_var", initial_additive_error="add_init",
+    minimum_additive_error="add_min", maximum_additive_error="add_max",
+    additive_error_proposal_variance="add_prop_var")
+
+
+def make_options(**kw):
+    """gbp_options.  Accepts gbp_options field names or the reference's option-file keys.
+
+    Defaults = documentation_source/.../options_files/resolve_options with the ``None`` entries
+    replaced as user_parameters.__init__ does (factor 10, gradient std 1.5, covariance scaling 1).
+    """
+    vals = dict(_OPTION_DEFAULTS)
+    for k, v in kw.items():
+        if v is None:
+            continue
+        k = _REFERENCE_KEYS.get(k, k)
+        if k not in vals:
+            continue  # keys of the reference options file that do not concern the sampler kernel
+        vals[k] = v
+    o = OptionsC()
+    for k, v in vals.items():
+        if isinstance(getattr(o, k), int):
+            v = int(v)
+        else:
+            v = float(np.asarray(v).reshape(-1)[0])
+        setattr(o, k, v)
+    return o
+
+
+def n_depth(opt):
+    return int(_lib.load().gbp_n_depth(ctypes.addressof(opt)))
+
+
+def posterior_grids(opt, halfspace):
+    """Bin edges of the posterior arrays, as the reference builds them.
+
+    sigma edges: Model.set_posteriors (Model.py:666-684); depth edges: RectilinearMesh1D.set_posteriors
+    (RectilinearMesh1D.py:1438-1455); error edges: DataPoint.set_*_error_posterior (DataPoint.py:668-695).
+    """
+    s = np.log(1.0 + opt.factor)
+    t = opt.sigma_bins_nstd * s
+    sig = np.exp(np.linspace(-t, t, opt.n_sigma_bins + 1) + np.log(halfspace))
+    depth = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
+    rel = np.exp(np.linspace(np.log(opt.rel_min), np.log(opt.rel_max), opt.n_err_bins + 1))
+    add = np.exp(np.linspace(np.log(opt.add_min), np.log(opt.add_max), opt.n_err_bins + 1))
+    return dict(sigma_edges=sig, depth_edges=depth, rel_edges=rel, add_edges=add,
+                ncells_centres=np.arange(0.0, opt.max_layers + 1.0))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def fdem_forward(system, nlayers, sigma, thickness, altitude, precision=PRECISION_F32, device=0, sensitivity=False):
+    """Predicted data [B, 2F] (and Jacobian [B, 2F, Lstride] w.r.t. ln sigma) for B soundings.
+
+    sigma / thickness are [B, Lstride] (Lstride <= 30); entries beyond nlayers[b] are ignored, the last
+    layer is an infinite half-space.  numpy in -> numpy out (host path); torch CUDA in -> torch out.
+    """
+    lib = _lib.require_cuda()
+    if _is_torch(sigma):
+        import torch
+        assert sigma.is_cuda and sigma.dtype == torch.float64 and sigma.is_contiguous()
+        B, ls = sigma.shape
+        F = system.n_freq
+        thickness = thickness.contiguous()
+        altitude = altitude.contiguous()
+        nlayers = nlayers.to(torch.int32).contiguous()
+        out = torch.empty((B, 2 * F), dtype=torch.float64, device=sigma.device)
+        st = torch.cuda.current_stream(sigma.device).cuda_stream
+        with torch.cuda.device(sigma.device):
+            if sensitivity:
+                J = torch.empty((B, 2 * F, ls), dtype=torch.float64, device=sigma.device)
+                _lib.check(lib.gbp_fdem_sensitivity(ctypes.addressof(system), B, ls, nlayers.data_ptr(), sigma.data_ptr(),
+                                                    thickness.data_ptr(), altitude.data_ptr(), out.data_ptr(),
+                                                    J.data_ptr(), precision, st))
+                return out, J
+            _lib.check(lib.gbp_fdem_forward(ctypes.addressof(system), B, ls, nlayers.data_ptr(), sigma.data_ptr(),
+                                            thickness.data_ptr(), altitude.data_ptr(), out.data_ptr(), precision, st))
+            return out
+    sigma = _np(np.atleast_2d(sigma), np.float64)
+    thickness = _np(np.atleast_2d(thickness), np.float64)
+    B, ls = sigma.shape
+    nlayers = _np(np.atleast_1d(nlayers), np.int32)
+    altitude = _np(np.atleast_1d(altitude), np.float64)
+    assert thickness.shape == sigma.shape and nlayers.shape == (B,) and altitude.shape == (B,)
+    F = system.n_freq
+    out = np.empty((B, 2 * F))
+    if sensitivity:
+        J = np.empty((B, 2 * F, ls))
+        _lib.check(lib.gbp_fdem_sensitivity_host(ctypes.addressof(system), B, ls, nlayers.ctypes.data, sigma.ctypes.data,
+                                                 thickness.ctypes.data, altitude.ctypes.data, out.ctypes.data,
+                                                 J.ctypes.data, precision, device))
+        return out, J
+    _lib.check(lib.gbp_fdem_forward_host(ctypes.addressof(system), B, ls, nlayers.ctypes.data, sigma.ctypes.data,
+                                         thickness.ctypes.data, altitude.ctypes.data, out.ctypes.data, precision, device))
+    return out
+
+
+def chain_buffer_shapes(opt, B):
+    nd = n_depth(opt)
+    N2 = 2 * opt.n_markov_chains
+    ml = opt.max_layers
+    return dict(
+        hitmap=((B, opt.n_sigma_bins, nd), np.int32), edges_hist=((B, nd), np.int32),
+        ncells_hist=((B, ml + 1), np.int32), rel_hist=((B, opt.n_err_bins), np.int32),
+        add_hist=((B, opt.n_err_bins), np.int32), misfit_trace=((B, N2), np.float64),
+        accept_trace=((B, N2), np.uint8), best_sigma=((B, ml), np.float64), best_edges=((B, ml + 1), np.float64),
+        cur_sigma=((B, ml), np.float64), cur_edges=((B, ml + 1), np.float64), scalars=((B, NSCALARS), np.float64))
+
+
+DEFAULT_OUTPUTS = BUFFER_FIELDS
+
+
+def rjmcmc_run(system, opt, data, altitude, seed=0, first_index=0, max_iterations=0, precision=PRECISION_F32,
+               device=0, outputs=DEFAULT_OUTPUTS, buffers=None):
+    """Run B independent rjMCMC chains (one per sounding) on the GPU.
+
+    data [B, 2F] observed ppm, altitude [B].  numpy in -> dict of numpy arrays (host path, copies inside the
+    C call); torch CUDA in -> dict of torch tensors left on the device (``buffers`` may supply pre-zeroed
+    result tensors to reuse).
+    """
+    lib = _lib.require_cuda()
+    outputs = tuple(outputs)
+    if "scalars" not in outputs:
+        outputs = outputs + ("scalars",)
+    if _is_torch(data):
+        import torch
+        assert data.is_cuda and data.dtype == torch.float64
+        data = data.contiguous()
+        altitude = altitude.contiguous()
+        B = data.shape[0]
+        shapes = chain_buffer_shapes(opt, B)
+        tdt = {np.int32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}
+        res = {}
+        cb = ChainBuffersC()
+        for name in outputs:
+            shp, dt = shapes[name]
+            if buffers is not None and name in buffers:
+                t = buffers[name]
+                t.zero_()
+            else:
+                t = torch.zeros(shp, dtype=tdt[dt], device=data.device)
+            res[name] = t
+            setattr(cb, name, t.data_ptr())
+        st = torch.cuda.current_stream(data.device).cuda_stream
+        with torch.cuda.device(data.device):
+            _lib.check(lib.gbp_rjmcmc_run(ctypes.addressof(system), ctypes.addressof(opt), B, data.data_ptr(),
+                                          altitude.data_ptr(), int(seed), int(first_index), int(max_iterations),
+                                          ctypes.addressof(cb), precision, st))
+        return res
+    data = _np(np.atleast_2d(data), np.float64)
+    altitude = _np(np.atleast_1d(altitude), np.float64)
+    B = data.shape[0]
+    assert data.shape[1] == 2 * system.n_freq and altitude.shape == (B,)
+    shapes = chain_buffer_shapes(opt, B)
+    res = {}
+    cb = ChainBuffersC()
+    for name in outputs:
+        shp, dt = shapes[name]
+        a = buffers[name] if (buffers is not None and name in buffers) else np.zeros(shp, dtype=dt)
+        res[name] = a
+        setattr(cb, name, a.ctypes.data)
+    _lib.check(lib.gbp_rjmcmc_run_host(ctypes.addressof(system), ctypes.addressof(opt), B, data.ctypes.data,
+                                       altitude.ctypes.data, int(seed), int(first_index), int(max_iterations),
+                                       ctypes.addressof(cb), precision, device))
+    return res
+
+
+def last_kernel_ms():
+    ms = ctypes.c_float(0.0)
+    _lib.check(_lib.load().gbp_last_kernel_ms(ctypes.byref(ms)))
+    return float(ms.value)
+
+
+def launch_count():
+    return int(_lib.load().gbp_launch_count())
+
+
+def flops_per_forward(system, n_layers):
+    return float(_lib.load().gbp_flops_per_forward(ctypes.addressof(system), int(n_layers)))
+
+
+def filter_points(system):
+    return int(_lib.load().gbp_filter_points(ctypes.addressof(system)))

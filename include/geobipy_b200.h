@@ -1,0 +1,152 @@
+/* geobipy_b200 - C-ABI of the B200-native per-sounding rjMCMC EM inversion path.
+ *
+ * The reference (DOI-USGS/geobipy) is pure Python; it has no FFI seam, its seams are the
+ * Python call signatures listed in SURVEY.md section 8(b).  This header is the drop-in
+ * boundary those seams bind to (ctypes stub: INTEGRATION.md):
+ *
+ *   gbp_fdem_forward*      replaces nbFdem1dfwd / fdem1dfwd / FdemDataPoint.forward
+ *                          (geobipy/src/classes/forwardmodelling/Electromagnetic/FD/fdem1d_numba.py:25,
+ *                           fdem1d.py:10, classes/data/datapoint/FdemDataPoint.py:524-545)
+ *   gbp_fdem_sensitivity*  replaces nbFdem1dsen / fdem1dsen / FdemDataPoint.sensitivity
+ *                          (fdem1d_numba.py:72, fdem1d.py:87, FdemDataPoint.py:548-557)
+ *   gbp_rjmcmc_run*        replaces Inference1D.initialize + Inference1D.infer for a batch of
+ *                          soundings (geobipy/src/inversion/Inference1D.py:353, :633), i.e. the
+ *                          loop Inference3D.infer_serial / _infer_mpi_worker_task drive
+ *                          (geobipy/src/inversion/Inference3D.py:458-492, :587-635).
+ *
+ * Plain pointers and sizes only.  "_host" entry points take HOST buffers and do the
+ * host<->device copies themselves; the others take DEVICE pointers and a cudaStream_t
+ * (passed as void*) and are stream ordered.  All functions return 0 on success, non-zero
+ * on error (message: gbp_last_error()).  There is no CPU fallback: without a CUDA device
+ * every compute entry point fails.
+ */
+#ifndef GEOBIPY_B200_H
+#define GEOBIPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBP_MAXF 16              /* max frequencies of one FDEM system */
+#define GBP_MAXC (2 * GBP_MAXF)  /* max data channels (in-phase + quadrature) */
+#define GBP_MAXL 30              /* max layers (resolve_options: maximum_number_of_layers) */
+
+#define GBP_PRECISION_F32 32     /* forward / Jacobian arithmetic in fp32 (fast path) */
+#define GBP_PRECISION_F64 64     /* forward / Jacobian arithmetic in fp64 (validation path) */
+
+/* One FDEM acquisition system = the rows of an .stm file (FdemSystem.read, FdemSystem.py:146-183).
+ * tid = 1 + 3*rx_orientation + tx_orientation, x=0 y=1 z=2 (FdemSystem.py:199-203): zz=9, xx=1, 3, 7. */
+typedef struct {
+    int32_t n_freq;
+    int32_t tid[GBP_MAXF];
+    double freq[GBP_MAXF];
+    double tmom[GBP_MAXF], tx[GBP_MAXF], ty[GBP_MAXF], tz[GBP_MAXF];
+    double rmom[GBP_MAXF], rx[GBP_MAXF], ry[GBP_MAXF], rz[GBP_MAXF];
+} gbp_fdem_system;
+
+/* Sampler options = the keys of a reference options file (resolve_options) with the defaults of
+ * user_parameters.py:40-44 and Inference1D.__init__ (Inference1D.py:78-96). */
+typedef struct {
+    int32_t n_markov_chains;
+    int32_t update_plot_every;
+    int32_t max_layers;                 /* maximum_number_of_layers, <= GBP_MAXL */
+    int32_t solve_parameter, solve_gradient, solve_relative_error, solve_additive_error;
+    int32_t reset_limit;
+    double min_edge, max_edge, min_width;  /* minimum_depth, maximum_depth, minimum_thickness */
+    double p_birth, p_death, p_move, p_none;
+    double factor;                      /* value prior std = ln(1 + factor) */
+    double gradient_std;                /* gradient_standard_deviation */
+    double covariance_scaling;
+    double rel_init, rel_min, rel_max, rel_prop_var;
+    double add_init, add_min, add_max, add_prop_var;
+    int32_t n_sigma_bins;               /* 250 (Model.set_posteriors, Model.py:675) */
+    int32_t n_err_bins;                 /* 99  (Uniform.bins default) */
+    double sigma_bins_nstd;             /* 4.0 */
+    int32_t burn_in_min_iter;           /* 5000 (Inference1D.py:726) */
+    int32_t pad_;
+} gbp_options;
+
+/* Per-chain scalar slots of gbp_chain_buffers.scalars ([B][GBP_NSCALARS] doubles). */
+enum {
+    GBP_S_ITER = 0, GBP_S_BURNED_IN, GBP_S_BURNED_IN_ITER, GBP_S_BEST_ITER, GBP_S_BEST_K, GBP_S_CUR_K,
+    GBP_S_HALFSPACE, GBP_S_FAILED, GBP_S_N_ACCEPT, GBP_S_N_FORWARD, GBP_S_N_SENS, GBP_S_BEST_POSTERIOR,
+    GBP_S_CUR_REL, GBP_S_CUR_ADD, GBP_S_CUR_MISFIT, GBP_S_CUR_PRIOR, GBP_S_CUR_LIKELIHOOD,
+    GBP_S_BEST_REL, GBP_S_BEST_ADD, GBP_S_N_RESETS, GBP_S_N_BIRTH, GBP_S_N_DEATH, GBP_S_N_MOVE, GBP_S_N_NONE,
+    GBP_NSCALARS = 32
+};
+
+/* Posterior / result arrays of a batch of B chains - exactly what Inference1D.writeHdf
+ * serialises per sounding (Inference1D.py:1050-1090).  Any pointer may be NULL to skip that
+ * output, except scalars.  Row-major, leading dimension B. */
+typedef struct {
+    int32_t *hitmap;        /* [B][n_sigma_bins][n_depth]   model.values.posterior.counts   */
+    int32_t *edges_hist;    /* [B][n_depth]                 model.mesh.edges.posterior      */
+    int32_t *ncells_hist;   /* [B][max_layers + 1]          model.mesh.nCells.posterior     */
+    int32_t *rel_hist;      /* [B][n_err_bins]              datapoint.relative_error.posterior */
+    int32_t *add_hist;      /* [B][n_err_bins]              datapoint.additive_error.posterior */
+    double *misfit_trace;   /* [B][2 * n_markov_chains]     data_misfit_v                   */
+    uint8_t *accept_trace;  /* [B][2 * n_markov_chains]     acceptance_v                    */
+    double *best_sigma;     /* [B][max_layers]   NaN padded best_model.values               */
+    double *best_edges;     /* [B][max_layers + 1]          best_model.mesh.edges           */
+    double *cur_sigma;      /* [B][max_layers]              model.values                    */
+    double *cur_edges;      /* [B][max_layers + 1]          model.mesh.edges                */
+    double *scalars;        /* [B][GBP_NSCALARS]                                            */
+} gbp_chain_buffers;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char *gbp_version(void);
+const char *gbp_last_error(void);
+int gbp_device_count(void);
+/* depth cells of the posterior grids: len(arange(0, 1.1*max_edge, 0.5*min_width)) - 1
+ * (RectilinearMesh1D.set_posteriors, RectilinearMesh1D.py:1450) */
+int gbp_n_depth(const gbp_options *opt);
+/* algorithmic flop / special-function count of one forward (SURVEY.md section 8(d) convention) */
+double gbp_flops_per_forward(const gbp_fdem_system *sys, int n_layers);
+/* number of (frequency, abscissa) filter points one forward evaluates (RESOLVE: 860) */
+int gbp_filter_points(const gbp_fdem_system *sys);
+/* kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t gbp_launch_count(void);
+/* mean duration [ms] and launch count of the last gbp_rjmcmc_run / forward kernel, measured with CUDA
+ * events on the launching stream (valid after the stream has been synchronised) */
+int gbp_last_kernel_ms(float *ms);
+
+/* ---- FDEM forward / Jacobian, DEVICE pointers --------------------------------------------- */
+/* sigma, thickness: [B][l_stride] (thickness of the last layer is ignored = infinite half-space);
+ * out: [B][2F] (real parts then imaginary parts, ppm); J: [B][2F][l_stride] = d out / d ln(sigma). */
+int gbp_fdem_forward(const gbp_fdem_system *sys, int B, int l_stride, const int32_t *d_nlayers,
+                     const double *d_sigma, const double *d_thickness, const double *d_altitude,
+                     double *d_out, int precision, void *stream);
+int gbp_fdem_sensitivity(const gbp_fdem_system *sys, int B, int l_stride, const int32_t *d_nlayers,
+                         const double *d_sigma, const double *d_thickness, const double *d_altitude,
+                         double *d_out, double *d_J, int precision, void *stream);
+
+/* ---- FDEM forward / Jacobian, HOST pointers (copies inside) -------------------------------- */
+int gbp_fdem_forward_host(const gbp_fdem_system *sys, int B, int l_stride, const int32_t *nlayers,
+                          const double *sigma, const double *thickness, const double *altitude,
+                          double *out, int precision, int device);
+int gbp_fdem_sensitivity_host(const gbp_fdem_system *sys, int B, int l_stride, const int32_t *nlayers,
+                              const double *sigma, const double *thickness, const double *altitude,
+                              double *out, double *J, int precision, int device);
+
+/* ---- rjMCMC ------------------------------------------------------------------------------- */
+/* Runs B independent chains (one warp each, persistent kernel).  data: [B][2F] observed ppm
+ * (<= 0 or NaN = inactive channel, EmDataPoint.active); altitude: [B].
+ * Random stream of chain b: Philox4x32-10, key = seed, counter = (block, first_index + b).
+ * max_iterations > 0 caps the number of accept_reject+update pairs per chain (tests);
+ * 0 = run to the reference's own termination rule (Inference1D.infer :650-677).
+ * d_buf: struct in HOST memory whose members are DEVICE pointers. */
+int gbp_rjmcmc_run(const gbp_fdem_system *sys, const gbp_options *opt, int B, const double *d_data,
+                   const double *d_altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                   const gbp_chain_buffers *d_buf, int precision, void *stream);
+/* Same with HOST buffers: uploads data/altitude, allocates + zeroes device results, runs,
+ * downloads every non-NULL member of h_buf. */
+int gbp_rjmcmc_run_host(const gbp_fdem_system *sys, const gbp_options *opt, int B, const double *data,
+                        const double *altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                        const gbp_chain_buffers *h_buf, int precision, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,111 @@
+/* TEST INFRASTRUCTURE ONLY (oracle) - see fdem1d_oracle.c / rjmcmc_oracle.c headers. */
+#ifndef GBO_ORACLE_H
+#define GBO_ORACLE_H
+
+#include <stdint.h>
+
+#define GBO_MAXL 64  /* max layers the oracle accepts */
+#define GBO_MAXF 16  /* max frequencies per system   */
+#define GBO_MAXC (2 * GBO_MAXF)
+
+/* One FDEM acquisition system (one row per frequency of an .stm file,
+ * geobipy/src/classes/system/FdemSystem.py:146-183).
+ * tid = 1 + 3*rx_orientation + tx_orientation with x=0,y=1,z=2 (FdemSystem.py:199-203). */
+typedef struct {
+    int32_t n_freq;
+    int32_t tid[GBO_MAXF];
+    double freq[GBO_MAXF];
+    double tmom[GBO_MAXF], tx[GBO_MAXF], ty[GBO_MAXF], tz[GBO_MAXF];
+    double rmom[GBO_MAXF], rx[GBO_MAXF], ry[GBO_MAXF], rz[GBO_MAXF];
+} gbo_fdem_system;
+
+/* Sampler options (documentation_source/.../options_files/resolve_options,
+ * geobipy/src/inversion/user_parameters.py:40-44, Inference1D.py:78-96). */
+typedef struct {
+    int32_t n_markov_chains;
+    int32_t update_plot_every;
+    int32_t max_layers;
+    int32_t solve_parameter, solve_gradient, solve_relative_error, solve_additive_error;
+    int32_t reset_limit;
+    double min_edge, max_edge, min_width;
+    double p_birth, p_death, p_move, p_none;
+    double factor;                 /* value prior std = ln(1 + factor) */
+    double gradient_std;
+    double covariance_scaling;     /* alpha of the stochastic-Newton step */
+    double rel_init, rel_min, rel_max, rel_prop_var;
+    double add_init, add_min, add_max, add_prop_var;
+    int32_t n_sigma_bins;          /* 250 */
+    int32_t n_err_bins;            /* 99 */
+    double sigma_bins_nstd;        /* 4.0 */
+    int32_t burn_in_min_iter;      /* 5000 (Inference1D.py:726) */
+    int32_t pad_;
+} gbo_options;
+
+/* Everything one chain produces (caller allocates; sizes from gbo_sizes()). */
+typedef struct {
+    int32_t *hitmap;        /* [n_sigma_bins][n_depth] */
+    int32_t *edges_hist;    /* [n_depth] */
+    int32_t *ncells_hist;   /* [max_layers + 1] */
+    int32_t *rel_hist;      /* [n_err_bins] */
+    int32_t *add_hist;      /* [n_err_bins] */
+    double *misfit_trace;   /* [2 * n_markov_chains] */
+    uint8_t *accept_trace;  /* [2 * n_markov_chains] */
+    double *best_sigma;     /* [max_layers] */
+    double *best_edges;     /* [max_layers + 1] */
+    double *cur_sigma;      /* [max_layers] */
+    double *cur_edges;      /* [max_layers + 1] */
+    double *scalars;        /* [GBO_NSCALARS], see below */
+} gbo_chain_out;
+
+enum {
+    GBO_S_ITER = 0, GBO_S_BURNED_IN, GBO_S_BURNED_IN_ITER, GBO_S_BEST_ITER, GBO_S_BEST_K, GBO_S_CUR_K,
+    GBO_S_HALFSPACE, GBO_S_FAILED, GBO_S_N_ACCEPT, GBO_S_N_FORWARD, GBO_S_N_SENS, GBO_S_BEST_POSTERIOR,
+    GBO_S_CUR_REL, GBO_S_CUR_ADD, GBO_S_CUR_MISFIT, GBO_S_CUR_PRIOR, GBO_S_CUR_LIKELIHOOD,
+    GBO_S_BEST_REL, GBO_S_BEST_ADD, GBO_S_N_RESETS, GBO_S_N_BIRTH, GBO_S_N_DEATH, GBO_S_N_MOVE, GBO_S_N_NONE,
+    GBO_NSCALARS = 32
+};
+
+int gbo_n_depth(const gbo_options *o);
+
+void gbo_fdem_geometry(const gbo_fdem_system *sys, double altitude, double *tHeight, double *rHeight,
+                       double *scale, double *xsep, double *sep);
+int gbo_fdem_forward(const gbo_fdem_system *sys, double altitude, int L, const double *sigma,
+                     const double *thickness, double *out);
+int gbo_fdem_sensitivity(const gbo_fdem_system *sys, double altitude, int L, const double *sigma,
+                         const double *thickness, double *J);
+
+/* Philox4x32-10 block (Salmon et al. 2011). */
+void gbo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Deterministic term evaluation for one proposed transition (used to pin the restatement
+ * against records captured from the live reference).  See rjmcmc_oracle.c. */
+typedef struct {
+    /* inputs */
+    int32_t k;                    /* layers of remapped/test model */
+    int32_t action;               /* 0 birth 1 death 2 move 3 none */
+    double altitude;
+    double sigma_ref;             /* half-space conductivity (value prior mean) */
+    double edges[GBO_MAXL + 1];   /* edges of remapped == test model, edges[k] = inf */
+    double sigma_remap[GBO_MAXL];
+    double sigma_test[GBO_MAXL];
+    double rel_cur, add_cur;      /* errors of the current datapoint (used for the Hessian) */
+    double rel_test, add_test;    /* errors of the proposed datapoint */
+    double data[GBO_MAXC];        /* observed */
+    double J_in[GBO_MAXC * GBO_MAXL];   /* stored Jacobian (row-major [C][k]) used when action == none */
+    double pred_in[GBO_MAXC];           /* stored predicted data used when action == none */
+    /* outputs */
+    double hessian[GBO_MAXL * GBO_MAXL];  /* precision A = Wm'Wm + J'Wd'WdJ, row-major [k][k] */
+    double gradient[GBO_MAXL];
+    double newton_mean[GBO_MAXL];         /* exp(ln sigma_remap - alpha * A^-1 gradient) */
+    double pred_test[GBO_MAXC];
+    double misfit_test, prior_test, likelihood_test, proposal, proposal1;
+} gbo_transition;
+
+int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *opt, gbo_transition *t);
+
+/* Full chain for one sounding.  Random stream: Philox4x32-10, key = (seed lo, seed hi),
+ * counter = (block lo, block hi, sounding lo, sounding hi). */
+int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const double *data, double altitude,
+                  uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out);
+
+#endif

@@ -1,0 +1,892 @@
+/* TEST INFRASTRUCTURE ONLY (oracle) - never linked or called by the product path.
+ *
+ * Plain-C fp64 restatement of the reference's per-sounding trans-dimensional
+ * (reversible-jump) MCMC sampler for one FDEM sounding.  One function call = one chain.
+ *
+ * PARITY PIN: the deterministic terms (Hessian, gradient, Newton mean, misfit, prior,
+ * likelihood, forward/reverse proposal densities, posterior bin indices) are checked by
+ * tests/test_oracle_golden.py against transition records captured from the live reference
+ * in the build container (tests/golden/transitions.npz, made by tests/golden/make_golden.py),
+ * and the stationary behaviour (posterior statistics, acceptance rate, layer-count
+ * distribution) against reference chains (tests/golden/ref_chain_*.npz).  The reference's
+ * NumPy random stream (PCG64DXSM + SVD-based multivariate_normal + data-dependent retry
+ * loops) is not reproducible off-host, so the random stream here is our own
+ * (Philox4x32-10, counter based) and is the bit-level twin of the CUDA kernel's.
+ *
+ * Reference followed (paths relative to geobipy/src/):
+ *   inversion/Inference1D.py:353-464  initialize            -> chain_init()
+ *   inversion/Inference1D.py:485-535  initialize_model      -> chain_init()
+ *   classes/data/datapoint/EmDataPoint.py:148-186 find_best_halfspace -> best_halfspace()
+ *   inversion/Inference1D.py:537-631  accept_reject         -> chain_step()
+ *   inversion/Inference1D.py:633-688  infer (loop control)  -> gbo_run_chain()
+ *   inversion/Inference1D.py:705-790  update                -> chain_update()
+ *   classes/mesh/RectilinearMesh1D.py:993-1120 perturb      -> perturb_structure()
+ *   classes/mesh/RectilinearMesh1D.py:643-689 delete_edge, :805-838 insert_edge
+ *   classes/mesh/RectilinearMesh1D.py:691-714 gradient, :747-786 gradient_operator
+ *   classes/model/Model.py:368-419 stochastic_newton_perturbation, :421-430 prior_derivative
+ *   classes/model/Model.py:533-575 probability, :213-234 gradient_probability
+ *   classes/model/Model.py:577-660 proposal_probabilities
+ *   classes/model/Model.py:819-847 update_parameter_posterior
+ *   classes/mesh/RectilinearMesh1D.py:1122-1160 piecewise_constant_interpolate
+ *   classes/mesh/RectilinearMesh1D.py:1594-1610 update_posteriors
+ *   classes/data/datapoint/DataPoint.py:268-282 std, :340-349 prior_derivative,
+ *       :351-395 probability, :491-525 likelihood / data_misfit, :531-573 perturb
+ *   classes/statistics/StatArray.py:578-638 propose (<= 10 prior-respecting retries)
+ *   classes/statistics/MvNormalDistribution.py:183-216 log-pdf
+ *   classes/statistics/CategoricalDistribution.py:67-82 rng
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "oracle.h"
+
+#define LOG2PI 1.8378770664093454835606594728112
+
+/* ------------------------------------------------------------------ Philox4x32-10 */
+void gbo_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+typedef struct {
+    uint64_t seed, sounding, block;
+} rng_t;
+
+/* One Philox block -> two 53-bit uniforms in [0,1). */
+static void rng_block(rng_t *g, double *ua, double *ub)
+{
+    uint32_t ctr[4] = {(uint32_t)g->block, (uint32_t)(g->block >> 32), (uint32_t)g->sounding, (uint32_t)(g->sounding >> 32)};
+    uint32_t key[2] = {(uint32_t)g->seed, (uint32_t)(g->seed >> 32)};
+    uint32_t x[4];
+    gbo_philox4x32_10(ctr, key, x);
+    g->block++;
+    *ua = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6)) * (1.0 / 9007199254740992.0);
+    *ub = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6)) * (1.0 / 9007199254740992.0);
+}
+static double rng_uniform(rng_t *g)
+{
+    double a, b;
+    rng_block(g, &a, &b);
+    return a;
+}
+/* Box-Muller pair from one block. */
+static void rng_normal2(rng_t *g, double *z0, double *z1)
+{
+    double a, b;
+    rng_block(g, &a, &b);
+    double r = sqrt(-2.0 * log(1.0 - a));
+    double th = 2.0 * M_PI * b;
+    *z0 = r * cos(th);
+    *z1 = r * sin(th);
+}
+static double rng_normal(rng_t *g)
+{
+    double z0, z1;
+    rng_normal2(g, &z0, &z1);
+    return z0;
+}
+
+/* ------------------------------------------------------------------ small dense SPD algebra */
+/* In-place lower Cholesky of row-major n x n (ld = n).  Returns 0 on success. */
+static int cholesky(int n, double *A)
+{
+    for (int j = 0; j < n; ++j) {
+        double d = A[j * n + j];
+        for (int p = 0; p < j; ++p) d -= A[j * n + p] * A[j * n + p];
+        if (!(d > 0.0)) return -1;
+        d = sqrt(d);
+        A[j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = A[i * n + j];
+            for (int p = 0; p < j; ++p) s -= A[i * n + p] * A[j * n + p];
+            A[i * n + j] = s / d;
+        }
+    }
+    return 0;
+}
+/* Solve L y = b (forward) */
+static void solve_L(int n, const double *Lm, const double *b, double *y)
+{
+    for (int i = 0; i < n; ++i) {
+        double s = b[i];
+        for (int p = 0; p < i; ++p) s -= Lm[i * n + p] * y[p];
+        y[i] = s / Lm[i * n + i];
+    }
+}
+/* Solve L^T x = y (backward) */
+static void solve_LT(int n, const double *Lm, const double *y, double *x)
+{
+    for (int i = n - 1; i >= 0; --i) {
+        double s = y[i];
+        for (int p = i + 1; p < n; ++p) s -= Lm[p * n + i] * x[p];
+        x[i] = s / Lm[i * n + i];
+    }
+}
+/* |L^T v|^2 = v' A v */
+static double quad_L(int n, const double *Lm, const double *v)
+{
+    double q = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int i = j; i < n; ++i) s += Lm[i * n + j] * v[i];
+        q += s * s;
+    }
+    return q;
+}
+
+/* ------------------------------------------------------------------ model / datapoint pieces */
+typedef struct {
+    int k;
+    double edges[GBO_MAXL + 2]; /* edges[0] = 0, edges[k] = inf */
+    double sigma[GBO_MAXL + 1];
+} model_t;
+
+typedef struct {
+    double rel, add;
+    double pred[GBO_MAXC];
+    double J[GBO_MAXC * GBO_MAXL]; /* row-major [C][k] */
+    int Jk;                        /* columns of J */
+} dpoint_t;
+
+static void model_thickness(const model_t *m, double *thk)
+{
+    for (int i = 0; i < m->k; ++i) thk[i] = m->edges[i + 1] - m->edges[i];
+}
+
+int gbo_n_depth(const gbo_options *o)
+{
+    /* numpy.arange(0, 1.1*max_edge, 0.5*min_width) has ceil(stop/step) entries = edges
+     * (RectilinearMesh1D.py:1450) -> cells = entries - 1 */
+    double stop = 1.1 * o->max_edge, step = 0.5 * o->min_width;
+    int n_edges = (int)ceil(stop / step);
+    return n_edges - 1;
+}
+
+/* DataPoint.std (DataPoint.py:268-282): variance_i = (rel * d_i)^2 + add^2 */
+static void data_variance(int C, const double *data, double rel, double add, double *var)
+{
+    for (int i = 0; i < C; ++i) {
+        double a = rel * data[i];
+        var[i] = a * a + add * add;
+    }
+}
+
+/* EmDataPoint.active (EmDataPoint.py:44-56): observed > 0 and not NaN */
+static int is_active(double d) { return d > 0.0; }
+
+static double data_misfit(int C, const double *data, const double *pred, const double *var)
+{
+    double s = 0.0;
+    for (int i = 0; i < C; ++i)
+        if (is_active(data[i])) {
+            double t = (1.0 / sqrt(var[i])) * (pred[i] - data[i]);
+            s += t * t;
+        }
+    return s;
+}
+
+/* MvNormal log-pdf with diagonal covariance (MvNormalDistribution.py:209-216) */
+static double data_likelihood(int C, const double *data, const double *pred, const double *var)
+{
+    double n = 0.0, logdet = 0.0, q = 0.0;
+    for (int i = 0; i < C; ++i)
+        if (is_active(data[i])) {
+            n += 1.0;
+            logdet += log(var[i]);
+            double r = pred[i] - data[i];
+            q += r * r / var[i];
+        }
+    return -(0.5 * n) * LOG2PI - 0.5 * logdet - 0.5 * q;
+}
+
+/* Uniform(log=True).probability(log=True) (UniformDistribution.py:109-121) */
+static double log_uniform_logpdf(double x, double mn, double mx)
+{
+    double lx = log(x), a = log(mn), b = log(mx);
+    if (lx < a || lx > b) return -INFINITY;
+    return -log(b - a);
+}
+
+static double datapoint_probability(const gbo_options *o, double rel, double add)
+{
+    double p = 0.0;
+    if (o->solve_relative_error) p += log_uniform_logpdf(rel, o->rel_min, o->rel_max);
+    if (o->solve_additive_error) p += log_uniform_logpdf(add, o->add_min, o->add_max);
+    return p;
+}
+
+/* Model.probability (Model.py:533-575) with value_bounds = None */
+static double model_probability(const gbo_options *o, const model_t *m, double sigma_ref)
+{
+    /* Uniform(1, kmax).probability(k) = scipy uniform.logpdf(k, 1, kmax - 1) */
+    double p = (m->k >= 1 && m->k <= o->max_layers) ? -log((double)o->max_layers - 1.0) : -INFINITY;
+    if (o->solve_parameter) {
+        double s2 = log(1.0 + o->factor);
+        s2 *= s2;
+        double q = 0.0;
+        for (int i = 0; i < m->k; ++i) {
+            double d = log(m->sigma[i]) - log(sigma_ref);
+            q += d * d / s2;
+        }
+        p += -(0.5 * m->k) * LOG2PI - 0.5 * m->k * log(s2) - 0.5 * q;
+    }
+    if (o->solve_gradient) {
+        double g2 = o->gradient_std * o->gradient_std;
+        if (m->k == 1) {
+            /* Model.py:230-232: a virtual 2-layer model with equal values -> gradient 0 */
+            p += -0.5 * LOG2PI - 0.5 * log(g2);
+        } else {
+            int n = m->k - 1;
+            double q = 0.0;
+            for (int i = 0; i < n; ++i) {
+                /* RectilinearMesh1D.py:713: diff(ln sigma) / ln(width_i) */
+                double g = (log(m->sigma[i + 1]) - log(m->sigma[i])) / log(m->edges[i + 1] - m->edges[i]);
+                q += g * g / g2;
+            }
+            p += -(0.5 * n) * LOG2PI - 0.5 * n * log(g2) - 0.5 * q;
+        }
+    }
+    return p;
+}
+
+/* Wm'Wm = values-prior precision + Wz' (1/g^2) Wz (Model.py:421-430, RectilinearMesh1D.py:747-786) */
+static void prior_operator(const gbo_options *o, const model_t *m, double *A)
+{
+    const int k = m->k;
+    double s2 = log(1.0 + o->factor);
+    s2 *= s2;
+    const double g2 = o->gradient_std * o->gradient_std;
+    memset(A, 0, sizeof(double) * k * k);
+    for (int i = 0; i < k; ++i) A[i * k + i] = 1.0 / s2;
+    if (k == 1) {
+        A[0] += 1.0 / g2; /* gradient_operator = ones((1,1)) */
+        return;
+    }
+    double x[GBO_MAXL];
+    model_thickness(m, x);
+    if (k == 2) x[k - 1] = x[0];
+    else x[k - 1] = x[k - 2] + (m->edges[k - 1] - m->edges[0]);
+    for (int i = 0; i < k - 1; ++i) {
+        double c2c = 0.5 * (x[i] + x[i + 1]);
+        double t = 1.0 / (c2c * (double)(k - 1));
+        double t2 = t * t / g2;
+        A[i * k + i] += t2;
+        A[(i + 1) * k + (i + 1)] += t2;
+        A[i * k + (i + 1)] -= t2;
+        A[(i + 1) * k + i] -= t2;
+    }
+}
+
+/* A = Wm'Wm + J' Wd'Wd J ; g = Wm'Wm (ln sigma - ln sigma_ref) + J' Wd'Wd (pred - data)
+ * (Model.py:250-272, :347-357; DataPoint.py:340-349) */
+static void hessian_gradient(const gbo_options *o, const model_t *m, double sigma_ref, int C, const double *data,
+                             const double *var, const double *J, const double *pred, double *A, double *g)
+{
+    const int k = m->k;
+    double P[GBO_MAXL * GBO_MAXL];
+    prior_operator(o, m, P);
+    for (int i = 0; i < k; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += P[i * k + j] * (log(m->sigma[j]) - log(sigma_ref));
+        g[i] = s;
+    }
+    if (A) memcpy(A, P, sizeof(double) * k * k);
+    for (int c = 0; c < C; ++c) {
+        if (!is_active(data[c])) continue;
+        double w = 1.0 / var[c];
+        double r = (pred[c] - data[c]) * w;
+        for (int i = 0; i < k; ++i) {
+            g[i] += J[c * k + i] * r;
+            if (A)
+                for (int j = 0; j < k; ++j) A[i * k + j] += J[c * k + i] * w * J[c * k + j];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ structure proposal */
+enum { ACT_BIRTH = 0, ACT_DEATH = 1, ACT_MOVE = 2, ACT_NONE = 3 };
+
+static double min_width_of(int nedges, const double *z)
+{
+    double h = INFINITY;
+    for (int i = 0; i + 1 < nedges; ++i) {
+        double d = z[i + 1] - z[i];
+        if (d < h) h = d;
+    }
+    return h;
+}
+
+/* RectilinearMesh1D.perturb (:993-1120).  Returns the action; writes the remapped model. */
+static int perturb_structure(const gbo_options *o, rng_t *g, const model_t *cur, model_t *out)
+{
+    const double cum0 = o->p_birth, cum1 = cum0 + o->p_death, cum2 = cum1 + o->p_move, cum3 = cum2 + o->p_none;
+    const int k = cur->k;
+    for (;;) {
+        int event;
+        for (;;) {
+            /* Categorical.rng: searchsorted(cumsum(p), U) (left) */
+            double u = rng_uniform(g);
+            event = (u <= cum0) ? 0 : (u <= cum1) ? 1 : (u <= cum2) ? 2 : 3;
+            (void)cum3;
+            if (k == 1 && (event == 1 || event == 2)) continue;
+            if (k == o->max_layers && event == 0) continue;
+            break;
+        }
+        if (event == ACT_NONE) {
+            *out = *cur;
+            return ACT_NONE;
+        }
+        if (event == ACT_BIRTH) {
+            int ok = 0, pos = 0;
+            double e = 0.0;
+            double z[GBO_MAXL + 3];
+            for (int tries = 1; tries <= 10; ++tries) {
+                double lo = log(o->min_edge), hi = log(o->max_edge);
+                e = exp(lo + (hi - lo) * rng_uniform(g));
+                pos = 0; /* searchsorted(edges, e) (left) */
+                while (pos <= k && cur->edges[pos] < e) ++pos;
+                for (int i = 0; i < pos; ++i) z[i] = cur->edges[i];
+                z[pos] = e;
+                for (int i = pos; i <= k; ++i) z[i + 1] = cur->edges[i];
+                double h = min_width_of(k + 2, z);
+                if (tries == 10) break; /* 10th try always restarts (:1078-1080) */
+                if (h > o->min_width) { ok = 1; break; }
+            }
+            if (!ok) continue;
+            out->k = k + 1;
+            memcpy(out->edges, z, sizeof(double) * (k + 2));
+            /* values.insert(pos, values[pos-1]) (:835) */
+            for (int i = 0; i < pos; ++i) out->sigma[i] = cur->sigma[i];
+            out->sigma[pos] = cur->sigma[pos - 1];
+            for (int i = pos; i < k; ++i) out->sigma[i + 1] = cur->sigma[i];
+            return ACT_BIRTH;
+        }
+        if (event == ACT_DEATH) {
+            int i = (int)(rng_uniform(g) * (double)(k - 1)) + 1; /* :1085 */
+            out->k = k - 1;
+            for (int j = 0; j < i; ++j) out->edges[j] = cur->edges[j];
+            for (int j = i + 1; j <= k; ++j) out->edges[j - 1] = cur->edges[j];
+            double val = 0.5 * (cur->sigma[i - 1] + cur->sigma[i]); /* :684-686 */
+            for (int j = 0; j < i; ++j) out->sigma[j] = cur->sigma[j];
+            for (int j = i + 1; j < k; ++j) out->sigma[j - 1] = cur->sigma[j];
+            out->sigma[i - 1] = val;
+            return ACT_DEATH;
+        }
+        /* ACT_MOVE (:1088-1118) */
+        {
+            int ok = 0;
+            double z[GBO_MAXL + 2];
+            for (int tries = 1; tries <= 10; ++tries) {
+                memcpy(z, cur->edges, sizeof(double) * (k + 1));
+                int i = (int)(1.0 + ((double)k - 1.0) * rng_uniform(g)); /* uniform(1, nEdges-1) */
+                double zn = rng_normal(g);
+                double sgn = (zn > 0.0) ? 1.0 : (zn < 0.0 ? -1.0 : 0.0);
+                double dz = sgn * o->min_width * rng_uniform(g);
+                z[i] += dz;
+                double h = min_width_of(k + 1, z);
+                if (tries == 10) break;
+                if (h > o->min_width && z[1] > o->min_edge && z[k - 1] < o->max_edge) { ok = 1; break; }
+            }
+            if (!ok) continue;
+            *out = *cur;
+            memcpy(out->edges, z, sizeof(double) * (k + 1));
+            return ACT_MOVE;
+        }
+    }
+}
+
+/* StatArray.propose with imposePrior (StatArray.py:578-638) for a 1-D MvLogNormal random walk */
+static double propose_error(rng_t *g, double cur, double prop_var, double mn, double mx)
+{
+    double sd = sqrt(prop_var);
+    double x = exp(log(cur) + sd * rng_normal(g));
+    int tries = 0;
+    while (log_uniform_logpdf(x, mn, mx) == -INFINITY) {
+        x = exp(log(cur) + sd * rng_normal(g));
+        tries++;
+        if (tries == 10) return cur;
+    }
+    return x;
+}
+
+/* ------------------------------------------------------------------ posterior accumulators */
+typedef struct {
+    int n_depth, n_sig, n_err, kmax;
+    double depth_step;
+    double sig_lo, sig_dx;   /* ln(sigma) bins */
+    double rel_lo, rel_dx, add_lo, add_dx; /* ln(err) bins */
+} grids_t;
+
+static void make_grids(const gbo_options *o, double sigma_ref, grids_t *G)
+{
+    G->n_depth = gbo_n_depth(o);
+    G->depth_step = 0.5 * o->min_width;
+    G->n_sig = o->n_sigma_bins;
+    G->n_err = o->n_err_bins;
+    G->kmax = o->max_layers;
+    /* Model.set_posteriors :666-684 + MvLogNormal.bins: linspace(-nStd*s, nStd*s, n+1) + ln(sigma_ref) */
+    double s = log(1.0 + o->factor);
+    G->sig_lo = log(sigma_ref) - o->sigma_bins_nstd * s;
+    G->sig_dx = 2.0 * o->sigma_bins_nstd * s / (double)G->n_sig;
+    /* DataPoint.set_relative_error_posterior :668-695 + Uniform.bins: linspace(ln min, ln max, n+1) */
+    G->rel_lo = log(o->rel_min);
+    G->rel_dx = (log(o->rel_max) - log(o->rel_min)) / (double)G->n_err;
+    G->add_lo = log(o->add_min);
+    G->add_dx = (log(o->add_max) - log(o->add_min)) / (double)G->n_err;
+}
+
+/* searchsorted(edges, v, 'right') - 1 clipped, for uniform edges lo + i*dx */
+static int uniform_bin(double v, double lo, double dx, int n)
+{
+    double f = floor((v - lo) / dx);
+    int i = (f < 0.0) ? 0 : (f > (double)(n - 1) ? n - 1 : (int)f);
+    /* guard against round-off of the division at an edge */
+    while (i + 1 < n && v >= lo + (double)(i + 1) * dx) ++i;
+    while (i > 0 && v < lo + (double)i * dx) --i;
+    return i;
+}
+
+/* value at depth y of np.interp on the duplicated-edge staircase (RectilinearMesh1D.py:1148-1158) */
+static double staircase_value(const gbo_options *o, const model_t *m, double y)
+{
+    const int k = m->k;
+    if (k == 1) return m->sigma[0];
+    /* xp = [e0*1.000001, e1, e1*1.000001, e2, ..., e_k := max_edge], fp = [v0,v0,v1,v1,...] */
+    for (int i = 1; i < k; ++i) {
+        double e = m->edges[i];
+        double e2 = e * 1.000001;
+        if (y < e) return m->sigma[i - 1];
+        if (y < e2) { /* linear ramp between the two layers */
+            double t = (y - e) / (e2 - e);
+            return m->sigma[i - 1] + t * (m->sigma[i] - m->sigma[i - 1]);
+        }
+    }
+    (void)o;
+    return m->sigma[k - 1];
+}
+
+static void accumulate_posteriors(const gbo_options *o, const grids_t *G, const model_t *m, double rel, double add,
+                                  gbo_chain_out *out)
+{
+    /* nCells histogram (RectilinearMesh1D.py:1597) */
+    out->ncells_hist[m->k] += 1;
+    /* interface histogram (:1600-1610) with ratio = 0.5 */
+    for (int i = 1; i < m->k; ++i) {
+        double r = exp(log(m->sigma[i]) - log(m->sigma[i - 1]));
+        if (r <= 0.5 || r >= 1.5) {
+            double d = m->edges[i];
+            if (d >= 0.0 && d < (double)G->n_depth * G->depth_step) {
+                int j = uniform_bin(d, 0.0, G->depth_step, G->n_depth);
+                out->edges_hist[j] += 1;
+            }
+        }
+    }
+    /* hitmap (Model.py:819-847) */
+    for (int j = 0; j < G->n_depth; ++j) {
+        double y = ((double)j + 0.5) * G->depth_step;
+        double v = staircase_value(o, m, y);
+        int b = uniform_bin(log(v), G->sig_lo, G->sig_dx, G->n_sig);
+        out->hitmap[(size_t)b * G->n_depth + j] += 1;
+    }
+    /* error histograms (EmDataPoint.py:225-239) */
+    if (o->solve_relative_error) out->rel_hist[uniform_bin(log(rel), G->rel_lo, G->rel_dx, G->n_err)] += 1;
+    if (o->solve_additive_error) out->add_hist[uniform_bin(log(add), G->add_lo, G->add_dx, G->n_err)] += 1;
+}
+
+static void reset_posteriors(const gbo_options *o, const grids_t *G, gbo_chain_out *out)
+{
+    memset(out->hitmap, 0, sizeof(int32_t) * (size_t)G->n_sig * G->n_depth);
+    memset(out->edges_hist, 0, sizeof(int32_t) * G->n_depth);
+    memset(out->ncells_hist, 0, sizeof(int32_t) * (o->max_layers + 1));
+    memset(out->rel_hist, 0, sizeof(int32_t) * G->n_err);
+    memset(out->add_hist, 0, sizeof(int32_t) * G->n_err);
+}
+
+/* ------------------------------------------------------------------ the chain */
+typedef struct {
+    const gbo_fdem_system *sys;
+    const gbo_options *o;
+    int C;
+    double data[GBO_MAXC];
+    double altitude;
+    double sigma_ref;
+    grids_t G;
+    rng_t rng;
+    model_t model;
+    dpoint_t dp;
+    double misfit, prior, likelihood, posterior;
+    int64_t iteration;
+    int burned_in;
+    int64_t burned_in_iter, best_iter;
+    model_t best_model;
+    double best_rel, best_add, best_posterior;
+    int accepted;
+    int n_zero_acc, n_resets, limiters;
+    int64_t n_accept, n_forward, n_sens, n_act[4];
+    int n_active;
+} chain_t;
+
+static void forward(chain_t *c, const model_t *m, double *pred)
+{
+    double thk[GBO_MAXL];
+    model_thickness(m, thk);
+    gbo_fdem_forward(c->sys, c->altitude, m->k, m->sigma, thk, pred);
+    c->n_forward++;
+}
+static void sensitivity(chain_t *c, const model_t *m, dpoint_t *dp)
+{
+    double thk[GBO_MAXL];
+    model_thickness(m, thk);
+    gbo_fdem_sensitivity(c->sys, c->altitude, m->k, m->sigma, thk, dp->J);
+    dp->Jk = m->k;
+    c->n_sens++;
+}
+
+/* EmDataPoint.find_best_halfspace: argmin of misfit over logspace(-4, 4, 100) */
+static double best_halfspace(chain_t *c, double rel, double add)
+{
+    double var[GBO_MAXC], pred[GBO_MAXC];
+    data_variance(c->C, c->data, rel, add, var);
+    model_t m;
+    m.k = 1;
+    m.edges[0] = 0.0;
+    m.edges[1] = INFINITY;
+    double best = INFINITY, best_c = 0.0;
+    for (int i = 0; i < 100; ++i) {
+        /* numpy.logspace(-4, 4, 100) = 10 ** linspace(-4, 4, 100) */
+        double e = -4.0 + (double)i * (8.0 / 99.0);
+        if (i == 99) e = 4.0;
+        m.sigma[0] = pow(10.0, e);
+        forward(c, &m, pred);
+        double phi = data_misfit(c->C, c->data, pred, var);
+        if (phi < best) { best = phi; best_c = m.sigma[0]; }
+    }
+    return best_c;
+}
+
+static void chain_init(chain_t *c, gbo_chain_out *out)
+{
+    const gbo_options *o = c->o;
+    c->dp.rel = o->rel_init;
+    c->dp.add = o->add_init;
+    c->sigma_ref = best_halfspace(c, c->dp.rel, c->dp.add);
+    c->model.k = 1;
+    c->model.edges[0] = 0.0;
+    c->model.edges[1] = INFINITY;
+    c->model.sigma[0] = c->sigma_ref;
+    forward(c, &c->model, c->dp.pred);
+    sensitivity(c, &c->model, &c->dp);
+    make_grids(o, c->sigma_ref, &c->G);
+    reset_posteriors(o, &c->G, out);
+    memset(out->misfit_trace, 0, sizeof(double) * 2 * (size_t)o->n_markov_chains);
+    memset(out->accept_trace, 0, 2 * (size_t)o->n_markov_chains);
+    double var[GBO_MAXC];
+    data_variance(c->C, c->data, c->dp.rel, c->dp.add, var);
+    c->misfit = data_misfit(c->C, c->data, c->dp.pred, var);
+    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->dp.rel, c->dp.add);
+    c->likelihood = data_likelihood(c->C, c->data, c->dp.pred, var);
+    c->posterior = c->likelihood + c->prior;
+    c->burned_in = 0;
+    c->burned_in_iter = 0;
+    c->iteration = 0;
+    out->misfit_trace[0] = c->misfit;
+    c->accepted = 0;
+    c->best_model = c->model;
+    c->best_rel = c->dp.rel;
+    c->best_add = c->dp.add;
+    c->best_posterior = c->posterior;
+    c->best_iter = 0;
+    c->n_zero_acc = 0;
+}
+
+/* Inference1D.accept_reject.  Returns 1 if the chain failed (singular Hessian). */
+static int chain_step(chain_t *c)
+{
+    const gbo_options *o = c->o;
+    const int C = c->C;
+    model_t remap, test;
+    dpoint_t tdp = c->dp; /* deepcopy(self.datapoint) */
+    double var[GBO_MAXC], A[GBO_MAXL * GBO_MAXL], grad[GBO_MAXL], y[GBO_MAXL], step[GBO_MAXL], z[GBO_MAXL + 1];
+
+    c->accepted = 0;
+    int action = perturb_structure(o, &c->rng, &c->model, &remap);
+    c->n_act[action]++;
+    const int k = remap.k;
+
+    if (action != ACT_NONE) { /* observation.fm_dlogc(remapped) */
+        forward(c, &remap, tdp.pred);
+        sensitivity(c, &remap, &tdp);
+    }
+    data_variance(C, c->data, tdp.rel, tdp.add, var);
+    hessian_gradient(o, &remap, c->sigma_ref, C, c->data, var, tdp.J, tdp.pred, A, grad);
+    if (cholesky(k, A)) return 1;
+    /* pk = -H grad ; mean = ln sigma + alpha pk */
+    solve_L(k, A, grad, y);
+    solve_LT(k, A, y, step);
+    double mean[GBO_MAXL];
+    for (int i = 0; i < k; ++i) mean[i] = log(remap.sigma[i]) - o->covariance_scaling * step[i];
+    /* sigma' ~ exp(N(mean, H)) with H = A^-1 = L^-T L^-1  ->  mean + L^-T z */
+    for (int j = 0; j < (k + 1) / 2; ++j) rng_normal2(&c->rng, &z[2 * j], &z[2 * j + 1]);
+    double dx[GBO_MAXL];
+    solve_LT(k, A, z, dx);
+    test = remap;
+    for (int i = 0; i < k; ++i) test.sigma[i] = exp(mean[i] + dx[i]);
+
+    /* test_datapoint.perturb() */
+    if (o->solve_relative_error) tdp.rel = propose_error(&c->rng, tdp.rel, o->rel_prop_var, o->rel_min, o->rel_max);
+    if (o->solve_additive_error) tdp.add = propose_error(&c->rng, tdp.add, o->add_prop_var, o->add_min, o->add_max);
+
+    forward(c, &test, tdp.pred);
+    data_variance(C, c->data, tdp.rel, tdp.add, var);
+    double t_misfit = data_misfit(C, c->data, tdp.pred, var);
+    double t_prior = datapoint_probability(o, tdp.rel, tdp.add);
+    if (t_prior == -INFINITY) return 0;
+    t_prior += model_probability(o, &test, c->sigma_ref);
+    if (t_prior == -INFINITY) return 0;
+    double t_like = data_likelihood(C, c->data, tdp.pred, var);
+
+    double proposal = 1.0, proposal1 = 1.0;
+    if (action == ACT_BIRTH || action == ACT_DEATH) {
+        sensitivity(c, &test, &tdp);
+        double g2[GBO_MAXL], s2[GBO_MAXL], xr[GBO_MAXL], xf[GBO_MAXL];
+        hessian_gradient(o, &test, c->sigma_ref, C, c->data, var, tdp.J, tdp.pred, NULL, g2);
+        solve_L(k, A, g2, y);
+        solve_LT(k, A, y, s2); /* H dfk */
+        int bad = 0;
+        double logdetL = 0.0;
+        for (int i = 0; i < k; ++i) {
+            /* log_values = ln(sigma') - alpha*pk with pk = -H dfk  (Model.py:626-628) */
+            double lv = log(test.sigma[i]) + o->covariance_scaling * s2[i];
+            double mv = exp(lv);
+            if (mv == INFINITY || mv == 0.0) bad = 1;
+            xr[i] = log(remap.sigma[i]) - lv;
+            xf[i] = log(test.sigma[i]) - log(remap.sigma[i]);
+            logdetL += log(A[i * k + i]);
+        }
+        if (bad) {
+            proposal = -INFINITY;
+            proposal1 = -INFINITY;
+        } else {
+            proposal = -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xr);
+            proposal1 = -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xf);
+        }
+    }
+    double log_alpha = (t_prior - c->prior) + (t_like - c->likelihood) + (proposal - proposal1);
+    double u = rng_uniform(&c->rng);
+    c->accepted = exp(log_alpha) > u; /* NaN compares false */
+    if (c->accepted) {
+        c->misfit = t_misfit;
+        c->prior = t_prior;
+        c->likelihood = t_like;
+        c->posterior = t_prior + t_like;
+        c->model = test;
+        c->dp = tdp;
+        c->n_accept++;
+    }
+    return 0;
+}
+
+/* Inference1D.update.  Returns 1 if a reset was triggered. */
+static int chain_update(chain_t *c, gbo_chain_out *out)
+{
+    const gbo_options *o = c->o;
+    const int64_t N2 = 2 * (int64_t)o->n_markov_chains;
+    int do_reset = 0;
+    c->iteration++;
+    if (c->iteration - 1 < N2) out->misfit_trace[c->iteration - 1] = c->misfit;
+    if (!c->burned_in) {
+        if (c->iteration > o->burn_in_min_iter && c->misfit < (double)c->n_active) {
+            c->burned_in = 1;
+            c->burned_in_iter = c->iteration;
+            c->best_iter = c->iteration;
+            c->best_model = c->model;
+            c->best_rel = c->dp.rel;
+            c->best_add = c->dp.add;
+            c->best_posterior = c->posterior;
+            reset_posteriors(o, &c->G, out);
+        }
+    }
+    if (c->posterior > c->best_posterior) {
+        c->best_iter = c->iteration;
+        c->best_model = c->model;
+        c->best_rel = c->dp.rel;
+        c->best_add = c->dp.add;
+        c->best_posterior = c->posterior;
+    }
+    if (c->iteration < N2) out->accept_trace[c->iteration] = (uint8_t)c->accepted;
+    if (c->iteration % o->update_plot_every == 0) {
+        /* acceptance_percent over acceptance_v[it-upe : it] (Inference1D.py:125-131) */
+        int64_t lo = c->iteration > o->update_plot_every ? c->iteration - o->update_plot_every : 0;
+        int64_t s = 0;
+        for (int64_t i = lo; i < c->iteration && i < N2; ++i) s += out->accept_trace[i];
+        if (o->update_plot_every > 1) {
+            if (!c->burned_in) {
+                if (s == 0) {
+                    c->n_zero_acc++;
+                    if (c->n_zero_acc == o->reset_limit) {
+                        do_reset = 1;
+                        c->n_zero_acc = 0;
+                    }
+                } else c->n_zero_acc = 0;
+            } else if (s == 0) c->limiters = 0;
+        }
+    }
+    if (do_reset) return 1; /* reset() re-initialises everything, then update continues below on the new state */
+    accumulate_posteriors(o, &c->G, &c->model, c->dp.rel, c->dp.add, out);
+    return 0;
+}
+
+int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const double *data, double altitude,
+                  uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out)
+{
+    chain_t *c = (chain_t *)calloc(1, sizeof(chain_t));
+    if (!c) return -1;
+    c->sys = sys;
+    c->o = opt;
+    c->C = 2 * sys->n_freq;
+    memcpy(c->data, data, sizeof(double) * c->C);
+    c->altitude = altitude;
+    c->rng.seed = seed;
+    c->rng.sounding = sounding_index;
+    c->rng.block = 0;
+    c->n_active = 0;
+    for (int i = 0; i < c->C; ++i) c->n_active += is_active(data[i]);
+    chain_init(c, out);
+
+    int failed = (c->n_active == 0);
+    int go = !failed;
+    int64_t total = 0;
+    const int64_t N = opt->n_markov_chains;
+    while (go) {
+        failed = chain_step(c);
+        int reset = chain_update(c, out);
+        total++;
+        if (reset) {
+            /* Inference1D.reset(): re-initialise, continue the random stream */
+            c->n_resets++;
+            chain_init(c, out);
+            accumulate_posteriors(opt, &c->G, &c->model, c->dp.rel, c->dp.add, out);
+        }
+        go = !failed && (c->iteration <= N + c->burned_in_iter);
+        if (!failed && !c->burned_in) {
+            go = c->iteration < N;
+            if (!go) failed = 1;
+        }
+        if (c->n_resets == 3 && !c->burned_in) {
+            if (!c->limiters) {
+                c->limiters = 1;
+                c->n_resets = 1;
+                chain_init(c, out);
+            } else {
+                go = 0;
+                failed = 1;
+            }
+        }
+        if (max_iterations > 0 && total >= max_iterations) go = 0;
+    }
+
+    double *s = out->scalars;
+    memset(s, 0, sizeof(double) * GBO_NSCALARS);
+    s[GBO_S_ITER] = (double)c->iteration;
+    s[GBO_S_BURNED_IN] = c->burned_in;
+    s[GBO_S_BURNED_IN_ITER] = (double)c->burned_in_iter;
+    s[GBO_S_BEST_ITER] = (double)c->best_iter;
+    s[GBO_S_BEST_K] = c->best_model.k;
+    s[GBO_S_CUR_K] = c->model.k;
+    s[GBO_S_HALFSPACE] = c->sigma_ref;
+    s[GBO_S_FAILED] = failed;
+    s[GBO_S_N_ACCEPT] = (double)c->n_accept;
+    s[GBO_S_N_FORWARD] = (double)c->n_forward;
+    s[GBO_S_N_SENS] = (double)c->n_sens;
+    s[GBO_S_BEST_POSTERIOR] = c->best_posterior;
+    s[GBO_S_CUR_REL] = c->dp.rel;
+    s[GBO_S_CUR_ADD] = c->dp.add;
+    s[GBO_S_CUR_MISFIT] = c->misfit;
+    s[GBO_S_CUR_PRIOR] = c->prior;
+    s[GBO_S_CUR_LIKELIHOOD] = c->likelihood;
+    s[GBO_S_BEST_REL] = c->best_rel;
+    s[GBO_S_BEST_ADD] = c->best_add;
+    s[GBO_S_N_RESETS] = c->n_resets;
+    s[GBO_S_N_BIRTH] = (double)c->n_act[0];
+    s[GBO_S_N_DEATH] = (double)c->n_act[1];
+    s[GBO_S_N_MOVE] = (double)c->n_act[2];
+    s[GBO_S_N_NONE] = (double)c->n_act[3];
+    for (int i = 0; i < opt->max_layers; ++i) {
+        out->best_sigma[i] = i < c->best_model.k ? c->best_model.sigma[i] : NAN;
+        out->cur_sigma[i] = i < c->model.k ? c->model.sigma[i] : NAN;
+    }
+    for (int i = 0; i <= opt->max_layers; ++i) {
+        out->best_edges[i] = i <= c->best_model.k ? c->best_model.edges[i] : NAN;
+        out->cur_edges[i] = i <= c->model.k ? c->model.edges[i] : NAN;
+    }
+    free(c);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ term-level pin */
+int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *o, gbo_transition *t)
+{
+    const int k = t->k, C = 2 * sys->n_freq;
+    model_t remap, test;
+    remap.k = test.k = k;
+    memcpy(remap.edges, t->edges, sizeof(double) * (k + 1));
+    memcpy(test.edges, t->edges, sizeof(double) * (k + 1));
+    memcpy(remap.sigma, t->sigma_remap, sizeof(double) * k);
+    memcpy(test.sigma, t->sigma_test, sizeof(double) * k);
+    double thk[GBO_MAXL], var[GBO_MAXC], J[GBO_MAXC * GBO_MAXL], pred[GBO_MAXC];
+    double A[GBO_MAXL * GBO_MAXL], y[GBO_MAXL], step[GBO_MAXL];
+    model_thickness(&remap, thk);
+    if (t->action != ACT_NONE) {
+        gbo_fdem_forward(sys, t->altitude, k, remap.sigma, thk, pred);
+        gbo_fdem_sensitivity(sys, t->altitude, k, remap.sigma, thk, J);
+    } else {
+        memcpy(pred, t->pred_in, sizeof(double) * C);
+        memcpy(J, t->J_in, sizeof(double) * C * k);
+    }
+    data_variance(C, t->data, t->rel_cur, t->add_cur, var);
+    hessian_gradient(o, &remap, t->sigma_ref, C, t->data, var, J, pred, A, t->gradient);
+    memcpy(t->hessian, A, sizeof(double) * k * k);
+    if (cholesky(k, A)) return 1;
+    solve_L(k, A, t->gradient, y);
+    solve_LT(k, A, y, step);
+    for (int i = 0; i < k; ++i) t->newton_mean[i] = exp(log(remap.sigma[i]) - o->covariance_scaling * step[i]);
+
+    gbo_fdem_forward(sys, t->altitude, k, test.sigma, thk, t->pred_test);
+    data_variance(C, t->data, t->rel_test, t->add_test, var);
+    t->misfit_test = data_misfit(C, t->data, t->pred_test, var);
+    t->prior_test = datapoint_probability(o, t->rel_test, t->add_test) + model_probability(o, &test, t->sigma_ref);
+    t->likelihood_test = data_likelihood(C, t->data, t->pred_test, var);
+    t->proposal = 1.0;
+    t->proposal1 = 1.0;
+    if (t->action == ACT_BIRTH || t->action == ACT_DEATH) {
+        double g2[GBO_MAXL], s2[GBO_MAXL], xr[GBO_MAXL], xf[GBO_MAXL], logdetL = 0.0;
+        gbo_fdem_sensitivity(sys, t->altitude, k, test.sigma, thk, J);
+        hessian_gradient(o, &test, t->sigma_ref, C, t->data, var, J, t->pred_test, NULL, g2);
+        solve_L(k, A, g2, y);
+        solve_LT(k, A, y, s2);
+        for (int i = 0; i < k; ++i) {
+            double lv = log(test.sigma[i]) + o->covariance_scaling * s2[i];
+            xr[i] = log(remap.sigma[i]) - lv;
+            xf[i] = log(test.sigma[i]) - log(remap.sigma[i]);
+            logdetL += log(A[i * k + i]);
+        }
+        t->proposal = -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xr);
+        t->proposal1 = -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xf);
+    }
+    return 0;
+}

@@ -1,0 +1,284 @@
+"""Generate the committed golden vectors under tests/golden/ (BUILD CONTAINER ONLY).
+
+Needs the read-only reference tree at /root/reference; imports the *unmodified* reference
+through oracle/ref_shims.py and records its outputs.  The GPU box never runs this.
+
+    python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
+    python tests/golden/make_golden.py bins         # posterior_bins.npz
+    python tests/golden/make_golden.py transitions  # transitions.npz
+    python tests/golden/make_golden.py chain <i>    # ref_chain_<i>.npz   (minutes each)
+
+Files written
+  resolve_clean.npz       the reference's own known-answer vectors
+                          (tests/data_checks/resolve_*_clean.csv, 6 models x 79 soundings x 12 channels;
+                          tests/test_synthetic_data.py:16-30) plus the model definitions
+                          (Model.create_synthetic_model, classes/model/Model.py:885-920).
+  fdem_random_models.npz  nbFdem1dfwd / nbFdem1dsen outputs (fdem1d_numba.py:25,72) for random models.
+  posterior_bins.npz      bin indices the reference's Histogram meshes assign to probe values.
+  transitions.npz         per-term records of Inference1D.accept_reject (Inference1D.py:537-631).
+  ref_chain_<i>.npz       posterior arrays of full reference chains (Inference1D.infer loop).
+"""
+import os
+import sys
+import time
+import warnings
+from copy import deepcopy
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+import ref_shims  # noqa: E402
+
+REF = ref_shims.REFERENCE_ROOT
+SUP = os.path.join(REF, "documentation_source/source/supplementary")
+
+MODELS = ["glacial", "saline_clay", "resistive_dolomites", "resistive_basement", "coastal_salt_water",
+          "ice_over_salt_water"]
+
+
+def _geobipy():
+    return ref_shims.import_reference()
+
+
+def _options(n_markov_chains):
+    from geobipy import user_parameters
+    kw = user_parameters.read(os.path.join(SUP, "options_files/resolve_options"))
+    kw["interactive_plot"] = False
+    kw["save_hdf5"] = True
+    kw["n_markov_chains"] = n_markov_chains
+    for k in ("data_type", "data_filename", "system_filename", "data_directory"):
+        kw.pop(k, None)
+    kw.pop("seed")
+    return dict(kw)
+
+
+def _system():
+    from geobipy import FdemSystem
+    return FdemSystem.read(os.path.join(SUP, "data/resolve.stm"))
+
+
+def _datapoint(system, data, z):
+    from geobipy import FdemDataPoint
+    return FdemDataPoint(x=0.0, y=0.0, z=z, elevation=0.0, data=data, std=None, predictedData=None,
+                         system=system, lineNumber=0.0, fiducial=0.0)
+
+
+def _model(edges, sigma):
+    from geobipy import Model, RectilinearMesh1D, StatArray
+    mesh = RectilinearMesh1D(edges=np.asarray(edges, dtype=np.float64))
+    return Model(mesh=mesh, values=StatArray(np.asarray(sigma, dtype=np.float64), "Conductivity", "S/m"))
+
+
+from geobipy_b200.synthetic import synthetic_sounding  # noqa: E402
+
+
+def make_fdem():
+    import pandas as pd
+    _geobipy()
+    nb = ref_shims.load_numba_kernels()
+    from geobipy import Model
+    data = np.zeros((6, 79, 12))
+    sig = np.zeros((6, 3))
+    for m, name in enumerate(MODELS):
+        df = pd.read_csv(os.path.join(REF, "tests/data_checks/resolve_%s_clean.csv" % name))
+        data[m] = df.values[:, 6:18]
+        assert np.all(df["Height"].values == 30.0)
+        mod = Model.create_synthetic_model(name)
+        sig[m] = np.asarray(mod.values[0, :])
+    zwedge = np.linspace(50.0, 1.0, 79) / 10.0
+    zdeep = np.linspace(75.0, 500.0, 79) / 10.0
+    np.savez_compressed(os.path.join(HERE, "resolve_clean.npz"), data=data, sigma=sig, zwedge=zwedge, zdeep=zdeep,
+                        height=30.0, models=np.array(MODELS))
+
+    s = _system()
+    tid = np.asarray(s.tensor_id, dtype=np.int32)
+    freq = np.asarray(s.frequencies)
+    sep = np.asarray(s.loop_separation)
+    tmom = np.asarray(s.transmitter.moment, dtype=np.float64)
+    rmom = np.asarray(s.receiver.moment, dtype=np.float64)
+    xs = np.asarray(s.loop_offsets[0, :])
+
+    def run(f, sigma, thk, z):
+        tH = z + np.zeros(6)
+        rH = -tH
+        return f(tid, freq, tH, rH, tmom, xs, sep, s.w0, s.lamda0, s.lamda02, s.w1, s.lamda1, s.lamda12,
+                 tmom * rmom, sigma, np.zeros_like(sigma), np.zeros_like(sigma), thk)
+
+    rng = np.random.default_rng(20261017)
+    n = 256
+    Ls = np.r_[np.arange(1, 31), rng.integers(1, 31, n - 30)]
+    sigma = np.full((n, 30), np.nan)
+    thk = np.full((n, 30), np.nan)
+    height = rng.uniform(25.0, 45.0, n)
+    fwd = np.zeros((n, 12))
+    sens = np.full((n, 12, 30), np.nan)
+    for i in range(n):
+        L = int(Ls[i])
+        sg = 10.0 ** rng.uniform(-4.0, 1.0, L)
+        t = np.r_[np.exp(rng.uniform(np.log(1.0), np.log(60.0), L - 1)), np.inf]
+        sigma[i, :L] = sg
+        thk[i, :L] = t
+        r = run(nb.nbFdem1dfwd, sg, t, height[i])
+        fwd[i] = np.r_[r.real, r.imag]
+        J = run(nb.nbFdem1dsen, sg, t, height[i])
+        sens[i, :, :L] = np.vstack([J.real, J.imag])
+    np.savez_compressed(os.path.join(HERE, "fdem_random_models.npz"), nlayers=Ls.astype(np.int32), sigma=sigma,
+                        thickness=thk, height=height, forward=fwd, sensitivity=sens)
+    print("fdem goldens written")
+
+
+def _initialised_inference(data, z, n_markov_chains, seed):
+    from geobipy import Inference1D, get_prng
+    kw = _options(n_markov_chains)
+    kw["prng"] = get_prng(seed=seed)
+    inf = Inference1D(**kw)
+    dp = _datapoint(_system(), np.asarray(data, dtype=np.float64), z)
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        inf.initialize(dp)
+    return inf
+
+
+def _observed(i):
+    edges, sigma, height, noise = synthetic_sounding(i)
+    dp = _datapoint(_system(), None, height)
+    dp.forward(_model(edges, sigma))
+    clean = np.asarray(dp.predictedData).copy()
+    std = np.sqrt((0.05 * clean) ** 2 + 5.0 ** 2)
+    return clean + noise * std, height, edges, sigma
+
+
+def make_bins():
+    _geobipy()
+    data, z, _, _ = _observed(0)
+    inf = _initialised_inference(data, z, 1000, 7)
+    rng = np.random.default_rng(3)
+    hs = float(inf.halfspace.item())
+    h = inf.model.values.posterior
+    v = hs * np.exp(rng.uniform(-11.0, 11.0, 4000))
+    sig_idx = np.asarray(h.cellIndex(v, axis=0, clip=True))
+    d = rng.uniform(0.0, 219.9, 4000)
+    dep_idx = np.asarray(inf.model.mesh.edges.posterior.mesh.cellIndices(d, clip=True))
+    re = np.exp(rng.uniform(np.log(0.001), np.log(0.5), 2000))
+    ae = np.exp(rng.uniform(np.log(3.0), np.log(20.0), 2000))
+    rel_idx = np.asarray(inf.datapoint.relative_error.posterior.mesh.cellIndices(re, clip=True))
+    add_idx = np.asarray(inf.datapoint.additive_error.posterior.mesh.cellIndices(ae, clip=True))
+    centres = np.asarray(h.axis(1).centres)
+    np.savez_compressed(os.path.join(HERE, "posterior_bins.npz"), halfspace=hs, sigma_probe=v, sigma_idx=sig_idx,
+                        depth_probe=d, depth_idx=dep_idx, rel_probe=re, rel_idx=rel_idx, add_probe=ae,
+                        add_idx=add_idx, hitmap_shape=np.asarray(h.counts.shape), depth_centres=centres,
+                        ncells_bins=int(inf.model.mesh.nCells.posterior.counts.size),
+                        err_bins=int(inf.datapoint.relative_error.posterior.counts.size))
+    print("bins golden written", h.counts.shape)
+
+
+ACT = {"insert": 0, "delete": 1, "perturb": 2, "none": 3}
+
+
+def make_transitions(n_soundings=6, n_iter=250):
+    _geobipy()
+    from numpy import inf as npinf
+    recs = []
+    for sidx in range(n_soundings):
+        data, z, _, _ = _observed(sidx)
+        inf = _initialised_inference(data, z, 100000, 1000 + sidx)
+        hs = float(inf.halfspace.item())
+        init = dict(prior=float(inf.prior), likelihood=float(inf.likelihood), misfit=float(inf.data_misfit))
+        for it in range(n_iter):
+            dp0, m0 = inf.datapoint, inf.model
+            J_in = np.asarray(dp0.sensitivity_matrix).copy()
+            pred_in = np.asarray(dp0.predictedData).copy()
+            rel_cur = float(np.asarray(dp0.relative_error).item())
+            add_cur = float(np.asarray(dp0.additive_error).item())
+            tdp = deepcopy(dp0)
+            remapped, test = m0.perturb(tdp, -npinf, npinf, alpha=inf.covariance_scaling)
+            action = ACT[remapped.mesh.action[0]]
+            k = int(remapped.nCells.item())
+            grad = np.asarray(remapped.local_gradient(observation=tdp)).copy()
+            H = np.asarray(test.values.proposal.variance).copy()
+            mean = np.asarray(test.values.proposal.mean).copy()
+            tdp.perturb()
+            tdp.forward(test)
+            misfit = float(tdp.data_misfit())
+            prior = float(tdp.probability) + float(test.probability(inf.solve_parameter, inf.solve_gradient))
+            like = float(tdp.likelihood(log=True))
+            prop, prop1 = test.proposal_probabilities(remapped, tdp, alpha=inf.covariance_scaling)
+            rec = dict(sounding=sidx, altitude=z, sigma_ref=hs, data=np.asarray(data), k=k, action=action,
+                       edges=np.asarray(remapped.mesh.edges).copy(), sigma_remap=np.asarray(remapped.values).copy(),
+                       sigma_test=np.asarray(test.values).copy(), rel_cur=rel_cur, add_cur=add_cur,
+                       rel_test=float(np.asarray(tdp.relative_error).item()),
+                       add_test=float(np.asarray(tdp.additive_error).item()), J_in=J_in, pred_in=pred_in,
+                       H=H, gradient=grad, newton_mean=mean, pred_test=np.asarray(tdp.predictedData).copy(),
+                       misfit_test=misfit, prior_test=prior, likelihood_test=like, proposal=float(prop),
+                       proposal1=float(prop1), init_prior=init["prior"], init_likelihood=init["likelihood"],
+                       init_misfit=init["misfit"])
+            recs.append(rec)
+            # accept / reject exactly as Inference1D.accept_reject :604-623 does
+            log_alpha = (prior - inf.prior) + (like - inf.likelihood) + (prop - prop1)
+            if np.exp(log_alpha) > inf.prng.uniform():
+                inf.data_misfit, inf.prior, inf.likelihood = misfit, prior, like
+                inf.model, inf.datapoint = test, tdp
+        print("sounding", sidx, "k now", inf.model.nCells.item(), flush=True)
+    n = len(recs)
+    out = {}
+    for key in recs[0]:
+        vals = [r[key] for r in recs]
+        if np.ndim(vals[0]) == 0:
+            out[key] = np.asarray(vals)
+        else:
+            obj = np.empty(n, dtype=object)
+            for i, v in enumerate(vals):
+                obj[i] = np.asarray(v)
+            out[key] = obj
+    np.savez_compressed(os.path.join(HERE, "transitions.npz"), **out)
+    print("transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
+
+
+def make_chain(sidx, n_markov_chains=10000):
+    _geobipy()
+    data, z, edges, sigma = _observed(sidx)
+    inf = _initialised_inference(data, z, n_markov_chains, 5000 + sidx)
+    t0 = time.time()
+    import io
+    import contextlib
+    go, failed = True, False
+    with contextlib.redirect_stdout(io.StringIO()):
+        while go:  # Inference1D.infer :650-677 without the HDF5 write
+            failed = inf.accept_reject()
+            inf.update()
+            go = (not failed) and (inf.iteration <= inf.n_markov_chains + inf.burned_in_iteration)
+            if (not failed) and (not inf.burned_in):
+                go = inf.iteration < inf.n_markov_chains
+                if not go:
+                    failed = True
+    dt = time.time() - t0
+    it = int(inf.iteration)
+    np.savez_compressed(
+        os.path.join(HERE, "ref_chain_%d.npz" % sidx), sounding=sidx, data=data, altitude=z, true_edges=edges,
+        true_sigma=sigma, halfspace=float(inf.halfspace.item()), iterations=it, failed=bool(failed),
+        burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
+        hitmap=np.asarray(inf.model.values.posterior.counts, dtype=np.int32),
+        edges_hist=np.asarray(inf.model.mesh.edges.posterior.counts, dtype=np.int32),
+        ncells_hist=np.asarray(inf.model.mesh.nCells.posterior.counts, dtype=np.int32),
+        rel_hist=np.asarray(inf.datapoint.relative_error.posterior.counts, dtype=np.int32),
+        add_hist=np.asarray(inf.datapoint.additive_error.posterior.counts, dtype=np.int32),
+        misfit_trace=np.asarray(inf.data_misfit_v[:it], dtype=np.float32),
+        accept_trace=np.asarray(inf.acceptance_v[:it + 1], dtype=np.uint8),
+        seconds=dt, n_markov_chains=n_markov_chains)
+    print("chain", sidx, "iterations", it, "burned in", inf.burned_in, inf.burned_in_iteration, "s/it", dt / it)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    if what == "fdem":
+        make_fdem()
+    elif what == "bins":
+        make_bins()
+    elif what == "transitions":
+        make_transitions()
+    elif what == "chain":
+        make_chain(int(sys.argv[2]))
