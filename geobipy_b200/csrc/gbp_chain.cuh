@@ -732,8 +732,8 @@ template <typename T, int NC> struct Chain {
         int act = 0;
         if (lane < C) {
             double d = P.data[(size_t)chain * C + lane];
-            w.data[lane] = d;
-            act = d > 0.0;
+            act = d > 0.0;               // EmDataPoint.active: observed > 0 and not NaN
+            w.data[lane] = act ? d : 0.0;
         }
         n_active = warp_sum_i(act);
         n_accept = n_forward = n_sens = 0;

@@ -6,7 +6,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
     python tests/golden/make_golden.py bins         # posterior_bins.npz
     python tests/golden/make_golden.py transitions  # transitions.npz
-    python tests/golden/make_golden.py chain <i>    # ref_chain_<i>.npz   (minutes each)
+    python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
 
 Files written
   resolve_clean.npz       the reference's own known-answer vectors
@@ -238,10 +238,10 @@ def make_transitions(n_soundings=6, n_iter=250):
     print("transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
 
 
-def make_chain(sidx, n_markov_chains=10000):
+def make_chain(sidx, rep=0, n_markov_chains=10000):
     _geobipy()
     data, z, edges, sigma = _observed(sidx)
-    inf = _initialised_inference(data, z, n_markov_chains, 5000 + sidx)
+    inf = _initialised_inference(data, z, n_markov_chains, 5000 + sidx + 100 * rep)
     t0 = time.time()
     import io
     import contextlib
@@ -258,7 +258,7 @@ def make_chain(sidx, n_markov_chains=10000):
     dt = time.time() - t0
     it = int(inf.iteration)
     np.savez_compressed(
-        os.path.join(HERE, "ref_chain_%d.npz" % sidx), sounding=sidx, data=data, altitude=z, true_edges=edges,
+        os.path.join(HERE, "ref_chain_%d.npz" % sidx if rep == 0 else "ref_chain_%d_r%d.npz" % (sidx, rep)), sounding=sidx, data=data, altitude=z, true_edges=edges,
         true_sigma=sigma, halfspace=float(inf.halfspace.item()), iterations=it, failed=bool(failed),
         burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
         hitmap=np.asarray(inf.model.values.posterior.counts, dtype=np.int32),
@@ -281,4 +281,4 @@ if __name__ == "__main__":
     elif what == "transitions":
         make_transitions()
     elif what == "chain":
-        make_chain(int(sys.argv[2]))
+        make_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)

@@ -1,0 +1,81 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/geobipy_b200.h declares, and the
+host-side logic (options mapping, grids, synthetic inputs) behaves.  No compute call is made."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "geobipy_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(gbp_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from geobipy_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert sorted(_lib.EXPORTS) == declared
+    assert built_lib.gbp_version().startswith(b"geobipy_b200")
+
+
+def test_struct_layouts_match_oracle(built_lib, oracle):
+    from geobipy_b200 import _lib
+    assert ctypes.sizeof(_lib.FdemSystemC) == ctypes.sizeof(oracle.FdemSystemC)
+    assert ctypes.sizeof(_lib.OptionsC) == ctypes.sizeof(oracle.OptionsC)
+    assert [f[0] for f in _lib.OptionsC._fields_] == [f[0] for f in oracle.OptionsC._fields_]
+
+
+def test_host_helpers(built_lib):
+    from geobipy_b200 import ops
+    s = ops.resolve_system_struct()
+    assert list(s.tid[:6]) == [9, 9, 1, 9, 9, 9]
+    assert ops.filter_points(s) == 5 * 120 + 120 + 140 == 860
+    assert ops.flops_per_forward(s, 10) == 860 * (75 * 10 + 39)
+    o = ops.make_options(maximum_number_of_layers=12, minimum_depth=1.0, maximum_depth=550.0, minimum_thickness=2.0,
+                         covariance_scaling=None, factor=None, n_markov_chains=1234)
+    assert (o.max_layers, o.min_edge, o.max_edge, o.min_width, o.n_markov_chains) == (12, 1.0, 550.0, 2.0, 1234)
+    assert o.covariance_scaling == 1.0 and o.factor == 10.0          # user_parameters.py:40-44 defaults
+    assert ops.n_depth(ops.make_options()) == 440                      # resolve_options -> hitmap [250, 440]
+    assert ops.n_depth(o) == len(np.arange(0.0, 1.1 * 550.0, 1.0)) - 1
+    shapes = ops.chain_buffer_shapes(ops.make_options(n_markov_chains=10), 3)
+    assert shapes["hitmap"][0] == (3, 250, 440) and shapes["misfit_trace"][0] == (3, 20)
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    """Without a CUDA device the product path must fail loudly (never route through the oracle)."""
+    from geobipy_b200 import _lib, ops
+    if built_lib.gbp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = ops.resolve_system_struct()
+    with pytest.raises(_lib.GeobipyB200Error):
+        ops.fdem_forward(s, [1], [[0.01]], [[np.inf]], [30.0])
+    with pytest.raises(_lib.GeobipyB200Error):
+        ops.rjmcmc_run(s, ops.make_options(), np.ones((1, 12)), np.array([30.0]))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "geobipy_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle_py" not in src and "ref_shims" not in src and "oracle/" not in src, f
+
+
+def test_synthetic_inputs():
+    from geobipy_b200.synthetic import synthetic_batch, synthetic_sounding
+    e, s, h, n = synthetic_sounding(7)
+    e2, s2, h2, n2 = synthetic_sounding(7)
+    assert np.array_equal(e, e2) and np.array_equal(s, s2) and h == h2 and np.array_equal(n, n2)
+    assert e[0] == 0.0 and np.isinf(e[-1]) and (np.diff(e[:-1]) >= 1.0).all() and 25 <= h <= 45
+    b = synthetic_batch(5, 4)
+    assert b["sigma"].shape == (4, 30) and b["nlayers"][2] == s.size
+    assert np.array_equal(b["sigma"][2, : s.size], s)

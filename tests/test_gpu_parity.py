@@ -1,0 +1,281 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the oracle and the
+committed golden vectors.
+
+Tolerances (north_star: "stated fp64 -> fp32 tolerance"):
+  fp64 instantiation : forward |d - ref| <= 5e-8 (|ref| + 1 ppm); Jacobian 1e-8 of max |J|
+                       (the reference's own (H-H0)/H0 round-off floor is ~1e-8 ppm)
+  fp32 instantiation : forward |d - ref| <= 2e-4 (|ref| + 1 ppm); Jacobian 1e-4 of max |J|
+  fp64 chains        : same random stream as the oracle -> identical accept/reject trajectories
+                       (>= 90 % of chains bit-identical over 400 iterations; others may flip on round-off)
+  fp32 chains        : statistical agreement with the oracle ensemble
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F64_FWD, F64_J = 5e-8, 1e-8
+F32_FWD, F32_J = 2e-4, 1e-4
+
+
+@pytest.fixture(scope="module")
+def gpu(built_lib):
+    from geobipy_b200 import _lib, ops
+    _lib.require_cuda()
+    return ops
+
+
+@pytest.fixture(scope="module")
+def systems(gpu, oracle):
+    return gpu.resolve_system_struct(), oracle.make_system()
+
+
+def _observed(oracle, osys, n, first=0):
+    from geobipy_b200.synthetic import synthetic_batch
+    b = synthetic_batch(first, n)
+    data = np.zeros((n, 12))
+    for i in range(n):
+        L = int(b["nlayers"][i])
+        clean = oracle.fdem_forward(osys, b["height"][i], b["sigma"][i, :L], b["thickness"][i, :L])
+        data[i] = clean + b["noise"][i] * np.sqrt((0.05 * clean) ** 2 + 25.0)
+    return data, b["height"]
+
+
+@pytest.mark.parametrize("prec,tol", [(64, F64_FWD), (32, F32_FWD)])
+def test_forward_reference_csv_goldens(gpu, systems, golden_dir, prec, tol):
+    """The reference's own known-answer vectors: 6 models x 79 soundings x 12 channels."""
+    g = np.load(os.path.join(golden_dir, "resolve_clean.npz"))
+    sig = np.repeat(g["sigma"][:, None, :], 79, axis=1).reshape(-1, 3)
+    thk = np.tile(np.stack([g["zwedge"], g["zdeep"] - g["zwedge"], np.full(79, np.inf)], axis=1), (6, 1))
+    out = gpu.fdem_forward(systems[0], np.full(474, 3, np.int32), sig, thk, np.full(474, float(g["height"])), precision=prec)
+    ref = g["data"].reshape(-1, 12)
+    assert np.allclose(out, ref, rtol=1e-3 if prec == 32 else 1e-5)   # the reference's own criterion
+    assert np.max(np.abs(out - ref) / (np.abs(ref) + 1.0)) < tol
+
+
+@pytest.mark.parametrize("prec,tf,tj", [(64, F64_FWD, F64_J), (32, F32_FWD, F32_J)])
+def test_forward_and_jacobian_random_models(gpu, systems, golden_dir, prec, tf, tj):
+    g = np.load(os.path.join(golden_dir, "fdem_random_models.npz"))
+    nl = g["nlayers"]
+    sig = np.nan_to_num(g["sigma"], nan=1.0)
+    thk = np.nan_to_num(g["thickness"], nan=1.0, posinf=np.inf)
+    pred, J = gpu.fdem_forward(systems[0], nl, sig, thk, g["height"], precision=prec, sensitivity=True)
+    pred2 = gpu.fdem_forward(systems[0], nl, sig, thk, g["height"], precision=prec)
+    assert np.array_equal(pred, pred2) or np.max(np.abs(pred - pred2) / (np.abs(pred) + 1)) < tf
+    assert np.max(np.abs(pred - g["forward"]) / (np.abs(g["forward"]) + 1.0)) < tf
+    refJ = np.nan_to_num(g["sensitivity"], nan=0.0)
+    err = np.abs(J - refJ).max(axis=(1, 2)) / np.abs(refJ).max(axis=(1, 2))
+    assert err.max() < tj
+    # columns beyond nlayers are zero
+    for i in range(len(nl)):
+        assert not J[i, :, nl[i]:].any()
+
+
+def test_forward_against_oracle_extremes(gpu, systems, oracle):
+    """Conductive / resistive extremes, 1 and 30 layers, thin and thick layers, low and high sensors."""
+    rng = np.random.default_rng(99)
+    n = 200
+    nl = rng.choice([1, 2, 3, 10, 30], n).astype(np.int32)
+    sig = 10 ** rng.uniform(-4.5, 1.0, (n, 30))
+    sig[:40] = 10 ** rng.choice([-4.0, 1.0], (40, 30))
+    thk = np.exp(rng.uniform(np.log(1.0), np.log(150.0), (n, 30)))
+    alt = rng.uniform(10.0, 120.0, n)
+    for prec, tf, tj in ((64, F64_FWD, F64_J), (32, F32_FWD, F32_J)):
+        pred, J = gpu.fdem_forward(systems[0], nl, sig, thk, alt, precision=prec, sensitivity=True)
+        for i in range(n):
+            L = int(nl[i])
+            t = np.r_[thk[i, :L - 1], np.inf]
+            ref = oracle.fdem_forward(systems[1], alt[i], sig[i, :L], t)
+            refJ = oracle.fdem_sensitivity(systems[1], alt[i], sig[i, :L], t)
+            assert np.max(np.abs(pred[i] - ref) / (np.abs(ref) + 1.0)) < tf, (prec, i, L)
+            assert np.max(np.abs(J[i, :, :L] - refJ)) / np.max(np.abs(refJ)) < tj, (prec, i, L)
+
+
+def test_forward_device_pointer_path(gpu, systems):
+    import torch
+    from geobipy_b200.synthetic import synthetic_batch
+    b = synthetic_batch(0, 64)
+    host = gpu.fdem_forward(systems[0], b["nlayers"], b["sigma"], b["thickness"], b["height"], precision=64)
+    dev = gpu.fdem_forward(systems[0], torch.tensor(b["nlayers"], device="cuda"), torch.tensor(b["sigma"], device="cuda"),
+                           torch.tensor(b["thickness"], device="cuda"), torch.tensor(b["height"], device="cuda"), precision=64)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_error_paths(gpu, systems):
+    from geobipy_b200 import _lib
+    s = gpu.resolve_system_struct()
+    s.tid[1] = 5   # y-oriented coil: the reference has no branch for it either (fdem1d_numba.py:57-66)
+    with pytest.raises(_lib.GeobipyB200Error):
+        gpu.fdem_forward(s, [1], [[0.01]], [[np.inf]], [30.0])
+    with pytest.raises(_lib.GeobipyB200Error):
+        gpu.fdem_forward(systems[0], [31], np.ones((1, 30)), np.ones((1, 30)), [30.0])   # nlayers out of range
+    with pytest.raises(_lib.GeobipyB200Error):
+        gpu.rjmcmc_run(systems[0], gpu.make_options(max_layers=31), np.ones((1, 12)), np.array([30.0]))
+    # empty batch is a no-op
+    out = gpu.rjmcmc_run(systems[0], gpu.make_options(n_markov_chains=10), np.zeros((0, 12)), np.zeros(0))
+    assert out["scalars"].shape == (0, 32)
+
+
+def _merge_centre(h):
+    """sigma == sigma_ref sits exactly on the edge between bins 124|125 (round-off decides, in the
+    reference too): merge the two bins before comparing hitmaps."""
+    h = h.copy()
+    h[..., 124, :] += h[..., 125, :]
+    h[..., 125, :] = 0
+    return h
+
+
+def test_chain_fp64_is_trajectory_twin_of_oracle(gpu, systems, oracle):
+    B, nit = 24, 400
+    data, alt = _observed(oracle, systems[1], B)
+    opt = gpu.make_options(n_markov_chains=1000)
+    oo = oracle.resolve_options(n_markov_chains=1000)
+    res = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=2026, first_index=7, max_iterations=nit, precision=64)
+    identical = 0
+    for b in range(B):
+        r = oracle.run_chain(systems[1], oo, data[b], alt[b], 2026, 7 + b, max_iterations=nit)
+        s, q = res["scalars"][b], r["scalars"]
+        assert s[oracle.S_ITER] == q[oracle.S_ITER] == nit
+        assert abs(s[oracle.S_HALFSPACE] / q[oracle.S_HALFSPACE] - 1) < 1e-12
+        same = (np.array_equal(res["accept_trace"][b], r["accept_trace"])
+                and np.array_equal(_merge_centre(res["hitmap"][b]), _merge_centre(r["hitmap"]))
+                and np.array_equal(res["ncells_hist"][b], r["ncells_hist"])
+                and np.array_equal(res["edges_hist"][b], r["edges_hist"])
+                and np.array_equal(res["rel_hist"][b], r["rel_hist"])
+                and np.array_equal(res["add_hist"][b], r["add_hist"]))
+        if same:
+            identical += 1
+            assert np.allclose(res["misfit_trace"][b, :nit], r["misfit_trace"][:nit], rtol=1e-6)
+            assert np.allclose(res["cur_sigma"][b], r["cur_sigma"], rtol=1e-7, equal_nan=True)
+            assert np.allclose(res["cur_edges"][b], r["cur_edges"], rtol=1e-9, equal_nan=True)
+            assert np.allclose(res["best_sigma"][b], r["best_sigma"], rtol=1e-7, equal_nan=True)
+            for j in (oracle.S_N_ACCEPT, oracle.S_CUR_K, oracle.S_BEST_K, oracle.S_BEST_ITER, oracle.S_N_BIRTH,
+                      oracle.S_N_DEATH, oracle.S_N_MOVE, oracle.S_N_NONE, oracle.S_N_FORWARD):
+                assert s[j] == q[j], j
+            for j in (oracle.S_CUR_MISFIT, oracle.S_CUR_PRIOR, oracle.S_CUR_LIKELIHOOD, oracle.S_BEST_POSTERIOR):
+                assert abs(s[j] - q[j]) <= 1e-6 * (abs(q[j]) + 1), j
+    assert identical >= 0.9 * B, identical
+
+
+def test_chain_full_termination_rule_and_burn_in(gpu, systems, oracle):
+    """Run to the reference's own termination rule (Inference1D.infer :650-677) with a short burn-in window so
+    that burn-in, posterior reset and the N + burn + 1 stopping rule are all exercised; fp64 twin of the oracle."""
+    B = 8
+    data, alt = _observed(oracle, systems[1], B, first=1)
+    kw = dict(n_markov_chains=600, burn_in_min_iter=150, update_plot_every=100)
+    res = gpu.rjmcmc_run(systems[0], gpu.make_options(**kw), data, alt, seed=5, precision=64)
+    oo = oracle.resolve_options(**kw)
+    nd = res["hitmap"].shape[2]
+    n_burned = 0
+    for b in range(B):
+        r = oracle.run_chain(systems[1], oo, data[b], alt[b], 5, b)
+        s, q = res["scalars"][b], r["scalars"]
+        it = int(s[oracle.S_ITER])
+        if s[oracle.S_BURNED_IN]:
+            n_burned += 1
+            assert it == 600 + int(s[oracle.S_BURNED_IN_ITER]) + 1 and s[oracle.S_FAILED] == 0
+            counted = it - int(s[oracle.S_BURNED_IN_ITER]) + 1
+        else:
+            assert it == 600 and s[oracle.S_FAILED] == 1
+            counted = it
+        assert res["hitmap"][b].sum() == counted * nd and (res["hitmap"][b].sum(axis=0) == counted).all()
+        assert res["ncells_hist"][b].sum() == counted
+        if np.array_equal(res["accept_trace"][b], r["accept_trace"]):
+            assert s[oracle.S_BURNED_IN_ITER] == q[oracle.S_BURNED_IN_ITER] and s[oracle.S_ITER] == q[oracle.S_ITER]
+            assert np.array_equal(_merge_centre(res["hitmap"][b]), _merge_centre(r["hitmap"]))
+    assert n_burned >= 1
+
+
+def test_chain_edge_cases(gpu, systems, oracle):
+    data, alt = _observed(oracle, systems[1], 6)
+    # inactive channels (<= 0 or NaN) are dropped from misfit / likelihood (EmDataPoint.active)
+    d2 = data.copy()
+    d2[0, 3] = -1.0
+    d2[1, 7] = np.nan
+    d2[2, :] = np.nan          # no active channel: chain does not run, flagged failed
+    opt = gpu.make_options(n_markov_chains=300)
+    oo = oracle.resolve_options(n_markov_chains=300)
+    res = gpu.rjmcmc_run(systems[0], opt, d2, alt, seed=3, max_iterations=150, precision=64)
+    assert res["scalars"][2, oracle.S_ITER] == 0 and res["scalars"][2, oracle.S_FAILED] == 1
+    for b in (0, 1, 3):
+        r = oracle.run_chain(systems[1], oo, np.nan_to_num(d2[b], nan=-1.0), alt[b], 3, b, max_iterations=150)
+        assert res["scalars"][b, oracle.S_ITER] == 150
+        assert abs(res["scalars"][b, oracle.S_HALFSPACE] / r["scalars"][oracle.S_HALFSPACE] - 1) < 1e-12
+        if np.array_equal(res["accept_trace"][b], r["accept_trace"]):
+            assert abs(res["scalars"][b, oracle.S_CUR_MISFIT] - r["scalars"][oracle.S_CUR_MISFIT]) < 1e-6 * r["scalars"][oracle.S_CUR_MISFIT]
+    # max_layers = 2: births at k = 2 are re-drawn (RectilinearMesh1D.perturb :1047)
+    res = gpu.rjmcmc_run(systems[0], gpu.make_options(n_markov_chains=300, max_layers=2), data, alt, seed=4,
+                         max_iterations=200, precision=32)
+    assert res["ncells_hist"][:, 3:].sum() == 0 and res["ncells_hist"].sum() == 6 * 200
+    assert (res["scalars"][:, oracle.S_CUR_K] <= 2).all()
+
+
+def test_chain_fp32_statistics_match_oracle_ensemble(gpu, systems, oracle, golden_dir):
+    """fp32 chains take different accept/reject decisions than the fp64 oracle, so parity is statistical:
+    512 GPU chains vs 6 oracle chains (and the 7 reference chains) on the same observed data."""
+    g = np.load(os.path.join(golden_dir, "ref_chain_1.npz"))
+    B = 512
+    data = np.tile(g["data"], (B, 1))
+    alt = np.full(B, float(g["altitude"]))
+    opt = gpu.make_options(n_markov_chains=10000)
+    res = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=77, precision=32,
+                         outputs=("hitmap", "ncells_hist", "scalars"))
+    sc = res["scalars"]
+    acc = sc[:, oracle.S_N_ACCEPT].sum() / sc[:, oracle.S_ITER].sum()
+    nc = res["ncells_hist"].sum(axis=0).astype(np.float64)
+    kbar = (nc * np.arange(nc.size)).sum() / nc.sum()
+    assert np.all(np.abs(sc[:, oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-6)
+    oo = oracle.resolve_options(n_markov_chains=10000)
+    runs = [oracle.run_chain(systems[1], oo, g["data"], float(g["altitude"]), 300 + j, 1) for j in range(6)]
+    o_acc = np.mean([r["scalars"][oracle.S_N_ACCEPT] / r["scalars"][oracle.S_ITER] for r in runs])
+    o_nc = sum(r["ncells_hist"].astype(np.float64) for r in runs)
+    o_kbar = (o_nc * np.arange(o_nc.size)).sum() / o_nc.sum()
+    assert abs(acc - o_acc) < 0.05, (acc, o_acc)
+    assert abs(kbar - o_kbar) < 0.5, (kbar, o_kbar)
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_chain_1"))
+    refs = [np.load(os.path.join(golden_dir, f)) for f in files]
+    r_acc = np.mean([r["accept_trace"].mean() for r in refs])
+    assert abs(acc - r_acc) < 0.05, (acc, r_acc)
+
+    def med(h):
+        c = np.cumsum(h, axis=0)
+        return np.array([np.searchsorted(c[:, j], 0.5 * c[-1, j]) for j in range(h.shape[1])])
+    ens = np.array([med(r["hitmap"]) for r in refs] + [med(r["hitmap"]) for r in runs])
+    m = med(res["hitmap"].sum(axis=0, dtype=np.int64))[:120]
+    inside = (m >= ens.min(axis=0)[:120] - 2) & (m <= ens.max(axis=0)[:120] + 2)
+    assert inside.mean() >= 0.9
+
+
+def test_full_size_properties(gpu, systems):
+    """BASELINE config-2 batch size (4096 soundings) through size-independent invariants, device-pointer path."""
+    import torch
+    from geobipy_b200.synthetic import synthetic_batch
+    B, nit = 4096, 60
+    b = synthetic_batch(0, 256)
+    sig = torch.tensor(np.tile(b["sigma"], (16, 1)), device="cuda")
+    thk = torch.tensor(np.tile(b["thickness"], (16, 1)), device="cuda")
+    nl = torch.tensor(np.tile(b["nlayers"], 16), device="cuda")
+    alt = torch.tensor(np.tile(b["height"], 16), device="cuda")
+    data = gpu.fdem_forward(systems[0], nl, sig, thk, alt, precision=64)
+    opt = gpu.make_options(n_markov_chains=1000)
+    res = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=1, max_iterations=nit, precision=32,
+                         outputs=("hitmap", "ncells_hist", "edges_hist", "rel_hist", "add_hist", "accept_trace", "scalars"))
+    torch.cuda.synchronize()
+    sc = res["scalars"].cpu().numpy()
+    assert (sc[:, 0] == nit).all()
+    nd = res["hitmap"].shape[2]
+    assert (res["hitmap"].sum(dim=1) == nit).all()                 # every depth cell visited once per iteration
+    assert (res["ncells_hist"].sum(dim=1) == nit).all()
+    assert (res["rel_hist"].sum(dim=1) == nit).all() and (res["add_hist"].sum(dim=1) == nit).all()
+    assert np.array_equal(res["accept_trace"][:, :nit + 1].sum(dim=1).cpu().numpy(), sc[:, 8])
+    assert (sc[:, 20:24].sum(axis=1) == nit).all()
+    # identical soundings with different sounding indices take different random paths
+    assert len(set(sc[::256, 8])) > 1
+    # idempotence: same seed -> bit-identical result
+    res2 = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=1, max_iterations=nit, precision=32, outputs=("hitmap", "scalars"))
+    torch.cuda.synchronize()
+    assert torch.equal(res["hitmap"], res2["hitmap"])
+    assert nd == 440
