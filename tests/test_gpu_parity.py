@@ -4,7 +4,9 @@ committed golden vectors.
 Tolerances (north_star: "stated fp64 -> fp32 tolerance"):
   fp64 instantiation : forward |d - ref| <= 5e-8 (|ref| + 1 ppm); Jacobian 1e-8 of max |J|
                        (the reference's own (H-H0)/H0 round-off floor is ~1e-8 ppm)
-  fp32 instantiation : forward |d - ref| <= 2e-4 (|ref| + 1 ppm); Jacobian 1e-4 of max |J|
+  fp32 instantiation : forward |d - ref| <= 2e-4 |ref| + 2e-3 ppm (the absolute floor is the fp32 round-off
+                       of a 120/140-term oscillating filter sum, 1e-3 of the smallest additive error the
+                       options allow, 3 ppm); Jacobian 1e-4 of max |J|
   fp64 chains        : same random stream as the oracle -> identical accept/reject trajectories
                        (>= 90 % of chains bit-identical over 400 iterations; others may flip on round-off)
   fp32 chains        : statistical agreement with the oracle ensemble
@@ -16,8 +18,12 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-F64_FWD, F64_J = 5e-8, 1e-8
-F32_FWD, F32_J = 2e-4, 1e-4
+F64_FWD, F64_J = (5e-8, 5e-8), 1e-8      # (relative, absolute ppm)
+F32_FWD, F32_J = (2e-4, 2e-3), 1e-4
+
+
+def fwd_ok(pred, ref, tol):
+    return bool(np.all(np.abs(pred - ref) <= tol[0] * np.abs(ref) + tol[1]))
 
 
 @pytest.fixture(scope="module")
@@ -51,8 +57,8 @@ def test_forward_reference_csv_goldens(gpu, systems, golden_dir, prec, tol):
     thk = np.tile(np.stack([g["zwedge"], g["zdeep"] - g["zwedge"], np.full(79, np.inf)], axis=1), (6, 1))
     out = gpu.fdem_forward(systems[0], np.full(474, 3, np.int32), sig, thk, np.full(474, float(g["height"])), precision=prec)
     ref = g["data"].reshape(-1, 12)
-    assert np.allclose(out, ref, rtol=1e-3 if prec == 32 else 1e-5)   # the reference's own criterion
-    assert np.max(np.abs(out - ref) / (np.abs(ref) + 1.0)) < tol
+    assert np.allclose(out, ref)   # the reference's own criterion (tests/test_synthetic_data.py:30)
+    assert fwd_ok(out, ref, tol)
 
 
 @pytest.mark.parametrize("prec,tf,tj", [(64, F64_FWD, F64_J), (32, F32_FWD, F32_J)])
@@ -63,8 +69,8 @@ def test_forward_and_jacobian_random_models(gpu, systems, golden_dir, prec, tf, 
     thk = np.nan_to_num(g["thickness"], nan=1.0, posinf=np.inf)
     pred, J = gpu.fdem_forward(systems[0], nl, sig, thk, g["height"], precision=prec, sensitivity=True)
     pred2 = gpu.fdem_forward(systems[0], nl, sig, thk, g["height"], precision=prec)
-    assert np.array_equal(pred, pred2) or np.max(np.abs(pred - pred2) / (np.abs(pred) + 1)) < tf
-    assert np.max(np.abs(pred - g["forward"]) / (np.abs(g["forward"]) + 1.0)) < tf
+    assert fwd_ok(pred2, pred, tf)
+    assert fwd_ok(pred, g["forward"], tf)
     refJ = np.nan_to_num(g["sensitivity"], nan=0.0)
     err = np.abs(J - refJ).max(axis=(1, 2)) / np.abs(refJ).max(axis=(1, 2))
     assert err.max() < tj
@@ -89,7 +95,7 @@ def test_forward_against_oracle_extremes(gpu, systems, oracle):
             t = np.r_[thk[i, :L - 1], np.inf]
             ref = oracle.fdem_forward(systems[1], alt[i], sig[i, :L], t)
             refJ = oracle.fdem_sensitivity(systems[1], alt[i], sig[i, :L], t)
-            assert np.max(np.abs(pred[i] - ref) / (np.abs(ref) + 1.0)) < tf, (prec, i, L)
+            assert fwd_ok(pred[i], ref, tf), (prec, i, L, np.max(np.abs(pred[i] - ref)))
             assert np.max(np.abs(J[i, :, :L] - refJ)) / np.max(np.abs(refJ)) < tj, (prec, i, L)
 
 
