@@ -51,30 +51,33 @@ struct ChainParams {
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // searchsorted(edges, v, 'right') - 1 clipped, uniform edges lo + i*dx
-__device__ __forceinline__ int uniform_bin(double v, double lo, double dx, int n)
+__device__ __noinline__ int uniform_bin(double v, double lo, double dx, int n)
 {
     double f = floor((v - lo) / dx);
     int i = (f < 0.0) ? 0 : (f > (double)(n - 1) ? n - 1 : (int)f);
+    #pragma unroll 1
     while (i + 1 < n && v >= lo + (double)(i + 1) * dx) ++i;
+    #pragma unroll 1
     while (i > 0 && v < lo + (double)i * dx) --i;
     return i;
 }
 
-__device__ __forceinline__ double log_uniform_logpdf(double x, double mn, double mx)
+__device__ __noinline__ double log_uniform_logpdf(double x, double mn, double mx)
 {
-    double lx = log(x), a = log(mn), b = log(mx);
+    double lx = dlog_(x), a = dlog_(mn), b = dlog_(mx);
     if (lx < a || lx > b) return -INFINITY;
-    return -log(b - a);
+    return -dlog_(b - a);
 }
 
 // StatArray.propose(imposePrior=True) for a 1-D log-normal random walk (StatArray.py:578-638)
-__device__ __forceinline__ double propose_error(Rng& g, double cur, double prop_var, double mn, double mx)
+__device__ __noinline__ double propose_error(Rng& g, double cur, double prop_var, double mn, double mx)
 {
     const double sd = sqrt(prop_var);
-    double x = exp(log(cur) + sd * rng_normal(g));
+    double x = dexp_(dlog_(cur) + sd * rng_normal(g));
     int tries = 0;
+    #pragma unroll 1
     while (log_uniform_logpdf(x, mn, mx) == -INFINITY) {
-        x = exp(log(cur) + sd * rng_normal(g));
+        x = dexp_(dlog_(cur) + sd * rng_normal(g));
         tries++;
         if (tries == 10) return cur;
     }
@@ -116,14 +119,14 @@ template <typename T, int NC> struct Chain {
         }
         __syncwarp();
     }
-    __device__ __forceinline__ void forward(int kk, const double* sig, const double* edges, T* pred)
+    __device__ __noinline__ void forward(int kk, const double* sig, const double* edges, T* pred)
     {
         load_model(kk, sig, edges);
         fdem_eval<T, false>(S, tab, alt, kk, w.msig, w.mthk, pred, nullptr);
         n_forward++;
     }
     // forward + Jacobian in one pass (FdemDataPoint.fm_dlogc, FdemDataPoint.py:535)
-    __device__ __forceinline__ void forward_sens(int kk, const double* sig, const double* edges, T* pred, T* J)
+    __device__ __noinline__ void forward_sens(int kk, const double* sig, const double* edges, T* pred, T* J)
     {
         load_model(kk, sig, edges);
         fdem_eval<T, true>(S, tab, alt, kk, w.msig, w.mthk, pred, J);
@@ -133,7 +136,7 @@ template <typename T, int NC> struct Chain {
 
     // ------------------------------------------------------------ data terms
     // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
-    __device__ __forceinline__ void set_ivar(double r, double a)
+    __device__ __noinline__ void set_ivar(double r, double a)
     {
         if (lane < C) {
             double d = w.data[lane];
@@ -143,7 +146,7 @@ template <typename T, int NC> struct Chain {
         __syncwarp();
     }
     // misfit (DataPoint.py:502-525) and Gaussian log-likelihood (MvNormalDistribution.py:209-216)
-    __device__ __forceinline__ void misfit_likelihood(const T* pred, double* mis, double* like)
+    __device__ __noinline__ void misfit_likelihood(const T* pred, double* mis, double* like)
     {
         double q = 0.0, ld = 0.0;
         if (lane < C) {
@@ -151,7 +154,7 @@ template <typename T, int NC> struct Chain {
             if (iv > 0.0) {
                 double r = (double)pred[lane] - w.data[lane];
                 q = r * r * iv;
-                ld = -log(iv);
+                ld = -dlog_(iv);
             }
         }
         q = warp_sum(q);
@@ -159,7 +162,7 @@ template <typename T, int NC> struct Chain {
         *mis = q;
         *like = -(0.5 * (double)n_active) * LOG2PI - 0.5 * ld - 0.5 * q;
     }
-    __device__ __forceinline__ double datapoint_probability(double r, double a)
+    __device__ __noinline__ double datapoint_probability(double r, double a)
     {
         double p = 0.0;
         if (P.opt.solve_relative_error) p += log_uniform_logpdf(r, P.opt.rel_min, P.opt.rel_max);
@@ -167,34 +170,34 @@ template <typename T, int NC> struct Chain {
         return p;
     }
     // Model.probability :533-575 (value_bounds = None)
-    __device__ __forceinline__ double model_probability(int kk, const double* sig, const double* edges)
+    __device__ __noinline__ double model_probability(int kk, const double* sig, const double* edges)
     {
         const gbp_options& o = P.opt;
-        double p = (kk >= 1 && kk <= o.max_layers) ? -log((double)o.max_layers - 1.0) : -INFINITY;
+        double p = (kk >= 1 && kk <= o.max_layers) ? -dlog_((double)o.max_layers - 1.0) : -INFINITY;
         if (o.solve_parameter) {
-            double s2 = log(1.0 + o.factor);
+            double s2 = dlog_(1.0 + o.factor);
             s2 *= s2;
             double q = 0.0;
             if (lane < kk) {
-                double d = log(sig[lane]) - ln_ref;
+                double d = dlog_(sig[lane]) - ln_ref;
                 q = d * d / s2;
             }
             q = warp_sum(q);
-            p += -(0.5 * kk) * LOG2PI - 0.5 * kk * log(s2) - 0.5 * q;
+            p += -(0.5 * kk) * LOG2PI - 0.5 * kk * dlog_(s2) - 0.5 * q;
         }
         if (o.solve_gradient) {
             const double g2 = o.gradient_std * o.gradient_std;
             if (kk == 1) {
-                p += -0.5 * LOG2PI - 0.5 * log(g2);
+                p += -0.5 * LOG2PI - 0.5 * dlog_(g2);
             } else {
                 const int n = kk - 1;
                 double q = 0.0;
                 if (lane < n) {
-                    double g = (log(sig[lane + 1]) - log(sig[lane])) / log(edges[lane + 1] - edges[lane]);
+                    double g = (dlog_(sig[lane + 1]) - dlog_(sig[lane])) / dlog_(edges[lane + 1] - edges[lane]);
                     q = g * g / g2;
                 }
                 q = warp_sum(q);
-                p += -(0.5 * n) * LOG2PI - 0.5 * n * log(g2) - 0.5 * q;
+                p += -(0.5 * n) * LOG2PI - 0.5 * n * dlog_(g2) - 0.5 * q;
             }
         }
         return p;
@@ -202,10 +205,10 @@ template <typename T, int NC> struct Chain {
 
     // ------------------------------------------------------------ Gauss-Newton system
     // t2[i] = 1/(g^2 (c2c_i (k-1))^2)  (RectilinearMesh1D.gradient_operator :747-786), lns = ln sigma - ln ref
-    __device__ __forceinline__ void prior_setup(int kk, const double* sig, const double* edges)
+    __device__ __noinline__ void prior_setup(int kk, const double* sig, const double* edges)
     {
         const double g2 = P.opt.gradient_std * P.opt.gradient_std;
-        if (lane < kk) w.lns[lane] = log(sig[lane]) - ln_ref;
+        if (lane < kk) w.lns[lane] = dlog_(sig[lane]) - ln_ref;
         if (kk >= 2 && lane < kk - 1) {
             double x0 = edges[lane + 1] - edges[lane];
             double x1;
@@ -219,7 +222,7 @@ template <typename T, int NC> struct Chain {
     }
     __device__ __forceinline__ double prior_op(int kk, int i, int j) const
     {
-        double s2 = log(1.0 + P.opt.factor);
+        double s2 = dlog_(1.0 + P.opt.factor);
         s2 *= s2;
         if (kk == 1) return 1.0 / s2 + 1.0 / (P.opt.gradient_std * P.opt.gradient_std);
         if (i == j) {
@@ -233,13 +236,14 @@ template <typename T, int NC> struct Chain {
         return 0.0;
     }
     // gradient of lane i: Wm'Wm (ln s - ln ref) + J' Wd'Wd (pred - d)   (Model.local_gradient :347-357)
-    __device__ __forceinline__ double gradient_lane(int kk, const T* J, const T* pred)
+    __device__ __noinline__ double gradient_lane(int kk, const T* J, const T* pred)
     {
         double g = 0.0;
         if (lane < kk) {
             g = prior_op(kk, lane, lane) * w.lns[lane];
             if (lane > 0) g += prior_op(kk, lane, lane - 1) * w.lns[lane - 1];
             if (lane < kk - 1) g += prior_op(kk, lane, lane + 1) * w.lns[lane + 1];
+            #pragma unroll 1
             for (int c = 0; c < C; ++c) {
                 double iv = w.ivar[c];
                 g += (double)J[c * KS + lane] * (((double)pred[c] - w.data[c]) * iv);
@@ -248,11 +252,13 @@ template <typename T, int NC> struct Chain {
         return g;
     }
     // A = Wm'Wm + J' Wd'Wd J (Model.local_precision :250-272), packed lower triangle
-    __device__ __forceinline__ void assemble(int kk, const T* J)
+    __device__ __noinline__ void assemble(int kk, const T* J)
     {
+        #pragma unroll 1
         for (int i = 0; i < kk; ++i) {
             if (lane <= i) {
                 double s = prior_op(kk, i, lane);
+                #pragma unroll 1
                 for (int c = 0; c < C; ++c) s += (double)J[c * KS + i] * w.ivar[c] * (double)J[c * KS + lane];
                 w.A[pk(i, lane)] = s;
             }
@@ -260,20 +266,22 @@ template <typename T, int NC> struct Chain {
         __syncwarp();
     }
     // in-place packed Cholesky, lane = row.  Returns false if not positive definite.  logdetL = sum ln L_jj
-    __device__ __forceinline__ bool cholesky(int kk, double* logdetL)
+    __device__ __noinline__ bool cholesky(int kk, double* logdetL)
     {
         double ld = 0.0;
         bool ok = true;
+        #pragma unroll 1
         for (int j = 0; j < kk; ++j) {
             double s = 0.0;
             if (lane >= j && lane < kk) {
                 s = w.A[pk(lane, j)];
+                #pragma unroll 1
                 for (int p = 0; p < j; ++p) s -= w.A[pk(lane, p)] * w.A[pk(j, p)];
             }
             double d = __shfl_sync(FULL, s, j);
             if (!(d > 0.0)) ok = false;
             double dj = sqrt(d);
-            ld += log(dj);
+            ld += dlog_(dj);
             if (lane == j) w.A[pk(j, j)] = dj;
             else if (lane > j && lane < kk) w.A[pk(lane, j)] = s / dj;
             __syncwarp();
@@ -282,8 +290,9 @@ template <typename T, int NC> struct Chain {
         return ok;
     }
     // lane i holds b_i; returns (L L')^-1 b for lane i
-    __device__ __forceinline__ double solve_L(int kk, double x)
+    __device__ __noinline__ double solve_L(int kk, double x)
     {
+        #pragma unroll 1
         for (int j = 0; j < kk; ++j) {
             double yj = __shfl_sync(FULL, x, j) / w.A[pk(j, j)];
             if (lane == j) x = yj;
@@ -291,8 +300,9 @@ template <typename T, int NC> struct Chain {
         }
         return x;
     }
-    __device__ __forceinline__ double solve_LT(int kk, double x)
+    __device__ __noinline__ double solve_LT(int kk, double x)
     {
+        #pragma unroll 1
         for (int j = kk - 1; j >= 0; --j) {
             double xj = __shfl_sync(FULL, x, j) / w.A[pk(j, j)];
             if (lane == j) x = xj;
@@ -301,12 +311,13 @@ template <typename T, int NC> struct Chain {
         return x;
     }
     // v' A v = |L' v|^2 with v_i held by lane i
-    __device__ __forceinline__ double quad(int kk, double v)
+    __device__ __noinline__ double quad(int kk, double v)
     {
         if (lane < kk) w.vec[lane] = v;
         __syncwarp();
         double s = 0.0;
         if (lane < kk)
+            #pragma unroll 1
             for (int i = lane; i < kk; ++i) s += w.A[pk(i, lane)] * w.vec[i];
         __syncwarp();
         return warp_sum(s * s);
@@ -314,7 +325,7 @@ template <typename T, int NC> struct Chain {
 
     // ------------------------------------------------------------ structure proposal (lane 0, serial)
     // RectilinearMesh1D.perturb :993-1120.  Writes edges_p / sig_r, returns action and new k via shuffle.
-    __device__ __forceinline__ int perturb_structure(int* knew)
+    __device__ __noinline__ int perturb_structure(int* knew)
     {
         int action = 0, kn = k;
         unsigned long long blk = rng.block;
@@ -326,8 +337,10 @@ template <typename T, int NC> struct Chain {
             const double* s0 = w.sig_c;
             double* z = w.edges_p;
             double* sr = w.sig_r;
+            #pragma unroll 1
             for (;;) {
                 int event;
+                #pragma unroll 1
                 for (;;) {
                     double u = rng_uniform(g);
                     event = (u <= cum0) ? 0 : (u <= cum1) ? 1 : (u <= cum2) ? 2 : 3;
@@ -336,7 +349,9 @@ template <typename T, int NC> struct Chain {
                     break;
                 }
                 if (event == ACT_NONE) {
+                    #pragma unroll 1
                     for (int i = 0; i <= k; ++i) z[i] = e0[i];
+                    #pragma unroll 1
                     for (int i = 0; i < k; ++i) sr[i] = s0[i];
                     action = ACT_NONE;
                     kn = k;
@@ -345,13 +360,16 @@ template <typename T, int NC> struct Chain {
                 if (event == ACT_BIRTH) {
                     bool ok = false;
                     int pos = 0;
-                    const double lo = log(o.min_edge), hi = log(o.max_edge);
+                    const double lo = dlog_(o.min_edge), hi = dlog_(o.max_edge);
+                    #pragma unroll 1
                     for (int tries = 1; tries <= 10; ++tries) {
-                        double e = exp(lo + (hi - lo) * rng_uniform(g));
+                        double e = dexp_(lo + (hi - lo) * rng_uniform(g));
                         pos = 0;
+                        #pragma unroll 1
                         while (pos <= k && e0[pos] < e) ++pos;
                         // min width of the edges with e inserted at pos: only the two new cells can shrink
                         double h = INFINITY;
+                        #pragma unroll 1
                         for (int i = 0; i + 1 <= k; ++i) {
                             if (i + 1 == pos) continue;
                             double d = e0[i + 1] - e0[i];
@@ -362,15 +380,19 @@ template <typename T, int NC> struct Chain {
                         if (tries == 10) break;
                         if (h > o.min_width) {
                             ok = true;
+                            #pragma unroll 1
                             for (int i = 0; i < pos; ++i) z[i] = e0[i];
                             z[pos] = e;
+                            #pragma unroll 1
                             for (int i = pos; i <= k; ++i) z[i + 1] = e0[i];
                             break;
                         }
                     }
                     if (!ok) continue;
+                    #pragma unroll 1
                     for (int i = 0; i < pos; ++i) sr[i] = s0[i];
                     sr[pos] = s0[pos - 1];
+                    #pragma unroll 1
                     for (int i = pos; i < k; ++i) sr[i + 1] = s0[i];
                     action = ACT_BIRTH;
                     kn = k + 1;
@@ -378,10 +400,14 @@ template <typename T, int NC> struct Chain {
                 }
                 if (event == ACT_DEATH) {
                     int i = (int)(rng_uniform(g) * (double)(k - 1)) + 1;
+                    #pragma unroll 1
                     for (int j = 0; j < i; ++j) z[j] = e0[j];
+                    #pragma unroll 1
                     for (int j = i + 1; j <= k; ++j) z[j - 1] = e0[j];
                     double val = 0.5 * (s0[i - 1] + s0[i]);
+                    #pragma unroll 1
                     for (int j = 0; j < i; ++j) sr[j] = s0[j];
+                    #pragma unroll 1
                     for (int j = i + 1; j < k; ++j) sr[j - 1] = s0[j];
                     sr[i - 1] = val;
                     action = ACT_DEATH;
@@ -390,7 +416,9 @@ template <typename T, int NC> struct Chain {
                 }
                 {  // ACT_MOVE
                     bool ok = false;
+                    #pragma unroll 1
                     for (int tries = 1; tries <= 10; ++tries) {
+                        #pragma unroll 1
                         for (int i = 0; i <= k; ++i) z[i] = e0[i];
                         int i = (int)(1.0 + ((double)k - 1.0) * rng_uniform(g));
                         double zn = rng_normal(g);
@@ -398,6 +426,7 @@ template <typename T, int NC> struct Chain {
                         double dz = sgn * o.min_width * rng_uniform(g);
                         z[i] += dz;
                         double h = INFINITY;
+                        #pragma unroll 1
                         for (int q = 0; q + 1 <= k; ++q) {
                             double d = z[q + 1] - z[q];
                             if (d < h) h = d;
@@ -409,6 +438,7 @@ template <typename T, int NC> struct Chain {
                         }
                     }
                     if (!ok) continue;
+                    #pragma unroll 1
                     for (int i = 0; i < k; ++i) sr[i] = s0[i];
                     action = ACT_MOVE;
                     kn = k;
@@ -429,7 +459,7 @@ template <typename T, int NC> struct Chain {
     __device__ __forceinline__ size_t nsig() const { return (size_t)P.opt.n_sigma_bins; }
 
     // add `count` visits of the CURRENT model / errors to every histogram
-    __device__ __forceinline__ void flush(int count)
+    __device__ __noinline__ void flush(int count)
     {
         if (count <= 0) return;
         const gbp_chain_buffers& o = P.out;
@@ -437,14 +467,14 @@ template <typename T, int NC> struct Chain {
         if (lane == 0) {
             if (o.ncells_hist) o.ncells_hist[(size_t)chain * (P.opt.max_layers + 1) + k] += count;
             if (o.rel_hist && P.opt.solve_relative_error)
-                o.rel_hist[(size_t)chain * P.opt.n_err_bins + uniform_bin(log(rel), rel_lo, rel_dx, P.opt.n_err_bins)] += count;
+                o.rel_hist[(size_t)chain * P.opt.n_err_bins + uniform_bin(dlog_(rel), rel_lo, rel_dx, P.opt.n_err_bins)] += count;
             if (o.add_hist && P.opt.solve_additive_error)
-                o.add_hist[(size_t)chain * P.opt.n_err_bins + uniform_bin(log(add), add_lo, add_dx, P.opt.n_err_bins)] += count;
+                o.add_hist[(size_t)chain * P.opt.n_err_bins + uniform_bin(dlog_(add), add_lo, add_dx, P.opt.n_err_bins)] += count;
         }
         // per-layer conductivity bin; interface histogram (RectilinearMesh1D.update_posteriors :1594-1610)
-        if (lane < k) w.sbin[lane] = uniform_bin(log(w.sig_c[lane]), sig_lo, sig_dx, P.opt.n_sigma_bins);
+        if (lane < k) w.sbin[lane] = uniform_bin(dlog_(w.sig_c[lane]), sig_lo, sig_dx, P.opt.n_sigma_bins);
         if (lane >= 1 && lane < k && o.edges_hist) {
-            double r = exp(log(w.sig_c[lane]) - log(w.sig_c[lane - 1]));
+            double r = dexp_(dlog_(w.sig_c[lane]) - dlog_(w.sig_c[lane - 1]));
             double d = w.edges_c[lane];
             if ((r <= 0.5 || r >= 1.5) && d >= 0.0 && d < (double)nd * depth_step)
                 atomicAdd(&o.edges_hist[(size_t)chain * nd + uniform_bin(d, 0.0, depth_step, nd)], count);
@@ -453,9 +483,11 @@ template <typename T, int NC> struct Chain {
         // hitmap (Model.update_parameter_posterior :819-847; staircase interp RectilinearMesh1D.py:1148-1158)
         if (o.hitmap) {
             int32_t* hm = o.hitmap + (size_t)chain * nsig() * nd;
+            #pragma unroll 1
             for (int j = lane; j < nd; j += 32) {
                 const double y = ((double)j + 0.5) * depth_step;
                 int b = w.sbin[k - 1];
+                #pragma unroll 1
                 for (int i = 1; i < k; ++i) {
                     const double e = w.edges_c[i];
                     if (y < e) {
@@ -466,7 +498,7 @@ template <typename T, int NC> struct Chain {
                     if (y < e2) {
                         double t = (y - e) / (e2 - e);
                         double v = w.sig_c[i - 1] + t * (w.sig_c[i] - w.sig_c[i - 1]);
-                        b = uniform_bin(log(v), sig_lo, sig_dx, P.opt.n_sigma_bins);
+                        b = uniform_bin(dlog_(v), sig_lo, sig_dx, P.opt.n_sigma_bins);
                         break;
                     }
                 }
@@ -476,32 +508,38 @@ template <typename T, int NC> struct Chain {
         __syncwarp();
     }
 
-    __device__ __forceinline__ void zero_posteriors()
+    __device__ __noinline__ void zero_posteriors()
     {
         const gbp_chain_buffers& o = P.out;
         const int nd = P.n_depth;
         if (o.hitmap) {
             int32_t* hm = o.hitmap + (size_t)chain * nsig() * nd;
             const size_t n = nsig() * nd;
+            #pragma unroll 1
             for (size_t i = lane; i < n; i += 32) hm[i] = 0;
         }
         if (o.edges_hist)
+            #pragma unroll 1
             for (int i = lane; i < nd; i += 32) o.edges_hist[(size_t)chain * nd + i] = 0;
         if (o.ncells_hist)
+            #pragma unroll 1
             for (int i = lane; i <= P.opt.max_layers; i += 32) o.ncells_hist[(size_t)chain * (P.opt.max_layers + 1) + i] = 0;
         if (o.rel_hist)
+            #pragma unroll 1
             for (int i = lane; i < P.opt.n_err_bins; i += 32) o.rel_hist[(size_t)chain * P.opt.n_err_bins + i] = 0;
         if (o.add_hist)
+            #pragma unroll 1
             for (int i = lane; i < P.opt.n_err_bins; i += 32) o.add_hist[(size_t)chain * P.opt.n_err_bins + i] = 0;
         __syncwarp();
     }
 
-    __device__ __forceinline__ void save_best()
+    __device__ __noinline__ void save_best()
     {
         const gbp_chain_buffers& o = P.out;
         const int ml = P.opt.max_layers;
         if (o.best_sigma && lane < ml) o.best_sigma[(size_t)chain * ml + lane] = lane < k ? w.sig_c[lane] : NAN;
         if (o.best_edges)
+            #pragma unroll 1
             for (int i = lane; i <= ml; i += 32) o.best_edges[(size_t)chain * (ml + 1) + i] = i <= k ? w.edges_c[i] : NAN;
         best_k = k;
         best_rel = rel;
@@ -511,7 +549,7 @@ template <typename T, int NC> struct Chain {
     }
 
     // ------------------------------------------------------------ Inference1D.initialize
-    __device__ __forceinline__ void initialize(bool first)
+    __device__ __noinline__ void initialize(bool first)
     {
         const gbp_options& o = P.opt;
         rel = o.rel_init;
@@ -524,9 +562,10 @@ template <typename T, int NC> struct Chain {
         }
         __syncwarp();
         double best = INFINITY, best_c = 0.0;
+        #pragma unroll 1
         for (int i = 0; i < 100; ++i) {
             double e = (i == 99) ? 4.0 : -4.0 + (double)i * (8.0 / 99.0);
-            double c = pow(10.0, e);
+            double c = dexp_(e * 2.302585092994045684017991454684);
             if (lane == 0) w.sig_c[0] = c;
             __syncwarp();
             forward(1, w.sig_c, w.edges_c, w.pred_c);
@@ -538,26 +577,28 @@ template <typename T, int NC> struct Chain {
             }
         }
         sigma_ref = best_c;
-        ln_ref = log(sigma_ref);
+        ln_ref = dlog_(sigma_ref);
         k = 1;
         if (lane == 0) w.sig_c[0] = sigma_ref;
         __syncwarp();
         forward_sens(1, w.sig_c, w.edges_c, w.pred_c, w.Jc);
         // posterior grids (Model.set_posteriors :666-684, DataPoint.set_*_error_posterior :668-695)
-        const double s = log(1.0 + o.factor);
+        const double s = dlog_(1.0 + o.factor);
         sig_lo = ln_ref - o.sigma_bins_nstd * s;
         sig_dx = 2.0 * o.sigma_bins_nstd * s / (double)o.n_sigma_bins;
-        rel_lo = log(o.rel_min);
-        rel_dx = (log(o.rel_max) - log(o.rel_min)) / (double)o.n_err_bins;
-        add_lo = log(o.add_min);
-        add_dx = (log(o.add_max) - log(o.add_min)) / (double)o.n_err_bins;
+        rel_lo = dlog_(o.rel_min);
+        rel_dx = (dlog_(o.rel_max) - dlog_(o.rel_min)) / (double)o.n_err_bins;
+        add_lo = dlog_(o.add_min);
+        add_dx = (dlog_(o.add_max) - dlog_(o.add_min)) / (double)o.n_err_bins;
         depth_step = 0.5 * o.min_width;
         if (!first) {  // reset(): posteriors and traces are re-created
             zero_posteriors();
             const size_t N2 = 2 * (size_t)o.n_markov_chains;
             if (P.out.misfit_trace)
+                #pragma unroll 1
                 for (size_t i = lane; i < N2; i += 32) P.out.misfit_trace[(size_t)chain * N2 + i] = 0.0;
             if (P.out.accept_trace)
+                #pragma unroll 1
                 for (size_t i = lane; i < N2; i += 32) P.out.accept_trace[(size_t)chain * N2 + i] = 0;
             __syncwarp();
         }
@@ -576,7 +617,7 @@ template <typename T, int NC> struct Chain {
 
     // ------------------------------------------------------------ Inference1D.accept_reject
     // returns true if the chain failed (Gauss-Newton matrix not positive definite)
-    __device__ __forceinline__ bool step(bool* accepted_out)
+    __device__ __noinline__ bool step(bool* accepted_out)
     {
         const gbp_options& o = P.opt;
         *accepted_out = false;
@@ -596,14 +637,14 @@ template <typename T, int NC> struct Chain {
         }
         set_ivar(rel, add);
         prior_setup(kn, w.sig_r, w.edges_p);
-        const double ln_r = (lane < kn) ? log(w.sig_r[lane]) : 0.0;
+        const double ln_r = (lane < kn) ? dlog_(w.sig_r[lane]) : 0.0;
         const double g = gradient_lane(kn, Jh, ph);
         assemble(kn, Jh);
         double logdetL;
         if (!cholesky(kn, &logdetL)) return true;
         const double stepv = solve_LT(kn, solve_L(kn, g));       // H * dfk
         const double mean = ln_r - o.covariance_scaling * stepv;  // ln sigma + alpha * pk, pk = -H dfk
-        // sigma' ~ exp(N(mean, H)),  H = (L L')^-1  ->  mean + L^-T z
+        // sigma' ~ dexp_(N(mean, H)),  H = (L L')^-1  ->  mean + L^-T z
         double z0 = 0.0, z1 = 0.0;
         const int npair = (kn + 1) / 2;
         if (lane < npair) normal2_at(rng, rng.block + (unsigned long long)lane, &z0, &z1);
@@ -612,7 +653,7 @@ template <typename T, int NC> struct Chain {
         const double zi = (lane < kn) ? ((lane & 1) ? zb : za) : 0.0;
         const double dx = solve_LT(kn, zi);
         const double ln_t = mean + dx;
-        if (lane < kn) w.sig_t[lane] = exp(ln_t);
+        if (lane < kn) w.sig_t[lane] = dexp_(ln_t);
         __syncwarp();
 
         // test_datapoint.perturb() (DataPoint.py:531-573)
@@ -639,7 +680,7 @@ template <typename T, int NC> struct Chain {
             const double g2 = gradient_lane(kn, w.Jt, w.pred_t);
             const double s2 = solve_LT(kn, solve_L(kn, g2));  // H dfk'
             const double lv = ln_t + o.covariance_scaling * s2;  // Model.py:626 (sign as in the reference)
-            const double mv = exp(lv);
+            const double mv = dexp_(lv);
             const int bad = __any_sync(FULL, lane < kn && (mv == INFINITY || mv == 0.0));
             const double q_r = quad(kn, (lane < kn) ? (ln_r - lv) : 0.0);
             const double q_f = quad(kn, (lane < kn) ? (ln_t - ln_r) : 0.0);
@@ -653,7 +694,7 @@ template <typename T, int NC> struct Chain {
         }
         const double log_alpha = (t_prior - prior) + (t_like - likelihood) + (proposal - proposal1);
         const double u = rng_uniform(rng);
-        const bool acc = exp(log_alpha) > u;
+        const bool acc = dexp_(log_alpha) > u;
         if (acc) {
             flush(dwell);  // the outgoing model's visits
             dwell = 0;
@@ -668,6 +709,7 @@ template <typename T, int NC> struct Chain {
             if (lane <= kn) w.edges_c[lane] = w.edges_p[lane];
             if (lane < C) w.pred_c[lane] = w.pred_t[lane];
             if (action != ACT_NONE)
+                #pragma unroll 1
                 for (int i = lane; i < C * KS; i += 32) w.Jc[i] = w.Jt[i];
             __syncwarp();
             n_accept++;
@@ -677,7 +719,7 @@ template <typename T, int NC> struct Chain {
     }
 
     // ------------------------------------------------------------ Inference1D.update; returns true on reset
-    __device__ __forceinline__ bool update(bool accepted)
+    __device__ __noinline__ bool update(bool accepted)
     {
         const gbp_options& o = P.opt;
         const long long N2 = 2 * (long long)o.n_markov_chains;
@@ -747,6 +789,7 @@ template <typename T, int NC> struct Chain {
         bool go = !failed;
         long long total = 0;
         const long long N = o.n_markov_chains;
+        #pragma unroll 1
         while (go) {
             bool accepted;
             failed = step(&accepted);
@@ -781,9 +824,11 @@ template <typename T, int NC> struct Chain {
         const int ml = o.max_layers;
         if (ob.cur_sigma && lane < ml) ob.cur_sigma[(size_t)chain * ml + lane] = lane < k ? w.sig_c[lane] : NAN;
         if (ob.cur_edges)
+            #pragma unroll 1
             for (int i = lane; i <= ml; i += 32) ob.cur_edges[(size_t)chain * (ml + 1) + i] = i <= k ? w.edges_c[i] : NAN;
         if (lane == 0) {
             double* s = ob.scalars + (size_t)chain * GBP_NSCALARS;
+            #pragma unroll 1
             for (int i = 0; i < GBP_NSCALARS; ++i) s[i] = 0.0;
             s[GBP_S_ITER] = (double)iteration;
             s[GBP_S_BURNED_IN] = burned_in;
@@ -831,6 +876,7 @@ __global__ void __launch_bounds__(512, 1) rjmcmc_kernel(const __grid_constant__ 
     // persistent: the first wave is assigned statically, later chains come from a device-side counter
     int c = blockIdx.x * (blockDim.x >> 5) + warp;
     const int lane = threadIdx.x & 31;
+    #pragma unroll 1
     while (c < P.B) {
         ch.run(c);
         int nxt = 0;
@@ -861,6 +907,7 @@ __global__ void __launch_bounds__(256) fdem_kernel(const __grid_constant__ SysDe
     T* mthk = base + KS;
     T* pred = base + 2 * KS;
     T* J = base + 2 * KS + GBP_MAXC;
+    #pragma unroll 1
     for (int b = blockIdx.x * wpb + warp; b < B; b += gridDim.x * wpb) {
         const int L = nlayers[b];
         if (lane < L) {
@@ -871,6 +918,7 @@ __global__ void __launch_bounds__(256) fdem_kernel(const __grid_constant__ SysDe
         fdem_eval<T, SENS>(S, tab, (T)altitude[b], L, msig, mthk, pred, SENS ? J : nullptr);
         if (lane < C) out[(size_t)b * C + lane] = (double)pred[lane];
         if (SENS) {
+            #pragma unroll 1
             for (int i = lane; i < C * l_stride; i += 32) {
                 const int c = i / l_stride, kk = i % l_stride;
                 Jout[(size_t)b * C * l_stride + i] = (kk < L) ? (double)J[c * KS + kk] : 0.0;

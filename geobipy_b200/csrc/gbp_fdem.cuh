@@ -60,6 +60,7 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
             : "memory");
     }
     uint32_t done = 0;
+    #pragma unroll 1
     while (!done) {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
@@ -74,7 +75,7 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
 // msig/mthk: shared memory, per-warp model (conductivity, thickness) in T; mthk[L-1] unused.
 // pred: [2F] (real then imag).  J: [2F][KS] (only if SENS).  All lanes of the warp must call.
 template <typename T, bool SENS>
-__device__ __forceinline__ void fdem_eval(const SysDev& S, const T* __restrict__ tab, T alt, int L,
+__device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ tab, T alt, int L,
                                           const T* __restrict__ msig, const T* __restrict__ mthk,
                                           T* __restrict__ pred, T* __restrict__ J)
 {
@@ -94,19 +95,23 @@ __device__ __forceinline__ void fdem_eval(const SysDev& S, const T* __restrict__
     T jr[SENS ? KS : 1], ji[SENS ? KS : 1];
 
     int seg = 0;
+    #pragma unroll 1
     for (int f = 0; f < F; ++f) {
         const T omu = (T)S.omu[f];
         const T k2 = (T)S.k2re[f];
         const T hd = (T)S.hd0[f] - T(2) * alt;
         cx<T> acc = {T(0), T(0)};
         if (SENS) {
+            #pragma unroll 1
             for (int k = 0; k < L; ++k) {
                 jr[k] = T(0);
                 ji[k] = T(0);
             }
         }
+        #pragma unroll 1
         for (; seg < S.n_seg && S.seg[seg].freq == f; ++seg) {
             const int s0 = S.seg[seg].start, cnt = S.seg[seg].count;
+            #pragma unroll 1
             for (int j = lane; j < cnt; j += 32) {
                 const int i = s0 + j;
                 const T lam = t_lam[i];
@@ -120,12 +125,19 @@ __device__ __forceinline__ void fdem_eval(const SysDev& S, const T* __restrict__
                     lr[L - 1] = T(-0.5) * b * iu.im;
                     li[L - 1] = T(0.5) * b * iu.re;
                 }
+                #pragma unroll 1
                 for (int k = L - 2; k >= 0; --k) {
                     b = omu * msig[k];
                     const T t = mthk[k];
                     u = csqrt_q1<T>(a, b);
                     // tanh(u t) = (1 - e)/(1 + e), e = exp(-2ut), Re(u) > 0 always (cTanh first branch)
-                    cx<T> e = cexp_<T>(mk<T>(T(-2) * t * u.re, T(-2) * t * u.im));
+                    // |Im(2ut)| <= Re(2ut); beyond Re(2ut) = 60 the term e^-60 is below fp64 round-off
+                    // of tanh = 1: clamp so that the sin/cos argument stays small (t may be huge)
+                    // (then e is set to exactly 0, as exp() underflows to in the reference)
+                    const T two_t = T(2) * t;
+                    const T sc = fmin(two_t, T(60) * rt<T>::rcp(u.re));
+                    cx<T> e = cexp_<T>(mk<T>(-sc * u.re, -sc * u.im));
+                    if (two_t * u.re > T(60)) e = mk<T>(T(0), T(0));
                     cx<T> th = mk<T>(T(1) - e.re, -e.im) * cinv(mk<T>(T(1) + e.re, e.im));
                     cx<T> den = u + y * th;
                     cx<T> num = y + u * th;
@@ -155,6 +167,7 @@ __device__ __forceinline__ void fdem_eval(const SysDev& S, const T* __restrict__
                 acc = acc + rte * K;
                 if (SENS) {
                     cx<T> P = (u0 * is * is) * T(-2) * K;  // d rTE/dy1 * K
+                    #pragma unroll 1
                     for (int k = 0; k < L; ++k) {
                         cx<T> v = P * mk<T>(lr[k], li[k]);
                         jr[k] += v.re;
@@ -170,6 +183,7 @@ __device__ __forceinline__ void fdem_eval(const SysDev& S, const T* __restrict__
             pred[F + f] = si;
         }
         if (SENS) {
+            #pragma unroll 1
             for (int k = 0; k < L; ++k) {
                 const T a = warp_sum(jr[k]), b = warp_sum(ji[k]);
                 if (lane == 0) {
