@@ -1,0 +1,379 @@
+"""Host-side mirror of the reference's object interface for the per-sounding inference path.
+
+Same names, argument meaning and error behaviour as the reference classes on this path, so that the
+calls a GeoBIPy driver makes (`Inference3D.infer_serial`, geobipy/src/inversion/Inference3D.py:483-492)
+
+    dp  = FdemDataPoint(x, y, z, elevation, data=..., system=FdemSystem.read("resolve.stm"))
+    inf = Inference1D(**options, prng=...)        # options = keys of a reference options file
+    inf.initialize(dp)
+    failed = inf.infer(hdf_file_handle)
+
+run on the GPU.  Everything numerical happens behind the C-ABI (ops.py); these classes only carry data.
+Mirrored: FdemSystem (classes/system/FdemSystem.py), CircularLoop (classes/system/CircularLoop.py),
+RectilinearMesh1D / Model (containers only), FdemDataPoint (classes/data/datapoint/FdemDataPoint.py,
+DataPoint.py, EmDataPoint.py), Histogram (classes/statistics/Histogram.py: counts + mean/percentile),
+Inference1D (inversion/Inference1D.py) and a batched Inference3D.infer replacement (`infer_batch`).
+"""
+import numpy as np
+
+from . import _lib, ops
+
+__all__ = ["CircularLoop", "FdemSystem", "RectilinearMesh1D", "Model", "FdemDataPoint", "Histogram",
+           "Inference1D", "infer_batch"]
+
+_ORI = {"x": 0, "y": 1, "z": 2}
+
+
+class CircularLoop:
+    """Loop description: orientation ('x'|'y'|'z'), moment and offsets (classes/system/CircularLoop.py)."""
+
+    def __init__(self, orientation=None, moment=None, x=None, y=None, z=None, **kwargs):
+        n = 0 if orientation is None else len(orientation)
+        self.orientation = [str(o).strip() for o in (orientation if orientation is not None else [])]
+        self._orientation = np.asarray([_ORI[o] for o in self.orientation], dtype=np.int32)
+
+        def arr(v):
+            return np.zeros(n) if v is None else np.asarray(v, dtype=np.float64).reshape(-1)
+        self.moment, self.x, self.y, self.z = arr(moment), arr(x), arr(y), arr(z)
+
+
+class FdemSystem:
+    """Frequency-domain acquisition system (classes/system/FdemSystem.py)."""
+
+    def __init__(self, frequencies=None, transmitter=None, receiver=None):
+        self.frequencies = np.asarray(frequencies if frequencies is not None else [], dtype=np.float64)
+        self.transmitter = transmitter if transmitter is not None else CircularLoop()
+        self.receiver = receiver if receiver is not None else CircularLoop()
+        self._filename = None
+        self._struct = None
+
+    @classmethod
+    def read(cls, filename):
+        """Read an .stm file: header line, then `freq, tor, tmom, tx, ty, tz, ror, rmom, rx, ry, rz`
+        per frequency (FdemSystem.read, FdemSystem.py:146-183)."""
+        rows = []
+        with open(filename) as f:
+            next(f)
+            for line in f:
+                p = [t.strip() for t in line.strip().split(",")]
+                if len(p) >= 11:
+                    rows.append(p)
+        col = lambda i: [r[i] for r in rows]  # noqa: E731
+        num = lambda i: [float(r[i]) for r in rows]  # noqa: E731
+        self = cls(num(0), CircularLoop(col(1), num(2), num(3), num(4), num(5)),
+                   CircularLoop(col(6), num(7), num(8), num(9), num(10)))
+        self._filename = filename
+        return self
+
+    @property
+    def nFrequencies(self):
+        return self.frequencies.size
+
+    @property
+    def tensor_id(self):
+        return 1 + 3 * self.receiver._orientation + self.transmitter._orientation
+
+    @property
+    def loop_offsets(self):
+        return np.vstack([self.receiver.x - self.transmitter.x, self.receiver.y - self.transmitter.y,
+                          self.receiver.z - self.transmitter.z])
+
+    @property
+    def loop_separation(self):
+        return np.linalg.norm(self.loop_offsets, axis=0)
+
+    @property
+    def lamda0(self):
+        l0 = 10.0 ** (np.arange(120, dtype=np.float64) * 9.04226468670e-2 - 8.3885)
+        return np.outer(1.0 / self.loop_separation, l0)
+
+    @property
+    def lamda1(self):
+        l1 = 10.0 ** (np.arange(140, dtype=np.float64) * 8.7967143957e-2 - 7.91001919)
+        return np.outer(1.0 / self.loop_separation, l1)
+
+    @property
+    def c_struct(self):
+        if self._struct is None:
+            t, r = self.transmitter, self.receiver
+            self._struct = ops.make_system_struct(self.frequencies, t.orientation, t.moment, t.x, t.y, t.z,
+                                                  r.orientation, r.moment, r.x, r.y, r.z)
+        return self._struct
+
+
+class RectilinearMesh1D:
+    """Layer edges container (classes/mesh/RectilinearMesh1D.py): edges[0] = top, edges[-1] = inf."""
+
+    def __init__(self, edges=None, centres=None, widths=None, **kwargs):
+        if edges is None and widths is not None:
+            edges = np.r_[0.0, np.cumsum(widths)]
+        self.edges = np.asarray(edges, dtype=np.float64)
+
+    @property
+    def nCells(self):
+        return self.edges.size - 1
+
+    @property
+    def nEdges(self):
+        return self.edges.size
+
+    @property
+    def widths(self):
+        return np.diff(self.edges)
+
+    @property
+    def centres(self):
+        return 0.5 * (self.edges[1:] + self.edges[:-1])
+
+
+class Model:
+    """Values on a mesh (classes/model/Model.py, container part)."""
+
+    def __init__(self, mesh=None, values=None):
+        self.mesh = mesh
+        self.values = np.asarray(values, dtype=np.float64) if values is not None else np.zeros(mesh.nCells)
+        self.posterior = None  # Histogram (hitmap) after an inference
+
+    @property
+    def nCells(self):
+        return self.mesh.nCells
+
+
+class Histogram:
+    """Posterior accumulator (classes/statistics/Histogram.py): `counts` on a 1-D or 2-D mesh.
+
+    2-D hitmaps are [n_x (conductivity bins), n_y (depth cells)] like the reference's
+    `model.values.posterior.counts`; x edges are in linear units, binned uniformly in ln."""
+
+    def __init__(self, counts, x_edges=None, y_edges=None, log_x=False):
+        self.counts = np.asarray(counts)
+        self.x_edges, self.y_edges, self.log_x = x_edges, y_edges, log_x
+
+    @property
+    def values(self):
+        return self.counts
+
+    def _xc(self):
+        e = np.log(self.x_edges) if self.log_x else np.asarray(self.x_edges)
+        return 0.5 * (e[1:] + e[:-1])
+
+    def mean(self):
+        """Mean along the value axis for every depth cell (Mesh._mean, classes/mesh/Mesh.py:80)."""
+        c = self._xc()
+        h = self.counts.astype(np.float64)
+        if h.ndim == 1:
+            m = (h * c).sum() / max(h.sum(), 1.0)
+        else:
+            m = (h * c[:, None]).sum(axis=0) / np.maximum(h.sum(axis=0), 1.0)
+        return np.exp(m) if self.log_x else m
+
+    def percentile(self, percent):
+        """Value-axis percentile per depth cell (Mesh._percentile, classes/mesh/Mesh.py:173-217)."""
+        c = self._xc()
+        h = np.atleast_2d(self.counts.T).T if self.counts.ndim == 1 else self.counts
+        cs = np.cumsum(h, axis=0).astype(np.float64)
+        tot = np.maximum(cs[-1], 1.0)
+        idx = np.minimum((cs < (percent / 100.0) * tot).sum(axis=0), c.size - 1)
+        out = c[idx]
+        out = np.exp(out) if self.log_x else out
+        return out if self.counts.ndim > 1 else out.item()
+
+    def median(self):
+        return self.percentile(50.0)
+
+
+class FdemDataPoint:
+    """One frequency-domain sounding (FdemDataPoint.py / EmDataPoint.py / DataPoint.py).
+
+    data / predictedData are [in-phase(F), quadrature(F)] in ppm."""
+
+    def __init__(self, x=0.0, y=0.0, z=0.0, elevation=0.0, data=None, std=None, predictedData=None, system=None,
+                 lineNumber=0.0, fiducial=0.0, precision=_lib.PRECISION_F64, **kwargs):
+        if isinstance(system, str):
+            system = FdemSystem.read(system)
+        if isinstance(system, (list, tuple)):
+            assert len(system) == 1, NotImplementedError("one FDEM system per datapoint")
+            system = system[0]
+        assert isinstance(system, FdemSystem), TypeError("system must have type FdemSystem")
+        self.system = system
+        self.x, self.y, self.z, self.elevation = float(x), float(y), float(z), float(elevation)
+        self.lineNumber, self.fiducial = lineNumber, fiducial
+        n = 2 * system.nFrequencies
+        self.data = np.zeros(n) if data is None else np.asarray(data, dtype=np.float64).copy()
+        self._std = np.full(n, 0.01) if std is None else np.asarray(std, dtype=np.float64).copy()
+        self.predictedData = np.zeros(n) if predictedData is None else np.asarray(predictedData, dtype=np.float64).copy()
+        assert self.data.size == n and self.predictedData.size == n, ValueError("data must have 2 x nFrequencies entries")
+        self.relative_error = np.asarray([0.01])
+        self.additive_error = np.asarray([0.0])
+        self._use_errors = False
+        self.sensitivity_matrix = None
+        self.precision = precision
+        self.posteriors = {}
+
+    # -- EmDataPoint.active :44-56
+    @property
+    def active(self):
+        d = self.data.copy()
+        d[~(d > 0.0)] = np.nan
+        return ~np.isnan(d)
+
+    @property
+    def n_active_channels(self):
+        return int(self.active.sum())
+
+    @property
+    def nChannels(self):
+        return self.data.size
+
+    # -- DataPoint.std :268-282
+    @property
+    def std(self):
+        if self._use_errors:
+            assert np.all(self.relative_error > 0.0), ValueError("relative_error must be > 0.0")
+            self._std = np.sqrt((self.relative_error[0] * self.data) ** 2 + self.additive_error[0] ** 2)
+        return self._std
+
+    def initialize(self, **kwargs):
+        self.relative_error = np.atleast_1d(np.asarray(kwargs["initial_relative_error"], dtype=np.float64))
+        self.additive_error = np.atleast_1d(np.asarray(kwargs["initial_additive_error"], dtype=np.float64))
+        self._use_errors = True
+
+    @property
+    def deltaD(self):
+        return self.predictedData - self.data
+
+    def _model_arrays(self, mod):
+        assert isinstance(mod, Model), TypeError("Invalid model class for forward modeling [1D]")
+        assert np.isinf(mod.mesh.edges[-1]), ValueError("mod.edges must have last entry be infinity for forward modelling.")
+        assert self.z >= mod.mesh.edges[0], "Sensor altitude must be above the top of the model"  # fdem1d.py:29
+        L = mod.nCells
+        assert 1 <= L <= _lib.MAXL, ValueError("1..%d layers supported" % _lib.MAXL)
+        return (np.asarray([L], np.int32), mod.values.reshape(1, L).astype(np.float64),
+                mod.mesh.widths.reshape(1, L).astype(np.float64), np.asarray([self.z - mod.mesh.edges[0]]))
+
+    def forward(self, mod):
+        """Fill predictedData from a 1-D layered model (FdemDataPoint.forward :524 -> fdem1dfwd)."""
+        nl, s, t, a = self._model_arrays(mod)
+        self.predictedData[:] = ops.fdem_forward(self.system.c_struct, nl, s, t, a, precision=self.precision)[0]
+
+    def sensitivity(self, mod, **kwargs):
+        """Jacobian d(predicted)/d ln(sigma), shape [nChannels, nCells] (FdemDataPoint.sensitivity :531)."""
+        nl, s, t, a = self._model_arrays(mod)
+        _, J = ops.fdem_forward(self.system.c_struct, nl, s, t, a, precision=self.precision, sensitivity=True)
+        self.sensitivity_matrix = J[0]
+        return self.sensitivity_matrix
+
+    def fm_dlogc(self, mod):
+        nl, s, t, a = self._model_arrays(mod)
+        p, J = ops.fdem_forward(self.system.c_struct, nl, s, t, a, precision=self.precision, sensitivity=True)
+        self.predictedData[:] = p[0]
+        self.sensitivity_matrix = J[0]
+
+    # -- DataPoint.data_misfit :502-525, likelihood :491-500 (MvNormal log-pdf :209-216)
+    def data_misfit(self):
+        a = self.active
+        return float(np.sum((self.deltaD[a] / self.std[a]) ** 2))
+
+    def likelihood(self, log=True):
+        a = self.active
+        var = self.std[a] ** 2
+        ll = -0.5 * a.sum() * np.log(2.0 * np.pi) - 0.5 * np.sum(np.log(var)) - 0.5 * np.sum(self.deltaD[a] ** 2 / var)
+        return float(ll) if log else float(np.exp(ll))
+
+
+class Inference1D:
+    """Per-sounding rjMCMC sampler with the reference's interface (inversion/Inference1D.py).
+
+    `__init__` takes the keys of a reference options file (resolve_options) plus `prng`/`seed`;
+    `initialize(datapoint)` then `infer(hdf_file_handle)` -> failed.  Afterwards the attributes the
+    reference's `writeHdf` (:1050-1090) serialises are available: model (+ `.posterior` hitmap),
+    n_cells_posterior, edges_posterior, relative_error_posterior, additive_error_posterior, best_model,
+    data_misfit_v, acceptance_v, iteration, burned_in, burned_in_iteration, best_iteration, halfspace."""
+
+    def __init__(self, covariance_scaling=0.75, ignore_likelihood=False, interactive_plot=False, multiplier=1.0,
+                 n_markov_chains=100000, parameter_limits=None, prng=None, seed=None, save_hdf5=True, save_png=False,
+                 solve_gradient=True, solve_parameter=False, update_plot_every=5000, precision=_lib.PRECISION_F32,
+                 device=0, sounding_index=0, **kwargs):
+        assert interactive_plot or save_hdf5, Exception("You have chosen to neither view or save the inversion results!")
+        assert not ignore_likelihood, NotImplementedError("ignore_likelihood=True (prior sampling) is not on the GPU path")
+        assert parameter_limits is None, NotImplementedError("parameter_limits")
+        if seed is None:
+            # any numpy Generator can seed the counter-based device stream
+            seed = int(prng.integers(0, 2 ** 63 - 1)) if prng is not None else 0
+        self.seed, self.sounding_index = int(seed) & (2 ** 64 - 1), int(sounding_index)
+        self.n_markov_chains, self.update_plot_every = int(n_markov_chains), int(update_plot_every)
+        self.precision, self.device = precision, device
+        self.options = ops.make_options(covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains,
+                                        update_plot_every=update_plot_every, solve_gradient=int(bool(solve_gradient)),
+                                        solve_parameter=int(bool(solve_parameter)), **kwargs)
+        self.user_options = kwargs
+        self.datapoint = None
+
+    def initialize(self, datapoint):
+        assert isinstance(datapoint, FdemDataPoint), TypeError("datapoint must be a FdemDataPoint")
+        self.datapoint = datapoint
+        datapoint.initialize(initial_relative_error=self.options.rel_init, initial_additive_error=self.options.add_init)
+        self.iteration, self.burned_in, self.burned_in_iteration = 0, False, 0
+
+    def infer(self, hdf_file_handle=None, max_iterations=0):
+        dp = self.datapoint
+        if dp.n_active_channels == 0:
+            return True
+        r = ops.rjmcmc_run(dp.system.c_struct, self.options, dp.data.reshape(1, -1), np.asarray([dp.z]), seed=self.seed,
+                           first_index=self.sounding_index, max_iterations=max_iterations, precision=self.precision,
+                           device=self.device)
+        self._fill(r, 0)
+        return self.failed
+
+    def _fill(self, r, b):
+        o, s = self.options, r["scalars"][b]
+        self.halfspace = float(s[_lib.S_HALFSPACE])
+        g = ops.posterior_grids(o, self.halfspace)
+        self.iteration = int(s[_lib.S_ITER])
+        self.burned_in = bool(s[_lib.S_BURNED_IN])
+        self.burned_in_iteration = int(s[_lib.S_BURNED_IN_ITER])
+        self.best_iteration = int(s[_lib.S_BEST_ITER])
+        self.failed = bool(s[_lib.S_FAILED])
+        self.data_misfit = float(s[_lib.S_CUR_MISFIT])
+        self.prior, self.likelihood = float(s[_lib.S_CUR_PRIOR]), float(s[_lib.S_CUR_LIKELIHOOD])
+        self.posterior = self.prior + self.likelihood
+        self.best_posterior = float(s[_lib.S_BEST_POSTERIOR])
+        self.acceptance_rate = 100.0 * s[_lib.S_N_ACCEPT] / max(self.iteration, 1)
+        self.n_forward_evals = int(s[_lib.S_N_FORWARD])
+
+        def model(k, sig, edges):
+            k = int(k)
+            return Model(RectilinearMesh1D(edges=edges[:k + 1]), sig[:k])
+        self.model = model(s[_lib.S_CUR_K], r["cur_sigma"][b], r["cur_edges"][b])
+        self.best_model = model(s[_lib.S_BEST_K], r["best_sigma"][b], r["best_edges"][b])
+        self.model.posterior = Histogram(r["hitmap"][b], g["sigma_edges"], g["depth_edges"], log_x=True)
+        self.hitmap = self.model.posterior
+        self.n_cells_posterior = Histogram(r["ncells_hist"][b], np.arange(-0.5, o.max_layers + 1.0))
+        self.edges_posterior = Histogram(r["edges_hist"][b], g["depth_edges"])
+        self.relative_error_posterior = Histogram(r["rel_hist"][b], g["rel_edges"], log_x=True)
+        self.additive_error_posterior = Histogram(r["add_hist"][b], g["add_edges"], log_x=True)
+        self.data_misfit_v = r["misfit_trace"][b]
+        self.acceptance_v = r["accept_trace"][b]
+        dp = self.datapoint
+        dp.relative_error = np.asarray([s[_lib.S_CUR_REL]])
+        dp.additive_error = np.asarray([s[_lib.S_CUR_ADD]])
+        dp.forward(self.model)
+        self.best_relative_error, self.best_additive_error = float(s[_lib.S_BEST_REL]), float(s[_lib.S_BEST_ADD])
+
+    def interface_probability(self):
+        """edges histogram / sum (Inference2D.interface_probability, Inference2D.py:959-961)."""
+        c = self.edges_posterior.counts.astype(np.float64)
+        return c / max(c.sum(), 1.0)
+
+
+def infer_batch(system, data, altitude, seed=0, precision=_lib.PRECISION_F32, device=0, first_index=0,
+                outputs=ops.DEFAULT_OUTPUTS, max_iterations=0, **options):
+    """Batched replacement of the `Inference3D.infer_serial` loop (Inference3D.py:458-492): all soundings of
+    `data` [B, 2F] are inverted concurrently, one warp per sounding.  Returns the dict of posterior arrays
+    (`include/geobipy_b200.h` gbp_chain_buffers) plus the options struct used."""
+    s = system.c_struct if isinstance(system, FdemSystem) else system
+    opt = ops.make_options(**options)
+    r = ops.rjmcmc_run(s, opt, data, altitude, seed=seed, first_index=first_index, max_iterations=max_iterations,
+                       precision=precision, device=device, outputs=outputs)
+    r["options"] = opt
+    return r

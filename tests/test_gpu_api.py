@@ -1,0 +1,108 @@
+"""GPU tests of the reference-shaped object interface (geobipy_b200/api.py) - they read like the
+reference's own usage (documentation_source/source/examples/Datapoints/plot_resolve_datapoint.py,
+Inference_1D/plot_inference_1d_resolve.py, tests/test_synthetic_data.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(built_lib):
+    from geobipy_b200 import _lib, api
+    _lib.require_cuda()
+    return api
+
+
+def _resolve(api):
+    t = api.CircularLoop(orientation=list("zzxzzz"), moment=[1, 1, -1, 1, 1, 1], x=[0] * 6, y=[0] * 6, z=[0] * 6)
+    r = api.CircularLoop(orientation=list("zzxzzz"), moment=[1] * 6, x=[7.93, 7.91, 9.03, 7.91, 7.91, 7.89], y=[0] * 6, z=[0] * 6)
+    return api.FdemSystem([380.0, 1776.0, 3345.0, 8171.0, 41020.0, 129550.0], t, r)
+
+
+def test_system_read_and_properties(api, tmp_path):
+    p = tmp_path / "resolve.stm"
+    p.write_text("freq, tor, tmom, tx, ty, tzoff, ror, rmom, rx, ry, rzoff\n"
+                 "380, z, 1, 0, 0, 0, z, 1, 7.93, 0, 0\n1776, z, 1, 0, 0, 0, z, 1, 7.91, 0, 0\n"
+                 "3345, x, -1, 0, 0, 0, x, 1, 9.03, 0, 0\n8171, z, 1, 0, 0, 0, z, 1, 7.91, 0, 0\n"
+                 "41020, z, 1, 0, 0, 0, z, 1, 7.91, 0, 0\n129550, z, 1, 0, 0, 0, z, 1, 7.89, 0, 0\n")
+    s = api.FdemSystem.read(str(p))
+    assert list(s.tensor_id) == [9, 9, 1, 9, 9, 9]
+    assert np.allclose(s.loop_separation, [7.93, 7.91, 9.03, 7.91, 7.91, 7.89])
+    assert s.lamda0.shape == (6, 120) and s.lamda1.shape == (6, 140)
+    assert bytes(s.c_struct) == bytes(_resolve(api).c_struct)
+
+
+def test_datapoint_forward_matches_reference_golden(api, golden_dir):
+    """test_resolve of the reference (tests/test_synthetic_data.py:16-30): the 'glacial' golden CSV."""
+    g = np.load(os.path.join(golden_dir, "resolve_clean.npz"))
+    dp = api.FdemDataPoint(x=0.0, y=0.0, z=float(g["height"]), elevation=0.0, system=_resolve(api))
+    for i in (0, 40, 78):
+        mod = api.Model(api.RectilinearMesh1D(edges=np.r_[0.0, g["zwedge"][i], g["zdeep"][i], np.inf]), g["sigma"][0])
+        dp.forward(mod)
+        assert np.allclose(dp.predictedData, g["data"][0, i])
+        J = dp.sensitivity(mod)
+        assert J.shape == (12, 3)
+        dp.fm_dlogc(mod)
+        assert np.array_equal(dp.sensitivity_matrix, J)
+
+
+def test_datapoint_error_conventions(api):
+    dp = api.FdemDataPoint(z=30.0, system=_resolve(api))
+    with pytest.raises(AssertionError):   # FdemDataPoint.py:541: last edge must be inf
+        dp.forward(api.Model(api.RectilinearMesh1D(edges=[0.0, 5.0, 10.0]), [0.01, 0.1]))
+    with pytest.raises(AssertionError):   # fdem1d.py:29: sensor below the top of the model
+        api.FdemDataPoint(z=-1.0, system=_resolve(api)).forward(api.Model(api.RectilinearMesh1D(edges=[0.0, np.inf]), [0.01]))
+    with pytest.raises(AssertionError):
+        api.FdemDataPoint(z=30.0, system="not a system object".split())
+
+
+def test_inference1d_runs_like_the_reference(api, oracle):
+    """BASELINE configs[0]: one RESOLVE sounding, 3-layer 'glacial' model, 1000 iterations.  As in the
+    reference, 1000 iterations never burn in (> 5000 needed), so the sounding is reported failed while the
+    histograms are still filled."""
+    system = _resolve(api)
+    true = api.Model(api.RectilinearMesh1D(edges=[0.0, 5.0, 7.5, np.inf]), [1e-2, 1e-1, 0.03333333])
+    dp = api.FdemDataPoint(z=30.0, system=system)
+    dp.forward(true)
+    dp.data[:] = dp.predictedData
+    options = dict(n_markov_chains=1000, update_plot_every=5000, solve_parameter=False, solve_gradient=True,
+                   maximum_number_of_layers=30, minimum_depth=0.1, maximum_depth=200.0, minimum_thickness=1.0,
+                   initial_relative_error=0.05, minimum_relative_error=0.001, maximum_relative_error=0.5,
+                   initial_additive_error=5.0, minimum_additive_error=3.0, maximum_additive_error=20.0,
+                   relative_error_proposal_variance=1e-6, additive_error_proposal_variance=1e-6,
+                   probability_of_birth=1 / 6, probability_of_death=1 / 6, probability_of_perturb=1 / 6,
+                   probability_of_no_change=0.5, covariance_scaling=1.0, solve_relative_error=True,
+                   solve_additive_error=True, interactive_plot=False, save_hdf5=True)
+    inf = api.Inference1D(prng=np.random.default_rng(0), precision=64, **options)
+    inf.initialize(dp)
+    failed = inf.infer(None)
+    assert failed and not inf.burned_in and inf.iteration == 1000
+    assert abs(inf.halfspace - 0.03199267) < 1e-7          # the reference's best half-space for this sounding
+    assert inf.hitmap.counts.shape == (250, 440) and inf.hitmap.counts.sum() == 440 * 1000
+    assert inf.n_cells_posterior.counts.sum() == 1000 and inf.data_misfit_v.shape == (2000,)
+    assert 30.0 < inf.acceptance_rate < 90.0                 # reference: 60.9 % on this sounding
+    assert inf.data_misfit < 124.6                           # started from the half-space misfit 124.59
+    med = inf.hitmap.median()
+    assert med.shape == (440,) and np.all(med > 0)
+    assert abs(inf.interface_probability().sum() - 1.0) < 1e-12 or inf.edges_posterior.counts.sum() == 0
+    # the stored predicted data are those of the final model
+    chk = api.FdemDataPoint(z=30.0, system=system)
+    chk.forward(inf.model)
+    assert np.allclose(chk.predictedData, dp.predictedData)
+
+
+def test_infer_batch(api, oracle):
+    from geobipy_b200.synthetic import synthetic_batch
+    system = _resolve(api)
+    b = synthetic_batch(0, 32)
+    from geobipy_b200 import ops
+    clean = ops.fdem_forward(system.c_struct, b["nlayers"], b["sigma"], b["thickness"], b["height"], precision=64)
+    data = clean + b["noise"] * np.sqrt((0.05 * clean) ** 2 + 25.0)
+    r = api.infer_batch(system, data, b["height"], seed=9, n_markov_chains=500, max_iterations=200)
+    assert (r["scalars"][:, 0] == 200).all() and r["hitmap"].shape == (32, 250, 440)
+    # batch composition does not change a sounding's result (stream = (seed, sounding index))
+    r2 = api.infer_batch(system, data[5:9], b["height"][5:9], seed=9, first_index=5, n_markov_chains=500, max_iterations=200)
+    assert np.array_equal(r2["hitmap"], r["hitmap"][5:9]) and np.array_equal(r2["scalars"], r["scalars"][5:9])
