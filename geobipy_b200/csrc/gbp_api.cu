@@ -125,32 +125,27 @@ int launch_fdem(TableCache* tc, int B, int l_stride, const int32_t* nl, const do
     return time_end(st);
 }
 
-template <typename T, int NC>
+template <typename R, typename T, int NC, int WARPS>
 int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
 {
     const size_t tab_bytes = ((size_t)TAB_ROWS * tc->host.dev.tab_stride * sizeof(T) + 127) & ~(size_t)127;
-    const size_t per_warp = sizeof(WarpState<T, NC>);
+    const size_t per_warp = sizeof(WarpState<R, T, NC>);
     int dev = 0, max_smem = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int warps = (int)(((size_t)max_smem - tab_bytes - 1024) / per_warp);
-    if (warps > 16) warps = 16;
-    const char* env = std::getenv("GBP_WARPS_PER_CTA");
-    if (env && std::atoi(env) > 0 && std::atoi(env) < warps) warps = std::atoi(env);
-    if (warps < 1) return fail("not enough shared memory for one chain");
-    const int threads = warps * 32;
-    const size_t smem = tab_bytes + (size_t)warps * per_warp;
-    auto kern = rjmcmc_kernel<T, NC>;
+    const size_t smem = tab_bytes + (size_t)WARPS * per_warp;
+    if (smem + 2048 > (size_t)max_smem) return fail("rjmcmc kernel does not fit in shared memory on this device");
+    auto kern = rjmcmc_kernel<R, T, NC, WARPS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count();
-    const int need = (P.B + warps - 1) / warps;
+    const int need = (P.B + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     ChainParams Q = P;
-    Q.n_warps_total = grid * warps;
+    Q.n_warps_total = grid * WARPS;
     // device-side work counter: chains beyond the first wave are claimed dynamically
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
     if (time_begin(st)) return 1;
-    kern<<<grid, threads, smem, st>>>(tc->host.dev, tab_ptr<T>(tc), Q);
+    kern<<<grid, WARPS * 32, smem, st>>>(tc->host.dev, tab_ptr<T>(tc), Q);
     g_launches++;
     CK(cudaGetLastError());
     return time_end(st);
@@ -339,10 +334,11 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
     if (get_counter(&P.work_counter)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     const bool small = P.C <= 12;
+    // fp32: 28 chains per SM (148 x 28 = 4144 resident chains: BASELINE configs[1] is one wave); fp64: 8 per SM
     if (precision == GBP_PRECISION_F32)
-        return small ? launch_chain<float, 12>(tc, P, st) : launch_chain<float, GBP_MAXC>(tc, P, st);
+        return small ? launch_chain<float, float, 12, 28>(tc, P, st) : launch_chain<float, float, GBP_MAXC, 16>(tc, P, st);
     if (precision == GBP_PRECISION_F64)
-        return small ? launch_chain<double, 12>(tc, P, st) : launch_chain<double, GBP_MAXC>(tc, P, st);
+        return small ? launch_chain<double, double, 12, 8>(tc, P, st) : launch_chain<double, double, GBP_MAXC, 8>(tc, P, st);
     return fail("precision must be 32 or 64");
 }
 

@@ -25,6 +25,12 @@ template <> struct rt<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
         return r;
     }
+    static __device__ __forceinline__ float log(float x)
+    {
+        float r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r * 0.6931471805599453f;
+    }
     static __device__ __forceinline__ float rcp(float x)
     {
         float r;
@@ -47,6 +53,7 @@ __device__ __noinline__ void dsincos_(double x, double* s, double* c) { ::sincos
 template <> struct rt<double> {
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double exp(double x) { return dexp_(x); }
+    static __device__ __forceinline__ double log(double x) { return dlog_(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ void sincos(double x, double* s, double* c) { dsincos_(x, s, c); }
 };
@@ -118,36 +125,44 @@ __device__ __noinline__ void philox_block(const Rng& g, unsigned long long block
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-// one block -> two 53-bit uniforms in [0,1)
-__device__ __forceinline__ void uniforms_at(const Rng& g, unsigned long long block, double* ua, double* ub)
+// one block -> two uniforms in [0,1): 53-bit for double, 24-bit for float
+template <typename R> __device__ __forceinline__ void uniforms_at(const Rng& g, unsigned long long block, R* ua, R* ub);
+template <> __device__ __forceinline__ void uniforms_at<double>(const Rng& g, unsigned long long block, double* ua, double* ub)
 {
     uint32_t x[4];
     philox_block(g, block, x);
     *ua = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6)) * (1.0 / 9007199254740992.0);
     *ub = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6)) * (1.0 / 9007199254740992.0);
 }
-__device__ __forceinline__ double rng_uniform(Rng& g)
+template <> __device__ __forceinline__ void uniforms_at<float>(const Rng& g, unsigned long long block, float* ua, float* ub)
 {
-    double a, b;
-    uniforms_at(g, g.block, &a, &b);
+    uint32_t x[4];
+    philox_block(g, block, x);
+    *ua = (float)(x[0] >> 8) * (1.0f / 16777216.0f);
+    *ub = (float)(x[2] >> 8) * (1.0f / 16777216.0f);
+}
+template <typename R> __device__ __forceinline__ R rng_uniform(Rng& g)
+{
+    R a, b;
+    uniforms_at<R>(g, g.block, &a, &b);
     g.block++;
     return a;
 }
 // Box-Muller pair of the block at an explicit counter
-__device__ __noinline__ void normal2_at(const Rng& g, unsigned long long block, double* z0, double* z1)
+template <typename R> __device__ __noinline__ void normal2_at(const Rng& g, unsigned long long block, R* z0, R* z1)
 {
-    double a, b;
-    uniforms_at(g, block, &a, &b);
-    double r = sqrt(-2.0 * dlog_(1.0 - a));
-    double s, c;
-    dsincos_(6.283185307179586476925286766559 * b, &s, &c);
+    R a, b;
+    uniforms_at<R>(g, block, &a, &b);
+    const R r = rt<R>::sqrt(R(-2) * rt<R>::log(R(1) - a));
+    R s, c;
+    rt<R>::sincos(R(6.283185307179586476925286766559) * b, &s, &c);
     *z0 = r * c;
     *z1 = r * s;
 }
-__device__ __forceinline__ double rng_normal(Rng& g)
+template <typename R> __device__ __forceinline__ R rng_normal(Rng& g)
 {
-    double z0, z1;
-    normal2_at(g, g.block, &z0, &z1);
+    R z0, z1;
+    normal2_at<R>(g, g.block, &z0, &z1);
     g.block++;
     return z0;
 }
