@@ -139,11 +139,16 @@ template <typename R> __device__ __forceinline__ R warp_min(R v)
     return v;
 }
 
+// tell the compiler that the chain state and the constants live in shared memory (LDS/STS, not generic)
+#define GBP_SHARED_STATE              \
+    __builtin_assume(__isShared(&w)); \
+    __builtin_assume(__isShared(&K))
+
 template <typename R, typename T, int NC> struct Chain {
     typedef WarpState<R, T, NC> WS;
     WS& w;
     const Consts<R>& K;
-    const SysDev& S;
+    const SysShared<T>& S;
     const T* tab;
     const ChainParams& P;
     const int lane;
@@ -163,7 +168,7 @@ template <typename R, typename T, int NC> struct Chain {
     int burned_in, n_zero, n_resets, limiters, n_active, acc_win, dwell, best_k;
     R best_rel, best_add;
 
-    __device__ Chain(WS& w_, const Consts<R>& K_, const SysDev& S_, const T* tab_, const ChainParams& P_)
+    __device__ Chain(WS& w_, const Consts<R>& K_, const SysShared<T>& S_, const T* tab_, const ChainParams& P_)
         : w(w_), K(K_), S(S_), tab(tab_), P(P_), lane(threadIdx.x & 31), C(P_.C)
     {
     }
@@ -172,24 +177,22 @@ template <typename R, typename T, int NC> struct Chain {
     // J == nullptr: forward only.  Otherwise forward + Jacobian in one pass (FdemDataPoint.fm_dlogc :535)
     __device__ __noinline__ void forward(int kk, const R* sig, const R* edges, T* pred, T* J)
     {
+        GBP_SHARED_STATE;
         if (lane < kk) {
             w.msig[lane] = (T)sig[lane];
             w.mthk[lane] = (T)(edges[lane + 1] - edges[lane]);
         }
         __syncwarp();
         n_forward++;
-        if (J) {
-            n_sens++;
-            fdem_eval<T, true>(S, tab, alt, kk, w.msig, w.mthk, pred, J);
-        } else {
-            fdem_eval<T, false>(S, tab, alt, kk, w.msig, w.mthk, pred, nullptr);
-        }
+        if (J) n_sens++;
+        fdem_eval<T>(S, tab, alt, kk, w.msig, w.mthk, pred, J, J != nullptr);
     }
 
     // ------------------------------------------------------------ data terms
     // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
     __device__ __noinline__ void set_ivar(R r, R a)
     {
+        GBP_SHARED_STATE;
         if (lane < C) {
             R d = w.data[lane];
             R s = r * d;
@@ -200,6 +203,7 @@ template <typename R, typename T, int NC> struct Chain {
     // misfit (DataPoint.py:502-525) and Gaussian log-likelihood (MvNormalDistribution.py:209-216)
     __device__ __noinline__ void misfit_likelihood(const T* pred, R* mis, R* like)
     {
+        GBP_SHARED_STATE;
         R q = R(0), ld = R(0);
         if (lane < C) {
             R iv = w.ivar[lane];
@@ -225,6 +229,7 @@ template <typename R, typename T, int NC> struct Chain {
     // Model.probability :533-575 (value_bounds = None); ls = ln sigma, lnh = ln thickness
     __device__ __noinline__ R model_probability(int kk, const R* ls, const R* lnh)
     {
+        GBP_SHARED_STATE;
         const gbp_options& o = P.opt;
         R p = (kk >= 1 && kk <= o.max_layers) ? K.lp_k : (R)-INFINITY;
         if (o.solve_parameter) {
@@ -254,6 +259,7 @@ template <typename R, typename T, int NC> struct Chain {
     // lnh[i] = ln(thickness_i), t2[i] = 1/(g^2 (c2c_i (k-1))^2)  (RectilinearMesh1D.gradient_operator :747-786)
     __device__ __noinline__ void mesh_setup(int kk, MeshBuf<R>& m)
     {
+        GBP_SHARED_STATE;
         if (kk >= 2 && lane < kk - 1) {
             const R* e = m.edges;
             R x0 = e[lane + 1] - e[lane];
@@ -283,6 +289,7 @@ template <typename R, typename T, int NC> struct Chain {
     // gradient of lane i: Wm'Wm (ln s - ln ref) + J' Wd'Wd (pred - d)   (Model.local_gradient :347-357)
     __device__ __noinline__ R gradient_lane(int kk, const R* t2, const R* ls, const T* J, const T* pred)
     {
+        GBP_SHARED_STATE;
         R g = R(0);
         if (lane < kk) {
             g = prior_op(kk, t2, lane, lane) * (ls[lane] - ln_ref);
@@ -296,6 +303,7 @@ template <typename R, typename T, int NC> struct Chain {
     // A = Wm'Wm + J' Wd'Wd J (Model.local_precision :250-272), packed lower triangle
     __device__ __noinline__ void assemble(int kk, const R* t2, const T* J)
     {
+        GBP_SHARED_STATE;
 #pragma unroll 1
         for (int i = 0; i < kk; ++i) {
             if (lane <= i) {
@@ -310,6 +318,7 @@ template <typename R, typename T, int NC> struct Chain {
     // in-place packed Cholesky, lane = row.  Returns false if the matrix is not positive definite.
     __device__ __noinline__ bool cholesky(int kk)
     {
+        GBP_SHARED_STATE;
         bool ok = true;
 #pragma unroll 1
         for (int j = 0; j < kk; ++j) {
@@ -331,6 +340,7 @@ template <typename R, typename T, int NC> struct Chain {
     // lane i holds b_i; returns lane i of L^-1 b
     __device__ __noinline__ R solve_L(int kk, R x)
     {
+        GBP_SHARED_STATE;
 #pragma unroll 1
         for (int j = 0; j < kk; ++j) {
             const R yj = __shfl_sync(FULL, x, j) / w.A[pk(j, j)];
@@ -341,6 +351,7 @@ template <typename R, typename T, int NC> struct Chain {
     }
     __device__ __noinline__ R solve_LT(int kk, R x)
     {
+        GBP_SHARED_STATE;
 #pragma unroll 1
         for (int j = kk - 1; j >= 0; --j) {
             const R xj = __shfl_sync(FULL, x, j) / w.A[pk(j, j)];
@@ -352,6 +363,7 @@ template <typename R, typename T, int NC> struct Chain {
     // v' A v = |L' v|^2 with v_i held by lane i
     __device__ __noinline__ R quad(int kk, R v)
     {
+        GBP_SHARED_STATE;
         if (lane < kk) w.vec[lane] = v;
         __syncwarp();
         R s = R(0);
@@ -368,6 +380,7 @@ template <typename R, typename T, int NC> struct Chain {
     // buffers (mesh[mcur^1], val[vcur^1], ls_r) and returns the action; for ACT_NONE only ls_r is filled.
     __device__ __noinline__ int perturb_structure(int* knew)
     {
+        GBP_SHARED_STATE;
         const MeshBuf<R>& m0 = w.mesh[mcur];
         const ValBuf<R>& v0 = w.val[vcur];
         MeshBuf<R>& m1 = w.mesh[mcur ^ 1];
@@ -490,6 +503,7 @@ template <typename R, typename T, int NC> struct Chain {
     // add `count` visits of the CURRENT model / errors to every histogram
     __device__ __noinline__ void flush(int count)
     {
+        GBP_SHARED_STATE;
         if (count <= 0) return;
         const gbp_chain_buffers& o = P.out;
         const int nd = P.n_depth, nsb = P.opt.n_sigma_bins, neb = P.opt.n_err_bins;
@@ -664,6 +678,7 @@ template <typename R, typename T, int NC> struct Chain {
     // returns true if the chain failed (Gauss-Newton matrix not positive definite)
     __device__ __noinline__ bool step(bool* accepted_out)
     {
+        GBP_SHARED_STATE;
         const gbp_options& o = P.opt;
         *accepted_out = false;
         int kn;
@@ -913,15 +928,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ Consts<R> consts;
+    __shared__ SysShared<T> sys_s;
     T* tab = reinterpret_cast<T*>(smem);
     const uint32_t tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
-    if (threadIdx.x == 0) make_consts<R>(P.opt, P.n_depth, consts);
+    if (threadIdx.x == 0) {
+        make_consts<R>(P.opt, P.n_depth, consts);
+        fill_sys_shared<T>(S, sys_s);
+    }
     tma_stage(tab, g_tab, tab_bytes, &bar);
     __syncthreads();
     const uint32_t tab_pad = (tab_bytes + 127u) & ~127u;
     const int warp = threadIdx.x >> 5;
     WarpState<R, T, NC>* ws = reinterpret_cast<WarpState<R, T, NC>*>(smem + tab_pad) + warp;
-    Chain<R, T, NC> ch(*ws, consts, S, tab, P);
+    Chain<R, T, NC> ch(*ws, consts, sys_s, tab, P);
     // persistent: the first wave is assigned statically, later chains come from a device-side counter
     int c = blockIdx.x * WARPS + warp;
     const int lane = threadIdx.x & 31;
@@ -944,9 +963,12 @@ __global__ void __launch_bounds__(256) fdem_kernel(const __grid_constant__ SysDe
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
+    __shared__ SysShared<T> sys_s;
     T* tab = reinterpret_cast<T*>(smem);
     const uint32_t tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
+    if (threadIdx.x == 0) fill_sys_shared<T>(S, sys_s);
     tma_stage(tab, g_tab, tab_bytes, &bar);
+    __syncthreads();
     const uint32_t tab_pad = (tab_bytes + 127u) & ~127u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int C = 2 * S.n_freq;
@@ -964,7 +986,7 @@ __global__ void __launch_bounds__(256) fdem_kernel(const __grid_constant__ SysDe
             mthk[lane] = (T)thickness[(size_t)b * l_stride + lane];
         }
         __syncwarp();
-        fdem_eval<T, SENS>(S, tab, (T)altitude[b], L, msig, mthk, pred, SENS ? J : nullptr);
+        fdem_eval<T>(sys_s, tab, (T)altitude[b], L, msig, mthk, pred, SENS ? J : nullptr, SENS);
         if (lane < C) out[(size_t)b * C + lane] = (double)pred[lane];
         if (SENS) {
 #pragma unroll 1

@@ -70,18 +70,44 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
     }
 }
 
-// ---------------------------------------------------------------- the operator
-// tab: shared memory, TAB_ROWS rows of tab_stride values of T.
-// msig/mthk: shared memory, per-warp model (conductivity, thickness) in T; mthk[L-1] unused.
-// pred: [2F] (real then imag).  J: [2F][KS] (only if SENS).  All lanes of the warp must call.
-template <typename T, bool SENS>
-__device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ tab, T alt, int L,
-                                          const T* __restrict__ msig, const T* __restrict__ mthk,
-                                          T* __restrict__ pred, T* __restrict__ J)
+// Per-CTA copy of the per-frequency constants in the arithmetic type T (shared memory).
+template <typename T> struct SysShared {
+    int n_freq, n_seg, tab_stride, pad;
+    Seg seg[MAX_SEG];
+    T omu[GBP_MAXF], k2re[GBP_MAXF], hd0[GBP_MAXF];
+};
+template <typename T> __device__ __forceinline__ void fill_sys_shared(const SysDev& S, SysShared<T>& q)
 {
+    q.n_freq = S.n_freq;
+    q.n_seg = S.n_seg;
+    q.tab_stride = S.tab_stride;
+    for (int i = 0; i < MAX_SEG; ++i) q.seg[i] = S.seg[i];
+    for (int i = 0; i < GBP_MAXF; ++i) {
+        q.omu[i] = (T)S.omu[i];
+        q.k2re[i] = (T)S.k2re[i];
+        q.hd0[i] = (T)S.hd0[i];
+    }
+}
+
+// ---------------------------------------------------------------- the operator
+// Q, tab, msig, mthk, pred, J all live in SHARED memory (asserted to the compiler so that the loads are
+// LDS, not generic).  tab: TAB_ROWS rows of tab_stride values of T.  msig/mthk: per-warp model
+// (conductivity, thickness); mthk[L-1] unused.  pred: [2F] (real then imag).  J: [2F][KS], written only
+// if sens.  One function body serves forward-only and forward+Jacobian calls (`sens` is warp-uniform) so
+// that all warps of an SM share the same instruction-cache lines.  All lanes of the warp must call.
+template <typename T>
+__device__ __noinline__ void fdem_eval(const SysShared<T>& Q, const T* __restrict__ tab, T alt, int L,
+                                       const T* __restrict__ msig, const T* __restrict__ mthk, T* __restrict__ pred,
+                                       T* __restrict__ J, const bool sens)
+{
+    __builtin_assume(__isShared(&Q));
+    __builtin_assume(__isShared(tab));
+    __builtin_assume(__isShared(msig));
+    __builtin_assume(__isShared(mthk));
+    __builtin_assume(__isShared(pred));
     const int lane = threadIdx.x & 31;
-    const int F = S.n_freq;
-    const int ts = S.tab_stride;
+    const int F = Q.n_freq;
+    const int ts = Q.tab_stride;
     const T* t_lam = tab;
     const T* t_u0r = tab + ts;
     const T* t_u0i = tab + 2 * ts;
@@ -90,28 +116,28 @@ __device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ ta
     const T* t_cr = tab + 5 * ts;
     const T* t_ci = tab + 6 * ts;
 
-    // thread-local scratch of the chain-rule pass (SENS only): D_k = dy_k/dy_{k+1}, l_k = dy_k/dln(sigma_k)
-    T Dr[SENS ? KS : 1], Di[SENS ? KS : 1], lr[SENS ? KS : 1], li[SENS ? KS : 1];
-    T jr[SENS ? KS : 1], ji[SENS ? KS : 1];
+    // thread-local scratch of the chain-rule pass (sens only): D_k = dy_k/dy_{k+1}, l_k = dy_k/dln(sigma_k)
+    T Dr[KS], Di[KS], lr[KS], li[KS];
+    T jr[KS], ji[KS];
 
     int seg = 0;
-    #pragma unroll 1
+#pragma unroll 1
     for (int f = 0; f < F; ++f) {
-        const T omu = (T)S.omu[f];
-        const T k2 = (T)S.k2re[f];
-        const T hd = (T)S.hd0[f] - T(2) * alt;
+        const T omu = Q.omu[f];
+        const T k2 = Q.k2re[f];
+        const T hd = Q.hd0[f] - T(2) * alt;
         cx<T> acc = {T(0), T(0)};
-        if (SENS) {
-            #pragma unroll 1
+        if (sens) {
+#pragma unroll 1
             for (int k = 0; k < L; ++k) {
                 jr[k] = T(0);
                 ji[k] = T(0);
             }
         }
-        #pragma unroll 1
-        for (; seg < S.n_seg && S.seg[seg].freq == f; ++seg) {
-            const int s0 = S.seg[seg].start, cnt = S.seg[seg].count;
-            #pragma unroll 1
+#pragma unroll 1
+        for (; seg < Q.n_seg && Q.seg[seg].freq == f; ++seg) {
+            const int s0 = Q.seg[seg].start, cnt = Q.seg[seg].count;
+#pragma unroll 1
             for (int j = lane; j < cnt; j += 32) {
                 const int i = s0 + j;
                 const T lam = t_lam[i];
@@ -120,20 +146,20 @@ __device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ ta
                 T b = omu * msig[L - 1];
                 cx<T> u = csqrt_q1<T>(a, b);
                 cx<T> y = u;
-                if (SENS) {  // i*b/(2u)
+                if (sens) {  // i*b/(2u)
                     cx<T> iu = cinv(u);
                     lr[L - 1] = T(-0.5) * b * iu.im;
                     li[L - 1] = T(0.5) * b * iu.re;
                 }
-                #pragma unroll 1
+#pragma unroll 1
                 for (int k = L - 2; k >= 0; --k) {
                     b = omu * msig[k];
                     const T t = mthk[k];
                     u = csqrt_q1<T>(a, b);
-                    // tanh(u t) = (1 - e)/(1 + e), e = exp(-2ut), Re(u) > 0 always (cTanh first branch)
-                    // |Im(2ut)| <= Re(2ut); beyond Re(2ut) = 60 the term e^-60 is below fp64 round-off
-                    // of tanh = 1: clamp so that the sin/cos argument stays small (t may be huge)
-                    // (then e is set to exactly 0, as exp() underflows to in the reference)
+                    // tanh(u t) = (1 - e)/(1 + e), e = exp(-2ut), Re(u) > 0 always (cTanh first branch).
+                    // |Im(2ut)| <= Re(2ut); beyond Re(2ut) = 60 the term e^-60 is below fp64 round-off of
+                    // tanh = 1: clamp so that the sin/cos argument stays small (t may be huge), and set e to
+                    // exactly 0 there, as exp() underflows to in the reference
                     const T two_t = T(2) * t;
                     const T sc = fmin(two_t, T(60) * rt<T>::rcp(u.re));
                     cx<T> e = cexp_<T>(mk<T>(-sc * u.re, -sc * u.im));
@@ -142,7 +168,7 @@ __device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ ta
                     cx<T> den = u + y * th;
                     cx<T> num = y + u * th;
                     cx<T> inv = cinv(den);
-                    if (SENS) {
+                    if (sens) {
                         cx<T> u2 = mk<T>(a, b);
                         cx<T> th2 = th * th;
                         cx<T> inv2 = inv * inv;
@@ -165,9 +191,9 @@ __device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ ta
                 const cx<T> rte = (u0 - y) * is;
                 const cx<T> K = mk<T>(t_cr[i], t_ci[i]) * cexp_<T>(mk<T>(t_er[i] * hd, t_ei[i] * hd));
                 acc = acc + rte * K;
-                if (SENS) {
+                if (sens) {
                     cx<T> P = (u0 * is * is) * T(-2) * K;  // d rTE/dy1 * K
-                    #pragma unroll 1
+#pragma unroll 1
                     for (int k = 0; k < L; ++k) {
                         cx<T> v = P * mk<T>(lr[k], li[k]);
                         jr[k] += v.re;
@@ -182,8 +208,8 @@ __device__ __noinline__ void fdem_eval(const SysDev& S, const T* __restrict__ ta
             pred[f] = sr;
             pred[F + f] = si;
         }
-        if (SENS) {
-            #pragma unroll 1
+        if (sens) {
+#pragma unroll 1
             for (int k = 0; k < L; ++k) {
                 const T a = warp_sum(jr[k]), b = warp_sum(ji[k]);
                 if (lane == 0) {
