@@ -21,8 +21,11 @@
 //  * R = arithmetic type of the sampler.  R = double: trajectory twin of the CPU oracle (validation).
 //    R = float: production path (forward/Jacobian AND statistics in fp32, MUFU log/exp); counters and
 //    histograms are integers in both.
-//  * the code is split into one non-inlined function per phase so that the kernel stays small: the first
-//    version (everything inlined, 532 KB of SASS) was bound by instruction-cache misses.
+//  * instruction footprint is a first-class concern (ncu: the first version, 532 KB of SASS, and every
+//    later one were bound by instruction fetch, `stall_no_instruction`): helpers that are called from
+//    several places are single non-inlined copies taking shared-memory pointers; the once-per-iteration
+//    control code is inlined into the kernel so that its state stays in registers and the options come
+//    from the constant bank; cold per-chain counters live in shared memory.
 #pragma once
 #include "gbp_fdem.cuh"
 
@@ -30,6 +33,11 @@ namespace gbp {
 
 constexpr int NPACK = GBP_MAXL * (GBP_MAXL + 1) / 2;
 enum { ACT_BIRTH = 0, ACT_DEATH = 1, ACT_MOVE = 2, ACT_NONE = 3 };
+// cold per-chain integers kept in shared memory
+enum { CT_N_ACCEPT = 0, CT_N_FWD, CT_N_SENS, CT_ACT0, CT_ACT1, CT_ACT2, CT_ACT3, CT_BEST_K, CT_BEST_ITER, CT_BURN_ITER,
+       CT_N_ZERO, CT_N_RESETS, CT_LIMITERS, CT_ACC_WIN, CT_TO_PLOT, CT_N = 16 };
+enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_N = 4 };
+enum { OP_HITMAP = 0, OP_EDGES, OP_NCELLS, OP_REL, OP_ADD, OP_MISFIT, OP_ACCEPT, OP_N = 8 };
 
 template <typename R> struct MeshBuf {
     R edges[GBP_MAXL + 2];  // edges[0] = 0, edges[k] = inf
@@ -52,6 +60,9 @@ template <typename R, typename T, int NC> struct __align__(16) WarpState {
     T pred[2][NC];
     T msig[KS], mthk[KS];
     int sbin[GBP_MAXL + 2];
+    int ctr[CT_N];          // cold counters
+    R bestv[BV_N];          // best posterior / errors
+    void* outp[OP_N];       // this chain's output rows
 };
 
 // Option-derived constants, computed once per CTA in fp64 and shared by its warps.
@@ -62,10 +73,12 @@ template <typename R> struct Consts {
     R lp_k;                                   // -ln(kmax - 1)
     R c_grad, c_val;                          // per-dimension constants of the gradient / value prior
     R half_log2pi;
-    R rel_lnmin, rel_lnmax, rel_sd, rel_lp, rel_ln0;
-    R add_lnmin, add_lnmax, add_sd, add_lp, add_ln0;
+    R rel_lnmin, rel_lnmax, rel_sd, rel_lp, rel_ln0, rel0;
+    R add_lnmin, add_lnmax, add_sd, add_lp, add_ln0, add0;
     R sig_halfspan, sig_dx, rel_dx, add_dx, depth_step, depth_max;
     R ln_half, ln_3half;
+    int kmax, n_depth, n_sig, n_err, C, solve_par, solve_grad, solve_rel, solve_add;
+    int n_chains, upe, burn_min, reset_limit;
 };
 
 struct ChainParams {
@@ -79,7 +92,7 @@ struct ChainParams {
     int* work_counter;
 };
 
-template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, Consts<R>& c)
+template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c)
 {
     c.cum0 = (R)o.p_birth;
     c.cum1 = (R)(o.p_birth + o.p_death);
@@ -103,11 +116,13 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
     c.rel_sd = (R)::sqrt(o.rel_prop_var);
     c.rel_lp = (R)(-dlog_(dlog_(o.rel_max) - dlog_(o.rel_min)));
     c.rel_ln0 = (R)dlog_(o.rel_init);
+    c.rel0 = (R)o.rel_init;
     c.add_lnmin = (R)dlog_(o.add_min);
     c.add_lnmax = (R)dlog_(o.add_max);
     c.add_sd = (R)::sqrt(o.add_prop_var);
     c.add_lp = (R)(-dlog_(dlog_(o.add_max) - dlog_(o.add_min)));
     c.add_ln0 = (R)dlog_(o.add_init);
+    c.add0 = (R)o.add_init;
     c.sig_halfspan = (R)(o.sigma_bins_nstd * s);
     c.sig_dx = (R)(2.0 * o.sigma_bins_nstd * s / (double)o.n_sigma_bins);
     c.rel_dx = (R)((dlog_(o.rel_max) - dlog_(o.rel_min)) / (double)o.n_err_bins);
@@ -116,9 +131,25 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
     c.depth_max = (R)((double)n_depth * 0.5 * o.min_width);
     c.ln_half = (R)dlog_(0.5);
     c.ln_3half = (R)dlog_(1.5);
+    c.kmax = o.max_layers;
+    c.n_depth = n_depth;
+    c.n_sig = o.n_sigma_bins;
+    c.n_err = o.n_err_bins;
+    c.C = C;
+    c.solve_par = o.solve_parameter;
+    c.solve_grad = o.solve_gradient;
+    c.solve_rel = o.solve_relative_error;
+    c.solve_add = o.solve_additive_error;
+    c.n_chains = o.n_markov_chains;
+    c.upe = o.update_plot_every;
+    c.burn_min = o.burn_in_min_iter;
+    c.reset_limit = o.reset_limit;
 }
 
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+#define GBP_SHARED(p) __builtin_assume(__isShared(p))
 
 // searchsorted(edges, v, 'right') - 1 clipped, uniform edges lo + i*dx
 template <typename R> __device__ __noinline__ int uniform_bin(R v, R lo, R dx, int n)
@@ -139,785 +170,885 @@ template <typename R> __device__ __forceinline__ R warp_min(R v)
     return v;
 }
 
-// tell the compiler that the chain state and the constants live in shared memory (LDS/STS, not generic)
-#define GBP_SHARED_STATE              \
-    __builtin_assume(__isShared(&w)); \
-    __builtin_assume(__isShared(&K))
-
-template <typename R, typename T, int NC> struct Chain {
-    typedef WarpState<R, T, NC> WS;
-    WS& w;
-    const Consts<R>& K;
-    const SysShared<T>& S;
-    const T* tab;
-    const ChainParams& P;
-    const int lane;
-    const int C;
-    // ---- per-chain scalars
-    Rng rng;
-    int chain;
-    T alt;
-    int k;                       // layers of the current model
-    int mcur, vcur, jcur, pcur;  // which buffer holds the current mesh / values / Jacobian / predicted data
-    R ln_rel, ln_add, rel, add, ln_ref;
-    double sigma_ref;
-    R misfit, prior, likelihood, posterior, best_posterior;
-    R sig_lo;                    // lower edge of the conductivity bins (ln)
-    int iteration, burned_in_iter, best_iter, n_accept, n_forward, n_sens;
-    int n_act[4];
-    int burned_in, n_zero, n_resets, limiters, n_active, acc_win, dwell, best_k;
-    R best_rel, best_add;
-
-    __device__ Chain(WS& w_, const Consts<R>& K_, const SysShared<T>& S_, const T* tab_, const ChainParams& P_)
-        : w(w_), K(K_), S(S_), tab(tab_), P(P_), lane(threadIdx.x & 31), C(P_.C)
-    {
+// ================================================================ shared, non-inlined helpers
+// J == nullptr: forward only.  Otherwise forward + Jacobian in one pass (FdemDataPoint.fm_dlogc :535)
+template <typename R, typename T, int NC>
+__device__ __noinline__ void ch_forward(WarpState<R, T, NC>* w, const SysShared<T>* S, const T* tab, T alt, int kk,
+                                        const R* sig, const R* edges, T* pred, T* J)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(sig);
+    GBP_SHARED(edges);
+    const int lane = lane_id();
+    if (lane < kk) {
+        w->msig[lane] = (T)sig[lane];
+        w->mthk[lane] = (T)(edges[lane + 1] - edges[lane]);
     }
+    if (lane == 0) {
+        w->ctr[CT_N_FWD]++;
+        if (J) w->ctr[CT_N_SENS]++;
+    }
+    __syncwarp();
+    fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
+}
 
-    // ------------------------------------------------------------ forward wrapper
-    // J == nullptr: forward only.  Otherwise forward + Jacobian in one pass (FdemDataPoint.fm_dlogc :535)
-    __device__ __noinline__ void forward(int kk, const R* sig, const R* edges, T* pred, T* J)
-    {
-        GBP_SHARED_STATE;
+// DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
+template <typename R, typename T, int NC> __device__ __noinline__ void ch_set_ivar(WarpState<R, T, NC>* w, int C, R r, R a)
+{
+    GBP_SHARED(w);
+    const int lane = lane_id();
+    if (lane < C) {
+        R d = w->data[lane];
+        R s = r * d;
+        w->ivar[lane] = (d > R(0)) ? R(1) / (s * s + a * a) : R(0);
+    }
+    __syncwarp();
+}
+
+// misfit (DataPoint.py:502-525) and Gaussian log-likelihood (MvNormalDistribution.py:209-216)
+template <typename R, typename T, int NC>
+__device__ __noinline__ pair_t<R> ch_misfit_like(WarpState<R, T, NC>* w, int C, R n_active_half_log2pi, const T* pred)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(pred);
+    const int lane = lane_id();
+    R q = R(0), ld = R(0);
+    if (lane < C) {
+        R iv = w->ivar[lane];
+        if (iv > R(0)) {
+            R r = (R)pred[lane] - w->data[lane];
+            q = r * r * iv;
+            ld = -rt<R>::log(iv);
+        }
+    }
+    q = warp_sum(q);
+    ld = warp_sum(ld);
+    return pair_t<R>{q, -n_active_half_log2pi - R(0.5) * ld - R(0.5) * q};
+}
+
+// Model.probability :533-575 (value_bounds = None); ls = ln sigma, lnh = ln thickness
+template <typename R>
+__device__ __noinline__ R ch_model_prob(const Consts<R>* K, int kk, const R* ls, const R* lnh, R ln_ref)
+{
+    GBP_SHARED(K);
+    GBP_SHARED(ls);
+    GBP_SHARED(lnh);
+    const int lane = lane_id();
+    R p = (kk >= 1 && kk <= K->kmax) ? K->lp_k : (R)-INFINITY;
+    if (K->solve_par) {
+        R q = R(0);
         if (lane < kk) {
-            w.msig[lane] = (T)sig[lane];
-            w.mthk[lane] = (T)(edges[lane + 1] - edges[lane]);
+            R d = ls[lane] - ln_ref;
+            q = d * d * K->inv_s2;
         }
-        __syncwarp();
-        n_forward++;
-        if (J) n_sens++;
-        fdem_eval<T>(S, tab, alt, kk, w.msig, w.mthk, pred, J, J != nullptr);
+        p += (R)kk * K->c_val - R(0.5) * warp_sum(q);
     }
-
-    // ------------------------------------------------------------ data terms
-    // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
-    __device__ __noinline__ void set_ivar(R r, R a)
-    {
-        GBP_SHARED_STATE;
-        if (lane < C) {
-            R d = w.data[lane];
-            R s = r * d;
-            w.ivar[lane] = (d > R(0)) ? R(1) / (s * s + a * a) : R(0);
-        }
-        __syncwarp();
-    }
-    // misfit (DataPoint.py:502-525) and Gaussian log-likelihood (MvNormalDistribution.py:209-216)
-    __device__ __noinline__ void misfit_likelihood(const T* pred, R* mis, R* like)
-    {
-        GBP_SHARED_STATE;
-        R q = R(0), ld = R(0);
-        if (lane < C) {
-            R iv = w.ivar[lane];
-            if (iv > R(0)) {
-                R r = (R)pred[lane] - w.data[lane];
-                q = r * r * iv;
-                ld = -rt<R>::log(iv);
-            }
-        }
-        q = warp_sum(q);
-        ld = warp_sum(ld);
-        *mis = q;
-        *like = -(R)n_active * K.half_log2pi - R(0.5) * ld - R(0.5) * q;
-    }
-    // Uniform(log=True) priors on the errors (DataPoint.probability :351-395), arguments in ln space
-    __device__ __forceinline__ R datapoint_probability(R lr, R la)
-    {
-        R p = R(0);
-        if (P.opt.solve_relative_error) p += (lr < K.rel_lnmin || lr > K.rel_lnmax) ? (R)-INFINITY : K.rel_lp;
-        if (P.opt.solve_additive_error) p += (la < K.add_lnmin || la > K.add_lnmax) ? (R)-INFINITY : K.add_lp;
-        return p;
-    }
-    // Model.probability :533-575 (value_bounds = None); ls = ln sigma, lnh = ln thickness
-    __device__ __noinline__ R model_probability(int kk, const R* ls, const R* lnh)
-    {
-        GBP_SHARED_STATE;
-        const gbp_options& o = P.opt;
-        R p = (kk >= 1 && kk <= o.max_layers) ? K.lp_k : (R)-INFINITY;
-        if (o.solve_parameter) {
+    if (K->solve_grad) {
+        if (kk == 1) {
+            p += K->c_grad;  // Model.py:230-232: a virtual 2-layer model with equal values
+        } else {
             R q = R(0);
-            if (lane < kk) {
-                R d = ls[lane] - ln_ref;
-                q = d * d * K.inv_s2;
+            if (lane < kk - 1) {
+                R g = (ls[lane + 1] - ls[lane]) / lnh[lane];
+                q = g * g * K->inv_g2;
             }
-            p += (R)kk * K.c_val - R(0.5) * warp_sum(q);
+            p += (R)(kk - 1) * K->c_grad - R(0.5) * warp_sum(q);
         }
-        if (o.solve_gradient) {
-            if (kk == 1) {
-                p += K.c_grad;  // Model.py:230-232: a virtual 2-layer model with equal values
-            } else {
-                R q = R(0);
-                if (lane < kk - 1) {
-                    R g = (ls[lane + 1] - ls[lane]) / lnh[lane];
-                    q = g * g * K.inv_g2;
-                }
-                p += (R)(kk - 1) * K.c_grad - R(0.5) * warp_sum(q);
-            }
-        }
-        return p;
     }
+    return p;
+}
 
-    // ------------------------------------------------------------ mesh-derived quantities
-    // lnh[i] = ln(thickness_i), t2[i] = 1/(g^2 (c2c_i (k-1))^2)  (RectilinearMesh1D.gradient_operator :747-786)
-    __device__ __noinline__ void mesh_setup(int kk, MeshBuf<R>& m)
-    {
-        GBP_SHARED_STATE;
-        if (kk >= 2 && lane < kk - 1) {
-            const R* e = m.edges;
-            R x0 = e[lane + 1] - e[lane];
-            R x1;
-            if (lane + 1 < kk - 1) x1 = e[lane + 2] - e[lane + 1];
-            else x1 = (kk == 2) ? x0 : (e[kk - 1] - e[kk - 2]) + (e[kk - 1] - e[0]);
-            R c2c = R(0.5) * (x0 + x1);
-            R t = R(1) / (c2c * (R)(kk - 1));
-            m.t2[lane] = t * t * K.inv_g2;
-            m.lnh[lane] = rt<R>::log(x0);
-        }
-        __syncwarp();
+// lnh[i] = ln(thickness_i), t2[i] = 1/(g^2 (c2c_i (k-1))^2)  (RectilinearMesh1D.gradient_operator :747-786)
+template <typename R> __device__ __noinline__ void ch_mesh_setup(const Consts<R>* K, int kk, MeshBuf<R>* m)
+{
+    GBP_SHARED(K);
+    GBP_SHARED(m);
+    const int lane = lane_id();
+    if (kk >= 2 && lane < kk - 1) {
+        const R* e = m->edges;
+        R x0 = e[lane + 1] - e[lane];
+        R x1;
+        if (lane + 1 < kk - 1) x1 = e[lane + 2] - e[lane + 1];
+        else x1 = (kk == 2) ? x0 : (e[kk - 1] - e[kk - 2]) + (e[kk - 1] - e[0]);
+        R c2c = R(0.5) * (x0 + x1);
+        R t = R(1) / (c2c * (R)(kk - 1));
+        m->t2[lane] = t * t * K->inv_g2;
+        m->lnh[lane] = rt<R>::log(x0);
     }
-    __device__ __forceinline__ R prior_op(int kk, const R* t2, int i, int j) const
-    {
-        if (kk == 1) return K.inv_s2 + K.inv_g2;  // gradient_operator = ones((1,1))
-        if (i == j) {
-            R d = K.inv_s2;
-            if (i > 0) d += t2[i - 1];
-            if (i < kk - 1) d += t2[i];
-            return d;
-        }
-        if (i == j + 1) return -t2[j];
-        if (j == i + 1) return -t2[i];
-        return R(0);
+    __syncwarp();
+}
+
+template <typename R> __device__ __forceinline__ R prior_op(const Consts<R>* K, int kk, const R* t2, int i, int j)
+{
+    if (kk == 1) return K->inv_s2 + K->inv_g2;  // gradient_operator = ones((1,1))
+    if (i == j) {
+        R d = K->inv_s2;
+        if (i > 0) d += t2[i - 1];
+        if (i < kk - 1) d += t2[i];
+        return d;
     }
-    // gradient of lane i: Wm'Wm (ln s - ln ref) + J' Wd'Wd (pred - d)   (Model.local_gradient :347-357)
-    __device__ __noinline__ R gradient_lane(int kk, const R* t2, const R* ls, const T* J, const T* pred)
-    {
-        GBP_SHARED_STATE;
-        R g = R(0);
-        if (lane < kk) {
-            g = prior_op(kk, t2, lane, lane) * (ls[lane] - ln_ref);
-            if (lane > 0) g += prior_op(kk, t2, lane, lane - 1) * (ls[lane - 1] - ln_ref);
-            if (lane < kk - 1) g += prior_op(kk, t2, lane, lane + 1) * (ls[lane + 1] - ln_ref);
+    if (i == j + 1) return -t2[j];
+    if (j == i + 1) return -t2[i];
+    return R(0);
+}
+
+// gradient of lane i: Wm'Wm (ln s - ln ref) + J' Wd'Wd (pred - d)   (Model.local_gradient :347-357)
+template <typename R, typename T, int NC>
+__device__ __noinline__ R ch_gradient(WarpState<R, T, NC>* w, const Consts<R>* K, int kk, const R* t2, const R* ls,
+                                      const T* J, const T* pred, R ln_ref)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    GBP_SHARED(t2);
+    GBP_SHARED(ls);
+    GBP_SHARED(J);
+    GBP_SHARED(pred);
+    const int lane = lane_id();
+    const int C = K->C;
+    R g = R(0);
+    if (lane < kk) {
+        g = prior_op(K, kk, t2, lane, lane) * (ls[lane] - ln_ref);
+        if (lane > 0) g += prior_op(K, kk, t2, lane, lane - 1) * (ls[lane - 1] - ln_ref);
+        if (lane < kk - 1) g += prior_op(K, kk, t2, lane, lane + 1) * (ls[lane + 1] - ln_ref);
 #pragma unroll 1
-            for (int c = 0; c < C; ++c) g += (R)J[c * KS + lane] * (((R)pred[c] - w.data[c]) * w.ivar[c]);
-        }
-        return g;
+        for (int c = 0; c < C; ++c) g += (R)J[c * KS + lane] * (((R)pred[c] - w->data[c]) * w->ivar[c]);
     }
-    // A = Wm'Wm + J' Wd'Wd J (Model.local_precision :250-272), packed lower triangle
-    __device__ __noinline__ void assemble(int kk, const R* t2, const T* J)
-    {
-        GBP_SHARED_STATE;
+    return g;
+}
+
+// A = Wm'Wm + J' Wd'Wd J (Model.local_precision :250-272), packed lower triangle
+template <typename R, typename T, int NC>
+__device__ __noinline__ void ch_assemble(WarpState<R, T, NC>* w, const Consts<R>* K, int kk, const R* t2, const T* J)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    GBP_SHARED(t2);
+    GBP_SHARED(J);
+    const int lane = lane_id();
+    const int C = K->C;
 #pragma unroll 1
-        for (int i = 0; i < kk; ++i) {
-            if (lane <= i) {
-                R s = prior_op(kk, t2, i, lane);
+    for (int i = 0; i < kk; ++i) {
+        if (lane <= i) {
+            R s = prior_op(K, kk, t2, i, lane);
 #pragma unroll 1
-                for (int c = 0; c < C; ++c) s += (R)J[c * KS + i] * w.ivar[c] * (R)J[c * KS + lane];
-                w.A[pk(i, lane)] = s;
-            }
+            for (int c = 0; c < C; ++c) s += (R)J[c * KS + i] * w->ivar[c] * (R)J[c * KS + lane];
+            w->A[pk(i, lane)] = s;
         }
-        __syncwarp();
     }
-    // in-place packed Cholesky, lane = row.  Returns false if the matrix is not positive definite.
-    __device__ __noinline__ bool cholesky(int kk)
-    {
-        GBP_SHARED_STATE;
-        bool ok = true;
+    __syncwarp();
+}
+
+// in-place packed Cholesky, lane = row.  Returns false if the matrix is not positive definite.
+template <typename R> __device__ __noinline__ bool ch_cholesky(R* A, int kk)
+{
+    GBP_SHARED(A);
+    const int lane = lane_id();
+    bool ok = true;
 #pragma unroll 1
-        for (int j = 0; j < kk; ++j) {
-            R s = R(0);
-            if (lane >= j && lane < kk) {
-                s = w.A[pk(lane, j)];
-#pragma unroll 1
-                for (int p = 0; p < j; ++p) s -= w.A[pk(lane, p)] * w.A[pk(j, p)];
-            }
-            const R d = __shfl_sync(FULL, s, j);
-            if (!(d > R(0))) ok = false;
-            const R dj = rt<R>::sqrt(d);
-            if (lane == j) w.A[pk(j, j)] = dj;
-            else if (lane > j && lane < kk) w.A[pk(lane, j)] = s / dj;
-            __syncwarp();
-        }
-        return ok;
-    }
-    // lane i holds b_i; returns lane i of L^-1 b
-    __device__ __noinline__ R solve_L(int kk, R x)
-    {
-        GBP_SHARED_STATE;
-#pragma unroll 1
-        for (int j = 0; j < kk; ++j) {
-            const R yj = __shfl_sync(FULL, x, j) / w.A[pk(j, j)];
-            if (lane == j) x = yj;
-            else if (lane > j && lane < kk) x -= w.A[pk(lane, j)] * yj;
-        }
-        return x;
-    }
-    __device__ __noinline__ R solve_LT(int kk, R x)
-    {
-        GBP_SHARED_STATE;
-#pragma unroll 1
-        for (int j = kk - 1; j >= 0; --j) {
-            const R xj = __shfl_sync(FULL, x, j) / w.A[pk(j, j)];
-            if (lane == j) x = xj;
-            else if (lane < j) x -= w.A[pk(j, lane)] * xj;
-        }
-        return x;
-    }
-    // v' A v = |L' v|^2 with v_i held by lane i
-    __device__ __noinline__ R quad(int kk, R v)
-    {
-        GBP_SHARED_STATE;
-        if (lane < kk) w.vec[lane] = v;
-        __syncwarp();
+    for (int j = 0; j < kk; ++j) {
         R s = R(0);
-        if (lane < kk) {
+        if (lane >= j && lane < kk) {
+            s = A[pk(lane, j)];
 #pragma unroll 1
-            for (int i = lane; i < kk; ++i) s += w.A[pk(i, lane)] * w.vec[i];
+            for (int p = 0; p < j; ++p) s -= A[pk(lane, p)] * A[pk(j, p)];
         }
+        const R d = __shfl_sync(FULL, s, j);
+        if (!(d > R(0))) ok = false;
+        const R dj = rt<R>::sqrt(d);
+        if (lane == j) A[pk(j, j)] = dj;
+        else if (lane > j && lane < kk) A[pk(lane, j)] = s / dj;
         __syncwarp();
-        return warp_sum(s * s);
     }
+    return ok;
+}
+// lane i holds b_i; returns lane i of L^-1 b
+template <typename R> __device__ __noinline__ R ch_solve_L(const R* A, int kk, R x)
+{
+    GBP_SHARED(A);
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int j = 0; j < kk; ++j) {
+        const R yj = __shfl_sync(FULL, x, j) / A[pk(j, j)];
+        if (lane == j) x = yj;
+        else if (lane > j && lane < kk) x -= A[pk(lane, j)] * yj;
+    }
+    return x;
+}
+template <typename R> __device__ __noinline__ R ch_solve_LT(const R* A, int kk, R x)
+{
+    GBP_SHARED(A);
+    const int lane = lane_id();
+#pragma unroll 1
+    for (int j = kk - 1; j >= 0; --j) {
+        const R xj = __shfl_sync(FULL, x, j) / A[pk(j, j)];
+        if (lane == j) x = xj;
+        else if (lane < j) x -= A[pk(j, lane)] * xj;
+    }
+    return x;
+}
+// v' A v = |L' v|^2 with v_i held by lane i
+template <typename R> __device__ __noinline__ R ch_quad(const R* A, R* vec, int kk, R v)
+{
+    GBP_SHARED(A);
+    GBP_SHARED(vec);
+    const int lane = lane_id();
+    if (lane < kk) vec[lane] = v;
+    __syncwarp();
+    R s = R(0);
+    if (lane < kk) {
+#pragma unroll 1
+        for (int i = lane; i < kk; ++i) s += A[pk(i, lane)] * vec[i];
+    }
+    __syncwarp();
+    return warp_sum(s * s);
+}
 
-    // ------------------------------------------------------------ structure proposal (warp-uniform)
-    // RectilinearMesh1D.perturb :993-1120.  Writes the proposed mesh / remapped values into the spare
-    // buffers (mesh[mcur^1], val[vcur^1], ls_r) and returns the action; for ACT_NONE only ls_r is filled.
-    __device__ __noinline__ int perturb_structure(int* knew)
-    {
-        GBP_SHARED_STATE;
-        const MeshBuf<R>& m0 = w.mesh[mcur];
-        const ValBuf<R>& v0 = w.val[vcur];
-        MeshBuf<R>& m1 = w.mesh[mcur ^ 1];
-        ValBuf<R>& v1 = w.val[vcur ^ 1];
-        const int kmax = P.opt.max_layers;
+// StatArray.propose(imposePrior=True) for a 1-D log-normal random walk (StatArray.py:578-638), in ln space
+template <typename R> struct prop_t {
+    R x;
+    uint32_t block;  // advanced Philox block counter
+};
+template <typename R> __device__ __noinline__ prop_t<R> ch_propose_ln_error(Rng g, R ln_cur, R sd, R lnmin, R lnmax)
+{
+    R x = ln_cur + sd * rng_normal<R>(g);
+    int tries = 0;
 #pragma unroll 1
-        for (;;) {
-            int event;
+    while (x < lnmin || x > lnmax) {
+        x = ln_cur + sd * rng_normal<R>(g);
+        tries++;
+        if (tries == 10) {
+            x = ln_cur;
+            break;
+        }
+    }
+    return prop_t<R>{x, g.block};
+}
+
+// add `count` visits of the current model / errors to every histogram
+template <typename R, typename T, int NC>
+__device__ __noinline__ void ch_flush(WarpState<R, T, NC>* w, const Consts<R>* K, int k, int mcur, int vcur, R ln_rel,
+                                      R ln_add, R sig_lo, int count)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    if (count <= 0) return;
+    const int lane = lane_id();
+    const int nd = K->n_depth, nsb = K->n_sig, neb = K->n_err;
+    const MeshBuf<R>& m = w->mesh[mcur];
+    const ValBuf<R>& v = w->val[vcur];
+    int32_t* hitmap = (int32_t*)w->outp[OP_HITMAP];
+    int32_t* edges_hist = (int32_t*)w->outp[OP_EDGES];
+    if (lane == 0) {
+        int32_t* nc = (int32_t*)w->outp[OP_NCELLS];
+        int32_t* rh = (int32_t*)w->outp[OP_REL];
+        int32_t* ah = (int32_t*)w->outp[OP_ADD];
+        if (nc) nc[k] += count;
+        if (rh && K->solve_rel) rh[uniform_bin<R>(ln_rel, K->rel_lnmin, K->rel_dx, neb)] += count;
+        if (ah && K->solve_add) ah[uniform_bin<R>(ln_add, K->add_lnmin, K->add_dx, neb)] += count;
+    }
+    // per-layer conductivity bin; interface histogram (RectilinearMesh1D.update_posteriors :1594-1610):
+    // ratio sigma_i / sigma_{i-1} <= 0.5 or >= 1.5
+    if (lane < k) w->sbin[lane] = uniform_bin<R>(v.ls[lane], sig_lo, K->sig_dx, nsb);
+    if (lane >= 1 && lane < k && edges_hist) {
+        const R dl = v.ls[lane] - v.ls[lane - 1];
+        const R d = m.edges[lane];
+        if ((dl <= K->ln_half || dl >= K->ln_3half) && d >= R(0) && d < K->depth_max)
+            atomicAdd(&edges_hist[uniform_bin<R>(d, R(0), K->depth_step, nd)], count);
+    }
+    __syncwarp();
+    // hitmap (Model.update_parameter_posterior :819-847; staircase interp RectilinearMesh1D.py:1148-1158)
+    if (hitmap) {
 #pragma unroll 1
-            for (;;) {  // Categorical.rng: searchsorted(cumsum(p), U), re-drawn while illegal (:1041-1049)
-                const R u = rng_uniform<R>(rng);
-                event = (u <= K.cum0) ? 0 : (u <= K.cum1) ? 1 : (u <= K.cum2) ? 2 : 3;
-                if (k == 1 && (event == 1 || event == 2)) continue;
-                if (k == kmax && event == 0) continue;
-                break;
-            }
-            if (event == ACT_NONE) {
-                if (lane < k) w.ls_r[lane] = v0.ls[lane];
-                __syncwarp();
-                *knew = k;
-                return ACT_NONE;
-            }
-            if (event == ACT_BIRTH) {  // :1061-1081
-                bool ok = false;
-                int pos = 0;
-                R e = R(0);
+        for (int j = lane; j < nd; j += 32) {
+            const R y = ((R)j + R(0.5)) * K->depth_step;
+            int b = w->sbin[k - 1];
 #pragma unroll 1
-                for (int tries = 1; tries <= 10; ++tries) {
-                    e = rt<R>::exp(K.ln_min_edge + K.ln_edge_span * rng_uniform<R>(rng));
-                    pos = __popc(__ballot_sync(FULL, lane <= k && m0.edges[lane] < e));  // searchsorted (left)
-                    R d = INFINITY;  // widths after insertion: cell pos-1 is split in two
-                    if (lane < k)
-                        d = (lane == pos - 1) ? fmin(e - m0.edges[lane], m0.edges[lane + 1] - e)
-                                              : m0.edges[lane + 1] - m0.edges[lane];
-                    const R h = warp_min(d);
-                    if (tries == 10) break;  // the 10th try always restarts (:1078-1080)
-                    if (h > K.min_width) {
-                        ok = true;
-                        break;
-                    }
+            for (int i = 1; i < k; ++i) {
+                const R e = m.edges[i];
+                if (y < e) {
+                    b = w->sbin[i - 1];
+                    break;
                 }
-                if (!ok) continue;
-                if (lane <= k + 1) m1.edges[lane] = (lane < pos) ? m0.edges[lane] : (lane == pos ? e : m0.edges[lane - 1]);
-                if (lane <= k) {  // values.insert(pos, values[pos-1]) (:835)
-                    const int src = (lane < pos) ? lane : lane - 1;
-                    v1.sig[lane] = v0.sig[src];
-                    w.ls_r[lane] = v0.ls[src];
+                const R e2 = e * R(1.000001);
+                if (y < e2) {
+                    const R t = (y - e) / (e2 - e);
+                    const R s = v.sig[i - 1] + t * (v.sig[i] - v.sig[i - 1]);
+                    b = uniform_bin<R>(rt<R>::log(s), sig_lo, K->sig_dx, nsb);
+                    break;
                 }
-                __syncwarp();
-                *knew = k + 1;
-                return ACT_BIRTH;
             }
-            if (event == ACT_DEATH) {  // :1083-1087, delete_edge :643-689
-                const int i = (int)(rng_uniform<R>(rng) * (R)(k - 1)) + 1;
-                if (lane <= k - 1) m1.edges[lane] = m0.edges[lane + (lane >= i ? 1 : 0)];
-                if (lane < k - 1) {
-                    const int src = lane + (lane >= i ? 1 : 0);
-                    R s = v0.sig[src], l = v0.ls[src];
-                    if (lane == i - 1) {
-                        s = R(0.5) * (v0.sig[i - 1] + v0.sig[i]);
-                        l = rt<R>::log(s);
-                    }
-                    v1.sig[lane] = s;
-                    w.ls_r[lane] = l;
-                }
-                __syncwarp();
-                *knew = k - 1;
-                return ACT_DEATH;
-            }
-            {  // ACT_MOVE :1088-1118
-                bool ok = false;
-                int i = 1;
-                R dz = R(0);
-#pragma unroll 1
-                for (int tries = 1; tries <= 10; ++tries) {
-                    i = (int)(R(1) + ((R)k - R(1)) * rng_uniform<R>(rng));
-                    const R zn = rng_normal<R>(rng);
-                    const R sgn = (zn > R(0)) ? R(1) : (zn < R(0) ? R(-1) : R(0));
-                    dz = sgn * K.min_width * rng_uniform<R>(rng);
-                    R d = INFINITY;
-                    if (lane < k)
-                        d = (m0.edges[lane + 1] + (lane + 1 == i ? dz : R(0))) - (m0.edges[lane] + (lane == i ? dz : R(0)));
-                    const R h = warp_min(d);
-                    const R z1 = m0.edges[1] + (i == 1 ? dz : R(0));
-                    const R zl = m0.edges[k - 1] + (i == k - 1 ? dz : R(0));
-                    if (tries == 10) break;
-                    if (h > K.min_width && z1 > K.min_edge && zl < K.max_edge) {
-                        ok = true;
-                        break;
-                    }
-                }
-                if (!ok) continue;
-                if (lane <= k) m1.edges[lane] = m0.edges[lane] + (lane == i ? dz : R(0));
-                if (lane < k) {
-                    v1.sig[lane] = v0.sig[lane];
-                    w.ls_r[lane] = v0.ls[lane];
-                }
-                __syncwarp();
-                *knew = k;
-                return ACT_MOVE;
-            }
+            atomicAdd(&hitmap[(size_t)b * nd + j], count);  // RED.ADD, coalesced along depth
         }
     }
+    __syncwarp();
+}
 
-    // StatArray.propose(imposePrior=True) for a 1-D log-normal random walk (StatArray.py:578-638), in ln space
-    __device__ __noinline__ R propose_ln_error(R ln_cur, R sd, R lnmin, R lnmax)
-    {
-        R x = ln_cur + sd * rng_normal<R>(rng);
-        int tries = 0;
+template <typename R, typename T, int NC> __device__ __noinline__ void ch_zero_posteriors(WarpState<R, T, NC>* w, const Consts<R>* K)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    const int lane = lane_id();
+    const int nd = K->n_depth;
+    int32_t* p;
+    if ((p = (int32_t*)w->outp[OP_HITMAP])) {
+        const size_t n = (size_t)K->n_sig * nd;
 #pragma unroll 1
-        while (x < lnmin || x > lnmax) {
-            x = ln_cur + sd * rng_normal<R>(rng);
-            tries++;
-            if (tries == 10) return ln_cur;
-        }
-        return x;
+        for (size_t i = lane; i < n; i += 32) p[i] = 0;
     }
+    if ((p = (int32_t*)w->outp[OP_EDGES])) {
+#pragma unroll 1
+        for (int i = lane; i < nd; i += 32) p[i] = 0;
+    }
+    if ((p = (int32_t*)w->outp[OP_NCELLS])) {
+#pragma unroll 1
+        for (int i = lane; i <= K->kmax; i += 32) p[i] = 0;
+    }
+    if ((p = (int32_t*)w->outp[OP_REL])) {
+#pragma unroll 1
+        for (int i = lane; i < K->n_err; i += 32) p[i] = 0;
+    }
+    if ((p = (int32_t*)w->outp[OP_ADD])) {
+#pragma unroll 1
+        for (int i = lane; i < K->n_err; i += 32) p[i] = 0;
+    }
+    __syncwarp();
+}
 
-    // ------------------------------------------------------------ posterior accumulators
-    // add `count` visits of the CURRENT model / errors to every histogram
-    __device__ __noinline__ void flush(int count)
-    {
-        GBP_SHARED_STATE;
-        if (count <= 0) return;
-        const gbp_chain_buffers& o = P.out;
-        const int nd = P.n_depth, nsb = P.opt.n_sigma_bins, neb = P.opt.n_err_bins;
-        const MeshBuf<R>& m = w.mesh[mcur];
-        const ValBuf<R>& v = w.val[vcur];
-        if (lane == 0) {
-            if (o.ncells_hist) o.ncells_hist[(size_t)chain * (P.opt.max_layers + 1) + k] += count;
-            if (o.rel_hist && P.opt.solve_relative_error)
-                o.rel_hist[(size_t)chain * neb + uniform_bin<R>(ln_rel, K.rel_lnmin, K.rel_dx, neb)] += count;
-            if (o.add_hist && P.opt.solve_additive_error)
-                o.add_hist[(size_t)chain * neb + uniform_bin<R>(ln_add, K.add_lnmin, K.add_dx, neb)] += count;
-        }
-        // per-layer conductivity bin; interface histogram (RectilinearMesh1D.update_posteriors :1594-1610):
-        // ratio sigma_i / sigma_{i-1} <= 0.5 or >= 1.5
-        if (lane < k) w.sbin[lane] = uniform_bin<R>(v.ls[lane], sig_lo, K.sig_dx, nsb);
-        if (lane >= 1 && lane < k && o.edges_hist) {
-            const R dl = v.ls[lane] - v.ls[lane - 1];
-            const R d = m.edges[lane];
-            if ((dl <= K.ln_half || dl >= K.ln_3half) && d >= R(0) && d < K.depth_max)
-                atomicAdd(&o.edges_hist[(size_t)chain * nd + uniform_bin<R>(d, R(0), K.depth_step, nd)], count);
-        }
+template <typename R, typename T, int NC>
+__device__ __noinline__ void ch_write_model(WarpState<R, T, NC>* w, int ml, int k, int mcur, int vcur, double* sig_out, double* edges_out)
+{
+    GBP_SHARED(w);
+    const int lane = lane_id();
+    const MeshBuf<R>& m = w->mesh[mcur];
+    const ValBuf<R>& v = w->val[vcur];
+    if (sig_out && lane < ml) sig_out[lane] = lane < k ? (double)v.sig[lane] : NAN;
+    if (edges_out) {
+#pragma unroll 1
+        for (int i = lane; i <= ml; i += 32) edges_out[i] = i <= k ? (double)m.edges[i] : NAN;
+    }
+}
+
+template <typename R> struct init_out {
+    R ln_ref, misfit, likelihood, prior;
+    double sigma_ref;
+};
+
+// Inference1D.initialize :353-464 / initialize_model :485-535: best half-space, first forward + Jacobian,
+// initial misfit / likelihood / prior, cold counters.  `first == false` is reset() (:984-999).
+template <typename R, typename T, int NC>
+__device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC>* w, const Consts<R>* K, const SysShared<T>* S, const T* tab,
+                                                  T alt, R nahl, bool first, double* best_sig_out, double* best_edg_out)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    const int lane = lane_id();
+    const int C = K->C;
+    ch_set_ivar(w, C, K->rel0, K->add0);
+    // EmDataPoint.find_best_halfspace :148-186: argmin misfit over logspace(-4, 4, 100)
+    MeshBuf<R>& m = w->mesh[0];
+    ValBuf<R>& v = w->val[0];
+    if (lane == 0) {
+        m.edges[0] = R(0);
+        m.edges[1] = INFINITY;
+    }
+    __syncwarp();
+    R best = INFINITY;
+    double best_c = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 100; ++i) {
+        const double e = (i == 99) ? 4.0 : -4.0 + (double)i * (8.0 / 99.0);
+        const double c = dexp_(e * 2.302585092994045684017991454684);
+        if (lane == 0) v.sig[0] = (R)c;
         __syncwarp();
-        // hitmap (Model.update_parameter_posterior :819-847; staircase interp RectilinearMesh1D.py:1148-1158)
-        if (o.hitmap) {
-            int32_t* hm = o.hitmap + (size_t)chain * nsb * nd;
+        ch_forward(w, S, tab, alt, 1, v.sig, m.edges, w->pred[0], (T*)nullptr);
+        const pair_t<R> ml_ = ch_misfit_like(w, C, nahl, w->pred[0]);
+        if (ml_.a < best) {
+            best = ml_.a;
+            best_c = c;
+        }
+    }
+    init_out<R> io;
+    io.sigma_ref = best_c;
+    io.ln_ref = (R)dlog_(best_c);
+    if (lane == 0) {
+        v.sig[0] = (R)best_c;
+        v.ls[0] = io.ln_ref;
+    }
+    __syncwarp();
+    ch_forward(w, S, tab, alt, 1, v.sig, m.edges, w->pred[0], w->J[0]);
+    if (!first) {  // reset(): posteriors and traces are re-created
+        ch_zero_posteriors(w, K);
+        const long long N2 = 2 * (long long)K->n_chains;
+        double* mt = (double*)w->outp[OP_MISFIT];
+        uint8_t* at = (uint8_t*)w->outp[OP_ACCEPT];
+        if (mt) {
 #pragma unroll 1
-            for (int j = lane; j < nd; j += 32) {
-                const R y = ((R)j + R(0.5)) * K.depth_step;
-                int b = w.sbin[k - 1];
+            for (long long i = lane; i < N2; i += 32) mt[i] = 0.0;
+        }
+        if (at) {
 #pragma unroll 1
-                for (int i = 1; i < k; ++i) {
-                    const R e = m.edges[i];
-                    if (y < e) {
-                        b = w.sbin[i - 1];
-                        break;
-                    }
-                    const R e2 = e * R(1.000001);
-                    if (y < e2) {
-                        const R t = (y - e) / (e2 - e);
-                        const R s = v.sig[i - 1] + t * (v.sig[i] - v.sig[i - 1]);
-                        b = uniform_bin<R>(rt<R>::log(s), sig_lo, K.sig_dx, nsb);
-                        break;
-                    }
-                }
-                atomicAdd(&hm[(size_t)b * nd + j], count);  // RED.ADD, coalesced along depth
-            }
+            for (long long i = lane; i < N2; i += 32) at[i] = 0;
         }
         __syncwarp();
     }
-
-    __device__ __noinline__ void zero_posteriors()
-    {
-        const gbp_chain_buffers& o = P.out;
-        const int nd = P.n_depth;
-        if (o.hitmap) {
-            int32_t* hm = o.hitmap + (size_t)chain * P.opt.n_sigma_bins * nd;
-            const size_t n = (size_t)P.opt.n_sigma_bins * nd;
-#pragma unroll 1
-            for (size_t i = lane; i < n; i += 32) hm[i] = 0;
-        }
-        if (o.edges_hist) {
-#pragma unroll 1
-            for (int i = lane; i < nd; i += 32) o.edges_hist[(size_t)chain * nd + i] = 0;
-        }
-        if (o.ncells_hist) {
-#pragma unroll 1
-            for (int i = lane; i <= P.opt.max_layers; i += 32) o.ncells_hist[(size_t)chain * (P.opt.max_layers + 1) + i] = 0;
-        }
-        if (o.rel_hist) {
-#pragma unroll 1
-            for (int i = lane; i < P.opt.n_err_bins; i += 32) o.rel_hist[(size_t)chain * P.opt.n_err_bins + i] = 0;
-        }
-        if (o.add_hist) {
-#pragma unroll 1
-            for (int i = lane; i < P.opt.n_err_bins; i += 32) o.add_hist[(size_t)chain * P.opt.n_err_bins + i] = 0;
-        }
-        __syncwarp();
+    const pair_t<R> ml0 = ch_misfit_like(w, C, nahl, w->pred[0]);
+    io.misfit = ml0.a;
+    io.likelihood = ml0.b;
+    R dp = R(0);
+    if (K->solve_rel) dp += K->rel_lp;
+    if (K->solve_add) dp += K->add_lp;
+    io.prior = ch_model_prob(K, 1, v.ls, m.lnh, io.ln_ref) + dp;
+    if (lane == 0) {
+        double* mt = (double*)w->outp[OP_MISFIT];
+        if (mt) mt[0] = (double)io.misfit;
+        w->ctr[CT_BURN_ITER] = 0;
+        w->ctr[CT_N_ZERO] = 0;
+        w->ctr[CT_ACC_WIN] = 0;
+        w->ctr[CT_TO_PLOT] = K->upe;
+        w->ctr[CT_BEST_K] = 1;
+        w->ctr[CT_BEST_ITER] = 0;
+        w->bestv[BV_POSTERIOR] = io.likelihood + io.prior;
+        w->bestv[BV_REL] = K->rel0;
+        w->bestv[BV_ADD] = K->add0;
     }
+    ch_write_model(w, K->kmax, 1, 0, 0, best_sig_out, best_edg_out);
+    __syncwarp();
+    return io;
+}
 
-    __device__ __noinline__ void write_model(double* sig_out, double* edges_out)
-    {
-        const int ml = P.opt.max_layers;
-        const MeshBuf<R>& m = w.mesh[mcur];
-        const ValBuf<R>& v = w.val[vcur];
-        if (sig_out && lane < ml) sig_out[(size_t)chain * ml + lane] = lane < k ? (double)v.sig[lane] : NAN;
-        if (edges_out) {
-#pragma unroll 1
-            for (int i = lane; i <= ml; i += 32) edges_out[(size_t)chain * (ml + 1) + i] = i <= k ? (double)m.edges[i] : NAN;
-        }
+template <typename R, typename T, int NC>
+__device__ __noinline__ void ch_save_best(WarpState<R, T, NC>* w, int ml, int k, int mcur, int vcur, int iteration, R posterior,
+                                          R rel, R add, double* best_sig_out, double* best_edg_out)
+{
+    GBP_SHARED(w);
+    ch_write_model(w, ml, k, mcur, vcur, best_sig_out, best_edg_out);
+    if (lane_id() == 0) {
+        w->ctr[CT_BEST_K] = k;
+        w->ctr[CT_BEST_ITER] = iteration;
+        w->bestv[BV_POSTERIOR] = posterior;
+        w->bestv[BV_REL] = rel;
+        w->bestv[BV_ADD] = add;
     }
-    __device__ __noinline__ void save_best()
+    __syncwarp();
+}
+
+// ================================================================ the chain (inlined into the kernel)
+template <typename R, typename T, int NC>
+__device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R>* K, const SysShared<T>* S, const T* tab,
+                                          const ChainParams& P, const int chain)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    const int lane = lane_id();
+    const int C = K->C;
+    const int ml = K->kmax;
+    const int N = K->n_chains;
+    const long long N2 = 2 * (long long)N;
+
+    // ---- hot state (registers)
+    Rng rng;
+    rng.seed_lo = (uint32_t)P.seed;
+    rng.seed_hi = (uint32_t)(P.seed >> 32);
     {
-        write_model(P.out.best_sigma, P.out.best_edges);
-        best_k = k;
-        best_rel = rel;
-        best_add = add;
-        best_posterior = posterior;
-        best_iter = iteration;
-    }
-
-    // ------------------------------------------------------------ Inference1D.initialize
-    __device__ __noinline__ void initialize(bool first)
-    {
-        const gbp_options& o = P.opt;
-        mcur = vcur = jcur = pcur = 0;
-        ln_rel = K.rel_ln0;
-        ln_add = K.add_ln0;
-        rel = (R)o.rel_init;
-        add = (R)o.add_init;
-        set_ivar(rel, add);
-        // EmDataPoint.find_best_halfspace :148-186: argmin misfit over logspace(-4, 4, 100)
-        MeshBuf<R>& m = w.mesh[0];
-        ValBuf<R>& v = w.val[0];
-        if (lane == 0) {
-            m.edges[0] = R(0);
-            m.edges[1] = INFINITY;
-        }
-        __syncwarp();
-        R best = INFINITY;
-        double best_c = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < 100; ++i) {
-            const double e = (i == 99) ? 4.0 : -4.0 + (double)i * (8.0 / 99.0);
-            const double c = dexp_(e * 2.302585092994045684017991454684);
-            if (lane == 0) v.sig[0] = (R)c;
-            __syncwarp();
-            forward(1, v.sig, m.edges, w.pred[0], nullptr);
-            R mis, like;
-            misfit_likelihood(w.pred[0], &mis, &like);
-            if (mis < best) {
-                best = mis;
-                best_c = c;
-            }
-        }
-        sigma_ref = best_c;
-        ln_ref = (R)dlog_(best_c);
-        k = 1;
-        if (lane == 0) {
-            v.sig[0] = (R)best_c;
-            v.ls[0] = ln_ref;
-        }
-        __syncwarp();
-        forward(1, v.sig, m.edges, w.pred[0], w.J[0]);
-        sig_lo = ln_ref - K.sig_halfspan;  // Model.set_posteriors :666-684
-        if (!first) {                       // reset(): posteriors and traces are re-created
-            zero_posteriors();
-            const size_t N2 = 2 * (size_t)o.n_markov_chains;
-            if (P.out.misfit_trace) {
-#pragma unroll 1
-                for (size_t i = lane; i < N2; i += 32) P.out.misfit_trace[(size_t)chain * N2 + i] = 0.0;
-            }
-            if (P.out.accept_trace) {
-#pragma unroll 1
-                for (size_t i = lane; i < N2; i += 32) P.out.accept_trace[(size_t)chain * N2 + i] = 0;
-            }
-            __syncwarp();
-        }
-        misfit_likelihood(w.pred[0], &misfit, &likelihood);
-        prior = model_probability(1, v.ls, m.lnh) + datapoint_probability(ln_rel, ln_add);
-        posterior = likelihood + prior;
-        burned_in = 0;
-        burned_in_iter = 0;
-        iteration = 0;
-        if (P.out.misfit_trace && lane == 0) P.out.misfit_trace[(size_t)chain * 2 * o.n_markov_chains] = (double)misfit;
-        save_best();
-        n_zero = 0;
-        acc_win = 0;
-        dwell = 0;
-    }
-
-    // ------------------------------------------------------------ Inference1D.accept_reject
-    // returns true if the chain failed (Gauss-Newton matrix not positive definite)
-    __device__ __noinline__ bool step(bool* accepted_out)
-    {
-        GBP_SHARED_STATE;
-        const gbp_options& o = P.opt;
-        *accepted_out = false;
-        int kn;
-        const int action = perturb_structure(&kn);
-        n_act[action]++;
-        const bool changed = action != ACT_NONE;
-        const int mp = changed ? (mcur ^ 1) : mcur;  // proposed mesh buffer
-        const int vp = vcur ^ 1;                     // proposed values buffer
-        MeshBuf<R>& mesh_p = w.mesh[mp];
-        ValBuf<R>& val_p = w.val[vp];
-
-        const T* Jh = w.J[jcur];
-        const T* ph = w.pred[pcur];
-        T* pred_t = w.pred[pcur ^ 1];
-        T* J_t = w.J[jcur ^ 1];
-        if (changed) {  // observation.fm_dlogc(remapped_model): J and predicted data of the test datapoint
-            mesh_setup(kn, mesh_p);
-            forward(kn, val_p.sig, mesh_p.edges, pred_t, J_t);
-            Jh = J_t;
-            ph = pred_t;
-        }
-        set_ivar(rel, add);
-        const R ln_r = (lane < kn) ? w.ls_r[lane] : R(0);
-        const R g = gradient_lane(kn, mesh_p.t2, w.ls_r, Jh, ph);
-        assemble(kn, mesh_p.t2, Jh);
-        if (!cholesky(kn)) return true;
-        const R stepv = solve_LT(kn, solve_L(kn, g));   // H * dfk
-        const R mean = ln_r - K.alpha * stepv;           // ln sigma + alpha * pk, pk = -H dfk
-        // sigma' ~ exp(N(mean, H)),  H = (L L')^-1  ->  mean + L^-T z
-        R z0 = R(0), z1 = R(0);
-        const int npair = (kn + 1) / 2;
-        if (lane < npair) normal2_at<R>(rng, rng.block + (unsigned long long)lane, &z0, &z1);
-        rng.block += (unsigned long long)npair;
-        const R za = __shfl_sync(FULL, z0, lane >> 1), zb = __shfl_sync(FULL, z1, lane >> 1);
-        const R zi = (lane < kn) ? ((lane & 1) ? zb : za) : R(0);
-        const R ln_t = mean + solve_LT(kn, zi);
-        if (lane < kn) {
-            val_p.ls[lane] = ln_t;
-            val_p.sig[lane] = rt<R>::exp(ln_t);
-        }
-        __syncwarp();
-
-        // test_datapoint.perturb() (DataPoint.py:531-573)
-        R lr_t = ln_rel, la_t = ln_add;
-        if (o.solve_relative_error) lr_t = propose_ln_error(ln_rel, K.rel_sd, K.rel_lnmin, K.rel_lnmax);
-        if (o.solve_additive_error) la_t = propose_ln_error(ln_add, K.add_sd, K.add_lnmin, K.add_lnmax);
-        const R rel_t = (lr_t == ln_rel) ? rel : rt<R>::exp(lr_t);
-        const R add_t = (la_t == ln_add) ? add : rt<R>::exp(la_t);
-
-        const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
-        // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
-        // (Model.proposal_probabilities :619) - fused into the same pass.
-        forward(kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : nullptr);
-        set_ivar(rel_t, add_t);
-        R t_misfit, t_like;
-        misfit_likelihood(pred_t, &t_misfit, &t_like);
-        R t_prior = datapoint_probability(lr_t, la_t);
-        if (t_prior == (R)-INFINITY) return false;
-        t_prior += model_probability(kn, val_p.ls, mesh_p.lnh);
-        if (t_prior == (R)-INFINITY) return false;
-
-        R proposal = R(1), proposal1 = R(1);
-        if (jump) {
-            const R g2 = gradient_lane(kn, mesh_p.t2, val_p.ls, J_t, pred_t);
-            const R s2 = solve_LT(kn, solve_L(kn, g2));   // H dfk'
-            const R lv = ln_t + K.alpha * s2;              // Model.py:626 (sign as in the reference)
-            const R mv = rt<R>::exp(lv);
-            const int bad = __any_sync(FULL, lane < kn && (mv == (R)INFINITY || mv == R(0)));
-            const R q_r = quad(kn, (lane < kn) ? (ln_r - lv) : R(0));
-            const R q_f = quad(kn, (lane < kn) ? (ln_t - ln_r) : R(0));
-            const R logdetL = warp_sum((lane < kn) ? rt<R>::log(w.A[pk(lane, lane)]) : R(0));
-            if (bad) {
-                proposal = (R)-INFINITY;
-                proposal1 = (R)-INFINITY;
-            } else {
-                proposal = -(R)kn * K.half_log2pi + logdetL - R(0.5) * q_r;
-                proposal1 = -(R)kn * K.half_log2pi + logdetL - R(0.5) * q_f;
-            }
-        }
-        const R log_alpha = (t_prior - prior) + (t_like - likelihood) + (proposal - proposal1);
-        const R u = rng_uniform<R>(rng);
-        const bool acc = rt<R>::exp(log_alpha) > u;
-        if (acc) {
-            flush(dwell);  // the outgoing model's visits
-            dwell = 0;
-            misfit = t_misfit;
-            prior = t_prior;
-            likelihood = t_like;
-            posterior = t_prior + t_like;
-            k = kn;
-            rel = rel_t;
-            add = add_t;
-            ln_rel = lr_t;
-            ln_add = la_t;
-            mcur = mp;
-            vcur = vp;
-            pcur ^= 1;
-            if (changed) jcur ^= 1;  // action none keeps the (stale) Jacobian, as the reference does
-            n_accept++;
-        }
-        *accepted_out = acc;
-        return false;
-    }
-
-    // ------------------------------------------------------------ Inference1D.update; returns true on reset
-    __device__ __noinline__ bool update(bool accepted)
-    {
-        const gbp_options& o = P.opt;
-        const long long N2 = 2 * (long long)o.n_markov_chains;
-        bool do_reset = false;
-        iteration++;
-        if (P.out.misfit_trace && lane == 0 && iteration - 1 < N2)
-            P.out.misfit_trace[(size_t)chain * N2 + (iteration - 1)] = (double)misfit;
-        if (!burned_in && iteration > o.burn_in_min_iter && misfit < (R)n_active) {
-            burned_in = 1;
-            burned_in_iter = iteration;
-            save_best();
-            zero_posteriors();
-            dwell = 0;
-        }
-        if (posterior > best_posterior) save_best();
-        if (P.out.accept_trace && lane == 0 && iteration < N2)
-            P.out.accept_trace[(size_t)chain * N2 + iteration] = accepted ? 1 : 0;
-        if (iteration % o.update_plot_every == 0) {
-            // acceptance over acceptance_v[it-upe : it] (Inference1D.py:125-131): excludes this iteration
-            const int s = acc_win;
-            acc_win = 0;
-            if (o.update_plot_every > 1) {
-                if (!burned_in) {
-                    if (s == 0) {
-                        n_zero++;
-                        if (n_zero == o.reset_limit) {
-                            do_reset = true;
-                            n_zero = 0;
-                        }
-                    } else n_zero = 0;
-                } else if (s == 0) limiters = 0;
-            }
-        }
-        acc_win += accepted ? 1 : 0;
-        if (do_reset) return true;
-        dwell++;
-        return false;
-    }
-
-    // ------------------------------------------------------------ Inference1D.infer
-    __device__ __noinline__ void run(int chain_)
-    {
-        const gbp_options& o = P.opt;
-        chain = chain_;
         const unsigned long long snd = P.first_index + (unsigned long long)chain;
-        rng.seed_lo = (uint32_t)P.seed;
-        rng.seed_hi = (uint32_t)(P.seed >> 32);
         rng.snd_lo = (uint32_t)snd;
         rng.snd_hi = (uint32_t)(snd >> 32);
-        rng.block = 0;
-        alt = (T)P.altitude[chain];
-        int act = 0;
-        if (lane < C) {
-            double d = P.data[(size_t)chain * C + lane];
-            act = d > 0.0;               // EmDataPoint.active: observed > 0 and not NaN
-            w.data[lane] = act ? (R)d : R(0);
-        }
-        n_active = warp_sum_i(act);
-        n_accept = n_forward = n_sens = 0;
-        n_act[0] = n_act[1] = n_act[2] = n_act[3] = 0;
-        n_resets = 0;
-        limiters = 0;
-        __syncwarp();
-        initialize(true);
+    }
+    rng.block = 0u;
+    const T alt = (T)P.altitude[chain];
+    int k = 1, mcur = 0, vcur = 0, jcur = 0, pcur = 0;
+    R ln_rel, ln_add, rel, add, ln_ref = R(0), sig_lo = R(0);
+    double sigma_ref = 0.0;
+    R misfit = R(0), prior = R(0), likelihood = R(0);
+    int iteration = 0, burned_in = 0, dwell = 0;
 
-        bool failed = (n_active == 0);
-        bool go = !failed;
-        long long total = 0;
-        const int N = o.n_markov_chains;
+    // ---- per-chain setup
+    int act = 0;
+    if (lane < C) {
+        const double d = P.data[(size_t)chain * C + lane];
+        act = d > 0.0;               // EmDataPoint.active: observed > 0 and not NaN
+        w->data[lane] = act ? (R)d : R(0);
+    }
+    const int n_active = warp_sum_i(act);
+    const R nahl = (R)n_active * K->half_log2pi;
+    if (lane == 0) {
+        const gbp_chain_buffers& o = P.out;
+        w->outp[OP_HITMAP] = o.hitmap ? o.hitmap + (size_t)chain * K->n_sig * K->n_depth : nullptr;
+        w->outp[OP_EDGES] = o.edges_hist ? o.edges_hist + (size_t)chain * K->n_depth : nullptr;
+        w->outp[OP_NCELLS] = o.ncells_hist ? o.ncells_hist + (size_t)chain * (ml + 1) : nullptr;
+        w->outp[OP_REL] = o.rel_hist ? o.rel_hist + (size_t)chain * K->n_err : nullptr;
+        w->outp[OP_ADD] = o.add_hist ? o.add_hist + (size_t)chain * K->n_err : nullptr;
+        w->outp[OP_MISFIT] = o.misfit_trace ? o.misfit_trace + (size_t)chain * N2 : nullptr;
+        w->outp[OP_ACCEPT] = o.accept_trace ? o.accept_trace + (size_t)chain * N2 : nullptr;
+        for (int i = 0; i < CT_N; ++i) w->ctr[i] = 0;
+    }
+    __syncwarp();
+    double* const best_sig_out = P.out.best_sigma ? P.out.best_sigma + (size_t)chain * ml : nullptr;
+    double* const best_edg_out = P.out.best_edges ? P.out.best_edges + (size_t)chain * (ml + 1) : nullptr;
+
+    // Inference1D.initialize :353-464 (also used by reset() :984-999): cold, one shared copy
+    auto initialize = [&](bool first) {
+        const init_out<R> io = ch_initialize<R, T, NC>(w, K, S, tab, alt, nahl, first, best_sig_out, best_edg_out);
+        mcur = vcur = jcur = pcur = 0;
+        ln_rel = K->rel_ln0;
+        ln_add = K->add_ln0;
+        rel = K->rel0;
+        add = K->add0;
+        sigma_ref = io.sigma_ref;
+        ln_ref = io.ln_ref;
+        sig_lo = ln_ref - K->sig_halfspan;  // Model.set_posteriors :666-684
+        misfit = io.misfit;
+        likelihood = io.likelihood;
+        prior = io.prior;
+        k = 1;
+        burned_in = 0;
+        iteration = 0;
+        dwell = 0;
+    };
+    auto save_best = [&]() {
+        ch_save_best<R, T, NC>(w, ml, k, mcur, vcur, iteration, likelihood + prior, rel, add, best_sig_out, best_edg_out);
+    };
+
+    initialize(true);
+
+    bool failed = (n_active == 0);
+    bool go = !failed;
+    long long total = 0;
 #pragma unroll 1
-        while (go) {
-            bool accepted;
-            failed = step(&accepted);
-            const bool reset = update(accepted);
-            total++;
-            if (reset) {
-                n_resets++;
-                initialize(false);
-                dwell = 1;  // update() continues on the re-initialised state
-            }
-            go = !failed && (iteration <= N + burned_in_iter);
-            if (!failed && !burned_in) {
-                go = iteration < N;
-                if (!go) failed = true;
-            }
-            if (n_resets == 3 && !burned_in) {
-                if (!limiters) {
-                    limiters = 1;
-                    n_resets = 1;
-                    initialize(false);
-                } else {
-                    go = false;
-                    failed = true;
+    while (go) {
+        // ==================================================== Inference1D.accept_reject :537-631
+        bool accepted = false;
+        bool chol_failed = false;
+        {
+            // ---- RectilinearMesh1D.perturb :993-1120 (warp-uniform).  Proposed mesh -> mesh[mcur^1],
+            //      remapped values -> val[vcur^1].sig and ls_r; for ACT_NONE only ls_r is filled.
+            const MeshBuf<R>& m0 = w->mesh[mcur];
+            const ValBuf<R>& v0 = w->val[vcur];
+            MeshBuf<R>& m1 = w->mesh[mcur ^ 1];
+            ValBuf<R>& v1 = w->val[vcur ^ 1];
+            int action, kn;
+#pragma unroll 1
+            for (;;) {
+                int event;
+#pragma unroll 1
+                for (;;) {  // Categorical.rng: searchsorted(cumsum(p), U), re-drawn while illegal (:1041-1049)
+                    const R u = rng_uniform<R>(rng);
+                    event = (u <= K->cum0) ? 0 : (u <= K->cum1) ? 1 : (u <= K->cum2) ? 2 : 3;
+                    if (k == 1 && (event == 1 || event == 2)) continue;
+                    if (k == ml && event == 0) continue;
+                    break;
+                }
+                action = event;
+                kn = k;
+                if (event == ACT_NONE) {
+                    if (lane < k) w->ls_r[lane] = v0.ls[lane];
+                    break;
+                }
+                if (event == ACT_BIRTH) {  // :1061-1081
+                    bool ok = false;
+                    int pos = 0;
+                    R e = R(0);
+#pragma unroll 1
+                    for (int tries = 1; tries <= 10; ++tries) {
+                        e = rt<R>::exp(K->ln_min_edge + K->ln_edge_span * rng_uniform<R>(rng));
+                        pos = __popc(__ballot_sync(FULL, lane <= k && m0.edges[lane] < e));  // searchsorted (left)
+                        R d = INFINITY;  // widths after insertion: cell pos-1 is split in two
+                        if (lane < k)
+                            d = (lane == pos - 1) ? fmin(e - m0.edges[lane], m0.edges[lane + 1] - e)
+                                                  : m0.edges[lane + 1] - m0.edges[lane];
+                        const R h = warp_min(d);
+                        if (tries == 10) break;  // the 10th try always restarts (:1078-1080)
+                        if (h > K->min_width) {
+                            ok = true;
+                            break;
+                        }
+                    }
+                    if (!ok) continue;
+                    if (lane <= k + 1) m1.edges[lane] = (lane < pos) ? m0.edges[lane] : (lane == pos ? e : m0.edges[lane - 1]);
+                    if (lane <= k) {  // values.insert(pos, values[pos-1]) (:835)
+                        const int src = (lane < pos) ? lane : lane - 1;
+                        v1.sig[lane] = v0.sig[src];
+                        w->ls_r[lane] = v0.ls[src];
+                    }
+                    kn = k + 1;
+                    break;
+                }
+                if (event == ACT_DEATH) {  // :1083-1087, delete_edge :643-689
+                    const int i = (int)(rng_uniform<R>(rng) * (R)(k - 1)) + 1;
+                    if (lane <= k - 1) m1.edges[lane] = m0.edges[lane + (lane >= i ? 1 : 0)];
+                    if (lane < k - 1) {
+                        const int src = lane + (lane >= i ? 1 : 0);
+                        R s = v0.sig[src], l = v0.ls[src];
+                        if (lane == i - 1) {
+                            s = R(0.5) * (v0.sig[i - 1] + v0.sig[i]);
+                            l = rt<R>::log(s);
+                        }
+                        v1.sig[lane] = s;
+                        w->ls_r[lane] = l;
+                    }
+                    kn = k - 1;
+                    break;
+                }
+                {  // ACT_MOVE :1088-1118
+                    bool ok = false;
+                    int i = 1;
+                    R dz = R(0);
+#pragma unroll 1
+                    for (int tries = 1; tries <= 10; ++tries) {
+                        i = (int)(R(1) + ((R)k - R(1)) * rng_uniform<R>(rng));
+                        const R zn = rng_normal<R>(rng);
+                        const R sgn = (zn > R(0)) ? R(1) : (zn < R(0) ? R(-1) : R(0));
+                        dz = sgn * K->min_width * rng_uniform<R>(rng);
+                        R d = INFINITY;
+                        if (lane < k)
+                            d = (m0.edges[lane + 1] + (lane + 1 == i ? dz : R(0))) - (m0.edges[lane] + (lane == i ? dz : R(0)));
+                        const R h = warp_min(d);
+                        const R z1 = m0.edges[1] + (i == 1 ? dz : R(0));
+                        const R zl = m0.edges[k - 1] + (i == k - 1 ? dz : R(0));
+                        if (tries == 10) break;
+                        if (h > K->min_width && z1 > K->min_edge && zl < K->max_edge) {
+                            ok = true;
+                            break;
+                        }
+                    }
+                    if (!ok) continue;
+                    if (lane <= k) m1.edges[lane] = m0.edges[lane] + (lane == i ? dz : R(0));
+                    if (lane < k) {
+                        v1.sig[lane] = v0.sig[lane];
+                        w->ls_r[lane] = v0.ls[lane];
+                    }
+                    break;
                 }
             }
-            if (P.max_iterations > 0 && total >= P.max_iterations) go = false;
-        }
-        flush(dwell);
-        dwell = 0;
+            __syncwarp();
+            if (lane == 0) w->ctr[CT_ACT0 + action]++;
 
-        write_model(P.out.cur_sigma, P.out.cur_edges);
-        if (lane == 0) {
-            double* s = P.out.scalars + (size_t)chain * GBP_NSCALARS;
-#pragma unroll 1
-            for (int i = 0; i < GBP_NSCALARS; ++i) s[i] = 0.0;
-            s[GBP_S_ITER] = (double)iteration;
-            s[GBP_S_BURNED_IN] = burned_in;
-            s[GBP_S_BURNED_IN_ITER] = (double)burned_in_iter;
-            s[GBP_S_BEST_ITER] = (double)best_iter;
-            s[GBP_S_BEST_K] = best_k;
-            s[GBP_S_CUR_K] = k;
-            s[GBP_S_HALFSPACE] = sigma_ref;
-            s[GBP_S_FAILED] = failed ? 1.0 : 0.0;
-            s[GBP_S_N_ACCEPT] = (double)n_accept;
-            s[GBP_S_N_FORWARD] = (double)n_forward;
-            s[GBP_S_N_SENS] = (double)n_sens;
-            s[GBP_S_BEST_POSTERIOR] = (double)best_posterior;
-            s[GBP_S_CUR_REL] = (double)rel;
-            s[GBP_S_CUR_ADD] = (double)add;
-            s[GBP_S_CUR_MISFIT] = (double)misfit;
-            s[GBP_S_CUR_PRIOR] = (double)prior;
-            s[GBP_S_CUR_LIKELIHOOD] = (double)likelihood;
-            s[GBP_S_BEST_REL] = (double)best_rel;
-            s[GBP_S_BEST_ADD] = (double)best_add;
-            s[GBP_S_N_RESETS] = n_resets;
-            s[GBP_S_N_BIRTH] = (double)n_act[0];
-            s[GBP_S_N_DEATH] = (double)n_act[1];
-            s[GBP_S_N_MOVE] = (double)n_act[2];
-            s[GBP_S_N_NONE] = (double)n_act[3];
+            // ---- Model.stochastic_newton_perturbation :368-419
+            const bool changed = action != ACT_NONE;
+            const int mp = changed ? (mcur ^ 1) : mcur;  // proposed mesh buffer
+            const int vp = vcur ^ 1;                     // proposed values buffer
+            MeshBuf<R>& mesh_p = w->mesh[mp];
+            ValBuf<R>& val_p = w->val[vp];
+            const T* Jh = w->J[jcur];
+            const T* ph = w->pred[pcur];
+            T* pred_t = w->pred[pcur ^ 1];
+            T* J_t = w->J[jcur ^ 1];
+            if (changed) {  // observation.fm_dlogc(remapped_model): J and predicted data of the test datapoint
+                ch_mesh_setup(K, kn, &mesh_p);
+                ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, J_t);
+                Jh = J_t;
+                ph = pred_t;
+            }
+            ch_set_ivar(w, C, rel, add);
+            const R ln_r = (lane < kn) ? w->ls_r[lane] : R(0);
+            const R g = ch_gradient(w, K, kn, mesh_p.t2, w->ls_r, Jh, ph, ln_ref);
+            ch_assemble(w, K, kn, mesh_p.t2, Jh);
+            if (!ch_cholesky(w->A, kn)) {
+                chol_failed = true;
+            } else {
+                const R stepv = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g));  // H * dfk
+                const R mean = ln_r - K->alpha * stepv;  // ln sigma + alpha * pk, pk = -H dfk
+                // sigma' ~ exp(N(mean, H)),  H = (L L')^-1  ->  mean + L^-T z
+                pair_t<R> zz = {R(0), R(0)};
+                const int npair = (kn + 1) / 2;
+                if (lane < npair) zz = normal2_at<R>(rng.block + (uint32_t)lane, rng.snd_lo, rng.snd_hi, rng.seed_lo, rng.seed_hi);
+                rng.block += (uint32_t)npair;
+                const R za = __shfl_sync(FULL, zz.a, lane >> 1), zb = __shfl_sync(FULL, zz.b, lane >> 1);
+                const R zi = (lane < kn) ? ((lane & 1) ? zb : za) : R(0);
+                const R ln_t = mean + ch_solve_LT(w->A, kn, zi);
+                if (lane < kn) {
+                    val_p.ls[lane] = ln_t;
+                    val_p.sig[lane] = rt<R>::exp(ln_t);
+                }
+                __syncwarp();
+
+                // ---- test_datapoint.perturb() (DataPoint.py:531-573)
+                R lr_t = ln_rel, la_t = ln_add;
+                if (K->solve_rel) {
+                    const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_rel, K->rel_sd, K->rel_lnmin, K->rel_lnmax);
+                    lr_t = pr.x;
+                    rng.block = pr.block;
+                }
+                if (K->solve_add) {
+                    const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_add, K->add_sd, K->add_lnmin, K->add_lnmax);
+                    la_t = pr.x;
+                    rng.block = pr.block;
+                }
+                const R rel_t = (lr_t == ln_rel) ? rel : rt<R>::exp(lr_t);
+                const R add_t = (la_t == ln_add) ? add : rt<R>::exp(la_t);
+
+                const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
+                // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
+                // (Model.proposal_probabilities :619) - fused into the same pass.
+                ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : (T*)nullptr);
+                ch_set_ivar(w, C, rel_t, add_t);
+                const pair_t<R> tml = ch_misfit_like(w, C, nahl, pred_t);
+                // error priors: the proposals above are forced inside their bounds (or fall back to the
+                // current values), so DataPoint.probability is the constant rel_lp + add_lp
+                R t_prior = R(0);
+                if (K->solve_rel) t_prior += K->rel_lp;
+                if (K->solve_add) t_prior += K->add_lp;
+                t_prior += ch_model_prob(K, kn, val_p.ls, mesh_p.lnh, ln_ref);
+                if (t_prior != (R)-INFINITY) {  // early reject on -inf prior (:581, :589): no accept draw
+                    R proposal = R(1), proposal1 = R(1);
+                    if (jump) {
+                        const R g2 = ch_gradient(w, K, kn, mesh_p.t2, val_p.ls, J_t, pred_t, ln_ref);
+                        const R s2 = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g2));  // H dfk'
+                        const R lv = ln_t + K->alpha * s2;  // Model.py:626 (sign as in the reference)
+                        const R mv = rt<R>::exp(lv);
+                        const int bad = __any_sync(FULL, lane < kn && (mv == (R)INFINITY || mv == R(0)));
+                        const R q_r = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_r - lv) : R(0));
+                        const R q_f = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_t - ln_r) : R(0));
+                        const R logdetL = warp_sum((lane < kn) ? rt<R>::log(w->A[pk(lane, lane)]) : R(0));
+                        if (bad) {
+                            proposal = (R)-INFINITY;
+                            proposal1 = (R)-INFINITY;
+                        } else {
+                            proposal = -(R)kn * K->half_log2pi + logdetL - R(0.5) * q_r;
+                            proposal1 = -(R)kn * K->half_log2pi + logdetL - R(0.5) * q_f;
+                        }
+                    }
+                    const R log_alpha = (t_prior - prior) + (tml.b - likelihood) + (proposal - proposal1);
+                    const R u = rng_uniform<R>(rng);
+                    accepted = rt<R>::exp(log_alpha) > u;
+                    if (accepted) {
+                        ch_flush(w, K, k, mcur, vcur, ln_rel, ln_add, sig_lo, dwell);  // the outgoing model's visits
+                        dwell = 0;
+                        misfit = tml.a;
+                        prior = t_prior;
+                        likelihood = tml.b;
+                        k = kn;
+                        rel = rel_t;
+                        add = add_t;
+                        ln_rel = lr_t;
+                        ln_add = la_t;
+                        mcur = mp;
+                        vcur = vp;
+                        pcur ^= 1;
+                        if (changed) jcur ^= 1;  // action none keeps the (stale) Jacobian, as the reference does
+                        if (lane == 0) w->ctr[CT_N_ACCEPT]++;
+                    }
+                }
+            }
         }
-        __syncwarp();
+        failed = chol_failed;
+
+        // ==================================================== Inference1D.update :705-790
+        bool do_reset = false;
+        iteration++;
+        {
+            double* mt = (double*)w->outp[OP_MISFIT];
+            if (mt && lane == 0 && iteration - 1 < N2) mt[iteration - 1] = (double)misfit;
+        }
+        if (!burned_in && iteration > K->burn_min && misfit < (R)n_active) {
+            burned_in = 1;
+            if (lane == 0) w->ctr[CT_BURN_ITER] = iteration;
+            save_best();
+            ch_zero_posteriors(w, K);
+            dwell = 0;
+        }
+        if (likelihood + prior > w->bestv[BV_POSTERIOR]) save_best();
+        {
+            uint8_t* at = (uint8_t*)w->outp[OP_ACCEPT];
+            if (at && lane == 0 && iteration < N2) at[iteration] = accepted ? 1 : 0;
+        }
+        {
+            // acceptance over acceptance_v[it-upe : it] (Inference1D.py:125-131): excludes this iteration
+            int to_plot = w->ctr[CT_TO_PLOT] - 1;
+            int win = w->ctr[CT_ACC_WIN];
+            __syncwarp();
+            if (to_plot == 0) {
+                to_plot = K->upe;
+                if (K->upe > 1) {
+                    if (!burned_in) {
+                        if (win == 0) {
+                            int nz = w->ctr[CT_N_ZERO] + 1;
+                            if (nz == K->reset_limit) {
+                                do_reset = true;
+                                nz = 0;
+                            }
+                            __syncwarp();
+                            if (lane == 0) w->ctr[CT_N_ZERO] = nz;
+                        } else if (lane == 0) w->ctr[CT_N_ZERO] = 0;
+                    } else if (win == 0 && lane == 0) w->ctr[CT_LIMITERS] = 0;
+                }
+                win = 0;
+            }
+            win += accepted ? 1 : 0;
+            if (lane == 0) {
+                w->ctr[CT_TO_PLOT] = to_plot;
+                w->ctr[CT_ACC_WIN] = win;
+            }
+            __syncwarp();
+        }
+        if (!do_reset) dwell++;
+
+        // ==================================================== Inference1D.infer :650-677 (loop control)
+        total++;
+        if (do_reset) {
+            int nr = w->ctr[CT_N_RESETS] + 1;
+            __syncwarp();
+            if (lane == 0) w->ctr[CT_N_RESETS] = nr;
+            initialize(false);
+            dwell = 1;  // update() goes on to accumulate the re-initialised model
+        }
+        const int burn_iter = w->ctr[CT_BURN_ITER];
+        go = !failed && (iteration <= N + burn_iter);
+        if (!failed && !burned_in) {
+            go = iteration < N;
+            if (!go) failed = true;
+        }
+        if (w->ctr[CT_N_RESETS] == 3 && !burned_in) {
+            const int lim = w->ctr[CT_LIMITERS];
+            __syncwarp();
+            if (!lim) {
+                if (lane == 0) {
+                    w->ctr[CT_LIMITERS] = 1;
+                    w->ctr[CT_N_RESETS] = 1;
+                }
+                initialize(false);
+            } else {
+                go = false;
+                failed = true;
+            }
+        }
+        if (P.max_iterations > 0 && total >= P.max_iterations) go = false;
     }
-};
+    ch_flush(w, K, k, mcur, vcur, ln_rel, ln_add, sig_lo, dwell);
+
+    ch_write_model(w, ml, k, mcur, vcur, P.out.cur_sigma ? P.out.cur_sigma + (size_t)chain * ml : nullptr,
+                   P.out.cur_edges ? P.out.cur_edges + (size_t)chain * (ml + 1) : nullptr);
+    if (lane == 0) {
+        double* s = P.out.scalars + (size_t)chain * GBP_NSCALARS;
+#pragma unroll 1
+        for (int i = 0; i < GBP_NSCALARS; ++i) s[i] = 0.0;
+        s[GBP_S_ITER] = (double)iteration;
+        s[GBP_S_BURNED_IN] = burned_in;
+        s[GBP_S_BURNED_IN_ITER] = (double)w->ctr[CT_BURN_ITER];
+        s[GBP_S_BEST_ITER] = (double)w->ctr[CT_BEST_ITER];
+        s[GBP_S_BEST_K] = w->ctr[CT_BEST_K];
+        s[GBP_S_CUR_K] = k;
+        s[GBP_S_HALFSPACE] = sigma_ref;
+        s[GBP_S_FAILED] = failed ? 1.0 : 0.0;
+        s[GBP_S_N_ACCEPT] = (double)w->ctr[CT_N_ACCEPT];
+        s[GBP_S_N_FORWARD] = (double)w->ctr[CT_N_FWD];
+        s[GBP_S_N_SENS] = (double)w->ctr[CT_N_SENS];
+        s[GBP_S_BEST_POSTERIOR] = (double)w->bestv[BV_POSTERIOR];
+        s[GBP_S_CUR_REL] = (double)rel;
+        s[GBP_S_CUR_ADD] = (double)add;
+        s[GBP_S_CUR_MISFIT] = (double)misfit;
+        s[GBP_S_CUR_PRIOR] = (double)prior;
+        s[GBP_S_CUR_LIKELIHOOD] = (double)likelihood;
+        s[GBP_S_BEST_REL] = (double)w->bestv[BV_REL];
+        s[GBP_S_BEST_ADD] = (double)w->bestv[BV_ADD];
+        s[GBP_S_N_RESETS] = w->ctr[CT_N_RESETS];
+        s[GBP_S_N_BIRTH] = (double)w->ctr[CT_ACT0];
+        s[GBP_S_N_DEATH] = (double)w->ctr[CT_ACT1];
+        s[GBP_S_N_MOVE] = (double)w->ctr[CT_ACT2];
+        s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
+    }
+    __syncwarp();
+}
 
 // ---------------------------------------------------------------- kernels
 // R = sampler arithmetic, T = forward/Jacobian arithmetic, NC = channel capacity, WARPS = warps per CTA
@@ -932,7 +1063,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     T* tab = reinterpret_cast<T*>(smem);
     const uint32_t tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
     if (threadIdx.x == 0) {
-        make_consts<R>(P.opt, P.n_depth, consts);
+        make_consts<R>(P.opt, P.n_depth, P.C, consts);
         fill_sys_shared<T>(S, sys_s);
     }
     tma_stage(tab, g_tab, tab_bytes, &bar);
@@ -940,13 +1071,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     const uint32_t tab_pad = (tab_bytes + 127u) & ~127u;
     const int warp = threadIdx.x >> 5;
     WarpState<R, T, NC>* ws = reinterpret_cast<WarpState<R, T, NC>*>(smem + tab_pad) + warp;
-    Chain<R, T, NC> ch(*ws, consts, sys_s, tab, P);
     // persistent: the first wave is assigned statically, later chains come from a device-side counter
     int c = blockIdx.x * WARPS + warp;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     while (c < P.B) {
-        ch.run(c);
+        run_chain<R, T, NC>(ws, &consts, &sys_s, tab, P, c);
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(P.work_counter, 1);
         c = __shfl_sync(FULL, nxt, 0);

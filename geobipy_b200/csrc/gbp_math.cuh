@@ -106,14 +106,15 @@ __device__ __forceinline__ int warp_sum_i(int v)
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
+// Everything by value so that the generator state stays in registers: key = 64-bit seed,
+// counter = (block, 0, sounding lo, sounding hi).  A chain draws far fewer than 2^32 blocks.
 struct Rng {
     uint32_t seed_lo, seed_hi, snd_lo, snd_hi;
-    unsigned long long block;
+    uint32_t block;
 };
-__device__ __noinline__ void philox_block(const Rng& g, unsigned long long block, uint32_t out[4])
+__device__ __noinline__ uint4 philox4(uint32_t c0, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
-    uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = g.snd_lo, c3 = g.snd_hi;
-    uint32_t k0 = g.seed_lo, k1 = g.seed_hi;
+    uint32_t c1 = 0u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -123,48 +124,45 @@ __device__ __noinline__ void philox_block(const Rng& g, unsigned long long block
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
 }
 // one block -> two uniforms in [0,1): 53-bit for double, 24-bit for float
-template <typename R> __device__ __forceinline__ void uniforms_at(const Rng& g, unsigned long long block, R* ua, R* ub);
-template <> __device__ __forceinline__ void uniforms_at<double>(const Rng& g, unsigned long long block, double* ua, double* ub)
+template <typename R> __device__ __forceinline__ void uniforms_of(uint4 x, R* ua, R* ub);
+template <> __device__ __forceinline__ void uniforms_of<double>(uint4 x, double* ua, double* ub)
 {
-    uint32_t x[4];
-    philox_block(g, block, x);
-    *ua = ((double)(x[0] >> 5) * 67108864.0 + (double)(x[1] >> 6)) * (1.0 / 9007199254740992.0);
-    *ub = ((double)(x[2] >> 5) * 67108864.0 + (double)(x[3] >> 6)) * (1.0 / 9007199254740992.0);
+    *ua = ((double)(x.x >> 5) * 67108864.0 + (double)(x.y >> 6)) * (1.0 / 9007199254740992.0);
+    *ub = ((double)(x.z >> 5) * 67108864.0 + (double)(x.w >> 6)) * (1.0 / 9007199254740992.0);
 }
-template <> __device__ __forceinline__ void uniforms_at<float>(const Rng& g, unsigned long long block, float* ua, float* ub)
+template <> __device__ __forceinline__ void uniforms_of<float>(uint4 x, float* ua, float* ub)
 {
-    uint32_t x[4];
-    philox_block(g, block, x);
-    *ua = (float)(x[0] >> 8) * (1.0f / 16777216.0f);
-    *ub = (float)(x[2] >> 8) * (1.0f / 16777216.0f);
+    *ua = (float)(x.x >> 8) * (1.0f / 16777216.0f);
+    *ub = (float)(x.z >> 8) * (1.0f / 16777216.0f);
 }
 template <typename R> __device__ __forceinline__ R rng_uniform(Rng& g)
 {
     R a, b;
-    uniforms_at<R>(g, g.block, &a, &b);
+    uniforms_of<R>(philox4(g.block, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi), &a, &b);
     g.block++;
     return a;
 }
 // Box-Muller pair of the block at an explicit counter
-template <typename R> __device__ __noinline__ void normal2_at(const Rng& g, unsigned long long block, R* z0, R* z1)
+template <typename R> struct pair_t {
+    R a, b;
+};
+template <typename R> __device__ __noinline__ pair_t<R> normal2_at(uint32_t block, uint32_t snd_lo, uint32_t snd_hi, uint32_t k0, uint32_t k1)
 {
     R a, b;
-    uniforms_at<R>(g, block, &a, &b);
+    uniforms_of<R>(philox4(block, snd_lo, snd_hi, k0, k1), &a, &b);
     const R r = rt<R>::sqrt(R(-2) * rt<R>::log(R(1) - a));
     R s, c;
     rt<R>::sincos(R(6.283185307179586476925286766559) * b, &s, &c);
-    *z0 = r * c;
-    *z1 = r * s;
+    return pair_t<R>{r * c, r * s};
 }
 template <typename R> __device__ __forceinline__ R rng_normal(Rng& g)
 {
-    R z0, z1;
-    normal2_at<R>(g, g.block, &z0, &z1);
+    const pair_t<R> z = normal2_at<R>(g.block, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
     g.block++;
-    return z0;
+    return z.a;
 }
 
 }  // namespace gbp
