@@ -28,6 +28,7 @@
 //    from the constant bank; cold per-chain counters live in shared memory.
 #pragma once
 #include "gbp_fdem.cuh"
+#include "gbp_fdem_f2.cuh"
 
 namespace gbp {
 
