@@ -125,6 +125,9 @@ int launch_fdem(TableCache* tc, int B, int l_stride, const int32_t* nl, const do
     return time_end(st);
 }
 
+void* g_jstore[64] = {nullptr};
+size_t g_jstore_cap[64] = {0};
+
 template <typename R, typename T, int NC, int WARPS>
 int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
 {
@@ -137,11 +140,22 @@ int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
     if (smem + 2048 > (size_t)max_smem) return fail("rjmcmc kernel does not fit in shared memory on this device");
     auto kern = rjmcmc_kernel<R, T, NC, WARPS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // per-chain Jacobian mirror (L2 resident: 1.4 KB per chain in fp32)
+    const size_t jbytes = (size_t)P.B * NC * KS * sizeof(T);
+    if (dev < 0 || dev >= 64) return fail("device index out of range");
+    if (g_jstore_cap[dev] < jbytes) {
+        if (g_jstore[dev]) CK(cudaFree(g_jstore[dev]));
+        g_jstore[dev] = nullptr;
+        g_jstore_cap[dev] = 0;
+        CK(cudaMalloc(&g_jstore[dev], jbytes));
+        g_jstore_cap[dev] = jbytes;
+    }
     int grid = sm_count();
     const int need = (P.B + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     ChainParams Q = P;
     Q.n_warps_total = grid * WARPS;
+    Q.jstore = g_jstore[dev];
     // device-side work counter: chains beyond the first wave are claimed dynamically
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
     if (time_begin(st)) return 1;

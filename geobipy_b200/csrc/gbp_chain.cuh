@@ -57,7 +57,7 @@ template <typename R, typename T, int NC> struct __align__(16) WarpState {
     R ls_r[GBP_MAXL];       // ln(sigma) of the remapped model
     R vec[GBP_MAXL + 2];
     R data[NC], ivar[NC];   // observed data (0 where inactive), 1/variance (0 where inactive)
-    T J[2][NC * KS];
+    alignas(16) T J[NC * KS];  // working Jacobian; the current model's Jacobian is mirrored in HBM/L2 (ChainParams.jstore)
     T pred[2][NC];
     T msig[KS], mthk[KS];
     int sbin[GBP_MAXL + 2];
@@ -91,6 +91,7 @@ struct ChainParams {
     long long max_iterations;
     gbp_chain_buffers out;
     int* work_counter;
+    void* jstore;            // [B][NC*KS] of T: Jacobian of each chain's current model
 };
 
 template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c)
@@ -529,6 +530,16 @@ __device__ __noinline__ void ch_write_model(WarpState<R, T, NC>* w, int ml, int 
     }
 }
 
+// 16-byte vectorised copy of nbytes (multiple of 16) by one warp
+__device__ __noinline__ void ch_copy16(void* dst, const void* src, int nbytes)
+{
+    const int4* s4 = (const int4*)src;
+    int4* d4 = (int4*)dst;
+#pragma unroll 1
+    for (int i = lane_id(); i < nbytes / 16; i += 32) d4[i] = s4[i];
+    __syncwarp();
+}
+
 template <typename R> struct init_out {
     R ln_ref, misfit, likelihood, prior;
     double sigma_ref;
@@ -576,7 +587,7 @@ __device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC>* w, const 
         v.ls[0] = io.ln_ref;
     }
     __syncwarp();
-    ch_forward(w, S, tab, alt, 1, v.sig, m.edges, w->pred[0], w->J[0]);
+    ch_forward(w, S, tab, alt, 1, v.sig, m.edges, w->pred[0], w->J);
     if (!first) {  // reset(): posteriors and traces are re-created
         ch_zero_posteriors(w, K);
         const long long N2 = 2 * (long long)K->n_chains;
@@ -644,7 +655,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
     const int C = K->C;
     const int ml = K->kmax;
     const int N = K->n_chains;
-    const long long N2 = 2 * (long long)N;
+#define N2 (2 * (long long)N)
 
     // ---- hot state (registers)
     Rng rng;
@@ -657,7 +668,10 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
     }
     rng.block = 0u;
     const T alt = (T)P.altitude[chain];
-    int k = 1, mcur = 0, vcur = 0, jcur = 0, pcur = 0;
+    int k = 1, mcur = 0, vcur = 0, pcur = 0;
+    bool j_valid = true;  // the shared-memory Jacobian is the current model's
+    T* const jg = (T*)P.jstore + (size_t)chain * NC * KS;
+    constexpr int JBYTES = NC * KS * (int)sizeof(T);
     R ln_rel, ln_add, rel, add, ln_ref = R(0), sig_lo = R(0);
     double sigma_ref = 0.0;
     R misfit = R(0), prior = R(0), likelihood = R(0);
@@ -684,13 +698,15 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         for (int i = 0; i < CT_N; ++i) w->ctr[i] = 0;
     }
     __syncwarp();
-    double* const best_sig_out = P.out.best_sigma ? P.out.best_sigma + (size_t)chain * ml : nullptr;
-    double* const best_edg_out = P.out.best_edges ? P.out.best_edges + (size_t)chain * (ml + 1) : nullptr;
+#define GBP_BEST_SIG (P.out.best_sigma ? P.out.best_sigma + (size_t)chain * ml : nullptr)
+#define GBP_BEST_EDG (P.out.best_edges ? P.out.best_edges + (size_t)chain * (ml + 1) : nullptr)
 
     // Inference1D.initialize :353-464 (also used by reset() :984-999): cold, one shared copy
     auto initialize = [&](bool first) {
-        const init_out<R> io = ch_initialize<R, T, NC>(w, K, S, tab, alt, nahl, first, best_sig_out, best_edg_out);
-        mcur = vcur = jcur = pcur = 0;
+        const init_out<R> io = ch_initialize<R, T, NC>(w, K, S, tab, alt, nahl, first, GBP_BEST_SIG, GBP_BEST_EDG);
+        mcur = vcur = pcur = 0;
+        ch_copy16(jg, w->J, JBYTES);
+        j_valid = true;
         ln_rel = K->rel_ln0;
         ln_add = K->add_ln0;
         rel = K->rel0;
@@ -707,14 +723,14 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         dwell = 0;
     };
     auto save_best = [&]() {
-        ch_save_best<R, T, NC>(w, ml, k, mcur, vcur, iteration, likelihood + prior, rel, add, best_sig_out, best_edg_out);
+        ch_save_best<R, T, NC>(w, ml, k, mcur, vcur, iteration, likelihood + prior, rel, add, GBP_BEST_SIG, GBP_BEST_EDG);
     };
 
     initialize(true);
 
     bool failed = (n_active == 0);
     bool go = !failed;
-    long long total = 0;
+    int total = 0;
 #pragma unroll 1
     while (go) {
         // ==================================================== Inference1D.accept_reject :537-631
@@ -830,15 +846,18 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
             const int vp = vcur ^ 1;                     // proposed values buffer
             MeshBuf<R>& mesh_p = w->mesh[mp];
             ValBuf<R>& val_p = w->val[vp];
-            const T* Jh = w->J[jcur];
             const T* ph = w->pred[pcur];
             T* pred_t = w->pred[pcur ^ 1];
-            T* J_t = w->J[jcur ^ 1];
+            T* const Jh = w->J;
+            T* const J_t = w->J;
             if (changed) {  // observation.fm_dlogc(remapped_model): J and predicted data of the test datapoint
                 ch_mesh_setup(K, kn, &mesh_p);
                 ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, J_t);
-                Jh = J_t;
+                j_valid = false;
                 ph = pred_t;
+            } else if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
+                ch_copy16(w->J, jg, JBYTES);
+                j_valid = true;
             }
             ch_set_ivar(w, C, rel, add);
             const R ln_r = (lane < kn) ? w->ls_r[lane] : R(0);
@@ -926,7 +945,10 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
                         mcur = mp;
                         vcur = vp;
                         pcur ^= 1;
-                        if (changed) jcur ^= 1;  // action none keeps the (stale) Jacobian, as the reference does
+                        if (changed) {  // action none keeps the (stale) Jacobian, as the reference does
+                            ch_copy16(jg, w->J, JBYTES);
+                            j_valid = true;
+                        }
                         if (lane == 0) w->ctr[CT_N_ACCEPT]++;
                     }
                 }
@@ -1049,6 +1071,9 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
     }
     __syncwarp();
+#undef N2
+#undef GBP_BEST_SIG
+#undef GBP_BEST_EDG
 }
 
 // ---------------------------------------------------------------- kernels
