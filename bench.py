@@ -62,7 +62,7 @@ def _cpu_chain(job):
     import oracle_py as O
     idx, data, alt, chains, max_it = job
     r = O.run_chain(O.make_system(), O.resolve_options(n_markov_chains=chains), data, alt, SEED, idx, max_iterations=max_it)
-    return float(r["scalars"][O.S_ITER])
+    return float(r["scalars"][O.S_TOTAL_ITER])
 
 
 def _observed_cpu(n):
@@ -218,7 +218,7 @@ def run_b200_arm(args):
         r = ops.rjmcmc_run(system, opt, d_data, t_alt, seed=SEED + i, first_index=first, precision=args.precision,
                            outputs=outputs, buffers=buffers)
         if count:
-            iters_dev.add_(r["scalars"][:, _lib.S_ITER].sum())
+            iters_dev.add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
         return r
 
     def barrier():
@@ -245,7 +245,7 @@ def run_b200_arm(args):
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     iters = iters_dev.clone().reshape(1)
     last_kernel_ms = ops.last_kernel_ms()
-    last_iters = float(res["scalars"][:, _lib.S_ITER].sum().item())
+    last_iters = float(res["scalars"][:, _lib.S_TOTAL_ITER].sum().item())
     n_fwd = float(res["scalars"][:, _lib.S_N_FORWARD].sum().item())
     n_sens = float(res["scalars"][:, _lib.S_N_SENS].sum().item())
     mean_k = float((res["ncells_hist"].sum(dim=0).double() * torch.arange(opt.max_layers + 1, device=dev)).sum().item()
@@ -294,7 +294,7 @@ def run_b200_arm(args):
         for i in range(n_e2e):
             r = ops.rjmcmc_run(system, opt, h_data, h_alt, seed=SEED + i, first_index=first, precision=args.precision,
                                device=local_rank, outputs=outputs, buffers=hb)
-            e_iters += float(r["scalars"][:, _lib.S_ITER].sum())
+            e_iters += float(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
         torch.cuda.synchronize()
         el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         ei = torch.tensor([e_iters], dtype=torch.float64, device=dev)

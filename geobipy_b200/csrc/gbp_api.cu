@@ -151,8 +151,7 @@ int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
         g_jstore_cap[dev] = jbytes;
     }
     int grid = sm_count();
-    const int need = (P.B + WARPS - 1) / WARPS;
-    if (grid > need) grid = need;
+    if (grid > P.B) grid = P.B;
     ChainParams Q = P;
     Q.n_warps_total = grid * WARPS;
     Q.jstore = g_jstore[dev];

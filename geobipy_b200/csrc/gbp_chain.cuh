@@ -1069,6 +1069,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         s[GBP_S_N_DEATH] = (double)w->ctr[CT_ACT1];
         s[GBP_S_N_MOVE] = (double)w->ctr[CT_ACT2];
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
+        s[GBP_S_TOTAL_ITER] = (double)total;
     }
     __syncwarp();
 #undef N2
@@ -1097,8 +1098,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     const uint32_t tab_pad = (tab_bytes + 127u) & ~127u;
     const int warp = threadIdx.x >> 5;
     WarpState<R, T, NC>* ws = reinterpret_cast<WarpState<R, T, NC>*>(smem + tab_pad) + warp;
-    // persistent: the first wave is assigned statically, later chains come from a device-side counter
-    int c = blockIdx.x * WARPS + warp;
+    // persistent: the first wave is dealt round-robin over the CTAs (one CTA per SM) so that a batch smaller
+    // than the machine still spreads evenly; later chains are claimed from a device-side counter
+    int c = warp * gridDim.x + blockIdx.x;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     while (c < P.B) {

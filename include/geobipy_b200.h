@@ -74,6 +74,7 @@ enum {
     GBP_S_HALFSPACE, GBP_S_FAILED, GBP_S_N_ACCEPT, GBP_S_N_FORWARD, GBP_S_N_SENS, GBP_S_BEST_POSTERIOR,
     GBP_S_CUR_REL, GBP_S_CUR_ADD, GBP_S_CUR_MISFIT, GBP_S_CUR_PRIOR, GBP_S_CUR_LIKELIHOOD,
     GBP_S_BEST_REL, GBP_S_BEST_ADD, GBP_S_N_RESETS, GBP_S_N_BIRTH, GBP_S_N_DEATH, GBP_S_N_MOVE, GBP_S_N_NONE,
+    GBP_S_TOTAL_ITER,   /* accept_reject+update pairs executed, including those before a reset() */
     GBP_NSCALARS = 32
 };
 

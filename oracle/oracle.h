@@ -61,7 +61,7 @@ enum {
     GBO_S_ITER = 0, GBO_S_BURNED_IN, GBO_S_BURNED_IN_ITER, GBO_S_BEST_ITER, GBO_S_BEST_K, GBO_S_CUR_K,
     GBO_S_HALFSPACE, GBO_S_FAILED, GBO_S_N_ACCEPT, GBO_S_N_FORWARD, GBO_S_N_SENS, GBO_S_BEST_POSTERIOR,
     GBO_S_CUR_REL, GBO_S_CUR_ADD, GBO_S_CUR_MISFIT, GBO_S_CUR_PRIOR, GBO_S_CUR_LIKELIHOOD,
-    GBO_S_BEST_REL, GBO_S_BEST_ADD, GBO_S_N_RESETS, GBO_S_N_BIRTH, GBO_S_N_DEATH, GBO_S_N_MOVE, GBO_S_N_NONE,
+    GBO_S_BEST_REL, GBO_S_BEST_ADD, GBO_S_N_RESETS, GBO_S_N_BIRTH, GBO_S_N_DEATH, GBO_S_N_MOVE, GBO_S_N_NONE, GBO_S_TOTAL_ITER,
     GBO_NSCALARS = 32
 };
 

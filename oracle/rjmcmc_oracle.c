@@ -826,6 +826,7 @@ int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const doub
     s[GBO_S_N_DEATH] = (double)c->n_act[1];
     s[GBO_S_N_MOVE] = (double)c->n_act[2];
     s[GBO_S_N_NONE] = (double)c->n_act[3];
+    s[GBO_S_TOTAL_ITER] = (double)total;
     for (int i = 0; i < opt->max_layers; ++i) {
         out->best_sigma[i] = i < c->best_model.k ? c->best_model.sigma[i] : NAN;
         out->cur_sigma[i] = i < c->model.k ? c->model.sigma[i] : NAN;
