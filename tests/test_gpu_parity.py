@@ -259,6 +259,39 @@ def test_chain_fp32_statistics_match_oracle_ensemble(gpu, systems, oracle, golde
     assert inside.mean() >= 0.9
 
 
+def test_chain_fp32_matches_fp64_ensemble(gpu, systems, oracle):
+    """Production path (fp32 forward AND fp32 sampler arithmetic, MUFU log/exp, fp32 Cholesky) against the
+    fp64 instantiation (the oracle's trajectory twin) on the same soundings, 384 chains each.  The yardstick
+    is the fp64 path's own seed-to-seed scatter: the fp32-vs-fp64 discrepancy of every statistic must not
+    exceed 2.5x the discrepancy between two fp64 ensembles with different seeds (plus a small floor):
+    acceptance rate, mean layer count, layer-count distribution (total variation), and the posterior-mean
+    conductivity bin per depth cell over the top 60 m (RMS; bin width = 8 sigma_prior / 250 = 0.077 ln-units)."""
+    nrep = 384
+    for sidx in (1, 5):
+        data, alt = _observed(oracle, systems[1], 1, first=sidx)
+        d = np.tile(data, (nrep, 1))
+        a = np.full(nrep, alt[0])
+        opt = gpu.make_options(n_markov_chains=10000)
+        st = {}
+        for tag, prec, seed in (("f32", 32, 4242), ("f64", 64, 4242), ("f64b", 64, 777)):
+            r = gpu.rjmcmc_run(systems[0], opt, d, a, seed=seed, precision=prec, outputs=("hitmap", "ncells_hist", "scalars"))
+            sc = r["scalars"]
+            nc = r["ncells_hist"].sum(axis=0).astype(np.float64)
+            hm = r["hitmap"].sum(axis=0, dtype=np.int64)[:, :120].astype(np.float64)
+            st[tag] = dict(acc=sc[:, oracle.S_N_ACCEPT].sum() / sc[:, oracle.S_TOTAL_ITER].sum(), nc=nc / nc.sum(),
+                           kbar=(nc * np.arange(nc.size)).sum() / nc.sum(),
+                           mean_bin=(hm * np.arange(hm.shape[0])[:, None]).sum(axis=0) / hm.sum(axis=0))
+
+        def dist(x, y):
+            return dict(acc=abs(x["acc"] - y["acc"]), kbar=abs(x["kbar"] - y["kbar"]),
+                        tv=0.5 * np.abs(x["nc"] - y["nc"]).sum(),
+                        rms=float(np.sqrt(np.mean((x["mean_bin"] - y["mean_bin"]) ** 2))))
+        d32, d64 = dist(st["f32"], st["f64"]), dist(st["f64b"], st["f64"])
+        floor = dict(acc=0.01, kbar=0.05, tv=0.02, rms=0.25)
+        for key in floor:
+            assert d32[key] <= 2.5 * d64[key] + floor[key], (sidx, key, d32, d64)
+
+
 def test_full_size_properties(gpu, systems):
     """BASELINE config-2 batch size (4096 soundings) through size-independent invariants, device-pointer path."""
     import torch
