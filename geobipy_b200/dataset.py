@@ -1,0 +1,205 @@
+"""Survey-level input and output either side of the hot path.
+
+Input  : `FdemData.read_csv` reads a reference-format frequency-domain CSV (same header conventions as
+         geobipy/src/classes/data/dataset/FdemData.py:520-683, Data.py:488-528, pointcloud/Point.py:336-383)
+         into the batched device layout the sampler takes.
+Driver : `Inference3D` replaces the per-record loop of geobipy/src/inversion/Inference3D.py:458-492 - one
+         call inverts every sounding of the survey concurrently (optionally sharded over the GPUs of the
+         node, parallel.run_sharded) - and collects, per flight line, the arrays Inference1D.writeHdf
+         (:1050-1090) / Inference2D.createHdf (:2001-2016) store.
+Output : one `<line>.npz` per flight line with those arrays (h5py is not available in this image, so the
+         HDF5 container itself is not written; the array names follow the reference's dataset names), plus
+         the posterior summaries the reference derives afterwards: mean / median / 5-95 % credible interval
+         of conductivity with depth (Mesh._mean, Mesh._percentile, classes/mesh/Mesh.py:80, :173-217) and the
+         interface probability (Inference2D.interface_probability, Inference2D.py:959-961).
+"""
+import csv
+import os
+
+import numpy as np
+
+from . import _lib, api, ops
+
+__all__ = ["FdemData", "Inference3D"]
+
+_LINE = ("line", "linenumber", "line_number")
+_FID = ("fid", "fiducial", "id")
+_X = ("e", "x", "easting")
+_Y = ("n", "y", "northing")
+_Z = ("alt", "altitude", "laser", "bheight", "height")
+_ELEV = ("dtm", "dem_elev", "dem_np", "topo", "elev", "elevation")
+
+
+def _csv_channels(header):
+    """Column roles from the header, as the reference assigns them."""
+    roles = dict(line=None, fid=None, x=None, y=None, z=None, elev=None, inphase=[], quad=[], inerr=[], quaderr=[])
+    for ch in header:
+        c = ch.strip().lower()
+        if c in _LINE:
+            roles["line"] = ch
+        elif c in _FID:
+            roles["fid"] = ch
+        elif c in _X:
+            roles["x"] = ch
+        elif c in _Y:
+            roles["y"] = ch
+        elif c in _Z:
+            roles["z"] = ch
+        elif c in _ELEV:
+            roles["elev"] = ch
+        elif any(lbl in c for lbl in ("cpi", "i_", "in_phase")):
+            (roles["inerr"] if "err" in c else roles["inphase"]).append(ch)
+        elif any(lbl in c for lbl in ("cpq", "q_", "quad")):
+            (roles["quaderr"] if "err" in c else roles["quad"]).append(ch)
+    assert roles["line"] is not None and roles["fid"] is not None, Exception("File must contain columns for line and fiducial.")
+    assert None not in (roles["x"], roles["y"], roles["z"]), Exception(
+        "File must contain columns for easting, northing, height. May also have an elevation column")
+    return roles
+
+
+class FdemData:
+    """Whole-survey frequency-domain table (classes/data/dataset/FdemData.py, reader part)."""
+
+    def __init__(self, system=None):
+        if isinstance(system, str):
+            system = api.FdemSystem.read(system)
+        self.system = system
+        self.lineNumber = self.fiducial = self.x = self.y = self.z = self.elevation = None
+        self.data = self.std = None
+
+    @property
+    def nPoints(self):
+        return 0 if self.data is None else self.data.shape[0]
+
+    @property
+    def nChannels(self):
+        return 2 * self.system.nFrequencies
+
+    @classmethod
+    def read_csv(cls, dataFilename, system):
+        """Read a data file whose header names Line, Fiducial, Easting, Northing, Height[, Elevation] and one
+        in-phase + one quadrature column per frequency (any order; `*err*` columns are uncertainties)."""
+        self = cls(system=system)
+        with open(dataFilename, newline="") as f:
+            sample = f.readline()
+            f.seek(0)
+            delim = "," if "," in sample else None
+            if delim:
+                rows = list(csv.reader(f, skipinitialspace=True))
+            else:
+                rows = [ln.split() for ln in f if ln.strip()]
+        header, body = [h.strip() for h in rows[0]], [r for r in rows[1:] if len(r)]
+        roles = _csv_channels(header)
+        col = {h: i for i, h in enumerate(header)}
+
+        def num(name):
+            j = col[name]
+            return np.asarray([np.nan if r[j].strip().lower() == "nan" else float(r[j]) for r in body], dtype=np.float64)
+        self.lineNumber, self.fiducial = num(roles["line"]), num(roles["fid"])
+        self.x, self.y, self.z = num(roles["x"]), num(roles["y"]), num(roles["z"])
+        self.elevation = num(roles["elev"]) if roles["elev"] else np.zeros(len(body))
+        chans = roles["inphase"] + roles["quad"]
+        assert len(chans) == self.nChannels, ValueError(
+            "file has %d data channels, the system needs %d" % (len(chans), self.nChannels))
+        self.data = np.stack([num(c) for c in chans], axis=1)
+        errs = roles["inerr"] + roles["quaderr"]
+        self.std = np.stack([num(c) for c in errs], axis=1) if errs else 0.1 * self.data
+        return self
+
+    def datapoint(self, i):
+        return api.FdemDataPoint(x=self.x[i], y=self.y[i], z=self.z[i], elevation=self.elevation[i], data=self.data[i],
+                                 std=self.std[i], system=self.system, lineNumber=self.lineNumber[i], fiducial=self.fiducial[i])
+
+    def line(self, line_number):
+        return np.flatnonzero(self.lineNumber == line_number)
+
+    @property
+    def lines(self):
+        return np.unique(self.lineNumber)
+
+
+def _percentile_bins(hitmap, percent):
+    """First bin whose cumulative count reaches percent of the column total (Mesh._percentile)."""
+    cs = np.cumsum(hitmap, axis=-2, dtype=np.float64)
+    tot = np.maximum(cs[..., -1:, :], 1.0)
+    return np.minimum((cs < (percent / 100.0) * tot).sum(axis=-2), hitmap.shape[-2] - 1)
+
+
+def summarise(result, opt):
+    """Posterior summaries per sounding from the raw arrays of `ops.rjmcmc_run`:
+    conductivity mean / p5 / p50 / p95 per depth cell [B, n_depth] and interface probability [B, n_depth]."""
+    hm = np.asarray(result["hitmap"])
+    hs = np.asarray(result["scalars"])[:, _lib.S_HALFSPACE]
+    s = np.log(1.0 + opt.factor) * opt.sigma_bins_nstd
+    edges = np.linspace(-s, s, opt.n_sigma_bins + 1)[None, :] + np.log(hs)[:, None]   # ln sigma bin edges
+    centres = 0.5 * (edges[:, 1:] + edges[:, :-1])
+    h = hm.astype(np.float64)
+    tot = np.maximum(h.sum(axis=1), 1.0)
+    out = {"mean": np.exp((h * centres[:, :, None]).sum(axis=1) / tot)}
+    for p in (5.0, 50.0, 95.0):
+        idx = _percentile_bins(hm, p)
+        out["p%g" % p] = np.exp(np.take_along_axis(centres, idx, axis=1))
+    eh = np.asarray(result["edges_hist"]).astype(np.float64)
+    out["interface_probability"] = eh / np.maximum(eh.sum(axis=1, keepdims=True), 1.0)
+    out["depth_edges"] = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
+    return out
+
+
+class Inference3D:
+    """Survey driver: `Inference3D(data).infer(**options)` (inversion/Inference3D.py:451-492, :503-635)."""
+
+    def __init__(self, data, prng=None, seed=None, world=None):
+        assert isinstance(data, FdemData), TypeError("data must be a FdemData")
+        self.data = data
+        if seed is None:
+            seed = int(prng.integers(0, 2 ** 63 - 1)) if prng is not None else 0
+        self.seed = int(seed) & (2 ** 64 - 1)
+        self.results = None
+        self.options = None
+
+    def infer(self, index=None, fiducial=None, line_number=None, precision=_lib.PRECISION_F32, device=0,
+              max_iterations=0, sharded=False, **options):
+        """Invert every sounding (or the one selected by index / fiducial+line_number, as the reference's
+        `infer`).  Sounding i always uses random stream (seed, i)."""
+        d = self.data
+        if index is None and fiducial is not None:
+            index = int(np.flatnonzero((d.fiducial == fiducial) & ((d.lineNumber == line_number) if line_number is not None else True))[0])
+        sel = np.arange(d.nPoints) if index is None else np.atleast_1d(index)
+        opt = ops.make_options(**options)
+        self.options = opt
+        sysc = d.system.c_struct
+        if sharded:
+            from . import parallel
+            res = parallel.run_sharded(sysc, opt, d.data[sel], d.z[sel], seed=self.seed, precision=precision,
+                                       outputs=ops.DEFAULT_OUTPUTS, max_iterations=max_iterations)
+            if res is None:
+                return None
+            res = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
+        elif sel.size == d.nPoints:
+            res = ops.rjmcmc_run(sysc, opt, d.data, d.z, seed=self.seed, first_index=0, max_iterations=max_iterations,
+                                 precision=precision, device=device)
+        else:
+            parts = [ops.rjmcmc_run(sysc, opt, d.data[i:i + 1], d.z[i:i + 1], seed=self.seed, first_index=int(i),
+                                    max_iterations=max_iterations, precision=precision, device=device) for i in sel]
+            res = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+        res["index"] = sel
+        res.update({"summary_" + k: v for k, v in summarise(res, opt).items()})
+        self.results = res
+        return res
+
+    def save(self, directory):
+        """One `<line>.npz` per flight line (the reference writes one `<line>.h5` per line)."""
+        assert self.results is not None, "run infer() first"
+        os.makedirs(directory, exist_ok=True)
+        r, d = self.results, self.data
+        files = []
+        for ln in np.unique(d.lineNumber[r["index"]]):
+            m = d.lineNumber[r["index"]] == ln
+            idx = r["index"][m]
+            path = os.path.join(directory, "%s.npz" % (("%g" % ln)))
+            np.savez_compressed(
+                path, line_number=ln, fiducial=d.fiducial[idx], x=d.x[idx], y=d.y[idx], z=d.z[idx],
+                elevation=d.elevation[idx], data=d.data[idx],
+                **{k: (v[m] if isinstance(v, np.ndarray) and v.shape[:1] == m.shape else v) for k, v in r.items()})
+            files.append(path)
+        return files

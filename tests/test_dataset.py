@@ -1,0 +1,86 @@
+"""Survey-level reader / driver (geobipy_b200/dataset.py).  The CSV layout is the reference's
+(tests/data_checks/resolve_*_clean.csv, documentation_source/source/supplementary/data/resolve_*.csv)."""
+import os
+
+import numpy as np
+import pytest
+
+HEADER = ("Line_number,Fiducial,Easting,Northing,Height,Elevation,In_Phase_380.0,In_Phase_1776.0,In_Phase_3345.0,"
+          "In_Phase_8171.0,In_Phase_41020.0,In_Phase_129550.0,Quadrature_380.0,Quadrature_1776.0,Quadrature_3345.0,"
+          "Quadrature_8171.0,Quadrature_41020.0,Quadrature_129550.0")
+STM = ("freq, tor, tmom, tx, ty, tzoff, ror, rmom, rx, ry, rzoff\n380, z, 1, 0, 0, 0, z, 1, 7.93, 0, 0\n"
+       "1776, z, 1, 0, 0, 0, z, 1, 7.91, 0, 0\n3345, x, -1, 0, 0, 0, x, 1, 9.03, 0, 0\n8171, z, 1, 0, 0, 0, z, 1, 7.91, 0, 0\n"
+       "41020, z, 1, 0, 0, 0, z, 1, 7.91, 0, 0\n129550, z, 1, 0, 0, 0, z, 1, 7.89, 0, 0\n")
+
+
+def _write_survey(tmp_path, golden_dir, n=6):
+    g = np.load(os.path.join(golden_dir, "resolve_clean.npz"))
+    stm = tmp_path / "resolve.stm"
+    stm.write_text(STM)
+    rows = [HEADER]
+    for i in range(n):
+        line = 100.0 if i < n // 2 else 200.0
+        vals = [line, i, float(i), 0.0, 30.0, 0.0] + list(g["data"][0, i * 10])
+        rows.append(",".join(repr(float(v)) if j != 1 else str(int(v)) for j, v in enumerate(vals)))
+    rows[2] = rows[2].replace(rows[2].split(",")[8], "NaN")   # one missing channel
+    csvf = tmp_path / "resolve_glacial_clean.csv"
+    csvf.write_text("\n".join(rows) + "\n")
+    return str(csvf), str(stm), g
+
+
+def test_read_csv_reference_layout(tmp_path, golden_dir, built_lib):
+    from geobipy_b200.dataset import FdemData
+    csvf, stm, g = _write_survey(tmp_path, golden_dir)
+    d = FdemData.read_csv(csvf, stm)
+    assert d.nPoints == 6 and d.nChannels == 12 and d.data.shape == (6, 12)
+    assert list(d.lines) == [100.0, 200.0] and list(d.line(200.0)) == [3, 4, 5]
+    assert np.array_equal(d.fiducial, np.arange(6.0)) and np.all(d.z == 30.0) and np.all(d.elevation == 0.0)
+    assert np.isnan(d.data[1, 2]) and np.allclose(d.data[0], g["data"][0, 0])
+    assert np.allclose(d.std[0], 0.1 * d.data[0])             # FdemData.read_csv default when no error columns
+    dp = d.datapoint(3)
+    assert dp.fiducial == 3.0 and dp.lineNumber == 200.0 and dp.n_active_channels == 12
+    assert d.datapoint(1).n_active_channels == 11             # NaN channel is inactive (EmDataPoint.active)
+    with pytest.raises(AssertionError):                        # header without a fiducial column
+        bad = tmp_path / "bad.csv"
+        bad.write_text(HEADER.replace("Fiducial", "Foo") + "\n" + "0,0,0,0,30,0," + ",".join(["1"] * 12) + "\n")
+        FdemData.read_csv(str(bad), stm)
+
+
+def test_summaries_match_histogram_class(built_lib):
+    """dataset.summarise (batched) against api.Histogram (per sounding; mirrors Mesh._mean/_percentile)."""
+    from geobipy_b200 import api, dataset, ops, _lib
+    opt = ops.make_options()
+    rng = np.random.default_rng(1)
+    nd = ops.n_depth(opt)
+    hm = rng.integers(0, 30, (2, opt.n_sigma_bins, nd)).astype(np.int32)
+    sc = np.zeros((2, _lib.NSCALARS))
+    sc[:, _lib.S_HALFSPACE] = [0.01, 0.2]
+    res = dict(hitmap=hm, scalars=sc, edges_hist=rng.integers(0, 5, (2, nd)).astype(np.int32))
+    s = dataset.summarise(res, opt)
+    for b in range(2):
+        g = ops.posterior_grids(opt, sc[b, _lib.S_HALFSPACE])
+        h = api.Histogram(hm[b], g["sigma_edges"], g["depth_edges"], log_x=True)
+        assert np.allclose(s["mean"][b], h.mean()) and np.allclose(s["p50"][b], h.median())
+        assert np.allclose(s["p5"][b], h.percentile(5.0)) and np.allclose(s["p95"][b], h.percentile(95.0))
+        assert abs(s["interface_probability"][b].sum() - 1.0) < 1e-12
+
+
+@pytest.mark.gpu
+def test_inference3d_end_to_end(tmp_path, golden_dir, built_lib):
+    from geobipy_b200 import _lib
+    from geobipy_b200.dataset import FdemData, Inference3D
+    _lib.require_cuda()
+    csvf, stm, g = _write_survey(tmp_path, golden_dir)
+    d = FdemData.read_csv(csvf, stm)
+    inv = Inference3D(d, seed=5)
+    r = inv.infer(n_markov_chains=400, max_iterations=300)
+    assert r["hitmap"].shape == (6, 250, 440) and (r["scalars"][:, _lib.S_ITER] == 300).all()
+    assert r["summary_p50"].shape == (6, 440) and np.all(r["summary_p5"] <= r["summary_p95"])
+    one = Inference3D(d, seed=5).infer(index=4, n_markov_chains=400, max_iterations=300)
+    assert np.array_equal(one["hitmap"][0], r["hitmap"][4])       # (seed, sounding index) fixes the stream
+    byfid = Inference3D(d, seed=5).infer(fiducial=4.0, line_number=200.0, n_markov_chains=400, max_iterations=300)
+    assert np.array_equal(byfid["scalars"], one["scalars"])
+    files = inv.save(str(tmp_path / "out"))
+    assert [os.path.basename(f) for f in files] == ["100.npz", "200.npz"]
+    z = np.load(files[1])
+    assert z["hitmap"].shape == (3, 250, 440) and list(z["fiducial"]) == [3.0, 4.0, 5.0]
