@@ -6,7 +6,10 @@
 
 #define GBO_MAXL 64  /* max layers the oracle accepts */
 #define GBO_MAXF 16  /* max frequencies per system   */
-#define GBO_MAXC (2 * GBO_MAXF)
+#define GBO_MAXSYS 2      /* systems per datapoint (SkyTEM dual moment) */
+#define GBO_TD_NFREQ 32   /* spline nodes of the TDEM frequency-domain response */
+#define GBO_TD_MAXLAM 32  /* Hankel abscissae */
+#define GBO_MAXC 64       /* max data channels (FDEM: 2 x frequencies; TDEM: windows of all systems) */
 
 /* One FDEM acquisition system (one row per frequency of an .stm file,
  * geobipy/src/classes/system/FdemSystem.py:146-183).
@@ -38,16 +41,33 @@ typedef struct {
     int32_t n_err_bins;            /* 99 */
     double sigma_bins_nstd;        /* 4.0 */
     int32_t burn_in_min_iter;      /* 5000 (Inference1D.py:726) */
-    int32_t pad_;
+    int32_t n_systems;             /* 0/1: one system; 2: the *_2 fields below describe system 1 (skytem_options lists) */
+    double rel_init2, rel_min2, rel_max2, rel_prop_var2;
+    double add_init2, add_min2, add_max2, add_prop_var2;
 } gbo_options;
+
+/* One time-domain datapoint type = n_sys GA-AEM style systems sharing one transmitter/receiver geometry
+ * (TdemDataPoint with system=[SkytemHM.stm, SkytemLM.stm]).  Everything model independent is prebuilt by
+ * the caller (oracle_py.make_tdem_system): see tdem1d_oracle.c. */
+typedef struct {
+    int32_t n_sys, n_freq, n_lam, C;
+    int32_t n_win[GBO_MAXSYS];
+    int32_t pad_[2];
+    double freq[GBO_TD_NFREQ];        /* spline nodes [Hz], log spaced, shared by the systems */
+    double xi[GBO_TD_MAXLAM];         /* ln(lambda * ZH / 2), uniform */
+    double rx_dx, rx_dy, rx_dz;       /* receiver offset from the transmitter [m] (z up) */
+    double loop_radius;               /* ModellingLoopRadius */
+    double MR[GBO_MAXC * GBO_TD_NFREQ], MI[GBO_MAXC * GBO_TD_NFREQ]; /* [C][n_freq] window operator */
+    double t_centre[GBO_MAXC];        /* window centre times = off_time (TdemSystem_GAAEM.py:33) */
+} gbo_tdem_system;
 
 /* Everything one chain produces (caller allocates; sizes from gbo_sizes()). */
 typedef struct {
     int32_t *hitmap;        /* [n_sigma_bins][n_depth] */
     int32_t *edges_hist;    /* [n_depth] */
     int32_t *ncells_hist;   /* [max_layers + 1] */
-    int32_t *rel_hist;      /* [n_err_bins] */
-    int32_t *add_hist;      /* [n_err_bins] */
+    int32_t *rel_hist;      /* [n_systems][n_err_bins] */
+    int32_t *add_hist;      /* [n_systems][n_err_bins] */
     double *misfit_trace;   /* [2 * n_markov_chains] */
     uint8_t *accept_trace;  /* [2 * n_markov_chains] */
     double *best_sigma;     /* [max_layers] */
@@ -62,6 +82,7 @@ enum {
     GBO_S_HALFSPACE, GBO_S_FAILED, GBO_S_N_ACCEPT, GBO_S_N_FORWARD, GBO_S_N_SENS, GBO_S_BEST_POSTERIOR,
     GBO_S_CUR_REL, GBO_S_CUR_ADD, GBO_S_CUR_MISFIT, GBO_S_CUR_PRIOR, GBO_S_CUR_LIKELIHOOD,
     GBO_S_BEST_REL, GBO_S_BEST_ADD, GBO_S_N_RESETS, GBO_S_N_BIRTH, GBO_S_N_DEATH, GBO_S_N_MOVE, GBO_S_N_NONE, GBO_S_TOTAL_ITER,
+    GBO_S_CUR_REL2, GBO_S_CUR_ADD2, GBO_S_BEST_REL2, GBO_S_BEST_ADD2,   /* system 1 of a dual-moment datapoint */
     GBO_NSCALARS = 32
 };
 
@@ -73,6 +94,13 @@ int gbo_fdem_forward(const gbo_fdem_system *sys, double altitude, int L, const d
                      const double *thickness, double *out);
 int gbo_fdem_sensitivity(const gbo_fdem_system *sys, double altitude, int L, const double *sigma,
                          const double *thickness, double *J);
+
+int gbo_tdem_forward(const gbo_tdem_system *sys, double altitude, int L, const double *sigma,
+                     const double *thickness, double *out);
+int gbo_tdem_sensitivity(const gbo_tdem_system *sys, double altitude, int L, const double *sigma,
+                         const double *thickness, double *J);
+int gbo_tdem_frequency_response(const gbo_tdem_system *sys, double altitude, int L, const double *sigma,
+                                const double *thickness, double *S_re, double *S_im);
 
 /* Philox4x32-10 block (Salmon et al. 2011). */
 void gbo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
@@ -88,8 +116,8 @@ typedef struct {
     double edges[GBO_MAXL + 1];   /* edges of remapped == test model, edges[k] = inf */
     double sigma_remap[GBO_MAXL];
     double sigma_test[GBO_MAXL];
-    double rel_cur, add_cur;      /* errors of the current datapoint (used for the Hessian) */
-    double rel_test, add_test;    /* errors of the proposed datapoint */
+    double rel_cur[GBO_MAXSYS], add_cur[GBO_MAXSYS];    /* errors of the current datapoint (used for the Hessian) */
+    double rel_test[GBO_MAXSYS], add_test[GBO_MAXSYS];  /* errors of the proposed datapoint */
     double data[GBO_MAXC];        /* observed */
     double J_in[GBO_MAXC * GBO_MAXL];   /* stored Jacobian (row-major [C][k]) used when action == none */
     double pred_in[GBO_MAXC];           /* stored predicted data used when action == none */
@@ -102,10 +130,14 @@ typedef struct {
 } gbo_transition;
 
 int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *opt, gbo_transition *t);
+int gbo_eval_transition_tdem(const gbo_tdem_system *sys, const gbo_options *opt, gbo_transition *t);
 
 /* Full chain for one sounding.  Random stream: Philox4x32-10, key = (seed lo, seed hi),
  * counter = (block lo, block hi, sounding lo, sounding hi). */
 int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const double *data, double altitude,
                   uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out);
+/* Same sampler for a time-domain (dual moment) datapoint: data [C] = windows of system 0 then system 1. */
+int gbo_run_chain_tdem(const gbo_tdem_system *sys, const gbo_options *opt, const double *data, double altitude,
+                       uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out);
 
 #endif

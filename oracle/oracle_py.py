@@ -13,12 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libgbp_oracle.so")
 
 MAXL, MAXF = 64, 16
-MAXC = 2 * MAXF
+MAXC = 64
+MAXSYS, TD_NFREQ, TD_MAXLAM = 2, 32, 32
 NSCALARS = 32
 
 S_ITER, S_BURNED_IN, S_BURNED_IN_ITER, S_BEST_ITER, S_BEST_K, S_CUR_K, S_HALFSPACE, S_FAILED, S_N_ACCEPT, \
     S_N_FORWARD, S_N_SENS, S_BEST_POSTERIOR, S_CUR_REL, S_CUR_ADD, S_CUR_MISFIT, S_CUR_PRIOR, S_CUR_LIKELIHOOD, \
-    S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER = range(25)
+    S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER, \
+    S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2 = range(29)
 
 
 class FdemSystemC(ctypes.Structure):
@@ -41,7 +43,24 @@ class OptionsC(ctypes.Structure):
         ("add_init", ctypes.c_double), ("add_min", ctypes.c_double), ("add_max", ctypes.c_double),
         ("add_prop_var", ctypes.c_double),
         ("n_sigma_bins", ctypes.c_int32), ("n_err_bins", ctypes.c_int32), ("sigma_bins_nstd", ctypes.c_double),
-        ("burn_in_min_iter", ctypes.c_int32), ("pad_", ctypes.c_int32),
+        ("burn_in_min_iter", ctypes.c_int32), ("n_systems", ctypes.c_int32),
+        ("rel_init2", ctypes.c_double), ("rel_min2", ctypes.c_double), ("rel_max2", ctypes.c_double),
+        ("rel_prop_var2", ctypes.c_double),
+        ("add_init2", ctypes.c_double), ("add_min2", ctypes.c_double), ("add_max2", ctypes.c_double),
+        ("add_prop_var2", ctypes.c_double),
+    ]
+
+
+class TdemSystemC(ctypes.Structure):
+    """gbo_tdem_system"""
+    _fields_ = [
+        ("n_sys", ctypes.c_int32), ("n_freq", ctypes.c_int32), ("n_lam", ctypes.c_int32), ("C", ctypes.c_int32),
+        ("n_win", ctypes.c_int32 * MAXSYS), ("pad_", ctypes.c_int32 * 2),
+        ("freq", ctypes.c_double * TD_NFREQ), ("xi", ctypes.c_double * TD_MAXLAM),
+        ("rx_dx", ctypes.c_double), ("rx_dy", ctypes.c_double), ("rx_dz", ctypes.c_double),
+        ("loop_radius", ctypes.c_double),
+        ("MR", ctypes.c_double * (MAXC * TD_NFREQ)), ("MI", ctypes.c_double * (MAXC * TD_NFREQ)),
+        ("t_centre", ctypes.c_double * MAXC),
     ]
 
 
@@ -57,8 +76,8 @@ class TransitionC(ctypes.Structure):
         ("sigma_ref", ctypes.c_double),
         ("edges", ctypes.c_double * (MAXL + 1)), ("sigma_remap", ctypes.c_double * MAXL),
         ("sigma_test", ctypes.c_double * MAXL),
-        ("rel_cur", ctypes.c_double), ("add_cur", ctypes.c_double),
-        ("rel_test", ctypes.c_double), ("add_test", ctypes.c_double),
+        ("rel_cur", ctypes.c_double * MAXSYS), ("add_cur", ctypes.c_double * MAXSYS),
+        ("rel_test", ctypes.c_double * MAXSYS), ("add_test", ctypes.c_double * MAXSYS),
         ("data", ctypes.c_double * MAXC), ("J_in", ctypes.c_double * (MAXC * MAXL)),
         ("pred_in", ctypes.c_double * MAXC),
         ("hessian", ctypes.c_double * (MAXL * MAXL)), ("gradient", ctypes.c_double * MAXL),
@@ -72,7 +91,7 @@ def build(force=False):
     """Compile the oracle with gcc (a few seconds)."""
     if force or not os.path.exists(LIB_PATH) or any(
             os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB_PATH)
-            for f in ("fdem1d_oracle.c", "rjmcmc_oracle.c", "oracle.h")):
+            for f in ("fdem1d_oracle.c", "tdem1d_oracle.c", "rjmcmc_oracle.c", "oracle.h")):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB_PATH
 
@@ -91,6 +110,10 @@ def lib():
         _lib.gbo_run_chain.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                        ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_void_p]
         _lib.gbo_n_depth.restype = ctypes.c_int
+        _lib.gbo_run_chain_tdem.restype = ctypes.c_int
+        _lib.gbo_run_chain_tdem.argtypes = _lib.gbo_run_chain.argtypes
+        for n in ("gbo_tdem_forward", "gbo_tdem_sensitivity", "gbo_tdem_frequency_response"):
+            getattr(_lib, n).restype = ctypes.c_int
     return _lib
 
 
@@ -173,22 +196,25 @@ def philox(ctr, key):
 
 
 def run_chain(sys, opt, data, altitude, seed, sounding_index, max_iterations=0):
-    """Run one chain; returns a dict of numpy arrays."""
+    """Run one chain (FDEM system or TdemSystemC); returns a dict of numpy arrays."""
     data = np.ascontiguousarray(data, dtype=np.float64)
     nd = lib().gbo_n_depth(ctypes.byref(opt))
     N2 = 2 * opt.n_markov_chains
+    tdem = isinstance(sys, TdemSystemC)
+    eshape = (sys.n_sys, opt.n_err_bins) if tdem else (opt.n_err_bins,)
     r = dict(
         hitmap=np.zeros((opt.n_sigma_bins, nd), np.int32), edges_hist=np.zeros(nd, np.int32),
-        ncells_hist=np.zeros(opt.max_layers + 1, np.int32), rel_hist=np.zeros(opt.n_err_bins, np.int32),
-        add_hist=np.zeros(opt.n_err_bins, np.int32), misfit_trace=np.zeros(N2), accept_trace=np.zeros(N2, np.uint8),
+        ncells_hist=np.zeros(opt.max_layers + 1, np.int32), rel_hist=np.zeros(eshape, np.int32),
+        add_hist=np.zeros(eshape, np.int32), misfit_trace=np.zeros(N2), accept_trace=np.zeros(N2, np.uint8),
         best_sigma=np.zeros(opt.max_layers), best_edges=np.zeros(opt.max_layers + 1),
         cur_sigma=np.zeros(opt.max_layers), cur_edges=np.zeros(opt.max_layers + 1), scalars=np.zeros(NSCALARS))
     co = ChainOutC()
     for k, v in r.items():
         setattr(co, k, v.ctypes.data)
-    rc = lib().gbo_run_chain(ctypes.addressof(sys), ctypes.addressof(opt), data.ctypes.data, float(altitude),
-                             int(seed), int(sounding_index), int(max_iterations), ctypes.addressof(co))
-    assert rc == 0
+    fn = lib().gbo_run_chain_tdem if tdem else lib().gbo_run_chain
+    rc = fn(ctypes.addressof(sys), ctypes.addressof(opt), data.ctypes.data, float(altitude),
+            int(seed), int(sounding_index), int(max_iterations), ctypes.addressof(co))
+    assert rc == 0, rc
     return r
 
 
@@ -196,13 +222,16 @@ def eval_transition(sys, opt, **kw):
     t = TransitionC()
     k = int(kw["k"])
     t.k, t.action, t.altitude, t.sigma_ref = k, int(kw["action"]), float(kw["altitude"]), float(kw["sigma_ref"])
-    C = 2 * sys.n_freq
+    tdem = isinstance(sys, TdemSystemC)
+    C = sys.C if tdem else 2 * sys.n_freq
     for i in range(k + 1):
         t.edges[i] = float(kw["edges"][i])
     for i in range(k):
         t.sigma_remap[i] = float(kw["sigma_remap"][i])
         t.sigma_test[i] = float(kw["sigma_test"][i])
-    t.rel_cur, t.add_cur, t.rel_test, t.add_test = (float(kw[n]) for n in ("rel_cur", "add_cur", "rel_test", "add_test"))
+    for n in ("rel_cur", "add_cur", "rel_test", "add_test"):
+        for i, v in enumerate(np.atleast_1d(np.asarray(kw[n], dtype=np.float64))):
+            getattr(t, n)[i] = float(v)
     for i in range(C):
         t.data[i] = float(kw["data"][i])
         t.pred_in[i] = float(kw["pred_in"][i])
@@ -211,9 +240,117 @@ def eval_transition(sys, opt, **kw):
         for c in range(C):
             for i in range(k):
                 t.J_in[c * k + i] = Jin[c, i]
-    rc = lib().gbo_eval_transition(ctypes.byref(sys), ctypes.byref(opt), ctypes.byref(t))
+    fn = lib().gbo_eval_transition_tdem if tdem else lib().gbo_eval_transition
+    rc = fn(ctypes.byref(sys), ctypes.byref(opt), ctypes.byref(t))
     return rc, dict(
         hessian=np.array(t.hessian[:k * k]).reshape(k, k), gradient=np.array(t.gradient[:k]),
         newton_mean=np.array(t.newton_mean[:k]), pred_test=np.array(t.pred_test[:C]),
         misfit_test=t.misfit_test, prior_test=t.prior_test, likelihood_test=t.likelihood_test,
         proposal=t.proposal, proposal1=t.proposal1)
+
+
+# ---------------------------------------------------------------------------------- time domain (SkyTEM)
+# Instrument descriptions = the reference's .stm files, parsed into JSON (geobipy_b200/data/*.json hold the
+# numbers of documentation_source/source/supplementary/data/SkytemHM.stm / SkytemLM.stm).
+def skytem_definitions():
+    import json
+    d = os.path.join(HERE, "..", "geobipy_b200", "data")
+    return [json.load(open(os.path.join(d, n))) for n in ("skytem_hm.json", "skytem_lm.json")]
+
+
+TD_XI_LO, TD_XI_HI = -4.6, 2.3   # ln(lambda ZH / 2) range of the Hankel trapezoid rule
+
+
+def tdem_nodes(defs):
+    """Spline-node frequencies shared by the systems: TD_NFREQ log-spaced values from the lowest base
+    frequency to the highest digitising Nyquist frequency."""
+    lo = min(d["base_frequency"] for d in defs)
+    hi = max(0.5 * d["digitising_frequency"] for d in defs)
+    return lo * (hi / lo) ** (np.arange(TD_NFREQ) / (TD_NFREQ - 1.0))
+
+
+def tdem_window_operator(d, fnodes):
+    """MR, MI [n_windows, n_nodes]: window averages of dBz/dt from the node values of S(f) (see
+    tdem1d_oracle.c step 3).  Independent numpy/scipy statement of what the product builds in C++."""
+    from scipy.interpolate import CubicSpline
+    base, nyq = d["base_frequency"], 0.5 * d["digitising_frequency"]
+    T = 1.0 / base
+    f = np.arange(1, int(nyq / base) + 1, 2) * base          # odd harmonics of the bipolar waveform
+    w = 2.0 * np.pi * f
+    wt, wa = np.asarray(d["waveform_time"]), np.asarray(d["waveform_current"])
+    slope = np.diff(wa) / np.diff(wt)
+    dn = np.zeros(f.size, complex)                            # Fourier coefficients of dI/dt
+    for j, s in enumerate(slope):
+        if s != 0.0:
+            dn += s * (np.exp(-1j * w * wt[j]) - np.exp(-1j * w * wt[j + 1])) / (1j * w)
+    dn *= 2.0 / T                                             # second half period = minus the first
+    F = np.ones(f.size, complex)
+    for fc, order in zip(d["filter_cutoff"], d["filter_order"]):
+        F *= (1.0 / (1.0 + 1j * f / fc)) ** order             # cascaded first-order stages
+    ta, tb = np.asarray(d["window_start"])[:, None], np.asarray(d["window_end"])[:, None]
+    A = dn * F * (np.exp(1j * w * tb) - np.exp(1j * w * ta)) / (1j * w * (tb - ta))
+    lf = np.log10(fnodes)
+    G = np.stack([CubicSpline(lf, e)(np.log10(f)) for e in np.eye(fnodes.size)], axis=1)  # harmonics x nodes
+    # minus: the reference flips the sign of gatdaem1d's z component (TdemDataPoint.py:1015-1016)
+    return -2.0 * A.real @ G, 2.0 * A.imag @ G
+
+
+def make_tdem_system(defs=None, rx_offset=(-13.0, 0.0, 2.0)):
+    defs = skytem_definitions() if defs is None else defs
+    s = TdemSystemC()
+    fn = tdem_nodes(defs)
+    n_lam = 2 * ((max(d["n_abscissae"] for d in defs) + 1) // 2)
+    s.n_sys, s.n_freq, s.n_lam = len(defs), TD_NFREQ, n_lam
+    for i, v in enumerate(fn):
+        s.freq[i] = v
+    for i, v in enumerate(np.linspace(TD_XI_LO, TD_XI_HI, n_lam)):
+        s.xi[i] = v
+    s.rx_dx, s.rx_dy, s.rx_dz = rx_offset
+    s.loop_radius = defs[0]["loop_radius"]
+    c = 0
+    for k, d in enumerate(defs):
+        MR, MI = tdem_window_operator(d, fn)
+        s.n_win[k] = MR.shape[0]
+        for i in range(MR.shape[0]):
+            for j in range(TD_NFREQ):
+                s.MR[c * TD_NFREQ + j] = MR[i, j]
+                s.MI[c * TD_NFREQ + j] = MI[i, j]
+            s.t_centre[c] = 0.5 * (d["window_start"][i] + d["window_end"][i])
+            c += 1
+    s.C = c
+    return s
+
+
+def tdem_forward(sys, altitude, sigma, thickness):
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    thickness = np.ascontiguousarray(thickness, dtype=np.float64)
+    out = np.zeros(sys.C)
+    rc = lib().gbo_tdem_forward(ctypes.byref(sys), ctypes.c_double(altitude), ctypes.c_int(sigma.size), _p(sigma),
+                                _p(thickness), _p(out))
+    assert rc == 0
+    return out
+
+
+def tdem_sensitivity(sys, altitude, sigma, thickness):
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    thickness = np.ascontiguousarray(thickness, dtype=np.float64)
+    J = np.zeros((sys.C, sigma.size))
+    rc = lib().gbo_tdem_sensitivity(ctypes.byref(sys), ctypes.c_double(altitude), ctypes.c_int(sigma.size),
+                                    _p(sigma), _p(thickness), _p(J))
+    assert rc == 0
+    return J
+
+
+def skytem_options(**over):
+    """skytem_options (documentation_source/source/supplementary/options_files/skytem_options)."""
+    o = resolve_options()
+    o.min_edge, o.max_edge, o.min_width = 1.0, 550.0, 1.0   # minimum_thickness None -> 1.0 (RectilinearMesh1D.py:358)
+    o.covariance_scaling = 0.5
+    o.n_systems = 2
+    o.rel_init, o.rel_min, o.rel_max, o.rel_prop_var = 0.05, 0.005, 0.5, 1e-6
+    o.rel_init2, o.rel_min2, o.rel_max2, o.rel_prop_var2 = 0.05, 0.005, 0.5, 1e-6
+    o.add_init, o.add_min, o.add_max, o.add_prop_var = 2e-14, 1e-16, 1e-10, 1e-5
+    o.add_init2, o.add_min2, o.add_max2, o.add_prop_var2 = 2e-13, 1e-16, 1e-10, 1e-5
+    for k, v in over.items():
+        setattr(o, k, v)
+    return o

@@ -1,7 +1,9 @@
 /* TEST INFRASTRUCTURE ONLY (oracle) - never linked or called by the product path.
  *
  * Plain-C fp64 restatement of the reference's per-sounding trans-dimensional
- * (reversible-jump) MCMC sampler for one FDEM sounding.  One function call = one chain.
+ * (reversible-jump) MCMC sampler for one sounding: an FDEM datapoint (one system) or a time-domain
+ * datapoint with one or two systems (TdemDataPoint: per-system relative/additive errors, additive error
+ * scaled by (t/1ms)^-0.5, TdemDataPoint.py:329-379).  One function call = one chain.
  *
  * PARITY PIN: the deterministic terms (Hessian, gradient, Newton mean, misfit, prior,
  * likelihood, forward/reverse proposal densities, posterior bin indices) are checked by
@@ -157,7 +159,7 @@ typedef struct {
 } model_t;
 
 typedef struct {
-    double rel, add;
+    double rel[GBO_MAXSYS], add[GBO_MAXSYS];
     double pred[GBO_MAXC];
     double J[GBO_MAXC * GBO_MAXL]; /* row-major [C][k] */
     int Jk;                        /* columns of J */
@@ -177,12 +179,61 @@ int gbo_n_depth(const gbo_options *o)
     return n_edges - 1;
 }
 
-/* DataPoint.std (DataPoint.py:268-282): variance_i = (rel * d_i)^2 + add^2 */
-static void data_variance(int C, const double *data, double rel, double add, double *var)
+/* what kind of datapoint the chain inverts */
+typedef struct {
+    const gbo_fdem_system *fdem;   /* frequency domain (one system) ... */
+    const gbo_tdem_system *tdem;   /* ... or time domain (1-2 systems) */
+    int C, n_sys;
+    int sys_of[GBO_MAXC];          /* system of channel c */
+    double log_t[GBO_MAXC];        /* ln(off_time) of channel c (TDEM) */
+} survey_t;
+
+static void survey_fdem(survey_t *v, const gbo_fdem_system *sys)
 {
-    for (int i = 0; i < C; ++i) {
-        double a = rel * data[i];
-        var[i] = a * a + add * add;
+    memset(v, 0, sizeof(*v));
+    v->fdem = sys;
+    v->C = 2 * sys->n_freq;
+    v->n_sys = 1;
+}
+static void survey_tdem(survey_t *v, const gbo_tdem_system *sys)
+{
+    memset(v, 0, sizeof(*v));
+    v->tdem = sys;
+    v->C = sys->C;
+    v->n_sys = sys->n_sys;
+    int c = 0;
+    for (int s = 0; s < sys->n_sys; ++s)
+        for (int i = 0; i < sys->n_win[s]; ++i, ++c) {
+            v->sys_of[c] = s;
+            v->log_t[c] = log(sys->t_centre[c]);
+        }
+}
+
+/* per-system option accessors (skytem_options gives lists, one entry per system) */
+static double o_rel_init(const gbo_options *o, int s) { return s ? o->rel_init2 : o->rel_init; }
+static double o_rel_min(const gbo_options *o, int s) { return s ? o->rel_min2 : o->rel_min; }
+static double o_rel_max(const gbo_options *o, int s) { return s ? o->rel_max2 : o->rel_max; }
+static double o_rel_var(const gbo_options *o, int s) { return s ? o->rel_prop_var2 : o->rel_prop_var; }
+static double o_add_init(const gbo_options *o, int s) { return s ? o->add_init2 : o->add_init; }
+static double o_add_min(const gbo_options *o, int s) { return s ? o->add_min2 : o->add_min; }
+static double o_add_max(const gbo_options *o, int s) { return s ? o->add_max2 : o->add_max; }
+static double o_add_var(const gbo_options *o, int s) { return s ? o->add_prop_var2 : o->add_prop_var; }
+
+/* DataPoint.std (DataPoint.py:268-282): variance_i = (rel * d_i)^2 + add^2.
+ * TdemDataPoint.std (TdemDataPoint.py:329-379): per system rel / add, and
+ * add_i = exp(ln(add) - 0.5 (ln t_i - ln 1e-3)). */
+static void data_variance(const survey_t *v, const double *data, const double *rel, const double *add, double *var)
+{
+    for (int i = 0; i < v->C; ++i) {
+        if (v->tdem) {
+            const int s = v->sys_of[i];
+            double a = rel[s] * data[i];
+            double b = exp(log(add[s]) - 0.5 * (v->log_t[i] - log(1e-3)));
+            var[i] = a * a + b * b;
+        } else {
+            double a = rel[0] * data[i];
+            var[i] = a * a + add[0] * add[0];
+        }
     }
 }
 
@@ -222,11 +273,15 @@ static double log_uniform_logpdf(double x, double mn, double mx)
     return -log(b - a);
 }
 
-static double datapoint_probability(const gbo_options *o, double rel, double add)
+/* DataPoint.probability :351-395: multivariate Uniform(log=True) priors sum over the systems
+ * (UniformDistribution.py:116) */
+static double datapoint_probability(const gbo_options *o, int n_sys, const double *rel, const double *add)
 {
     double p = 0.0;
-    if (o->solve_relative_error) p += log_uniform_logpdf(rel, o->rel_min, o->rel_max);
-    if (o->solve_additive_error) p += log_uniform_logpdf(add, o->add_min, o->add_max);
+    for (int s = 0; s < n_sys; ++s) {
+        if (o->solve_relative_error) p += log_uniform_logpdf(rel[s], o_rel_min(o, s), o_rel_max(o, s));
+        if (o->solve_additive_error) p += log_uniform_logpdf(add[s], o_add_min(o, s), o_add_max(o, s));
+    }
     return p;
 }
 
@@ -424,16 +479,42 @@ static double propose_error(rng_t *g, double cur, double prop_var, double mn, do
     return x;
 }
 
+/* Same for a dual-moment datapoint: the 2-vector is proposed jointly (MvLogNormal, diagonal variance) and
+ * re-drawn, at most 10 times, while ANY component leaves its prior; then the whole vector falls back
+ * (StatArray.py:619-636).  One Box-Muller pair per draw. */
+static void propose_error2(rng_t *g, double *x, const double *var, const double *mn, const double *mx)
+{
+    const double c0 = x[0], c1 = x[1];
+    double z0, z1;
+    rng_normal2(g, &z0, &z1);
+    x[0] = exp(log(c0) + sqrt(var[0]) * z0);
+    x[1] = exp(log(c1) + sqrt(var[1]) * z1);
+    int tries = 0;
+    while (log_uniform_logpdf(x[0], mn[0], mx[0]) == -INFINITY || log_uniform_logpdf(x[1], mn[1], mx[1]) == -INFINITY) {
+        rng_normal2(g, &z0, &z1);
+        x[0] = exp(log(c0) + sqrt(var[0]) * z0);
+        x[1] = exp(log(c1) + sqrt(var[1]) * z1);
+        tries++;
+        if (tries == 10) {
+            x[0] = c0;
+            x[1] = c1;
+            return;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ posterior accumulators */
 typedef struct {
     int n_depth, n_sig, n_err, kmax;
     double depth_step;
     double sig_lo, sig_dx;   /* ln(sigma) bins */
-    double rel_lo, rel_dx, add_lo, add_dx; /* ln(err) bins */
+    double rel_lo[GBO_MAXSYS], rel_dx[GBO_MAXSYS], add_lo[GBO_MAXSYS], add_dx[GBO_MAXSYS]; /* ln(err) bins */
+    int n_sys;
 } grids_t;
 
-static void make_grids(const gbo_options *o, double sigma_ref, grids_t *G)
+static void make_grids(const gbo_options *o, int n_sys, double sigma_ref, grids_t *G)
 {
+    G->n_sys = n_sys;
     G->n_depth = gbo_n_depth(o);
     G->depth_step = 0.5 * o->min_width;
     G->n_sig = o->n_sigma_bins;
@@ -444,10 +525,12 @@ static void make_grids(const gbo_options *o, double sigma_ref, grids_t *G)
     G->sig_lo = log(sigma_ref) - o->sigma_bins_nstd * s;
     G->sig_dx = 2.0 * o->sigma_bins_nstd * s / (double)G->n_sig;
     /* DataPoint.set_relative_error_posterior :668-695 + Uniform.bins: linspace(ln min, ln max, n+1) */
-    G->rel_lo = log(o->rel_min);
-    G->rel_dx = (log(o->rel_max) - log(o->rel_min)) / (double)G->n_err;
-    G->add_lo = log(o->add_min);
-    G->add_dx = (log(o->add_max) - log(o->add_min)) / (double)G->n_err;
+    for (int s = 0; s < n_sys; ++s) {
+        G->rel_lo[s] = log(o_rel_min(o, s));
+        G->rel_dx[s] = (log(o_rel_max(o, s)) - log(o_rel_min(o, s))) / (double)G->n_err;
+        G->add_lo[s] = log(o_add_min(o, s));
+        G->add_dx[s] = (log(o_add_max(o, s)) - log(o_add_min(o, s))) / (double)G->n_err;
+    }
 }
 
 /* searchsorted(edges, v, 'right') - 1 clipped, for uniform edges lo + i*dx */
@@ -480,8 +563,8 @@ static double staircase_value(const gbo_options *o, const model_t *m, double y)
     return m->sigma[k - 1];
 }
 
-static void accumulate_posteriors(const gbo_options *o, const grids_t *G, const model_t *m, double rel, double add,
-                                  gbo_chain_out *out)
+static void accumulate_posteriors(const gbo_options *o, const grids_t *G, const model_t *m, const double *rel,
+                                  const double *add, gbo_chain_out *out)
 {
     /* nCells histogram (RectilinearMesh1D.py:1597) */
     out->ncells_hist[m->k] += 1;
@@ -504,8 +587,12 @@ static void accumulate_posteriors(const gbo_options *o, const grids_t *G, const 
         out->hitmap[(size_t)b * G->n_depth + j] += 1;
     }
     /* error histograms (EmDataPoint.py:225-239) */
-    if (o->solve_relative_error) out->rel_hist[uniform_bin(log(rel), G->rel_lo, G->rel_dx, G->n_err)] += 1;
-    if (o->solve_additive_error) out->add_hist[uniform_bin(log(add), G->add_lo, G->add_dx, G->n_err)] += 1;
+    for (int s = 0; s < G->n_sys; ++s) {
+        if (o->solve_relative_error)
+            out->rel_hist[s * G->n_err + uniform_bin(log(rel[s]), G->rel_lo[s], G->rel_dx[s], G->n_err)] += 1;
+        if (o->solve_additive_error)
+            out->add_hist[s * G->n_err + uniform_bin(log(add[s]), G->add_lo[s], G->add_dx[s], G->n_err)] += 1;
+    }
 }
 
 static void reset_posteriors(const gbo_options *o, const grids_t *G, gbo_chain_out *out)
@@ -513,13 +600,13 @@ static void reset_posteriors(const gbo_options *o, const grids_t *G, gbo_chain_o
     memset(out->hitmap, 0, sizeof(int32_t) * (size_t)G->n_sig * G->n_depth);
     memset(out->edges_hist, 0, sizeof(int32_t) * G->n_depth);
     memset(out->ncells_hist, 0, sizeof(int32_t) * (o->max_layers + 1));
-    memset(out->rel_hist, 0, sizeof(int32_t) * G->n_err);
-    memset(out->add_hist, 0, sizeof(int32_t) * G->n_err);
+    memset(out->rel_hist, 0, sizeof(int32_t) * G->n_sys * G->n_err);
+    memset(out->add_hist, 0, sizeof(int32_t) * G->n_sys * G->n_err);
 }
 
 /* ------------------------------------------------------------------ the chain */
 typedef struct {
-    const gbo_fdem_system *sys;
+    survey_t sv;
     const gbo_options *o;
     int C;
     double data[GBO_MAXC];
@@ -534,7 +621,7 @@ typedef struct {
     int burned_in;
     int64_t burned_in_iter, best_iter;
     model_t best_model;
-    double best_rel, best_add, best_posterior;
+    double best_rel[GBO_MAXSYS], best_add[GBO_MAXSYS], best_posterior;
     int accepted;
     int n_zero_acc, n_resets, limiters;
     int64_t n_accept, n_forward, n_sens, n_act[4];
@@ -545,23 +632,25 @@ static void forward(chain_t *c, const model_t *m, double *pred)
 {
     double thk[GBO_MAXL];
     model_thickness(m, thk);
-    gbo_fdem_forward(c->sys, c->altitude, m->k, m->sigma, thk, pred);
+    if (c->sv.tdem) gbo_tdem_forward(c->sv.tdem, c->altitude, m->k, m->sigma, thk, pred);
+    else gbo_fdem_forward(c->sv.fdem, c->altitude, m->k, m->sigma, thk, pred);
     c->n_forward++;
 }
 static void sensitivity(chain_t *c, const model_t *m, dpoint_t *dp)
 {
     double thk[GBO_MAXL];
     model_thickness(m, thk);
-    gbo_fdem_sensitivity(c->sys, c->altitude, m->k, m->sigma, thk, dp->J);
+    if (c->sv.tdem) gbo_tdem_sensitivity(c->sv.tdem, c->altitude, m->k, m->sigma, thk, dp->J);
+    else gbo_fdem_sensitivity(c->sv.fdem, c->altitude, m->k, m->sigma, thk, dp->J);
     dp->Jk = m->k;
     c->n_sens++;
 }
 
 /* EmDataPoint.find_best_halfspace: argmin of misfit over logspace(-4, 4, 100) */
-static double best_halfspace(chain_t *c, double rel, double add)
+static double best_halfspace(chain_t *c, const double *rel, const double *add)
 {
     double var[GBO_MAXC], pred[GBO_MAXC];
-    data_variance(c->C, c->data, rel, add, var);
+    data_variance(&c->sv, c->data, rel, add, var);
     model_t m;
     m.k = 1;
     m.edges[0] = 0.0;
@@ -582,8 +671,10 @@ static double best_halfspace(chain_t *c, double rel, double add)
 static void chain_init(chain_t *c, gbo_chain_out *out)
 {
     const gbo_options *o = c->o;
-    c->dp.rel = o->rel_init;
-    c->dp.add = o->add_init;
+    for (int s = 0; s < c->sv.n_sys; ++s) {
+        c->dp.rel[s] = o_rel_init(o, s);
+        c->dp.add[s] = o_add_init(o, s);
+    }
     c->sigma_ref = best_halfspace(c, c->dp.rel, c->dp.add);
     c->model.k = 1;
     c->model.edges[0] = 0.0;
@@ -591,14 +682,14 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
     c->model.sigma[0] = c->sigma_ref;
     forward(c, &c->model, c->dp.pred);
     sensitivity(c, &c->model, &c->dp);
-    make_grids(o, c->sigma_ref, &c->G);
+    make_grids(o, c->sv.n_sys, c->sigma_ref, &c->G);
     reset_posteriors(o, &c->G, out);
     memset(out->misfit_trace, 0, sizeof(double) * 2 * (size_t)o->n_markov_chains);
     memset(out->accept_trace, 0, 2 * (size_t)o->n_markov_chains);
     double var[GBO_MAXC];
-    data_variance(c->C, c->data, c->dp.rel, c->dp.add, var);
+    data_variance(&c->sv, c->data, c->dp.rel, c->dp.add, var);
     c->misfit = data_misfit(c->C, c->data, c->dp.pred, var);
-    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->dp.rel, c->dp.add);
+    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->sv.n_sys, c->dp.rel, c->dp.add);
     c->likelihood = data_likelihood(c->C, c->data, c->dp.pred, var);
     c->posterior = c->likelihood + c->prior;
     c->burned_in = 0;
@@ -607,8 +698,8 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
     out->misfit_trace[0] = c->misfit;
     c->accepted = 0;
     c->best_model = c->model;
-    c->best_rel = c->dp.rel;
-    c->best_add = c->dp.add;
+    memcpy(c->best_rel, c->dp.rel, sizeof(c->best_rel));
+    memcpy(c->best_add, c->dp.add, sizeof(c->best_add));
     c->best_posterior = c->posterior;
     c->best_iter = 0;
     c->n_zero_acc = 0;
@@ -632,7 +723,7 @@ static int chain_step(chain_t *c)
         forward(c, &remap, tdp.pred);
         sensitivity(c, &remap, &tdp);
     }
-    data_variance(C, c->data, tdp.rel, tdp.add, var);
+    data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
     hessian_gradient(o, &remap, c->sigma_ref, C, c->data, var, tdp.J, tdp.pred, A, grad);
     if (cholesky(k, A)) return 1;
     /* pk = -H grad ; mean = ln sigma + alpha pk */
@@ -648,13 +739,20 @@ static int chain_step(chain_t *c)
     for (int i = 0; i < k; ++i) test.sigma[i] = exp(mean[i] + dx[i]);
 
     /* test_datapoint.perturb() */
-    if (o->solve_relative_error) tdp.rel = propose_error(&c->rng, tdp.rel, o->rel_prop_var, o->rel_min, o->rel_max);
-    if (o->solve_additive_error) tdp.add = propose_error(&c->rng, tdp.add, o->add_prop_var, o->add_min, o->add_max);
+    if (c->sv.n_sys == 1) {
+        if (o->solve_relative_error) tdp.rel[0] = propose_error(&c->rng, tdp.rel[0], o->rel_prop_var, o->rel_min, o->rel_max);
+        if (o->solve_additive_error) tdp.add[0] = propose_error(&c->rng, tdp.add[0], o->add_prop_var, o->add_min, o->add_max);
+    } else {
+        const double rv[2] = {o_rel_var(o, 0), o_rel_var(o, 1)}, rmn[2] = {o_rel_min(o, 0), o_rel_min(o, 1)}, rmx[2] = {o_rel_max(o, 0), o_rel_max(o, 1)};
+        const double av[2] = {o_add_var(o, 0), o_add_var(o, 1)}, amn[2] = {o_add_min(o, 0), o_add_min(o, 1)}, amx[2] = {o_add_max(o, 0), o_add_max(o, 1)};
+        if (o->solve_relative_error) propose_error2(&c->rng, tdp.rel, rv, rmn, rmx);
+        if (o->solve_additive_error) propose_error2(&c->rng, tdp.add, av, amn, amx);
+    }
 
     forward(c, &test, tdp.pred);
-    data_variance(C, c->data, tdp.rel, tdp.add, var);
+    data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
     double t_misfit = data_misfit(C, c->data, tdp.pred, var);
-    double t_prior = datapoint_probability(o, tdp.rel, tdp.add);
+    double t_prior = datapoint_probability(o, c->sv.n_sys, tdp.rel, tdp.add);
     if (t_prior == -INFINITY) return 0;
     t_prior += model_probability(o, &test, c->sigma_ref);
     if (t_prior == -INFINITY) return 0;
@@ -715,8 +813,8 @@ static int chain_update(chain_t *c, gbo_chain_out *out)
             c->burned_in_iter = c->iteration;
             c->best_iter = c->iteration;
             c->best_model = c->model;
-            c->best_rel = c->dp.rel;
-            c->best_add = c->dp.add;
+            memcpy(c->best_rel, c->dp.rel, sizeof(c->best_rel));
+            memcpy(c->best_add, c->dp.add, sizeof(c->best_add));
             c->best_posterior = c->posterior;
             reset_posteriors(o, &c->G, out);
         }
@@ -724,8 +822,8 @@ static int chain_update(chain_t *c, gbo_chain_out *out)
     if (c->posterior > c->best_posterior) {
         c->best_iter = c->iteration;
         c->best_model = c->model;
-        c->best_rel = c->dp.rel;
-        c->best_add = c->dp.add;
+        memcpy(c->best_rel, c->dp.rel, sizeof(c->best_rel));
+        memcpy(c->best_add, c->dp.add, sizeof(c->best_add));
         c->best_posterior = c->posterior;
     }
     if (c->iteration < N2) out->accept_trace[c->iteration] = (uint8_t)c->accepted;
@@ -751,14 +849,14 @@ static int chain_update(chain_t *c, gbo_chain_out *out)
     return 0;
 }
 
-int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const double *data, double altitude,
-                  uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out)
+static int run_chain_impl(const survey_t *sv, const gbo_options *opt, const double *data, double altitude,
+                          uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out)
 {
     chain_t *c = (chain_t *)calloc(1, sizeof(chain_t));
     if (!c) return -1;
-    c->sys = sys;
+    c->sv = *sv;
     c->o = opt;
-    c->C = 2 * sys->n_freq;
+    c->C = sv->C;
     memcpy(c->data, data, sizeof(double) * c->C);
     c->altitude = altitude;
     c->rng.seed = seed;
@@ -814,13 +912,17 @@ int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const doub
     s[GBO_S_N_FORWARD] = (double)c->n_forward;
     s[GBO_S_N_SENS] = (double)c->n_sens;
     s[GBO_S_BEST_POSTERIOR] = c->best_posterior;
-    s[GBO_S_CUR_REL] = c->dp.rel;
-    s[GBO_S_CUR_ADD] = c->dp.add;
+    s[GBO_S_CUR_REL] = c->dp.rel[0];
+    s[GBO_S_CUR_ADD] = c->dp.add[0];
+    s[GBO_S_CUR_REL2] = c->dp.rel[1];
+    s[GBO_S_CUR_ADD2] = c->dp.add[1];
+    s[GBO_S_BEST_REL2] = c->best_rel[1];
+    s[GBO_S_BEST_ADD2] = c->best_add[1];
     s[GBO_S_CUR_MISFIT] = c->misfit;
     s[GBO_S_CUR_PRIOR] = c->prior;
     s[GBO_S_CUR_LIKELIHOOD] = c->likelihood;
-    s[GBO_S_BEST_REL] = c->best_rel;
-    s[GBO_S_BEST_ADD] = c->best_add;
+    s[GBO_S_BEST_REL] = c->best_rel[0];
+    s[GBO_S_BEST_ADD] = c->best_add[0];
     s[GBO_S_N_RESETS] = c->n_resets;
     s[GBO_S_N_BIRTH] = (double)c->n_act[0];
     s[GBO_S_N_DEATH] = (double)c->n_act[1];
@@ -839,10 +941,52 @@ int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const doub
     return 0;
 }
 
+int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const double *data, double altitude,
+                  uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out)
+{
+    survey_t sv;
+    survey_fdem(&sv, sys);
+    return run_chain_impl(&sv, opt, data, altitude, seed, sounding_index, max_iterations, out);
+}
+
+int gbo_run_chain_tdem(const gbo_tdem_system *sys, const gbo_options *opt, const double *data, double altitude,
+                       uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out)
+{
+    survey_t sv;
+    survey_tdem(&sv, sys);
+    if ((opt->n_systems > 1 ? opt->n_systems : 1) != sv.n_sys) return -2;
+    return run_chain_impl(&sv, opt, data, altitude, seed, sounding_index, max_iterations, out);
+}
+
 /* ------------------------------------------------------------------ term-level pin */
+static void sv_forward(const survey_t *sv, double alt, int k, const double *sig, const double *thk, double *pred)
+{
+    if (sv->tdem) gbo_tdem_forward(sv->tdem, alt, k, sig, thk, pred);
+    else gbo_fdem_forward(sv->fdem, alt, k, sig, thk, pred);
+}
+static void sv_sensitivity(const survey_t *sv, double alt, int k, const double *sig, const double *thk, double *J)
+{
+    if (sv->tdem) gbo_tdem_sensitivity(sv->tdem, alt, k, sig, thk, J);
+    else gbo_fdem_sensitivity(sv->fdem, alt, k, sig, thk, J);
+}
+
+static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_transition *t);
 int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *o, gbo_transition *t)
 {
-    const int k = t->k, C = 2 * sys->n_freq;
+    survey_t sv;
+    survey_fdem(&sv, sys);
+    return eval_transition_impl(&sv, o, t);
+}
+int gbo_eval_transition_tdem(const gbo_tdem_system *sys, const gbo_options *o, gbo_transition *t)
+{
+    survey_t sv;
+    survey_tdem(&sv, sys);
+    return eval_transition_impl(&sv, o, t);
+}
+
+static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_transition *t)
+{
+    const int k = t->k, C = sv->C;
     model_t remap, test;
     remap.k = test.k = k;
     memcpy(remap.edges, t->edges, sizeof(double) * (k + 1));
@@ -853,13 +997,13 @@ int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *o, gbo_tr
     double A[GBO_MAXL * GBO_MAXL], y[GBO_MAXL], step[GBO_MAXL];
     model_thickness(&remap, thk);
     if (t->action != ACT_NONE) {
-        gbo_fdem_forward(sys, t->altitude, k, remap.sigma, thk, pred);
-        gbo_fdem_sensitivity(sys, t->altitude, k, remap.sigma, thk, J);
+        sv_forward(sv, t->altitude, k, remap.sigma, thk, pred);
+        sv_sensitivity(sv, t->altitude, k, remap.sigma, thk, J);
     } else {
         memcpy(pred, t->pred_in, sizeof(double) * C);
         memcpy(J, t->J_in, sizeof(double) * C * k);
     }
-    data_variance(C, t->data, t->rel_cur, t->add_cur, var);
+    data_variance(sv, t->data, t->rel_cur, t->add_cur, var);
     hessian_gradient(o, &remap, t->sigma_ref, C, t->data, var, J, pred, A, t->gradient);
     memcpy(t->hessian, A, sizeof(double) * k * k);
     if (cholesky(k, A)) return 1;
@@ -867,16 +1011,16 @@ int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *o, gbo_tr
     solve_LT(k, A, y, step);
     for (int i = 0; i < k; ++i) t->newton_mean[i] = exp(log(remap.sigma[i]) - o->covariance_scaling * step[i]);
 
-    gbo_fdem_forward(sys, t->altitude, k, test.sigma, thk, t->pred_test);
-    data_variance(C, t->data, t->rel_test, t->add_test, var);
+    sv_forward(sv, t->altitude, k, test.sigma, thk, t->pred_test);
+    data_variance(sv, t->data, t->rel_test, t->add_test, var);
     t->misfit_test = data_misfit(C, t->data, t->pred_test, var);
-    t->prior_test = datapoint_probability(o, t->rel_test, t->add_test) + model_probability(o, &test, t->sigma_ref);
+    t->prior_test = datapoint_probability(o, sv->n_sys, t->rel_test, t->add_test) + model_probability(o, &test, t->sigma_ref);
     t->likelihood_test = data_likelihood(C, t->data, t->pred_test, var);
     t->proposal = 1.0;
     t->proposal1 = 1.0;
     if (t->action == ACT_BIRTH || t->action == ACT_DEATH) {
         double g2[GBO_MAXL], s2[GBO_MAXL], xr[GBO_MAXL], xf[GBO_MAXL], logdetL = 0.0;
-        gbo_fdem_sensitivity(sys, t->altitude, k, test.sigma, thk, J);
+        sv_sensitivity(sv, t->altitude, k, test.sigma, thk, J);
         hessian_gradient(o, &test, t->sigma_ref, C, t->data, var, J, t->pred_test, NULL, g2);
         solve_L(k, A, g2, y);
         solve_LT(k, A, y, s2);

@@ -4,6 +4,7 @@ Needs the read-only reference tree at /root/reference; imports the *unmodified* 
 through oracle/ref_shims.py and records its outputs.  The GPU box never runs this.
 
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
+    python tests/golden/make_golden.py tdem         # skytem_clean.npz
     python tests/golden/make_golden.py bins         # posterior_bins.npz
     python tests/golden/make_golden.py transitions  # transitions.npz
     python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
@@ -13,6 +14,9 @@ Files written
                           (tests/data_checks/resolve_*_clean.csv, 6 models x 79 soundings x 12 channels;
                           tests/test_synthetic_data.py:16-30) plus the model definitions
                           (Model.create_synthetic_model, classes/model/Model.py:885-920).
+  skytem_clean.npz        the reference's only known-answer vectors for the time-domain path
+                          (tests/data_checks/skytem_*_clean.csv, 6 models x 79 soundings x 45 windows,
+                          tests/test_synthetic_data.py:32-48) plus model definitions and geometry columns.
   fdem_random_models.npz  nbFdem1dfwd / nbFdem1dsen outputs (fdem1d_numba.py:25,72) for random models.
   posterior_bins.npz      bin indices the reference's Histogram meshes assign to probe values.
   transitions.npz         per-term records of Inference1D.accept_reject (Inference1D.py:537-631).
@@ -128,6 +132,26 @@ def make_fdem():
     np.savez_compressed(os.path.join(HERE, "fdem_random_models.npz"), nlayers=Ls.astype(np.int32), sigma=sigma,
                         thickness=thk, height=height, forward=fwd, sensitivity=sens)
     print("fdem goldens written")
+
+
+def make_tdem():
+    """The SkyTEM known-answer CSVs (plain CSV: no reference import needed)."""
+    import pandas as pd
+    data = np.zeros((6, 79, 45))
+    sig = np.array([[1e-2, 1e-1, 0.03333333], [1e-2, 1e-1, 1.0], [2e-2, 2e-3, 2e-2], [1e-2, 1e-1, 1e-4],
+                    [1.0, 1e-2, 5e-2], [1e-4, 1e-2, 1.0]])  # Model.create_synthetic_model, Model.py:902-908
+    geom = None
+    for m, name in enumerate(MODELS):
+        df = pd.read_csv(os.path.join(REF, "tests/data_checks/skytem_%s_clean.csv" % name))
+        data[m] = df.values[:, 15:60]
+        g = df[["Height", "tx_pitch", "tx_roll", "tx_yaw", "txrx_dx", "txrx_dy", "txrx_dz", "rx_pitch", "rx_roll",
+                "rx_yaw"]].values
+        assert np.all(g == g[0])
+        geom = g[0]
+        times = np.array([float(c.split("_")[-1]) for c in df.columns[15:60]])
+    np.savez_compressed(os.path.join(HERE, "skytem_clean.npz"), data=data, sigma=sig,
+                        zwedge=np.linspace(50.0, 1.0, 79), zdeep=np.linspace(75.0, 500.0, 79), geometry=geom,
+                        times=times, models=np.array(MODELS))
 
 
 def _initialised_inference(data, z, n_markov_chains, seed):
@@ -274,6 +298,8 @@ def make_chain(sidx, rep=0, n_markov_chains=10000):
 
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "tdem":
+        make_tdem()
     if what == "fdem":
         make_fdem()
     elif what == "bins":
