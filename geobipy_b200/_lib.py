@@ -14,12 +14,14 @@ LIB_PATH = os.path.join(HERE, "libgeobipy_b200.so")
 
 MAXF, MAXL = 16, 30
 MAXC = 2 * MAXF
+TD_MAXSYS, TD_NFREQ, TD_MAXLAM, TD_MAXWIN, TD_MAXC, TD_MAXWAVE, TD_MAXFILT = 2, 32, 32, 32, 64, 64, 4
 NSCALARS = 32
 PRECISION_F32, PRECISION_F64 = 32, 64
 
 (S_ITER, S_BURNED_IN, S_BURNED_IN_ITER, S_BEST_ITER, S_BEST_K, S_CUR_K, S_HALFSPACE, S_FAILED, S_N_ACCEPT,
  S_N_FORWARD, S_N_SENS, S_BEST_POSTERIOR, S_CUR_REL, S_CUR_ADD, S_CUR_MISFIT, S_CUR_PRIOR, S_CUR_LIKELIHOOD,
- S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER) = range(25)
+ S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER,
+ S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2) = range(29)
 
 
 class FdemSystemC(ctypes.Structure):
@@ -44,8 +46,31 @@ class OptionsC(ctypes.Structure):
         ("add_init", ctypes.c_double), ("add_min", ctypes.c_double), ("add_max", ctypes.c_double),
         ("add_prop_var", ctypes.c_double),
         ("n_sigma_bins", ctypes.c_int32), ("n_err_bins", ctypes.c_int32), ("sigma_bins_nstd", ctypes.c_double),
-        ("burn_in_min_iter", ctypes.c_int32), ("pad_", ctypes.c_int32),
+        ("burn_in_min_iter", ctypes.c_int32), ("n_systems", ctypes.c_int32),
+        ("rel_init2", ctypes.c_double), ("rel_min2", ctypes.c_double), ("rel_max2", ctypes.c_double),
+        ("rel_prop_var2", ctypes.c_double),
+        ("add_init2", ctypes.c_double), ("add_min2", ctypes.c_double), ("add_max2", ctypes.c_double),
+        ("add_prop_var2", ctypes.c_double),
     ]
+
+
+class TdemSystemC(ctypes.Structure):
+    """gbp_tdem_system"""
+    _fields_ = [
+        ("n_wave", ctypes.c_int32), ("n_windows", ctypes.c_int32), ("n_filters", ctypes.c_int32),
+        ("n_abscissae", ctypes.c_int32),
+        ("base_frequency", ctypes.c_double), ("digitising_frequency", ctypes.c_double),
+        ("loop_radius", ctypes.c_double),
+        ("wave_time", ctypes.c_double * TD_MAXWAVE), ("wave_current", ctypes.c_double * TD_MAXWAVE),
+        ("window_start", ctypes.c_double * TD_MAXWIN), ("window_end", ctypes.c_double * TD_MAXWIN),
+        ("filter_cutoff", ctypes.c_double * TD_MAXFILT), ("filter_order", ctypes.c_int32 * TD_MAXFILT),
+    ]
+
+
+class TdemSurveyC(ctypes.Structure):
+    """gbp_tdem_survey"""
+    _fields_ = [("n_systems", ctypes.c_int32), ("pad_", ctypes.c_int32), ("sys", TdemSystemC * TD_MAXSYS),
+                ("rx_dx", ctypes.c_double), ("rx_dy", ctypes.c_double), ("rx_dz", ctypes.c_double)]
 
 
 BUFFER_FIELDS = ("hitmap", "edges_hist", "ncells_hist", "rel_hist", "add_hist", "misfit_trace", "accept_trace",
@@ -63,6 +88,9 @@ EXPORTS = (
     "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host",
+    "gbp_tdem_n_channels", "gbp_tdem_window_operator", "gbp_tdem_flops_per_forward",
+    "gbp_tdem_forward", "gbp_tdem_sensitivity", "gbp_tdem_forward_host", "gbp_tdem_sensitivity_host",
+    "gbp_tdem_rjmcmc_run", "gbp_tdem_rjmcmc_run_host",
 )
 
 _lib = None
@@ -107,6 +135,18 @@ def load():
     lib.gbp_rjmcmc_run.argtypes = [vp, vp, i32, vp, vp, u64, u64, i64, vp, i32, vp]
     lib.gbp_rjmcmc_run_host.restype = i32
     lib.gbp_rjmcmc_run_host.argtypes = [vp, vp, i32, vp, vp, u64, u64, i64, vp, i32, i32]
+    lib.gbp_tdem_n_channels.restype = i32
+    lib.gbp_tdem_n_channels.argtypes = [vp]
+    lib.gbp_tdem_window_operator.restype = i32
+    lib.gbp_tdem_window_operator.argtypes = [vp, vp, vp, vp, vp]
+    lib.gbp_tdem_flops_per_forward.restype = dbl
+    lib.gbp_tdem_flops_per_forward.argtypes = [vp, i32]
+    for name, ref in (("gbp_tdem_forward", lib.gbp_fdem_forward), ("gbp_tdem_sensitivity", lib.gbp_fdem_sensitivity),
+                      ("gbp_tdem_forward_host", lib.gbp_fdem_forward_host),
+                      ("gbp_tdem_sensitivity_host", lib.gbp_fdem_sensitivity_host),
+                      ("gbp_tdem_rjmcmc_run", lib.gbp_rjmcmc_run), ("gbp_tdem_rjmcmc_run_host", lib.gbp_rjmcmc_run_host)):
+        getattr(lib, name).restype = i32
+        getattr(lib, name).argtypes = ref.argtypes
     _lib = lib
     return lib
 

@@ -11,6 +11,7 @@
 
 #include "gbp_chain.cuh"
 #include "gbp_tables.h"
+#include "gbp_tdem_tables.h"
 
 using namespace gbp;
 
@@ -125,20 +126,91 @@ int launch_fdem(TableCache* tc, int B, int l_stride, const int32_t* nl, const do
     return time_end(st);
 }
 
+// device copies of the time-domain window operator, cached per (device, survey)
+constexpr double TD_F32_SCALE = 1099511627776.0;  // 2^40: fp32 path works in scaled data units (exact in fp64)
+struct TdCache {
+    int device = -1;
+    gbp_tdem_survey sv;
+    TdHost host;
+    float* d_f32 = nullptr;   // Mt * TD_F32_SCALE
+    double* d_f64 = nullptr;
+};
+std::vector<TdCache*> g_td_cache;
+
+int get_td_tables(const gbp_tdem_survey* sv, TdCache** out, bool need_device)
+{
+    int dev = -1;
+    if (need_device) CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (TdCache* c : g_td_cache)
+        if (c->device == dev && std::memcmp(&c->sv, sv, sizeof(*sv)) == 0) {
+            *out = c;
+            return 0;
+        }
+    TdCache* c = new TdCache();
+    c->device = dev;
+    c->sv = *sv;
+    if (!build_tdem_tables(*sv, c->host)) {
+        std::string e = c->host.error;
+        delete c;
+        return fail(e);
+    }
+    if (need_device) {
+        const size_t n = c->host.Mt.size();
+        std::vector<float> f32(n);
+        for (size_t i = 0; i < n; ++i) f32[i] = (float)(c->host.Mt[i] * TD_F32_SCALE);
+        CK(cudaMalloc(&c->d_f32, n * sizeof(float)));
+        CK(cudaMalloc(&c->d_f64, n * sizeof(double)));
+        CK(cudaMemcpy(c->d_f32, f32.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_f64, c->host.Mt.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    g_td_cache.push_back(c);
+    *out = c;
+    return 0;
+}
+template <typename T> const T* td_ptr(TdCache* c);
+template <> const float* td_ptr<float>(TdCache* c) { return c->d_f32; }
+template <> const double* td_ptr<double>(TdCache* c) { return c->d_f64; }
+
+template <typename T, bool SENS>
+int launch_tdem(TdCache* tc, int B, int l_stride, const int32_t* nl, const double* sig, const double* thk,
+                const double* alt, double* out, double* J, double out_scale, cudaStream_t st)
+{
+    const int threads = 256, wpb = threads / 32;
+    const size_t mt_bytes = (size_t)TD_ROWS * TD_CP * sizeof(T);
+    const size_t per_warp = (2 * KS + 2 * GBP_TD_MAXLAM + TD_ROWS + TD_CP + (SENS ? TD_CP * KS : 0)) * sizeof(T);
+    const size_t smem = mt_bytes + wpb * per_warp;
+    auto kern = tdem_kernel<T, SENS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int grid = sm_count() * blocks_per_sm;
+    const int need = (B + wpb - 1) / wpb;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (time_begin(st)) return 1;
+    kern<<<grid, threads, smem, st>>>(tc->host.dev, td_ptr<T>(tc), B, l_stride, nl, sig, thk, alt, out, J, out_scale);
+    g_launches++;
+    CK(cudaGetLastError());
+    return time_end(st);
+}
+
 void* g_jstore[64] = {nullptr};
 size_t g_jstore_cap[64] = {0};
 
-template <typename R, typename T, int NC, int WARPS>
-int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
+template <typename R, typename T, int NC, int WARPS, int KIND>
+int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, size_t tab_bytes_raw, const ChainParams& P,
+                 cudaStream_t st)
 {
-    const size_t tab_bytes = ((size_t)TAB_ROWS * tc->host.dev.tab_stride * sizeof(T) + 127) & ~(size_t)127;
-    const size_t per_warp = sizeof(WarpState<R, T, NC>);
+    const size_t tab_bytes = (tab_bytes_raw + 127) & ~(size_t)127;
+    const size_t per_warp = sizeof(WarpState<R, T, NC, KIND>);
     int dev = 0, max_smem = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t smem = tab_bytes + (size_t)WARPS * per_warp;
     if (smem + 2048 > (size_t)max_smem) return fail("rjmcmc kernel does not fit in shared memory on this device");
-    auto kern = rjmcmc_kernel<R, T, NC, WARPS>;
+    auto kern = rjmcmc_kernel<R, T, NC, WARPS, KIND>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // per-chain Jacobian mirror (L2 resident: 1.4 KB per chain in fp32)
     const size_t jbytes = (size_t)P.B * NC * KS * sizeof(T);
@@ -158,7 +230,7 @@ int launch_chain(TableCache* tc, const ChainParams& P, cudaStream_t st)
     // device-side work counter: chains beyond the first wave are claimed dynamically
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
     if (time_begin(st)) return 1;
-    kern<<<grid, WARPS * 32, smem, st>>>(tc->host.dev, tab_ptr<T>(tc), Q);
+    kern<<<grid, WARPS * 32, smem, st>>>(sysdev, d_tab, Q);
     g_launches++;
     CK(cudaGetLastError());
     return time_end(st);
@@ -344,26 +416,38 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
     P.first_index = first_index;
     P.max_iterations = max_iterations;
     P.out = *d_buf;
+    P.data_scale = 1.0;
+    if (opt->n_systems > 1) return fail("an FDEM datapoint has one system (gbp_options.n_systems must be 0 or 1)");
     if (get_counter(&P.work_counter)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     const bool small = P.C <= 12;
+    const SysDev& sd = tc->host.dev;
     // fp32: 28 chains per SM (148 x 28 = 4144 resident chains: BASELINE configs[1] is one wave); fp64: 8 per SM
-    if (precision == GBP_PRECISION_F32)
-        return small ? launch_chain<float, float, 12, 28>(tc, P, st) : launch_chain<float, float, GBP_MAXC, 16>(tc, P, st);
-    if (precision == GBP_PRECISION_F64)
-        return small ? launch_chain<double, double, 12, 8>(tc, P, st) : launch_chain<double, double, GBP_MAXC, 8>(tc, P, st);
+    if (precision == GBP_PRECISION_F32) {
+        const size_t tb = (size_t)TAB_ROWS * sd.tab_stride * sizeof(float);
+        return small ? launch_chain<float, float, 12, 28, KIND_FDEM>(sd, tc->d_f32, tb, P, st)
+                     : launch_chain<float, float, GBP_MAXC, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
+    }
+    if (precision == GBP_PRECISION_F64) {
+        const size_t tb = (size_t)TAB_ROWS * sd.tab_stride * sizeof(double);
+        return small ? launch_chain<double, double, 12, 8, KIND_FDEM>(sd, tc->d_f64, tb, P, st)
+                     : launch_chain<double, double, GBP_MAXC, 8, KIND_FDEM>(sd, tc->d_f64, tb, P, st);
+    }
     return fail("precision must be 32 or 64");
 }
 
-int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int B, const double* data,
-                        const double* altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
-                        const gbp_chain_buffers* h, int precision, int device)
+}  // extern "C"
+
+// shared body of the *_rjmcmc_run_host entry points; `run` launches on the device buffers
+template <typename RunFn>
+static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* data, const double* altitude,
+                            const gbp_chain_buffers* h, int device, RunFn run)
 {
     if (B <= 0) return 0;
     if (check_options(opt)) return 1;
     if (!h || !h->scalars) return fail("gbp_chain_buffers.scalars is required");
     CK(cudaSetDevice(device));
-    const int C = 2 * sys->n_freq, nd = gbp_n_depth(opt), ml = opt->max_layers;
+    const int nd = gbp_n_depth(opt), ml = opt->max_layers, nsys = opt->n_systems > 1 ? 2 : 1;
     const size_t N2 = 2 * (size_t)opt->n_markov_chains;
     struct Item {
         void* const* host;
@@ -376,8 +460,8 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
         {(void* const*)&h->hitmap, (void**)&d.hitmap, (size_t)B * opt->n_sigma_bins * nd * sizeof(int32_t)},
         {(void* const*)&h->edges_hist, (void**)&d.edges_hist, (size_t)B * nd * sizeof(int32_t)},
         {(void* const*)&h->ncells_hist, (void**)&d.ncells_hist, (size_t)B * (ml + 1) * sizeof(int32_t)},
-        {(void* const*)&h->rel_hist, (void**)&d.rel_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
-        {(void* const*)&h->add_hist, (void**)&d.add_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
+        {(void* const*)&h->rel_hist, (void**)&d.rel_hist, (size_t)B * nsys * opt->n_err_bins * sizeof(int32_t)},
+        {(void* const*)&h->add_hist, (void**)&d.add_hist, (size_t)B * nsys * opt->n_err_bins * sizeof(int32_t)},
         {(void* const*)&h->misfit_trace, (void**)&d.misfit_trace, (size_t)B * N2 * sizeof(double)},
         {(void* const*)&h->accept_trace, (void**)&d.accept_trace, (size_t)B * N2},
         {(void* const*)&h->best_sigma, (void**)&d.best_sigma, (size_t)B * ml * sizeof(double)},
@@ -411,7 +495,7 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
     CKC(cudaMalloc(&d_alt, (size_t)B * sizeof(double)));
     CKC(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, nullptr));
     CKC(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    rc = gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, &d, precision, nullptr);
+    rc = run(d_data, d_alt, &d);
     if (!rc) {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) rc = fail(std::string("kernel: ") + cudaGetErrorString(e));
@@ -421,6 +505,196 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
             if (*it.host) CKC(cudaMemcpy(*it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost));
     cleanup();
     return rc;
+}
+
+extern "C" {
+
+int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int B, const double* data,
+                        const double* altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                        const gbp_chain_buffers* h, int precision, int device)
+{
+    return rjmcmc_host_impl(2 * sys->n_freq, opt, B, data, altitude, h, device,
+                            [&](const double* d_data, const double* d_alt, const gbp_chain_buffers* d) {
+                                return gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
+                                                      precision, nullptr);
+                            });
+}
+
+// ------------------------------------------------------------------------------------------ time domain
+int gbp_tdem_n_channels(const gbp_tdem_survey* sv)
+{
+    int c = 0;
+    for (int s = 0; s < sv->n_systems && s < GBP_TD_MAXSYS; ++s) c += sv->sys[s].n_windows;
+    return c;
+}
+
+int gbp_tdem_window_operator(const gbp_tdem_survey* sv, double* freq, double* MR, double* MI, double* t_centre)
+{
+    TdCache* tc;
+    if (get_td_tables(sv, &tc, false)) return 1;
+    const int C = tc->host.dev.C;
+    if (freq) std::memcpy(freq, tc->host.freq, sizeof(double) * TD_NF);
+    for (int c = 0; c < C; ++c)
+        for (int i = 0; i < TD_NF; ++i) {
+            if (MR) MR[c * TD_NF + i] = tc->host.Mt[(size_t)i * TD_CP + c];
+            if (MI) MI[c * TD_NF + i] = tc->host.Mt[(size_t)(TD_NF + i) * TD_CP + c];
+        }
+    if (t_centre) {
+        int c = 0;
+        for (int s = 0; s < sv->n_systems; ++s)
+            for (int i = 0; i < sv->sys[s].n_windows; ++i, ++c)
+                t_centre[c] = 0.5 * (sv->sys[s].window_start[i] + sv->sys[s].window_end[i]);
+    }
+    return 0;
+}
+
+double gbp_tdem_flops_per_forward(const gbp_tdem_survey* sv, int L)
+{
+    TdCache* tc;
+    if (get_td_tables(sv, &tc, false)) return 0.0;
+    return (double)TD_NF * tc->host.dev.n_lam * (75.0 * (double)L + 39.0) + 2.0 * tc->host.dev.C * TD_ROWS;
+}
+
+static int tdem_dev(bool sens, const gbp_tdem_survey* sv, int B, int l_stride, const int32_t* d_nlayers,
+                    const double* d_sigma, const double* d_thickness, const double* d_altitude, double* d_out, double* d_J,
+                    int precision, void* stream)
+{
+    if (B <= 0) return 0;
+    if (l_stride < 1 || l_stride > GBP_MAXL) return fail("l_stride must be in [1, 30]");
+    TdCache* tc;
+    if (get_td_tables(sv, &tc, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == GBP_PRECISION_F32)
+        return sens ? launch_tdem<float, true>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, d_J, 1.0 / TD_F32_SCALE, st)
+                    : launch_tdem<float, false>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, nullptr, 1.0 / TD_F32_SCALE, st);
+    if (precision == GBP_PRECISION_F64)
+        return sens ? launch_tdem<double, true>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, d_J, 1.0, st)
+                    : launch_tdem<double, false>(tc, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, nullptr, 1.0, st);
+    return fail("precision must be 32 or 64");
+}
+
+int gbp_tdem_forward(const gbp_tdem_survey* sv, int B, int l_stride, const int32_t* d_nlayers, const double* d_sigma,
+                     const double* d_thickness, const double* d_altitude, double* d_out, int precision, void* stream)
+{
+    return tdem_dev(false, sv, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, nullptr, precision, stream);
+}
+
+int gbp_tdem_sensitivity(const gbp_tdem_survey* sv, int B, int l_stride, const int32_t* d_nlayers, const double* d_sigma,
+                         const double* d_thickness, const double* d_altitude, double* d_out, double* d_J, int precision,
+                         void* stream)
+{
+    return tdem_dev(true, sv, B, l_stride, d_nlayers, d_sigma, d_thickness, d_altitude, d_out, d_J, precision, stream);
+}
+
+static int tdem_host(bool sens, const gbp_tdem_survey* sv, int B, int l_stride, const int32_t* nlayers,
+                     const double* sigma, const double* thickness, const double* altitude, double* out, double* J,
+                     int precision, int device)
+{
+    if (B <= 0) return 0;
+    for (int b = 0; b < B; ++b) {
+        if (nlayers[b] < 1 || nlayers[b] > l_stride) return fail("nlayers out of range");
+        if (!(altitude[b] > 0.0)) return fail("Sensor altitude must be above the top of the model");  // tdem1d.py:32
+    }
+    CK(cudaSetDevice(device));
+    const int C = gbp_tdem_n_channels(sv);
+    int32_t* d_nl = nullptr;
+    double *d_s = nullptr, *d_t = nullptr, *d_a = nullptr, *d_o = nullptr, *d_J = nullptr;
+    const size_t nm = (size_t)B * l_stride;
+    CK(cudaMalloc(&d_nl, B * sizeof(int32_t)));
+    CK(cudaMalloc(&d_s, nm * sizeof(double)));
+    CK(cudaMalloc(&d_t, nm * sizeof(double)));
+    CK(cudaMalloc(&d_a, B * sizeof(double)));
+    CK(cudaMalloc(&d_o, (size_t)B * C * sizeof(double)));
+    if (sens) CK(cudaMalloc(&d_J, (size_t)B * C * l_stride * sizeof(double)));
+    CK(cudaMemcpy(d_nl, nlayers, B * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_s, sigma, nm * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_t, thickness, nm * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_a, altitude, B * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = tdem_dev(sens, sv, B, l_stride, d_nl, d_s, d_t, d_a, d_o, d_J, precision, nullptr);
+    if (!rc) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(std::string("kernel: ") + cudaGetErrorString(e));
+    }
+    if (!rc) {
+        CK(cudaMemcpy(out, d_o, (size_t)B * C * sizeof(double), cudaMemcpyDeviceToHost));
+        if (sens) CK(cudaMemcpy(J, d_J, (size_t)B * C * l_stride * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_nl);
+    cudaFree(d_s);
+    cudaFree(d_t);
+    cudaFree(d_a);
+    cudaFree(d_o);
+    cudaFree(d_J);
+    return rc;
+}
+
+int gbp_tdem_forward_host(const gbp_tdem_survey* sv, int B, int l_stride, const int32_t* nlayers, const double* sigma,
+                          const double* thickness, const double* altitude, double* out, int precision, int device)
+{
+    return tdem_host(false, sv, B, l_stride, nlayers, sigma, thickness, altitude, out, nullptr, precision, device);
+}
+
+int gbp_tdem_sensitivity_host(const gbp_tdem_survey* sv, int B, int l_stride, const int32_t* nlayers, const double* sigma,
+                              const double* thickness, const double* altitude, double* out, double* J, int precision,
+                              int device)
+{
+    return tdem_host(true, sv, B, l_stride, nlayers, sigma, thickness, altitude, out, J, precision, device);
+}
+
+int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B, const double* d_data,
+                        const double* d_altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                        const gbp_chain_buffers* d_buf, int precision, void* stream)
+{
+    if (B <= 0) return 0;
+    if (check_options(opt)) return 1;
+    if (!d_buf || !d_buf->scalars) return fail("gbp_chain_buffers.scalars is required");
+    if ((opt->n_systems > 1 ? 2 : 1) != sv->n_systems)
+        return fail("gbp_options.n_systems must equal the number of systems of the datapoint type");
+    TdCache* tc;
+    if (get_td_tables(sv, &tc, true)) return 1;
+    ChainParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.opt = *opt;
+    P.B = B;
+    P.n_depth = gbp_n_depth(opt);
+    P.C = tc->host.dev.C;
+    P.data = d_data;
+    P.altitude = d_altitude;
+    P.seed = seed;
+    P.first_index = first_index;
+    P.max_iterations = max_iterations;
+    P.out = *d_buf;
+    P.data_scale = 1.0;
+    if (get_counter(&P.work_counter)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const TdDev& sd = tc->host.dev;
+    if (precision == GBP_PRECISION_F32) {
+        // scaled data units: additive errors scale with the data
+        P.data_scale = TD_F32_SCALE;
+        P.opt.add_init *= TD_F32_SCALE;
+        P.opt.add_min *= TD_F32_SCALE;
+        P.opt.add_max *= TD_F32_SCALE;
+        P.opt.add_init2 *= TD_F32_SCALE;
+        P.opt.add_min2 *= TD_F32_SCALE;
+        P.opt.add_max2 *= TD_F32_SCALE;
+        return launch_chain<float, float, 48, 16, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
+    }
+    if (precision == GBP_PRECISION_F64)
+        return launch_chain<double, double, 48, 8, KIND_TDEM>(sd, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
+    return fail("precision must be 32 or 64");
+}
+
+int gbp_tdem_rjmcmc_run_host(const gbp_tdem_survey* sv, const gbp_options* opt, int B, const double* data,
+                             const double* altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                             const gbp_chain_buffers* h, int precision, int device)
+{
+    for (int b = 0; b < B; ++b)
+        if (!(altitude[b] > 0.0)) return fail("Sensor altitude must be above the top of the model");
+    return rjmcmc_host_impl(gbp_tdem_n_channels(sv), opt, B, data, altitude, h, device,
+                            [&](const double* d_data, const double* d_alt, const gbp_chain_buffers* d) {
+                                return gbp_tdem_rjmcmc_run(sv, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
+                                                           precision, nullptr);
+                            });
 }
 
 }  // extern "C"

@@ -29,6 +29,7 @@
 #pragma once
 #include "gbp_fdem.cuh"
 #include "gbp_fdem_f2.cuh"
+#include "gbp_tdem.cuh"
 
 namespace gbp {
 
@@ -37,7 +38,30 @@ enum { ACT_BIRTH = 0, ACT_DEATH = 1, ACT_MOVE = 2, ACT_NONE = 3 };
 // cold per-chain integers kept in shared memory
 enum { CT_N_ACCEPT = 0, CT_N_FWD, CT_N_SENS, CT_ACT0, CT_ACT1, CT_ACT2, CT_ACT3, CT_BEST_K, CT_BEST_ITER, CT_BURN_ITER,
        CT_N_ZERO, CT_N_RESETS, CT_LIMITERS, CT_ACC_WIN, CT_TO_PLOT, CT_N = 16 };
-enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_N = 4 };
+enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_REL2, BV_ADD2, BV_N = 8 };
+
+// KIND of datapoint a kernel instantiation inverts: frequency domain (FdemDataPoint, one system) or time
+// domain (TdemDataPoint, one or two systems with per-system errors, TdemDataPoint.py:329-379)
+enum { KIND_FDEM = 0, KIND_TDEM = 1 };
+__host__ __device__ constexpr int ns_of(int kind) { return kind == KIND_TDEM ? GBP_TD_MAXSYS : 1; }
+template <typename T, int KIND> struct SysOf {
+    typedef SysShared<T> shared;
+    typedef SysDev dev;
+};
+template <typename T> struct SysOf<T, KIND_TDEM> {
+    typedef TdShared<T> shared;
+    typedef TdDev dev;
+};
+// per-chain scratch of the forward operator
+template <typename T, int KIND> struct FwdExtra {};
+template <typename T> struct FwdExtra<T, KIND_TDEM> {
+    T lam[GBP_TD_MAXLAM], wgt[GBP_TD_MAXLAM];  // this sounding's Hankel abscissae and geometry weights
+    T sbuf[TD_ROWS];
+};
+// relative / additive errors, one per system (registers)
+template <typename R, int NS> struct Errs {
+    R rel[NS], add[NS];
+};
 enum { OP_HITMAP = 0, OP_EDGES, OP_NCELLS, OP_REL, OP_ADD, OP_MISFIT, OP_ACCEPT, OP_N = 8 };
 
 template <typename R> struct MeshBuf {
@@ -50,7 +74,7 @@ template <typename R> struct ValBuf {
     R ls[GBP_MAXL];         // ln(conductivity)
 };
 
-template <typename R, typename T, int NC> struct __align__(16) WarpState {
+template <typename R, typename T, int NC, int KIND> struct __align__(16) WarpState {
     R A[NPACK];             // packed lower triangle: Gauss-Newton matrix, then its Cholesky factor
     MeshBuf<R> mesh[2];
     ValBuf<R> val[2];
@@ -64,6 +88,7 @@ template <typename R, typename T, int NC> struct __align__(16) WarpState {
     int ctr[CT_N];          // cold counters
     R bestv[BV_N];          // best posterior / errors
     void* outp[OP_N];       // this chain's output rows
+    FwdExtra<T, KIND> fx;
 };
 
 // Option-derived constants, computed once per CTA in fp64 and shared by its warps.
@@ -74,12 +99,16 @@ template <typename R> struct Consts {
     R lp_k;                                   // -ln(kmax - 1)
     R c_grad, c_val;                          // per-dimension constants of the gradient / value prior
     R half_log2pi;
-    R rel_lnmin, rel_lnmax, rel_sd, rel_lp, rel_ln0, rel0;
-    R add_lnmin, add_lnmax, add_sd, add_lp, add_ln0, add0;
-    R sig_halfspan, sig_dx, rel_dx, add_dx, depth_step, depth_max;
+    R rel_lnmin[2], rel_lnmax[2], rel_sd[2], rel_ln0[2], rel0[2], rel_dx[2];   // per system
+    R add_lnmin[2], add_lnmax[2], add_sd[2], add_ln0[2], add0[2], add_dx[2];
+    R err_lp;                                 // log prior of the (always in-bounds) errors, all systems
+    R sig_halfspan, sig_dx, depth_step, depth_max;
     R ln_half, ln_3half;
     int kmax, n_depth, n_sig, n_err, C, solve_par, solve_grad, solve_rel, solve_add;
     int n_chains, upe, burn_min, reset_limit;
+    int n_sys;
+    R tsc[GBP_TD_MAXC];                       // additive-error scale of channel c (time domain), else unused
+    unsigned char csys[GBP_TD_MAXC];          // system of channel c
 };
 
 struct ChainParams {
@@ -90,6 +119,8 @@ struct ChainParams {
     unsigned long long seed, first_index;
     long long max_iterations;
     gbp_chain_buffers out;
+    double data_scale;       // observed data and additive errors are multiplied by this on the way in (fp32
+                             // time-domain path: 2^40, so that squares of 1e-15 V/Am^4 stay normal numbers)
     int* work_counter;
     void* jstore;            // [B][NC*KS] of T: Jacobian of each chain's current model
 };
@@ -113,22 +144,41 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
     c.c_grad = (R)(-0.5 * l2pi - 0.5 * dlog_(g2));
     c.c_val = (R)(-0.5 * l2pi - 0.5 * dlog_(s * s));
     c.half_log2pi = (R)(0.5 * l2pi);
-    c.rel_lnmin = (R)dlog_(o.rel_min);
-    c.rel_lnmax = (R)dlog_(o.rel_max);
-    c.rel_sd = (R)::sqrt(o.rel_prop_var);
-    c.rel_lp = (R)(-dlog_(dlog_(o.rel_max) - dlog_(o.rel_min)));
-    c.rel_ln0 = (R)dlog_(o.rel_init);
-    c.rel0 = (R)o.rel_init;
-    c.add_lnmin = (R)dlog_(o.add_min);
-    c.add_lnmax = (R)dlog_(o.add_max);
-    c.add_sd = (R)::sqrt(o.add_prop_var);
-    c.add_lp = (R)(-dlog_(dlog_(o.add_max) - dlog_(o.add_min)));
-    c.add_ln0 = (R)dlog_(o.add_init);
-    c.add0 = (R)o.add_init;
+    c.n_sys = o.n_systems > 1 ? 2 : 1;
+    double lp = 0.0;
+    for (int i = 0; i < c.n_sys; ++i) {
+        const double rmin = i ? o.rel_min2 : o.rel_min, rmax = i ? o.rel_max2 : o.rel_max;
+        const double amin = i ? o.add_min2 : o.add_min, amax = i ? o.add_max2 : o.add_max;
+        c.rel_lnmin[i] = (R)dlog_(rmin);
+        c.rel_lnmax[i] = (R)dlog_(rmax);
+        c.rel_sd[i] = (R)::sqrt(i ? o.rel_prop_var2 : o.rel_prop_var);
+        c.rel_ln0[i] = (R)dlog_(i ? o.rel_init2 : o.rel_init);
+        c.rel0[i] = (R)(i ? o.rel_init2 : o.rel_init);
+        c.rel_dx[i] = (R)((dlog_(rmax) - dlog_(rmin)) / (double)o.n_err_bins);
+        c.add_lnmin[i] = (R)dlog_(amin);
+        c.add_lnmax[i] = (R)dlog_(amax);
+        c.add_sd[i] = (R)::sqrt(i ? o.add_prop_var2 : o.add_prop_var);
+        c.add_ln0[i] = (R)dlog_(i ? o.add_init2 : o.add_init);
+        c.add0[i] = (R)(i ? o.add_init2 : o.add_init);
+        c.add_dx[i] = (R)((dlog_(amax) - dlog_(amin)) / (double)o.n_err_bins);
+        // Uniform(log=True) priors: the proposals are forced inside their bounds (or fall back to the current
+        // values), so DataPoint.probability (:351-395) is this constant
+        if (o.solve_relative_error) lp += -dlog_(dlog_(rmax) - dlog_(rmin));
+        if (o.solve_additive_error) lp += -dlog_(dlog_(amax) - dlog_(amin));
+    }
+    if (c.n_sys == 1) {
+        c.rel_lnmin[1] = c.rel_lnmin[0]; c.rel_lnmax[1] = c.rel_lnmax[0]; c.rel_sd[1] = c.rel_sd[0];
+        c.rel_ln0[1] = c.rel_ln0[0]; c.rel0[1] = c.rel0[0]; c.rel_dx[1] = c.rel_dx[0];
+        c.add_lnmin[1] = c.add_lnmin[0]; c.add_lnmax[1] = c.add_lnmax[0]; c.add_sd[1] = c.add_sd[0];
+        c.add_ln0[1] = c.add_ln0[0]; c.add0[1] = c.add0[0]; c.add_dx[1] = c.add_dx[0];
+    }
+    c.err_lp = (R)lp;
+    for (int i = 0; i < GBP_TD_MAXC; ++i) {
+        c.tsc[i] = R(1);
+        c.csys[i] = 0;
+    }
     c.sig_halfspan = (R)(o.sigma_bins_nstd * s);
     c.sig_dx = (R)(2.0 * o.sigma_bins_nstd * s / (double)o.n_sigma_bins);
-    c.rel_dx = (R)((dlog_(o.rel_max) - dlog_(o.rel_min)) / (double)o.n_err_bins);
-    c.add_dx = (R)((dlog_(o.add_max) - dlog_(o.add_min)) / (double)o.n_err_bins);
     c.depth_step = (R)(0.5 * o.min_width);
     c.depth_max = (R)((double)n_depth * 0.5 * o.min_width);
     c.ln_half = (R)dlog_(0.5);
@@ -174,9 +224,9 @@ template <typename R> __device__ __forceinline__ R warp_min(R v)
 
 // ================================================================ shared, non-inlined helpers
 // J == nullptr: forward only.  Otherwise forward + Jacobian in one pass (FdemDataPoint.fm_dlogc :535)
-template <typename R, typename T, int NC>
-__device__ __noinline__ void ch_forward(WarpState<R, T, NC>* w, const SysShared<T>* S, const T* tab, T alt, int kk,
-                                        const R* sig, const R* edges, T* pred, T* J)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const typename SysOf<T, KIND>::shared* S, const T* tab,
+                                        T alt, int kk, const R* sig, const R* edges, T* pred, T* J)
 {
     GBP_SHARED(w);
     GBP_SHARED(sig);
@@ -191,36 +241,58 @@ __device__ __noinline__ void ch_forward(WarpState<R, T, NC>* w, const SysShared<
         if (J) w->ctr[CT_N_SENS]++;
     }
     __syncwarp();
-    fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
+    if constexpr (KIND == KIND_TDEM)
+        tdem_eval<T>(*S, tab, w->fx.lam, w->fx.wgt, kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
+    else
+        fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
 }
 
 // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
-template <typename R, typename T, int NC> __device__ __noinline__ void ch_set_ivar(WarpState<R, T, NC>* w, int C, R r, R a)
+// TdemDataPoint.std :329-379: per-system errors, additive error of channel c times (t_c / 1 ms)^-0.5
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_set_ivar(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, int C, Errs<R, ns_of(KIND)> e)
 {
     GBP_SHARED(w);
+    GBP_SHARED(K);
     const int lane = lane_id();
-    if (lane < C) {
-        R d = w->data[lane];
-        R s = r * d;
-        w->ivar[lane] = (d > R(0)) ? R(1) / (s * s + a * a) : R(0);
+#pragma unroll
+    for (int p = 0; p < (NC + 31) / 32; ++p) {
+        const int c = lane + 32 * p;
+        if (c < C) {
+            R d = w->data[c];
+            R r = e.rel[0], a = e.add[0];
+            if constexpr (KIND == KIND_TDEM) {
+                if (K->csys[c]) {
+                    r = e.rel[ns_of(KIND) - 1];
+                    a = e.add[ns_of(KIND) - 1];
+                }
+                a *= K->tsc[c];
+            }
+            R s = r * d;
+            w->ivar[c] = (d > R(0)) ? R(1) / (s * s + a * a) : R(0);
+        }
     }
     __syncwarp();
 }
 
 // misfit (DataPoint.py:502-525) and Gaussian log-likelihood (MvNormalDistribution.py:209-216)
-template <typename R, typename T, int NC>
-__device__ __noinline__ pair_t<R> ch_misfit_like(WarpState<R, T, NC>* w, int C, R n_active_half_log2pi, const T* pred)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ pair_t<R> ch_misfit_like(WarpState<R, T, NC, KIND>* w, int C, R n_active_half_log2pi, const T* pred)
 {
     GBP_SHARED(w);
     GBP_SHARED(pred);
     const int lane = lane_id();
     R q = R(0), ld = R(0);
-    if (lane < C) {
-        R iv = w->ivar[lane];
-        if (iv > R(0)) {
-            R r = (R)pred[lane] - w->data[lane];
-            q = r * r * iv;
-            ld = -rt<R>::log(iv);
+#pragma unroll
+    for (int p = 0; p < (NC + 31) / 32; ++p) {
+        const int c = lane + 32 * p;
+        if (c < C) {
+            R iv = w->ivar[c];
+            if (iv > R(0)) {
+                R r = (R)pred[c] - w->data[c];
+                q += r * r * iv;
+                ld += -rt<R>::log(iv);
+            }
         }
     }
     q = warp_sum(q);
@@ -295,8 +367,8 @@ template <typename R> __device__ __forceinline__ R prior_op(const Consts<R>* K, 
 }
 
 // gradient of lane i: Wm'Wm (ln s - ln ref) + J' Wd'Wd (pred - d)   (Model.local_gradient :347-357)
-template <typename R, typename T, int NC>
-__device__ __noinline__ R ch_gradient(WarpState<R, T, NC>* w, const Consts<R>* K, int kk, const R* t2, const R* ls,
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ R ch_gradient(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, int kk, const R* t2, const R* ls,
                                       const T* J, const T* pred, R ln_ref)
 {
     GBP_SHARED(w);
@@ -319,8 +391,8 @@ __device__ __noinline__ R ch_gradient(WarpState<R, T, NC>* w, const Consts<R>* K
 }
 
 // A = Wm'Wm + J' Wd'Wd J (Model.local_precision :250-272), packed lower triangle
-template <typename R, typename T, int NC>
-__device__ __noinline__ void ch_assemble(WarpState<R, T, NC>* w, const Consts<R>* K, int kk, const R* t2, const T* J)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_assemble(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, int kk, const R* t2, const T* J)
 {
     GBP_SHARED(w);
     GBP_SHARED(K);
@@ -426,10 +498,41 @@ template <typename R> __device__ __noinline__ prop_t<R> ch_propose_ln_error(Rng 
     return prop_t<R>{x, g.block};
 }
 
+// Dual-moment datapoint: the 2-vector is proposed jointly (MvLogNormal with diagonal variance) and re-drawn, at
+// most 10 times, while ANY component leaves its prior; then the whole vector falls back (StatArray.py:619-636).
+// One Box-Muller pair per draw.
+template <typename R> struct prop2_t {
+    R x0, x1;
+    uint32_t block;
+};
+template <typename R>
+__device__ __noinline__ prop2_t<R> ch_propose_ln_error2(Rng g, R c0, R c1, const R* sd, const R* lnmin, const R* lnmax)
+{
+    GBP_SHARED(sd);
+    GBP_SHARED(lnmin);
+    GBP_SHARED(lnmax);
+    pair_t<R> z = normal2_at<R>(g.block++, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
+    R x0 = c0 + sd[0] * z.a, x1 = c1 + sd[1] * z.b;
+    int tries = 0;
+#pragma unroll 1
+    while (x0 < lnmin[0] || x0 > lnmax[0] || x1 < lnmin[1] || x1 > lnmax[1]) {
+        z = normal2_at<R>(g.block++, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
+        x0 = c0 + sd[0] * z.a;
+        x1 = c1 + sd[1] * z.b;
+        tries++;
+        if (tries == 10) {
+            x0 = c0;
+            x1 = c1;
+            break;
+        }
+    }
+    return prop2_t<R>{x0, x1, g.block};
+}
+
 // add `count` visits of the current model / errors to every histogram
-template <typename R, typename T, int NC>
-__device__ __noinline__ void ch_flush(WarpState<R, T, NC>* w, const Consts<R>* K, int k, int mcur, int vcur, R ln_rel,
-                                      R ln_add, R sig_lo, int count)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_flush(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, int k, int mcur, int vcur,
+                                      Errs<R, ns_of(KIND)> ln_err, R sig_lo, int count)
 {
     GBP_SHARED(w);
     GBP_SHARED(K);
@@ -445,8 +548,13 @@ __device__ __noinline__ void ch_flush(WarpState<R, T, NC>* w, const Consts<R>* K
         int32_t* rh = (int32_t*)w->outp[OP_REL];
         int32_t* ah = (int32_t*)w->outp[OP_ADD];
         if (nc) nc[k] += count;
-        if (rh && K->solve_rel) rh[uniform_bin<R>(ln_rel, K->rel_lnmin, K->rel_dx, neb)] += count;
-        if (ah && K->solve_add) ah[uniform_bin<R>(ln_add, K->add_lnmin, K->add_dx, neb)] += count;
+#pragma unroll
+        for (int s = 0; s < ns_of(KIND); ++s) {
+            if (s < K->n_sys) {
+                if (rh && K->solve_rel) rh[s * neb + uniform_bin<R>(ln_err.rel[s], K->rel_lnmin[s], K->rel_dx[s], neb)] += count;
+                if (ah && K->solve_add) ah[s * neb + uniform_bin<R>(ln_err.add[s], K->add_lnmin[s], K->add_dx[s], neb)] += count;
+            }
+        }
     }
     // per-layer conductivity bin; interface histogram (RectilinearMesh1D.update_posteriors :1594-1610):
     // ratio sigma_i / sigma_{i-1} <= 0.5 or >= 1.5
@@ -485,7 +593,8 @@ __device__ __noinline__ void ch_flush(WarpState<R, T, NC>* w, const Consts<R>* K
     __syncwarp();
 }
 
-template <typename R, typename T, int NC> __device__ __noinline__ void ch_zero_posteriors(WarpState<R, T, NC>* w, const Consts<R>* K)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_zero_posteriors(WarpState<R, T, NC, KIND>* w, const Consts<R>* K)
 {
     GBP_SHARED(w);
     GBP_SHARED(K);
@@ -507,17 +616,17 @@ template <typename R, typename T, int NC> __device__ __noinline__ void ch_zero_p
     }
     if ((p = (int32_t*)w->outp[OP_REL])) {
 #pragma unroll 1
-        for (int i = lane; i < K->n_err; i += 32) p[i] = 0;
+        for (int i = lane; i < K->n_sys * K->n_err; i += 32) p[i] = 0;
     }
     if ((p = (int32_t*)w->outp[OP_ADD])) {
 #pragma unroll 1
-        for (int i = lane; i < K->n_err; i += 32) p[i] = 0;
+        for (int i = lane; i < K->n_sys * K->n_err; i += 32) p[i] = 0;
     }
     __syncwarp();
 }
 
-template <typename R, typename T, int NC>
-__device__ __noinline__ void ch_write_model(WarpState<R, T, NC>* w, int ml, int k, int mcur, int vcur, double* sig_out, double* edges_out)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_write_model(WarpState<R, T, NC, KIND>* w, int ml, int k, int mcur, int vcur, double* sig_out, double* edges_out)
 {
     GBP_SHARED(w);
     const int lane = lane_id();
@@ -547,15 +656,22 @@ template <typename R> struct init_out {
 
 // Inference1D.initialize :353-464 / initialize_model :485-535: best half-space, first forward + Jacobian,
 // initial misfit / likelihood / prior, cold counters.  `first == false` is reset() (:984-999).
-template <typename R, typename T, int NC>
-__device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC>* w, const Consts<R>* K, const SysShared<T>* S, const T* tab,
-                                                  T alt, R nahl, bool first, double* best_sig_out, double* best_edg_out)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC, KIND>* w, const Consts<R>* K,
+                                                  const typename SysOf<T, KIND>::shared* S, const T* tab, T alt, R nahl,
+                                                  bool first, double* best_sig_out, double* best_edg_out)
 {
     GBP_SHARED(w);
     GBP_SHARED(K);
     const int lane = lane_id();
     const int C = K->C;
-    ch_set_ivar(w, C, K->rel0, K->add0);
+    Errs<R, ns_of(KIND)> e0;
+#pragma unroll
+    for (int s = 0; s < ns_of(KIND); ++s) {
+        e0.rel[s] = K->rel0[s];
+        e0.add[s] = K->add0[s];
+    }
+    ch_set_ivar(w, K, C, e0);
     // EmDataPoint.find_best_halfspace :148-186: argmin misfit over logspace(-4, 4, 100)
     MeshBuf<R>& m = w->mesh[0];
     ValBuf<R>& v = w->val[0];
@@ -606,10 +722,7 @@ __device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC>* w, const 
     const pair_t<R> ml0 = ch_misfit_like(w, C, nahl, w->pred[0]);
     io.misfit = ml0.a;
     io.likelihood = ml0.b;
-    R dp = R(0);
-    if (K->solve_rel) dp += K->rel_lp;
-    if (K->solve_add) dp += K->add_lp;
-    io.prior = ch_model_prob(K, 1, v.ls, m.lnh, io.ln_ref) + dp;
+    io.prior = ch_model_prob(K, 1, v.ls, m.lnh, io.ln_ref) + K->err_lp;
     if (lane == 0) {
         double* mt = (double*)w->outp[OP_MISFIT];
         if (mt) mt[0] = (double)io.misfit;
@@ -620,17 +733,19 @@ __device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC>* w, const 
         w->ctr[CT_BEST_K] = 1;
         w->ctr[CT_BEST_ITER] = 0;
         w->bestv[BV_POSTERIOR] = io.likelihood + io.prior;
-        w->bestv[BV_REL] = K->rel0;
-        w->bestv[BV_ADD] = K->add0;
+        w->bestv[BV_REL] = K->rel0[0];
+        w->bestv[BV_ADD] = K->add0[0];
+        w->bestv[BV_REL2] = K->rel0[1];
+        w->bestv[BV_ADD2] = K->add0[1];
     }
     ch_write_model(w, K->kmax, 1, 0, 0, best_sig_out, best_edg_out);
     __syncwarp();
     return io;
 }
 
-template <typename R, typename T, int NC>
-__device__ __noinline__ void ch_save_best(WarpState<R, T, NC>* w, int ml, int k, int mcur, int vcur, int iteration, R posterior,
-                                          R rel, R add, double* best_sig_out, double* best_edg_out)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_save_best(WarpState<R, T, NC, KIND>* w, int ml, int k, int mcur, int vcur, int iteration,
+                                          R posterior, Errs<R, ns_of(KIND)> e, double* best_sig_out, double* best_edg_out)
 {
     GBP_SHARED(w);
     ch_write_model(w, ml, k, mcur, vcur, best_sig_out, best_edg_out);
@@ -638,17 +753,22 @@ __device__ __noinline__ void ch_save_best(WarpState<R, T, NC>* w, int ml, int k,
         w->ctr[CT_BEST_K] = k;
         w->ctr[CT_BEST_ITER] = iteration;
         w->bestv[BV_POSTERIOR] = posterior;
-        w->bestv[BV_REL] = rel;
-        w->bestv[BV_ADD] = add;
+        w->bestv[BV_REL] = e.rel[0];
+        w->bestv[BV_ADD] = e.add[0];
+        w->bestv[BV_REL2] = e.rel[ns_of(KIND) - 1];
+        w->bestv[BV_ADD2] = e.add[ns_of(KIND) - 1];
     }
     __syncwarp();
 }
 
 // ================================================================ the chain (inlined into the kernel)
-template <typename R, typename T, int NC>
-__device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R>* K, const SysShared<T>* S, const T* tab,
-                                          const ChainParams& P, const int chain)
+template <typename R, typename T, int NC, int KIND>
+__device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Consts<R>* K,
+                                          const typename SysOf<T, KIND>::shared* S, const typename SysOf<T, KIND>::dev& Sdev,
+                                          const T* tab, const ChainParams& P, const int chain)
 {
+    constexpr int NS = ns_of(KIND);
+    typedef Errs<R, NS> errs_t;
     GBP_SHARED(w);
     GBP_SHARED(K);
     const int lane = lane_id();
@@ -672,27 +792,34 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
     bool j_valid = true;  // the shared-memory Jacobian is the current model's
     T* const jg = (T*)P.jstore + (size_t)chain * NC * KS;
     constexpr int JBYTES = NC * KS * (int)sizeof(T);
-    R ln_rel, ln_add, rel, add, ln_ref = R(0), sig_lo = R(0);
+    errs_t ln_err, err;  // ln(relative / additive error) and the errors themselves, per system
+    R ln_ref = R(0), sig_lo = R(0);
     double sigma_ref = 0.0;
     R misfit = R(0), prior = R(0), likelihood = R(0);
     int iteration = 0, burned_in = 0, dwell = 0;
 
     // ---- per-chain setup
     int act = 0;
-    if (lane < C) {
-        const double d = P.data[(size_t)chain * C + lane];
-        act = d > 0.0;               // EmDataPoint.active: observed > 0 and not NaN
-        w->data[lane] = act ? (R)d : R(0);
+#pragma unroll
+    for (int p = 0; p < (NC + 31) / 32; ++p) {
+        const int c = lane + 32 * p;
+        if (c < C) {
+            const double d = P.data[(size_t)chain * C + c];
+            const int a = d > 0.0;   // EmDataPoint.active: observed > 0 and not NaN
+            act += a;
+            w->data[c] = a ? (R)(d * P.data_scale) : R(0);
+        }
     }
     const int n_active = warp_sum_i(act);
+    if constexpr (KIND == KIND_TDEM) td_geometry<T>(Sdev, P.altitude[chain], w->fx.lam, w->fx.wgt);
     const R nahl = (R)n_active * K->half_log2pi;
     if (lane == 0) {
         const gbp_chain_buffers& o = P.out;
         w->outp[OP_HITMAP] = o.hitmap ? o.hitmap + (size_t)chain * K->n_sig * K->n_depth : nullptr;
         w->outp[OP_EDGES] = o.edges_hist ? o.edges_hist + (size_t)chain * K->n_depth : nullptr;
         w->outp[OP_NCELLS] = o.ncells_hist ? o.ncells_hist + (size_t)chain * (ml + 1) : nullptr;
-        w->outp[OP_REL] = o.rel_hist ? o.rel_hist + (size_t)chain * K->n_err : nullptr;
-        w->outp[OP_ADD] = o.add_hist ? o.add_hist + (size_t)chain * K->n_err : nullptr;
+        w->outp[OP_REL] = o.rel_hist ? o.rel_hist + (size_t)chain * K->n_sys * K->n_err : nullptr;
+        w->outp[OP_ADD] = o.add_hist ? o.add_hist + (size_t)chain * K->n_sys * K->n_err : nullptr;
         w->outp[OP_MISFIT] = o.misfit_trace ? o.misfit_trace + (size_t)chain * N2 : nullptr;
         w->outp[OP_ACCEPT] = o.accept_trace ? o.accept_trace + (size_t)chain * N2 : nullptr;
         for (int i = 0; i < CT_N; ++i) w->ctr[i] = 0;
@@ -703,14 +830,17 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
 
     // Inference1D.initialize :353-464 (also used by reset() :984-999): cold, one shared copy
     auto initialize = [&](bool first) {
-        const init_out<R> io = ch_initialize<R, T, NC>(w, K, S, tab, alt, nahl, first, GBP_BEST_SIG, GBP_BEST_EDG);
+        const init_out<R> io = ch_initialize<R, T, NC, KIND>(w, K, S, tab, alt, nahl, first, GBP_BEST_SIG, GBP_BEST_EDG);
         mcur = vcur = pcur = 0;
         ch_copy16(jg, w->J, JBYTES);
         j_valid = true;
-        ln_rel = K->rel_ln0;
-        ln_add = K->add_ln0;
-        rel = K->rel0;
-        add = K->add0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            ln_err.rel[s] = K->rel_ln0[s];
+            ln_err.add[s] = K->add_ln0[s];
+            err.rel[s] = K->rel0[s];
+            err.add[s] = K->add0[s];
+        }
         sigma_ref = io.sigma_ref;
         ln_ref = io.ln_ref;
         sig_lo = ln_ref - K->sig_halfspan;  // Model.set_posteriors :666-684
@@ -723,7 +853,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         dwell = 0;
     };
     auto save_best = [&]() {
-        ch_save_best<R, T, NC>(w, ml, k, mcur, vcur, iteration, likelihood + prior, rel, add, GBP_BEST_SIG, GBP_BEST_EDG);
+        ch_save_best<R, T, NC, KIND>(w, ml, k, mcur, vcur, iteration, likelihood + prior, err, GBP_BEST_SIG, GBP_BEST_EDG);
     };
 
     initialize(true);
@@ -859,7 +989,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
                 ch_copy16(w->J, jg, JBYTES);
                 j_valid = true;
             }
-            ch_set_ivar(w, C, rel, add);
+            ch_set_ivar(w, K, C, err);
             const R ln_r = (lane < kn) ? w->ls_r[lane] : R(0);
             const R g = ch_gradient(w, K, kn, mesh_p.t2, w->ls_r, Jh, ph, ln_ref);
             ch_assemble(w, K, kn, mesh_p.t2, Jh);
@@ -883,31 +1013,47 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
                 __syncwarp();
 
                 // ---- test_datapoint.perturb() (DataPoint.py:531-573)
-                R lr_t = ln_rel, la_t = ln_add;
-                if (K->solve_rel) {
-                    const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_rel, K->rel_sd, K->rel_lnmin, K->rel_lnmax);
-                    lr_t = pr.x;
-                    rng.block = pr.block;
+                errs_t ln_t_err = ln_err, err_t = err;
+                if (NS == 1 || K->n_sys == 1) {
+                    if (K->solve_rel) {
+                        const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_err.rel[0], K->rel_sd[0], K->rel_lnmin[0], K->rel_lnmax[0]);
+                        ln_t_err.rel[0] = pr.x;
+                        rng.block = pr.block;
+                    }
+                    if (K->solve_add) {
+                        const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_err.add[0], K->add_sd[0], K->add_lnmin[0], K->add_lnmax[0]);
+                        ln_t_err.add[0] = pr.x;
+                        rng.block = pr.block;
+                    }
+                } else {
+                    if (K->solve_rel) {
+                        const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.rel[0], ln_err.rel[NS - 1], K->rel_sd, K->rel_lnmin, K->rel_lnmax);
+                        ln_t_err.rel[0] = pr.x0;
+                        ln_t_err.rel[NS - 1] = pr.x1;
+                        rng.block = pr.block;
+                    }
+                    if (K->solve_add) {
+                        const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.add[0], ln_err.add[NS - 1], K->add_sd, K->add_lnmin, K->add_lnmax);
+                        ln_t_err.add[0] = pr.x0;
+                        ln_t_err.add[NS - 1] = pr.x1;
+                        rng.block = pr.block;
+                    }
                 }
-                if (K->solve_add) {
-                    const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_add, K->add_sd, K->add_lnmin, K->add_lnmax);
-                    la_t = pr.x;
-                    rng.block = pr.block;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    err_t.rel[s] = (ln_t_err.rel[s] == ln_err.rel[s]) ? err.rel[s] : rt<R>::exp(ln_t_err.rel[s]);
+                    err_t.add[s] = (ln_t_err.add[s] == ln_err.add[s]) ? err.add[s] : rt<R>::exp(ln_t_err.add[s]);
                 }
-                const R rel_t = (lr_t == ln_rel) ? rel : rt<R>::exp(lr_t);
-                const R add_t = (la_t == ln_add) ? add : rt<R>::exp(la_t);
 
                 const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
                 // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
                 // (Model.proposal_probabilities :619) - fused into the same pass.
                 ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : (T*)nullptr);
-                ch_set_ivar(w, C, rel_t, add_t);
+                ch_set_ivar(w, K, C, err_t);
                 const pair_t<R> tml = ch_misfit_like(w, C, nahl, pred_t);
                 // error priors: the proposals above are forced inside their bounds (or fall back to the
-                // current values), so DataPoint.probability is the constant rel_lp + add_lp
-                R t_prior = R(0);
-                if (K->solve_rel) t_prior += K->rel_lp;
-                if (K->solve_add) t_prior += K->add_lp;
+                // current values), so DataPoint.probability is the constant err_lp
+                R t_prior = K->err_lp;
                 t_prior += ch_model_prob(K, kn, val_p.ls, mesh_p.lnh, ln_ref);
                 if (t_prior != (R)-INFINITY) {  // early reject on -inf prior (:581, :589): no accept draw
                     R proposal = R(1), proposal1 = R(1);
@@ -932,16 +1078,14 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
                     const R u = rng_uniform<R>(rng);
                     accepted = rt<R>::exp(log_alpha) > u;
                     if (accepted) {
-                        ch_flush(w, K, k, mcur, vcur, ln_rel, ln_add, sig_lo, dwell);  // the outgoing model's visits
+                        ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
                         dwell = 0;
                         misfit = tml.a;
                         prior = t_prior;
                         likelihood = tml.b;
                         k = kn;
-                        rel = rel_t;
-                        add = add_t;
-                        ln_rel = lr_t;
-                        ln_add = la_t;
+                        err = err_t;
+                        ln_err = ln_t_err;
                         mcur = mp;
                         vcur = vp;
                         pcur ^= 1;
@@ -1037,7 +1181,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         }
         if (P.max_iterations > 0 && total >= P.max_iterations) go = false;
     }
-    ch_flush(w, K, k, mcur, vcur, ln_rel, ln_add, sig_lo, dwell);
+    ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);
 
     ch_write_model(w, ml, k, mcur, vcur, P.out.cur_sigma ? P.out.cur_sigma + (size_t)chain * ml : nullptr,
                    P.out.cur_edges ? P.out.cur_edges + (size_t)chain * (ml + 1) : nullptr);
@@ -1056,14 +1200,23 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
         s[GBP_S_N_ACCEPT] = (double)w->ctr[CT_N_ACCEPT];
         s[GBP_S_N_FORWARD] = (double)w->ctr[CT_N_FWD];
         s[GBP_S_N_SENS] = (double)w->ctr[CT_N_SENS];
-        s[GBP_S_BEST_POSTERIOR] = (double)w->bestv[BV_POSTERIOR];
-        s[GBP_S_CUR_REL] = (double)rel;
-        s[GBP_S_CUR_ADD] = (double)add;
+        // undo the data scaling: variances scale by data_scale^2, so the log-likelihood shifts by n ln(scale)
+        const double inv_sc = 1.0 / P.data_scale;
+        const double lik_shift = (P.data_scale != 1.0) ? (double)n_active * dlog_(P.data_scale) : 0.0;
+        s[GBP_S_BEST_POSTERIOR] = (double)w->bestv[BV_POSTERIOR] + lik_shift;
+        s[GBP_S_CUR_REL] = (double)err.rel[0];
+        s[GBP_S_CUR_ADD] = (double)err.add[0] * inv_sc;
         s[GBP_S_CUR_MISFIT] = (double)misfit;
         s[GBP_S_CUR_PRIOR] = (double)prior;
-        s[GBP_S_CUR_LIKELIHOOD] = (double)likelihood;
+        s[GBP_S_CUR_LIKELIHOOD] = (double)likelihood + lik_shift;
         s[GBP_S_BEST_REL] = (double)w->bestv[BV_REL];
-        s[GBP_S_BEST_ADD] = (double)w->bestv[BV_ADD];
+        s[GBP_S_BEST_ADD] = (double)w->bestv[BV_ADD] * inv_sc;
+        if (NS > 1 && K->n_sys > 1) {
+            s[GBP_S_CUR_REL2] = (double)err.rel[NS - 1];
+            s[GBP_S_CUR_ADD2] = (double)err.add[NS - 1] * inv_sc;
+            s[GBP_S_BEST_REL2] = (double)w->bestv[BV_REL2];
+            s[GBP_S_BEST_ADD2] = (double)w->bestv[BV_ADD2] * inv_sc;
+        }
         s[GBP_S_N_RESETS] = w->ctr[CT_N_RESETS];
         s[GBP_S_N_BIRTH] = (double)w->ctr[CT_ACT0];
         s[GBP_S_N_DEATH] = (double)w->ctr[CT_ACT1];
@@ -1079,32 +1232,44 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC>* w, const Consts<R
 
 // ---------------------------------------------------------------- kernels
 // R = sampler arithmetic, T = forward/Jacobian arithmetic, NC = channel capacity, WARPS = warps per CTA
-template <typename R, typename T, int NC, int WARPS>
+// KIND_TDEM: S is the TdDev of the datapoint type and g_tab the window operator Mt (TD_ROWS x TD_CP)
+template <typename R, typename T, int NC, int WARPS, int KIND>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-    rjmcmc_kernel(const __grid_constant__ SysDev S, const T* __restrict__ g_tab, const __grid_constant__ ChainParams P)
+    rjmcmc_kernel(const __grid_constant__ typename SysOf<T, KIND>::dev S, const T* __restrict__ g_tab,
+                  const __grid_constant__ ChainParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ Consts<R> consts;
-    __shared__ SysShared<T> sys_s;
+    __shared__ typename SysOf<T, KIND>::shared sys_s;
     T* tab = reinterpret_cast<T*>(smem);
-    const uint32_t tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
+    uint32_t tab_bytes;
+    if constexpr (KIND == KIND_TDEM) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
+    else tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
     if (threadIdx.x == 0) {
         make_consts<R>(P.opt, P.n_depth, P.C, consts);
-        fill_sys_shared<T>(S, sys_s);
+        if constexpr (KIND == KIND_TDEM) {
+            fill_td_shared<T>(S, sys_s);
+            for (int i = 0; i < GBP_TD_MAXC; ++i) {
+                consts.tsc[i] = (R)S.tsc[i];
+                consts.csys[i] = (unsigned char)S.csys[i];
+            }
+        } else {
+            fill_sys_shared<T>(S, sys_s);
+        }
     }
     tma_stage(tab, g_tab, tab_bytes, &bar);
     __syncthreads();
     const uint32_t tab_pad = (tab_bytes + 127u) & ~127u;
     const int warp = threadIdx.x >> 5;
-    WarpState<R, T, NC>* ws = reinterpret_cast<WarpState<R, T, NC>*>(smem + tab_pad) + warp;
+    WarpState<R, T, NC, KIND>* ws = reinterpret_cast<WarpState<R, T, NC, KIND>*>(smem + tab_pad) + warp;
     // persistent: the first wave is dealt round-robin over the CTAs (one CTA per SM) so that a batch smaller
     // than the machine still spreads evenly; later chains are claimed from a device-side counter
     int c = warp * gridDim.x + blockIdx.x;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     while (c < P.B) {
-        run_chain<R, T, NC>(ws, &consts, &sys_s, tab, P, c);
+        run_chain<R, T, NC, KIND>(ws, &consts, &sys_s, S, tab, P, c);
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(P.work_counter, 1);
         c = __shfl_sync(FULL, nxt, 0);

@@ -10,7 +10,8 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import (BUFFER_FIELDS, NSCALARS, PRECISION_F32, PRECISION_F64, ChainBuffersC, FdemSystemC, OptionsC)
+from ._lib import (BUFFER_FIELDS, NSCALARS, PRECISION_F32, PRECISION_F64, ChainBuffersC, FdemSystemC, OptionsC,
+                   TdemSurveyC, TdemSystemC)
 
 _ORI = {"x": 0, "y": 1, "z": 2}
 
@@ -38,13 +39,89 @@ def resolve_system_struct():
         [0] * 6, list("zzxzzz"), [1] * 6, [7.93, 7.91, 9.03, 7.91, 7.91, 7.89], [0] * 6, [0] * 6)
 
 
+def make_tdem_system_struct(d):
+    """gbp_tdem_system from a parsed .stm description (tdem.read_stm / geobipy_b200/data/*.json)."""
+    s = TdemSystemC()
+    nw, nwin, nf = len(d["waveform_time"]), len(d["window_start"]), len(d["filter_cutoff"])
+    if nw > _lib.TD_MAXWAVE or nwin > _lib.TD_MAXWIN or nf > _lib.TD_MAXFILT:
+        raise ValueError("time-domain system too large for the C-ABI limits")
+    if d.get("x_scaling", 0.0) != 0.0 or d.get("y_scaling", 0.0) != 0.0 or d.get("z_scaling", 1.0) == 0.0:
+        raise ValueError("only Z-component systems are supported")
+    if str(d.get("output_type", "dB/dt")).strip().lower() != "db/dt":
+        raise ValueError("only dB/dt output is supported")
+    s.n_wave, s.n_windows, s.n_filters, s.n_abscissae = nw, nwin, nf, int(d["n_abscissae"])
+    s.base_frequency, s.digitising_frequency = float(d["base_frequency"]), float(d["digitising_frequency"])
+    s.loop_radius = float(d.get("loop_radius", 0.0))
+    for i in range(nw):
+        s.wave_time[i], s.wave_current[i] = float(d["waveform_time"][i]), float(d["waveform_current"][i])
+    for i in range(nwin):
+        s.window_start[i], s.window_end[i] = float(d["window_start"][i]), float(d["window_end"][i])
+    for i in range(nf):
+        s.filter_cutoff[i], s.filter_order[i] = float(d["filter_cutoff"][i]), int(d["filter_order"][i])
+    return s
+
+
+def make_tdem_survey_struct(definitions, rx_offset=(-13.0, 0.0, 2.0)):
+    """gbp_tdem_survey: the systems of one time-domain datapoint type + the transmitter->receiver offset."""
+    if not 1 <= len(definitions) <= _lib.TD_MAXSYS:
+        raise ValueError("a time-domain datapoint has 1..%d systems" % _lib.TD_MAXSYS)
+    sv = TdemSurveyC()
+    sv.n_systems = len(definitions)
+    for i, d in enumerate(definitions):
+        sv.sys[i] = make_tdem_system_struct(d)
+    sv.rx_dx, sv.rx_dy, sv.rx_dz = (float(v) for v in rx_offset)
+    return sv
+
+
+def skytem_definitions():
+    """SkyTEM high / low moment (documentation_source/source/supplementary/data/SkytemHM.stm, SkytemLM.stm)."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    return [json.load(open(os.path.join(d, n))) for n in ("skytem_hm.json", "skytem_lm.json")]
+
+
+def skytem_survey_struct(rx_offset=(-13.0, 0.0, 2.0)):
+    return make_tdem_survey_struct(skytem_definitions(), rx_offset)
+
+
+def is_tdem(system):
+    return isinstance(system, TdemSurveyC)
+
+
+def n_channels(system):
+    if is_tdem(system):
+        return int(_lib.load().gbp_tdem_n_channels(ctypes.addressof(system)))
+    return 2 * system.n_freq
+
+
+def tdem_window_operator(survey):
+    """(freq [32], MR [C, 32], MI [C, 32], t_centre [C]) - the model-independent tables of the time-domain path."""
+    C = n_channels(survey)
+    f, MR, MI, t = np.zeros(_lib.TD_NFREQ), np.zeros((C, _lib.TD_NFREQ)), np.zeros((C, _lib.TD_NFREQ)), np.zeros(C)
+    _lib.check(_lib.load().gbp_tdem_window_operator(ctypes.addressof(survey), f.ctypes.data, MR.ctypes.data,
+                                                    MI.ctypes.data, t.ctypes.data))
+    return f, MR, MI, t
+
+
+# skytem_options (documentation_source/source/supplementary/options_files/skytem_options); minimum_thickness None -> 1.0
+# (RectilinearMesh1D.py:358)
+SKYTEM_OPTIONS = dict(
+    min_edge=1.0, max_edge=550.0, min_width=1.0, covariance_scaling=0.5, n_systems=2,
+    rel_init=0.05, rel_min=0.005, rel_max=0.5, rel_prop_var=1e-6, add_init=2e-14, add_min=1e-16, add_max=1e-10,
+    add_prop_var=1e-5, rel_init2=0.05, rel_min2=0.005, rel_max2=0.5, rel_prop_var2=1e-6, add_init2=2e-13,
+    add_min2=1e-16, add_max2=1e-10, add_prop_var2=1e-5)
+
 _OPTION_DEFAULTS = dict(
     n_markov_chains=100000, update_plot_every=5000, max_layers=30, solve_parameter=0, solve_gradient=1,
     solve_relative_error=1, solve_additive_error=1, reset_limit=1, min_edge=0.1, max_edge=200.0, min_width=1.0,
     p_birth=1.0 / 6.0, p_death=1.0 / 6.0, p_move=1.0 / 6.0, p_none=0.5, factor=10.0, gradient_std=1.5,
     covariance_scaling=1.0, rel_init=0.05, rel_min=0.001, rel_max=0.5, rel_prop_var=1e-6, add_init=5.0,
     add_min=3.0, add_max=20.0, add_prop_var=1e-6, n_sigma_bins=250, n_err_bins=99, sigma_bins_nstd=4.0,
-    burn_in_min_iter=5000)
+    burn_in_min_iter=5000, n_systems=1,
+    rel_init2=0.05, rel_min2=0.001, rel_max2=0.5, rel_prop_var2=1e-6, add_init2=5.0, add_min2=3.0, add_max2=20.0,
+    add_prop_var2=1e-6)
+_PER_SYSTEM = ("rel_init", "rel_min", "rel_max", "rel_prop_var", "add_init", "add_min", "add_max", "add_prop_var")
 
 # reference option-file keys -> gbp_options fields (resolve_options; user_parameters.py:40-44)
 _REFERENCE_KEYS = dict(
@@ -74,6 +151,11 @@ def make_options(**kw):
         k = _REFERENCE_KEYS.get(k, k)
         if k not in vals:
             continue  # keys of the reference options file that do not concern the sampler kernel
+        if k in _PER_SYSTEM and np.size(v) > 1:  # per-system lists of a dual-moment options file (skytem_options)
+            v = np.asarray(v, dtype=np.float64).reshape(-1)
+            vals[k], vals[k + "2"] = float(v[0]), float(v[1])
+            vals["n_systems"] = 2
+            continue
         vals[k] = v
     o = OptionsC()
     for k, v in vals.items():
@@ -101,6 +183,9 @@ def posterior_grids(opt, halfspace):
     depth = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
     rel = np.exp(np.linspace(np.log(opt.rel_min), np.log(opt.rel_max), opt.n_err_bins + 1))
     add = np.exp(np.linspace(np.log(opt.add_min), np.log(opt.add_max), opt.n_err_bins + 1))
+    if opt.n_systems > 1:
+        rel = np.stack([rel, np.exp(np.linspace(np.log(opt.rel_min2), np.log(opt.rel_max2), opt.n_err_bins + 1))])
+        add = np.stack([add, np.exp(np.linspace(np.log(opt.add_min2), np.log(opt.add_max2), opt.n_err_bins + 1))])
     return dict(sigma_edges=sig, depth_edges=depth, rel_edges=rel, add_edges=add,
                 ncells_centres=np.arange(0.0, opt.max_layers + 1.0))
 
@@ -120,24 +205,28 @@ def fdem_forward(system, nlayers, sigma, thickness, altitude, precision=PRECISIO
     layer is an infinite half-space.  numpy in -> numpy out (host path); torch CUDA in -> torch out.
     """
     lib = _lib.require_cuda()
+    td = is_tdem(system)
+    f_fwd, f_sens = (lib.gbp_tdem_forward, lib.gbp_tdem_sensitivity) if td else (lib.gbp_fdem_forward, lib.gbp_fdem_sensitivity)
+    f_fwd_h, f_sens_h = ((lib.gbp_tdem_forward_host, lib.gbp_tdem_sensitivity_host) if td
+                         else (lib.gbp_fdem_forward_host, lib.gbp_fdem_sensitivity_host))
+    C = n_channels(system)
     if _is_torch(sigma):
         import torch
         assert sigma.is_cuda and sigma.dtype == torch.float64 and sigma.is_contiguous()
         B, ls = sigma.shape
-        F = system.n_freq
         thickness = thickness.contiguous()
         altitude = altitude.contiguous()
         nlayers = nlayers.to(torch.int32).contiguous()
-        out = torch.empty((B, 2 * F), dtype=torch.float64, device=sigma.device)
+        out = torch.empty((B, C), dtype=torch.float64, device=sigma.device)
         st = torch.cuda.current_stream(sigma.device).cuda_stream
         with torch.cuda.device(sigma.device):
             if sensitivity:
-                J = torch.empty((B, 2 * F, ls), dtype=torch.float64, device=sigma.device)
-                _lib.check(lib.gbp_fdem_sensitivity(ctypes.addressof(system), B, ls, nlayers.data_ptr(), sigma.data_ptr(),
+                J = torch.empty((B, C, ls), dtype=torch.float64, device=sigma.device)
+                _lib.check(f_sens(ctypes.addressof(system), B, ls, nlayers.data_ptr(), sigma.data_ptr(),
                                                     thickness.data_ptr(), altitude.data_ptr(), out.data_ptr(),
                                                     J.data_ptr(), precision, st))
                 return out, J
-            _lib.check(lib.gbp_fdem_forward(ctypes.addressof(system), B, ls, nlayers.data_ptr(), sigma.data_ptr(),
+            _lib.check(f_fwd(ctypes.addressof(system), B, ls, nlayers.data_ptr(), sigma.data_ptr(),
                                             thickness.data_ptr(), altitude.data_ptr(), out.data_ptr(), precision, st))
             return out
     sigma = _np(np.atleast_2d(sigma), np.float64)
@@ -146,27 +235,30 @@ def fdem_forward(system, nlayers, sigma, thickness, altitude, precision=PRECISIO
     nlayers = _np(np.atleast_1d(nlayers), np.int32)
     altitude = _np(np.atleast_1d(altitude), np.float64)
     assert thickness.shape == sigma.shape and nlayers.shape == (B,) and altitude.shape == (B,)
-    F = system.n_freq
-    out = np.empty((B, 2 * F))
+    out = np.empty((B, C))
     if sensitivity:
-        J = np.empty((B, 2 * F, ls))
-        _lib.check(lib.gbp_fdem_sensitivity_host(ctypes.addressof(system), B, ls, nlayers.ctypes.data, sigma.ctypes.data,
+        J = np.empty((B, C, ls))
+        _lib.check(f_sens_h(ctypes.addressof(system), B, ls, nlayers.ctypes.data, sigma.ctypes.data,
                                                  thickness.ctypes.data, altitude.ctypes.data, out.ctypes.data,
                                                  J.ctypes.data, precision, device))
         return out, J
-    _lib.check(lib.gbp_fdem_forward_host(ctypes.addressof(system), B, ls, nlayers.ctypes.data, sigma.ctypes.data,
+    _lib.check(f_fwd_h(ctypes.addressof(system), B, ls, nlayers.ctypes.data, sigma.ctypes.data,
                                          thickness.ctypes.data, altitude.ctypes.data, out.ctypes.data, precision, device))
     return out
+
+
+tdem_forward = None  # bound below: same operator, dispatched on the system type
 
 
 def chain_buffer_shapes(opt, B):
     nd = n_depth(opt)
     N2 = 2 * opt.n_markov_chains
     ml = opt.max_layers
+    eshape = (B, 2, opt.n_err_bins) if opt.n_systems > 1 else (B, opt.n_err_bins)
     return dict(
         hitmap=((B, opt.n_sigma_bins, nd), np.int32), edges_hist=((B, nd), np.int32),
-        ncells_hist=((B, ml + 1), np.int32), rel_hist=((B, opt.n_err_bins), np.int32),
-        add_hist=((B, opt.n_err_bins), np.int32), misfit_trace=((B, N2), np.float64),
+        ncells_hist=((B, ml + 1), np.int32), rel_hist=(eshape, np.int32),
+        add_hist=(eshape, np.int32), misfit_trace=((B, N2), np.float64),
         accept_trace=((B, N2), np.uint8), best_sigma=((B, ml), np.float64), best_edges=((B, ml + 1), np.float64),
         cur_sigma=((B, ml), np.float64), cur_edges=((B, ml + 1), np.float64), scalars=((B, NSCALARS), np.float64))
 
@@ -183,6 +275,8 @@ def rjmcmc_run(system, opt, data, altitude, seed=0, first_index=0, max_iteration
     result tensors to reuse).
     """
     lib = _lib.require_cuda()
+    td = is_tdem(system)
+    f_run, f_run_h = (lib.gbp_tdem_rjmcmc_run, lib.gbp_tdem_rjmcmc_run_host) if td else (lib.gbp_rjmcmc_run, lib.gbp_rjmcmc_run_host)
     outputs = tuple(outputs)
     if "scalars" not in outputs:
         outputs = outputs + ("scalars",)
@@ -207,14 +301,14 @@ def rjmcmc_run(system, opt, data, altitude, seed=0, first_index=0, max_iteration
             setattr(cb, name, t.data_ptr())
         st = torch.cuda.current_stream(data.device).cuda_stream
         with torch.cuda.device(data.device):
-            _lib.check(lib.gbp_rjmcmc_run(ctypes.addressof(system), ctypes.addressof(opt), B, data.data_ptr(),
+            _lib.check(f_run(ctypes.addressof(system), ctypes.addressof(opt), B, data.data_ptr(),
                                           altitude.data_ptr(), int(seed), int(first_index), int(max_iterations),
                                           ctypes.addressof(cb), precision, st))
         return res
     data = _np(np.atleast_2d(data), np.float64)
     altitude = _np(np.atleast_1d(altitude), np.float64)
     B = data.shape[0]
-    assert data.shape[1] == 2 * system.n_freq and altitude.shape == (B,)
+    assert data.shape[1] == n_channels(system) and altitude.shape == (B,)
     shapes = chain_buffer_shapes(opt, B)
     res = {}
     cb = ChainBuffersC()
@@ -223,7 +317,7 @@ def rjmcmc_run(system, opt, data, altitude, seed=0, first_index=0, max_iteration
         a = buffers[name] if (buffers is not None and name in buffers) else np.zeros(shp, dtype=dt)
         res[name] = a
         setattr(cb, name, a.ctypes.data)
-    _lib.check(lib.gbp_rjmcmc_run_host(ctypes.addressof(system), ctypes.addressof(opt), B, data.ctypes.data,
+    _lib.check(f_run_h(ctypes.addressof(system), ctypes.addressof(opt), B, data.ctypes.data,
                                        altitude.ctypes.data, int(seed), int(first_index), int(max_iterations),
                                        ctypes.addressof(cb), precision, device))
     return res
@@ -240,8 +334,18 @@ def launch_count():
 
 
 def flops_per_forward(system, n_layers):
+    if is_tdem(system):
+        return float(_lib.load().gbp_tdem_flops_per_forward(ctypes.addressof(system), int(n_layers)))
     return float(_lib.load().gbp_flops_per_forward(ctypes.addressof(system), int(n_layers)))
 
 
 def filter_points(system):
     return int(_lib.load().gbp_filter_points(ctypes.addressof(system)))
+
+
+def forward(system, nlayers, sigma, thickness, altitude, **kw):
+    """Forward / Jacobian operator of either datapoint type (FDEM system struct or time-domain survey struct)."""
+    return fdem_forward(system, nlayers, sigma, thickness, altitude, **kw)
+
+
+tdem_forward = forward

@@ -14,6 +14,12 @@
  *                          loop Inference3D.infer_serial / _infer_mpi_worker_task drive
  *                          (geobipy/src/inversion/Inference3D.py:458-492, :587-635).
  *
+ *   gbp_tdem_forward*      replaces TdemDataPoint.forward and the external gatdaem1d forward model it calls
+ *                          (classes/data/datapoint/TdemDataPoint.py:997-1022,
+ *                           classes/forwardmodelling/Electromagnetic/TD/tdem1d.py:89-96)
+ *   gbp_tdem_sensitivity*  replaces TdemDataPoint.sensitivity / fm_dlogc (TdemDataPoint.py:1024-1055, tdem1d.py:98-154)
+ *   gbp_tdem_rjmcmc_run*   the same sampler for time-domain (single or dual moment) datapoints
+ *
  * Plain pointers and sizes only.  "_host" entry points take HOST buffers and do the
  * host<->device copies themselves; the others take DEVICE pointers and a cudaStream_t
  * (passed as void*) and are stream ordered.  All functions return 0 on success, non-zero
@@ -32,6 +38,14 @@ extern "C" {
 #define GBP_MAXF 16              /* max frequencies of one FDEM system */
 #define GBP_MAXC (2 * GBP_MAXF)  /* max data channels (in-phase + quadrature) */
 #define GBP_MAXL 30              /* max layers (resolve_options: maximum_number_of_layers) */
+
+#define GBP_TD_MAXSYS 2          /* systems of one time-domain datapoint (SkyTEM: high + low moment) */
+#define GBP_TD_NFREQ 32          /* spline nodes of the frequency-domain response (one per lane) */
+#define GBP_TD_MAXLAM 32         /* Hankel abscissae */
+#define GBP_TD_MAXWIN 32         /* receiver windows of one system */
+#define GBP_TD_MAXC 64           /* data channels of one time-domain datapoint */
+#define GBP_TD_MAXWAVE 64        /* vertices of the current waveform */
+#define GBP_TD_MAXFILT 4         /* receiver low-pass filters */
 
 #define GBP_PRECISION_F32 32     /* forward / Jacobian arithmetic in fp32 (fast path) */
 #define GBP_PRECISION_F64 64     /* forward / Jacobian arithmetic in fp64 (validation path) */
@@ -65,8 +79,34 @@ typedef struct {
     int32_t n_err_bins;                 /* 99  (Uniform.bins default) */
     double sigma_bins_nstd;             /* 4.0 */
     int32_t burn_in_min_iter;           /* 5000 (Inference1D.py:726) */
-    int32_t pad_;
+    int32_t n_systems;                  /* 0 or 1: one system.  2: dual-moment datapoint, the *2 fields below are the
+                                           second entries of the options file's lists (skytem_options) */
+    double rel_init2, rel_min2, rel_max2, rel_prop_var2;
+    double add_init2, add_min2, add_max2, add_prop_var2;
 } gbp_options;
+
+/* One time-domain acquisition system = the contents of a GA-AEM .stm file as gatdaem1d's TDAEMSystem reads
+ * it (classes/system/TdemSystem_GAAEM.py:26-40; e.g. documentation_source/.../data/SkytemHM.stm).
+ * Vertical-axis transmitter loop, Z-component dB/dt receiver, unit moment, no secondary-field normalisation. */
+typedef struct {
+    int32_t n_wave, n_windows, n_filters;
+    int32_t n_abscissae;                /* NumberOfAbsiccaInHankelTransformEvaluation */
+    double base_frequency;              /* BaseFrequency [Hz] */
+    double digitising_frequency;        /* WaveformDigitisingFrequency [Hz] (harmonics up to its Nyquist limit) */
+    double loop_radius;                 /* ModellingLoopRadius [m], 0 = point dipole */
+    double wave_time[GBP_TD_MAXWAVE], wave_current[GBP_TD_MAXWAVE];  /* WaveFormCurrent: half a period */
+    double window_start[GBP_TD_MAXWIN], window_end[GBP_TD_MAXWIN];   /* WindowTimes [s] */
+    double filter_cutoff[GBP_TD_MAXFILT];                            /* LowPassFilter CutOffFrequency [Hz] */
+    int32_t filter_order[GBP_TD_MAXFILT];                            /* LowPassFilter Order */
+} gbp_tdem_system;
+
+/* A time-domain datapoint type: its systems and the transmitter->receiver offset (Loop_pair.Geometry,
+ * classes/system/Loop_pair.py:62-78; z up, zero pitch/roll/yaw). */
+typedef struct {
+    int32_t n_systems, pad_;
+    gbp_tdem_system sys[GBP_TD_MAXSYS];
+    double rx_dx, rx_dy, rx_dz;
+} gbp_tdem_survey;
 
 /* Per-chain scalar slots of gbp_chain_buffers.scalars ([B][GBP_NSCALARS] doubles). */
 enum {
@@ -75,6 +115,7 @@ enum {
     GBP_S_CUR_REL, GBP_S_CUR_ADD, GBP_S_CUR_MISFIT, GBP_S_CUR_PRIOR, GBP_S_CUR_LIKELIHOOD,
     GBP_S_BEST_REL, GBP_S_BEST_ADD, GBP_S_N_RESETS, GBP_S_N_BIRTH, GBP_S_N_DEATH, GBP_S_N_MOVE, GBP_S_N_NONE,
     GBP_S_TOTAL_ITER,   /* accept_reject+update pairs executed, including those before a reset() */
+    GBP_S_CUR_REL2, GBP_S_CUR_ADD2, GBP_S_BEST_REL2, GBP_S_BEST_ADD2,  /* system 1 of a dual-moment datapoint */
     GBP_NSCALARS = 32
 };
 
@@ -85,8 +126,8 @@ typedef struct {
     int32_t *hitmap;        /* [B][n_sigma_bins][n_depth]   model.values.posterior.counts   */
     int32_t *edges_hist;    /* [B][n_depth]                 model.mesh.edges.posterior      */
     int32_t *ncells_hist;   /* [B][max_layers + 1]          model.mesh.nCells.posterior     */
-    int32_t *rel_hist;      /* [B][n_err_bins]              datapoint.relative_error.posterior */
-    int32_t *add_hist;      /* [B][n_err_bins]              datapoint.additive_error.posterior */
+    int32_t *rel_hist;      /* [B][n_systems][n_err_bins]   datapoint.relative_error.posterior */
+    int32_t *add_hist;      /* [B][n_systems][n_err_bins]   datapoint.additive_error.posterior */
     double *misfit_trace;   /* [B][2 * n_markov_chains]     data_misfit_v                   */
     uint8_t *accept_trace;  /* [B][2 * n_markov_chains]     acceptance_v                    */
     double *best_sigma;     /* [B][max_layers]   NaN padded best_model.values               */
@@ -146,6 +187,41 @@ int gbp_rjmcmc_run(const gbp_fdem_system *sys, const gbp_options *opt, int B, co
 int gbp_rjmcmc_run_host(const gbp_fdem_system *sys, const gbp_options *opt, int B, const double *data,
                         const double *altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
                         const gbp_chain_buffers *h_buf, int precision, int device);
+
+/* ---- time domain (SkyTEM-type systems) ---------------------------------------------------------- */
+/* total number of data channels = windows of every system, system 0 first (TdemDataPoint channel order) */
+int gbp_tdem_n_channels(const gbp_tdem_survey *sv);
+/* The model-independent tables the kernels use (tests / inspection): freq [GBP_TD_NFREQ] spline-node
+ * frequencies; MR, MI [C][GBP_TD_NFREQ] window operator d_c = sum_i MR[c][i] Re S_i + MI[c][i] Im S_i;
+ * t_centre [C] window centres.  Any pointer may be NULL.  Host only, no device needed. */
+int gbp_tdem_window_operator(const gbp_tdem_survey *sv, double *freq, double *MR, double *MI, double *t_centre);
+/* algorithmic flop count of one forward: n_freq x n_abscissae admittance recursions (75 L + 39 each, the
+ * SURVEY.md 8(d) convention) + the 2 C x 2 n_freq window products */
+double gbp_tdem_flops_per_forward(const gbp_tdem_survey *sv, int n_layers);
+
+/* out: [B][C] dBz/dt window averages (V/(A m^4) for unit moment), J: [B][C][l_stride] = d out / d ln(sigma).
+ * altitude = transmitter height above ground [B].  DEVICE pointers, stream ordered. */
+int gbp_tdem_forward(const gbp_tdem_survey *sv, int B, int l_stride, const int32_t *d_nlayers,
+                     const double *d_sigma, const double *d_thickness, const double *d_altitude,
+                     double *d_out, int precision, void *stream);
+int gbp_tdem_sensitivity(const gbp_tdem_survey *sv, int B, int l_stride, const int32_t *d_nlayers,
+                         const double *d_sigma, const double *d_thickness, const double *d_altitude,
+                         double *d_out, double *d_J, int precision, void *stream);
+/* HOST pointers (copies inside) */
+int gbp_tdem_forward_host(const gbp_tdem_survey *sv, int B, int l_stride, const int32_t *nlayers,
+                          const double *sigma, const double *thickness, const double *altitude,
+                          double *out, int precision, int device);
+int gbp_tdem_sensitivity_host(const gbp_tdem_survey *sv, int B, int l_stride, const int32_t *nlayers,
+                              const double *sigma, const double *thickness, const double *altitude,
+                              double *out, double *J, int precision, int device);
+/* rjMCMC for time-domain datapoints: data [B][C]; errors per system (gbp_options.n_systems must equal
+ * sv->n_systems); additive error of channel c scaled by (t_c / 1 ms)^-0.5 (TdemDataPoint.std :329-379). */
+int gbp_tdem_rjmcmc_run(const gbp_tdem_survey *sv, const gbp_options *opt, int B, const double *d_data,
+                        const double *d_altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                        const gbp_chain_buffers *d_buf, int precision, void *stream);
+int gbp_tdem_rjmcmc_run_host(const gbp_tdem_survey *sv, const gbp_options *opt, int B, const double *data,
+                             const double *altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
+                             const gbp_chain_buffers *h_buf, int precision, int device);
 
 #ifdef __cplusplus
 }
