@@ -9,6 +9,9 @@ Workload (config.workload): BASELINE.json configs[1] - 4096 synthetic RESOLVE FD
 (Inference1D.infer: N iterations, or N + burn-in + 1 once burned in).  One "step" = one pass of the fused
 rjMCMC kernel over that whole batch.  unit: one accept_reject()+update() pair of one sounding.
 Prints ONE JSON line (rank 0).
+
+    python bench.py --workload skytem ...   # BASELINE configs[3] family: SkyTEM dual-moment time-domain soundings
+                                            # (45 windows, skytem_options); not the default bench line
 """
 import argparse
 import json
@@ -39,12 +42,58 @@ def parse():
     ap.add_argument("--soundings", type=int, default=SOUNDINGS_PER_GPU, help="soundings per GPU")
     ap.add_argument("--chains", type=int, default=N_MARKOV_CHAINS, help="n_markov_chains")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+class Workload:
+    """What differs between the frequency-domain (RESOLVE) and time-domain (SkyTEM) benches."""
+
+    def __init__(self, name):
+        self.name = name
+        self.tdem = name == "skytem"
+        self.C = 45 if self.tdem else 12
+        self.synth = dict(max_depth=400.0, n_channels=45) if self.tdem else {}
+
+    def product(self, chains):
+        from geobipy_b200 import ops
+        if self.tdem:
+            return ops.skytem_survey_struct(), ops.make_options(n_markov_chains=chains, **ops.SKYTEM_OPTIONS)
+        return ops.resolve_system_struct(), ops.make_options(n_markov_chains=chains)
+
+    def noise_std(self, clean, xp):
+        """sqrt((5 % d)^2 + additive^2): RESOLVE 5 ppm; SkyTEM 2e-14 / 2e-13 V/Am^4 at 1 ms scaled by t^-1/2."""
+        if not self.tdem:
+            return xp.sqrt((0.05 * clean) ** 2 + 25.0)
+        from geobipy_b200 import ops
+        _, _, _, t = ops.tdem_window_operator(ops.skytem_survey_struct())
+        add = np.r_[np.full(26, 2e-14), np.full(19, 2e-13)] * np.sqrt(1e-3 / t)
+        if xp is not np:
+            add = xp.tensor(add, device=clean.device)
+        return xp.sqrt((0.05 * clean) ** 2 + add ** 2)
+
+    def oracle(self, chains):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as O
+        if self.tdem:
+            return O, O.make_tdem_system(), O.skytem_options(n_markov_chains=chains), O.tdem_forward
+        return O, O.make_system(), O.resolve_options(n_markov_chains=chains), O.fdem_forward
+
+
 def workload_config(args, world):
+    if args.workload == "skytem":
+        nd = 1209
+        return {
+            "workload": "BASELINE configs[3] family: %d synthetic SkyTEM dual-moment TDEM soundings per GPU (26 + 19 windows), "
+                        "<=30 layers, n_markov_chains=%d, chains run to the reference's termination rule" % (args.soundings, args.chains),
+            "soundings_per_gpu": args.soundings, "soundings_total": args.soundings * world,
+            "n_markov_chains": args.chains, "options": "skytem_options", "parallelism": "shard%d" % world,
+            "forward_precision": "fp%d" % args.precision,
+            "l2": "no flush needed: each step rewrites %.1f GB of posterior arrays per GPU (> 126 MB L2)"
+                  % (args.soundings * (250 * nd * 4 + 2 * args.chains * 9) / 1e9),
+        }
     return {
         "workload": "BASELINE configs[1]: %d synthetic RESOLVE FDEM soundings per GPU (6 freq, 12 channels), "
                     "<=30 layers, n_markov_chains=%d, chains run to the reference's termination rule" % (args.soundings, args.chains),
@@ -57,34 +106,38 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+_CPU_CACHE = {}
+
+
 def _cpu_chain(job):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as O
-    idx, data, alt, chains, max_it = job
-    r = O.run_chain(O.make_system(), O.resolve_options(n_markov_chains=chains), data, alt, SEED, idx, max_iterations=max_it)
+    idx, data, alt, chains, max_it, wname = job
+    key = (wname, chains)
+    if key not in _CPU_CACHE:  # per worker process: the time-domain tables take ~0.5 s to build
+        _CPU_CACHE[key] = Workload(wname).oracle(chains)
+    O, osys, oopt, _ = _CPU_CACHE[key]
+    r = O.run_chain(osys, oopt, data, alt, SEED, idx, max_iterations=max_it)
     return float(r["scalars"][O.S_TOTAL_ITER])
 
 
-def _observed_cpu(n):
+def _observed_cpu(n, wname="resolve"):
     """Synthetic observed data of soundings 0..n-1 computed with the oracle forward (CPU arm only)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as O
     from geobipy_b200.synthetic import synthetic_batch
+    wl = Workload(wname)
+    O, osys, _, fwd = wl.oracle(1)
     O.build()
-    osys = O.make_system()
-    b = synthetic_batch(0, n)
-    data = np.zeros((n, 12))
+    b = synthetic_batch(0, n, **wl.synth)
+    data = np.zeros((n, wl.C))
     for i in range(n):
         L = int(b["nlayers"][i])
-        clean = O.fdem_forward(osys, b["height"][i], b["sigma"][i, :L], b["thickness"][i, :L])
-        data[i] = clean + b["noise"][i] * np.sqrt((0.05 * clean) ** 2 + 25.0)
+        clean = fwd(osys, b["height"][i], b["sigma"][i, :L], b["thickness"][i, :L])
+        data[i] = clean + b["noise"][i] * wl.noise_std(clean, np)
     return data, b["height"]
 
 
-def cpu_sample(chains, n_chains, max_it, pool):
+def cpu_sample(chains, n_chains, max_it, pool, wname="resolve"):
     """Run n_chains chains of the workload on the host cores (one process per core); returns (iterations, seconds)."""
-    data, alt = _observed_cpu(n_chains)
-    jobs = [(i, data[i], float(alt[i]), chains, max_it) for i in range(n_chains)]
+    data, alt = _observed_cpu(n_chains, wname)
+    jobs = [(i, data[i], float(alt[i]), chains, max_it, wname) for i in range(n_chains)]
     t0 = time.perf_counter()
     its = pool.map(_cpu_chain, jobs)
     return float(sum(its)), time.perf_counter() - t0
@@ -102,13 +155,13 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     n_chains = cores
     max_it = 4000  # bounded sample: first 4000 iterations of `cores` chains per step (~2-4 s per step)
-    _observed_cpu(1)
+    _observed_cpu(1, args.workload)
     with mp.get_context("spawn").Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_sample(args.chains, n_chains, 500, pool)
+            cpu_sample(args.chains, n_chains, 500, pool, args.workload)
         its, secs = 0.0, 0.0
         for _ in range(args.steps):
-            i, s = cpu_sample(args.chains, n_chains, max_it, pool)
+            i, s = cpu_sample(args.chains, n_chains, max_it, pool, args.workload)
             its += i
             secs += s
     value = its / secs
@@ -192,19 +245,19 @@ def run_b200_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    system = ops.resolve_system_struct()
-    opt = ops.make_options(n_markov_chains=args.chains)
+    wl = Workload(args.workload)
+    system, opt = wl.product(args.chains)
     B = args.soundings
     first = rank * B
-    # synthetic observed data: true models -> fp64 forward on the GPU + N(0, (5% d)^2 + 5^2) noise
-    sb = synthetic_batch(first, B)
+    # synthetic observed data: true models -> fp64 forward on the GPU + N(0, (5% d)^2 + additive^2) noise
+    sb = synthetic_batch(first, B, **wl.synth)
     t_sig = torch.tensor(sb["sigma"], device=dev)
     t_thk = torch.tensor(sb["thickness"], device=dev)
     t_nl = torch.tensor(sb["nlayers"], device=dev)
     t_alt = torch.tensor(sb["height"], device=dev)
-    clean = ops.fdem_forward(system, t_nl, t_sig, t_thk, t_alt, precision=64)
+    clean = ops.forward(system, t_nl, t_sig, t_thk, t_alt, precision=64)
     noise = torch.tensor(sb["noise"], device=dev)
-    d_data = (clean + noise * torch.sqrt((0.05 * clean) ** 2 + 25.0)).contiguous()
+    d_data = (clean + noise * wl.noise_std(clean, torch)).contiguous()
     torch.cuda.synchronize()
 
     outputs = ops.DEFAULT_OUTPUTS
@@ -315,11 +368,13 @@ def run_b200_arm(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         nz = ops.n_depth(opt)
         # algorithmic HBM bytes per iteration = 8 N_z + 8 (L-1) + 8 (1 + 2 S) + 9, S = 1 system
-        bytes_per_iter = 8.0 * nz + 8.0 * max(mean_k - 1.0, 0.0) + 8.0 * 3.0 + 9.0
+        n_sys = 2 if wl.tdem else 1
+        bytes_per_iter = 8.0 * nz + 8.0 * max(mean_k - 1.0, 0.0) + 8.0 * (1.0 + 2.0 * n_sys) + 9.0
         achieved = bytes_per_iter * last_iters / (last_kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "dram_bytes_per_launch" if not wl.tdem else "dram_bytes_per_launch_skytem")
         except Exception:
             pass
         # secondary (the binding one): scalar fp32 issue.  flops per unit from gbp_flops_per_forward at the mean
@@ -333,7 +388,7 @@ def run_b200_arm(args):
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "kernel": "gbp::rjmcmc_kernel<float,12>" if args.precision == 32 else "gbp::rjmcmc_kernel<double,12>",
+                         "traffic": traffic, "kernel": "gbp::rjmcmc_kernel<%s,%d,%s>" % ("float" if args.precision == 32 else "double", 48 if wl.tdem else 12, "TDEM" if wl.tdem else "FDEM"),
                          "kernel_ms": last_kernel_ms, "units_per_launch": last_iters, "bytes_per_unit": bytes_per_iter,
                          "peak_source": peak_src,
                          "note": "BASELINE.json asks for the HBM fraction; this path is bound by scalar FP/SFU issue and latency, not by HBM (SURVEY.md 8(d))"},
@@ -350,10 +405,10 @@ def run_b200_arm(args):
             import multiprocessing as mp
             cores = os.cpu_count() or 1
             with mp.get_context("spawn").Pool(cores) as pool:
-                cpu_sample(args.chains, cores, 200, pool)
-                its, secs = cpu_sample(args.chains, cores, 0, pool)
+                cpu_sample(args.chains, cores, 200, pool, args.workload)
+                its, secs = cpu_sample(args.chains, cores, 0 if not wl.tdem else 4000, pool, args.workload)
             line["cpu_baseline"] = {"value": its / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d chains (soundings 0..%d of the workload) run to termination, one process per core, C restatement of the reference (oracle/)" % (cores, cores - 1)}
+                                    "sample": "%d chains (soundings 0..%d of the workload) %s, one process per core, C restatement of the reference (oracle/)" % (cores, cores - 1, "run to termination" if not wl.tdem else "x first 4000 iterations")}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

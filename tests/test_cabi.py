@@ -79,3 +79,31 @@ def test_synthetic_inputs():
     b = synthetic_batch(5, 4)
     assert b["sigma"].shape == (4, 30) and b["nlayers"][2] == s.size
     assert np.array_equal(b["sigma"][2, : s.size], s)
+
+
+def test_tdem_structs_and_tables(built_lib, oracle):
+    """The time-domain window operator the product builds in C++ (gbp_tdem_tables.h) against the oracle's
+    independent numpy/scipy construction (oracle_py.tdem_window_operator): host only, no GPU."""
+    from geobipy_b200 import _lib, ops
+    sv = ops.skytem_survey_struct()
+    assert ops.n_channels(sv) == 45 and not ops.is_tdem(ops.resolve_system_struct())
+    f, MR, MI, t = ops.tdem_window_operator(sv)
+    S = oracle.make_tdem_system()
+    assert np.allclose(f, np.array(S.freq[:32]), rtol=1e-14)
+    MRo, MIo = np.array(S.MR[:45 * 32]).reshape(45, 32), np.array(S.MI[:45 * 32]).reshape(45, 32)
+    assert np.all(np.abs(MR - MRo).max(axis=1) <= 1e-12 * np.abs(MRo).max(axis=1))
+    assert np.all(np.abs(MI - MIo).max(axis=1) <= 1e-12 * np.abs(MIo).max(axis=1))
+    assert np.allclose(t, np.array(S.t_centre[:45]))
+    assert ops.flops_per_forward(sv, 10) == 32 * 22 * (75 * 10 + 39) + 2 * 45 * 64
+    o = ops.make_options(initial_additive_error=[2e-14, 2e-13], minimum_depth=1.0, maximum_depth=550.0)
+    assert o.n_systems == 2 and o.add_init == 2e-14 and o.add_init2 == 2e-13 and ops.n_depth(o) == 1209
+    assert ops.chain_buffer_shapes(o, 3)["rel_hist"][0] == (3, 2, 99)
+    oo = oracle.skytem_options()
+    so = ops.make_options(**ops.SKYTEM_OPTIONS)
+    for name, _ in _lib.OptionsC._fields_:
+        assert getattr(oo, name) == getattr(so, name), name
+    # invalid descriptions are rejected with a message, not a crash
+    bad = ops.skytem_survey_struct()
+    bad.sys[0].base_frequency = 25.0   # waveform no longer spans half a period
+    with pytest.raises(_lib.GeobipyB200Error):
+        ops.tdem_window_operator(bad)
