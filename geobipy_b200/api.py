@@ -310,16 +310,27 @@ class Inference1D:
         self.datapoint = None
 
     def initialize(self, datapoint):
-        assert isinstance(datapoint, FdemDataPoint), TypeError("datapoint must be a FdemDataPoint")
+        from .tdem import TdemDataPoint
+        assert isinstance(datapoint, (FdemDataPoint, TdemDataPoint)), TypeError("datapoint must be a FdemDataPoint or TdemDataPoint")
         self.datapoint = datapoint
-        datapoint.initialize(initial_relative_error=self.options.rel_init, initial_additive_error=self.options.add_init)
+        o = self.options
+        self._tdem = isinstance(datapoint, TdemDataPoint)
+        ns = datapoint.nSystems if self._tdem else 1
+        assert (2 if o.n_systems > 1 else 1) == ns, ValueError(
+            "the error options must be lists with one entry per system ({})".format(ns))
+        if ns == 2:
+            datapoint.initialize(initial_relative_error=[o.rel_init, o.rel_init2], initial_additive_error=[o.add_init, o.add_init2])
+        else:
+            datapoint.initialize(initial_relative_error=o.rel_init, initial_additive_error=o.add_init)
         self.iteration, self.burned_in, self.burned_in_iteration = 0, False, 0
 
     def infer(self, hdf_file_handle=None, max_iterations=0):
         dp = self.datapoint
         if dp.n_active_channels == 0:
             return True
-        r = ops.rjmcmc_run(dp.system.c_struct, self.options, dp.data.reshape(1, -1), np.asarray([dp.z]), seed=self.seed,
+        struct = dp.c_struct if self._tdem else dp.system.c_struct
+        alt = dp.transmitter.z if self._tdem else dp.z
+        r = ops.rjmcmc_run(struct, self.options, dp.data.reshape(1, -1), np.asarray([alt]), seed=self.seed,
                            first_index=self.sounding_index, max_iterations=max_iterations, precision=self.precision,
                            device=self.device)
         self._fill(r, 0)
@@ -350,15 +361,25 @@ class Inference1D:
         self.hitmap = self.model.posterior
         self.n_cells_posterior = Histogram(r["ncells_hist"][b], np.arange(-0.5, o.max_layers + 1.0))
         self.edges_posterior = Histogram(r["edges_hist"][b], g["depth_edges"])
-        self.relative_error_posterior = Histogram(r["rel_hist"][b], g["rel_edges"], log_x=True)
-        self.additive_error_posterior = Histogram(r["add_hist"][b], g["add_edges"], log_x=True)
+        if o.n_systems > 1:  # one histogram per system, as DataPoint.set_relative_error_posterior builds them (:668-680)
+            self.relative_error_posterior = [Histogram(r["rel_hist"][b][i], g["rel_edges"][i], log_x=True) for i in range(2)]
+            self.additive_error_posterior = [Histogram(r["add_hist"][b][i], g["add_edges"][i], log_x=True) for i in range(2)]
+        else:
+            self.relative_error_posterior = Histogram(r["rel_hist"][b], g["rel_edges"], log_x=True)
+            self.additive_error_posterior = Histogram(r["add_hist"][b], g["add_edges"], log_x=True)
         self.data_misfit_v = r["misfit_trace"][b]
         self.acceptance_v = r["accept_trace"][b]
         dp = self.datapoint
-        dp.relative_error = np.asarray([s[_lib.S_CUR_REL]])
-        dp.additive_error = np.asarray([s[_lib.S_CUR_ADD]])
+        if o.n_systems > 1:
+            dp.relative_error = np.asarray([s[_lib.S_CUR_REL], s[_lib.S_CUR_REL2]])
+            dp.additive_error = np.asarray([s[_lib.S_CUR_ADD], s[_lib.S_CUR_ADD2]])
+            self.best_relative_error = np.asarray([s[_lib.S_BEST_REL], s[_lib.S_BEST_REL2]])
+            self.best_additive_error = np.asarray([s[_lib.S_BEST_ADD], s[_lib.S_BEST_ADD2]])
+        else:
+            dp.relative_error = np.asarray([s[_lib.S_CUR_REL]])
+            dp.additive_error = np.asarray([s[_lib.S_CUR_ADD]])
+            self.best_relative_error, self.best_additive_error = float(s[_lib.S_BEST_REL]), float(s[_lib.S_BEST_ADD])
         dp.forward(self.model)
-        self.best_relative_error, self.best_additive_error = float(s[_lib.S_BEST_REL]), float(s[_lib.S_BEST_ADD])
 
     def interface_probability(self):
         """edges histogram / sum (Inference2D.interface_probability, Inference2D.py:959-961)."""
@@ -371,7 +392,7 @@ def infer_batch(system, data, altitude, seed=0, precision=_lib.PRECISION_F32, de
     """Batched replacement of the `Inference3D.infer_serial` loop (Inference3D.py:458-492): all soundings of
     `data` [B, 2F] are inverted concurrently, one warp per sounding.  Returns the dict of posterior arrays
     (`include/geobipy_b200.h` gbp_chain_buffers) plus the options struct used."""
-    s = system.c_struct if isinstance(system, FdemSystem) else system
+    s = system.c_struct if hasattr(system, "c_struct") else system
     opt = ops.make_options(**options)
     r = ops.rjmcmc_run(s, opt, data, altitude, seed=seed, first_index=first_index, max_iterations=max_iterations,
                        precision=precision, device=device, outputs=outputs)

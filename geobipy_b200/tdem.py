@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's time-domain classes on the per-sounding inference path.
+
+Mirrored (same names, argument meaning and error behaviour):
+  TdemSystem    classes/system/TdemSystem_GAAEM.py (the wrapper of gatdaem1d.TDAEMSystem): `read(stm)`, `off_time`,
+                `nTimes`, `components`
+  TdemLoop      classes/system/CircularLoop.py as used by TdemDataPoint(transmitter_loop=, receiver_loop=)
+  TdemDataPoint classes/data/datapoint/TdemDataPoint.py: data = secondary_field [windows of system 0, system 1, ...];
+                `std` with per-system errors and the (t / 1 ms)^-1/2 additive scaling (:329-379); `forward`,
+                `sensitivity`, `fm_dlogc` (:997-1055)
+  TdemData      classes/data/dataset/TdemData.py read_csv: the column layout of the reference's skytem_*.csv
+                (Line_number, Fiducial, Easting, Northing, Height, Elevation, tx_pitch .. rx_yaw, then the windows)
+Everything numerical happens behind the C-ABI (ops.py / include/geobipy_b200.h gbp_tdem_*).
+"""
+import numpy as np
+
+from . import _lib, ops
+from .api import Model
+
+__all__ = ["read_stm", "TdemSystem", "TdemLoop", "TdemDataPoint", "TdemData"]
+
+
+def read_stm(filename):
+    """Parse a GA-AEM .stm file (block structured `Key = value` text; e.g. SkytemHM.stm) into the dictionary
+    `ops.make_tdem_system_struct` consumes."""
+    d, mode, wave, win = {}, None, [], []
+    with open(filename) as f:
+        for line in f:
+            s = line.strip()
+            if not s or s.startswith("//"):
+                continue
+            low = s.lower()
+            if low.startswith("waveformcurrent begin"):
+                mode = "wave"
+            elif low.startswith("waveformcurrent end") or low.startswith("windowtimes end"):
+                mode = None
+            elif low.startswith("windowtimes begin"):
+                mode = "win"
+            elif mode in ("wave", "win"):
+                a = s.split()
+                (wave if mode == "wave" else win).append((float(a[0]), float(a[1])))
+            elif "=" in s:
+                k, v = (x.strip() for x in s.split("=", 1))
+                d[k] = v
+    assert str(d.get("Type", "Time Domain")).lower().startswith("time"), ValueError("not a time-domain system file")
+    assert len(wave) >= 2 and len(win) >= 1, ValueError("system file has no waveform / windows: " + filename)
+    cut = [float(x) for x in d.get("CutOffFrequency", "").split()]
+    order = [int(float(x)) for x in d.get("Order", "").split()]
+    return dict(
+        name=d.get("Name", ""), base_frequency=float(d["BaseFrequency"]),
+        digitising_frequency=float(d["WaveformDigitisingFrequency"]),
+        n_turns=float(d.get("NumberOfTurns", 1)), peak_current=float(d.get("PeakCurrent", 1)),
+        loop_area=float(d.get("LoopArea", 1)),
+        waveform_time=[w[0] for w in wave], waveform_current=[w[1] for w in wave],
+        window_start=[w[0] for w in win], window_end=[w[1] for w in win],
+        filter_cutoff=cut, filter_order=order, loop_radius=float(d.get("ModellingLoopRadius", 0.0)),
+        output_type=d.get("OutputType", "dB/dt"), x_scaling=float(d.get("XOutputScaling", 0)),
+        y_scaling=float(d.get("YOutputScaling", 0)), z_scaling=float(d.get("ZOutputScaling", 1)),
+        frequencies_per_decade=int(float(d.get("FrequenciesPerDecade", 5))),
+        n_abscissae=int(float(d.get("NumberOfAbsiccaInHankelTransformEvaluation", 21))))
+
+
+class TdemSystem:
+    """One time-domain system (TdemSystem_GAAEM): built from an .stm file or a parsed description."""
+
+    def __init__(self, system_filename=None, definition=None):
+        if definition is None:
+            import os
+            assert system_filename is not None and os.path.exists(system_filename), \
+                'Could not open file: ' + str(system_filename)   # TdemSystem_GAAEM.py:29
+            definition = read_stm(system_filename)
+        self.definition = definition
+        self.filename = system_filename
+        self.off_time = 0.5 * (np.asarray(definition["window_start"]) + np.asarray(definition["window_end"]))
+        assert np.min(np.diff(self.off_time)) > 0.0 if self.off_time.size > 1 else True, ValueError(
+            "Receiver window times must monotonically increase for system " + str(system_filename))
+        self.components = ['z']
+
+    @classmethod
+    def read(cls, system_filename):
+        return cls(system_filename)
+
+    @property
+    def nTimes(self):
+        return self.off_time.size
+
+    @property
+    def n_components(self):
+        return 1
+
+    @property
+    def isGA(self):
+        return True
+
+
+class TdemLoop:
+    """Transmitter / receiver loop of a time-domain datapoint (CircularLoop): position offsets and attitude.
+    Only zero pitch / roll / yaw are supported on the GPU path."""
+
+    def __init__(self, x=0.0, y=0.0, z=0.0, elevation=0.0, orientation='z', moment=1.0, pitch=0.0, roll=0.0, yaw=0.0,
+                 radius=None, **kwargs):
+        self.x, self.y, self.z = float(x), float(y), float(z)
+        self.orientation, self.moment, self.radius = orientation, float(moment), radius
+        self.pitch, self.roll, self.yaw = float(pitch), float(roll), float(yaw)
+
+
+class TdemDataPoint:
+    """One time-domain sounding with 1-2 systems (TdemDataPoint.py).  Data are dBz/dt window averages in
+    V/(A m^4), system 0's windows first."""
+
+    def __init__(self, x=0.0, y=0.0, z=0.0, elevation=0.0, primary_field=None, secondary_field=None, relative_error=None,
+                 additive_error=None, std=None, predicted_primary_field=None, predicted_secondary_field=None,
+                 system=None, transmitter_loop=None, receiver_loop=None, lineNumber=0.0, fiducial=0.0,
+                 precision=_lib.PRECISION_F64, **kwargs):
+        if isinstance(system, (str, TdemSystem)):
+            system = [system]
+        assert system is not None and 1 <= len(system) <= _lib.TD_MAXSYS, ValueError("1 or 2 systems per datapoint")
+        self.system = [s if isinstance(s, TdemSystem) else TdemSystem(s) for s in system]
+        self.x, self.y, self.z, self.elevation = float(x), float(y), float(z), float(elevation)
+        self.lineNumber, self.fiducial = lineNumber, fiducial
+        self.transmitter = transmitter_loop if transmitter_loop is not None else TdemLoop(z=self.z)
+        self.receiver = receiver_loop if receiver_loop is not None else TdemLoop(x=-13.0, z=self.z + 2.0)
+        for lp in (self.transmitter, self.receiver):
+            assert lp.pitch == 0.0 and lp.roll == 0.0 and lp.yaw == 0.0, NotImplementedError(
+                "loop pitch / roll / yaw are not supported on the GPU path")
+        n = self.nChannels
+        self.secondary_field = np.zeros(n) if secondary_field is None else np.asarray(secondary_field, np.float64).copy()
+        self.predicted_secondary_field = (np.zeros(n) if predicted_secondary_field is None
+                                          else np.asarray(predicted_secondary_field, np.float64).copy())
+        assert self.secondary_field.size == n, ValueError("secondary_field must have %d entries" % n)
+        self._std = np.full(n, 0.01) if std is None else np.asarray(std, np.float64).copy()
+        ns = self.nSystems
+        self.relative_error = np.full(ns, 0.01) if relative_error is None else np.asarray(relative_error, np.float64).reshape(-1)
+        self.additive_error = np.zeros(ns) if additive_error is None else np.asarray(additive_error, np.float64).reshape(-1)
+        assert self.relative_error.size == ns, ValueError("relative_error must be a list of size equal to the number of systems {}".format(ns))
+        assert self.additive_error.size == ns, ValueError("additive_error must be a list of size equal to the number of systems {}".format(ns))
+        self._use_errors = relative_error is not None
+        self.sensitivity_matrix = None
+        self.precision = precision
+        self._struct = None
+
+    # -- layout
+    @property
+    def nSystems(self):
+        return len(self.system)
+
+    @property
+    def nTimes(self):
+        return np.asarray([s.nTimes for s in self.system])
+
+    @property
+    def nChannels(self):
+        return int(self.nTimes.sum())
+
+    @property
+    def components(self):
+        return ['z']
+
+    def off_time(self, system=0):
+        return self.system[system].off_time
+
+    def _systemIndices(self, system=0):
+        o = np.r_[0, np.cumsum(self.nTimes)]
+        return np.s_[o[system]:o[system + 1]]
+
+    @property
+    def data(self):
+        return self.secondary_field
+
+    @property
+    def predictedData(self):
+        return self.predicted_secondary_field
+
+    @property
+    def c_struct(self):
+        if self._struct is None:
+            off = (self.receiver.x - self.transmitter.x, self.receiver.y - self.transmitter.y, self.receiver.z - self.transmitter.z)
+            self._struct = ops.make_tdem_survey_struct([s.definition for s in self.system], off)
+        return self._struct
+
+    # -- EmDataPoint.active :44-56
+    @property
+    def active(self):
+        return self.secondary_field > 0.0
+
+    @property
+    def n_active_channels(self):
+        return int(self.active.sum())
+
+    # -- TdemDataPoint.std :329-379
+    @property
+    def std(self):
+        if self._use_errors:
+            assert np.all(self.relative_error > 0.0), ValueError('relative_error must be > 0.0')
+            for i in range(self.nSystems):
+                ic = self._systemIndices(i)
+                rel = self.relative_error[i] * self.secondary_field[ic]
+                add = np.exp(np.log(self.additive_error[i]) - 0.5 * (np.log(self.off_time(i)) - np.log(1e-3)))
+                self._std[ic] = np.sqrt(rel ** 2 + add ** 2)
+        return self._std
+
+    def initialize(self, **kwargs):
+        self.relative_error = np.asarray(kwargs['initial_relative_error'], np.float64).reshape(-1)
+        self.additive_error = np.asarray(kwargs['initial_additive_error'], np.float64).reshape(-1)
+        self._use_errors = True
+
+    @property
+    def deltaD(self):
+        return self.predicted_secondary_field - self.secondary_field
+
+    def _model_arrays(self, mod):
+        assert isinstance(mod, Model), TypeError("Invalid model class {} for forward modeling [1D]".format(type(mod)))
+        assert np.isinf(mod.mesh.edges[-1]), ValueError("mod.edges must have last entry be infinity for forward modelling.")
+        alt = self.transmitter.z - mod.mesh.edges[0]
+        assert self.z >= mod.mesh.edges[0] and alt > 0.0, "Sensor altitude must be above the top of the model"  # tdem1d.py:32
+        L = mod.nCells
+        assert 1 <= L <= _lib.MAXL, ValueError("1..%d layers supported" % _lib.MAXL)
+        return (np.asarray([L], np.int32), mod.values.reshape(1, L).astype(np.float64),
+                mod.mesh.widths.reshape(1, L).astype(np.float64), np.asarray([alt]))
+
+    def forward(self, mod):
+        """Fill predicted_secondary_field from a 1-D layered model (TdemDataPoint.forward :997)."""
+        nl, s, t, a = self._model_arrays(mod)
+        self.predicted_secondary_field[:] = ops.forward(self.c_struct, nl, s, t, a, precision=self.precision)[0]
+
+    def sensitivity(self, mod, ix=None, model_changed=False):
+        """d(predicted)/d ln(sigma) [nChannels, nCells] (TdemDataPoint.sensitivity :1024, gaTdem1dsen's sigma scaling)."""
+        nl, s, t, a = self._model_arrays(mod)
+        _, J = ops.forward(self.c_struct, nl, s, t, a, precision=self.precision, sensitivity=True)
+        self.sensitivity_matrix = J[0] if ix is None else J[0][:, ix]
+        return self.sensitivity_matrix
+
+    def fm_dlogc(self, mod):
+        nl, s, t, a = self._model_arrays(mod)
+        p, J = ops.forward(self.c_struct, nl, s, t, a, precision=self.precision, sensitivity=True)
+        self.predicted_secondary_field[:] = p[0]
+        self.sensitivity_matrix = J[0]
+
+    # -- DataPoint.data_misfit :502-525, likelihood :491-500
+    def data_misfit(self):
+        a = self.active
+        return float(np.sum((self.deltaD[a] / self.std[a]) ** 2))
+
+    def likelihood(self, log=True):
+        a = self.active
+        var = self.std[a] ** 2
+        ll = -0.5 * a.sum() * np.log(2.0 * np.pi) - 0.5 * np.sum(np.log(var)) - 0.5 * np.sum(self.deltaD[a] ** 2 / var)
+        return float(ll) if log else float(np.exp(ll))
+
+
+class TdemData:
+    """A time-domain survey file in the reference's CSV layout (TdemData.read_csv): one row per sounding."""
+
+    GEOMETRY = ("tx_pitch", "tx_roll", "tx_yaw", "txrx_dx", "txrx_dy", "txrx_dz", "rx_pitch", "rx_roll", "rx_yaw")
+
+    def __init__(self, system, line_number, fiducial, x, y, height, elevation, geometry, data):
+        self.system = system
+        self.line_number, self.fiducial, self.x, self.y = line_number, fiducial, x, y
+        self.height, self.elevation, self.geometry, self.data = height, elevation, geometry, data
+
+    @classmethod
+    def read_csv(cls, data_filename, system):
+        """`system`: list of .stm file names or TdemSystem objects (one per moment).  Columns: Line_number (or Line),
+        Fiducial, Easting (X), Northing (Y), Height, Elevation, the nine geometry columns, then
+        sum(nTimes) window columns, system 0 first; non-positive or NaN values are inactive channels."""
+        import pandas as pd
+        if isinstance(system, (str, TdemSystem)):
+            system = [system]
+        system = [s if isinstance(s, TdemSystem) else TdemSystem(s) for s in system]
+        df = pd.read_csv(data_filename, skipinitialspace=True, float_precision="round_trip")
+        low = {c.strip().lower(): c for c in df.columns}
+
+        def col(*names, default=None):
+            for n in names:
+                if n in low:
+                    return df[low[n]].to_numpy(dtype=np.float64)
+            assert default is not None, ValueError("column %s missing from %s" % (names[0], data_filename))
+            return np.full(len(df), default)
+        n = sum(s.nTimes for s in system)
+        known = {"line_number", "line", "fiducial", "fid", "easting", "x", "northing", "y", "height", "z", "dtm", "elevation"}
+        known |= set(cls.GEOMETRY)
+        dcols = [c for c in df.columns if c.strip().lower() not in known and not c.strip().lower().startswith("off")]
+        assert len(dcols) >= n, ValueError("expected %d window columns, found %d" % (n, len(dcols)))
+        geometry = np.stack([col(g, default=(-13.0 if g == "txrx_dx" else 2.0 if g == "txrx_dz" else 0.0)) for g in cls.GEOMETRY], axis=1)
+        return cls(system, col("line_number", "line"), col("fiducial", "fid"), col("easting", "x"), col("northing", "y"),
+                   col("height", "z"), col("elevation", "dtm", default=0.0), geometry,
+                   df[dcols[:n]].to_numpy(dtype=np.float64))
+
+    @property
+    def nPoints(self):
+        return self.data.shape[0]
+
+    @property
+    def nChannels(self):
+        return self.data.shape[1]
+
+    def survey_struct(self):
+        """One gbp_tdem_survey for the whole file: the GPU path needs a constant tx->rx offset and zero attitudes."""
+        g = self.geometry
+        assert np.all(g[:, [0, 1, 2, 6, 7, 8]] == 0.0), NotImplementedError("loop pitch / roll / yaw are not supported on the GPU path")
+        assert np.all(g[:, 3:6] == g[0, 3:6]), NotImplementedError("the transmitter-receiver offset must be constant over the file")
+        return ops.make_tdem_survey_struct([s.definition for s in self.system], tuple(g[0, 3:6]))
+
+    def datapoint(self, i):
+        """TdemDataPoint of row i (TdemData.datapoint)."""
+        g = self.geometry[i]
+        tx = TdemLoop(x=self.x[i], y=self.y[i], z=self.height[i])
+        rx = TdemLoop(x=self.x[i] + g[3], y=self.y[i] + g[4], z=self.height[i] + g[5])
+        return TdemDataPoint(self.x[i], self.y[i], self.height[i], self.elevation[i], secondary_field=self.data[i],
+                             system=self.system, transmitter_loop=tx, receiver_loop=rx, lineNumber=self.line_number[i],
+                             fiducial=self.fiducial[i])

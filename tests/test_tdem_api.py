@@ -1,0 +1,153 @@
+"""The reference-shaped time-domain classes (geobipy_b200/tdem.py): .stm / CSV readers on the CPU, the object
+interface on the GPU.  They read like the reference's own usage (tests/test_synthetic_data.py:32-48 test_skytem,
+documentation_source/source/examples/Datapoints/plot_skytem_datapoint.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_stm(path, d):
+    """Write a parsed description back in the GA-AEM .stm layout (the reference's SkytemHM.stm structure)."""
+    wave = "\n".join("%.9E\t%.6E" % (t, c) for t, c in zip(d["waveform_time"], d["waveform_current"]))
+    win = "\n".join("%.6E\t%.6E" % (a, b) for a, b in zip(d["window_start"], d["window_end"]))
+    path.write_text(
+        "System Begin\n\tName = %s\n\tType = Time Domain\n\tTransmitter Begin\n\t\tNumberOfTurns = 1\n\t\tPeakCurrent   = 1\n"
+        "\t\tLoopArea      = 1\n\t\tBaseFrequency = %r\n\t\tWaveformDigitisingFrequency = %r\n\t\tWaveFormCurrent Begin\n%s\n\n"
+        "\t\tWaveFormCurrent End\n\tTransmitter End\nReceiver Begin\n\tNumberOfWindows = %d\n\tWindowWeightingScheme = AreaUnderCurve\n"
+        "\tWindowTimes Begin\n%s\n\n\t\tWindowTimes End\n\t\tLowPassFilter Begin\n\t\t\tCutOffFrequency = %s\n\t\t\tOrder           = %s\n"
+        "\t\tLowPassFilter End\n\tReceiver End\nForwardModelling Begin\n\t\t//TX loop area is was 340.82 m^2 -> r = sqrt(340.82/pi)\n"
+        "\t\tModellingLoopRadius = %r\n\t\tOutputType = dB/dt\n\t\tXOutputScaling = 0\n\t\tYOutputScaling = 0\n\t\tZOutputScaling = 1\n"
+        "\t\tSecondaryFieldNormalisation  =  none\n\t\tFrequenciesPerDecade = 5\n\t\tNumberOfAbsiccaInHankelTransformEvaluation = %d\n"
+        "\tForwardModelling End\n\nSystem End\n" % (
+            d["name"], d["base_frequency"], d["digitising_frequency"], wave, len(d["window_start"]), win,
+            " ".join(repr(c) for c in d["filter_cutoff"]), " ".join(str(o) for o in d["filter_order"]), d["loop_radius"],
+            d["n_abscissae"]))
+
+
+@pytest.fixture()
+def stm_files(tmp_path):
+    out = []
+    for n in ("skytem_hm", "skytem_lm"):
+        d = json.load(open(os.path.join(ROOT, "geobipy_b200", "data", n + ".json")))
+        p = tmp_path / (n + ".stm")
+        _write_stm(p, d)
+        out.append((str(p), d))
+    return out
+
+
+def test_read_stm_round_trip(stm_files, built_lib):
+    from geobipy_b200 import ops, tdem
+    for path, d in stm_files:
+        r = tdem.read_stm(path)
+        for k in ("base_frequency", "digitising_frequency", "loop_radius", "n_abscissae", "filter_order"):
+            assert r[k] == d[k], k
+        for k in ("waveform_time", "waveform_current", "window_start", "window_end", "filter_cutoff"):
+            assert np.allclose(r[k], d[k], rtol=1e-9), k
+        s = tdem.TdemSystem.read(path)
+        assert s.nTimes == len(d["window_start"]) and s.components == ['z'] and s.isGA
+        assert np.allclose(s.off_time, 0.5 * (np.array(d["window_start"]) + np.array(d["window_end"])))
+    with pytest.raises(AssertionError):     # TdemSystem_GAAEM.py:29: the file must exist
+        tdem.TdemSystem("does_not_exist.stm")
+    sv = ops.make_tdem_survey_struct([tdem.read_stm(p) for p, _ in stm_files])
+    ref = ops.skytem_survey_struct()
+    f1, MR1, MI1, _ = ops.tdem_window_operator(sv)
+    f2, MR2, MI2, _ = ops.tdem_window_operator(ref)
+    assert np.allclose(MR1, MR2, rtol=1e-6, atol=1e-9 * np.abs(MR2).max()) and np.allclose(f1, f2)
+
+
+def test_datapoint_std_and_layout(stm_files, built_lib):
+    from geobipy_b200 import tdem
+    files = [p for p, _ in stm_files]
+    dp = tdem.TdemDataPoint(z=30.0, system=files, secondary_field=np.full(45, 1e-12), relative_error=[0.05, 0.03],
+                            additive_error=[2e-14, 2e-13])
+    assert dp.nSystems == 2 and list(dp.nTimes) == [26, 19] and dp.nChannels == 45
+    # TdemDataPoint.std :329-379
+    t0, t1 = dp.off_time(0), dp.off_time(1)
+    exp0 = np.sqrt((0.05 * 1e-12) ** 2 + (2e-14 * np.sqrt(1e-3 / t0)) ** 2)
+    exp1 = np.sqrt((0.03 * 1e-12) ** 2 + (2e-13 * np.sqrt(1e-3 / t1)) ** 2)
+    assert np.allclose(dp.std, np.r_[exp0, exp1], rtol=1e-12)
+    with pytest.raises(AssertionError):
+        tdem.TdemDataPoint(z=30.0, system=files, relative_error=[0.05])       # one entry per system
+    with pytest.raises(AssertionError):
+        tdem.TdemDataPoint(z=30.0, system=files, transmitter_loop=tdem.TdemLoop(z=30.0, pitch=2.0))
+    d = dp.secondary_field.copy()
+    d[3] = -1.0
+    d[7] = np.nan
+    dp.secondary_field[:] = d
+    assert dp.n_active_channels == 43
+
+
+def test_read_csv_reference_layout(stm_files, tmp_path, golden_dir, built_lib):
+    from geobipy_b200 import tdem
+    g = np.load(os.path.join(golden_dir, "skytem_clean.npz"))
+    hdr = ("Line_number,Fiducial,Easting,Northing,Height,Elevation,tx_pitch,tx_roll,tx_yaw,txrx_dx,txrx_dy,txrx_dz,rx_pitch,rx_roll,rx_yaw,"
+           + ",".join("S0Z_time_%.3e" % t for t in g["times"][:26]) + "," + ",".join("S1Z_time_%.3e" % t for t in g["times"][26:]))
+    rows = [hdr]
+    for i in range(5):
+        rows.append(",".join(repr(float(v)) for v in [0.0, i, float(i), 0.0, 30.0, 0.0, 0, 0, 0, -13.0, 0.0, 2.0, 0, 0, 0] + list(g["data"][0, i])))
+    f = tmp_path / "skytem_glacial_clean.csv"
+    f.write_text("\n".join(rows) + "\n")
+    ds = tdem.TdemData.read_csv(str(f), [p for p, _ in stm_files])
+    assert ds.nPoints == 5 and ds.nChannels == 45 and np.array_equal(ds.data, g["data"][0, :5])
+    assert np.all(ds.height == 30.0) and np.array_equal(ds.geometry[0, 3:6], [-13.0, 0.0, 2.0])
+    sv = ds.survey_struct()
+    assert (sv.rx_dx, sv.rx_dy, sv.rx_dz) == (-13.0, 0.0, 2.0) and sv.n_systems == 2
+    dp = ds.datapoint(2)
+    assert dp.z == 30.0 and dp.receiver.x - dp.transmitter.x == -13.0 and np.array_equal(dp.data, g["data"][0, 2])
+
+
+@pytest.mark.gpu
+def test_datapoint_forward_matches_reference_golden(stm_files, golden_dir, built_lib):
+    """test_skytem of the reference (tests/test_synthetic_data.py:32-48) at discretisation tolerance."""
+    from geobipy_b200 import _lib, api, tdem
+    _lib.require_cuda()
+    g = np.load(os.path.join(golden_dir, "skytem_clean.npz"))
+    dp = tdem.TdemDataPoint(x=0.0, y=0.0, z=30.0, elevation=0.0, system=[p for p, _ in stm_files])
+    for m, i in ((0, 0), (1, 40), (4, 10)):
+        mod = api.Model(api.RectilinearMesh1D(edges=np.r_[0.0, g["zwedge"][i], g["zdeep"][i], np.inf]), g["sigma"][m])
+        dp.forward(mod)
+        ref = g["data"][m, i]
+        assert np.median(np.abs(dp.predictedData / ref - 1.0)) < 3e-3
+        assert np.all(np.abs(dp.predictedData[:20] / ref[:20] - 1.0) < 0.03)
+        J = dp.sensitivity(mod)
+        assert J.shape == (45, 3)
+        dp.fm_dlogc(mod)
+        assert np.array_equal(dp.sensitivity_matrix, J)
+    with pytest.raises(AssertionError):   # last edge must be inf
+        dp.forward(api.Model(api.RectilinearMesh1D(edges=[0.0, 5.0, 10.0]), [0.01, 0.1]))
+
+
+@pytest.mark.gpu
+def test_inference1d_with_skytem_datapoint(stm_files, golden_dir, built_lib):
+    """The reference's driver sequence (Inference3D.infer_serial :483-492) with a dual-moment datapoint and the
+    keys of skytem_options."""
+    from geobipy_b200 import _lib, api, tdem
+    _lib.require_cuda()
+    g = np.load(os.path.join(golden_dir, "skytem_clean.npz"))
+    dp = tdem.TdemDataPoint(z=30.0, system=[p for p, _ in stm_files], secondary_field=g["data"][0, 30])
+    opts = dict(n_markov_chains=3000, update_plot_every=500, maximum_number_of_layers=30, minimum_depth=1.0, maximum_depth=550.0,
+                minimum_thickness=None, initial_relative_error=[0.05, 0.05], minimum_relative_error=[0.005, 0.005],
+                maximum_relative_error=[0.5, 0.5], initial_additive_error=[2e-14, 2e-13], minimum_additive_error=[1e-16, 1e-16],
+                maximum_additive_error=[1e-10, 1e-10], relative_error_proposal_variance=[1e-6, 1e-6],
+                additive_error_proposal_variance=[1e-5, 1e-5], covariance_scaling=0.5, solve_relative_error=True,
+                solve_additive_error=True, interactive_plot=False, save_hdf5=True, burn_in_min_iter=500)
+    inf = api.Inference1D(prng=np.random.default_rng(0), **opts)
+    inf.initialize(dp)
+    failed = inf.infer(None)
+    assert not failed and inf.burned_in
+    assert inf.model.posterior.counts.shape == (250, 1209)
+    assert len(inf.relative_error_posterior) == 2 and inf.relative_error_posterior[1].counts.sum() == 3001
+    assert dp.relative_error.shape == (2,) and dp.additive_error.shape == (2,)
+    # clean data, 5 % assumed error: the final model fits far inside the noise
+    assert inf.data_misfit < 45.0
+    # posterior median conductivity of the top 30 m within a factor 2 of the true first layer (0.01 S/m, 35 m thick)
+    med = inf.model.posterior.median()
+    depth = 0.5 * (inf.model.posterior.y_edges[1:] + inf.model.posterior.y_edges[:-1])
+    top = med[(depth > 5.0) & (depth < 25.0)]
+    assert np.all((top > 0.005) & (top < 0.02)), top
+    with pytest.raises(AssertionError):   # scalar error options with a dual-moment datapoint
+        api.Inference1D(prng=np.random.default_rng(0), interactive_plot=False, save_hdf5=True).initialize(dp)
