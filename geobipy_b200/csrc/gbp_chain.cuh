@@ -984,7 +984,11 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
                 ch_mesh_setup(K, kn, &mesh_p);
                 ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, J_t);
                 j_valid = false;
-                ph = pred_t;
+                // REFERENCE QUIRK (kept, it shapes the proposal): FdemDataPoint.fm_dlogc stores the remapped model's
+                // predicted data (FdemDataPoint.py:535-545); TdemDataPoint.fm_dlogc stores only the Jacobian, its
+                // predicted-data update is commented out (TdemDataPoint.py:1031-1055), so a time-domain death / move
+                // forms the Newton gradient with the CURRENT model's predicted data.
+                if constexpr (KIND == KIND_FDEM) ph = pred_t;
             } else if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
                 ch_copy16(w->J, jg, JBYTES);
                 j_valid = true;
@@ -1061,8 +1065,9 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
                         const R g2 = ch_gradient(w, K, kn, mesh_p.t2, val_p.ls, J_t, pred_t, ln_ref);
                         const R s2 = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g2));  // H dfk'
                         const R lv = ln_t + K->alpha * s2;  // Model.py:626 (sign as in the reference)
-                        const R mv = rt<R>::exp(lv);
-                        const int bad = __any_sync(FULL, lane < kn && (mv == (R)INFINITY || mv == R(0)));
+                        // mean = expReal(log_values) is inf above 11356 and underflows to 0 below the long-double
+                        // denormal limit (base/utilities.py:827-856): Model.py:630-633 then returns -inf, -inf
+                        const int bad = __any_sync(FULL, lane < kn && (lv > R(11356) || lv < R(-11399)));
                         const R q_r = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_r - lv) : R(0));
                         const R q_f = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_t - ln_r) : R(0));
                         const R logdetL = warp_sum((lane < kn) ? rt<R>::log(w->A[pk(lane, lane)]) : R(0));

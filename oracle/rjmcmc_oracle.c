@@ -720,7 +720,12 @@ static int chain_step(chain_t *c)
     const int k = remap.k;
 
     if (action != ACT_NONE) { /* observation.fm_dlogc(remapped) */
-        forward(c, &remap, tdp.pred);
+        /* REFERENCE QUIRK (kept, it shapes the proposal): FdemDataPoint.fm_dlogc stores the predicted data of the
+         * remapped model (FdemDataPoint.py:535-545), TdemDataPoint.fm_dlogc only stores the Jacobian - its
+         * predicted-data update is commented out (TdemDataPoint.py:1031-1055) - so the Newton gradient of a
+         * time-domain death / move uses the CURRENT model's predicted data with the remapped model's Jacobian. */
+        double scratch[GBO_MAXC];
+        forward(c, &remap, c->sv.tdem ? scratch : tdp.pred);
         sensitivity(c, &remap, &tdp);
     }
     data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
@@ -770,8 +775,9 @@ static int chain_step(chain_t *c)
         for (int i = 0; i < k; ++i) {
             /* log_values = ln(sigma') - alpha*pk with pk = -H dfk  (Model.py:626-628) */
             double lv = log(test.sigma[i]) + o->covariance_scaling * s2[i];
-            double mv = exp(lv);
-            if (mv == INFINITY || mv == 0.0) bad = 1;
+            /* mean = expReal(log_values) is inf above 11356 and underflows to 0 below the long-double
+             * denormal limit (base/utilities.py:827-856, Model.py:630-633) */
+            if (lv > 11356.0 || lv < -11399.0) bad = 1;
             xr[i] = log(remap.sigma[i]) - lv;
             xf[i] = log(test.sigma[i]) - log(remap.sigma[i]);
             logdetL += log(A[i * k + i]);
@@ -997,7 +1003,8 @@ static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_tr
     double A[GBO_MAXL * GBO_MAXL], y[GBO_MAXL], step[GBO_MAXL];
     model_thickness(&remap, thk);
     if (t->action != ACT_NONE) {
-        sv_forward(sv, t->altitude, k, remap.sigma, thk, pred);
+        if (sv->tdem) memcpy(pred, t->pred_in, sizeof(double) * C); /* TdemDataPoint.fm_dlogc quirk, see chain_step */
+        else sv_forward(sv, t->altitude, k, remap.sigma, thk, pred);
         sv_sensitivity(sv, t->altitude, k, remap.sigma, thk, J);
     } else {
         memcpy(pred, t->pred_in, sizeof(double) * C);
@@ -1024,14 +1031,16 @@ static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_tr
         hessian_gradient(o, &test, t->sigma_ref, C, t->data, var, J, t->pred_test, NULL, g2);
         solve_L(k, A, g2, y);
         solve_LT(k, A, y, s2);
+        int bad = 0;
         for (int i = 0; i < k; ++i) {
             double lv = log(test.sigma[i]) + o->covariance_scaling * s2[i];
+            if (lv > 11356.0 || lv < -11399.0) bad = 1; /* Model.py:630-633, as in chain_step */
             xr[i] = log(remap.sigma[i]) - lv;
             xf[i] = log(test.sigma[i]) - log(remap.sigma[i]);
             logdetL += log(A[i * k + i]);
         }
-        t->proposal = -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xr);
-        t->proposal1 = -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xf);
+        t->proposal = bad ? -INFINITY : -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xr);
+        t->proposal1 = bad ? -INFINITY : -(0.5 * k) * LOG2PI + logdetL - 0.5 * quad_L(k, A, xf);
     }
     return 0;
 }

