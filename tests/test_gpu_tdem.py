@@ -165,9 +165,10 @@ def test_chain_runs_to_termination_fp32(gpu, systems, oracle):
     s = r["scalars"]
     burned = s[:, 1] > 0
     assert burned.mean() > 0.5
-    # burned-in chains keep exactly n_markov_chains + 1 post-burn-in models in every histogram
-    assert np.all(r["ncells_hist"][burned].sum(axis=1) == 3000 + 1)
-    assert np.all(r["rel_hist"][burned].sum(axis=2) == 3000 + 1)
-    assert np.all(r["hitmap"][burned].sum(axis=(1, 2)) == (3000 + 1) * 1209)
+    # burned-in chains keep the models of iterations b .. b + N + 1 (Inference1D.infer runs while
+    # iteration <= N + b, :650-677): N + 2 entries in every histogram
+    assert np.all(r["ncells_hist"][burned].sum(axis=1) == 3000 + 2)
+    assert np.all(r["rel_hist"][burned].sum(axis=2) == 3000 + 2)
+    assert np.all(r["hitmap"][burned].sum(axis=(1, 2)) == (3000 + 2) * 1209)
     # misfit of burned-in chains is of the order of the number of active channels
     assert np.median(s[burned, 14]) < 3 * 45
