@@ -58,27 +58,6 @@ template <typename T> struct FwdExtra<T, KIND_TDEM> {
     T lam[GBP_TD_MAXLAM], wgt[GBP_TD_MAXLAM];  // this sounding's Hankel abscissae and geometry weights
     T sbuf[TD_ROWS];
 };
-// Team of warps for one chain.  When the batch has fewer chains left than the CTA has warps (small batches, and
-// the tail of every batch: a few chains run 3-6x longer than the median because of the reference's reset rule),
-// warps without a chain attach to a running chain of their CTA as helpers and evaluate whole frequencies of its
-// forward / Jacobian calls.  Hand-off through shared memory: the owner publishes a request (seq++), each helper
-// takes the frequencies rank, rank + T, ... and bumps `done`.  Rows of pred / J are disjoint per frequency, so
-// results are bitwise identical whatever the team size.
-constexpr int TEAM_MAX_HELPERS = 5;
-template <typename T> struct Team {
-    volatile int alive;       // the owner warp still has a chain (helpers may attach)
-    volatile int n_helpers;   // attached helpers; ranks 1..n_helpers
-    volatile unsigned req;    // (request counter << 8) | team size T of that request (owner = rank 0): one word,
-                              // so that a helper decides from a consistent snapshot whether it takes part
-    volatile int done;        // helpers finished with the current request
-    int kk, sens;
-    T alt;
-    const T* msig;
-    const T* mthk;
-    T* pred;
-    T* J;
-};
-
 // relative / additive errors, one per system (registers)
 template <typename R, int NS> struct Errs {
     R rel[NS], add[NS];
@@ -109,7 +88,6 @@ template <typename R, typename T, int NC, int KIND> struct __align__(16) WarpSta
     int ctr[CT_N];          // cold counters
     R bestv[BV_N];          // best posterior / errors
     void* outp[OP_N];       // this chain's output rows
-    Team<T>* team;          // this warp's team slot (shared memory)
     FwdExtra<T, KIND> fx;
 };
 
@@ -263,112 +241,10 @@ __device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const type
         if (J) w->ctr[CT_N_SENS]++;
     }
     __syncwarp();
-    if constexpr (KIND == KIND_TDEM) {
+    if constexpr (KIND == KIND_TDEM)
         tdem_eval<T>(*S, tab, w->fx.lam, w->fx.wgt, kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
-    } else {
-        Team<T>* tm = w->team;
-        GBP_SHARED(tm);
-        const int nh = __shfl_sync(FULL, (int)tm->n_helpers, 0);
-        if (nh == 0) {
-            fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
-        } else {  // team forward: publish the request, take rank 0's frequencies, wait for the helpers
-            const int Tn = 1 + (nh > TEAM_MAX_HELPERS ? TEAM_MAX_HELPERS : nh);
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                tm->kk = kk;
-                tm->sens = J != nullptr;
-                tm->alt = alt;
-                tm->msig = w->msig;
-                tm->mthk = w->mthk;
-                tm->pred = pred;
-                tm->J = J;
-                tm->done = 0;
-                __threadfence_block();
-                tm->req = (((tm->req >> 8) + 1u) << 8) | (unsigned)Tn;
-            }
-            __syncwarp();
-            fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr, 0, Tn);
-            if (lane == 0) {
-#pragma unroll 1
-                while (tm->done < Tn - 1) __nanosleep(32);
-            }
-            __threadfence_block();
-            __syncwarp();
-        }
-    }
-}
-
-// A warp without a chain serves the running chains of its CTA until none is left (frequency-domain kernels).
-template <typename T>
-__device__ __noinline__ void team_helper_loop(Team<T>* teams, int n_warps, const SysShared<T>* S, const T* tab)
-{
-    GBP_SHARED(teams);
-    const int lane = lane_id();
-#pragma unroll 1
-    for (;;) {
-        // attach to the running chain with the fewest helpers
-        int owner = -1, rank = 0;
-        unsigned seen = 0u;
-        if (lane == 0) {
-            int any_alive = 0, best = -1, bestn = TEAM_MAX_HELPERS;
-#pragma unroll 1
-            for (int o = 0; o < n_warps; ++o)
-                if (teams[o].alive) {
-                    any_alive = 1;
-                    const int n = teams[o].n_helpers;
-                    if (n < bestn) {
-                        bestn = n;
-                        best = o;
-                    }
-                }
-            if (best >= 0) {
-                seen = teams[best].req;  // BEFORE attaching: a request published after the attach must be seen as new
-                __threadfence_block();
-                rank = atomicAdd((int*)&teams[best].n_helpers, 1) + 1;
-                if (rank > TEAM_MAX_HELPERS) {  // lost a race for the last slot
-                    atomicSub((int*)&teams[best].n_helpers, 1);
-                    best = -2;
-                }
-            }
-            owner = (best >= 0) ? best : (any_alive ? -2 : -1);
-        }
-        owner = __shfl_sync(FULL, owner, 0);
-        rank = __shfl_sync(FULL, rank, 0);
-        if (owner == -1) return;
-        if (owner == -2) {
-            __nanosleep(2000);
-            continue;
-        }
-        Team<T>* tm = teams + owner;
-#pragma unroll 1
-        for (;;) {
-            int go = 0;
-            if (lane == 0) {  // `seen` lives in lane 0
-#pragma unroll 1
-                for (;;) {
-                    const unsigned r = tm->req;
-                    if (r != seen) {
-                        seen = r;
-                        go = 1 + (int)(r & 0xffu);
-                        break;
-                    }
-                    if (!tm->alive) break;
-                    __nanosleep(64);
-                }
-            }
-            go = __shfl_sync(FULL, go, 0);
-            if (!go) break;  // the owner finished: look for another chain
-            __threadfence_block();
-            const int Tn = go - 1;
-            if (rank < Tn) {
-                fdem_eval<T>(*S, tab, tm->alt, tm->kk, tm->msig, tm->mthk, tm->pred, tm->J, tm->sens != 0, rank, Tn);
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) atomicAdd((int*)&tm->done, 1);
-            }
-        }
-    }
+    else
+        fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
 }
 
 // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
@@ -1371,7 +1247,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     __shared__ uint64_t bar;
     __shared__ Consts<R> consts;
     __shared__ typename SysOf<T, KIND>::shared sys_s;
-    __shared__ Team<T> teams[WARPS];
     T* tab = reinterpret_cast<T*>(smem);
     uint32_t tab_bytes;
     if constexpr (KIND == KIND_TDEM) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
@@ -1397,29 +1272,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     // than the machine still spreads evenly; later chains are claimed from a device-side counter
     int c = warp * gridDim.x + blockIdx.x;
     const int lane = threadIdx.x & 31;
-    if (lane == 0) {
-        teams[warp].alive = c < P.B;
-        teams[warp].n_helpers = 0;
-        teams[warp].req = 1u;
-        teams[warp].done = 0;
-        ws->team = &teams[warp];
-    }
-    __syncthreads();
 #pragma unroll 1
     while (c < P.B) {
         run_chain<R, T, NC, KIND>(ws, &consts, &sys_s, S, tab, P, c);
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(P.work_counter, 1);
         c = __shfl_sync(FULL, nxt, 0);
-    }
-    if constexpr (KIND == KIND_FDEM) {
-        // out of chains: release this warp's helpers, then help the chains of this CTA that are still running
-        if (lane == 0) {
-            teams[warp].alive = 0;
-            __threadfence_block();
-        }
-        __syncwarp();
-        team_helper_loop<T>(teams, WARPS, &sys_s, tab);
     }
 }
 

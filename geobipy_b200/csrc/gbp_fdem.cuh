@@ -74,7 +74,6 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
 template <typename T> struct SysShared {
     int n_freq, n_seg, tab_stride, pad;
     Seg seg[MAX_SEG];
-    int seg_first[GBP_MAXF];  // first segment of each frequency (a team of warps splits a forward by frequency)
     T omu[GBP_MAXF], k2re[GBP_MAXF], hd0[GBP_MAXF];
 };
 template <typename T> __device__ __forceinline__ void fill_sys_shared(const SysDev& S, SysShared<T>& q)
@@ -83,8 +82,6 @@ template <typename T> __device__ __forceinline__ void fill_sys_shared(const SysD
     q.n_seg = S.n_seg;
     q.tab_stride = S.tab_stride;
     for (int i = 0; i < MAX_SEG; ++i) q.seg[i] = S.seg[i];
-    for (int f = 0; f < GBP_MAXF; ++f) q.seg_first[f] = S.n_seg;
-    for (int i = S.n_seg - 1; i >= 0; --i) q.seg_first[S.seg[i].freq] = i;
     for (int i = 0; i < GBP_MAXF; ++i) {
         q.omu[i] = (T)S.omu[i];
         q.k2re[i] = (T)S.k2re[i];
@@ -98,12 +95,10 @@ template <typename T> __device__ __forceinline__ void fill_sys_shared(const SysD
 // (conductivity, thickness); mthk[L-1] unused.  pred: [2F] (real then imag).  J: [2F][KS], written only
 // if sens.  One function body serves forward-only and forward+Jacobian calls (`sens` is warp-uniform) so
 // that all warps of an SM share the same instruction-cache lines.  All lanes of the warp must call.
-// Frequencies f0, f0 + fstep, ... are evaluated (0, 1 = all of them): the warps of a team each take a subset and
-// write disjoint rows of pred / J, so the result is bitwise independent of the team size.
 template <typename T>
 __device__ __noinline__ void fdem_eval(const SysShared<T>& Q, const T* __restrict__ tab, T alt, int L,
                                        const T* __restrict__ msig, const T* __restrict__ mthk, T* __restrict__ pred,
-                                       T* __restrict__ J, const bool sens, const int f0 = 0, const int fstep = 1)
+                                       T* __restrict__ J, const bool sens)
 {
     __builtin_assume(__isShared(&Q));
     __builtin_assume(__isShared(tab));
@@ -125,9 +120,9 @@ __device__ __noinline__ void fdem_eval(const SysShared<T>& Q, const T* __restric
     T Dr[KS], Di[KS], lr[KS], li[KS];
     T jr[KS], ji[KS];
 
+    int seg = 0;
 #pragma unroll 1
-    for (int f = f0; f < F; f += fstep) {
-        int seg = Q.seg_first[f];
+    for (int f = 0; f < F; ++f) {
         const T omu = Q.omu[f];
         const T k2 = Q.k2re[f];
         const T hd = Q.hd0[f] - T(2) * alt;

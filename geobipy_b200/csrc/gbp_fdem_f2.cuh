@@ -74,8 +74,7 @@ __device__ __forceinline__ c2 cexp(c2 z)
 template <>
 __device__ __noinline__ void fdem_eval<float>(const SysShared<float>& Q, const float* __restrict__ tab, float alt, int L,
                                               const float* __restrict__ msig, const float* __restrict__ mthk,
-                                              float* __restrict__ pred, float* __restrict__ J, const bool sens,
-                                              const int f0, const int fstep)
+                                              float* __restrict__ pred, float* __restrict__ J, const bool sens)
 {
     using namespace f2;
     __builtin_assume(__isShared(&Q));
@@ -98,9 +97,9 @@ __device__ __noinline__ void fdem_eval<float>(const SysShared<float>& Q, const f
     v2 Dr[KS], Di[KS], lr[KS], li[KS];
     v2 jr[KS], ji[KS];
 
+    int seg = 0;
 #pragma unroll 1
-    for (int f = f0; f < F; f += fstep) {
-        int seg = Q.seg_first[f];
+    for (int f = 0; f < F; ++f) {
         const float omu = Q.omu[f];
         const float k2 = Q.k2re[f];
         const float hd = Q.hd0[f] - 2.f * alt;
