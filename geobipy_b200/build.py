@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "gbp_api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("gbp_api.cu", "gbp_chain.cuh", "gbp_fdem.cuh", "gbp_fdem_f2.cuh", "gbp_tdem.cuh", "gbp_math.cuh", "gbp_tables.h",
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("gbp_api.cu", "gbp_chain.cuh", "gbp_fdem.cuh", "gbp_fdem_f2.cuh", "gbp_tdem.cuh", "gbp_tdem_f2.cuh", "gbp_math.cuh", "gbp_tables.h",
                                                      "gbp_tdem_tables.h")] + [
     os.path.join(ROOT, "include", f) for f in ("geobipy_b200.h", "gbp_filter_tables.h")]
 OUT = os.path.join(HERE, "libgeobipy_b200.so")

@@ -677,6 +677,9 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
         P.opt.add_init2 *= TD_F32_SCALE;
         P.opt.add_min2 *= TD_F32_SCALE;
         P.opt.add_max2 *= TD_F32_SCALE;
+        const char* e = std::getenv("GBP_TDEM_WARPS");  // experiment switch: resident chains per SM
+        if (e && std::atoi(e) == 18)
+            return launch_chain<float, float, 48, 18, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
         return launch_chain<float, float, 48, 16, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
     }
     if (precision == GBP_PRECISION_F64)

@@ -30,6 +30,7 @@
 #include "gbp_fdem.cuh"
 #include "gbp_fdem_f2.cuh"
 #include "gbp_tdem.cuh"
+#include "gbp_tdem_f2.cuh"
 
 namespace gbp {
 
