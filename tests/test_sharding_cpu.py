@@ -40,6 +40,8 @@ def _worker(rank, world, port, n_total, q):
     local = {
         "hitmap": (idx.view(-1, 1, 1) * torch.ones((1, 4, 5), dtype=torch.int64)).to(torch.int32),
         "scalars": torch.stack([idx.double(), idx.double() ** 2], dim=1),
+        # per-system error histograms of a dual-moment (time-domain) datapoint: [block, n_systems, n_err_bins]
+        "rel_hist": (idx.view(-1, 1, 1) + torch.arange(2).view(1, 2, 1) * 1000 + torch.zeros((1, 1, 99), dtype=torch.int64)).to(torch.int32),
     }
     out = gather_to_rank0(local, n_total)
     if rank == 0:
@@ -66,6 +68,8 @@ def test_gather_world_size_2_gloo(n_total):
     assert out["hitmap"].shape == (n_total, 4, 5)
     assert np.array_equal(out["hitmap"][:, 0, 0], np.arange(n_total))
     assert np.array_equal(out["scalars"][:, 1], np.arange(n_total) ** 2.0)
+    assert out["rel_hist"].shape == (n_total, 2, 99)
+    assert np.array_equal(out["rel_hist"][:, 1, 7], np.arange(n_total) + 1000)
 
 
 def test_summarise_hitmap_matches_numpy():
