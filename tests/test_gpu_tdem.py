@@ -172,3 +172,75 @@ def test_chain_runs_to_termination_fp32(gpu, systems, oracle):
     assert np.all(r["hitmap"][burned].sum(axis=(1, 2)) == (3000 + 2) * 1209)
     # misfit of burned-in chains is of the order of the number of active channels
     assert np.median(s[burned, 14]) < 3 * 45
+
+
+def test_chain_fp32_matches_fp64_ensemble(gpu, systems, oracle):
+    """Production path (fp32 forward and fp32 sampler arithmetic in 2^40-scaled data units) against the fp64
+    instantiation (the oracle's trajectory twin) on the same sounding, 192 chains each run to the reference's
+    termination rule.  Yardstick = the fp64 path's own seed-to-seed scatter: the fp32-vs-fp64 discrepancy of every
+    statistic must not exceed 2.5x the discrepancy between two fp64 ensembles with different seeds (plus a small
+    floor): acceptance rate, mean layer count, layer-count distribution (total variation), posterior-mean conductivity
+    bin per depth cell over the top 150 m (RMS, bin width 0.077 ln-units), and the posterior means of the four error
+    parameters (in histogram bins)."""
+    nrep = 192
+    data, alt = _observed(gpu, systems, oracle, 1, first=2)
+    d = np.tile(data, (nrep, 1))
+    a = np.full(nrep, alt[0])
+    opt = gpu.make_options(n_markov_chains=4000, update_plot_every=1000, burn_in_min_iter=1000, **gpu.SKYTEM_OPTIONS)
+    st = {}
+    for tag, prec, seed in (("f32", 32, 4242), ("f64", 64, 4242), ("f64b", 64, 777)):
+        r = gpu.rjmcmc_run(systems[0], opt, d, a, seed=seed, precision=prec, outputs=("hitmap", "ncells_hist", "rel_hist", "add_hist", "scalars"))
+        sc = r["scalars"]
+        nc = r["ncells_hist"].sum(axis=0).astype(np.float64)
+        hm = r["hitmap"].sum(axis=0, dtype=np.int64)[:, :300].astype(np.float64)
+        eh = np.concatenate([r["rel_hist"].sum(axis=0), r["add_hist"].sum(axis=0)]).astype(np.float64)   # [4, 99]
+        st[tag] = dict(acc=sc[:, oracle.S_N_ACCEPT].sum() / sc[:, oracle.S_TOTAL_ITER].sum(), nc=nc / nc.sum(),
+                       kbar=(nc * np.arange(nc.size)).sum() / nc.sum(),
+                       mean_bin=(hm * np.arange(hm.shape[0])[:, None]).sum(axis=0) / hm.sum(axis=0),
+                       err_bin=(eh * np.arange(99)).sum(axis=1) / eh.sum(axis=1), burned=sc[:, oracle.S_BURNED_IN].mean())
+    assert st["f64"]["burned"] > 0.5
+
+    def dist(x, y):
+        return dict(acc=abs(x["acc"] - y["acc"]), kbar=abs(x["kbar"] - y["kbar"]), tv=0.5 * np.abs(x["nc"] - y["nc"]).sum(),
+                    rms=float(np.sqrt(np.mean((x["mean_bin"] - y["mean_bin"]) ** 2))),
+                    err=float(np.max(np.abs(x["err_bin"] - y["err_bin"]))), burned=abs(x["burned"] - y["burned"]))
+    d32, d64 = dist(st["f32"], st["f64"]), dist(st["f64b"], st["f64"])
+    floor = dict(acc=0.01, kbar=0.05, tv=0.02, rms=0.25, err=0.5, burned=0.08)
+    for key in floor:
+        assert d32[key] <= 2.5 * d64[key] + floor[key], (key, d32, d64)
+
+
+def test_full_size_properties(gpu, systems):
+    """A 4096-sounding batch (the bench's size) through size-independent invariants, device-pointer path."""
+    import torch
+    from geobipy_b200.synthetic import synthetic_batch
+    B, nit = 4096, 50
+    b = synthetic_batch(0, 256, max_depth=400.0, n_channels=45)
+    sig = torch.tensor(np.tile(b["sigma"], (16, 1)), device="cuda")
+    thk = torch.tensor(np.tile(b["thickness"], (16, 1)), device="cuda")
+    nl = torch.tensor(np.tile(b["nlayers"], 16), device="cuda")
+    alt = torch.tensor(np.tile(b["height"], 16), device="cuda")
+    data = gpu.forward(systems[0], nl, sig, thk, alt, precision=64)
+    assert bool((data > 0).all())                                   # dBz/dt of a layered earth: positive windows
+    # linearity of the window operator in the frequency response: halving every conductivity is NOT linear, but
+    # the forward is invariant under splitting a layer in two equal-conductivity halves
+    sig2 = torch.cat([sig[:, :1], sig], dim=1)[:, :30].contiguous()
+    thk2 = torch.cat([0.5 * thk[:, :1], 0.5 * thk[:, :1], thk[:, 1:]], dim=1)[:, :30].contiguous()
+    ok = (nl >= 2) & (nl < 30)      # the first layer of a multi-layer model has a finite thickness
+    d2 = gpu.forward(systems[0], (nl + 1).to(torch.int32), sig2, thk2, alt, precision=64)
+    assert torch.allclose(d2[ok], data[ok], rtol=1e-9, atol=0.0)
+    opt = gpu.make_options(n_markov_chains=1000, **gpu.SKYTEM_OPTIONS)
+    res = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=1, max_iterations=nit, precision=32,
+                         outputs=("hitmap", "ncells_hist", "rel_hist", "add_hist", "accept_trace", "scalars"))
+    torch.cuda.synchronize()
+    sc = res["scalars"].cpu().numpy()
+    assert (sc[:, 0] == nit).all()
+    assert (res["hitmap"].sum(dim=1) == nit).all()                 # every depth cell visited once per iteration
+    assert (res["ncells_hist"].sum(dim=1) == nit).all()
+    assert (res["rel_hist"].sum(dim=2) == nit).all() and (res["add_hist"].sum(dim=2) == nit).all()
+    assert np.array_equal(res["accept_trace"][:, :nit + 1].sum(dim=1).cpu().numpy(), sc[:, 8])
+    assert (sc[:, 20:24].sum(axis=1) == nit).all()
+    assert len(set(sc[::256, 8])) > 1                               # same data, different sounding index: different paths
+    res2 = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=1, max_iterations=nit, precision=32, outputs=("hitmap", "scalars"))
+    torch.cuda.synchronize()
+    assert torch.equal(res2["hitmap"], res["hitmap"])               # idempotence: same seed -> bit-identical
