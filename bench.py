@@ -382,6 +382,9 @@ def run_b200_arm(args):
         fpf = ops.flops_per_forward(system, max(1, int(round(mean_k))))
         fwd_equiv = (n_fwd - n_sens) + 3.0 * n_sens
         flops = fpf * fwd_equiv
+        # measured denominators for the two pipes that bound the path; a Jacobian pass ~1.3 forwards of MUFU
+        fp32_peak, mufu_peak = ops.measure_peaks()
+        mufu = ops.mufu_per_forward(system, max(1, int(round(mean_k)))) * ((n_fwd - n_sens) + 1.3 * n_sens)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -394,7 +397,9 @@ def run_b200_arm(args):
                          "note": "BASELINE.json asks for the HBM fraction; this path is bound by scalar FP/SFU issue and latency, not by HBM (SURVEY.md 8(d))"},
             "roofline_compute": {"bound": "fp32-issue", "achieved": flops / (last_kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                  "flops_per_forward": fpf, "forward_equivalents_per_launch": fwd_equiv,
-                                 "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_source": "nominal 148 SM x 128 FMA/clk x 1965 MHz"},
+                                 "peak": fp32_peak, "peak_source": "measured on this device: 8 independent FFMA chains per thread (gbp_measure_peaks); nominal 148 SM x 128 FMA/clk x 1965 MHz = 74.4",
+                                 "mufu_achieved_gops": mufu / (last_kernel_ms * 1e-3) / 1e9, "mufu_peak_gops": mufu_peak,
+                                 "mufu_frac": mufu / (last_kernel_ms * 1e-3) / 1e9 / mufu_peak},
             "chain_stats": {"iterations_per_chain": last_iters / B, "mean_layers": mean_k, "forwards_per_iteration": n_fwd / last_iters,
                             "jacobians_per_iteration": n_sens / last_iters, "burned_in_fraction": burned / B},
         }

@@ -85,7 +85,8 @@ class ChainBuffersC(ctypes.Structure):
 # every symbol include/geobipy_b200.h declares
 EXPORTS = (
     "gbp_version", "gbp_last_error", "gbp_device_count", "gbp_n_depth", "gbp_flops_per_forward",
-    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms",
+    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_mufu_per_forward", "gbp_measure_peaks",
+    "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host",
     "gbp_tdem_n_channels", "gbp_tdem_window_operator", "gbp_tdem_flops_per_forward",
@@ -135,6 +136,12 @@ def load():
     lib.gbp_rjmcmc_run.argtypes = [vp, vp, i32, vp, vp, u64, u64, i64, vp, i32, vp]
     lib.gbp_rjmcmc_run_host.restype = i32
     lib.gbp_rjmcmc_run_host.argtypes = [vp, vp, i32, vp, vp, u64, u64, i64, vp, i32, i32]
+    lib.gbp_mufu_per_forward.restype = dbl
+    lib.gbp_mufu_per_forward.argtypes = [vp, i32]
+    lib.gbp_tdem_mufu_per_forward.restype = dbl
+    lib.gbp_tdem_mufu_per_forward.argtypes = [vp, i32]
+    lib.gbp_measure_peaks.restype = i32
+    lib.gbp_measure_peaks.argtypes = [vp, vp]
     lib.gbp_tdem_n_channels.restype = i32
     lib.gbp_tdem_n_channels.argtypes = [vp]
     lib.gbp_tdem_window_operator.restype = i32

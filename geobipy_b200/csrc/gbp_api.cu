@@ -236,6 +236,41 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
     return time_end(st);
 }
 
+// ---- microbenchmarks of the two pipes that bound this path (the roofline denominators for scalar
+// fp32 issue and special-function throughput must be measured on the same box)
+__global__ void __launch_bounds__(256) peak_fma_kernel(float* out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+__global__ void __launch_bounds__(256) peak_mufu_kernel(float* out, int iters)
+{
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + .1f, x2 = x0 + .2f, x3 = x0 + .3f, x4 = x0 + .4f, x5 = x0 + .5f, x6 = x0 + .6f, x7 = x0 + .7f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x0));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x1));
+            asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x2));
+            asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x3));
+            asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(x4));
+            asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(x5));
+            asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(x6));
+            asm volatile("cos.approx.ftz.f32 %0, %0;" : "+f"(x7));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
 int* g_counter[64] = {nullptr};
 int get_counter(int** out)
 {
@@ -518,6 +553,55 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                                 return gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
                                                       precision, nullptr);
                             });
+}
+
+int gbp_measure_peaks(double* fp32_tflops, double* mufu_gops)
+{
+    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best_f = 0.0, best_m = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0.f;
+        CK(cudaEventRecord(e0));
+        peak_fma_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double f = 2.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep && f > best_f) best_f = f;
+        CK(cudaEventRecord(e0));
+        peak_mufu_kernel<<<blocks, threads>>>(d, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double m = 32.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e9;
+        if (rep && m > best_m) best_m = m;
+        g_launches += 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (fp32_tflops) *fp32_tflops = best_f;
+    if (mufu_gops) *mufu_gops = best_m;
+    return 0;
+}
+
+// MUFU-class (special function unit) operations of one forward: per abscissa 3 (basement sqrt, sqrt, rcp) + 9 per
+// finite layer (3 complex sqrt, 1 clamp rcp, 3 exp/sin/cos, 2 complex reciprocals) + 4 (reflection coefficient, height term)
+double gbp_mufu_per_forward(const gbp_fdem_system* sys, int L)
+{
+    return (double)gbp_filter_points(sys) * (9.0 * (double)L - 2.0);
+}
+double gbp_tdem_mufu_per_forward(const gbp_tdem_survey* sv, int L)
+{
+    TdCache* tc;
+    if (get_td_tables(sv, &tc, false)) return 0.0;
+    // per (frequency, abscissa): basement 3 + 1, per finite layer 3 + 1 + 1 + 3 + 1, top 1
+    return (double)TD_NF * tc->host.dev.n_lam * (9.0 * (double)L - 4.0);
 }
 
 // ------------------------------------------------------------------------------------------ time domain

@@ -349,3 +349,18 @@ def forward(system, nlayers, sigma, thickness, altitude, **kw):
 
 
 tdem_forward = forward
+
+
+def mufu_per_forward(system, n_layers):
+    """Special-function-unit operations of one forward (rcp, sqrt, ex2, sin, cos)."""
+    lib = _lib.load()
+    f = lib.gbp_tdem_mufu_per_forward if is_tdem(system) else lib.gbp_mufu_per_forward
+    return float(f(ctypes.addressof(system), int(n_layers)))
+
+
+def measure_peaks():
+    """(fp32 TFLOP/s, MUFU Gop/s) measured on the current device with two microbenchmark kernels."""
+    lib = _lib.require_cuda()
+    a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    _lib.check(lib.gbp_measure_peaks(ctypes.byref(a), ctypes.byref(b)))
+    return float(a.value), float(b.value)

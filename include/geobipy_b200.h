@@ -148,6 +148,11 @@ int gbp_n_depth(const gbp_options *opt);
 double gbp_flops_per_forward(const gbp_fdem_system *sys, int n_layers);
 /* number of (frequency, abscissa) filter points one forward evaluates (RESOLVE: 860) */
 int gbp_filter_points(const gbp_fdem_system *sys);
+/* special-function-unit (MUFU: rcp, sqrt, ex2, sin, cos) operations of one forward, same convention */
+double gbp_mufu_per_forward(const gbp_fdem_system *sys, int n_layers);
+/* measured peaks of the two pipes that bound this path on the current device: dependent-free FFMA chains
+ * (TFLOP/s, 2 flops per FMA) and MUFU operations (Gop/s).  Two tiny kernels, best of 3 after warm-up. */
+int gbp_measure_peaks(double *fp32_tflops, double *mufu_gops);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t gbp_launch_count(void);
 /* mean duration [ms] and launch count of the last gbp_rjmcmc_run / forward kernel, measured with CUDA
@@ -198,6 +203,7 @@ int gbp_tdem_window_operator(const gbp_tdem_survey *sv, double *freq, double *MR
 /* algorithmic flop count of one forward: n_freq x n_abscissae admittance recursions (75 L + 39 each, the
  * SURVEY.md 8(d) convention) + the 2 C x 2 n_freq window products */
 double gbp_tdem_flops_per_forward(const gbp_tdem_survey *sv, int n_layers);
+double gbp_tdem_mufu_per_forward(const gbp_tdem_survey *sv, int n_layers);
 
 /* out: [B][C] dBz/dt window averages (V/(A m^4) for unit moment), J: [B][C][l_stride] = d out / d ln(sigma).
  * altitude = transmitter height above ground [B].  DEVICE pointers, stream ordered. */

@@ -244,3 +244,40 @@ def test_full_size_properties(gpu, systems):
     res2 = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=1, max_iterations=nit, precision=32, outputs=("hitmap", "scalars"))
     torch.cuda.synchronize()
     assert torch.equal(res2["hitmap"], res["hitmap"])               # idempotence: same seed -> bit-identical
+
+
+def test_single_moment_datapoint_twin(gpu, oracle):
+    """A time-domain datapoint with ONE system (high moment only): scalar error options, 1-D error proposals -
+    fp64 chains are again trajectory twins of the oracle."""
+    defs = oracle.skytem_definitions()[:1]
+    osys = oracle.make_tdem_system(defs)
+    sv = gpu.make_tdem_survey_struct(gpu.skytem_definitions()[:1])
+    assert gpu.n_channels(sv) == 26 and osys.C == 26 and osys.n_sys == 1
+    rng = np.random.default_rng(12)
+    B, NIT = 6, 300
+    alt = rng.uniform(28.0, 40.0, B)
+    data = np.zeros((B, 26))
+    t = np.array(osys.t_centre[:26])
+    for b in range(B):
+        sig = 10.0 ** rng.uniform(-2.5, -0.5, 3)
+        clean = oracle.tdem_forward(osys, alt[b], sig, [20.0, 40.0, 1.0])
+        data[b] = clean * (1.0 + 0.03 * rng.standard_normal(26)) + 1e-14 * np.sqrt(1e-3 / t) * rng.standard_normal(26)
+    kw = dict(min_edge=1.0, max_edge=550.0, min_width=1.0, covariance_scaling=0.5, rel_init=0.05, rel_min=0.005, rel_max=0.5,
+              rel_prop_var=1e-6, add_init=2e-14, add_min=1e-16, add_max=1e-10, add_prop_var=1e-5)
+    opt = gpu.make_options(n_markov_chains=2000, **kw)
+    oo = oracle.resolve_options(n_markov_chains=2000, **kw)
+    assert opt.n_systems <= 1
+    pred = gpu.forward(sv, np.full(B, 1, np.int32), np.full((B, 1), 0.02), np.ones((B, 1)), alt, precision=64)
+    for b in range(B):
+        ref = oracle.tdem_forward(osys, alt[b], [0.02], [1.0])
+        assert np.all(np.abs(pred[b] - ref) <= 5e-9 * np.abs(ref))
+    res = gpu.rjmcmc_run(sv, opt, data, alt, seed=5, max_iterations=NIT, precision=64)
+    assert res["rel_hist"].shape == (B, 99)
+    same = 0
+    for b in range(B):
+        r = oracle.run_chain(osys, oo, data[b], alt[b], 5, b, max_iterations=NIT)
+        same += (np.array_equal(res["hitmap"][b], r["hitmap"]) and np.array_equal(res["accept_trace"][b], r["accept_trace"])
+                 and np.array_equal(res["rel_hist"][b], r["rel_hist"].reshape(-1)) and np.array_equal(res["add_hist"][b], r["add_hist"].reshape(-1)))
+    assert same >= B - 1, same
+    r32 = gpu.rjmcmc_run(sv, opt, data, alt, seed=5, max_iterations=NIT, precision=32, outputs=("scalars",))
+    assert (r32["scalars"][:, 0] == NIT).all()
