@@ -209,8 +209,10 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t smem = tab_bytes + (size_t)WARPS * per_warp;
-    if (smem + 2048 > (size_t)max_smem) return fail("rjmcmc kernel does not fit in shared memory on this device");
     auto kern = rjmcmc_kernel<R, T, NC, WARPS, KIND>;
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kern));
+    if (smem + fa.sharedSizeBytes + 1024 > (size_t)max_smem) return fail("rjmcmc kernel does not fit in shared memory on this device");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // per-chain Jacobian mirror (L2 resident: 1.4 KB per chain in fp32)
     const size_t jbytes = (size_t)P.B * NC * KS * sizeof(T);
@@ -226,6 +228,13 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
     if (grid > P.B) grid = P.B;
     ChainParams Q = P;
     Q.n_warps_total = grid * WARPS;
+    {
+        const char* e = std::getenv("GBP_SPEC_HELPERS");  // 0 switches speculative evaluation off
+        int hmax = e ? std::atoi(e) : 12;
+        Q.spec_helpers = hmax < 0 ? 0 : (hmax > WARPS - 1 ? WARPS - 1 : hmax);
+        const char* m = std::getenv("GBP_SPEC_MIN_REJECTIONS");
+        Q.spec_min_rejections = m ? std::atoi(m) : 24;
+    }
     Q.jstore = g_jstore[dev];
     // device-side work counter: chains beyond the first wave are claimed dynamically
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));

@@ -122,6 +122,8 @@ struct ChainParams {
     gbp_chain_buffers out;
     double data_scale;       // observed data and additive errors are multiplied by this on the way in (fp32
                              // time-domain path: 2^40, so that squares of 1e-15 V/Am^4 stay normal numbers)
+    int spec_helpers;        // max warps that evaluate future iterations of one chain speculatively (0 = off)
+    int spec_min_rejections; // a chain speculates once it has rejected this many steps in a row
     int* work_counter;
     void* jstore;            // [B][NC*KS] of T: Jacobian of each chain's current model
 };
@@ -512,12 +514,12 @@ __device__ __noinline__ prop2_t<R> ch_propose_ln_error2(Rng g, R c0, R c1, const
     GBP_SHARED(sd);
     GBP_SHARED(lnmin);
     GBP_SHARED(lnmax);
-    pair_t<R> z = normal2_at<R>(g.block++, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
+    pair_t<R> z = normal2_at<R>(g.block++, g.iter, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
     R x0 = c0 + sd[0] * z.a, x1 = c1 + sd[1] * z.b;
     int tries = 0;
 #pragma unroll 1
     while (x0 < lnmin[0] || x0 > lnmax[0] || x1 < lnmin[1] || x1 > lnmax[1]) {
-        z = normal2_at<R>(g.block++, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
+        z = normal2_at<R>(g.block++, g.iter, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
         x0 = c0 + sd[0] * z.a;
         x1 = c1 + sd[1] * z.b;
         tries++;
@@ -762,11 +764,489 @@ __device__ __noinline__ void ch_save_best(WarpState<R, T, NC, KIND>* w, int ml, 
     __syncwarp();
 }
 
+// ================================================================ one accept_reject step
+// Hot state of a chain (registers of the warp that runs it).
+template <typename R, int NS> struct Hot {
+    Rng rng;
+    int k, mcur, vcur, pcur;
+    bool j_valid;            // the shared-memory Jacobian is the current model's
+    Errs<R, NS> ln_err, err; // ln(relative / additive error) and the errors themselves, per system
+    R ln_ref, sig_lo;
+    R misfit, prior, likelihood;
+    int dwell;
+};
+
+// Inference1D.accept_reject :537-631.  SPEC = false: the chain's own step (state updated on acceptance, outgoing
+// model flushed to the posteriors).  SPEC = true: speculative evaluation of a FUTURE iteration by another warp on
+// a private copy of the chain state: same arithmetic, same sub-stream of random numbers, but nothing is committed -
+// the caller only learns whether the step would be rejected.
+template <bool SPEC, typename R, typename T, int NC, int KIND>
+__device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Consts<R>* K,
+                                        const typename SysOf<T, KIND>::shared* S, const T* tab, const T alt, const R nahl,
+                                        T* const jg, Hot<R, ns_of(KIND)>& h, bool& accepted, bool& chol_failed)
+{
+    constexpr int NS = ns_of(KIND);
+    typedef Errs<R, NS> errs_t;
+    constexpr int JBYTES = NC * KS * (int)sizeof(T);
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    const int lane = lane_id();
+    const int C = K->C;
+    const int ml = K->kmax;
+    Rng& rng = h.rng;
+    int &k = h.k, &mcur = h.mcur, &vcur = h.vcur, &pcur = h.pcur, &dwell = h.dwell;
+    bool& j_valid = h.j_valid;
+    errs_t &ln_err = h.ln_err, &err = h.err;
+    R &misfit = h.misfit, &prior = h.prior, &likelihood = h.likelihood;
+    const R ln_ref = h.ln_ref, sig_lo = h.sig_lo;
+    {
+        // ---- RectilinearMesh1D.perturb :993-1120 (warp-uniform).  Proposed mesh -> mesh[mcur^1],
+        //      remapped values -> val[vcur^1].sig and ls_r; for ACT_NONE only ls_r is filled.
+        const MeshBuf<R>& m0 = w->mesh[mcur];
+        const ValBuf<R>& v0 = w->val[vcur];
+        MeshBuf<R>& m1 = w->mesh[mcur ^ 1];
+        ValBuf<R>& v1 = w->val[vcur ^ 1];
+        int action, kn;
+#pragma unroll 1
+        for (;;) {
+            int event;
+#pragma unroll 1
+            for (;;) {  // Categorical.rng: searchsorted(cumsum(p), U), re-drawn while illegal (:1041-1049)
+                const R u = rng_uniform<R>(rng);
+                event = (u <= K->cum0) ? 0 : (u <= K->cum1) ? 1 : (u <= K->cum2) ? 2 : 3;
+                if (k == 1 && (event == 1 || event == 2)) continue;
+                if (k == ml && event == 0) continue;
+                break;
+            }
+            action = event;
+            kn = k;
+            if (event == ACT_NONE) {
+                if (lane < k) w->ls_r[lane] = v0.ls[lane];
+                break;
+            }
+            if (event == ACT_BIRTH) {  // :1061-1081
+                bool ok = false;
+                int pos = 0;
+                R e = R(0);
+#pragma unroll 1
+                for (int tries = 1; tries <= 10; ++tries) {
+                    e = rt<R>::exp(K->ln_min_edge + K->ln_edge_span * rng_uniform<R>(rng));
+                    pos = __popc(__ballot_sync(FULL, lane <= k && m0.edges[lane] < e));  // searchsorted (left)
+                    R d = INFINITY;  // widths after insertion: cell pos-1 is split in two
+                    if (lane < k)
+                        d = (lane == pos - 1) ? fmin(e - m0.edges[lane], m0.edges[lane + 1] - e)
+                                              : m0.edges[lane + 1] - m0.edges[lane];
+                    const R h = warp_min(d);
+                    if (tries == 10) break;  // the 10th try always restarts (:1078-1080)
+                    if (h > K->min_width) {
+                        ok = true;
+                        break;
+                    }
+                }
+                if (!ok) continue;
+                if (lane <= k + 1) m1.edges[lane] = (lane < pos) ? m0.edges[lane] : (lane == pos ? e : m0.edges[lane - 1]);
+                if (lane <= k) {  // values.insert(pos, values[pos-1]) (:835)
+                    const int src = (lane < pos) ? lane : lane - 1;
+                    v1.sig[lane] = v0.sig[src];
+                    w->ls_r[lane] = v0.ls[src];
+                }
+                kn = k + 1;
+                break;
+            }
+            if (event == ACT_DEATH) {  // :1083-1087, delete_edge :643-689
+                const int i = (int)(rng_uniform<R>(rng) * (R)(k - 1)) + 1;
+                if (lane <= k - 1) m1.edges[lane] = m0.edges[lane + (lane >= i ? 1 : 0)];
+                if (lane < k - 1) {
+                    const int src = lane + (lane >= i ? 1 : 0);
+                    R s = v0.sig[src], l = v0.ls[src];
+                    if (lane == i - 1) {
+                        s = R(0.5) * (v0.sig[i - 1] + v0.sig[i]);
+                        l = rt<R>::log(s);
+                    }
+                    v1.sig[lane] = s;
+                    w->ls_r[lane] = l;
+                }
+                kn = k - 1;
+                break;
+            }
+            {  // ACT_MOVE :1088-1118
+                bool ok = false;
+                int i = 1;
+                R dz = R(0);
+#pragma unroll 1
+                for (int tries = 1; tries <= 10; ++tries) {
+                    i = (int)(R(1) + ((R)k - R(1)) * rng_uniform<R>(rng));
+                    const R zn = rng_normal<R>(rng);
+                    const R sgn = (zn > R(0)) ? R(1) : (zn < R(0) ? R(-1) : R(0));
+                    dz = sgn * K->min_width * rng_uniform<R>(rng);
+                    R d = INFINITY;
+                    if (lane < k)
+                        d = (m0.edges[lane + 1] + (lane + 1 == i ? dz : R(0))) - (m0.edges[lane] + (lane == i ? dz : R(0)));
+                    const R h = warp_min(d);
+                    const R z1 = m0.edges[1] + (i == 1 ? dz : R(0));
+                    const R zl = m0.edges[k - 1] + (i == k - 1 ? dz : R(0));
+                    if (tries == 10) break;
+                    if (h > K->min_width && z1 > K->min_edge && zl < K->max_edge) {
+                        ok = true;
+                        break;
+                    }
+                }
+                if (!ok) continue;
+                if (lane <= k) m1.edges[lane] = m0.edges[lane] + (lane == i ? dz : R(0));
+                if (lane < k) {
+                    v1.sig[lane] = v0.sig[lane];
+                    w->ls_r[lane] = v0.ls[lane];
+                }
+                break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) w->ctr[CT_ACT0 + action]++;
+
+        // ---- Model.stochastic_newton_perturbation :368-419
+        const bool changed = action != ACT_NONE;
+        const int mp = changed ? (mcur ^ 1) : mcur;  // proposed mesh buffer
+        const int vp = vcur ^ 1;                     // proposed values buffer
+        MeshBuf<R>& mesh_p = w->mesh[mp];
+        ValBuf<R>& val_p = w->val[vp];
+        const T* ph = w->pred[pcur];
+        T* pred_t = w->pred[pcur ^ 1];
+        T* const Jh = w->J;
+        T* const J_t = w->J;
+        if (changed) {  // observation.fm_dlogc(remapped_model): J and predicted data of the test datapoint
+            ch_mesh_setup(K, kn, &mesh_p);
+            ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, J_t);
+            j_valid = false;
+            // REFERENCE QUIRK (kept, it shapes the proposal): FdemDataPoint.fm_dlogc stores the remapped model's
+            // predicted data (FdemDataPoint.py:535-545); TdemDataPoint.fm_dlogc stores only the Jacobian, its
+            // predicted-data update is commented out (TdemDataPoint.py:1031-1055), so a time-domain death / move
+            // forms the Newton gradient with the CURRENT model's predicted data.
+            if constexpr (KIND == KIND_FDEM) ph = pred_t;
+        } else if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
+            ch_copy16(w->J, jg, JBYTES);
+            j_valid = true;
+        }
+        ch_set_ivar(w, K, C, err);
+        const R ln_r = (lane < kn) ? w->ls_r[lane] : R(0);
+        const R g = ch_gradient(w, K, kn, mesh_p.t2, w->ls_r, Jh, ph, ln_ref);
+        ch_assemble(w, K, kn, mesh_p.t2, Jh);
+        if (!ch_cholesky(w->A, kn)) {
+            chol_failed = true;
+        } else {
+            const R stepv = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g));  // H * dfk
+            const R mean = ln_r - K->alpha * stepv;  // ln sigma + alpha * pk, pk = -H dfk
+            // sigma' ~ exp(N(mean, H)),  H = (L L')^-1  ->  mean + L^-T z
+            pair_t<R> zz = {R(0), R(0)};
+            const int npair = (kn + 1) / 2;
+            if (lane < npair) zz = normal2_at<R>(rng.block + (uint32_t)lane, rng.iter, rng.snd_lo, rng.snd_hi, rng.seed_lo, rng.seed_hi);
+            rng.block += (uint32_t)npair;
+            const R za = __shfl_sync(FULL, zz.a, lane >> 1), zb = __shfl_sync(FULL, zz.b, lane >> 1);
+            const R zi = (lane < kn) ? ((lane & 1) ? zb : za) : R(0);
+            const R ln_t = mean + ch_solve_LT(w->A, kn, zi);
+            if (lane < kn) {
+                val_p.ls[lane] = ln_t;
+                val_p.sig[lane] = rt<R>::exp(ln_t);
+            }
+            __syncwarp();
+
+            // ---- test_datapoint.perturb() (DataPoint.py:531-573)
+            errs_t ln_t_err = ln_err, err_t = err;
+            if (NS == 1 || K->n_sys == 1) {
+                if (K->solve_rel) {
+                    const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_err.rel[0], K->rel_sd[0], K->rel_lnmin[0], K->rel_lnmax[0]);
+                    ln_t_err.rel[0] = pr.x;
+                    rng.block = pr.block;
+                }
+                if (K->solve_add) {
+                    const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_err.add[0], K->add_sd[0], K->add_lnmin[0], K->add_lnmax[0]);
+                    ln_t_err.add[0] = pr.x;
+                    rng.block = pr.block;
+                }
+            } else {
+                if (K->solve_rel) {
+                    const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.rel[0], ln_err.rel[NS - 1], K->rel_sd, K->rel_lnmin, K->rel_lnmax);
+                    ln_t_err.rel[0] = pr.x0;
+                    ln_t_err.rel[NS - 1] = pr.x1;
+                    rng.block = pr.block;
+                }
+                if (K->solve_add) {
+                    const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.add[0], ln_err.add[NS - 1], K->add_sd, K->add_lnmin, K->add_lnmax);
+                    ln_t_err.add[0] = pr.x0;
+                    ln_t_err.add[NS - 1] = pr.x1;
+                    rng.block = pr.block;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                err_t.rel[s] = (ln_t_err.rel[s] == ln_err.rel[s]) ? err.rel[s] : rt<R>::exp(ln_t_err.rel[s]);
+                err_t.add[s] = (ln_t_err.add[s] == ln_err.add[s]) ? err.add[s] : rt<R>::exp(ln_t_err.add[s]);
+            }
+
+            const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
+            // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
+            // (Model.proposal_probabilities :619) - fused into the same pass.
+            ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : (T*)nullptr);
+            ch_set_ivar(w, K, C, err_t);
+            const pair_t<R> tml = ch_misfit_like(w, C, nahl, pred_t);
+            // error priors: the proposals above are forced inside their bounds (or fall back to the
+            // current values), so DataPoint.probability is the constant err_lp
+            R t_prior = K->err_lp;
+            t_prior += ch_model_prob(K, kn, val_p.ls, mesh_p.lnh, ln_ref);
+            if (t_prior != (R)-INFINITY) {  // early reject on -inf prior (:581, :589): no accept draw
+                R proposal = R(1), proposal1 = R(1);
+                if (jump) {
+                    const R g2 = ch_gradient(w, K, kn, mesh_p.t2, val_p.ls, J_t, pred_t, ln_ref);
+                    const R s2 = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g2));  // H dfk'
+                    const R lv = ln_t + K->alpha * s2;  // Model.py:626 (sign as in the reference)
+                    // mean = expReal(log_values) is inf above 11356 and underflows to 0 below the long-double
+                    // denormal limit (base/utilities.py:827-856): Model.py:630-633 then returns -inf, -inf
+                    const int bad = __any_sync(FULL, lane < kn && (lv > R(11356) || lv < R(-11399)));
+                    const R q_r = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_r - lv) : R(0));
+                    const R q_f = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_t - ln_r) : R(0));
+                    const R logdetL = warp_sum((lane < kn) ? rt<R>::log(w->A[pk(lane, lane)]) : R(0));
+                    if (bad) {
+                        proposal = (R)-INFINITY;
+                        proposal1 = (R)-INFINITY;
+                    } else {
+                        proposal = -(R)kn * K->half_log2pi + logdetL - R(0.5) * q_r;
+                        proposal1 = -(R)kn * K->half_log2pi + logdetL - R(0.5) * q_f;
+                    }
+                }
+                const R log_alpha = (t_prior - prior) + (tml.b - likelihood) + (proposal - proposal1);
+                const R u = rng_uniform<R>(rng);
+                accepted = rt<R>::exp(log_alpha) > u;
+                if (accepted && !SPEC) {  // a speculative evaluation only reports the outcome
+                    ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
+                    dwell = 0;
+                    misfit = tml.a;
+                    prior = t_prior;
+                    likelihood = tml.b;
+                    k = kn;
+                    err = err_t;
+                    ln_err = ln_t_err;
+                    mcur = mp;
+                    vcur = vp;
+                    pcur ^= 1;
+                    if (changed) {  // action none keeps the (stale) Jacobian, as the reference does
+                        ch_copy16(jg, w->J, JBYTES);
+                        j_valid = true;
+                    }
+                    if (lane == 0) w->ctr[CT_N_ACCEPT]++;
+                }
+            }
+        }
+    }
+}
+
+// ================================================================ speculative evaluation of future iterations
+// Chains are sequential and their lengths differ by 6x (the reference's reset rule), so every batch ends with a
+// tail in which most warps of an SM have no chain left; small batches never fill the machine at all.  An
+// accept_reject step that is REJECTED leaves the chain state untouched, and (sub-streams, gbp_math.cuh) the random
+// numbers of iteration t do not depend on iterations < t.  So while the owner warp executes iteration t0 for real,
+// idle warps of the CTA evaluate iterations t0+1, t0+2, ... on private copies of the chain state, assuming t0 ..
+// are rejected.  The owner then commits the leading run of rejections (bookkeeping only) and continues at the
+// first iteration that was not a plain rejection, which it executes itself.  Results are bitwise identical to the
+// sequential chain; chains that are stuck (the ones the reset rule makes 3-6x longer) advance W iterations per
+// iteration time.
+constexpr int SPEC_RES = 256;  // iterations one round can cover
+enum { MB_BUSY = 0, MB_IDLE = 1, MB_CLAIMED = 2, MB_GO = 16 };  // mailbox states of a warp (MB_GO + owner warp)
+
+template <typename R, typename T, int NS> struct SpecRound {
+    Hot<R, NS> hot;            // chain state before iteration t0
+    T alt;
+    R nahl;
+    T* jg;
+    const void* owner_ws;
+    volatile int t0, t_end, W;
+    volatile int first_stop;   // smallest iteration whose step was not a plain rejection (INT_MAX: none yet)
+    volatile int done;         // helpers finished
+    unsigned char midx[32];    // member index of warp x in this round
+    volatile unsigned char res[SPEC_RES];  // per iteration t0+1+i: 0x80 valid | 0x40 stop | nsens << 4 | nfwd << 2 | action
+};
+template <typename R, typename T, int NS> struct TailCtx {
+    SpecRound<R, T, NS>* rounds;   // [n_warps]
+    volatile int* mailbox;         // [n_warps]
+    volatile int* n_alive;         // warps that still own a chain
+    volatile int* n_idle;          // warps waiting in tail_service()
+    int n_warps, max_helpers, warp;
+};
+
+// Evaluate iterations first, first + stride, ... < t_end speculatively on w (a private copy of the chain state, or the
+// owner's own WarpState: only scratch buffers are written).
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void spec_member_run(WarpState<R, T, NC, KIND>* w, SpecRound<R, T, ns_of(KIND)>* rd, const Consts<R>* K,
+                                             const typename SysOf<T, KIND>::shared* S, const T* tab, const int member)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(rd);
+    GBP_SHARED(K);
+    const int lane = lane_id();
+    Hot<R, ns_of(KIND)> h = rd->hot;
+    h.j_valid = false;
+    const int t0 = rd->t0, t_end = rd->t_end, W = rd->W;
+    const T alt = rd->alt;
+    const R nahl = rd->nahl;
+    T* const jg = rd->jg;
+#pragma unroll 1
+    for (int t = t0 + 1 + member; t < t_end; t += W) {
+        const int fs = __shfl_sync(FULL, (int)rd->first_stop, 0);
+        if (t > fs) break;
+        if (lane == 0) {
+            w->ctr[CT_N_FWD] = 0;
+            w->ctr[CT_N_SENS] = 0;
+            w->ctr[CT_ACT0] = 0;
+            w->ctr[CT_ACT1] = 0;
+            w->ctr[CT_ACT2] = 0;
+        }
+        __syncwarp();
+        h.rng.iter = (uint32_t)t + 1u;
+        h.rng.block = 0u;
+        bool accepted = false, chol_failed = false;
+        ar_step<true, R, T, NC, KIND>(w, K, S, tab, alt, nahl, jg, h, accepted, chol_failed);
+        const int stop = (accepted || chol_failed) ? 1 : 0;
+        __syncwarp();
+        if (lane == 0) {
+            const int action = w->ctr[CT_ACT0] ? 0 : (w->ctr[CT_ACT1] ? 1 : (w->ctr[CT_ACT2] ? 2 : 3));
+            const int byte = 0x80 | (stop << 6) | ((w->ctr[CT_N_SENS] & 3) << 4) | ((w->ctr[CT_N_FWD] & 3) << 2) | action;
+            if (stop) atomicMin((int*)&rd->first_stop, t);
+            rd->res[t - t0 - 1] = (unsigned char)byte;
+        }
+        if (stop) break;
+    }
+    __threadfence_block();
+    __syncwarp();
+}
+
+// A warp without a chain: serve speculative rounds of the chains of this CTA until none is left.
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc, const Consts<R>* K,
+                                          const typename SysOf<T, KIND>::shared* S, const T* tab)
+{
+    const int lane = lane_id();
+    if (lane == 0) {
+        tc.mailbox[tc.warp] = MB_IDLE;
+        __threadfence_block();
+        atomicAdd((int*)tc.n_idle, 1);
+    }
+#pragma unroll 1
+    for (;;) {
+        int cmd = 0;
+        if (lane == 0) {
+#pragma unroll 1
+            for (;;) {
+                cmd = tc.mailbox[tc.warp];
+                if (cmd >= MB_GO) break;
+                if (cmd == MB_IDLE && *tc.n_alive <= 0) {
+                    // nobody left to help; leave unless an owner claimed this warp in the meantime
+                    if (atomicCAS((int*)&tc.mailbox[tc.warp], MB_IDLE, MB_BUSY) == MB_IDLE) {
+                        cmd = -1;
+                        break;
+                    }
+                    continue;
+                }
+                __nanosleep(400);
+            }
+        }
+        cmd = __shfl_sync(FULL, cmd, 0);
+        if (cmd < 0) break;
+        SpecRound<R, T, ns_of(KIND)>* rd = tc.rounds + (cmd - MB_GO);
+        __threadfence_block();
+        ch_copy16(w, rd->owner_ws, (int)sizeof(WarpState<R, T, NC, KIND>));
+        const int member = (int)rd->midx[tc.warp] - 1;
+        spec_member_run<R, T, NC, KIND>(w, rd, K, S, tab, member);
+        if (lane == 0) {
+            atomicAdd((int*)&rd->done, 1);
+            __threadfence_block();
+            tc.mailbox[tc.warp] = MB_IDLE;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) atomicSub((int*)tc.n_idle, 1);
+}
+
+// Owner, before its real step of iteration `total`: claim idle warps and start a round covering iterations
+// total+1 .. total+len.  Returns the number of helpers (0: no round).
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc,
+                                             const Hot<R, ns_of(KIND)> h, T alt, R nahl, T* jg, int total, int mult)
+{
+    const int lane = lane_id();
+    SpecRound<R, T, ns_of(KIND)>* rd = tc.rounds + tc.warp;
+    GBP_SHARED(rd);
+    int nh = 0;
+    if (lane == 0) {
+#pragma unroll 1
+        for (int x = 0; x < tc.n_warps && nh < tc.max_helpers; ++x)
+            if (tc.mailbox[x] == MB_IDLE && atomicCAS((int*)&tc.mailbox[x], MB_IDLE, MB_CLAIMED) == MB_IDLE) rd->midx[x] = (unsigned char)(++nh);
+    }
+    nh = __shfl_sync(FULL, nh, 0);
+    if (nh == 0) return 0;
+    const int W = nh;  // the owner executes iteration `total` for real meanwhile, then waits
+    int len = W * mult;
+    if (len > SPEC_RES) len = SPEC_RES;
+#pragma unroll 1
+    for (int i = lane; i < len; i += 32) rd->res[i] = 0;
+    if (lane == 0) {
+        rd->hot = h;
+        rd->alt = alt;
+        rd->nahl = nahl;
+        rd->jg = jg;
+        rd->owner_ws = w;
+        rd->t0 = total;
+        rd->t_end = total + 1 + len;
+        rd->W = W;
+        rd->first_stop = 0x7fffffff;
+        rd->done = 0;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll 1
+        for (int x = 0; x < tc.n_warps; ++x)
+            if (tc.mailbox[x] == MB_CLAIMED && rd->midx[x] != 0) tc.mailbox[x] = MB_GO + tc.warp;
+    }
+    __syncwarp();
+    return nh;
+}
+
+// Owner, after its real step: wait for the helpers and return how many leading iterations after `total` are plain
+// rejections (their results are in rd->res).
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ int spec_round_end(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc, const Consts<R>* K,
+                                           const typename SysOf<T, KIND>::shared* S, const T* tab, int nh, bool own_step_changed_state)
+{
+    const int lane = lane_id();
+    SpecRound<R, T, ns_of(KIND)>* rd = tc.rounds + tc.warp;
+    GBP_SHARED(rd);
+    if (own_step_changed_state && lane == 0)
+        atomicMin((int*)&rd->first_stop, rd->t0);  // everything speculated is void: helpers stop early
+    if (lane == 0) {
+#pragma unroll 1
+        while (rd->done < nh) __nanosleep(100);
+        for (int x = 0; x < tc.n_warps; ++x) rd->midx[x] = 0;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (own_step_changed_state) return 0;
+    const int fs = rd->first_stop, t0 = rd->t0, te = rd->t_end;
+    int n = ((fs < te) ? fs : te) - t0 - 1;
+    if (n < 0) n = 0;
+    // every committed slot must hold a valid plain rejection (defensive: stop at the first that does not)
+    int bad = n;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32)
+        if ((rd->res[i] & 0xC0) != 0x80) bad = min(bad, i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad = min(bad, __shfl_xor_sync(FULL, bad, o));
+    return bad;
+}
+
 // ================================================================ the chain (inlined into the kernel)
 template <typename R, typename T, int NC, int KIND>
 __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Consts<R>* K,
                                           const typename SysOf<T, KIND>::shared* S, const typename SysOf<T, KIND>::dev& Sdev,
-                                          const T* tab, const ChainParams& P, const int chain)
+                                          const T* tab, const ChainParams& P, const int chain,
+                                          const TailCtx<R, T, ns_of(KIND)>& tc)
 {
     constexpr int NS = ns_of(KIND);
     typedef Errs<R, NS> errs_t;
@@ -779,7 +1259,8 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
 #define N2 (2 * (long long)N)
 
     // ---- hot state (registers)
-    Rng rng;
+    Hot<R, NS> h;
+    Rng& rng = h.rng;
     rng.seed_lo = (uint32_t)P.seed;
     rng.seed_hi = (uint32_t)(P.seed >> 32);
     {
@@ -788,16 +1269,21 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         rng.snd_hi = (uint32_t)(snd >> 32);
     }
     rng.block = 0u;
+    rng.iter = 0u;
     const T alt = (T)P.altitude[chain];
-    int k = 1, mcur = 0, vcur = 0, pcur = 0;
-    bool j_valid = true;  // the shared-memory Jacobian is the current model's
+    int &k = h.k, &mcur = h.mcur, &vcur = h.vcur, &pcur = h.pcur, &dwell = h.dwell;
+    bool& j_valid = h.j_valid;
+    errs_t &ln_err = h.ln_err, &err = h.err;
+    R &ln_ref = h.ln_ref, &sig_lo = h.sig_lo, &misfit = h.misfit, &prior = h.prior, &likelihood = h.likelihood;
+    k = 1;
+    mcur = vcur = pcur = 0;
+    j_valid = true;
+    ln_ref = sig_lo = misfit = prior = likelihood = R(0);
+    dwell = 0;
     T* const jg = (T*)P.jstore + (size_t)chain * NC * KS;
     constexpr int JBYTES = NC * KS * (int)sizeof(T);
-    errs_t ln_err, err;  // ln(relative / additive error) and the errors themselves, per system
-    R ln_ref = R(0), sig_lo = R(0);
     double sigma_ref = 0.0;
-    R misfit = R(0), prior = R(0), likelihood = R(0);
-    int iteration = 0, burned_in = 0, dwell = 0;
+    int iteration = 0, burned_in = 0;
 
     // ---- per-chain setup
     int act = 0;
@@ -862,249 +1348,42 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
     bool failed = (n_active == 0);
     bool go = !failed;
     int total = 0;
+    int spec_left = 0, spec_pos = 0, spec_mult = 1, rej_run = 0;
 #pragma unroll 1
     while (go) {
         // ==================================================== Inference1D.accept_reject :537-631
         bool accepted = false;
         bool chol_failed = false;
-        {
-            // ---- RectilinearMesh1D.perturb :993-1120 (warp-uniform).  Proposed mesh -> mesh[mcur^1],
-            //      remapped values -> val[vcur^1].sig and ls_r; for ACT_NONE only ls_r is filled.
-            const MeshBuf<R>& m0 = w->mesh[mcur];
-            const ValBuf<R>& v0 = w->val[vcur];
-            MeshBuf<R>& m1 = w->mesh[mcur ^ 1];
-            ValBuf<R>& v1 = w->val[vcur ^ 1];
-            int action, kn;
-#pragma unroll 1
-            for (;;) {
-                int event;
-#pragma unroll 1
-                for (;;) {  // Categorical.rng: searchsorted(cumsum(p), U), re-drawn while illegal (:1041-1049)
-                    const R u = rng_uniform<R>(rng);
-                    event = (u <= K->cum0) ? 0 : (u <= K->cum1) ? 1 : (u <= K->cum2) ? 2 : 3;
-                    if (k == 1 && (event == 1 || event == 2)) continue;
-                    if (k == ml && event == 0) continue;
-                    break;
-                }
-                action = event;
-                kn = k;
-                if (event == ACT_NONE) {
-                    if (lane < k) w->ls_r[lane] = v0.ls[lane];
-                    break;
-                }
-                if (event == ACT_BIRTH) {  // :1061-1081
-                    bool ok = false;
-                    int pos = 0;
-                    R e = R(0);
-#pragma unroll 1
-                    for (int tries = 1; tries <= 10; ++tries) {
-                        e = rt<R>::exp(K->ln_min_edge + K->ln_edge_span * rng_uniform<R>(rng));
-                        pos = __popc(__ballot_sync(FULL, lane <= k && m0.edges[lane] < e));  // searchsorted (left)
-                        R d = INFINITY;  // widths after insertion: cell pos-1 is split in two
-                        if (lane < k)
-                            d = (lane == pos - 1) ? fmin(e - m0.edges[lane], m0.edges[lane + 1] - e)
-                                                  : m0.edges[lane + 1] - m0.edges[lane];
-                        const R h = warp_min(d);
-                        if (tries == 10) break;  // the 10th try always restarts (:1078-1080)
-                        if (h > K->min_width) {
-                            ok = true;
-                            break;
-                        }
-                    }
-                    if (!ok) continue;
-                    if (lane <= k + 1) m1.edges[lane] = (lane < pos) ? m0.edges[lane] : (lane == pos ? e : m0.edges[lane - 1]);
-                    if (lane <= k) {  // values.insert(pos, values[pos-1]) (:835)
-                        const int src = (lane < pos) ? lane : lane - 1;
-                        v1.sig[lane] = v0.sig[src];
-                        w->ls_r[lane] = v0.ls[src];
-                    }
-                    kn = k + 1;
-                    break;
-                }
-                if (event == ACT_DEATH) {  // :1083-1087, delete_edge :643-689
-                    const int i = (int)(rng_uniform<R>(rng) * (R)(k - 1)) + 1;
-                    if (lane <= k - 1) m1.edges[lane] = m0.edges[lane + (lane >= i ? 1 : 0)];
-                    if (lane < k - 1) {
-                        const int src = lane + (lane >= i ? 1 : 0);
-                        R s = v0.sig[src], l = v0.ls[src];
-                        if (lane == i - 1) {
-                            s = R(0.5) * (v0.sig[i - 1] + v0.sig[i]);
-                            l = rt<R>::log(s);
-                        }
-                        v1.sig[lane] = s;
-                        w->ls_r[lane] = l;
-                    }
-                    kn = k - 1;
-                    break;
-                }
-                {  // ACT_MOVE :1088-1118
-                    bool ok = false;
-                    int i = 1;
-                    R dz = R(0);
-#pragma unroll 1
-                    for (int tries = 1; tries <= 10; ++tries) {
-                        i = (int)(R(1) + ((R)k - R(1)) * rng_uniform<R>(rng));
-                        const R zn = rng_normal<R>(rng);
-                        const R sgn = (zn > R(0)) ? R(1) : (zn < R(0) ? R(-1) : R(0));
-                        dz = sgn * K->min_width * rng_uniform<R>(rng);
-                        R d = INFINITY;
-                        if (lane < k)
-                            d = (m0.edges[lane + 1] + (lane + 1 == i ? dz : R(0))) - (m0.edges[lane] + (lane == i ? dz : R(0)));
-                        const R h = warp_min(d);
-                        const R z1 = m0.edges[1] + (i == 1 ? dz : R(0));
-                        const R zl = m0.edges[k - 1] + (i == k - 1 ? dz : R(0));
-                        if (tries == 10) break;
-                        if (h > K->min_width && z1 > K->min_edge && zl < K->max_edge) {
-                            ok = true;
-                            break;
-                        }
-                    }
-                    if (!ok) continue;
-                    if (lane <= k) m1.edges[lane] = m0.edges[lane] + (lane == i ? dz : R(0));
-                    if (lane < k) {
-                        v1.sig[lane] = v0.sig[lane];
-                        w->ls_r[lane] = v0.ls[lane];
-                    }
-                    break;
-                }
+        if (spec_left > 0) {
+            // this iteration was evaluated speculatively and is a plain rejection: only its bookkeeping remains
+            const int byte = tc.rounds[tc.warp].res[spec_pos];
+            spec_pos++;
+            spec_left--;
+            if (lane == 0) {
+                w->ctr[CT_ACT0 + (byte & 3)]++;
+                w->ctr[CT_N_FWD] += (byte >> 2) & 3;
+                w->ctr[CT_N_SENS] += (byte >> 4) & 3;
             }
             __syncwarp();
-            if (lane == 0) w->ctr[CT_ACT0 + action]++;
-
-            // ---- Model.stochastic_newton_perturbation :368-419
-            const bool changed = action != ACT_NONE;
-            const int mp = changed ? (mcur ^ 1) : mcur;  // proposed mesh buffer
-            const int vp = vcur ^ 1;                     // proposed values buffer
-            MeshBuf<R>& mesh_p = w->mesh[mp];
-            ValBuf<R>& val_p = w->val[vp];
-            const T* ph = w->pred[pcur];
-            T* pred_t = w->pred[pcur ^ 1];
-            T* const Jh = w->J;
-            T* const J_t = w->J;
-            if (changed) {  // observation.fm_dlogc(remapped_model): J and predicted data of the test datapoint
-                ch_mesh_setup(K, kn, &mesh_p);
-                ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, J_t);
-                j_valid = false;
-                // REFERENCE QUIRK (kept, it shapes the proposal): FdemDataPoint.fm_dlogc stores the remapped model's
-                // predicted data (FdemDataPoint.py:535-545); TdemDataPoint.fm_dlogc stores only the Jacobian, its
-                // predicted-data update is commented out (TdemDataPoint.py:1031-1055), so a time-domain death / move
-                // forms the Newton gradient with the CURRENT model's predicted data.
-                if constexpr (KIND == KIND_FDEM) ph = pred_t;
-            } else if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
-                ch_copy16(w->J, jg, JBYTES);
-                j_valid = true;
-            }
-            ch_set_ivar(w, K, C, err);
-            const R ln_r = (lane < kn) ? w->ls_r[lane] : R(0);
-            const R g = ch_gradient(w, K, kn, mesh_p.t2, w->ls_r, Jh, ph, ln_ref);
-            ch_assemble(w, K, kn, mesh_p.t2, Jh);
-            if (!ch_cholesky(w->A, kn)) {
-                chol_failed = true;
-            } else {
-                const R stepv = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g));  // H * dfk
-                const R mean = ln_r - K->alpha * stepv;  // ln sigma + alpha * pk, pk = -H dfk
-                // sigma' ~ exp(N(mean, H)),  H = (L L')^-1  ->  mean + L^-T z
-                pair_t<R> zz = {R(0), R(0)};
-                const int npair = (kn + 1) / 2;
-                if (lane < npair) zz = normal2_at<R>(rng.block + (uint32_t)lane, rng.snd_lo, rng.snd_hi, rng.seed_lo, rng.seed_hi);
-                rng.block += (uint32_t)npair;
-                const R za = __shfl_sync(FULL, zz.a, lane >> 1), zb = __shfl_sync(FULL, zz.b, lane >> 1);
-                const R zi = (lane < kn) ? ((lane & 1) ? zb : za) : R(0);
-                const R ln_t = mean + ch_solve_LT(w->A, kn, zi);
-                if (lane < kn) {
-                    val_p.ls[lane] = ln_t;
-                    val_p.sig[lane] = rt<R>::exp(ln_t);
-                }
-                __syncwarp();
-
-                // ---- test_datapoint.perturb() (DataPoint.py:531-573)
-                errs_t ln_t_err = ln_err, err_t = err;
-                if (NS == 1 || K->n_sys == 1) {
-                    if (K->solve_rel) {
-                        const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_err.rel[0], K->rel_sd[0], K->rel_lnmin[0], K->rel_lnmax[0]);
-                        ln_t_err.rel[0] = pr.x;
-                        rng.block = pr.block;
-                    }
-                    if (K->solve_add) {
-                        const prop_t<R> pr = ch_propose_ln_error<R>(rng, ln_err.add[0], K->add_sd[0], K->add_lnmin[0], K->add_lnmax[0]);
-                        ln_t_err.add[0] = pr.x;
-                        rng.block = pr.block;
-                    }
-                } else {
-                    if (K->solve_rel) {
-                        const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.rel[0], ln_err.rel[NS - 1], K->rel_sd, K->rel_lnmin, K->rel_lnmax);
-                        ln_t_err.rel[0] = pr.x0;
-                        ln_t_err.rel[NS - 1] = pr.x1;
-                        rng.block = pr.block;
-                    }
-                    if (K->solve_add) {
-                        const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.add[0], ln_err.add[NS - 1], K->add_sd, K->add_lnmin, K->add_lnmax);
-                        ln_t_err.add[0] = pr.x0;
-                        ln_t_err.add[NS - 1] = pr.x1;
-                        rng.block = pr.block;
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    err_t.rel[s] = (ln_t_err.rel[s] == ln_err.rel[s]) ? err.rel[s] : rt<R>::exp(ln_t_err.rel[s]);
-                    err_t.add[s] = (ln_t_err.add[s] == ln_err.add[s]) ? err.add[s] : rt<R>::exp(ln_t_err.add[s]);
-                }
-
-                const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
-                // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
-                // (Model.proposal_probabilities :619) - fused into the same pass.
-                ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : (T*)nullptr);
-                ch_set_ivar(w, K, C, err_t);
-                const pair_t<R> tml = ch_misfit_like(w, C, nahl, pred_t);
-                // error priors: the proposals above are forced inside their bounds (or fall back to the
-                // current values), so DataPoint.probability is the constant err_lp
-                R t_prior = K->err_lp;
-                t_prior += ch_model_prob(K, kn, val_p.ls, mesh_p.lnh, ln_ref);
-                if (t_prior != (R)-INFINITY) {  // early reject on -inf prior (:581, :589): no accept draw
-                    R proposal = R(1), proposal1 = R(1);
-                    if (jump) {
-                        const R g2 = ch_gradient(w, K, kn, mesh_p.t2, val_p.ls, J_t, pred_t, ln_ref);
-                        const R s2 = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g2));  // H dfk'
-                        const R lv = ln_t + K->alpha * s2;  // Model.py:626 (sign as in the reference)
-                        // mean = expReal(log_values) is inf above 11356 and underflows to 0 below the long-double
-                        // denormal limit (base/utilities.py:827-856): Model.py:630-633 then returns -inf, -inf
-                        const int bad = __any_sync(FULL, lane < kn && (lv > R(11356) || lv < R(-11399)));
-                        const R q_r = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_r - lv) : R(0));
-                        const R q_f = ch_quad(w->A, w->vec, kn, (lane < kn) ? (ln_t - ln_r) : R(0));
-                        const R logdetL = warp_sum((lane < kn) ? rt<R>::log(w->A[pk(lane, lane)]) : R(0));
-                        if (bad) {
-                            proposal = (R)-INFINITY;
-                            proposal1 = (R)-INFINITY;
-                        } else {
-                            proposal = -(R)kn * K->half_log2pi + logdetL - R(0.5) * q_r;
-                            proposal1 = -(R)kn * K->half_log2pi + logdetL - R(0.5) * q_f;
-                        }
-                    }
-                    const R log_alpha = (t_prior - prior) + (tml.b - likelihood) + (proposal - proposal1);
-                    const R u = rng_uniform<R>(rng);
-                    accepted = rt<R>::exp(log_alpha) > u;
-                    if (accepted) {
-                        ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
-                        dwell = 0;
-                        misfit = tml.a;
-                        prior = t_prior;
-                        likelihood = tml.b;
-                        k = kn;
-                        err = err_t;
-                        ln_err = ln_t_err;
-                        mcur = mp;
-                        vcur = vp;
-                        pcur ^= 1;
-                        if (changed) {  // action none keeps the (stale) Jacobian, as the reference does
-                            ch_copy16(jg, w->J, JBYTES);
-                            j_valid = true;
-                        }
-                        if (lane == 0) w->ctr[CT_N_ACCEPT]++;
-                    }
-                }
+        } else {
+            int nh = 0;
+            // only a chain that keeps rejecting speculates: its rounds are long, so the hand-off is amortised, and
+            // those are the chains that make the tail (a chain with a healthy acceptance rate gains little)
+            if (tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && *tc.n_idle > 0)
+                nh = spec_round_begin<R, T, NC, KIND>(w, tc, h, alt, nahl, jg, total, spec_mult);
+            rng.iter = (uint32_t)total + 1u;  // sub-stream of this accept_reject step
+            rng.block = 0u;
+            ar_step<false, R, T, NC, KIND>(w, K, S, tab, alt, nahl, jg, h, accepted, chol_failed);
+            if (nh > 0) {
+                spec_left = spec_round_end<R, T, NC, KIND>(w, tc, K, S, tab, nh, accepted || chol_failed);
+                spec_pos = 0;
+                // rounds grow while nothing but rejections comes back (a stuck chain), and start small again otherwise
+                const int covered = tc.rounds[tc.warp].t_end - tc.rounds[tc.warp].t0 - 1;
+                spec_mult = (!accepted && spec_left == covered) ? min(spec_mult * 2, 32) : 1;
             }
         }
         failed = chol_failed;
+        rej_run = accepted ? 0 : rej_run + 1;
 
         // ==================================================== Inference1D.update :705-790
         bool do_reset = false;
@@ -1163,6 +1442,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             __syncwarp();
             if (lane == 0) w->ctr[CT_N_RESETS] = nr;
             initialize(false);
+            spec_left = 0;  // speculated iterations assumed the old state
             dwell = 1;  // update() goes on to accumulate the re-initialised model
         }
         const int burn_iter = w->ctr[CT_BURN_ITER];
@@ -1180,6 +1460,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
                     w->ctr[CT_N_RESETS] = 1;
                 }
                 initialize(false);
+            spec_left = 0;  // speculated iterations assumed the old state
             } else {
                 go = false;
                 failed = true;
@@ -1248,6 +1529,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     __shared__ uint64_t bar;
     __shared__ Consts<R> consts;
     __shared__ typename SysOf<T, KIND>::shared sys_s;
+    __shared__ SpecRound<R, T, ns_of(KIND)> rounds[WARPS];
+    __shared__ int mailbox[WARPS];
+    __shared__ int n_alive, n_idle;
     T* tab = reinterpret_cast<T*>(smem);
     uint32_t tab_bytes;
     if constexpr (KIND == KIND_TDEM) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
@@ -1273,12 +1557,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     // than the machine still spreads evenly; later chains are claimed from a device-side counter
     int c = warp * gridDim.x + blockIdx.x;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        n_alive = 0;
+        n_idle = 0;
+    }
+    if (lane == 0) {
+        mailbox[warp] = MB_BUSY;
+        for (int x = 0; x < 32; ++x) rounds[warp].midx[x] = 0;
+    }
+    __syncthreads();
+    if (lane == 0 && c < P.B) atomicAdd(&n_alive, 1);
+    __syncthreads();
+    TailCtx<R, T, ns_of(KIND)> tc;
+    tc.rounds = rounds;
+    tc.mailbox = mailbox;
+    tc.n_alive = &n_alive;
+    tc.n_idle = &n_idle;
+    tc.n_warps = WARPS;
+    tc.max_helpers = P.spec_helpers;
+    tc.warp = warp;
+    const bool had_chain = c < P.B;
 #pragma unroll 1
     while (c < P.B) {
-        run_chain<R, T, NC, KIND>(ws, &consts, &sys_s, S, tab, P, c);
+        run_chain<R, T, NC, KIND>(ws, &consts, &sys_s, S, tab, P, c, tc);
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(P.work_counter, 1);
         c = __shfl_sync(FULL, nxt, 0);
+    }
+    if (P.spec_helpers > 0) {
+        // out of chains: evaluate future iterations of the chains of this CTA that are still running
+        if (lane == 0 && had_chain) atomicSub(&n_alive, 1);
+        __syncwarp();
+        tail_service<R, T, NC, KIND>(ws, tc, &consts, &sys_s, tab);
     }
 }
 

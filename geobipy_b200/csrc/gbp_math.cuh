@@ -107,14 +107,15 @@ __device__ __forceinline__ int warp_sum_i(int v)
 
 // ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
 // Everything by value so that the generator state stays in registers: key = 64-bit seed,
-// counter = (block, 0, sounding lo, sounding hi).  A chain draws far fewer than 2^32 blocks.
+// counter = (block, iteration, sounding lo, sounding hi): every accept_reject step of a chain has its own sub-stream
+// starting at block 0, so an iteration's numbers do not depend on how many the previous iterations consumed
+// (future iterations of a chain can be evaluated speculatively by other warps).
 struct Rng {
     uint32_t seed_lo, seed_hi, snd_lo, snd_hi;
-    uint32_t block;
+    uint32_t block, iter;
 };
-__device__ __noinline__ uint4 philox4(uint32_t c0, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+__device__ __noinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
-    uint32_t c1 = 0u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -141,7 +142,7 @@ template <> __device__ __forceinline__ void uniforms_of<float>(uint4 x, float* u
 template <typename R> __device__ __forceinline__ R rng_uniform(Rng& g)
 {
     R a, b;
-    uniforms_of<R>(philox4(g.block, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi), &a, &b);
+    uniforms_of<R>(philox4(g.block, g.iter, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi), &a, &b);
     g.block++;
     return a;
 }
@@ -149,10 +150,10 @@ template <typename R> __device__ __forceinline__ R rng_uniform(Rng& g)
 template <typename R> struct pair_t {
     R a, b;
 };
-template <typename R> __device__ __noinline__ pair_t<R> normal2_at(uint32_t block, uint32_t snd_lo, uint32_t snd_hi, uint32_t k0, uint32_t k1)
+template <typename R> __device__ __noinline__ pair_t<R> normal2_at(uint32_t block, uint32_t iter, uint32_t snd_lo, uint32_t snd_hi, uint32_t k0, uint32_t k1)
 {
     R a, b;
-    uniforms_of<R>(philox4(block, snd_lo, snd_hi, k0, k1), &a, &b);
+    uniforms_of<R>(philox4(block, iter, snd_lo, snd_hi, k0, k1), &a, &b);
     const R r = rt<R>::sqrt(R(-2) * rt<R>::log(R(1) - a));
     R s, c;
     rt<R>::sincos(R(6.283185307179586476925286766559) * b, &s, &c);
@@ -160,7 +161,7 @@ template <typename R> __device__ __noinline__ pair_t<R> normal2_at(uint32_t bloc
 }
 template <typename R> __device__ __forceinline__ R rng_normal(Rng& g)
 {
-    const pair_t<R> z = normal2_at<R>(g.block, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
+    const pair_t<R> z = normal2_at<R>(g.block, g.iter, g.snd_lo, g.snd_hi, g.seed_lo, g.seed_hi);
     g.block++;
     return z.a;
 }

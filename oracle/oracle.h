@@ -133,7 +133,7 @@ int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *opt, gbo_
 int gbo_eval_transition_tdem(const gbo_tdem_system *sys, const gbo_options *opt, gbo_transition *t);
 
 /* Full chain for one sounding.  Random stream: Philox4x32-10, key = (seed lo, seed hi),
- * counter = (block lo, block hi, sounding lo, sounding hi). */
+ * counter = (block, iteration, sounding lo, sounding hi): one sub-stream per accept_reject() call. */
 int gbo_run_chain(const gbo_fdem_system *sys, const gbo_options *opt, const double *data, double altitude,
                   uint64_t seed, uint64_t sounding_index, int64_t max_iterations, gbo_chain_out *out);
 /* Same sampler for a time-domain (dual moment) datapoint: data [C] = windows of system 0 then system 1. */

@@ -65,14 +65,19 @@ void gbo_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint3
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Random stream of one chain: Philox4x32-10, key = seed, counter = (block, iteration, sounding lo, sounding hi).
+ * Every accept_reject() call (iteration = 1, 2, ... counted over resets) starts its own sub-stream at block 0, so
+ * that the numbers an iteration draws do not depend on how many the previous ones consumed (the CUDA sampler
+ * evaluates future iterations of a chain speculatively on idle warps). */
 typedef struct {
-    uint64_t seed, sounding, block;
+    uint64_t seed, sounding;
+    uint32_t block, iteration;
 } rng_t;
 
 /* One Philox block -> two 53-bit uniforms in [0,1). */
 static void rng_block(rng_t *g, double *ua, double *ub)
 {
-    uint32_t ctr[4] = {(uint32_t)g->block, (uint32_t)(g->block >> 32), (uint32_t)g->sounding, (uint32_t)(g->sounding >> 32)};
+    uint32_t ctr[4] = {g->block, g->iteration, (uint32_t)g->sounding, (uint32_t)(g->sounding >> 32)};
     uint32_t key[2] = {(uint32_t)g->seed, (uint32_t)(g->seed >> 32)};
     uint32_t x[4];
     gbo_philox4x32_10(ctr, key, x);
@@ -715,6 +720,8 @@ static int chain_step(chain_t *c)
     double var[GBO_MAXC], A[GBO_MAXL * GBO_MAXL], grad[GBO_MAXL], y[GBO_MAXL], step[GBO_MAXL], z[GBO_MAXL + 1];
 
     c->accepted = 0;
+    c->rng.iteration++;
+    c->rng.block = 0;
     int action = perturb_structure(o, &c->rng, &c->model, &remap);
     c->n_act[action]++;
     const int k = remap.k;
@@ -868,6 +875,7 @@ static int run_chain_impl(const survey_t *sv, const gbo_options *opt, const doub
     c->rng.seed = seed;
     c->rng.sounding = sounding_index;
     c->rng.block = 0;
+    c->rng.iteration = 0;
     c->n_active = 0;
     for (int i = 0; i < c->C; ++i) c->n_active += is_active(data[i]);
     chain_init(c, out);
