@@ -299,6 +299,7 @@ def run_b200_arm(args):
     iters = iters_dev.clone().reshape(1)
     last_kernel_ms = ops.last_kernel_ms()
     last_iters = float(res["scalars"][:, _lib.S_TOTAL_ITER].sum().item())
+    n_spec = float(res["scalars"][:, _lib.S_N_SPECULATED].sum().item())
     n_fwd = float(res["scalars"][:, _lib.S_N_FORWARD].sum().item())
     n_sens = float(res["scalars"][:, _lib.S_N_SENS].sum().item())
     mean_k = float((res["ncells_hist"].sum(dim=0).double() * torch.arange(opt.max_layers + 1, device=dev)).sum().item()
@@ -400,6 +401,9 @@ def run_b200_arm(args):
                                  "peak": fp32_peak, "peak_source": "measured on this device: 8 independent FFMA chains per thread (gbp_measure_peaks); nominal 148 SM x 128 FMA/clk x 1965 MHz = 74.4",
                                  "mufu_achieved_gops": mufu / (last_kernel_ms * 1e-3) / 1e9, "mufu_peak_gops": mufu_peak,
                                  "mufu_frac": mufu / (last_kernel_ms * 1e-3) / 1e9 / mufu_peak},
+            "speculation": {"helpers_per_chain_max": int(os.environ.get("GBP_SPEC_HELPERS", "12")),
+                            "iterations_committed_from_speculation": n_spec / last_iters,
+                            "note": "idle warps evaluate future iterations of running chains; results bit-identical with it off (tests)"},
             "chain_stats": {"iterations_per_chain": last_iters / B, "mean_layers": mean_k, "forwards_per_iteration": n_fwd / last_iters,
                             "jacobians_per_iteration": n_sens / last_iters, "burned_in_fraction": burned / B},
         }

@@ -38,7 +38,7 @@ constexpr int NPACK = GBP_MAXL * (GBP_MAXL + 1) / 2;
 enum { ACT_BIRTH = 0, ACT_DEATH = 1, ACT_MOVE = 2, ACT_NONE = 3 };
 // cold per-chain integers kept in shared memory
 enum { CT_N_ACCEPT = 0, CT_N_FWD, CT_N_SENS, CT_ACT0, CT_ACT1, CT_ACT2, CT_ACT3, CT_BEST_K, CT_BEST_ITER, CT_BURN_ITER,
-       CT_N_ZERO, CT_N_RESETS, CT_LIMITERS, CT_ACC_WIN, CT_TO_PLOT, CT_N = 16 };
+       CT_N_ZERO, CT_N_RESETS, CT_LIMITERS, CT_ACC_WIN, CT_TO_PLOT, CT_N_SPEC, CT_N = 16 };
 enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_REL2, BV_ADD2, BV_N = 8 };
 
 // KIND of datapoint a kernel instantiation inverts: frequency domain (FdemDataPoint, one system) or time
@@ -1363,6 +1363,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
                 w->ctr[CT_ACT0 + (byte & 3)]++;
                 w->ctr[CT_N_FWD] += (byte >> 2) & 3;
                 w->ctr[CT_N_SENS] += (byte >> 4) & 3;
+                w->ctr[CT_N_SPEC]++;
             }
             __syncwarp();
         } else {
@@ -1510,6 +1511,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_N_MOVE] = (double)w->ctr[CT_ACT2];
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
         s[GBP_S_TOTAL_ITER] = (double)total;
+        s[GBP_S_N_SPECULATED] = (double)w->ctr[CT_N_SPEC];
     }
     __syncwarp();
 #undef N2

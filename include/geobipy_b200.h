@@ -116,6 +116,8 @@ enum {
     GBP_S_BEST_REL, GBP_S_BEST_ADD, GBP_S_N_RESETS, GBP_S_N_BIRTH, GBP_S_N_DEATH, GBP_S_N_MOVE, GBP_S_N_NONE,
     GBP_S_TOTAL_ITER,   /* accept_reject+update pairs executed, including those before a reset() */
     GBP_S_CUR_REL2, GBP_S_CUR_ADD2, GBP_S_BEST_REL2, GBP_S_BEST_ADD2,  /* system 1 of a dual-moment datapoint */
+    GBP_S_N_SPECULATED, /* iterations whose rejection was established speculatively by another warp (diagnostic; the
+                           only scalar that depends on scheduling) */
     GBP_NSCALARS = 32
 };
 

@@ -322,3 +322,42 @@ def test_full_size_properties(gpu, systems):
     torch.cuda.synchronize()
     assert torch.equal(res["hitmap"], res2["hitmap"])
     assert nd == 440
+
+
+@pytest.mark.parametrize("kind", ["fdem", "tdem"])
+def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, monkeypatch):
+    """Idle warps evaluate future iterations of running chains speculatively (gbp_chain.cuh, "speculative evaluation").
+    Per-iteration random sub-streams make that exact: every output of a batch that leaves most warps idle (so that
+    speculation is active from the start) is bit-identical with speculation switched off - except the diagnostic
+    count of speculated iterations."""
+    from geobipy_b200 import _lib
+    if kind == "fdem":
+        system, opt = systems[0], gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500)
+        data, alt = _observed(oracle, systems[1], 40)
+    else:
+        from geobipy_b200.synthetic import synthetic_batch, skytem_noise_std
+        system, opt = gpu.skytem_survey_struct(), gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500, **gpu.SKYTEM_OPTIONS)
+        tsys = oracle.make_tdem_system()
+        b = synthetic_batch(0, 40, max_depth=400.0, n_channels=45)
+        data = np.zeros((40, 45))
+        for i in range(40):
+            L = int(b["nlayers"][i])
+            clean = oracle.tdem_forward(tsys, b["height"][i], b["sigma"][i, :L], b["thickness"][i, :L])
+            data[i] = clean + b["noise"][i] * skytem_noise_std(clean, np.array(tsys.t_centre[:45]), (26, 19))
+        alt = b["height"]
+    out = {}
+    for helpers, minrej in (("0", "24"), ("12", "4"), ("27", "0")):
+        monkeypatch.setenv("GBP_SPEC_HELPERS", helpers)
+        monkeypatch.setenv("GBP_SPEC_MIN_REJECTIONS", minrej)
+        out[helpers] = gpu.rjmcmc_run(system, opt, data, alt, seed=99, precision=32)
+    ref = out["0"]
+    assert not ref["scalars"][:, _lib.S_N_SPECULATED].any()
+    for helpers in ("12", "27"):
+        r = out[helpers]
+        assert r["scalars"][:, _lib.S_N_SPECULATED].sum() > 0.05 * r["scalars"][:, _lib.S_TOTAL_ITER].sum()
+        for name in ref:
+            a, b_ = ref[name], r[name]
+            if name == "scalars":
+                a, b_ = a.copy(), b_.copy()
+                a[:, _lib.S_N_SPECULATED] = b_[:, _lib.S_N_SPECULATED] = 0
+            assert np.array_equal(a, b_, equal_nan=True), (kind, helpers, name)
