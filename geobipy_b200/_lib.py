@@ -21,7 +21,7 @@ PRECISION_F32, PRECISION_F64 = 32, 64
 (S_ITER, S_BURNED_IN, S_BURNED_IN_ITER, S_BEST_ITER, S_BEST_K, S_CUR_K, S_HALFSPACE, S_FAILED, S_N_ACCEPT,
  S_N_FORWARD, S_N_SENS, S_BEST_POSTERIOR, S_CUR_REL, S_CUR_ADD, S_CUR_MISFIT, S_CUR_PRIOR, S_CUR_LIKELIHOOD,
  S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER,
- S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2, S_N_SPECULATED) = range(30)
+ S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2, S_N_SPECULATED, S_SPEC_ROUNDS, S_SPEC_CYCLES) = range(32)
 
 
 class FdemSystemC(ctypes.Structure):
@@ -85,7 +85,7 @@ class ChainBuffersC(ctypes.Structure):
 # every symbol include/geobipy_b200.h declares
 EXPORTS = (
     "gbp_version", "gbp_last_error", "gbp_device_count", "gbp_n_depth", "gbp_flops_per_forward",
-    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_mufu_per_forward", "gbp_measure_peaks",
+    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters",
     "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host",
@@ -140,6 +140,8 @@ def load():
     lib.gbp_mufu_per_forward.argtypes = [vp, i32]
     lib.gbp_tdem_mufu_per_forward.restype = dbl
     lib.gbp_tdem_mufu_per_forward.argtypes = [vp, i32]
+    lib.gbp_debug_counters.restype = i32
+    lib.gbp_debug_counters.argtypes = [vp, i32]
     lib.gbp_measure_peaks.restype = i32
     lib.gbp_measure_peaks.argtypes = [vp, vp]
     lib.gbp_tdem_n_channels.restype = i32

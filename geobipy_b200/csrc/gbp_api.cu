@@ -234,6 +234,8 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
         Q.spec_helpers = hmax < 0 ? 0 : (hmax > WARPS - 1 ? WARPS - 1 : hmax);
         const char* m = std::getenv("GBP_SPEC_MIN_REJECTIONS");
         Q.spec_min_rejections = m ? std::atoi(m) : 24;
+        const char* ia = std::getenv("GBP_SPEC_IDLE_ALL");
+        Q.spec_idle_all = ia ? std::atoi(ia) : 1000;  // off by default: measured no gain (profiles/README.md)
     }
     Q.jstore = g_jstore[dev];
     // device-side work counter: chains beyond the first wave are claimed dynamically
@@ -562,6 +564,16 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                                 return gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
                                                       precision, nullptr);
                             });
+}
+
+int gbp_debug_counters(unsigned long long* out8, int reset)
+{
+    if (out8) CK(cudaMemcpyFromSymbol(out8, g_diag, 8 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        CK(cudaMemcpyToSymbol(g_diag, z, sizeof(z)));
+    }
+    return 0;
 }
 
 int gbp_measure_peaks(double* fp32_tflops, double* mufu_gops)

@@ -63,6 +63,12 @@ template <typename T> struct FwdExtra<T, KIND_TDEM> {
 template <typename R, int NS> struct Errs {
     R rel[NS], add[NS];
 };
+// outcome of a speculatively evaluated step that would be ACCEPTED: what the owner needs to adopt the proposed state
+template <typename R, int NS> struct SpecOut {
+    int kn, mp, vp, changed;
+    R misfit, prior, likelihood;
+    Errs<R, NS> err, ln_err;
+};
 enum { OP_HITMAP = 0, OP_EDGES, OP_NCELLS, OP_REL, OP_ADD, OP_MISFIT, OP_ACCEPT, OP_N = 8 };
 
 template <typename R> struct MeshBuf {
@@ -89,6 +95,7 @@ template <typename R, typename T, int NC, int KIND> struct __align__(16) WarpSta
     int ctr[CT_N];          // cold counters
     R bestv[BV_N];          // best posterior / errors
     void* outp[OP_N];       // this chain's output rows
+    SpecOut<R, ns_of(KIND)> sout;  // written by a speculative step that ends in an acceptance
     FwdExtra<T, KIND> fx;
 };
 
@@ -124,6 +131,7 @@ struct ChainParams {
                              // time-domain path: 2^40, so that squares of 1e-15 V/Am^4 stay normal numbers)
     int spec_helpers;        // max warps that evaluate future iterations of one chain speculatively (0 = off)
     int spec_min_rejections; // a chain speculates once it has rejected this many steps in a row
+    int spec_idle_all;       // ... or after 2 rejections once this many warps of its CTA are idle
     int* work_counter;
     void* jstore;            // [B][NC*KS] of T: Jacobian of each chain's current model
 };
@@ -1032,6 +1040,19 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                         j_valid = true;
                     }
                     if (lane == 0) w->ctr[CT_N_ACCEPT]++;
+                } else if (accepted) {  // SPEC: leave the proposed state in this warp's buffers and describe it
+                    if (lane == 0) {
+                        w->sout.kn = kn;
+                        w->sout.mp = mp;
+                        w->sout.vp = vp;
+                        w->sout.changed = changed ? 1 : 0;
+                        w->sout.misfit = tml.a;
+                        w->sout.prior = t_prior;
+                        w->sout.likelihood = tml.b;
+                        w->sout.err = err_t;
+                        w->sout.ln_err = ln_t_err;
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -1042,17 +1063,23 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
 // Chains are sequential and their lengths differ by 6x (the reference's reset rule), so every batch ends with a
 // tail in which most warps of an SM have no chain left; small batches never fill the machine at all.  An
 // accept_reject step that is REJECTED leaves the chain state untouched, and (sub-streams, gbp_math.cuh) the random
-// numbers of iteration t do not depend on iterations < t.  So while the owner warp executes iteration t0 for real,
-// idle warps of the CTA evaluate iterations t0+1, t0+2, ... on private copies of the chain state, assuming t0 ..
-// are rejected.  The owner then commits the leading run of rejections (bookkeeping only) and continues at the
-// first iteration that was not a plain rejection, which it executes itself.  Results are bitwise identical to the
-// sequential chain; chains that are stuck (the ones the reset rule makes 3-6x longer) advance W iterations per
-// iteration time.
+// numbers of iteration t do not depend on iterations < t.  So idle warps of the CTA evaluate iterations t0, t0+1, ...
+// of a running chain in parallel on private copies of its state, each assuming that all earlier ones are rejected.
+// The owner commits the leading run of rejections (bookkeeping only) and, if the first step that is not a plain
+// rejection is an acceptance, ADOPTS the proposed state from the warp that evaluated it.  Results are bitwise
+// identical to the sequential chain.  Chains that are stuck (the ones the reset rule makes 3-6x longer) advance W
+// iterations per iteration time; a chain with acceptance rate a advances about 1/a.
 constexpr int SPEC_RES = 256;  // iterations one round can cover
+// diagnostics of the speculation hand-off (gbp_debug_counters): [0] helper wake-ups, [1] cycles GO -> helper awake,
+// [2] cycles copying the chain state, [3] speculative steps, [4] cycles in speculative steps, [5] cycles a stopped
+// helper waits for release, [6] owner cycles waiting for `done`, [7] owner cycles copying the adopted proposal
+__device__ unsigned long long g_diag[8];
 enum { MB_BUSY = 0, MB_IDLE = 1, MB_CLAIMED = 2, MB_GO = 16 };  // mailbox states of a warp (MB_GO + owner warp)
+enum { STOP_NONE = 0, STOP_ACCEPT = 1, STOP_OTHER = 2 };
 
 template <typename R, typename T, int NS> struct SpecRound {
     Hot<R, NS> hot;            // chain state before iteration t0
+    SpecOut<R, NS> win;        // outcome of the accepted step the owner adopts
     T alt;
     R nahl;
     T* jg;
@@ -1060,8 +1087,11 @@ template <typename R, typename T, int NS> struct SpecRound {
     volatile int t0, t_end, W;
     volatile int first_stop;   // smallest iteration whose step was not a plain rejection (INT_MAX: none yet)
     volatile int done;         // helpers finished
-    unsigned char midx[32];    // member index of warp x in this round
-    volatile unsigned char res[SPEC_RES];  // per iteration t0+1+i: 0x80 valid | 0x40 stop | nsens << 4 | nfwd << 2 | action
+    volatile unsigned seq, released;  // round number; helpers keep their state until released == seq
+    long long t_go;
+    int win_byte;
+    unsigned char midx[32];    // member index + 1 of warp x in this round
+    volatile unsigned char res[SPEC_RES];  // per iteration t0+i: 0x80 valid | 0x40 stop | nsens << 4 | nfwd << 2 | action
 };
 template <typename R, typename T, int NS> struct TailCtx {
     SpecRound<R, T, NS>* rounds;   // [n_warps]
@@ -1071,10 +1101,19 @@ template <typename R, typename T, int NS> struct TailCtx {
     int n_warps, max_helpers, warp;
 };
 
-// Evaluate iterations first, first + stride, ... < t_end speculatively on w (a private copy of the chain state, or the
-// owner's own WarpState: only scratch buffers are written).
+// 4-byte-word copy of nbytes (multiple of 4) by one warp
+__device__ __forceinline__ void ch_copy4(void* dst, const void* src, int nbytes)
+{
+    const int* s4 = (const int*)src;
+    int* d4 = (int*)dst;
+#pragma unroll 1
+    for (int i = lane_id(); i < nbytes / 4; i += 32) d4[i] = s4[i];
+}
+
+// Evaluate iterations t0 + member, + W, ... < t_end speculatively on w (a private copy of the chain state).
+// Returns true if this warp stopped on a step that was not a plain rejection (its buffers then hold the proposal).
 template <typename R, typename T, int NC, int KIND>
-__device__ __noinline__ void spec_member_run(WarpState<R, T, NC, KIND>* w, SpecRound<R, T, ns_of(KIND)>* rd, const Consts<R>* K,
+__device__ __noinline__ bool spec_member_run(WarpState<R, T, NC, KIND>* w, SpecRound<R, T, ns_of(KIND)>* rd, const Consts<R>* K,
                                              const typename SysOf<T, KIND>::shared* S, const T* tab, const int member)
 {
     GBP_SHARED(w);
@@ -1087,8 +1126,9 @@ __device__ __noinline__ void spec_member_run(WarpState<R, T, NC, KIND>* w, SpecR
     const T alt = rd->alt;
     const R nahl = rd->nahl;
     T* const jg = rd->jg;
+    bool stopped = false;
 #pragma unroll 1
-    for (int t = t0 + 1 + member; t < t_end; t += W) {
+    for (int t = t0 + member; t < t_end; t += W) {
         const int fs = __shfl_sync(FULL, (int)rd->first_stop, 0);
         if (t > fs) break;
         if (lane == 0) {
@@ -1102,19 +1142,29 @@ __device__ __noinline__ void spec_member_run(WarpState<R, T, NC, KIND>* w, SpecR
         h.rng.iter = (uint32_t)t + 1u;
         h.rng.block = 0u;
         bool accepted = false, chol_failed = false;
+        const long long c_s = clock64();
         ar_step<true, R, T, NC, KIND>(w, K, S, tab, alt, nahl, jg, h, accepted, chol_failed);
+        if (lane == 0) {
+            atomicAdd(&g_diag[3], 1ull);
+            atomicAdd(&g_diag[4], (unsigned long long)(clock64() - c_s));
+        }
         const int stop = (accepted || chol_failed) ? 1 : 0;
         __syncwarp();
         if (lane == 0) {
             const int action = w->ctr[CT_ACT0] ? 0 : (w->ctr[CT_ACT1] ? 1 : (w->ctr[CT_ACT2] ? 2 : 3));
             const int byte = 0x80 | (stop << 6) | ((w->ctr[CT_N_SENS] & 3) << 4) | ((w->ctr[CT_N_FWD] & 3) << 2) | action;
+            w->ctr[CT_N_ACCEPT] = (accepted && !chol_failed) ? 1 : 0;  // kind of stop, read by the owner
             if (stop) atomicMin((int*)&rd->first_stop, t);
-            rd->res[t - t0 - 1] = (unsigned char)byte;
+            rd->res[t - t0] = (unsigned char)byte;
         }
-        if (stop) break;
+        if (stop) {
+            stopped = true;
+            break;
+        }
     }
     __threadfence_block();
     __syncwarp();
+    return stopped;
 }
 
 // A warp without a chain: serve speculative rounds of the chains of this CTA until none is left.
@@ -1144,18 +1194,33 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
                     }
                     continue;
                 }
-                __nanosleep(400);
+                __nanosleep(200);
             }
         }
         cmd = __shfl_sync(FULL, cmd, 0);
         if (cmd < 0) break;
         SpecRound<R, T, ns_of(KIND)>* rd = tc.rounds + (cmd - MB_GO);
         __threadfence_block();
+        const unsigned seq = __shfl_sync(FULL, (unsigned)rd->seq, 0);
+        const long long c_wake = clock64();
         ch_copy16(w, rd->owner_ws, (int)sizeof(WarpState<R, T, NC, KIND>));
+        const long long c_copied = clock64();
+        if (lane == 0) {
+            atomicAdd(&g_diag[0], 1ull);
+            atomicAdd(&g_diag[1], (unsigned long long)(c_wake - rd->t_go));
+            atomicAdd(&g_diag[2], (unsigned long long)(c_copied - c_wake));
+        }
         const int member = (int)rd->midx[tc.warp] - 1;
-        spec_member_run<R, T, NC, KIND>(w, rd, K, S, tab, member);
+        const bool stopped = spec_member_run<R, T, NC, KIND>(w, rd, K, S, tab, member);
         if (lane == 0) {
             atomicAdd((int*)&rd->done, 1);
+            // a warp that stopped may hold the proposal the owner adopts: keep the buffers until the owner is done
+            if (stopped) {
+                const long long c_r = clock64();
+#pragma unroll 1
+                while (rd->released != seq) __nanosleep(100);
+                atomicAdd(&g_diag[5], (unsigned long long)(clock64() - c_r));
+            }
             __threadfence_block();
             tc.mailbox[tc.warp] = MB_IDLE;
         }
@@ -1164,11 +1229,11 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
     if (lane == 0) atomicSub((int*)tc.n_idle, 1);
 }
 
-// Owner, before its real step of iteration `total`: claim idle warps and start a round covering iterations
-// total+1 .. total+len.  Returns the number of helpers (0: no round).
+// Owner: claim idle warps and start a round covering iterations total .. total+len-1.  Returns the number of helpers.
 template <typename R, typename T, int NC, int KIND>
 __device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc,
-                                             const Hot<R, ns_of(KIND)> h, T alt, R nahl, T* jg, int total, int mult)
+                                             const Hot<R, ns_of(KIND)> h, T alt, R nahl, T* jg, int total, int mult,
+                                             int want, int need)
 {
     const int lane = lane_id();
     SpecRound<R, T, ns_of(KIND)>* rd = tc.rounds + tc.warp;
@@ -1176,13 +1241,21 @@ __device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailC
     int nh = 0;
     if (lane == 0) {
 #pragma unroll 1
-        for (int x = 0; x < tc.n_warps && nh < tc.max_helpers; ++x)
+        for (int x = 0; x < tc.n_warps && nh < want; ++x)
             if (tc.mailbox[x] == MB_IDLE && atomicCAS((int*)&tc.mailbox[x], MB_IDLE, MB_CLAIMED) == MB_IDLE) rd->midx[x] = (unsigned char)(++nh);
+        if (nh < need) {  // the owner waits during a round: with too few helpers a round is slower than the chain itself
+#pragma unroll 1
+            for (int x = 0; x < tc.n_warps; ++x)
+                if (rd->midx[x] != 0) {
+                    rd->midx[x] = 0;
+                    tc.mailbox[x] = MB_IDLE;
+                }
+            nh = 0;
+        }
     }
     nh = __shfl_sync(FULL, nh, 0);
     if (nh == 0) return 0;
-    const int W = nh;  // the owner executes iteration `total` for real meanwhile, then waits
-    int len = W * mult;
+    int len = nh * mult;
     if (len > SPEC_RES) len = SPEC_RES;
 #pragma unroll 1
     for (int i = lane; i < len; i += 32) rd->res[i] = 0;
@@ -1193,14 +1266,17 @@ __device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailC
         rd->jg = jg;
         rd->owner_ws = w;
         rd->t0 = total;
-        rd->t_end = total + 1 + len;
-        rd->W = W;
+        rd->t_end = total + len;
+        rd->W = nh;
         rd->first_stop = 0x7fffffff;
         rd->done = 0;
+        rd->seq = rd->seq + 1u;
     }
     __threadfence_block();
     __syncwarp();
     if (lane == 0) {
+        rd->t_go = clock64();
+        __threadfence_block();
 #pragma unroll 1
         for (int x = 0; x < tc.n_warps; ++x)
             if (tc.mailbox[x] == MB_CLAIMED && rd->midx[x] != 0) tc.mailbox[x] = MB_GO + tc.warp;
@@ -1209,28 +1285,28 @@ __device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailC
     return nh;
 }
 
-// Owner, after its real step: wait for the helpers and return how many leading iterations after `total` are plain
-// rejections (their results are in rd->res).
+// Owner: wait for the helpers.  Returns the number of leading plain rejections from iteration t0 on (their results
+// are in rd->res); *stop_kind says what follows them: nothing evaluated (STOP_NONE), an acceptance whose proposed
+// state has been copied into the owner's scratch buffers and rd->win (STOP_ACCEPT), or something the owner has to
+// execute itself (STOP_OTHER).
 template <typename R, typename T, int NC, int KIND>
-__device__ __noinline__ int spec_round_end(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc, const Consts<R>* K,
-                                           const typename SysOf<T, KIND>::shared* S, const T* tab, int nh, bool own_step_changed_state)
+__device__ __noinline__ int spec_round_end(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc, int nh, int* stop_kind)
 {
     const int lane = lane_id();
     SpecRound<R, T, ns_of(KIND)>* rd = tc.rounds + tc.warp;
     GBP_SHARED(rd);
-    if (own_step_changed_state && lane == 0)
-        atomicMin((int*)&rd->first_stop, rd->t0);  // everything speculated is void: helpers stop early
+    GBP_SHARED(w);
     if (lane == 0) {
+        const long long c_w = clock64();
 #pragma unroll 1
         while (rd->done < nh) __nanosleep(100);
-        for (int x = 0; x < tc.n_warps; ++x) rd->midx[x] = 0;
+        atomicAdd(&g_diag[6], (unsigned long long)(clock64() - c_w));
     }
     __threadfence_block();
     __syncwarp();
-    if (own_step_changed_state) return 0;
-    const int fs = rd->first_stop, t0 = rd->t0, te = rd->t_end;
-    int n = ((fs < te) ? fs : te) - t0 - 1;
-    if (n < 0) n = 0;
+    const long long c_a = clock64();
+    const int fs = rd->first_stop, t0 = rd->t0, te = rd->t_end, W = rd->W;
+    int n = ((fs < te) ? fs : te) - t0;
     // every committed slot must hold a valid plain rejection (defensive: stop at the first that does not)
     int bad = n;
 #pragma unroll 1
@@ -1238,7 +1314,45 @@ __device__ __noinline__ int spec_round_end(WarpState<R, T, NC, KIND>* w, TailCtx
         if ((rd->res[i] & 0xC0) != 0x80) bad = min(bad, i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bad = min(bad, __shfl_xor_sync(FULL, bad, o));
-    return bad;
+    int kind = STOP_NONE;
+    if (bad < n) {
+        n = bad;
+        kind = STOP_OTHER;
+    } else if (fs < te) {
+        kind = STOP_OTHER;
+        // the warp that evaluated iteration fs: member (fs - t0) % W
+        const int member = (fs - t0) % W;
+        int x = -1;
+        if (lane < tc.n_warps && (int)rd->midx[lane] == member + 1) x = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(FULL, x, o));
+        if (x >= 0) {
+            const WarpState<R, T, NC, KIND>* hw = w + (x - tc.warp);
+            if (hw->ctr[CT_N_ACCEPT] == 1) {  // an acceptance: adopt the proposal
+                kind = STOP_ACCEPT;
+                const SpecOut<R, ns_of(KIND)> so = hw->sout;
+                const int pc = rd->hot.pcur ^ 1;
+                if (so.changed) ch_copy4(&w->mesh[so.mp], &hw->mesh[so.mp], (int)sizeof(MeshBuf<R>));
+                ch_copy4(&w->val[so.vp], &hw->val[so.vp], (int)sizeof(ValBuf<R>));
+                ch_copy4(w->pred[pc], hw->pred[pc], NC * (int)sizeof(T));
+                if (so.changed) ch_copy16(w->J, hw->J, NC * KS * (int)sizeof(T));
+                if (lane == 0) {
+                    rd->win = so;
+                    rd->win_byte = rd->res[fs - t0];
+                }
+            }
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        for (int x = 0; x < tc.n_warps; ++x) rd->midx[x] = 0;
+        rd->released = rd->seq;
+        atomicAdd(&g_diag[7], (unsigned long long)(clock64() - c_a));
+    }
+    __syncwarp();
+    *stop_kind = kind;
+    return n;
 }
 
 // ================================================================ the chain (inlined into the kernel)
@@ -1348,12 +1462,39 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
     bool failed = (n_active == 0);
     bool go = !failed;
     int total = 0;
-    int spec_left = 0, spec_pos = 0, spec_mult = 1, rej_run = 0;
+    int spec_left = 0, spec_pos = 0, spec_mult = 1, rej_run = 0, spec_stop = STOP_NONE;
+    int spec_rounds = 0, spec_helpers_sum = 0;   // diagnostics
+    long long spec_cycles = 0;
 #pragma unroll 1
     while (go) {
         // ==================================================== Inference1D.accept_reject :537-631
         bool accepted = false;
         bool chol_failed = false;
+        // only a chain that has just rejected a few steps speculates: long rejection runs make long rounds (the
+        // hand-off is amortised), and a chain that accepts every other step gains nothing
+        // (helpers are shared by the chains of a CTA: while several chains compete for them only long rejection runs,
+        // whose rounds use the helpers fully, may speculate; once nearly all warps of the CTA are idle any chain may)
+        const int n_idle_now = (tc.max_helpers > 0) ? *tc.n_idle : 0;
+        if (spec_left == 0 && spec_stop == STOP_NONE && n_idle_now > 0 &&
+            (rej_run >= P.spec_min_rejections || (n_idle_now >= P.spec_idle_all && rej_run >= 2))) {
+            // helpers asked for grow with the rejection run (a short run usually ends within a few steps); the owner
+            // waits during a round, so a round needs at least 2 (stuck chain) to 4 helpers to pay
+            int want = 4 + (rej_run >> 2);
+            if (want > tc.max_helpers) want = tc.max_helpers;
+            const int need = (rej_run >= 24) ? 2 : 4;
+            const long long c0 = clock64();
+            const int nh = spec_round_begin<R, T, NC, KIND>(w, tc, h, alt, nahl, jg, total, spec_mult, want, need);
+            if (nh > 0) {
+                spec_left = spec_round_end<R, T, NC, KIND>(w, tc, nh, &spec_stop);
+                spec_rounds++;
+                spec_cycles += clock64() - c0;
+                spec_helpers_sum += nh;
+                spec_pos = 0;
+                if (spec_stop == STOP_ACCEPT && tc.rounds[tc.warp].win.changed) j_valid = false;  // w->J now holds the proposal's
+                // rounds grow while nothing but rejections comes back (a stuck chain), and start small again otherwise
+                spec_mult = (spec_stop == STOP_NONE) ? min(spec_mult * 2, 32) : 1;
+            }
+        }
         if (spec_left > 0) {
             // this iteration was evaluated speculatively and is a plain rejection: only its bookkeeping remains
             const int byte = tc.rounds[tc.warp].res[spec_pos];
@@ -1366,22 +1507,41 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
                 w->ctr[CT_N_SPEC]++;
             }
             __syncwarp();
+        } else if (spec_stop == STOP_ACCEPT) {
+            // this iteration was evaluated speculatively and is an ACCEPTANCE: adopt the proposed state (already
+            // copied into this warp's scratch buffers), with the side effects of the chain's own accept path
+            spec_stop = STOP_NONE;
+            const SpecOut<R, NS> so = tc.rounds[tc.warp].win;
+            const int byte = tc.rounds[tc.warp].win_byte;
+            ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
+            dwell = 0;
+            misfit = so.misfit;
+            prior = so.prior;
+            likelihood = so.likelihood;
+            k = so.kn;
+            err = so.err;
+            ln_err = so.ln_err;
+            mcur = so.mp;
+            vcur = so.vp;
+            pcur ^= 1;
+            if (so.changed) {
+                ch_copy16(jg, w->J, JBYTES);
+                j_valid = true;
+            }
+            if (lane == 0) {
+                w->ctr[CT_N_ACCEPT]++;
+                w->ctr[CT_ACT0 + (byte & 3)]++;
+                w->ctr[CT_N_FWD] += (byte >> 2) & 3;
+                w->ctr[CT_N_SENS] += (byte >> 4) & 3;
+                w->ctr[CT_N_SPEC]++;
+            }
+            __syncwarp();
+            accepted = true;
         } else {
-            int nh = 0;
-            // only a chain that keeps rejecting speculates: its rounds are long, so the hand-off is amortised, and
-            // those are the chains that make the tail (a chain with a healthy acceptance rate gains little)
-            if (tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && *tc.n_idle > 0)
-                nh = spec_round_begin<R, T, NC, KIND>(w, tc, h, alt, nahl, jg, total, spec_mult);
+            spec_stop = STOP_NONE;
             rng.iter = (uint32_t)total + 1u;  // sub-stream of this accept_reject step
             rng.block = 0u;
             ar_step<false, R, T, NC, KIND>(w, K, S, tab, alt, nahl, jg, h, accepted, chol_failed);
-            if (nh > 0) {
-                spec_left = spec_round_end<R, T, NC, KIND>(w, tc, K, S, tab, nh, accepted || chol_failed);
-                spec_pos = 0;
-                // rounds grow while nothing but rejections comes back (a stuck chain), and start small again otherwise
-                const int covered = tc.rounds[tc.warp].t_end - tc.rounds[tc.warp].t0 - 1;
-                spec_mult = (!accepted && spec_left == covered) ? min(spec_mult * 2, 32) : 1;
-            }
         }
         failed = chol_failed;
         rej_run = accepted ? 0 : rej_run + 1;
@@ -1444,6 +1604,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             if (lane == 0) w->ctr[CT_N_RESETS] = nr;
             initialize(false);
             spec_left = 0;  // speculated iterations assumed the old state
+            spec_stop = STOP_NONE;
             dwell = 1;  // update() goes on to accumulate the re-initialised model
         }
         const int burn_iter = w->ctr[CT_BURN_ITER];
@@ -1462,6 +1623,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
                 }
                 initialize(false);
             spec_left = 0;  // speculated iterations assumed the old state
+            spec_stop = STOP_NONE;
             } else {
                 go = false;
                 failed = true;
@@ -1512,6 +1674,8 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
         s[GBP_S_TOTAL_ITER] = (double)total;
         s[GBP_S_N_SPECULATED] = (double)w->ctr[CT_N_SPEC];
+        s[GBP_S_SPEC_ROUNDS] = (double)spec_rounds;
+        s[GBP_S_SPEC_CYCLES] = (double)spec_cycles;
     }
     __syncwarp();
 #undef N2
@@ -1566,6 +1730,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     if (lane == 0) {
         mailbox[warp] = MB_BUSY;
         for (int x = 0; x < 32; ++x) rounds[warp].midx[x] = 0;
+        rounds[warp].seq = 0u;
+        rounds[warp].released = 0u;
     }
     __syncthreads();
     if (lane == 0 && c < P.B) atomicAdd(&n_alive, 1);
