@@ -299,7 +299,7 @@ def run_b200_arm(args):
     iters = iters_dev.clone().reshape(1)
     last_kernel_ms = ops.last_kernel_ms()
     last_iters = float(res["scalars"][:, _lib.S_TOTAL_ITER].sum().item())
-    n_spec = float(res["scalars"][:, _lib.S_N_SPECULATED].sum().item())
+    n_spec = float(ops.debug_counters()[8]) / max(args.steps + args.warmup, 1)  # per launch (all launches are alike)
     n_fwd = float(res["scalars"][:, _lib.S_N_FORWARD].sum().item())
     n_sens = float(res["scalars"][:, _lib.S_N_SENS].sum().item())
     mean_k = float((res["ncells_hist"].sum(dim=0).double() * torch.arange(opt.max_layers + 1, device=dev)).sum().item()

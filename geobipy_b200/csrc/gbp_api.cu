@@ -566,11 +566,12 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                             });
 }
 
-int gbp_debug_counters(unsigned long long* out8, int reset)
+int gbp_debug_counters(unsigned long long* out16, int reset)
 {
-    if (out8) CK(cudaMemcpyFromSymbol(out8, g_diag, 8 * sizeof(unsigned long long)));
+    if (out16) CK(cudaMemcpyFromSymbol(out16, g_diag, 16 * sizeof(unsigned long long)));
     if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long z[16];
+        std::memset(z, 0, sizeof(z));
         CK(cudaMemcpyToSymbol(g_diag, z, sizeof(z)));
     }
     return 0;

@@ -1072,8 +1072,11 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
 constexpr int SPEC_RES = 256;  // iterations one round can cover
 // diagnostics of the speculation hand-off (gbp_debug_counters): [0] helper wake-ups, [1] cycles GO -> helper awake,
 // [2] cycles copying the chain state, [3] speculative steps, [4] cycles in speculative steps, [5] cycles a stopped
-// helper waits for release, [6] owner cycles waiting for `done`, [7] owner cycles copying the adopted proposal
-__device__ unsigned long long g_diag[8];
+// helper waits for release, [6] owner cycles waiting for `done`, [7] owner cycles copying the adopted proposal,
+// [8] iterations committed from speculation, [9] rounds, [10] owner cycles spent in rounds.  These are the only
+// outputs that depend on scheduling; they are kept out of the per-chain result arrays, which are bit-identical
+// with speculation on or off.
+__device__ unsigned long long g_diag[16];
 enum { MB_BUSY = 0, MB_IDLE = 1, MB_CLAIMED = 2, MB_GO = 16 };  // mailbox states of a warp (MB_GO + owner warp)
 enum { STOP_NONE = 0, STOP_ACCEPT = 1, STOP_OTHER = 2 };
 
@@ -1182,6 +1185,9 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
     for (;;) {
         int cmd = 0;
         if (lane == 0) {
+            // poll with back-off: ncu showed 27 idle warps polling every ~50 ns (a short nanosleep returns almost at
+            // once) issuing 95 % of all instructions of a tail-dominated run and halving the speed of the working warps
+            unsigned ns = 1000u;
 #pragma unroll 1
             for (;;) {
                 cmd = tc.mailbox[tc.warp];
@@ -1194,7 +1200,8 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
                     }
                     continue;
                 }
-                __nanosleep(200);
+                __nanosleep(ns);
+                if (ns < 8000u) ns += 1000u;
             }
         }
         cmd = __shfl_sync(FULL, cmd, 0);
@@ -1218,7 +1225,7 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
             if (stopped) {
                 const long long c_r = clock64();
 #pragma unroll 1
-                while (rd->released != seq) __nanosleep(100);
+                while (rd->released != seq) __nanosleep(1000);
                 atomicAdd(&g_diag[5], (unsigned long long)(clock64() - c_r));
             }
             __threadfence_block();
@@ -1299,7 +1306,7 @@ __device__ __noinline__ int spec_round_end(WarpState<R, T, NC, KIND>* w, TailCtx
     if (lane == 0) {
         const long long c_w = clock64();
 #pragma unroll 1
-        while (rd->done < nh) __nanosleep(100);
+        while (rd->done < nh) __nanosleep(1000);
         atomicAdd(&g_diag[6], (unsigned long long)(clock64() - c_w));
     }
     __threadfence_block();
@@ -1673,9 +1680,11 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_N_MOVE] = (double)w->ctr[CT_ACT2];
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
         s[GBP_S_TOTAL_ITER] = (double)total;
-        s[GBP_S_N_SPECULATED] = (double)w->ctr[CT_N_SPEC];
-        s[GBP_S_SPEC_ROUNDS] = (double)spec_rounds;
-        s[GBP_S_SPEC_CYCLES] = (double)spec_cycles;
+        if (spec_rounds > 0) {
+            atomicAdd(&g_diag[8], (unsigned long long)w->ctr[CT_N_SPEC]);
+            atomicAdd(&g_diag[9], (unsigned long long)spec_rounds);
+            atomicAdd(&g_diag[10], (unsigned long long)spec_cycles);
+        }
     }
     __syncwarp();
 #undef N2

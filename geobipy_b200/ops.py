@@ -364,3 +364,10 @@ def measure_peaks():
     a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
     _lib.check(lib.gbp_measure_peaks(ctypes.byref(a), ctypes.byref(b)))
     return float(a.value), float(b.value)
+
+
+def debug_counters(reset=False):
+    """The 16 speculation diagnostics of include/geobipy_b200.h gbp_debug_counters (numpy uint64)."""
+    out = np.zeros(16, dtype=np.uint64)
+    _lib.check(_lib.load().gbp_debug_counters(out.ctypes.data, 1 if reset else 0))
+    return out

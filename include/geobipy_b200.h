@@ -116,10 +116,6 @@ enum {
     GBP_S_BEST_REL, GBP_S_BEST_ADD, GBP_S_N_RESETS, GBP_S_N_BIRTH, GBP_S_N_DEATH, GBP_S_N_MOVE, GBP_S_N_NONE,
     GBP_S_TOTAL_ITER,   /* accept_reject+update pairs executed, including those before a reset() */
     GBP_S_CUR_REL2, GBP_S_CUR_ADD2, GBP_S_BEST_REL2, GBP_S_BEST_ADD2,  /* system 1 of a dual-moment datapoint */
-    GBP_S_N_SPECULATED, /* iterations whose rejection was established speculatively by another warp (diagnostic; the
-                           only scalars that depend on scheduling: this one and the next two) */
-    GBP_S_SPEC_ROUNDS,  /* speculative rounds this chain started */
-    GBP_S_SPEC_CYCLES,  /* SM clock cycles the owner spent in those rounds (hand-off + waiting for the helpers) */
     GBP_NSCALARS = 32
 };
 
@@ -157,9 +153,10 @@ double gbp_mufu_per_forward(const gbp_fdem_system *sys, int n_layers);
 /* measured peaks of the two pipes that bound this path on the current device: dependent-free FFMA chains
  * (TFLOP/s, 2 flops per FMA) and MUFU operations (Gop/s).  Two tiny kernels, best of 3 after warm-up. */
 int gbp_measure_peaks(double *fp32_tflops, double *mufu_gops);
-/* diagnostics of the speculation hand-off, summed over all launches since the last reset (8 counters, see
- * gbp_chain.cuh g_diag); synchronises the device */
-int gbp_debug_counters(unsigned long long *out8, int reset);
+/* diagnostics of speculative evaluation, summed over all launches on the current device since the last reset
+ * (16 counters, see gbp_chain.cuh g_diag: [8] iterations committed from speculation, [9] rounds, ...).  The only
+ * outputs that depend on scheduling; synchronises the device */
+int gbp_debug_counters(unsigned long long *out16, int reset);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t gbp_launch_count(void);
 /* mean duration [ms] and launch count of the last gbp_rjmcmc_run / forward kernel, measured with CUDA
