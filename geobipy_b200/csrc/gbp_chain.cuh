@@ -131,7 +131,6 @@ struct ChainParams {
                              // time-domain path: 2^40, so that squares of 1e-15 V/Am^4 stay normal numbers)
     int spec_helpers;        // max warps that evaluate future iterations of one chain speculatively (0 = off)
     int spec_min_rejections; // a chain speculates once it has rejected this many steps in a row
-    int spec_idle_all;       // ... or after 2 rejections once this many warps of its CTA are idle
     int* work_counter;
     void* jstore;            // [B][NC*KS] of T: Jacobian of each chain's current model
 };
@@ -1479,11 +1478,9 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         bool chol_failed = false;
         // only a chain that has just rejected a few steps speculates: long rejection runs make long rounds (the
         // hand-off is amortised), and a chain that accepts every other step gains nothing
-        // (helpers are shared by the chains of a CTA: while several chains compete for them only long rejection runs,
-        // whose rounds use the helpers fully, may speculate; once nearly all warps of the CTA are idle any chain may)
-        const int n_idle_now = (tc.max_helpers > 0) ? *tc.n_idle : 0;
-        if (spec_left == 0 && spec_stop == STOP_NONE && n_idle_now > 0 &&
-            (rej_run >= P.spec_min_rejections || (n_idle_now >= P.spec_idle_all && rej_run >= 2))) {
+        // (helpers are shared by the chains of a CTA: long rejection runs use them fully, a chain with acceptance rate a
+        // commits about 1/a iterations per round whatever their number - lower thresholds were measured slower)
+        if (spec_left == 0 && spec_stop == STOP_NONE && tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && *tc.n_idle > 0) {
             // helpers asked for grow with the rejection run (a short run usually ends within a few steps); the owner
             // waits during a round, so a round needs at least 2 (stuck chain) to 4 helpers to pay
             int want = 4 + (rej_run >> 2);
