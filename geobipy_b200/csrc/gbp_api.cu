@@ -483,6 +483,28 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
 
 }  // extern "C"
 
+// Device buffers of the host-pointer sampler entry points are kept between calls (per device, one slot per result
+// array): allocating and freeing 2.5 GB of posterior arrays cost more per call than copying them.
+struct HostArena {
+    void* ptr[16];
+    size_t cap[16];
+};
+static HostArena g_arena[64];
+static std::mutex g_host_mu;
+static int arena_get(int dev, int slot, size_t bytes, void** out)
+{
+    HostArena& a = g_arena[dev];
+    if (a.cap[slot] < bytes) {
+        if (a.ptr[slot]) cudaFree(a.ptr[slot]);
+        a.ptr[slot] = nullptr;
+        a.cap[slot] = 0;
+        CK(cudaMalloc(&a.ptr[slot], bytes));
+        a.cap[slot] = bytes;
+    }
+    *out = a.ptr[slot];
+    return 0;
+}
+
 // shared body of the *_rjmcmc_run_host entry points; `run` launches on the device buffers
 template <typename RunFn>
 static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* data, const double* altitude,
@@ -515,31 +537,21 @@ static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* 
         {(void* const*)&h->cur_edges, (void**)&d.cur_edges, (size_t)B * (ml + 1) * sizeof(double)},
         {(void* const*)&h->scalars, (void**)&d.scalars, (size_t)B * GBP_NSCALARS * sizeof(double)},
     };
+    if (device < 0 || device >= 64) return fail("device index out of range");
+    std::lock_guard<std::mutex> lk(g_host_mu);  // the cached device buffers are shared by the callers of this process
     double *d_data = nullptr, *d_alt = nullptr;
-    int rc = 0;
-    auto cleanup = [&]() {
-        for (const Item& it : items)
-            if (*it.dev) cudaFree(*it.dev);
-        cudaFree(d_data);
-        cudaFree(d_alt);
-    };
-#define CKC(call)                                                                      \
-    do {                                                                               \
-        cudaError_t e_ = (call);                                                       \
-        if (e_ != cudaSuccess) {                                                       \
-            cleanup();                                                                 \
-            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));           \
-        }                                                                              \
-    } while (0)
-    for (const Item& it : items)
+    int rc = 0, slot = 0;
+    for (const Item& it : items) {
         if (*it.host) {
-            CKC(cudaMalloc(it.dev, it.bytes));
-            CKC(cudaMemsetAsync(*it.dev, 0, it.bytes, nullptr));
+            if (arena_get(device, slot, it.bytes, it.dev)) return 1;
+            CK(cudaMemsetAsync(*it.dev, 0, it.bytes, nullptr));
         }
-    CKC(cudaMalloc(&d_data, (size_t)B * C * sizeof(double)));
-    CKC(cudaMalloc(&d_alt, (size_t)B * sizeof(double)));
-    CKC(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    CKC(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+        ++slot;
+    }
+    if (arena_get(device, 12, (size_t)B * C * sizeof(double), (void**)&d_data)) return 1;
+    if (arena_get(device, 13, (size_t)B * sizeof(double), (void**)&d_alt)) return 1;
+    CK(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+    CK(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, nullptr));
     rc = run(d_data, d_alt, &d);
     if (!rc) {
         cudaError_t e = cudaDeviceSynchronize();
@@ -547,8 +559,7 @@ static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* 
     }
     if (!rc)
         for (const Item& it : items)
-            if (*it.host) CKC(cudaMemcpy(*it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost));
-    cleanup();
+            if (*it.host) CK(cudaMemcpy(*it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost));
     return rc;
 }
 
@@ -563,6 +574,20 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                                 return gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
                                                       precision, nullptr);
                             });
+}
+
+int gbp_release_host_buffers(void)
+{
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    for (int dev = 0; dev < 64; ++dev)
+        for (int s = 0; s < 16; ++s)
+            if (g_arena[dev].ptr[s]) {
+                cudaSetDevice(dev);
+                cudaFree(g_arena[dev].ptr[s]);
+                g_arena[dev].ptr[s] = nullptr;
+                g_arena[dev].cap[s] = 0;
+            }
+    return 0;
 }
 
 int gbp_debug_counters(unsigned long long* out16, int reset)

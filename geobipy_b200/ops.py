@@ -371,3 +371,8 @@ def debug_counters(reset=False):
     out = np.zeros(16, dtype=np.uint64)
     _lib.check(_lib.load().gbp_debug_counters(out.ctypes.data, 1 if reset else 0))
     return out
+
+
+def release_host_buffers():
+    """Free the device buffers the numpy (host-pointer) path of rjmcmc_run keeps between calls."""
+    _lib.check(_lib.load().gbp_release_host_buffers())

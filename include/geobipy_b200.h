@@ -196,6 +196,8 @@ int gbp_rjmcmc_run(const gbp_fdem_system *sys, const gbp_options *opt, int B, co
 int gbp_rjmcmc_run_host(const gbp_fdem_system *sys, const gbp_options *opt, int B, const double *data,
                         const double *altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
                         const gbp_chain_buffers *h_buf, int precision, int device);
+/* The *_rjmcmc_run_host entry points keep their device buffers between calls (per device); this frees them. */
+int gbp_release_host_buffers(void);
 
 /* ---- time domain (SkyTEM-type systems) ---------------------------------------------------------- */
 /* total number of data channels = windows of every system, system 0 first (TdemDataPoint channel order) */
