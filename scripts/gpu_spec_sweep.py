@@ -12,7 +12,7 @@ sb = synthetic_batch(0, 4096)
 t = {k: torch.tensor(v, device=dev) for k, v in sb.items()}
 clean = ops.forward(system, t["nlayers"], t["sigma"], t["thickness"], t["height"], precision=64)
 d = (clean + t["noise"] * torch.sqrt((0.05 * clean) ** 2 + 25.0)).contiguous(); h = t["height"]
-for helpers, minrej, idle_all in ((0, 24, 99), (12, 24, 99)):
+for helpers, minrej, idle_all in ((2, 24, 99), (3, 24, 99), (4, 24, 99), (6, 24, 99), (12, 24, 99)):
     os.environ["GBP_SPEC_HELPERS"] = str(helpers); os.environ["GBP_SPEC_MIN_REJECTIONS"] = str(minrej); pass
     import ctypes
     for rep in range(2):

@@ -6,6 +6,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
     python tests/golden/make_golden.py tdem         # skytem_clean.npz
     python tests/golden/make_golden.py tdem_transitions   # tdem_transitions.npz (reference sampler + fake_gatdaem1d)
+    python tests/golden/make_golden.py tdem_chain <i> [rep]   # ref_tdem_chain_<i>[_r<rep>].npz (minutes each)
     python tests/golden/make_golden.py bins         # posterior_bins.npz
     python tests/golden/make_golden.py transitions  # transitions.npz
     python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
@@ -359,6 +360,53 @@ def make_tdem_transitions(n_soundings=5, n_iter=200):
     print("tdem transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
 
 
+def make_tdem_chain(sidx, rep=0, n_markov_chains=10000):
+    """A full chain of the live reference with a dual-moment TdemDataPoint (skytem_options with n_markov_chains
+    reduced), driven through fake_gatdaem1d (oracle forward).  Posterior arrays -> ref_tdem_chain_<i>[_r<rep>].npz."""
+    kw = _tdem_setup()
+    from geobipy import Inference1D, get_prng
+    from geobipy_b200.synthetic import skytem_noise_std
+    import oracle_py as O
+    import io
+    import contextlib
+    tsys = O.make_tdem_system()
+    tc = np.array(tsys.t_centre[:45])
+    edges, sigma, z, noise = synthetic_sounding(sidx, 400.0, 45)
+    clean = O.tdem_forward(tsys, z, sigma, np.r_[np.diff(edges)[:-1], 1.0])
+    data = clean + noise * skytem_noise_std(clean, tc, (26, 19))
+    kw["n_markov_chains"] = n_markov_chains
+    kw["prng"] = get_prng(seed=7000 + sidx + 100 * rep)
+    inf = Inference1D(**kw)
+    dp = _tdem_datapoint(data, z)
+    t0 = time.time()
+    go, failed = True, False
+    with contextlib.redirect_stdout(io.StringIO()):
+        inf.initialize(dp)
+        while go:  # Inference1D.infer :650-677 without the HDF5 write
+            failed = inf.accept_reject()
+            inf.update()
+            go = (not failed) and (inf.iteration <= inf.n_markov_chains + inf.burned_in_iteration)
+            if (not failed) and (not inf.burned_in):
+                go = inf.iteration < inf.n_markov_chains
+                if not go:
+                    failed = True
+    dt = time.time() - t0
+    it = int(inf.iteration)
+    rel = np.stack([np.asarray(p.counts, dtype=np.int32) for p in inf.datapoint.relative_error.posterior])
+    add = np.stack([np.asarray(p.counts, dtype=np.int32) for p in inf.datapoint.additive_error.posterior])
+    np.savez_compressed(
+        os.path.join(HERE, "ref_tdem_chain_%d.npz" % sidx if rep == 0 else "ref_tdem_chain_%d_r%d.npz" % (sidx, rep)),
+        sounding=sidx, data=data, altitude=z, true_edges=edges, true_sigma=sigma, halfspace=float(inf.halfspace.item()),
+        iterations=it, failed=bool(failed), burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
+        hitmap=np.asarray(inf.model.values.posterior.counts, dtype=np.int32),
+        edges_hist=np.asarray(inf.model.mesh.edges.posterior.counts, dtype=np.int32),
+        ncells_hist=np.asarray(inf.model.mesh.nCells.posterior.counts, dtype=np.int32), rel_hist=rel, add_hist=add,
+        misfit_trace=np.asarray(inf.data_misfit_v[:it], dtype=np.float32),
+        accept_trace=np.asarray(inf.acceptance_v[:it + 1], dtype=np.uint8), seconds=dt, n_markov_chains=n_markov_chains)
+    print("tdem chain", sidx, rep, "iterations", it, "burned in", inf.burned_in, inf.burned_in_iteration, "s/it", dt / it,
+          "acc", np.asarray(inf.acceptance_v[:it + 1]).mean(), flush=True)
+
+
 def make_chain(sidx, rep=0, n_markov_chains=10000):
     _geobipy()
     data, z, edges, sigma = _observed(sidx)
@@ -399,6 +447,8 @@ if __name__ == "__main__":
         make_tdem()
     if what == "tdem_transitions":
         make_tdem_transitions()
+    if what == "tdem_chain":
+        make_tdem_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     if what == "fdem":
         make_fdem()
     elif what == "bins":

@@ -313,3 +313,39 @@ def test_tdem_initial_state_matches_live_reference(oracle, golden_dir):
     i = 0
     kw = {k: g[k][i] for k in g.files}
     assert int(kw["k"]) >= 1 and np.isfinite(kw["init_misfit"]) and np.isfinite(kw["init_likelihood"])
+
+
+def test_tdem_chain_statistics_match_reference_chains(oracle, golden_dir):
+    """Posterior statistics of oracle chains vs 6 full chains of the live reference (Inference1D with a dual-moment
+    TdemDataPoint and skytem_options at n_markov_chains = 10 000, gatdaem1d replaced by tests/golden/fake_gatdaem1d.py)
+    on the same observed data, different random streams.  Same yardsticks as the frequency-domain check: acceptance
+    rate +-5 points (measured: reference 0.208, 16 oracle chains 0.181), mean layer count +-0.75 (5.98 vs 6.27 +- 0.15),
+    pooled median conductivity profile inside the reference envelope +-2 bins for >= 90 % of the top 100 m, posterior
+    means of the four error parameters within 2 histogram bins; and the same chain length (both burn in at 5001)."""
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_tdem_chain_2"))
+    refs = [np.load(os.path.join(golden_dir, f)) for f in files]
+    assert len(refs) >= 6
+    g = refs[0]
+    s, o = oracle.make_tdem_system(), oracle.skytem_options(n_markov_chains=10000)
+    ref_acc = np.mean([r["accept_trace"].mean() for r in refs])
+    ref_nc = sum(r["ncells_hist"].astype(np.int64) for r in refs)
+    ref_med = np.array([_summary(r["hitmap"][:, :200]) for r in refs])
+    runs = [oracle.run_chain(s, o, g["data"], float(g["altitude"]), 200 + j, 2) for j in range(6)]
+    assert abs(runs[0]["scalars"][oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-12
+    for r in runs:
+        assert int(r["scalars"][oracle.S_ITER]) == int(g["iterations"])            # 10 000 + 5001 + 1
+        assert int(r["scalars"][oracle.S_BURNED_IN_ITER]) == int(g["burned_in_iteration"])
+        assert r["ncells_hist"].sum() == g["ncells_hist"].sum() == 10002           # iterations b .. b + N + 1
+    acc = np.mean([r["scalars"][oracle.S_N_ACCEPT] / r["scalars"][oracle.S_ITER] for r in runs])
+    assert abs(acc - ref_acc) < 0.05, (acc, ref_acc)
+    nc = sum(r["ncells_hist"].astype(np.int64) for r in runs)
+    k = np.arange(nc.size)
+    assert abs((nc * k).sum() / nc.sum() - (ref_nc * k).sum() / ref_nc.sum()) < 0.75
+    med = _summary(sum(r["hitmap"].astype(np.int64) for r in runs)[:, :200])
+    inside = (med >= ref_med.min(axis=0) - 2) & (med <= ref_med.max(axis=0) + 2)
+    assert inside.mean() >= 0.9, med
+    b = np.arange(99)
+    for name in ("rel_hist", "add_hist"):
+        rr = sum(r[name].astype(np.int64) for r in refs)
+        oo = sum(r[name].astype(np.int64) for r in runs)
+        assert np.all(np.abs((rr * b).sum(axis=1) / rr.sum(axis=1) - (oo * b).sum(axis=1) / oo.sum(axis=1)) < 2.0), name
