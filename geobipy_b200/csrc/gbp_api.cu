@@ -196,6 +196,9 @@ int launch_tdem(TdCache* tc, int B, int l_stride, const int32_t* nl, const doubl
     return time_end(st);
 }
 
+unsigned long long* g_finish[64] = {nullptr};  // debug timeline (GBP_DEBUG_TIMELINE)
+size_t g_finish_cap[64] = {0};
+int g_finish_B[64] = {0};
 void* g_jstore[64] = {nullptr};
 size_t g_jstore_cap[64] = {0};
 
@@ -237,6 +240,20 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
 
     }
     Q.jstore = g_jstore[dev];
+    Q.finish_ns = nullptr;
+    if (std::getenv("GBP_DEBUG_TIMELINE")) {
+        const size_t need = (size_t)(P.B + 1) * sizeof(unsigned long long);
+        if (g_finish_cap[dev] < need) {
+            if (g_finish[dev]) CK(cudaFree(g_finish[dev]));
+            g_finish[dev] = nullptr;
+            g_finish_cap[dev] = 0;
+            CK(cudaMalloc(&g_finish[dev], need));
+            g_finish_cap[dev] = need;
+        }
+        CK(cudaMemsetAsync(g_finish[dev], 0xff, need, st));
+        g_finish_B[dev] = P.B;
+        Q.finish_ns = g_finish[dev];
+    }
     // device-side work counter: chains beyond the first wave are claimed dynamically
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
     if (time_begin(st)) return 1;
@@ -587,6 +604,18 @@ int gbp_release_host_buffers(void)
                 g_arena[dev].ptr[s] = nullptr;
                 g_arena[dev].cap[s] = 0;
             }
+    return 0;
+}
+
+int gbp_debug_finish_times(double* out_ms, int n)
+{
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!g_finish[dev] || n > g_finish_B[dev]) return fail("no timeline recorded (set GBP_DEBUG_TIMELINE before the run)");
+    std::vector<unsigned long long> h((size_t)g_finish_B[dev] + 1);
+    CK(cudaMemcpy(h.data(), g_finish[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const unsigned long long t0 = h[g_finish_B[dev]];
+    for (int i = 0; i < n; ++i) out_ms[i] = (double)(h[i] - t0) * 1e-6;
     return 0;
 }
 

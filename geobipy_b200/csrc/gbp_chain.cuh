@@ -133,6 +133,7 @@ struct ChainParams {
     int spec_min_rejections; // a chain speculates once it has rejected this many steps in a row
     int* work_counter;
     void* jstore;            // [B][NC*KS] of T: Jacobian of each chain's current model
+    unsigned long long* finish_ns;  // debug (GBP_DEBUG_TIMELINE): [B + 1] %globaltimer at the end of each chain, [B] = earliest start
 };
 
 template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c)
@@ -1639,6 +1640,11 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
 
     ch_write_model(w, ml, k, mcur, vcur, P.out.cur_sigma ? P.out.cur_sigma + (size_t)chain * ml : nullptr,
                    P.out.cur_edges ? P.out.cur_edges + (size_t)chain * (ml + 1) : nullptr);
+    if (lane == 0 && P.finish_ns) {
+        unsigned long long tnow;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+        P.finish_ns[chain] = tnow;
+    }
     if (lane == 0) {
         double* s = P.out.scalars + (size_t)chain * GBP_NSCALARS;
 #pragma unroll 1
@@ -1742,6 +1748,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     __syncthreads();
     if (lane == 0 && c < P.B) atomicAdd(&n_alive, 1);
     __syncthreads();
+    if (threadIdx.x == 0 && P.finish_ns) {
+        unsigned long long tnow;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+        atomicMin(P.finish_ns + P.B, tnow);
+    }
     TailCtx<R, T, ns_of(KIND)> tc;
     tc.rounds = rounds;
     tc.mailbox = mailbox;

@@ -157,6 +157,9 @@ int gbp_measure_peaks(double *fp32_tflops, double *mufu_gops);
  * (16 counters, see gbp_chain.cuh g_diag: [8] iterations committed from speculation, [9] rounds, ...).  The only
  * outputs that depend on scheduling; synchronises the device */
 int gbp_debug_counters(unsigned long long *out16, int reset);
+/* with the environment variable GBP_DEBUG_TIMELINE set, the sampler records when each chain of the last launch
+ * on the current device finished; out_ms[i] = milliseconds after the start of the kernel (synchronises) */
+int gbp_debug_finish_times(double *out_ms, int n);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t gbp_launch_count(void);
 /* mean duration [ms] and launch count of the last gbp_rjmcmc_run / forward kernel, measured with CUDA
