@@ -484,10 +484,16 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
     cudaStream_t st = (cudaStream_t)stream;
     const bool small = P.C <= 12;
     const SysDev& sd = tc->host.dev;
-    // fp32: 28 chains per SM (148 x 28 = 4144 resident chains: BASELINE configs[1] is one wave); fp64: 8 per SM
+    // fp32: 16 chains per SM; fp64: 8 per SM
     if (precision == GBP_PRECISION_F32) {
         const size_t tb = (size_t)TAB_ROWS * sd.tab_stride * sizeof(float);
-        return small ? launch_chain<float, float, 12, 28, KIND_FDEM>(sd, tc->d_f32, tb, P, st)
+        // resident chains per SM: 16 (128 registers).  The SM's throughput saturates at ~16 warps (full waves of
+        // equal-length chains: 16 -> 34.7 M, 28 -> 36.6 M evals/s), and fewer, faster chains shorten the tail of real
+        // batches: 4096 soundings to termination 16: 1936 ms, 20: 2019, 24: 2086, 28: 2163 (profiles/README.md);
+        // 8192 and 16384 soundings: equal.  GBP_FDEM_WARPS=28 selects the 72-register build.
+        const char* e = std::getenv("GBP_FDEM_WARPS");
+        if (small && e && std::atoi(e) == 28) return launch_chain<float, float, 12, 28, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
+        return small ? launch_chain<float, float, 12, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st)
                      : launch_chain<float, float, GBP_MAXC, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
     }
     if (precision == GBP_PRECISION_F64) {
