@@ -842,8 +842,9 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
         P.opt.add_init2 *= TD_F32_SCALE;
         P.opt.add_min2 *= TD_F32_SCALE;
         P.opt.add_max2 *= TD_F32_SCALE;
-        // 16 chains per SM (128 registers); 18 (113 registers) was measured slower: 18.9 M vs 20.5 M evals/s
-        return launch_chain<float, float, 48, 16, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
+        // 12 chains per SM (to termination, scripts/gpu_tdem_warps.py: 4096 soundings 12: 3157 ms, 16: 3437, 8: 3656;
+        // 8192 soundings 12: 5312 ms, 16: 5505, 8: 6243; 18 chains per SM at 113 registers spill and are slower still)
+        return launch_chain<float, float, 48, 12, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
     }
     if (precision == GBP_PRECISION_F64)
         return launch_chain<double, double, 48, 8, KIND_TDEM>(sd, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
