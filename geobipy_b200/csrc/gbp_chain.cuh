@@ -1,4 +1,5 @@
-// One warp = one Markov chain: the fused trans-dimensional MCMC sampler for one FDEM sounding.
+// One warp = one Markov chain: the fused trans-dimensional MCMC sampler for one sounding - a frequency-domain
+// datapoint (FdemDataPoint, KIND_FDEM) or a time-domain one with one or two systems (TdemDataPoint, KIND_TDEM).
 //
 // Replaces the Python loop Inference1D.initialize + infer (geobipy/src/inversion/Inference1D.py:353-464,
 // :537-631 accept_reject, :633-688 infer, :705-790 update) together with everything it calls:
@@ -6,6 +7,7 @@
 //   Model.stochastic_newton_perturbation classes/model/Model.py:368-419 (+ :250-272, :347-357, :421-430)
 //   Model.probability / gradient_probability / proposal_probabilities  Model.py:533-575, :213-234, :577-660
 //   DataPoint.std / data_misfit / likelihood / probability / perturb   classes/data/datapoint/DataPoint.py
+//   TdemDataPoint.std (per-system errors, additive error x (t / 1 ms)^-1/2)  classes/data/datapoint/TdemDataPoint.py:329-379
 //   Model.update_parameter_posterior, RectilinearMesh1D.update_posteriors, EmDataPoint.update_posteriors
 //
 // Design
@@ -25,7 +27,10 @@
 //    later one were bound by instruction fetch, `stall_no_instruction`): helpers that are called from
 //    several places are single non-inlined copies taking shared-memory pointers; the once-per-iteration
 //    control code is inlined into the kernel so that its state stays in registers and the options come
-//    from the constant bank; cold per-chain counters live in shared memory.
+//    from the constant bank; cold per-chain counters live in shared memory;
+//  * every accept_reject step draws from its own Philox sub-stream, so warps that have run out of chains
+//    evaluate FUTURE iterations of the chains still running on their SM speculatively ("speculative evaluation"
+//    below): bit-identical results, the tail of a batch shrinks by a third.
 #pragma once
 #include "gbp_fdem.cuh"
 #include "gbp_fdem_f2.cuh"
