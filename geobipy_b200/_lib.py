@@ -88,7 +88,7 @@ EXPORTS = (
     "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times",
     "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
-    "gbp_rjmcmc_run", "gbp_rjmcmc_run_host", "gbp_release_host_buffers",
+    "gbp_rjmcmc_run", "gbp_rjmcmc_run_host", "gbp_release_host_buffers", "gbp_summarise_hitmap",
     "gbp_tdem_n_channels", "gbp_tdem_window_operator", "gbp_tdem_flops_per_forward",
     "gbp_tdem_forward", "gbp_tdem_sensitivity", "gbp_tdem_forward_host", "gbp_tdem_sensitivity_host",
     "gbp_tdem_rjmcmc_run", "gbp_tdem_rjmcmc_run_host",
@@ -140,6 +140,8 @@ def load():
     lib.gbp_mufu_per_forward.argtypes = [vp, i32]
     lib.gbp_tdem_mufu_per_forward.restype = dbl
     lib.gbp_tdem_mufu_per_forward.argtypes = [vp, i32]
+    lib.gbp_summarise_hitmap.restype = i32
+    lib.gbp_summarise_hitmap.argtypes = [vp, i32, i32, i32, vp, dbl, vp, i32, vp, vp, vp]
     lib.gbp_release_host_buffers.restype = i32
     lib.gbp_debug_finish_times.restype = i32
     lib.gbp_debug_finish_times.argtypes = [vp, i32]

@@ -298,6 +298,57 @@ __global__ void __launch_bounds__(256) peak_mufu_kernel(float* out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// ---- posterior summaries: per depth cell mean and percentiles of ln(sigma) from a hitmap
+// [B][n_sig][n_depth] (depth contiguous).  One thread per (sounding, depth cell): consecutive threads read
+// consecutive depth cells of one sigma row, so every load is coalesced; HBM bound (the hitmaps are read once from
+// HBM, the second pass over a column mostly hits L2).  Mesh._mean / Mesh._percentile (classes/mesh/Mesh.py:80,
+// :173-217): the percentile is the centre of the first bin whose cumulative count reaches p % of the column total.
+constexpr int SUMM_MAXP = 8;
+struct SummParams {
+    int B, n_sig, n_depth, n_pct;
+    double dx;
+    double pct[SUMM_MAXP];
+};
+template <int NP>
+__global__ void __launch_bounds__(256) summarise_kernel(const int32_t* __restrict__ hitmap, const double* __restrict__ sig_lo,
+                                                         const __grid_constant__ SummParams P, double* __restrict__ mean,
+                                                         double* __restrict__ pct)
+{
+    const long long n = (long long)P.B * P.n_depth;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / P.n_depth), j = (int)(i % P.n_depth);
+        const int32_t* col = hitmap + (size_t)b * P.n_sig * P.n_depth + j;
+        // integer inner loops (fp64 compares / conversions per element made the first version compute bound)
+        long long tot = 0;
+#pragma unroll 10
+        for (int s = 0; s < P.n_sig; ++s) tot += col[(size_t)s * P.n_depth];  // independent loads: 10 in flight per thread
+        const double totd = tot > 0 ? (double)tot : 1.0, lo = sig_lo[b];
+        long long thr[NP];  // cs < target  <=>  cs < ceil(target) for integer cs
+        int idx[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            thr[q] = (long long)ceil((P.pct[q] / 100.0) * totd);
+            idx[q] = 0;
+        }
+        long long cs = 0, wsum = 0;
+#pragma unroll 10
+        for (int s = 0; s < P.n_sig; ++s) {
+            const long long v = col[(size_t)s * P.n_depth];
+            cs += v;
+            wsum += v * s;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) idx[q] += (cs < thr[q]) ? 1 : 0;
+        }
+        const double acc = (double)tot * (lo + 0.5 * P.dx) + (double)wsum * P.dx;
+        mean[i] = acc / totd;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int k = idx[q] < P.n_sig - 1 ? idx[q] : P.n_sig - 1;
+            pct[(size_t)q * n + i] = lo + ((double)k + 0.5) * P.dx;
+        }
+    }
+}
+
 int* g_counter[64] = {nullptr};
 int get_counter(int** out)
 {
@@ -597,6 +648,37 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                                 return gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
                                                       precision, nullptr);
                             });
+}
+
+int gbp_summarise_hitmap(const int32_t* d_hitmap, int B, int n_sig, int n_depth, const double* d_sig_lo, double dx,
+                         const double* percentiles, int n_pct, double* d_mean, double* d_pct, void* stream)
+{
+    if (B <= 0) return 0;
+    if (n_pct < 1 || n_pct > SUMM_MAXP) return fail("1 to 8 percentiles");
+    if (n_sig < 1 || n_depth < 1) return fail("invalid hitmap shape");
+    SummParams P;
+    P.B = B;
+    P.n_sig = n_sig;
+    P.n_depth = n_depth;
+    P.n_pct = n_pct;
+    P.dx = dx;
+    for (int q = 0; q < SUMM_MAXP; ++q) P.pct[q] = q < n_pct ? percentiles[q] : 0.0;
+    const long long n = (long long)B * n_depth;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (time_begin(st)) return 1;
+    switch (n_pct) {
+#define GBP_SUMM_CASE(NP) case NP: summarise_kernel<NP><<<(int)blocks, 256, 0, st>>>(d_hitmap, d_sig_lo, P, d_mean, d_pct); break;
+        GBP_SUMM_CASE(1) GBP_SUMM_CASE(2) GBP_SUMM_CASE(3) GBP_SUMM_CASE(4) GBP_SUMM_CASE(5) GBP_SUMM_CASE(6) GBP_SUMM_CASE(7)
+        GBP_SUMM_CASE(8)
+#undef GBP_SUMM_CASE
+        default: summarise_kernel<1><<<(int)blocks, 256, 0, st>>>(d_hitmap, d_sig_lo, P, d_mean, nullptr); break;
+    }
+    g_launches++;
+    CK(cudaGetLastError());
+    return time_end(st);
 }
 
 int gbp_release_host_buffers(void)

@@ -376,3 +376,22 @@ def debug_counters(reset=False):
 def release_host_buffers():
     """Free the device buffers the numpy (host-pointer) path of rjmcmc_run keeps between calls."""
     _lib.check(_lib.load().gbp_release_host_buffers())
+
+
+def summarise_hitmap(hitmap, sig_lo, dx, percentiles=(5.0, 50.0, 95.0)):
+    """Per-depth-cell mean and percentiles of ln(sigma) of hitmaps [B, n_sig, n_depth] (torch CUDA int32) with the
+    hand-written kernel behind gbp_summarise_hitmap.  sig_lo [B] = ln(sigma) at the lower edge of bin 0 (torch CUDA
+    float64), dx = bin width in ln(sigma).  Returns (mean [B, n_depth], pct [n_pct, B, n_depth])."""
+    import torch
+    lib = _lib.require_cuda()
+    assert hitmap.is_cuda and hitmap.dtype == torch.int32 and hitmap.is_contiguous()
+    B, ns, nd = hitmap.shape
+    sig_lo = sig_lo.to(torch.float64).contiguous()
+    p = np.ascontiguousarray(percentiles, dtype=np.float64)
+    mean = torch.empty((B, nd), dtype=torch.float64, device=hitmap.device)
+    pct = torch.empty((p.size, B, nd), dtype=torch.float64, device=hitmap.device)
+    st = torch.cuda.current_stream(hitmap.device).cuda_stream
+    with torch.cuda.device(hitmap.device):
+        _lib.check(lib.gbp_summarise_hitmap(hitmap.data_ptr(), B, ns, nd, sig_lo.data_ptr(), float(dx), p.ctypes.data, int(p.size),
+                                            mean.data_ptr(), pct.data_ptr(), st))
+    return mean, pct

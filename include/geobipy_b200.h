@@ -199,6 +199,13 @@ int gbp_rjmcmc_run(const gbp_fdem_system *sys, const gbp_options *opt, int B, co
 int gbp_rjmcmc_run_host(const gbp_fdem_system *sys, const gbp_options *opt, int B, const double *data,
                         const double *altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
                         const gbp_chain_buffers *h_buf, int precision, int device);
+/* Posterior summaries of hitmaps on the device (replaces Mesh._mean / Mesh._percentile per sounding,
+ * geobipy/src/classes/mesh/Mesh.py:80, :173-217, as used by Inference2D's mean / percentile sections):
+ * d_hitmap [B][n_sig][n_depth]; sigma bin s of sounding b spans ln(sigma) in d_sig_lo[b] + [s, s+1) * dx.
+ * d_mean [B][n_depth]; d_pct [n_pct][B][n_depth] = centre of the first bin whose cumulative count reaches p %
+ * of the column total, in ln(sigma).  DEVICE pointers, stream ordered; at most 8 percentiles. */
+int gbp_summarise_hitmap(const int32_t *d_hitmap, int B, int n_sig, int n_depth, const double *d_sig_lo, double dx,
+                         const double *percentiles, int n_pct, double *d_mean, double *d_pct, void *stream);
 /* The *_rjmcmc_run_host entry points keep their device buffers between calls (per device); this frees them. */
 int gbp_release_host_buffers(void);
 

@@ -359,3 +359,29 @@ def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, mon
         assert nspec[helpers] > 0.05 * r["scalars"][:, _lib.S_TOTAL_ITER].sum()
         for name in ref:
             assert np.array_equal(ref[name], r[name], equal_nan=True), (kind, helpers, name)
+
+
+def test_summarise_kernel_matches_host_reference(gpu):
+    """gbp_summarise_hitmap (hand-written, one thread per depth cell) against the torch/numpy statement of
+    Mesh._mean / Mesh._percentile (geobipy_b200/parallel.py CPU branch; reference classes/mesh/Mesh.py:80, :173-217)."""
+    import torch
+    from geobipy_b200.parallel import summarise_hitmap
+    rng = np.random.default_rng(4)
+    B, ns, nd = 37, 250, 440
+    h = rng.integers(0, 40, (B, ns, nd)).astype(np.int32)
+    h[3] = 0                                   # an empty hitmap (failed chain)
+    h[5, :, 7] = 0
+    h[6, 100:, :] = 0
+    edges = np.linspace(-9.6, 9.6, ns + 1) + 0.3
+    cpu = summarise_hitmap(torch.tensor(h), torch.tensor(edges))
+    dev = summarise_hitmap(torch.tensor(h, device="cuda"), torch.tensor(edges, device="cuda"))
+    torch.cuda.synchronize()
+    for k in cpu:
+        assert torch.allclose(dev[k].cpu(), cpu[k], rtol=1e-12, atol=1e-12), k
+    # per-sounding bin origins (ln sigma_ref differs per sounding)
+    lo = torch.tensor(rng.uniform(-8, -3, B), device="cuda")
+    mean, pct = gpu.summarise_hitmap(torch.tensor(h, device="cuda"), lo, 0.0768, (50.0,))
+    mean0, pct0 = gpu.summarise_hitmap(torch.tensor(h, device="cuda"), torch.zeros(B, dtype=torch.float64, device="cuda"), 0.0768, (50.0,))
+    nz = torch.tensor(h.sum(axis=1) > 0, device="cuda")
+    assert torch.allclose((mean - mean0)[nz], lo.unsqueeze(1).expand(B, nd)[nz], atol=1e-9)
+    assert torch.allclose(pct[0] - pct0[0], lo.unsqueeze(1).expand(B, nd), atol=1e-12)
