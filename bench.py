@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--soundings", type=int, default=SOUNDINGS_PER_GPU, help="soundings per GPU")
     ap.add_argument("--chains", type=int, default=N_MARKOV_CHAINS, help="n_markov_chains")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
-    ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem"])
+    ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -83,6 +83,11 @@ class Workload:
 
 
 def workload_config(args, world):
+    if args.workload == "mixed":
+        return {"workload": "BASELINE configs[4] family: mixed flight line, %d soundings per GPU, even = RESOLVE FDEM, odd = SkyTEM TDEM, "
+                            "n_markov_chains=%d" % (args.soundings, args.chains), "soundings_per_gpu": args.soundings,
+                "soundings_total": args.soundings * world, "n_markov_chains": args.chains,
+                "options": "resolve_options / skytem_options", "parallelism": "shard%d" % world}
     if args.workload == "skytem":
         nd = 1209
         return {
@@ -155,15 +160,19 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     n_chains = cores
     max_it = 4000  # bounded sample: first 4000 iterations of `cores` chains per step (~2-4 s per step)
-    _observed_cpu(1, args.workload)
+    kinds = ("resolve", "skytem") if args.workload == "mixed" else (args.workload,)
+    for k in kinds:
+        _observed_cpu(1, k)
     with mp.get_context("spawn").Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_sample(args.chains, n_chains, 500, pool, args.workload)
+            for k in kinds:
+                cpu_sample(args.chains, n_chains, 500, pool, k)
         its, secs = 0.0, 0.0
         for _ in range(args.steps):
-            i, s = cpu_sample(args.chains, n_chains, max_it, pool, args.workload)
-            its += i
-            secs += s
+            for k in kinds:  # a mixed line: the same number of soundings of each kind
+                i, s = cpu_sample(args.chains, n_chains, max_it, pool, k)
+                its += i
+                secs += s
     value = its / secs
     sample = "%d chains (soundings 0..%d of the workload) x first %d iterations per step, one process per core" % (n_chains, n_chains - 1, max_it)
     line = {
@@ -424,10 +433,130 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+def run_mixed_arm(args):
+    """BASELINE configs[4] family: a mixed flight line - even soundings RESOLVE FDEM, odd soundings SkyTEM TDEM -
+    with posterior hitmaps and interface probabilities (edges histogram / sum, Inference2D.py:959-961) accumulated
+    per sounding.  The two sampler kernels are both persistent (one CTA per SM), so a step runs them back to back on
+    one stream.  Not the default bench line; prints the same JSON shape without the roofline block."""
+    import torch
+    import torch.distributed as dist
+    from geobipy_b200 import _lib, ops
+    from geobipy_b200.synthetic import synthetic_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.soundings
+    tdt = {np.int32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}
+    outputs = ("hitmap", "edges_hist", "ncells_hist", "scalars")
+    parts = []
+    for name, parity in (("resolve", 0), ("skytem", 1)):
+        wl = Workload(name)
+        system, opt = wl.product(args.chains)
+        idx = np.arange(rank * B + parity, (rank + 1) * B, 2)       # global sounding indices of this kind on this rank
+        sb = [synthetic_batch(int(i), 1, **wl.synth) for i in idx]
+        cat = {k: np.concatenate([b[k] for b in sb]) for k in sb[0]}
+        t = {k: torch.tensor(v, device=dev) for k, v in cat.items()}
+        clean = ops.forward(system, t["nlayers"], t["sigma"], t["thickness"], t["height"], precision=64)
+        data = (clean + t["noise"] * wl.noise_std(clean, torch)).contiguous()
+        shapes = ops.chain_buffer_shapes(opt, len(idx))
+        bufs = {n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]], device=dev) for n in outputs}
+        parts.append(dict(wl=wl, system=system, opt=opt, data=data, alt=t["height"], bufs=bufs, n=len(idx), first=int(idx[0])))
+    iters_dev = torch.zeros((), dtype=torch.float64, device=dev)
+
+    def step(i, count=True):
+        out = []
+        for p in parts:
+            # sounding index of the random stream: position within this kind's list (streams stay sharding independent)
+            r = ops.rjmcmc_run(p["system"], p["opt"], p["data"], p["alt"], seed=SEED + i, first_index=p["first"] // 2,
+                               precision=args.precision, outputs=outputs, buffers=p["bufs"])
+            if count:
+                iters_dev.add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+            # interface probability per sounding (Inference2D.interface_probability)
+            e = r["edges_hist"].to(torch.float64)
+            out.append((r, e / e.sum(dim=1, keepdim=True).clamp_min(1.0)))
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(1000 + i, count=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        res = step(i)
+    ev1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    iters = iters_dev.clone().reshape(1)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(iters, op=dist.ReduceOp.SUM)
+    # e2e through the host-pointer API (both kinds), one step
+    h = [dict(data=p["data"].cpu().numpy(), alt=p["alt"].cpu().numpy()) for p in parts]
+    h2d = sum(x["data"].nbytes + x["alt"].nbytes for x in h)
+    for p in parts:
+        for b in p["bufs"].values():
+            b.resize_(0)
+    del res
+    torch.cuda.empty_cache()
+    barrier()
+    t0 = time.perf_counter()
+    e_iters, d2h = 0.0, 0
+    for p, x in zip(parts, h):
+        r = ops.rjmcmc_run(p["system"], p["opt"], x["data"], x["alt"], seed=SEED, first_index=p["first"] // 2,
+                           precision=args.precision, device=local_rank, outputs=outputs)
+        e_iters += float(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+        d2h += sum(v.nbytes for v in r.values())
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    ei = torch.tensor([e_iters], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ei, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        total_ms = float(ms.item())
+        line = {
+            "metric": METRIC, "value": float(iters.item()) / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4] family: mixed flight line, %d soundings per GPU, even = RESOLVE FDEM, odd = SkyTEM TDEM, "
+                                   "n_markov_chains=%d, posterior hitmaps + interface probabilities" % (B, args.chains),
+                       "soundings_per_gpu": B, "soundings_total": B * world, "n_markov_chains": args.chains,
+                       "options": "resolve_options / skytem_options", "parallelism": "shard%d" % world,
+                       "l2": "no flush needed: each step rewrites GBs of posterior arrays per GPU (> 126 MB L2)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": float(ei.item()) / float(el.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": 1, "api": "geobipy_b200.ops.rjmcmc_run(numpy), one call per datapoint kind"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "mixed":
+        run_mixed_arm(args)
     else:
         run_b200_arm(args)
 
