@@ -349,3 +349,28 @@ def test_tdem_chain_statistics_match_reference_chains(oracle, golden_dir):
         rr = sum(r[name].astype(np.int64) for r in refs)
         oo = sum(r[name].astype(np.int64) for r in runs)
         assert np.all(np.abs((rr * b).sum(axis=1) / rr.sum(axis=1) - (oo * b).sum(axis=1) / oo.sum(axis=1)) < 2.0), name
+
+
+def test_tdem_chain_invariants(oracle, golden_dir):
+    """Book-keeping identities of a time-domain oracle chain (dual moment, per-system error histograms)."""
+    g = np.load(os.path.join(golden_dir, "ref_tdem_chain_2.npz"))
+    s, o = oracle.make_tdem_system(), oracle.skytem_options(n_markov_chains=1500, burn_in_min_iter=500, update_plot_every=500)
+    r = oracle.run_chain(s, o, g["data"], float(g["altitude"]), 3, 2)
+    sc = r["scalars"]
+    it = int(sc[oracle.S_ITER])
+    nd = r["hitmap"].shape[1]
+    assert nd == 1209 and r["rel_hist"].shape == (2, 99)
+    counted = it - int(sc[oracle.S_BURNED_IN_ITER]) + 1 if sc[oracle.S_BURNED_IN] else it
+    assert r["hitmap"].sum() == counted * nd and (r["hitmap"].sum(axis=0) == counted).all()
+    assert r["ncells_hist"].sum() == counted
+    assert (r["rel_hist"].sum(axis=1) == counted).all() and (r["add_hist"].sum(axis=1) == counted).all()
+    assert int(sc[oracle.S_N_BIRTH] + sc[oracle.S_N_DEATH] + sc[oracle.S_N_MOVE] + sc[oracle.S_N_NONE]) == it
+    assert r["accept_trace"][: it + 1].sum() == sc[oracle.S_N_ACCEPT]
+    for k in (oracle.S_CUR_REL, oracle.S_CUR_REL2):
+        assert 0.005 <= sc[k] <= 0.5
+    for k in (oracle.S_CUR_ADD, oracle.S_CUR_ADD2):
+        assert 1e-16 <= sc[k] <= 1e-10
+    # same seed and sounding index -> identical chain; another sounding index -> another stream
+    r2 = oracle.run_chain(s, o, g["data"], float(g["altitude"]), 3, 2)
+    r3 = oracle.run_chain(s, o, g["data"], float(g["altitude"]), 3, 5)
+    assert np.array_equal(r["hitmap"], r2["hitmap"]) and not np.array_equal(r["accept_trace"], r3["accept_trace"])
