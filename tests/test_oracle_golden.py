@@ -359,7 +359,7 @@ def test_tdem_chain_statistics_match_reference_chains(oracle, golden_dir):
     med = _summary(sum(r["hitmap"].astype(np.int64) for r in runs)[:, :200])
     inside = (med >= ref_med.min(axis=0) - 2) & (med <= ref_med.max(axis=0) + 2)
     assert inside.mean() >= 0.9, med
-    _extra_posterior_checks(refs, runs, 200, (0.7, 0.9))   # the 5 % profile of a 6-chain ensemble is noisy: 0.74 - 1.0 by seed set
+    _extra_posterior_checks(refs, runs, 200, (0.7, 0.8))   # tails of a 6-chain ensemble are noisy: 0.74 - 1.0 by seed set
     # data misfit after burn-in centred on the number of active channels (the reference's chi-squared criterion,
     # Inference1D.py:414-419, :713): reference chains 35-39, oracle chains 34-41 for 45 channels
     for r in runs:
