@@ -385,3 +385,42 @@ def test_summarise_kernel_matches_host_reference(gpu):
     nz = torch.tensor(h.sum(axis=1) > 0, device="cuda")
     assert torch.allclose((mean - mean0)[nz], lo.unsqueeze(1).expand(B, nd)[nz], atol=1e-9)
     assert torch.allclose(pct[0] - pct0[0], lo.unsqueeze(1).expand(B, nd), atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["fdem", "tdem"])
+def test_ten_thousand_random_models_fp32_vs_fp64(gpu, systems, oracle, kind):
+    """the fp32 kernels over >= 10^4 random models spanning sigma in [1e-4, 10] S/m and L in [1, 30],
+    against the fp64 kernels (the oracle's twins; a 200-model subset is checked against the oracle itself)."""
+    rng = np.random.default_rng(77)
+    B = 10240
+    nl = rng.integers(1, 31, B).astype(np.int32)
+    sig = 10.0 ** rng.uniform(-4.0, 1.0, (B, 30))
+    thk = 10.0 ** rng.uniform(0.0, 2.0, (B, 30))
+    alt = rng.uniform(25.0, 45.0, B)
+    if kind == "fdem":
+        system, osys, fwd = systems[0], systems[1], oracle.fdem_forward
+    else:
+        system, osys, fwd = gpu.skytem_survey_struct(), oracle.make_tdem_system(), oracle.tdem_forward
+    p64, J64 = gpu.forward(system, nl, sig, thk, alt, precision=64, sensitivity=True)
+    p32, J32 = gpu.forward(system, nl, sig, thk, alt, precision=32, sensitivity=True)
+    for b in range(0, B, B // 200):
+        L = int(nl[b])
+        ref = fwd(osys, alt[b], sig[b, :L], thk[b, :L])
+        assert np.all(np.abs(p64[b] - ref) <= 1e-7 * np.abs(ref) + (5e-8 if kind == "fdem" else 1e-24)), b
+    if kind == "fdem":
+        assert fwd_ok(p32, p64, F32_FWD)
+        err = np.abs(J32 - J64).max(axis=(1, 2)) / np.abs(J64).max(axis=(1, 2))
+        assert err.max() < 5 * F32_J and np.median(err) < F32_J / 10
+    else:
+        t = np.array(osys.t_centre[:45])
+        floor = np.r_[np.full(26, 2e-14), np.full(19, 2e-13)] * np.sqrt(1e-3 / t)
+        sn = np.sqrt((0.05 * p64) ** 2 + floor ** 2)
+        assert np.all(np.abs(p32 - p64) <= 2e-4 * np.abs(p64) + 0.01 * sn)
+        assert np.median(np.abs(p32 / p64 - 1.0)) < 2e-6
+        # Jacobian rows: 3 % of the row maximum, with an absolute floor of 1e-3 noise standard deviations (rows of
+        # late windows over resistive ground are orders of magnitude below the noise; d/d ln(sigma) has the data's units)
+        rowmax = np.abs(J64).max(axis=2)
+        dJ = np.abs(J32 - J64).max(axis=2)
+        ok = dJ <= 3e-2 * rowmax + 1e-3 * sn
+        assert ok.all(), (float((dJ / (3e-2 * rowmax + 1e-3 * sn)).max()), int((~ok).sum()))
+        assert np.median(dJ / rowmax) < 1e-4
