@@ -149,7 +149,8 @@ class Inference3D:
     """Survey driver: `Inference3D(data).infer(**options)` (inversion/Inference3D.py:451-492, :503-635)."""
 
     def __init__(self, data, prng=None, seed=None, world=None):
-        assert isinstance(data, FdemData), TypeError("data must be a FdemData")
+        from .tdem import TdemData
+        assert isinstance(data, (FdemData, TdemData)), TypeError("data must be a FdemData or a TdemData")
         self.data = data
         if seed is None:
             seed = int(prng.integers(0, 2 ** 63 - 1)) if prng is not None else 0
@@ -167,7 +168,7 @@ class Inference3D:
         sel = np.arange(d.nPoints) if index is None else np.atleast_1d(index)
         opt = ops.make_options(**options)
         self.options = opt
-        sysc = d.system.c_struct
+        sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct   # time-domain surveys: systems + tx-rx offset
         if sharded:
             from . import parallel
             res = parallel.run_sharded(sysc, opt, d.data[sel], d.z[sel], seed=self.seed, precision=precision,

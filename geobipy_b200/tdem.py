@@ -293,6 +293,19 @@ class TdemData:
     def nChannels(self):
         return self.data.shape[1]
 
+    # names the survey driver (dataset.Inference3D) shares with FdemData
+    @property
+    def z(self):
+        return self.height
+
+    @property
+    def lineNumber(self):
+        return self.line_number
+
+    @property
+    def c_struct(self):
+        return self.survey_struct()
+
     def survey_struct(self):
         """One gbp_tdem_survey for the whole file: the GPU path needs a constant tx->rx offset and zero attitudes."""
         g = self.geometry

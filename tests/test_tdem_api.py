@@ -152,3 +152,28 @@ def test_inference1d_with_skytem_datapoint(stm_files, golden_dir, built_lib):
     assert np.all((top > 0.004) & (top < 0.025)), top
     with pytest.raises(AssertionError):   # scalar error options with a dual-moment datapoint
         api.Inference1D(prng=np.random.default_rng(0), interactive_plot=False, save_hdf5=True).initialize(dp)
+
+
+@pytest.mark.gpu
+def test_inference3d_time_domain_survey(stm_files, tmp_path, golden_dir, built_lib):
+    """The survey driver (Inference3D.infer / save) on a time-domain CSV in the reference layout."""
+    from geobipy_b200 import _lib, ops, tdem
+    from geobipy_b200.dataset import Inference3D
+    _lib.require_cuda()
+    g = np.load(os.path.join(golden_dir, "skytem_clean.npz"))
+    hdr = ("Line_number,Fiducial,Easting,Northing,Height,Elevation,tx_pitch,tx_roll,tx_yaw,txrx_dx,txrx_dy,txrx_dz,rx_pitch,rx_roll,rx_yaw,"
+           + ",".join("S0Z_time_%.3e" % t for t in g["times"][:26]) + "," + ",".join("S1Z_time_%.3e" % t for t in g["times"][26:]))
+    rows = [hdr]
+    for i in range(4):
+        rows.append(",".join(repr(float(v)) for v in [100.0 + (i // 2), i, float(i), 0.0, 30.0, 0.0, 0, 0, 0, -13.0, 0.0, 2.0, 0, 0, 0] + list(g["data"][0, 10 * i])))
+    f = tmp_path / "skytem_glacial_clean.csv"
+    f.write_text("\n".join(rows) + "\n")
+    ds = tdem.TdemData.read_csv(str(f), [p for p, _ in stm_files])
+    inv = Inference3D(ds, seed=3)
+    r = inv.infer(n_markov_chains=400, max_iterations=200, **{k: v for k, v in ops.SKYTEM_OPTIONS.items()})
+    assert r["hitmap"].shape == (4, 250, 1209) and (r["scalars"][:, _lib.S_ITER] == 200).all()
+    assert r["rel_hist"].shape == (4, 2, 99) and r["summary_p50"].shape == (4, 1209)
+    one = Inference3D(ds, seed=3).infer(index=2, n_markov_chains=400, max_iterations=200, **{k: v for k, v in ops.SKYTEM_OPTIONS.items()})
+    assert np.array_equal(one["hitmap"][0], r["hitmap"][2])        # (seed, sounding index) fixes the stream
+    files = inv.save(str(tmp_path / "out"))
+    assert [os.path.basename(x) for x in files] == ["100.npz", "101.npz"]
