@@ -44,6 +44,11 @@ typedef struct {
     int32_t n_systems;             /* 0/1: one system; 2: the *_2 fields below describe system 1 (skytem_options lists) */
     double rel_init2, rel_min2, rel_max2, rel_prop_var2;
     double add_init2, add_min2, add_max2, add_prop_var2;
+    /* solve_z (Point.set_priors :959-961, set_proposals :977-979): sensor height sampled with a Uniform prior
+     * [z0 - max_height_change, z0 + max_height_change] and a Normal(z, height_prop_var) random walk */
+    int32_t solve_height;
+    int32_t pad_h_;
+    double max_height_change, height_prop_var;
 } gbo_options;
 
 /* One time-domain datapoint type = n_sys GA-AEM style systems sharing one transmitter/receiver geometry
@@ -75,6 +80,7 @@ typedef struct {
     double *cur_sigma;      /* [max_layers] */
     double *cur_edges;      /* [max_layers + 1] */
     double *scalars;        /* [GBO_NSCALARS], see below */
+    int32_t *height_hist;   /* [n_err_bins] (Point.set_z_posterior :1013-1020), may be NULL unless solve_height */
 } gbo_chain_out;
 
 enum {
@@ -83,6 +89,7 @@ enum {
     GBO_S_CUR_REL, GBO_S_CUR_ADD, GBO_S_CUR_MISFIT, GBO_S_CUR_PRIOR, GBO_S_CUR_LIKELIHOOD,
     GBO_S_BEST_REL, GBO_S_BEST_ADD, GBO_S_N_RESETS, GBO_S_N_BIRTH, GBO_S_N_DEATH, GBO_S_N_MOVE, GBO_S_N_NONE, GBO_S_TOTAL_ITER,
     GBO_S_CUR_REL2, GBO_S_CUR_ADD2, GBO_S_BEST_REL2, GBO_S_BEST_ADD2,   /* system 1 of a dual-moment datapoint */
+    GBO_S_CUR_HEIGHT, GBO_S_BEST_HEIGHT,                                /* sensor height (solve_height) */
     GBO_NSCALARS = 32
 };
 
@@ -127,6 +134,9 @@ typedef struct {
     double newton_mean[GBO_MAXL];         /* exp(ln sigma_remap - alpha * A^-1 gradient) */
     double pred_test[GBO_MAXC];
     double misfit_test, prior_test, likelihood_test, proposal, proposal1;
+    /* input, read only when opt->solve_height: height of the proposed datapoint (altitude = the current one's),
+     * and the centre of the height prior */
+    double altitude_test, altitude_ref;
 } gbo_transition;
 
 int gbo_eval_transition(const gbo_fdem_system *sys, const gbo_options *opt, gbo_transition *t);

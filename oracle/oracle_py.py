@@ -20,7 +20,7 @@ NSCALARS = 32
 S_ITER, S_BURNED_IN, S_BURNED_IN_ITER, S_BEST_ITER, S_BEST_K, S_CUR_K, S_HALFSPACE, S_FAILED, S_N_ACCEPT, \
     S_N_FORWARD, S_N_SENS, S_BEST_POSTERIOR, S_CUR_REL, S_CUR_ADD, S_CUR_MISFIT, S_CUR_PRIOR, S_CUR_LIKELIHOOD, \
     S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER, \
-    S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2 = range(29)
+    S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2, S_CUR_HEIGHT, S_BEST_HEIGHT = range(31)
 
 
 class FdemSystemC(ctypes.Structure):
@@ -48,6 +48,8 @@ class OptionsC(ctypes.Structure):
         ("rel_prop_var2", ctypes.c_double),
         ("add_init2", ctypes.c_double), ("add_min2", ctypes.c_double), ("add_max2", ctypes.c_double),
         ("add_prop_var2", ctypes.c_double),
+        ("solve_height", ctypes.c_int32), ("pad_h_", ctypes.c_int32),
+        ("max_height_change", ctypes.c_double), ("height_prop_var", ctypes.c_double),
     ]
 
 
@@ -67,7 +69,7 @@ class TdemSystemC(ctypes.Structure):
 class ChainOutC(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "hitmap", "edges_hist", "ncells_hist", "rel_hist", "add_hist", "misfit_trace", "accept_trace",
-        "best_sigma", "best_edges", "cur_sigma", "cur_edges", "scalars")]
+        "best_sigma", "best_edges", "cur_sigma", "cur_edges", "scalars", "height_hist")]
 
 
 class TransitionC(ctypes.Structure):
@@ -84,6 +86,7 @@ class TransitionC(ctypes.Structure):
         ("newton_mean", ctypes.c_double * MAXL), ("pred_test", ctypes.c_double * MAXC),
         ("misfit_test", ctypes.c_double), ("prior_test", ctypes.c_double), ("likelihood_test", ctypes.c_double),
         ("proposal", ctypes.c_double), ("proposal1", ctypes.c_double),
+        ("altitude_test", ctypes.c_double), ("altitude_ref", ctypes.c_double),
     ]
 
 
@@ -158,6 +161,7 @@ def resolve_options(**over):
     o.add_init, o.add_min, o.add_max, o.add_prop_var = 5.0, 3.0, 20.0, 1e-6
     o.n_sigma_bins, o.n_err_bins, o.sigma_bins_nstd = 250, 99, 4.0
     o.burn_in_min_iter = 5000
+    o.solve_height, o.max_height_change, o.height_prop_var = 0, 1.0, 0.01   # solve_z is off in the shipped options
     for k, v in over.items():
         setattr(o, k, v)
     return o
@@ -207,7 +211,8 @@ def run_chain(sys, opt, data, altitude, seed, sounding_index, max_iterations=0):
         ncells_hist=np.zeros(opt.max_layers + 1, np.int32), rel_hist=np.zeros(eshape, np.int32),
         add_hist=np.zeros(eshape, np.int32), misfit_trace=np.zeros(N2), accept_trace=np.zeros(N2, np.uint8),
         best_sigma=np.zeros(opt.max_layers), best_edges=np.zeros(opt.max_layers + 1),
-        cur_sigma=np.zeros(opt.max_layers), cur_edges=np.zeros(opt.max_layers + 1), scalars=np.zeros(NSCALARS))
+        cur_sigma=np.zeros(opt.max_layers), cur_edges=np.zeros(opt.max_layers + 1), scalars=np.zeros(NSCALARS),
+        height_hist=np.zeros(opt.n_err_bins, np.int32))
     co = ChainOutC()
     for k, v in r.items():
         setattr(co, k, v.ctypes.data)
@@ -222,6 +227,8 @@ def eval_transition(sys, opt, **kw):
     t = TransitionC()
     k = int(kw["k"])
     t.k, t.action, t.altitude, t.sigma_ref = k, int(kw["action"]), float(kw["altitude"]), float(kw["sigma_ref"])
+    t.altitude_test = float(kw.get("altitude_test", kw["altitude"]))
+    t.altitude_ref = float(kw.get("altitude_ref", kw["altitude"]))
     tdem = isinstance(sys, TdemSystemC)
     C = sys.C if tdem else 2 * sys.n_freq
     for i in range(k + 1):

@@ -168,6 +168,7 @@ typedef struct {
     double pred[GBO_MAXC];
     double J[GBO_MAXC * GBO_MAXL]; /* row-major [C][k] */
     int Jk;                        /* columns of J */
+    double z;                      /* sensor height (Point.z); constant unless solve_height */
 } dpoint_t;
 
 static void model_thickness(const model_t *m, double *thk)
@@ -280,9 +281,11 @@ static double log_uniform_logpdf(double x, double mn, double mx)
 
 /* DataPoint.probability :351-395: multivariate Uniform(log=True) priors sum over the systems
  * (UniformDistribution.py:116) */
-static double datapoint_probability(const gbo_options *o, int n_sys, const double *rel, const double *add)
+static double datapoint_probability(const gbo_options *o, int n_sys, const double *rel, const double *add, double dz)
 {
+    /* Point.probability :160-196 first (height prior, dz = z - z_ref), then the errors (DataPoint.probability :352-389) */
     double p = 0.0;
+    if (o->solve_height) p += (dz >= -o->max_height_change && dz <= o->max_height_change) ? -log(2.0 * o->max_height_change) : -INFINITY;
     for (int s = 0; s < n_sys; ++s) {
         if (o->solve_relative_error) p += log_uniform_logpdf(rel[s], o_rel_min(o, s), o_rel_max(o, s));
         if (o->solve_additive_error) p += log_uniform_logpdf(add[s], o_add_min(o, s), o_add_max(o, s));
@@ -484,6 +487,21 @@ static double propose_error(rng_t *g, double cur, double prop_var, double mn, do
     return x;
 }
 
+/* Point.perturb :614-622 = StatArray.propose with imposePrior for the Normal(z, var) height random walk under the
+ * Uniform[z_ref - dz, z_ref + dz] prior (scipy uniform.logpdf: closed support) */
+static double propose_height(rng_t *g, double cur, double prop_var, double lo, double hi)
+{
+    double sd = sqrt(prop_var);
+    double x = cur + sd * rng_normal(g);
+    int tries = 0;
+    while (!(x >= lo && x <= hi)) {
+        x = cur + sd * rng_normal(g);
+        tries++;
+        if (tries == 10) return cur;
+    }
+    return x;
+}
+
 /* Same for a dual-moment datapoint: the 2-vector is proposed jointly (MvLogNormal, diagonal variance) and
  * re-drawn, at most 10 times, while ANY component leaves its prior; then the whole vector falls back
  * (StatArray.py:619-636).  One Box-Muller pair per draw. */
@@ -515,6 +533,7 @@ typedef struct {
     double sig_lo, sig_dx;   /* ln(sigma) bins */
     double rel_lo[GBO_MAXSYS], rel_dx[GBO_MAXSYS], add_lo[GBO_MAXSYS], add_dx[GBO_MAXSYS]; /* ln(err) bins */
     int n_sys;
+    double z_lo, z_dx;       /* height bins, relative to the height the prior was centred on */
 } grids_t;
 
 static void make_grids(const gbo_options *o, int n_sys, double sigma_ref, grids_t *G)
@@ -536,6 +555,9 @@ static void make_grids(const gbo_options *o, int n_sys, double sigma_ref, grids_
         G->add_lo[s] = log(o_add_min(o, s));
         G->add_dx[s] = (log(o_add_max(o, s)) - log(o_add_min(o, s))) / (double)G->n_err;
     }
+    /* Point.set_z_posterior :1013-1020: Uniform.bins = linspace(z0 - dz, z0 + dz, 100), mesh relative_to z0 */
+    G->z_lo = -o->max_height_change;
+    G->z_dx = 2.0 * o->max_height_change / (double)G->n_err;
 }
 
 /* searchsorted(edges, v, 'right') - 1 clipped, for uniform edges lo + i*dx */
@@ -569,8 +591,10 @@ static double staircase_value(const gbo_options *o, const model_t *m, double y)
 }
 
 static void accumulate_posteriors(const gbo_options *o, const grids_t *G, const model_t *m, const double *rel,
-                                  const double *add, gbo_chain_out *out)
+                                  const double *add, double dz, gbo_chain_out *out)
 {
+    /* height histogram (Point.update_posteriors :1022-1025); dz = z - z_ref */
+    if (o->solve_height && out->height_hist) out->height_hist[uniform_bin(dz, G->z_lo, G->z_dx, G->n_err)] += 1;
     /* nCells histogram (RectilinearMesh1D.py:1597) */
     out->ncells_hist[m->k] += 1;
     /* interface histogram (:1600-1610) with ratio = 0.5 */
@@ -607,6 +631,7 @@ static void reset_posteriors(const gbo_options *o, const grids_t *G, gbo_chain_o
     memset(out->ncells_hist, 0, sizeof(int32_t) * (o->max_layers + 1));
     memset(out->rel_hist, 0, sizeof(int32_t) * G->n_sys * G->n_err);
     memset(out->add_hist, 0, sizeof(int32_t) * G->n_sys * G->n_err);
+    if (o->solve_height && out->height_hist) memset(out->height_hist, 0, sizeof(int32_t) * G->n_err);
 }
 
 /* ------------------------------------------------------------------ the chain */
@@ -616,6 +641,7 @@ typedef struct {
     int C;
     double data[GBO_MAXC];
     double altitude;
+    double z_ref;      /* centre of the height prior: the datapoint's height when the priors were (re)set */
     double sigma_ref;
     grids_t G;
     rng_t rng;
@@ -626,33 +652,34 @@ typedef struct {
     int burned_in;
     int64_t burned_in_iter, best_iter;
     model_t best_model;
-    double best_rel[GBO_MAXSYS], best_add[GBO_MAXSYS], best_posterior;
+    double best_rel[GBO_MAXSYS], best_add[GBO_MAXSYS], best_z, best_posterior;
     int accepted;
     int n_zero_acc, n_resets, limiters;
     int64_t n_accept, n_forward, n_sens, n_act[4];
     int n_active;
 } chain_t;
 
-static void forward(chain_t *c, const model_t *m, double *pred)
+static void forward(chain_t *c, const model_t *m, double z, double *pred)
 {
     double thk[GBO_MAXL];
     model_thickness(m, thk);
-    if (c->sv.tdem) gbo_tdem_forward(c->sv.tdem, c->altitude, m->k, m->sigma, thk, pred);
-    else gbo_fdem_forward(c->sv.fdem, c->altitude, m->k, m->sigma, thk, pred);
+    if (c->sv.tdem) gbo_tdem_forward(c->sv.tdem, z, m->k, m->sigma, thk, pred);
+    else gbo_fdem_forward(c->sv.fdem, z, m->k, m->sigma, thk, pred);
     c->n_forward++;
 }
 static void sensitivity(chain_t *c, const model_t *m, dpoint_t *dp)
 {
     double thk[GBO_MAXL];
     model_thickness(m, thk);
-    if (c->sv.tdem) gbo_tdem_sensitivity(c->sv.tdem, c->altitude, m->k, m->sigma, thk, dp->J);
-    else gbo_fdem_sensitivity(c->sv.fdem, c->altitude, m->k, m->sigma, thk, dp->J);
+    /* at the height the datapoint holds NOW: fm_dlogc(remapped) runs before datapoint.perturb() */
+    if (c->sv.tdem) gbo_tdem_sensitivity(c->sv.tdem, dp->z, m->k, m->sigma, thk, dp->J);
+    else gbo_fdem_sensitivity(c->sv.fdem, dp->z, m->k, m->sigma, thk, dp->J);
     dp->Jk = m->k;
     c->n_sens++;
 }
 
 /* EmDataPoint.find_best_halfspace: argmin of misfit over logspace(-4, 4, 100) */
-static double best_halfspace(chain_t *c, const double *rel, const double *add)
+static double best_halfspace(chain_t *c, const double *rel, const double *add, double z)
 {
     double var[GBO_MAXC], pred[GBO_MAXC];
     data_variance(&c->sv, c->data, rel, add, var);
@@ -666,7 +693,7 @@ static double best_halfspace(chain_t *c, const double *rel, const double *add)
         double e = -4.0 + (double)i * (8.0 / 99.0);
         if (i == 99) e = 4.0;
         m.sigma[0] = pow(10.0, e);
-        forward(c, &m, pred);
+        forward(c, &m, z, pred);
         double phi = data_misfit(c->C, c->data, pred, var);
         if (phi < best) { best = phi; best_c = m.sigma[0]; }
     }
@@ -680,12 +707,15 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
         c->dp.rel[s] = o_rel_init(o, s);
         c->dp.add[s] = o_add_init(o, s);
     }
-    c->sigma_ref = best_halfspace(c, c->dp.rel, c->dp.add);
+    /* Inference1D.reset :984-994 re-initialises with the CURRENT datapoint: its height is kept and the height prior,
+     * proposal and posterior bins are re-centred on it (Point.set_priors :959-961) */
+    c->z_ref = c->dp.z;
+    c->sigma_ref = best_halfspace(c, c->dp.rel, c->dp.add, c->dp.z);
     c->model.k = 1;
     c->model.edges[0] = 0.0;
     c->model.edges[1] = INFINITY;
     c->model.sigma[0] = c->sigma_ref;
-    forward(c, &c->model, c->dp.pred);
+    forward(c, &c->model, c->dp.z, c->dp.pred);
     sensitivity(c, &c->model, &c->dp);
     make_grids(o, c->sv.n_sys, c->sigma_ref, &c->G);
     reset_posteriors(o, &c->G, out);
@@ -694,7 +724,7 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
     double var[GBO_MAXC];
     data_variance(&c->sv, c->data, c->dp.rel, c->dp.add, var);
     c->misfit = data_misfit(c->C, c->data, c->dp.pred, var);
-    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->sv.n_sys, c->dp.rel, c->dp.add);
+    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->sv.n_sys, c->dp.rel, c->dp.add, 0.0);
     c->likelihood = data_likelihood(c->C, c->data, c->dp.pred, var);
     c->posterior = c->likelihood + c->prior;
     c->burned_in = 0;
@@ -705,6 +735,7 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
     c->best_model = c->model;
     memcpy(c->best_rel, c->dp.rel, sizeof(c->best_rel));
     memcpy(c->best_add, c->dp.add, sizeof(c->best_add));
+    c->best_z = c->dp.z;
     c->best_posterior = c->posterior;
     c->best_iter = 0;
     c->n_zero_acc = 0;
@@ -732,7 +763,7 @@ static int chain_step(chain_t *c)
          * predicted-data update is commented out (TdemDataPoint.py:1031-1055) - so the Newton gradient of a
          * time-domain death / move uses the CURRENT model's predicted data with the remapped model's Jacobian. */
         double scratch[GBO_MAXC];
-        forward(c, &remap, c->sv.tdem ? scratch : tdp.pred);
+        forward(c, &remap, tdp.z, c->sv.tdem ? scratch : tdp.pred);
         sensitivity(c, &remap, &tdp);
     }
     data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
@@ -750,7 +781,9 @@ static int chain_step(chain_t *c)
     test = remap;
     for (int i = 0; i < k; ++i) test.sigma[i] = exp(mean[i] + dx[i]);
 
-    /* test_datapoint.perturb() */
+    /* test_datapoint.perturb(): height first (Point.perturb :614-622), then the errors (DataPoint.perturb :561-573) */
+    if (o->solve_height)
+        tdp.z = propose_height(&c->rng, tdp.z, o->height_prop_var, c->z_ref - o->max_height_change, c->z_ref + o->max_height_change);
     if (c->sv.n_sys == 1) {
         if (o->solve_relative_error) tdp.rel[0] = propose_error(&c->rng, tdp.rel[0], o->rel_prop_var, o->rel_min, o->rel_max);
         if (o->solve_additive_error) tdp.add[0] = propose_error(&c->rng, tdp.add[0], o->add_prop_var, o->add_min, o->add_max);
@@ -761,10 +794,10 @@ static int chain_step(chain_t *c)
         if (o->solve_additive_error) propose_error2(&c->rng, tdp.add, av, amn, amx);
     }
 
-    forward(c, &test, tdp.pred);
+    forward(c, &test, tdp.z, tdp.pred);
     data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
     double t_misfit = data_misfit(C, c->data, tdp.pred, var);
-    double t_prior = datapoint_probability(o, c->sv.n_sys, tdp.rel, tdp.add);
+    double t_prior = datapoint_probability(o, c->sv.n_sys, tdp.rel, tdp.add, tdp.z - c->z_ref);
     if (t_prior == -INFINITY) return 0;
     t_prior += model_probability(o, &test, c->sigma_ref);
     if (t_prior == -INFINITY) return 0;
@@ -828,6 +861,7 @@ static int chain_update(chain_t *c, gbo_chain_out *out)
             c->best_model = c->model;
             memcpy(c->best_rel, c->dp.rel, sizeof(c->best_rel));
             memcpy(c->best_add, c->dp.add, sizeof(c->best_add));
+            c->best_z = c->dp.z;
             c->best_posterior = c->posterior;
             reset_posteriors(o, &c->G, out);
         }
@@ -837,6 +871,7 @@ static int chain_update(chain_t *c, gbo_chain_out *out)
         c->best_model = c->model;
         memcpy(c->best_rel, c->dp.rel, sizeof(c->best_rel));
         memcpy(c->best_add, c->dp.add, sizeof(c->best_add));
+        c->best_z = c->dp.z;
         c->best_posterior = c->posterior;
     }
     if (c->iteration < N2) out->accept_trace[c->iteration] = (uint8_t)c->accepted;
@@ -858,7 +893,7 @@ static int chain_update(chain_t *c, gbo_chain_out *out)
         }
     }
     if (do_reset) return 1; /* reset() re-initialises everything, then update continues below on the new state */
-    accumulate_posteriors(o, &c->G, &c->model, c->dp.rel, c->dp.add, out);
+    accumulate_posteriors(o, &c->G, &c->model, c->dp.rel, c->dp.add, c->dp.z - c->z_ref, out);
     return 0;
 }
 
@@ -872,6 +907,7 @@ static int run_chain_impl(const survey_t *sv, const gbo_options *opt, const doub
     c->C = sv->C;
     memcpy(c->data, data, sizeof(double) * c->C);
     c->altitude = altitude;
+    c->dp.z = altitude;
     c->rng.seed = seed;
     c->rng.sounding = sounding_index;
     c->rng.block = 0;
@@ -892,7 +928,7 @@ static int run_chain_impl(const survey_t *sv, const gbo_options *opt, const doub
             /* Inference1D.reset(): re-initialise, continue the random stream */
             c->n_resets++;
             chain_init(c, out);
-            accumulate_posteriors(opt, &c->G, &c->model, c->dp.rel, c->dp.add, out);
+            accumulate_posteriors(opt, &c->G, &c->model, c->dp.rel, c->dp.add, c->dp.z - c->z_ref, out);
         }
         go = !failed && (c->iteration <= N + c->burned_in_iter);
         if (!failed && !c->burned_in) {
@@ -943,6 +979,8 @@ static int run_chain_impl(const survey_t *sv, const gbo_options *opt, const doub
     s[GBO_S_N_MOVE] = (double)c->n_act[2];
     s[GBO_S_N_NONE] = (double)c->n_act[3];
     s[GBO_S_TOTAL_ITER] = (double)total;
+    s[GBO_S_CUR_HEIGHT] = c->dp.z;
+    s[GBO_S_BEST_HEIGHT] = c->best_z;
     for (int i = 0; i < opt->max_layers; ++i) {
         out->best_sigma[i] = i < c->best_model.k ? c->best_model.sigma[i] : NAN;
         out->cur_sigma[i] = i < c->model.k ? c->model.sigma[i] : NAN;
@@ -1026,16 +1064,18 @@ static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_tr
     solve_LT(k, A, y, step);
     for (int i = 0; i < k; ++i) t->newton_mean[i] = exp(log(remap.sigma[i]) - o->covariance_scaling * step[i]);
 
-    sv_forward(sv, t->altitude, k, test.sigma, thk, t->pred_test);
+    const double z_test = o->solve_height ? t->altitude_test : t->altitude;
+    sv_forward(sv, z_test, k, test.sigma, thk, t->pred_test);
     data_variance(sv, t->data, t->rel_test, t->add_test, var);
     t->misfit_test = data_misfit(C, t->data, t->pred_test, var);
-    t->prior_test = datapoint_probability(o, sv->n_sys, t->rel_test, t->add_test) + model_probability(o, &test, t->sigma_ref);
+    t->prior_test = datapoint_probability(o, sv->n_sys, t->rel_test, t->add_test, o->solve_height ? z_test - t->altitude_ref : 0.0) +
+                    model_probability(o, &test, t->sigma_ref);
     t->likelihood_test = data_likelihood(C, t->data, t->pred_test, var);
     t->proposal = 1.0;
     t->proposal1 = 1.0;
     if (t->action == ACT_BIRTH || t->action == ACT_DEATH) {
         double g2[GBO_MAXL], s2[GBO_MAXL], xr[GBO_MAXL], xf[GBO_MAXL], logdetL = 0.0;
-        sv_sensitivity(sv, t->altitude, k, test.sigma, thk, J);
+        sv_sensitivity(sv, z_test, k, test.sigma, thk, J);
         hessian_gradient(o, &test, t->sigma_ref, C, t->data, var, J, t->pred_test, NULL, g2);
         solve_L(k, A, g2, y);
         solve_LT(k, A, y, s2);

@@ -156,9 +156,16 @@ def make_tdem():
                         times=times, models=np.array(MODELS))
 
 
-def _initialised_inference(data, z, n_markov_chains, seed):
+# solve_z of the height tests: the sensor height handed to the inversion is 0.4 m above the one the data were
+# simulated at, the prior is +-1 m around it, the random walk has a 0.1 m standard deviation.
+HEIGHT_KW = dict(solve_z=True, maximum_z_change=1.0, z_proposal_variance=0.01)
+HEIGHT_BIAS = 0.4
+
+
+def _initialised_inference(data, z, n_markov_chains, seed, **extra):
     from geobipy import Inference1D, get_prng
     kw = _options(n_markov_chains)
+    kw.update(extra)
     kw["prng"] = get_prng(seed=seed)
     inf = Inference1D(**kw)
     dp = _datapoint(_system(), np.asarray(data, dtype=np.float64), z)
@@ -205,13 +212,17 @@ def make_bins():
 ACT = {"insert": 0, "delete": 1, "perturb": 2, "none": 3}
 
 
-def make_transitions(n_soundings=6, n_iter=250):
+def make_transitions(n_soundings=6, n_iter=250, height=False):
     _geobipy()
     from numpy import inf as npinf
     recs = []
     for sidx in range(n_soundings):
         data, z, _, _ = _observed(sidx)
-        inf = _initialised_inference(data, z, 100000, 1000 + sidx)
+        if height:
+            z = z + HEIGHT_BIAS
+            inf = _initialised_inference(data, z, 100000, 3000 + sidx, **HEIGHT_KW)
+        else:
+            inf = _initialised_inference(data, z, 100000, 1000 + sidx)
         hs = float(inf.halfspace.item())
         init = dict(prior=float(inf.prior), likelihood=float(inf.likelihood), misfit=float(inf.data_misfit))
         for it in range(n_iter):
@@ -221,6 +232,7 @@ def make_transitions(n_soundings=6, n_iter=250):
             rel_cur = float(np.asarray(dp0.relative_error).item())
             add_cur = float(np.asarray(dp0.additive_error).item())
             tdp = deepcopy(dp0)
+            z_cur = float(np.asarray(dp0.z).item())
             remapped, test = m0.perturb(tdp, -npinf, npinf, alpha=inf.covariance_scaling)
             action = ACT[remapped.mesh.action[0]]
             k = int(remapped.nCells.item())
@@ -233,7 +245,8 @@ def make_transitions(n_soundings=6, n_iter=250):
             prior = float(tdp.probability) + float(test.probability(inf.solve_parameter, inf.solve_gradient))
             like = float(tdp.likelihood(log=True))
             prop, prop1 = test.proposal_probabilities(remapped, tdp, alpha=inf.covariance_scaling)
-            rec = dict(sounding=sidx, altitude=z, sigma_ref=hs, data=np.asarray(data), k=k, action=action,
+            rec = dict(sounding=sidx, altitude=z_cur, altitude_ref=z, altitude_test=float(np.asarray(tdp.z).item()),
+                       sigma_ref=hs, data=np.asarray(data), k=k, action=action,
                        edges=np.asarray(remapped.mesh.edges).copy(), sigma_remap=np.asarray(remapped.values).copy(),
                        sigma_test=np.asarray(test.values).copy(), rel_cur=rel_cur, add_cur=add_cur,
                        rel_test=float(np.asarray(tdp.relative_error).item()),
@@ -260,7 +273,7 @@ def make_transitions(n_soundings=6, n_iter=250):
             for i, v in enumerate(vals):
                 obj[i] = np.asarray(v)
             out[key] = obj
-    np.savez_compressed(os.path.join(HERE, "transitions.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "transitions_height.npz" if height else "transitions.npz"), **out)
     print("transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
 
 
@@ -407,10 +420,14 @@ def make_tdem_chain(sidx, rep=0, n_markov_chains=10000):
           "acc", np.asarray(inf.acceptance_v[:it + 1]).mean(), flush=True)
 
 
-def make_chain(sidx, rep=0, n_markov_chains=10000):
+def make_chain(sidx, rep=0, n_markov_chains=10000, height=False):
     _geobipy()
     data, z, edges, sigma = _observed(sidx)
-    inf = _initialised_inference(data, z, n_markov_chains, 5000 + sidx + 100 * rep)
+    if height:
+        z = z + HEIGHT_BIAS
+        inf = _initialised_inference(data, z, n_markov_chains, 7000 + sidx + 100 * rep, **HEIGHT_KW)
+    else:
+        inf = _initialised_inference(data, z, n_markov_chains, 5000 + sidx + 100 * rep)
     t0 = time.time()
     import io
     import contextlib
@@ -426,8 +443,16 @@ def make_chain(sidx, rep=0, n_markov_chains=10000):
                     failed = True
     dt = time.time() - t0
     it = int(inf.iteration)
+    extra = {}
+    stem = "ref_chain_"
+    if height:
+        stem = "ref_height_chain_"
+        extra = dict(height_hist=np.asarray(inf.datapoint.z.posterior.counts, dtype=np.int32),
+                     height_cur=float(np.asarray(inf.datapoint.z).item()),
+                     height_best=float(np.asarray(inf.best_datapoint.z).item()))
     np.savez_compressed(
-        os.path.join(HERE, "ref_chain_%d.npz" % sidx if rep == 0 else "ref_chain_%d_r%d.npz" % (sidx, rep)), sounding=sidx, data=data, altitude=z, true_edges=edges,
+        os.path.join(HERE, stem + ("%d.npz" % sidx if rep == 0 else "%d_r%d.npz" % (sidx, rep))), **extra,
+        sounding=sidx, data=data, altitude=z, true_edges=edges,
         true_sigma=sigma, halfspace=float(inf.halfspace.item()), iterations=it, failed=bool(failed),
         burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
         hitmap=np.asarray(inf.model.values.posterior.counts, dtype=np.int32),
@@ -457,3 +482,7 @@ if __name__ == "__main__":
         make_transitions()
     elif what == "chain":
         make_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    elif what == "transitions_height":
+        make_transitions(n_soundings=3, n_iter=250, height=True)
+    elif what == "height_chain":
+        make_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0, height=True)

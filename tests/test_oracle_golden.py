@@ -196,6 +196,92 @@ def test_chain_statistics_match_reference_chains(oracle, golden_dir):
     _extra_posterior_checks(refs, runs, 120, (0.85, 0.9))
 
 
+# ------------------------------------------------------------------------------------------ solve_z (sensor height)
+HEIGHT = dict(solve_height=1, max_height_change=1.0, height_prop_var=0.01)   # = make_golden.HEIGHT_KW
+
+
+def test_height_transitions_match_live_reference(oracle, golden_dir):
+    """750 transitions recorded from the live reference with solve_z=True (Point.perturb :614-622): the proposed
+    height enters the forward model of the candidate and the Jacobian of a birth / death, the current height the
+    remapped model's Jacobian, and `none` steps reuse the stored Jacobian of whatever height it was computed at."""
+    g = np.load(os.path.join(golden_dir, "transitions_height.npz"), allow_pickle=True)
+    s, o = oracle.make_system(), oracle.resolve_options(**HEIGHT)
+    n = len(g["k"])
+    assert n >= 700 and set(np.unique(g["action"])) == {0, 1, 2, 3}
+    assert np.all(g["altitude_test"] != g["altitude"]) and np.all(np.abs(g["altitude_test"] - g["altitude_ref"]) <= 1.0)
+    for i in range(0, n, 2):
+        kw = {k: g[k][i] for k in g.files}
+        rc, r = oracle.eval_transition(s, o, **kw)
+        assert rc == 0
+        k = int(kw["k"])
+        Href = np.asarray(kw["H"], dtype=np.float64).reshape(k, k)
+        assert np.max(np.abs(np.linalg.inv(r["hessian"]) - Href)) <= 1e-7 * np.max(np.abs(Href))
+        gref = np.asarray(kw["gradient"], dtype=np.float64)
+        assert np.max(np.abs(r["gradient"] - gref)) <= 1e-6 * (np.max(np.abs(gref)) + 1e-12)
+        assert np.allclose(r["pred_test"], np.asarray(kw["pred_test"], dtype=np.float64), rtol=1e-9, atol=0.0)
+        for name in ("misfit_test", "prior_test", "likelihood_test", "proposal", "proposal1"):
+            a, b = r[name], float(kw[name])
+            if np.isfinite(b):
+                assert abs(a - b) <= 1e-7 * (abs(b) + 1.0), (i, name, a, b)
+            else:
+                assert (a == b) or (np.isnan(a) and np.isnan(b)), (i, name, a, b)
+    # with the height held at its current value the recorded candidates are NOT reproduced: the pin sees the height
+    o0 = oracle.resolve_options()
+    kw = {k: g[k][0] for k in g.files}
+    _, r0 = oracle.eval_transition(s, o0, **kw)
+    assert abs(r0["misfit_test"] - float(kw["misfit_test"])) > 1e-6 * abs(float(kw["misfit_test"]))
+
+
+def _height_mean(hist, dz=1.0):
+    c = -dz + (np.arange(hist.size) + 0.5) * (2 * dz / hist.size)
+    return float((hist * c).sum() / hist.sum())
+
+
+def test_height_chain_statistics_match_reference_chains(oracle, golden_dir):
+    """Chains with solve_z on data simulated 0.4 m below the height handed to the inversion (sounding 5, which burns
+    in at once): the posterior height of the oracle's chains moves away from the input by the same amount as in the
+    reference's chains (within their own scatter), and the other summaries stay consistent."""
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_height_chain_5"))
+    refs = [np.load(os.path.join(golden_dir, f)) for f in files]
+    assert len(refs) >= 4
+    g = refs[0]
+    s, o = oracle.make_system(), oracle.resolve_options(n_markov_chains=10000, **HEIGHT)
+    runs = [oracle.run_chain(s, o, g["data"], float(g["altitude"]), 300 + j, 5) for j in range(4)]
+    for r in runs:
+        sc = r["scalars"]
+        counted = int(sc[oracle.S_ITER]) - int(sc[oracle.S_BURNED_IN_ITER]) + 1
+        assert sc[oracle.S_BURNED_IN] == 1 and r["height_hist"].sum() == counted == r["rel_hist"].sum()
+        assert abs(sc[oracle.S_CUR_HEIGHT] - float(g["altitude"])) <= 1.0
+        assert abs(sc[oracle.S_BEST_HEIGHT] - float(g["altitude"])) <= 1.0
+    for r in refs:
+        assert r["height_hist"].sum() == r["rel_hist"].sum()
+    ref_h = np.array([_height_mean(r["height_hist"]) for r in refs])
+    our_h = np.array([_height_mean(r["height_hist"]) for r in runs])
+    # the data move the height well away from the input value, the same way in both (sounding 5: about +0.7 m; the
+    # height trades off against the near-surface conductivity, so it does not simply return to the simulated one)
+    assert abs(ref_h.mean()) > 0.3 and np.sign(ref_h.mean()) == np.sign(our_h.mean()), (ref_h, our_h)
+    assert abs(our_h.mean() - ref_h.mean()) < max(0.15, 3 * ref_h.std()), (ref_h, our_h)
+    ref_acc = np.mean([r["accept_trace"].mean() for r in refs])
+    acc = np.mean([r["scalars"][oracle.S_N_ACCEPT] / r["scalars"][oracle.S_ITER] for r in runs])
+    assert abs(acc - ref_acc) < 0.05, (acc, ref_acc)
+    k = np.arange(o.max_layers + 1)
+    ref_nc = sum(r["ncells_hist"].astype(np.int64) for r in refs)
+    nc = sum(r["ncells_hist"].astype(np.int64) for r in runs)
+    assert abs((nc * k).sum() / nc.sum() - (ref_nc * k).sum() / ref_nc.sum()) < 0.5
+
+
+def test_height_off_is_unchanged(oracle, golden_dir):
+    """solve_height = 0 leaves the random stream and every output of the chain as it was."""
+    g = np.load(os.path.join(golden_dir, "ref_chain_1.npz"))
+    s = oracle.make_system()
+    a = oracle.run_chain(s, oracle.resolve_options(n_markov_chains=300, burn_in_min_iter=100), g["data"], float(g["altitude"]), 3, 1)
+    b = oracle.run_chain(s, oracle.resolve_options(n_markov_chains=300, burn_in_min_iter=100, max_height_change=2.0,
+                                                   height_prop_var=1.0), g["data"], float(g["altitude"]), 3, 1)
+    for key in a:
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    assert a["scalars"][oracle.S_CUR_HEIGHT] == float(g["altitude"]) and a["height_hist"].sum() == 0
+
+
 # ------------------------------------------------------------------------------------------ time domain
 def _skytem_noise(oracle, tsys, ref):
     """The reference's own noise model for these data (skytem_options + TdemDataPoint.std :329-379)."""
