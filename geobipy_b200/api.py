@@ -379,6 +379,12 @@ class Inference1D:
             dp.relative_error = np.asarray([s[_lib.S_CUR_REL]])
             dp.additive_error = np.asarray([s[_lib.S_CUR_ADD]])
             self.best_relative_error, self.best_additive_error = float(s[_lib.S_BEST_REL]), float(s[_lib.S_BEST_ADD])
+        if o.solve_height:  # solve_z: datapoint.z / best_datapoint.z and datapoint.z.posterior (Point.py:1013-1025)
+            z0 = float(dp.z)
+            self.height_posterior = Histogram(r["height_hist"][b], z0 + np.linspace(-o.max_height_change, o.max_height_change,
+                                                                                  o.n_err_bins + 1))
+            self.best_height = float(s[_lib.S_BEST_HEIGHT])
+            dp.z = float(s[_lib.S_CUR_HEIGHT])
         dp.forward(self.model)
 
     def interface_probability(self):

@@ -237,6 +237,7 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
         Q.spec_helpers = hmax < 0 ? 0 : (hmax > WARPS - 1 ? WARPS - 1 : hmax);
         const char* m = std::getenv("GBP_SPEC_MIN_REJECTIONS");
         Q.spec_min_rejections = m ? std::atoi(m) : 24;
+        if (KIND == KIND_FDEM_Z) Q.spec_helpers = 0;  // a speculative step does not hand a proposed height back
 
     }
     Q.jstore = g_jstore[dev];
@@ -370,6 +371,8 @@ int check_options(const gbp_options* o)
     if (!(o->min_width * o->max_layers < o->max_edge))
         return fail("min_width * max_layers must be < max_edge (RectilinearMesh1D.set_priors)");
     if (o->n_sigma_bins < 1 || o->n_err_bins < 1) return fail("invalid bin counts");
+    if (o->solve_height && (!(o->max_height_change > 0.0) || !(o->height_prop_var > 0.0)))
+        return fail("solve_height needs max_height_change > 0 and height_prop_var > 0");
     return 0;
 }
 
@@ -535,6 +538,14 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
     cudaStream_t st = (cudaStream_t)stream;
     const bool small = P.C <= 12;
     const SysDev& sd = tc->host.dev;
+    if (opt->solve_height) {  // sampled sensor height: its own kernels (the fixed-height ones stay what they were)
+        if (!small) return fail("solve_height: systems with more than 6 frequencies are not built");
+        if (precision == GBP_PRECISION_F32)
+            return launch_chain<float, float, 12, 16, KIND_FDEM_Z>(sd, tc->d_f32, (size_t)TAB_ROWS * sd.tab_stride * sizeof(float), P, st);
+        if (precision == GBP_PRECISION_F64)
+            return launch_chain<double, double, 12, 8, KIND_FDEM_Z>(sd, tc->d_f64, (size_t)TAB_ROWS * sd.tab_stride * sizeof(double), P, st);
+        return fail("precision must be 32 or 64");
+    }
     // fp32: 16 chains per SM; fp64: 8 per SM
     if (precision == GBP_PRECISION_F32) {
         const size_t tb = (size_t)TAB_ROWS * sd.tab_stride * sizeof(float);
@@ -610,6 +621,7 @@ static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* 
         {(void* const*)&h->cur_sigma, (void**)&d.cur_sigma, (size_t)B * ml * sizeof(double)},
         {(void* const*)&h->cur_edges, (void**)&d.cur_edges, (size_t)B * (ml + 1) * sizeof(double)},
         {(void* const*)&h->scalars, (void**)&d.scalars, (size_t)B * GBP_NSCALARS * sizeof(double)},
+        {(void* const*)&h->height_hist, (void**)&d.height_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
     };
     if (device < 0 || device >= 64) return fail("device index out of range");
     std::lock_guard<std::mutex> lk(g_host_mu);  // the cached device buffers are shared by the callers of this process
@@ -622,8 +634,8 @@ static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* 
         }
         ++slot;
     }
-    if (arena_get(device, 12, (size_t)B * C * sizeof(double), (void**)&d_data)) return 1;
-    if (arena_get(device, 13, (size_t)B * sizeof(double), (void**)&d_alt)) return 1;
+    if (arena_get(device, 14, (size_t)B * C * sizeof(double), (void**)&d_data)) return 1;
+    if (arena_get(device, 15, (size_t)B * sizeof(double), (void**)&d_alt)) return 1;
     CK(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, nullptr));
     CK(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, nullptr));
     rc = run(d_data, d_alt, &d);
@@ -898,6 +910,7 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     if ((opt->n_systems > 1 ? 2 : 1) != sv->n_systems)
         return fail("gbp_options.n_systems must equal the number of systems of the datapoint type");
     TdCache* tc;
+    if (opt->solve_height) return fail("solve_height is not built for time-domain datapoints (the loop height enters the geometry weights)");
     if (get_td_tables(sv, &tc, true)) return 1;
     ChainParams P;
     std::memset(&P, 0, sizeof(P));

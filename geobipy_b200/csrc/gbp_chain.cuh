@@ -48,7 +48,9 @@ enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_REL2, BV_ADD2, BV_N = 8 };
 
 // KIND of datapoint a kernel instantiation inverts: frequency domain (FdemDataPoint, one system) or time
 // domain (TdemDataPoint, one or two systems with per-system errors, TdemDataPoint.py:329-379)
-enum { KIND_FDEM = 0, KIND_TDEM = 1 };
+// KIND_FDEM_Z: a frequency-domain datapoint whose sensor height is sampled too (solve_z: Point.perturb :614-622,
+// Point.set_priors :959-961).  Its own instantiation, so that the fixed-height kernels are what they were.
+enum { KIND_FDEM = 0, KIND_TDEM = 1, KIND_FDEM_Z = 2 };
 __host__ __device__ constexpr int ns_of(int kind) { return kind == KIND_TDEM ? GBP_TD_MAXSYS : 1; }
 template <typename T, int KIND> struct SysOf {
     typedef SysShared<T> shared;
@@ -74,7 +76,7 @@ template <typename R, int NS> struct SpecOut {
     R misfit, prior, likelihood;
     Errs<R, NS> err, ln_err;
 };
-enum { OP_HITMAP = 0, OP_EDGES, OP_NCELLS, OP_REL, OP_ADD, OP_MISFIT, OP_ACCEPT, OP_N = 8 };
+enum { OP_HITMAP = 0, OP_EDGES, OP_NCELLS, OP_REL, OP_ADD, OP_MISFIT, OP_ACCEPT, OP_HEIGHT, OP_N = 8 };
 
 template <typename R> struct MeshBuf {
     R edges[GBP_MAXL + 2];  // edges[0] = 0, edges[k] = inf
@@ -114,7 +116,8 @@ template <typename R> struct Consts {
     R half_log2pi;
     R rel_lnmin[2], rel_lnmax[2], rel_sd[2], rel_ln0[2], rel0[2], rel_dx[2];   // per system
     R add_lnmin[2], add_lnmax[2], add_sd[2], add_ln0[2], add0[2], add_dx[2];
-    R err_lp;                                 // log prior of the (always in-bounds) errors, all systems
+    R err_lp;                                 // log prior of the (always in-bounds) errors, all systems, and height
+    R z_sd, z_max, z_dx;                      // solve_z: proposal std, half-width of the Uniform prior, bin width
     R sig_halfspan, sig_dx, depth_step, depth_max;
     R ln_half, ln_3half;
     int kmax, n_depth, n_sig, n_err, C, solve_par, solve_grad, solve_rel, solve_add;
@@ -161,7 +164,11 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
     c.c_val = (R)(-0.5 * l2pi - 0.5 * dlog_(s * s));
     c.half_log2pi = (R)(0.5 * l2pi);
     c.n_sys = o.n_systems > 1 ? 2 : 1;
-    double lp = 0.0;
+    // Point.probability :160-196 comes first in DataPoint.probability: Uniform(z0 - dz, z0 + dz), always in bounds
+    double lp = o.solve_height ? -dlog_(2.0 * o.max_height_change) : 0.0;
+    c.z_sd = (R)::sqrt(o.height_prop_var);
+    c.z_max = (R)o.max_height_change;
+    c.z_dx = (R)(2.0 * o.max_height_change / (double)o.n_err_bins);
     for (int i = 0; i < c.n_sys; ++i) {
         const double rmin = i ? o.rel_min2 : o.rel_min, rmax = i ? o.rel_max2 : o.rel_max;
         const double amin = i ? o.add_min2 : o.add_min, amax = i ? o.add_max2 : o.add_max;
@@ -545,6 +552,37 @@ __device__ __noinline__ prop2_t<R> ch_propose_ln_error2(Rng g, R c0, R c1, const
     return prop2_t<R>{x0, x1, g.block};
 }
 
+// Point.perturb :614-622 = StatArray.propose :578-638 with imposePrior: Normal(z, var) random walk re-drawn while
+// outside the Uniform prior [lo, hi] (closed support), at most 10 times, then the current height is kept
+template <typename R> __device__ __noinline__ prop_t<R> ch_propose_height(Rng g, R cur, R sd, R lo, R hi)
+{
+    R x = cur + sd * rng_normal<R>(g);
+    int tries = 0;
+#pragma unroll 1
+    while (!(x >= lo && x <= hi)) {
+        x = cur + sd * rng_normal<R>(g);
+        tries++;
+        if (tries == 10) {
+            x = cur;
+            break;
+        }
+    }
+    return prop_t<R>{x, g.block};
+}
+
+// add `count` visits of the current height to its histogram (Point.update_posteriors :1022-1025; bins relative to
+// the height the prior is centred on, Point.set_z_posterior :1013-1020)
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ void ch_flush_height(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, R dz, int count)
+{
+    GBP_SHARED(w);
+    GBP_SHARED(K);
+    if (count <= 0) return;
+    int32_t* hh = (int32_t*)w->outp[OP_HEIGHT];
+    if (hh && lane_id() == 0) hh[uniform_bin<R>(dz, -K->z_max, K->z_dx, K->n_err)] += count;
+    __syncwarp();
+}
+
 // add `count` visits of the current model / errors to every histogram
 template <typename R, typename T, int NC, int KIND>
 __device__ __noinline__ void ch_flush(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, int k, int mcur, int vcur,
@@ -637,6 +675,10 @@ __device__ __noinline__ void ch_zero_posteriors(WarpState<R, T, NC, KIND>* w, co
     if ((p = (int32_t*)w->outp[OP_ADD])) {
 #pragma unroll 1
         for (int i = lane; i < K->n_sys * K->n_err; i += 32) p[i] = 0;
+    }
+    if ((p = (int32_t*)w->outp[OP_HEIGHT])) {
+#pragma unroll 1
+        for (int i = lane; i < K->n_err; i += 32) p[i] = 0;
     }
     __syncwarp();
 }
@@ -795,8 +837,8 @@ template <typename R, int NS> struct Hot {
 // the caller only learns whether the step would be rejected.
 template <bool SPEC, typename R, typename T, int NC, int KIND>
 __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Consts<R>* K,
-                                        const typename SysOf<T, KIND>::shared* S, const T* tab, const T alt, const R nahl,
-                                        T* const jg, Hot<R, ns_of(KIND)>& h, bool& accepted, bool& chol_failed)
+                                        const typename SysOf<T, KIND>::shared* S, const T* tab, T& alt, const T alt_ref,
+                                        const R nahl, T* const jg, Hot<R, ns_of(KIND)>& h, bool& accepted, bool& chol_failed)
 {
     constexpr int NS = ns_of(KIND);
     typedef Errs<R, NS> errs_t;
@@ -934,7 +976,7 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
             // predicted data (FdemDataPoint.py:535-545); TdemDataPoint.fm_dlogc stores only the Jacobian, its
             // predicted-data update is commented out (TdemDataPoint.py:1031-1055), so a time-domain death / move
             // forms the Newton gradient with the CURRENT model's predicted data.
-            if constexpr (KIND == KIND_FDEM) ph = pred_t;
+            if constexpr (KIND != KIND_TDEM) ph = pred_t;
         } else if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
             ch_copy16(w->J, jg, JBYTES);
             j_valid = true;
@@ -962,7 +1004,13 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
             }
             __syncwarp();
 
-            // ---- test_datapoint.perturb() (DataPoint.py:531-573)
+            // ---- test_datapoint.perturb() (DataPoint.py:531-573): height first (Point.perturb :614-622), then errors
+            T alt_t = alt;
+            if constexpr (KIND == KIND_FDEM_Z) {
+                const prop_t<R> pz = ch_propose_height<R>(rng, (R)alt, K->z_sd, (R)alt_ref - K->z_max, (R)alt_ref + K->z_max);
+                alt_t = (T)pz.x;
+                rng.block = pz.block;
+            }
             errs_t ln_t_err = ln_err, err_t = err;
             if (NS == 1 || K->n_sys == 1) {
                 if (K->solve_rel) {
@@ -998,7 +1046,7 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
             const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
             // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
             // (Model.proposal_probabilities :619) - fused into the same pass.
-            ch_forward(w, S, tab, alt, kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : (T*)nullptr);
+            ch_forward(w, S, tab, alt_t, kn, val_p.sig, mesh_p.edges, pred_t, jump ? J_t : (T*)nullptr);
             ch_set_ivar(w, K, C, err_t);
             const pair_t<R> tml = ch_misfit_like(w, C, nahl, pred_t);
             // error priors: the proposals above are forced inside their bounds (or fall back to the
@@ -1030,6 +1078,10 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                 accepted = rt<R>::exp(log_alpha) > u;
                 if (accepted && !SPEC) {  // a speculative evaluation only reports the outcome
                     ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
+                    if constexpr (KIND == KIND_FDEM_Z) {
+                        ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
+                        alt = alt_t;
+                    }
                     dwell = 0;
                     misfit = tml.a;
                     prior = t_prior;
@@ -1131,7 +1183,7 @@ __device__ __noinline__ bool spec_member_run(WarpState<R, T, NC, KIND>* w, SpecR
     Hot<R, ns_of(KIND)> h = rd->hot;
     h.j_valid = false;
     const int t0 = rd->t0, t_end = rd->t_end, W = rd->W;
-    const T alt = rd->alt;
+    T alt = rd->alt;   // (a sampled height, KIND_FDEM_Z, is not speculated on: the host turns speculation off)
     const R nahl = rd->nahl;
     T* const jg = rd->jg;
     bool stopped = false;
@@ -1151,7 +1203,7 @@ __device__ __noinline__ bool spec_member_run(WarpState<R, T, NC, KIND>* w, SpecR
         h.rng.block = 0u;
         bool accepted = false, chol_failed = false;
         const long long c_s = clock64();
-        ar_step<true, R, T, NC, KIND>(w, K, S, tab, alt, nahl, jg, h, accepted, chol_failed);
+        ar_step<true, R, T, NC, KIND>(w, K, S, tab, alt, alt, nahl, jg, h, accepted, chol_failed);
         if (lane == 0) {
             atomicAdd(&g_diag[3], 1ull);
             atomicAdd(&g_diag[4], (unsigned long long)(clock64() - c_s));
@@ -1396,7 +1448,8 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
     }
     rng.block = 0u;
     rng.iter = 0u;
-    const T alt = (T)P.altitude[chain];
+    T alt = (T)P.altitude[chain];   // sensor height: constant unless KIND_FDEM_Z samples it
+    T alt_ref = alt, best_alt = alt; // centre of the height prior; height of the best model
     int &k = h.k, &mcur = h.mcur, &vcur = h.vcur, &pcur = h.pcur, &dwell = h.dwell;
     bool& j_valid = h.j_valid;
     errs_t &ln_err = h.ln_err, &err = h.err;
@@ -1435,6 +1488,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         w->outp[OP_ADD] = o.add_hist ? o.add_hist + (size_t)chain * K->n_sys * K->n_err : nullptr;
         w->outp[OP_MISFIT] = o.misfit_trace ? o.misfit_trace + (size_t)chain * N2 : nullptr;
         w->outp[OP_ACCEPT] = o.accept_trace ? o.accept_trace + (size_t)chain * N2 : nullptr;
+        w->outp[OP_HEIGHT] = (KIND == KIND_FDEM_Z && o.height_hist) ? o.height_hist + (size_t)chain * K->n_err : nullptr;
         for (int i = 0; i < CT_N; ++i) w->ctr[i] = 0;
     }
     __syncwarp();
@@ -1443,6 +1497,10 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
 
     // Inference1D.initialize :353-464 (also used by reset() :984-999): cold, one shared copy
     auto initialize = [&](bool first) {
+        // reset() re-initialises with the CURRENT datapoint (Inference1D.py:984-994): a sampled height is kept and
+        // its prior, proposal and posterior bins are re-centred on it (Point.set_priors :959-961)
+        alt_ref = alt;
+        best_alt = alt;
         const init_out<R> io = ch_initialize<R, T, NC, KIND>(w, K, S, tab, alt, nahl, first, GBP_BEST_SIG, GBP_BEST_EDG);
         mcur = vcur = pcur = 0;
         ch_copy16(jg, w->J, JBYTES);
@@ -1466,6 +1524,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         dwell = 0;
     };
     auto save_best = [&]() {
+        best_alt = alt;
         ch_save_best<R, T, NC, KIND>(w, ml, k, mcur, vcur, iteration, likelihood + prior, err, GBP_BEST_SIG, GBP_BEST_EDG);
     };
 
@@ -1524,6 +1583,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             const SpecOut<R, NS> so = tc.rounds[tc.warp].win;
             const int byte = tc.rounds[tc.warp].win_byte;
             ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
+            if constexpr (KIND == KIND_FDEM_Z) ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
             dwell = 0;
             misfit = so.misfit;
             prior = so.prior;
@@ -1551,7 +1611,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             spec_stop = STOP_NONE;
             rng.iter = (uint32_t)total + 1u;  // sub-stream of this accept_reject step
             rng.block = 0u;
-            ar_step<false, R, T, NC, KIND>(w, K, S, tab, alt, nahl, jg, h, accepted, chol_failed);
+            ar_step<false, R, T, NC, KIND>(w, K, S, tab, alt, alt_ref, nahl, jg, h, accepted, chol_failed);
         }
         failed = chol_failed;
         rej_run = accepted ? 0 : rej_run + 1;
@@ -1642,6 +1702,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         if (P.max_iterations > 0 && total >= P.max_iterations) go = false;
     }
     ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);
+    if constexpr (KIND == KIND_FDEM_Z) ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
 
     ch_write_model(w, ml, k, mcur, vcur, P.out.cur_sigma ? P.out.cur_sigma + (size_t)chain * ml : nullptr,
                    P.out.cur_edges ? P.out.cur_edges + (size_t)chain * (ml + 1) : nullptr);
@@ -1688,6 +1749,8 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_N_MOVE] = (double)w->ctr[CT_ACT2];
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
         s[GBP_S_TOTAL_ITER] = (double)total;
+        s[GBP_S_CUR_HEIGHT] = (KIND == KIND_FDEM_Z) ? (double)alt : P.altitude[chain];
+        s[GBP_S_BEST_HEIGHT] = (KIND == KIND_FDEM_Z) ? (double)best_alt : P.altitude[chain];
         if (spec_rounds > 0) {
             atomicAdd(&g_diag[8], (unsigned long long)w->ctr[CT_N_SPEC]);
             atomicAdd(&g_diag[9], (unsigned long long)spec_rounds);

@@ -120,7 +120,7 @@ _OPTION_DEFAULTS = dict(
     add_min=3.0, add_max=20.0, add_prop_var=1e-6, n_sigma_bins=250, n_err_bins=99, sigma_bins_nstd=4.0,
     burn_in_min_iter=5000, n_systems=1,
     rel_init2=0.05, rel_min2=0.001, rel_max2=0.5, rel_prop_var2=1e-6, add_init2=5.0, add_min2=3.0, add_max2=20.0,
-    add_prop_var2=1e-6)
+    add_prop_var2=1e-6, solve_height=0, max_height_change=1.0, height_prop_var=0.01)
 _PER_SYSTEM = ("rel_init", "rel_min", "rel_max", "rel_prop_var", "add_init", "add_min", "add_max", "add_prop_var")
 
 # reference option-file keys -> gbp_options fields (resolve_options; user_parameters.py:40-44)
@@ -135,7 +135,8 @@ _REFERENCE_KEYS = dict(
     minimum_relative_error="rel_min", maximum_relative_error="rel_max",
     relative_error_proposal_variance="rel_prop_var", initial_additive_error="add_init",
     minimum_additive_error="add_min", maximum_additive_error="add_max",
-    additive_error_proposal_variance="add_prop_var")
+    additive_error_proposal_variance="add_prop_var",
+    solve_z="solve_height", maximum_z_change="max_height_change", z_proposal_variance="height_prop_var")
 
 
 def make_options(**kw):
@@ -260,10 +261,12 @@ def chain_buffer_shapes(opt, B):
         ncells_hist=((B, ml + 1), np.int32), rel_hist=(eshape, np.int32),
         add_hist=(eshape, np.int32), misfit_trace=((B, N2), np.float64),
         accept_trace=((B, N2), np.uint8), best_sigma=((B, ml), np.float64), best_edges=((B, ml + 1), np.float64),
-        cur_sigma=((B, ml), np.float64), cur_edges=((B, ml + 1), np.float64), scalars=((B, NSCALARS), np.float64))
+        cur_sigma=((B, ml), np.float64), cur_edges=((B, ml + 1), np.float64), scalars=((B, NSCALARS), np.float64),
+        height_hist=((B, opt.n_err_bins), np.int32))
 
 
-DEFAULT_OUTPUTS = BUFFER_FIELDS
+# height_hist (datapoint.z.posterior) joins the default outputs only when the options sample the height (solve_z)
+DEFAULT_OUTPUTS = tuple(f for f in BUFFER_FIELDS if f != "height_hist")
 
 
 def rjmcmc_run(system, opt, data, altitude, seed=0, first_index=0, max_iterations=0, precision=PRECISION_F32,
@@ -277,6 +280,8 @@ def rjmcmc_run(system, opt, data, altitude, seed=0, first_index=0, max_iteration
     lib = _lib.require_cuda()
     td = is_tdem(system)
     f_run, f_run_h = (lib.gbp_tdem_rjmcmc_run, lib.gbp_tdem_rjmcmc_run_host) if td else (lib.gbp_rjmcmc_run, lib.gbp_rjmcmc_run_host)
+    if opt.solve_height and outputs is DEFAULT_OUTPUTS:
+        outputs = DEFAULT_OUTPUTS + ("height_hist",)
     outputs = tuple(outputs)
     if "scalars" not in outputs:
         outputs = outputs + ("scalars",)

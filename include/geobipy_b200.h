@@ -83,6 +83,13 @@ typedef struct {
                                            second entries of the options file's lists (skytem_options) */
     double rel_init2, rel_min2, rel_max2, rel_prop_var2;
     double add_init2, add_min2, add_max2, add_prop_var2;
+    /* Sensor height as an unknown (the options file's solve_z / maximum_z_change / z_proposal_variance:
+     * Point.set_priors pointcloud/Point.py:959-961, set_proposals :977-979, perturb :614-622).  Frequency-domain
+     * datapoints with <= 6 frequencies; the time-domain entry points reject it. */
+    int32_t solve_height;
+    int32_t pad_h_;
+    double max_height_change;           /* prior Uniform[z0 - max_height_change, z0 + max_height_change] */
+    double height_prop_var;             /* variance of the Normal random-walk proposal */
 } gbp_options;
 
 /* One time-domain acquisition system = the contents of a GA-AEM .stm file as gatdaem1d's TDAEMSystem reads
@@ -116,6 +123,7 @@ enum {
     GBP_S_BEST_REL, GBP_S_BEST_ADD, GBP_S_N_RESETS, GBP_S_N_BIRTH, GBP_S_N_DEATH, GBP_S_N_MOVE, GBP_S_N_NONE,
     GBP_S_TOTAL_ITER,   /* accept_reject+update pairs executed, including those before a reset() */
     GBP_S_CUR_REL2, GBP_S_CUR_ADD2, GBP_S_BEST_REL2, GBP_S_BEST_ADD2,  /* system 1 of a dual-moment datapoint */
+    GBP_S_CUR_HEIGHT, GBP_S_BEST_HEIGHT,   /* datapoint.z / best_datapoint.z (the input height unless solve_height) */
     GBP_NSCALARS = 32
 };
 
@@ -135,6 +143,8 @@ typedef struct {
     double *cur_sigma;      /* [B][max_layers]              model.values                    */
     double *cur_edges;      /* [B][max_layers + 1]          model.mesh.edges                */
     double *scalars;        /* [B][GBP_NSCALARS]                                            */
+    int32_t *height_hist;   /* [B][n_err_bins]  datapoint.z.posterior (Point.set_z_posterior :1013-1020): bins of
+                               z - z0 over [-max_height_change, max_height_change]; written when solve_height */
 } gbp_chain_buffers;
 
 /* ---- library ---------------------------------------------------------------------------- */
