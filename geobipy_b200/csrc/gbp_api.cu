@@ -237,7 +237,6 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
         Q.spec_helpers = hmax < 0 ? 0 : (hmax > WARPS - 1 ? WARPS - 1 : hmax);
         const char* m = std::getenv("GBP_SPEC_MIN_REJECTIONS");
         Q.spec_min_rejections = m ? std::atoi(m) : 24;
-        if (KIND == KIND_FDEM_Z) Q.spec_helpers = 0;  // a speculative step does not hand a proposed height back
 
     }
     Q.jstore = g_jstore[dev];

@@ -75,6 +75,7 @@ template <typename R, int NS> struct SpecOut {
     int kn, mp, vp, changed;
     R misfit, prior, likelihood;
     Errs<R, NS> err, ln_err;
+    R alt;   // proposed sensor height (KIND_FDEM_Z)
 };
 enum { OP_HITMAP = 0, OP_EDGES, OP_NCELLS, OP_REL, OP_ADD, OP_MISFIT, OP_ACCEPT, OP_HEIGHT, OP_N = 8 };
 
@@ -1108,6 +1109,7 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                         w->sout.likelihood = tml.b;
                         w->sout.err = err_t;
                         w->sout.ln_err = ln_t_err;
+                        if constexpr (KIND == KIND_FDEM_Z) w->sout.alt = (R)alt_t;
                     }
                     __syncwarp();
                 }
@@ -1140,7 +1142,7 @@ enum { STOP_NONE = 0, STOP_ACCEPT = 1, STOP_OTHER = 2 };
 template <typename R, typename T, int NS> struct SpecRound {
     Hot<R, NS> hot;            // chain state before iteration t0
     SpecOut<R, NS> win;        // outcome of the accepted step the owner adopts
-    T alt;
+    T alt, alt_ref;            // sensor height of the chain state; centre of its prior (KIND_FDEM_Z)
     R nahl;
     T* jg;
     const void* owner_ws;
@@ -1183,7 +1185,8 @@ __device__ __noinline__ bool spec_member_run(WarpState<R, T, NC, KIND>* w, SpecR
     Hot<R, ns_of(KIND)> h = rd->hot;
     h.j_valid = false;
     const int t0 = rd->t0, t_end = rd->t_end, W = rd->W;
-    T alt = rd->alt;   // (a sampled height, KIND_FDEM_Z, is not speculated on: the host turns speculation off)
+    T alt = rd->alt;   // left alone by a speculative step; the proposed height goes back in SpecOut
+    const T alt_ref = rd->alt_ref;
     const R nahl = rd->nahl;
     T* const jg = rd->jg;
     bool stopped = false;
@@ -1203,7 +1206,7 @@ __device__ __noinline__ bool spec_member_run(WarpState<R, T, NC, KIND>* w, SpecR
         h.rng.block = 0u;
         bool accepted = false, chol_failed = false;
         const long long c_s = clock64();
-        ar_step<true, R, T, NC, KIND>(w, K, S, tab, alt, alt, nahl, jg, h, accepted, chol_failed);
+        ar_step<true, R, T, NC, KIND>(w, K, S, tab, alt, alt_ref, nahl, jg, h, accepted, chol_failed);
         if (lane == 0) {
             atomicAdd(&g_diag[3], 1ull);
             atomicAdd(&g_diag[4], (unsigned long long)(clock64() - c_s));
@@ -1296,7 +1299,7 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
 // Owner: claim idle warps and start a round covering iterations total .. total+len-1.  Returns the number of helpers.
 template <typename R, typename T, int NC, int KIND>
 __device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailCtx<R, T, ns_of(KIND)> tc,
-                                             const Hot<R, ns_of(KIND)> h, T alt, R nahl, T* jg, int total, int mult,
+                                             const Hot<R, ns_of(KIND)> h, T alt, T alt_ref, R nahl, T* jg, int total, int mult,
                                              int want, int need)
 {
     const int lane = lane_id();
@@ -1326,6 +1329,7 @@ __device__ __noinline__ int spec_round_begin(WarpState<R, T, NC, KIND>* w, TailC
     if (lane == 0) {
         rd->hot = h;
         rd->alt = alt;
+        rd->alt_ref = alt_ref;
         rd->nahl = nahl;
         rd->jg = jg;
         rd->owner_ws = w;
@@ -1552,7 +1556,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             if (want > tc.max_helpers) want = tc.max_helpers;
             const int need = (rej_run >= 24) ? 2 : 4;
             const long long c0 = clock64();
-            const int nh = spec_round_begin<R, T, NC, KIND>(w, tc, h, alt, nahl, jg, total, spec_mult, want, need);
+            const int nh = spec_round_begin<R, T, NC, KIND>(w, tc, h, alt, alt_ref, nahl, jg, total, spec_mult, want, need);
             if (nh > 0) {
                 spec_left = spec_round_end<R, T, NC, KIND>(w, tc, nh, &spec_stop);
                 spec_rounds++;
@@ -1583,7 +1587,10 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             const SpecOut<R, NS> so = tc.rounds[tc.warp].win;
             const int byte = tc.rounds[tc.warp].win_byte;
             ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
-            if constexpr (KIND == KIND_FDEM_Z) ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
+            if constexpr (KIND == KIND_FDEM_Z) {
+                ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
+                alt = (T)so.alt;
+            }
             dwell = 0;
             misfit = so.misfit;
             prior = so.prior;

@@ -106,3 +106,26 @@ def test_infer_batch(api, oracle):
     # batch composition does not change a sounding's result (stream = (seed, sounding index))
     r2 = api.infer_batch(system, data[5:9], b["height"][5:9], seed=9, first_index=5, n_markov_chains=500, max_iterations=200)
     assert np.array_equal(r2["hitmap"], r["hitmap"][5:9]) and np.array_equal(r2["scalars"], r["scalars"][5:9])
+
+
+def test_inference1d_solve_z(api, oracle):
+    """The options-file keys of the sampled sensor height (solve_z / maximum_z_change / z_proposal_variance,
+    Point.set_priors pointcloud/Point.py:959-961) through Inference1D: height posterior on the prior's bins, the
+    datapoint left at the last sampled height, predicted data consistent with it."""
+    system = _resolve(api)
+    true = api.Model(api.RectilinearMesh1D(edges=[0.0, 5.0, 7.5, np.inf]), [1e-2, 1e-1, 0.03333333])
+    dp = api.FdemDataPoint(z=30.0, system=system)
+    dp.forward(true)
+    dp.data[:] = dp.predictedData
+    dp.z = 30.5   # inverted with a height 0.5 m off
+    inf = api.Inference1D(prng=np.random.default_rng(0), precision=64, n_markov_chains=1000, solve_z=True,
+                          maximum_z_change=1.0, z_proposal_variance=0.01)
+    inf.initialize(dp)
+    inf.infer(None)
+    h = inf.height_posterior
+    assert h.counts.shape == (99,) and h.counts.sum() == inf.n_cells_posterior.counts.sum() == 1000
+    assert np.allclose(h.x_edges[[0, -1]], [29.5, 31.5])
+    assert 29.5 <= dp.z <= 31.5 and dp.z != 30.5 and 29.5 <= inf.best_height <= 31.5
+    chk = api.FdemDataPoint(z=dp.z, system=system)
+    chk.forward(inf.model)
+    assert np.allclose(chk.predictedData, dp.predictedData)

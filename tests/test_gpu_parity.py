@@ -324,7 +324,7 @@ def test_full_size_properties(gpu, systems):
     assert nd == 440
 
 
-@pytest.mark.parametrize("kind", ["fdem", "tdem"])
+@pytest.mark.parametrize("kind", ["fdem", "tdem", "fdem_solve_z"])
 def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, monkeypatch):
     """Idle warps evaluate future iterations of running chains speculatively (gbp_chain.cuh, "speculative evaluation").
     Per-iteration random sub-streams make that exact: every output of a batch that leaves most warps idle (so that
@@ -334,6 +334,11 @@ def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, mon
     if kind == "fdem":
         system, opt = systems[0], gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500)
         data, alt = _observed(oracle, systems[1], 40)
+    elif kind == "fdem_solve_z":   # sampled sensor height: the proposed height comes back from the speculating warp
+        system, opt = systems[0], gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500,
+                                                   solve_height=1, max_height_change=1.0, height_prop_var=0.01)
+        data, alt = _observed(oracle, systems[1], 40)
+        alt = alt + 0.4
     else:
         from geobipy_b200.synthetic import synthetic_batch, skytem_noise_std
         system, opt = gpu.skytem_survey_struct(), gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500, **gpu.SKYTEM_OPTIONS)
