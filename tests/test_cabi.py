@@ -107,3 +107,20 @@ def test_tdem_structs_and_tables(built_lib, oracle):
     bad.sys[0].base_frequency = 25.0   # waveform no longer spans half a period
     with pytest.raises(_lib.GeobipyB200Error):
         ops.tdem_window_operator(bad)
+
+
+def test_solve_z_option_keys_and_buffers(built_lib):
+    """The options file's solve_z / maximum_z_change / z_proposal_variance (Point.set_priors pointcloud/Point.py:959-961,
+    set_proposals :977-979) reach gbp_options; the height histogram is an output only when the height is sampled."""
+    from geobipy_b200 import _lib, ops
+    o = ops.make_options()
+    assert o.solve_height == 0 and "height_hist" not in ops.DEFAULT_OUTPUTS and "height_hist" in _lib.BUFFER_FIELDS
+    o = ops.make_options(solve_z=True, maximum_z_change=2.5, z_proposal_variance=0.04)
+    assert o.solve_height == 1 and o.max_height_change == 2.5 and o.height_prop_var == 0.04
+    shp = ops.chain_buffer_shapes(o, 5)
+    assert shp["height_hist"] == ((5, 99), np.int32)
+    assert _lib.S_CUR_HEIGHT == 29 and _lib.S_BEST_HEIGHT == 30 and _lib.NSCALARS == 32
+    # the struct mirrors stay in step with the header (field order and size)
+    import ctypes
+    assert [n for n, _ in _lib.OptionsC._fields_][-4:] == ["solve_height", "pad_h_", "max_height_change", "height_prop_var"]
+    assert ctypes.sizeof(_lib.OptionsC) == 288 and ctypes.sizeof(_lib.ChainBuffersC) == 13 * ctypes.sizeof(ctypes.c_void_p)

@@ -42,6 +42,8 @@ def _worker(rank, world, port, n_total, q):
         "scalars": torch.stack([idx.double(), idx.double() ** 2], dim=1),
         # per-system error histograms of a dual-moment (time-domain) datapoint: [block, n_systems, n_err_bins]
         "rel_hist": (idx.view(-1, 1, 1) + torch.arange(2).view(1, 2, 1) * 1000 + torch.zeros((1, 1, 99), dtype=torch.int64)).to(torch.int32),
+        # height histogram of a sampled sensor height (solve_z): [block, n_err_bins]
+        "height_hist": (idx.view(-1, 1) * 3 + torch.zeros((1, 99), dtype=torch.int64)).to(torch.int32),
     }
     out = gather_to_rank0(local, n_total)
     if rank == 0:
@@ -70,6 +72,7 @@ def test_gather_world_size_2_gloo(n_total):
     assert np.array_equal(out["scalars"][:, 1], np.arange(n_total) ** 2.0)
     assert out["rel_hist"].shape == (n_total, 2, 99)
     assert np.array_equal(out["rel_hist"][:, 1, 7], np.arange(n_total) + 1000)
+    assert out["height_hist"].shape == (n_total, 99) and np.array_equal(out["height_hist"][:, 50], 3 * np.arange(n_total))
 
 
 def test_summarise_hitmap_matches_numpy():
