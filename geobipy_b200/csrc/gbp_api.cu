@@ -34,6 +34,29 @@ int fail(const std::string& m)
         if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));        \
     } while (0)
 
+// Device allocations of one host-pointer call: freed when the scope ends, on the error paths too.
+struct DevScope {
+    std::vector<void*> ptrs;
+    std::vector<cudaEvent_t> events;
+    ~DevScope()
+    {
+        for (void* q : ptrs) cudaFree(q);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+    template <typename U> cudaError_t alloc(U** out, size_t bytes)
+    {
+        const cudaError_t e = cudaMalloc((void**)out, bytes);
+        if (e == cudaSuccess) ptrs.push_back((void*)*out);
+        return e;
+    }
+    cudaError_t event(cudaEvent_t* ev)
+    {
+        const cudaError_t e = cudaEventCreate(ev);
+        if (e == cudaSuccess) events.push_back(*ev);
+        return e;
+    }
+};
+
 // device copies of the filter-point table, cached per (device, system)
 struct TableCache {
     int device = -1;
@@ -468,12 +491,13 @@ static int fdem_host(bool sens, const gbp_fdem_system* sys, int B, int l_stride,
     int32_t* d_nl = nullptr;
     double *d_s = nullptr, *d_t = nullptr, *d_a = nullptr, *d_o = nullptr, *d_J = nullptr;
     const size_t nm = (size_t)B * l_stride;
-    CK(cudaMalloc(&d_nl, B * sizeof(int32_t)));
-    CK(cudaMalloc(&d_s, nm * sizeof(double)));
-    CK(cudaMalloc(&d_t, nm * sizeof(double)));
-    CK(cudaMalloc(&d_a, B * sizeof(double)));
-    CK(cudaMalloc(&d_o, (size_t)B * C * sizeof(double)));
-    if (sens) CK(cudaMalloc(&d_J, (size_t)B * C * l_stride * sizeof(double)));
+    DevScope ds;
+    CK(ds.alloc(&d_nl, B * sizeof(int32_t)));
+    CK(ds.alloc(&d_s, nm * sizeof(double)));
+    CK(ds.alloc(&d_t, nm * sizeof(double)));
+    CK(ds.alloc(&d_a, B * sizeof(double)));
+    CK(ds.alloc(&d_o, (size_t)B * C * sizeof(double)));
+    if (sens) CK(ds.alloc(&d_J, (size_t)B * C * l_stride * sizeof(double)));
     CK(cudaMemcpy(d_nl, nlayers, B * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_s, sigma, nm * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_t, thickness, nm * sizeof(double), cudaMemcpyHostToDevice));
@@ -488,12 +512,6 @@ static int fdem_host(bool sens, const gbp_fdem_system* sys, int B, int l_stride,
         CK(cudaMemcpy(out, d_o, (size_t)B * C * sizeof(double), cudaMemcpyDeviceToHost));
         if (sens) CK(cudaMemcpy(J, d_J, (size_t)B * C * l_stride * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    cudaFree(d_nl);
-    cudaFree(d_s);
-    cudaFree(d_t);
-    cudaFree(d_a);
-    cudaFree(d_o);
-    cudaFree(d_J);
     return rc;
 }
 
@@ -733,10 +751,11 @@ int gbp_measure_peaks(double* fp32_tflops, double* mufu_gops)
 {
     const int blocks = sm_count() * 8, threads = 256, iters = 4096;
     float* d = nullptr;
-    CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    DevScope ds;
+    CK(ds.alloc(&d, (size_t)blocks * threads * sizeof(float)));
     cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    CK(ds.event(&e0));
+    CK(ds.event(&e1));
     double best_f = 0.0, best_m = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         float ms = 0.f;
@@ -756,9 +775,7 @@ int gbp_measure_peaks(double* fp32_tflops, double* mufu_gops)
         if (rep && m > best_m) best_m = m;
         g_launches += 2;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
+    CK(cudaDeviceSynchronize());
     if (fp32_tflops) *fp32_tflops = best_f;
     if (mufu_gops) *mufu_gops = best_m;
     return 0;
@@ -858,12 +875,13 @@ static int tdem_host(bool sens, const gbp_tdem_survey* sv, int B, int l_stride, 
     int32_t* d_nl = nullptr;
     double *d_s = nullptr, *d_t = nullptr, *d_a = nullptr, *d_o = nullptr, *d_J = nullptr;
     const size_t nm = (size_t)B * l_stride;
-    CK(cudaMalloc(&d_nl, B * sizeof(int32_t)));
-    CK(cudaMalloc(&d_s, nm * sizeof(double)));
-    CK(cudaMalloc(&d_t, nm * sizeof(double)));
-    CK(cudaMalloc(&d_a, B * sizeof(double)));
-    CK(cudaMalloc(&d_o, (size_t)B * C * sizeof(double)));
-    if (sens) CK(cudaMalloc(&d_J, (size_t)B * C * l_stride * sizeof(double)));
+    DevScope ds;
+    CK(ds.alloc(&d_nl, B * sizeof(int32_t)));
+    CK(ds.alloc(&d_s, nm * sizeof(double)));
+    CK(ds.alloc(&d_t, nm * sizeof(double)));
+    CK(ds.alloc(&d_a, B * sizeof(double)));
+    CK(ds.alloc(&d_o, (size_t)B * C * sizeof(double)));
+    if (sens) CK(ds.alloc(&d_J, (size_t)B * C * l_stride * sizeof(double)));
     CK(cudaMemcpy(d_nl, nlayers, B * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_s, sigma, nm * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_t, thickness, nm * sizeof(double), cudaMemcpyHostToDevice));
@@ -877,12 +895,6 @@ static int tdem_host(bool sens, const gbp_tdem_survey* sv, int B, int l_stride, 
         CK(cudaMemcpy(out, d_o, (size_t)B * C * sizeof(double), cudaMemcpyDeviceToHost));
         if (sens) CK(cudaMemcpy(J, d_J, (size_t)B * C * l_stride * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    cudaFree(d_nl);
-    cudaFree(d_s);
-    cudaFree(d_t);
-    cudaFree(d_a);
-    cudaFree(d_o);
-    cudaFree(d_J);
     return rc;
 }
 
