@@ -1007,6 +1007,9 @@ int gbo_run_chain_tdem(const gbo_tdem_system *sys, const gbo_options *opt, const
     survey_t sv;
     survey_tdem(&sv, sys);
     if ((opt->n_systems > 1 ? opt->n_systems : 1) != sv.n_sys) return -2;
+    /* a time-domain datapoint's forward model takes the heights of its loops, sampled through Loop_pair's own priors
+     * (TdemDataPoint.perturb :681-683, EmLoop.set_priors); Point.z does not enter it.  Not restated. */
+    if (opt->solve_height) return -3;
     return run_chain_impl(&sv, opt, data, altitude, seed, sounding_index, max_iterations, out);
 }
 

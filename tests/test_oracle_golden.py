@@ -484,3 +484,11 @@ def test_tdem_chain_invariants(oracle, golden_dir):
     r2 = oracle.run_chain(s, o, g["data"], float(g["altitude"]), 3, 2)
     r3 = oracle.run_chain(s, o, g["data"], float(g["altitude"]), 3, 5)
     assert np.array_equal(r["hitmap"], r2["hitmap"]) and not np.array_equal(r["accept_trace"], r3["accept_trace"])
+
+
+def test_height_is_refused_for_time_domain_datapoints(oracle):
+    """The oracle does not restate the loop-geometry priors of a time-domain datapoint (TdemDataPoint.perturb :681-683):
+    asking for a sampled height there is an error, as it is in the product (gbp_tdem_rjmcmc_run)."""
+    s, o = oracle.make_tdem_system(), oracle.skytem_options(n_markov_chains=10, solve_height=1)
+    with pytest.raises(AssertionError):
+        oracle.run_chain(s, o, np.full(45, 1e-12), 30.0, 1, 0, max_iterations=1)
