@@ -168,6 +168,14 @@ def _extra_posterior_checks(refs, runs, top, p_inside, peak_cells=2):
     assert np.min(np.abs(np.argsort(re)[-3:] - oe.argmax())) <= peak_cells, (np.argsort(re)[-3:], oe.argmax())
 
 
+def _chains(oracle, s, o, data, altitude, seeds, sounding):
+    """Independent oracle chains, one per seed, on the host's cores (the C oracle keeps no global state and ctypes
+    releases the GIL during the call)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(seeds), os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda sd: oracle.run_chain(s, o, data, altitude, sd, sounding), seeds))
+
+
 def test_chain_statistics_match_reference_chains(oracle, golden_dir):
     """Posterior statistics of oracle chains vs 7 reference chains on the same observed data (different
     random streams).  10k-iteration chains of this sampler mix slowly - the reference's own chains differ
@@ -182,7 +190,7 @@ def test_chain_statistics_match_reference_chains(oracle, golden_dir):
     ref_acc = np.mean([r["accept_trace"].mean() for r in refs])
     ref_nc = sum(r["ncells_hist"].astype(np.int64) for r in refs)
     ref_med = np.array([_summary(r["hitmap"]) for r in refs])
-    runs = [oracle.run_chain(s, o, g["data"], float(g["altitude"]), 100 + j, 1) for j in range(7)]
+    runs = _chains(oracle, s, o, g["data"], float(g["altitude"]), [100 + j for j in range(7)], 1)
     acc = np.mean([r["scalars"][oracle.S_N_ACCEPT] / r["scalars"][oracle.S_ITER] for r in runs])
     hm = sum(r["hitmap"].astype(np.int64) for r in runs)
     nc = sum(r["ncells_hist"].astype(np.int64) for r in runs)
@@ -246,7 +254,7 @@ def test_height_chain_statistics_match_reference_chains(oracle, golden_dir):
     assert len(refs) >= 4
     g = refs[0]
     s, o = oracle.make_system(), oracle.resolve_options(n_markov_chains=10000, **HEIGHT)
-    runs = [oracle.run_chain(s, o, g["data"], float(g["altitude"]), 300 + j, 5) for j in range(4)]
+    runs = _chains(oracle, s, o, g["data"], float(g["altitude"]), [300 + j for j in range(4)], 5)
     for r in runs:
         sc = r["scalars"]
         counted = int(sc[oracle.S_ITER]) - int(sc[oracle.S_BURNED_IN_ITER]) + 1
@@ -432,7 +440,7 @@ def test_tdem_chain_statistics_match_reference_chains(oracle, golden_dir):
     ref_acc = np.mean([r["accept_trace"].mean() for r in refs])
     ref_nc = sum(r["ncells_hist"].astype(np.int64) for r in refs)
     ref_med = np.array([_summary(r["hitmap"][:, :200]) for r in refs])
-    runs = [oracle.run_chain(s, o, g["data"], float(g["altitude"]), 200 + j, 2) for j in range(6)]
+    runs = _chains(oracle, s, o, g["data"], float(g["altitude"]), [200 + j for j in range(6)], 2)
     assert abs(runs[0]["scalars"][oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-12
     for r in runs:
         assert int(r["scalars"][oracle.S_ITER]) == int(g["iterations"])            # 10 000 + 5001 + 1
