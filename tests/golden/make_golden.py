@@ -466,6 +466,35 @@ def make_chain(sidx, rep=0, n_markov_chains=10000, height=False):
     print("chain", sidx, "iterations", it, "burned in", inf.burned_in, inf.burned_in_iteration, "s/it", dt / it)
 
 
+def make_height_reset():
+    """What Inference1D.reset() (:984-994) does to a sampled height: recorded from the live reference."""
+    import io
+    import contextlib
+    import json
+    _geobipy()
+    data, z, _, _ = _observed(1)
+    z = z + HEIGHT_BIAS
+    inf = _initialised_inference(data, z, 2000, 5, **HEIGHT_KW)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(200):
+            inf.accept_reject()
+            inf.update()
+    d = inf.datapoint
+    rec = dict(z_input=float(z), z_before_reset=float(d.z.item()),
+               prior_before=[float(d.z.prior._min.item()), float(d.z.prior._max.item())],
+               relative_error_before=float(np.asarray(d.relative_error).item()))
+    with contextlib.redirect_stdout(io.StringIO()):
+        inf.reset()
+    d = inf.datapoint
+    rec.update(z_after_reset=float(d.z.item()), prior_after=[float(d.z.prior._min.item()), float(d.z.prior._max.item())],
+               proposal_mean_after=float(np.asarray(d.z.proposal.mean).item()),
+               posterior_relative_to_after=float(np.asarray(d.z.posterior.mesh.relative_to).item()),
+               posterior_edges_after=[float(np.asarray(d.z.posterior.mesh.edges)[0]), float(np.asarray(d.z.posterior.mesh.edges)[-1])],
+               relative_error_after=float(np.asarray(d.relative_error).item()), iteration_after=int(inf.iteration))
+    json.dump(rec, open(os.path.join(HERE, "height_reset.json"), "w"), indent=1)
+    print(rec)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "tdem":
@@ -484,5 +513,7 @@ if __name__ == "__main__":
         make_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     elif what == "transitions_height":
         make_transitions(n_soundings=3, n_iter=250, height=True)
+    elif what == "height_reset":
+        make_height_reset()
     elif what == "height_chain":
         make_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0, height=True)

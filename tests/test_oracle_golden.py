@@ -500,3 +500,30 @@ def test_height_is_refused_for_time_domain_datapoints(oracle):
     s, o = oracle.make_tdem_system(), oracle.skytem_options(n_markov_chains=10, solve_height=1)
     with pytest.raises(AssertionError):
         oracle.run_chain(s, o, np.full(45, 1e-12), 30.0, 1, 0, max_iterations=1)
+
+
+def test_height_prior_is_recentred_by_reset(oracle, golden_dir):
+    """Inference1D.reset() (:984-994) re-initialises with the CURRENT datapoint: recorded from the live reference
+    (tests/golden/height_reset.json) the sampled height is kept, its prior / proposal / posterior bins are re-centred
+    on it and the errors go back to their initial values.  The oracle does the same: with a +-0.05 m prior and a
+    3-iteration reset window the chains leave the original prior interval, by at most one half-width per (re)start."""
+    import json
+    ref = json.load(open(os.path.join(golden_dir, "height_reset.json")))
+    assert ref["z_after_reset"] == ref["z_before_reset"] != ref["z_input"]
+    assert np.allclose(ref["prior_after"], [ref["z_before_reset"] - 1.0, ref["z_before_reset"] + 1.0], rtol=0, atol=1e-12)
+    assert np.allclose(ref["prior_before"], [ref["z_input"] - 1.0, ref["z_input"] + 1.0], rtol=0, atol=1e-12)
+    assert ref["proposal_mean_after"] == ref["posterior_relative_to_after"] == ref["z_before_reset"]
+    assert ref["posterior_edges_after"] == [-1.0, 1.0] and ref["relative_error_after"] == 0.05 and ref["iteration_after"] == 0
+    g = np.load(os.path.join(golden_dir, "ref_height_chain_5.npz"))
+    z0, dz = float(g["altitude"]), 0.05
+    s = oracle.make_system()
+    o = oracle.resolve_options(n_markov_chains=400, update_plot_every=3, burn_in_min_iter=100000, solve_height=1,
+                               max_height_change=dz, height_prop_var=0.01)
+    moved = []
+    for seed in range(12):
+        sc = oracle.run_chain(s, o, g["data"], z0, seed, 5)["scalars"]
+        # three resets, the restart with limiters, two more resets, then the chain is given up (Inference1D.infer :666-677)
+        assert sc[oracle.S_N_RESETS] == 3 and sc[oracle.S_FAILED] == 1
+        moved.append(abs(sc[oracle.S_CUR_HEIGHT] - z0))
+        assert moved[-1] <= 7 * dz + 1e-12
+    assert np.mean(np.array(moved) > dz) >= 0.5, moved
