@@ -45,7 +45,10 @@ typedef struct {
     double rel_init2, rel_min2, rel_max2, rel_prop_var2;
     double add_init2, add_min2, add_max2, add_prop_var2;
     /* solve_z (Point.set_priors :959-961, set_proposals :977-979): sensor height sampled with a Uniform prior
-     * [z0 - max_height_change, z0 + max_height_change] and a Normal(z, height_prop_var) random walk */
+     * [z0 - max_height_change, z0 + max_height_change] and a Normal(z, height_prop_var) random walk.  For a time-domain
+     * datapoint this is the options file's solve_transmitter_z (tempest_options :104-108): the transmitter loop's
+     * height, receiver offset fixed (Loop_pair.set_priors Loop_pair.py:166-178, Loop_pair.Geometry :62-78), drawn
+     * after the error proposals (TdemDataPoint.perturb :681-683) */
     int32_t solve_height;
     int32_t pad_h_;
     double max_height_change, height_prop_var;

@@ -281,15 +281,24 @@ static double log_uniform_logpdf(double x, double mn, double mx)
 
 /* DataPoint.probability :351-395: multivariate Uniform(log=True) priors sum over the systems
  * (UniformDistribution.py:116) */
-static double datapoint_probability(const gbo_options *o, int n_sys, const double *rel, const double *add, double dz)
+static double height_logprior(const gbo_options *o, double dz)
 {
-    /* Point.probability :160-196 first (height prior, dz = z - z_ref), then the errors (DataPoint.probability :352-389) */
+    return (dz >= -o->max_height_change && dz <= o->max_height_change) ? -log(2.0 * o->max_height_change) : -INFINITY;
+}
+
+/* height_last = 0 (frequency domain, solve_z): Point.probability :160-196 first (height prior, dz = z - z_ref), then the
+ * errors (DataPoint.probability :352-389).  height_last = 1 (time domain, solve_transmitter_z): the sampled height is the
+ * transmitter loop's and its prior is added after the errors (TdemDataPoint.probability :950-951 =
+ * DataPoint.probability + Loop_pair.probability, Loop_pair.py:294-295). */
+static double datapoint_probability(const gbo_options *o, int n_sys, const double *rel, const double *add, double dz, int height_last)
+{
     double p = 0.0;
-    if (o->solve_height) p += (dz >= -o->max_height_change && dz <= o->max_height_change) ? -log(2.0 * o->max_height_change) : -INFINITY;
+    if (o->solve_height && !height_last) p += height_logprior(o, dz);
     for (int s = 0; s < n_sys; ++s) {
         if (o->solve_relative_error) p += log_uniform_logpdf(rel[s], o_rel_min(o, s), o_rel_max(o, s));
         if (o->solve_additive_error) p += log_uniform_logpdf(add[s], o_add_min(o, s), o_add_max(o, s));
     }
+    if (o->solve_height && height_last) p += height_logprior(o, dz);
     return p;
 }
 
@@ -724,7 +733,7 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
     double var[GBO_MAXC];
     data_variance(&c->sv, c->data, c->dp.rel, c->dp.add, var);
     c->misfit = data_misfit(c->C, c->data, c->dp.pred, var);
-    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->sv.n_sys, c->dp.rel, c->dp.add, 0.0);
+    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->sv.n_sys, c->dp.rel, c->dp.add, 0.0, c->sv.tdem != NULL);
     c->likelihood = data_likelihood(c->C, c->data, c->dp.pred, var);
     c->posterior = c->likelihood + c->prior;
     c->burned_in = 0;
@@ -781,8 +790,10 @@ static int chain_step(chain_t *c)
     test = remap;
     for (int i = 0; i < k; ++i) test.sigma[i] = exp(mean[i] + dx[i]);
 
-    /* test_datapoint.perturb(): height first (Point.perturb :614-622), then the errors (DataPoint.perturb :561-573) */
-    if (o->solve_height)
+    /* test_datapoint.perturb(): height first (Point.perturb :614-622), then the errors (DataPoint.perturb :561-573);
+     * a time-domain datapoint perturbs its loops after the errors (TdemDataPoint.perturb :681-683 -> Loop_pair.perturb
+     * Loop_pair.py:161-164 -> EmLoop.perturb -> Point.perturb on the transmitter: solve_transmitter_z) */
+    if (o->solve_height && !c->sv.tdem)
         tdp.z = propose_height(&c->rng, tdp.z, o->height_prop_var, c->z_ref - o->max_height_change, c->z_ref + o->max_height_change);
     if (c->sv.n_sys == 1) {
         if (o->solve_relative_error) tdp.rel[0] = propose_error(&c->rng, tdp.rel[0], o->rel_prop_var, o->rel_min, o->rel_max);
@@ -793,11 +804,13 @@ static int chain_step(chain_t *c)
         if (o->solve_relative_error) propose_error2(&c->rng, tdp.rel, rv, rmn, rmx);
         if (o->solve_additive_error) propose_error2(&c->rng, tdp.add, av, amn, amx);
     }
+    if (o->solve_height && c->sv.tdem)
+        tdp.z = propose_height(&c->rng, tdp.z, o->height_prop_var, c->z_ref - o->max_height_change, c->z_ref + o->max_height_change);
 
     forward(c, &test, tdp.z, tdp.pred);
     data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
     double t_misfit = data_misfit(C, c->data, tdp.pred, var);
-    double t_prior = datapoint_probability(o, c->sv.n_sys, tdp.rel, tdp.add, tdp.z - c->z_ref);
+    double t_prior = datapoint_probability(o, c->sv.n_sys, tdp.rel, tdp.add, tdp.z - c->z_ref, c->sv.tdem != NULL);
     if (t_prior == -INFINITY) return 0;
     t_prior += model_probability(o, &test, c->sigma_ref);
     if (t_prior == -INFINITY) return 0;
@@ -1007,9 +1020,8 @@ int gbo_run_chain_tdem(const gbo_tdem_system *sys, const gbo_options *opt, const
     survey_t sv;
     survey_tdem(&sv, sys);
     if ((opt->n_systems > 1 ? opt->n_systems : 1) != sv.n_sys) return -2;
-    /* a time-domain datapoint's forward model takes the heights of its loops, sampled through Loop_pair's own priors
-     * (TdemDataPoint.perturb :681-683, EmLoop.set_priors); Point.z does not enter it.  Not restated. */
-    if (opt->solve_height) return -3;
+    /* solve_height of a time-domain datapoint = the options file's solve_transmitter_z (the transmitter loop's height,
+     * receiver offset fixed: Loop_pair.Geometry Loop_pair.py:62-78); the other loop-geometry unknowns are not restated */
     return run_chain_impl(&sv, opt, data, altitude, seed, sounding_index, max_iterations, out);
 }
 
@@ -1071,7 +1083,7 @@ static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_tr
     sv_forward(sv, z_test, k, test.sigma, thk, t->pred_test);
     data_variance(sv, t->data, t->rel_test, t->add_test, var);
     t->misfit_test = data_misfit(C, t->data, t->pred_test, var);
-    t->prior_test = datapoint_probability(o, sv->n_sys, t->rel_test, t->add_test, o->solve_height ? z_test - t->altitude_ref : 0.0) +
+    t->prior_test = datapoint_probability(o, sv->n_sys, t->rel_test, t->add_test, o->solve_height ? z_test - t->altitude_ref : 0.0, sv->tdem != NULL) +
                     model_probability(o, &test, t->sigma_ref);
     t->likelihood_test = data_likelihood(C, t->data, t->pred_test, var);
     t->proposal = 1.0;

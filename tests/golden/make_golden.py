@@ -299,7 +299,11 @@ def _tdem_datapoint(data, z):
                          transmitter_loop=tx, receiver_loop=rx)
 
 
-def make_tdem_transitions(n_soundings=5, n_iter=200):
+# solve_transmitter_z of the time-domain height tests (tempest_options keys :104-108; same prior / proposal as HEIGHT_KW)
+TX_HEIGHT_KW = dict(solve_transmitter_z=True, maximum_transmitter_z_change=1.0, transmitter_z_proposal_variance=0.01)
+
+
+def make_tdem_transitions(n_soundings=5, n_iter=200, height=False):
     """Per-term records of the reference's Inference1D.accept_reject with a dual-moment TdemDataPoint; the external
     gatdaem1d is replaced by tests/golden/fake_gatdaem1d.py (oracle forward), so these pin the sampler terms
     AROUND the forward: time-domain std model, per-system error priors / proposals, 45-channel Hessian."""
@@ -318,7 +322,10 @@ def make_tdem_transitions(n_soundings=5, n_iter=200):
         clean = O.tdem_forward(tsys, z, sigma, np.r_[np.diff(edges)[:-1], 1.0])
         data = clean + noise * skytem_noise_std(clean, tc, (26, 19))
         kw = dict(kw0)
-        kw["prng"] = get_prng(seed=2000 + sidx)
+        kw["prng"] = get_prng(seed=(4000 if height else 2000) + sidx)
+        if height:
+            kw.update(TX_HEIGHT_KW)
+            z = z + HEIGHT_BIAS
         inf = Inference1D(**kw)
         dp = _tdem_datapoint(data, z)
         with contextlib.redirect_stdout(io.StringIO()):
@@ -331,6 +338,7 @@ def make_tdem_transitions(n_soundings=5, n_iter=200):
             pred_in = np.asarray(dp0.predictedData).copy()
             rel_cur = np.asarray(dp0.relative_error).copy()
             add_cur = np.asarray(dp0.additive_error).copy()
+            z_cur = float(np.asarray(dp0.transmitter.z).item())
             tdp = deepcopy(dp0)
             remapped, test = m0.perturb(tdp, -npinf, npinf, alpha=inf.covariance_scaling)
             action = ACT[remapped.mesh.action[0]]
@@ -344,7 +352,8 @@ def make_tdem_transitions(n_soundings=5, n_iter=200):
             prior = float(tdp.probability) + float(test.probability(inf.solve_parameter, inf.solve_gradient))
             like = float(tdp.likelihood(log=True))
             prop, prop1 = test.proposal_probabilities(remapped, tdp, alpha=inf.covariance_scaling)
-            recs.append(dict(sounding=sidx, altitude=z, sigma_ref=hs, data=np.asarray(data), k=k, action=action,
+            recs.append(dict(sounding=sidx, altitude=z_cur, altitude_ref=z,
+                             altitude_test=float(np.asarray(tdp.transmitter.z).item()), sigma_ref=hs, data=np.asarray(data), k=k, action=action,
                              edges=np.asarray(remapped.mesh.edges).copy(), sigma_remap=np.asarray(remapped.values).copy(),
                              sigma_test=np.asarray(test.values).copy(), rel_cur=rel_cur, add_cur=add_cur,
                              rel_test=np.asarray(tdp.relative_error).copy(), add_test=np.asarray(tdp.additive_error).copy(),
@@ -369,11 +378,11 @@ def make_tdem_transitions(n_soundings=5, n_iter=200):
             for i, v in enumerate(vals):
                 obj[i] = np.asarray(v)
             out[key] = obj
-    np.savez_compressed(os.path.join(HERE, "tdem_transitions.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "tdem_transitions_height.npz" if height else "tdem_transitions.npz"), **out)
     print("tdem transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
 
 
-def make_tdem_chain(sidx, rep=0, n_markov_chains=10000):
+def make_tdem_chain(sidx, rep=0, n_markov_chains=10000, height=False):
     """A full chain of the live reference with a dual-moment TdemDataPoint (skytem_options with n_markov_chains
     reduced), driven through fake_gatdaem1d (oracle forward).  Posterior arrays -> ref_tdem_chain_<i>[_r<rep>].npz."""
     kw = _tdem_setup()
@@ -388,7 +397,10 @@ def make_tdem_chain(sidx, rep=0, n_markov_chains=10000):
     clean = O.tdem_forward(tsys, z, sigma, np.r_[np.diff(edges)[:-1], 1.0])
     data = clean + noise * skytem_noise_std(clean, tc, (26, 19))
     kw["n_markov_chains"] = n_markov_chains
-    kw["prng"] = get_prng(seed=7000 + sidx + 100 * rep)
+    kw["prng"] = get_prng(seed=(9000 if height else 7000) + sidx + 100 * rep)
+    if height:   # transmitter height sampled, starting 0.4 m above the simulated one
+        kw.update(TX_HEIGHT_KW)
+        z = z + HEIGHT_BIAS
     inf = Inference1D(**kw)
     dp = _tdem_datapoint(data, z)
     t0 = time.time()
@@ -407,8 +419,14 @@ def make_tdem_chain(sidx, rep=0, n_markov_chains=10000):
     it = int(inf.iteration)
     rel = np.stack([np.asarray(p.counts, dtype=np.int32) for p in inf.datapoint.relative_error.posterior])
     add = np.stack([np.asarray(p.counts, dtype=np.int32) for p in inf.datapoint.additive_error.posterior])
+    extra, stem = {}, "ref_tdem_chain_"
+    if height:
+        stem = "ref_tdem_height_chain_"
+        extra = dict(height_hist=np.asarray(inf.datapoint.transmitter.z.posterior.counts, dtype=np.int32),
+                     height_cur=float(np.asarray(inf.datapoint.transmitter.z).item()),
+                     height_best=float(np.asarray(inf.best_datapoint.transmitter.z).item()))
     np.savez_compressed(
-        os.path.join(HERE, "ref_tdem_chain_%d.npz" % sidx if rep == 0 else "ref_tdem_chain_%d_r%d.npz" % (sidx, rep)),
+        os.path.join(HERE, stem + ("%d.npz" % sidx if rep == 0 else "%d_r%d.npz" % (sidx, rep))), **extra,
         sounding=sidx, data=data, altitude=z, true_edges=edges, true_sigma=sigma, halfspace=float(inf.halfspace.item()),
         iterations=it, failed=bool(failed), burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
         hitmap=np.asarray(inf.model.values.posterior.counts, dtype=np.int32),
@@ -501,8 +519,12 @@ if __name__ == "__main__":
         make_tdem()
     if what == "tdem_transitions":
         make_tdem_transitions()
+    if what == "tdem_transitions_height":
+        make_tdem_transitions(n_soundings=3, n_iter=200, height=True)
     if what == "tdem_chain":
         make_tdem_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    if what == "tdem_height_chain":
+        make_tdem_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0, height=True)
     if what == "fdem":
         make_fdem()
     elif what == "bins":
