@@ -303,9 +303,9 @@ class Inference1D:
         self.seed, self.sounding_index = int(seed) & (2 ** 64 - 1), int(sounding_index)
         self.n_markov_chains, self.update_plot_every = int(n_markov_chains), int(update_plot_every)
         self.precision, self.device = precision, device
-        self.options = ops.make_options(covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains,
-                                        update_plot_every=update_plot_every, solve_gradient=int(bool(solve_gradient)),
-                                        solve_parameter=int(bool(solve_parameter)), **kwargs)
+        self.options = ops.options_from_reference(
+            covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains, update_plot_every=update_plot_every,
+            solve_gradient=int(bool(solve_gradient)), solve_parameter=int(bool(solve_parameter)), **kwargs)
         self.user_options = kwargs
         self.datapoint = None
 
@@ -399,7 +399,7 @@ def infer_batch(system, data, altitude, seed=0, precision=_lib.PRECISION_F32, de
     `data` [B, 2F] are inverted concurrently, one warp per sounding.  Returns the dict of posterior arrays
     (`include/geobipy_b200.h` gbp_chain_buffers) plus the options struct used."""
     s = system.c_struct if hasattr(system, "c_struct") else system
-    opt = ops.make_options(**options)
+    opt = ops.options_from_reference(**options)
     r = ops.rjmcmc_run(s, opt, data, altitude, seed=seed, first_index=first_index, max_iterations=max_iterations,
                        precision=precision, device=device, outputs=outputs)
     r["options"] = opt

@@ -166,7 +166,7 @@ class Inference3D:
         if index is None and fiducial is not None:
             index = int(np.flatnonzero((d.fiducial == fiducial) & ((d.lineNumber == line_number) if line_number is not None else True))[0])
         sel = np.arange(d.nPoints) if index is None else np.atleast_1d(index)
-        opt = ops.make_options(**options)
+        opt = ops.options_from_reference(**options)
         self.options = opt
         sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct   # time-domain surveys: systems + tx-rx offset
         if sharded:

@@ -168,6 +168,33 @@ def make_options(**kw):
     return o
 
 
+# Keys the shipped option files carry (resolve_options :64, :113, :129; skytem_options :65) that the reference's classes
+# never read: Point.set_priors / set_proposals (pointcloud/Point.py:959-961, :977-979) look for solve_z,
+# maximum_z_change and z_proposal_variance, so `solve_height = True` in an options file samples nothing there.
+_DEAD_REFERENCE_KEYS = ("solve_height", "maximum_height_change", "height_proposal_variance")
+# unknowns of the reference that are not built here: asking for one is an error, not a silent no-op
+_UNBUILT_PREFIXES = ("solve_transmitter_", "solve_receiver_")
+_UNBUILT_KEYS = ("solve_x", "solve_y", "solve_calibration")
+
+
+def options_from_reference(**kw):
+    """`make_options` for keyword arguments that come from a reference options file (`Inference1D(**options)`,
+    `Inference3D.infer(**options)`): the keys the reference itself ignores are ignored here too (with a warning when
+    they ask for something), and unknowns this library does not sample raise instead of being dropped."""
+    import warnings
+    kw = dict(kw)
+    if kw.get("solve_height"):
+        warnings.warn("solve_height / maximum_height_change / height_proposal_variance are not read by the reference "
+                      "(Point.set_priors reads solve_z, maximum_z_change, z_proposal_variance): ignored, as there",
+                      stacklevel=3)
+    for k in _DEAD_REFERENCE_KEYS:
+        kw.pop(k, None)
+    for k, v in kw.items():
+        if (k in _UNBUILT_KEYS or k.startswith(_UNBUILT_PREFIXES)) and np.any(v):
+            raise NotImplementedError("%s: this unknown of the reference is not built in geobipy_b200 (DESIGN.md section 7)" % k)
+    return make_options(**kw)
+
+
 def n_depth(opt):
     return int(_lib.load().gbp_n_depth(ctypes.addressof(opt)))
 

@@ -124,3 +124,31 @@ def test_solve_z_option_keys_and_buffers(built_lib):
     import ctypes
     assert [n for n, _ in _lib.OptionsC._fields_][-4:] == ["solve_height", "pad_h_", "max_height_change", "height_prop_var"]
     assert ctypes.sizeof(_lib.OptionsC) == 288 and ctypes.sizeof(_lib.ChainBuffersC) == 13 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_options_from_a_reference_options_file(built_lib):
+    """Keyword arguments that come from a reference options file: the height keys the shipped files carry are dead in
+    the reference (Point.set_priors reads solve_z; checked on the live reference: solve_height=True leaves
+    datapoint.z without a prior) and are ignored here too; unknowns that are not built raise."""
+    import warnings
+    from geobipy_b200 import api, ops
+    shipped = dict(solve_height=False, maximum_height_change=1.0, height_proposal_variance=0.01, solve_calibration=False,
+                   solve_transmitter_z=False, solve_receiver_pitch=False, n_markov_chains=1000)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        o = ops.options_from_reference(**shipped)
+    assert o.solve_height == 0 and o.n_markov_chains == 1000
+    with pytest.warns(UserWarning, match="solve_height"):
+        o = ops.options_from_reference(**dict(shipped, solve_height=True))
+    assert o.solve_height == 0
+    o = ops.options_from_reference(**dict(shipped, solve_z=True, maximum_z_change=0.5, z_proposal_variance=0.02))
+    assert o.solve_height == 1 and o.max_height_change == 0.5 and o.height_prop_var == 0.02
+    for key in ("solve_transmitter_z", "solve_receiver_pitch", "solve_calibration", "solve_x"):
+        with pytest.raises(NotImplementedError, match=key):
+            ops.options_from_reference(**dict(shipped, **{key: True}))
+    # the object-level mirror goes through the same filter
+    with pytest.warns(UserWarning, match="solve_height"):
+        inf = api.Inference1D(prng=np.random.default_rng(0), **dict(shipped, solve_height=True))
+    assert inf.options.solve_height == 0
+    with pytest.raises(NotImplementedError):
+        api.Inference1D(prng=np.random.default_rng(0), **dict(shipped, solve_transmitter_z=True))
