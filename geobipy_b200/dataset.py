@@ -142,6 +142,10 @@ def summarise(result, opt):
     eh = np.asarray(result["edges_hist"]).astype(np.float64)
     out["interface_probability"] = eh / np.maximum(eh.sum(axis=1, keepdims=True), 1.0)
     out["depth_edges"] = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
+    if "height_hist" in result:   # sampled sensor height (solve_z): posterior mean of z - z0 per sounding [B]
+        hh = np.asarray(result["height_hist"]).astype(np.float64)
+        c = -opt.max_height_change + (np.arange(hh.shape[1]) + 0.5) * (2.0 * opt.max_height_change / hh.shape[1])
+        out["height_change_mean"] = (hh * c[None, :]).sum(axis=1) / np.maximum(hh.sum(axis=1), 1.0)
     return out
 
 
