@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib, api, ops
 
-__all__ = ["FdemData", "Inference3D"]
+__all__ = ["FdemData", "Inference3D", "summarise", "opacity_and_doi"]
 
 _LINE = ("line", "linenumber", "line_number")
 _FID = ("fid", "fiducial", "id")
@@ -149,6 +149,38 @@ def summarise(result, opt):
     return out
 
 
+def opacity_and_doi(p_low, p_high, depth_edges, doi_percent=67.0):
+    """Opacity and depth of investigation of one flight line from its credible intervals (restated from
+    Inference2D.compute_opacity inversion/Inference2D.py:1011-1023 = Histogram.opacity / transparency
+    classes/statistics/Histogram.py:330-354, 509-541 over Mesh._credible_range classes/mesh/Mesh.py:58-78, and
+    Inference2D.compute_doi :493-532; no HDF5 reader in this image, so not run against the reference's own).
+
+    p_low / p_high [n_soundings, n_depth]: the 5 % / 95 % conductivities (compute_opacity's percent = 90).  The credible
+    range is their ratio in decades (the hitmap's value axis has log = 10, Model.py:677-679); transparency is that
+    range normalised by its minimum and maximum over the WHOLE line, NaN -> 1; opacity = 1 - transparency.  The depth
+    of investigation is the centre of the deepest cell whose opacity reaches doi_percent / 100, searched from the
+    bottom up and never above the second cell from the top (the loop of compute_doi stops at j = 1... 0).
+    Returns (opacity [n, n_depth], doi [n])."""
+    lo, hi = np.asarray(p_low, dtype=np.float64), np.asarray(p_high, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rng = np.abs(np.log10(hi) - np.log10(lo))
+    mn, mx = np.nanmin(rng), np.nanmax(rng)
+    t = (rng - mn) / (mx - mn) if (mx - mn) > 0.0 else rng - mn
+    t = np.where(np.isnan(t), 1.0, t)
+    opacity = 1.0 - t
+    e = np.asarray(depth_edges, dtype=np.float64)
+    centres = 0.5 * (e[1:] + e[:-1])
+    p = 0.01 * doi_percent
+    n, nz = opacity.shape
+    doi = np.empty(n)
+    for i in range(n):
+        j = nz - 1
+        while opacity[i, j] < p and j >= 1:   # compute_doi :514-517
+            j -= 1
+        doi[i] = centres[j]
+    return opacity, doi
+
+
 class Inference3D:
     """Survey driver: `Inference3D(data).infer(**options)` (inversion/Inference3D.py:451-492, :503-635)."""
 
@@ -202,9 +234,12 @@ class Inference3D:
             m = d.lineNumber[r["index"]] == ln
             idx = r["index"][m]
             path = os.path.join(directory, "%s.npz" % (("%g" % ln)))
+            line = {}
+            if "summary_p5" in r and "summary_p95" in r:   # per-line products of Inference2D (opacity, doi)
+                line["opacity"], line["doi"] = opacity_and_doi(r["summary_p5"][m], r["summary_p95"][m], r["summary_depth_edges"])
             np.savez_compressed(
                 path, line_number=ln, fiducial=d.fiducial[idx], x=d.x[idx], y=d.y[idx], z=d.z[idx],
-                elevation=d.elevation[idx], data=d.data[idx],
+                elevation=d.elevation[idx], data=d.data[idx], **line,
                 **{k: (v[m] if isinstance(v, np.ndarray) and v.shape[:1] == m.shape else v) for k, v in r.items()})
             files.append(path)
         return files

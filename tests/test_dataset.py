@@ -96,3 +96,50 @@ def test_inference3d_end_to_end(tmp_path, golden_dir, built_lib):
     assert [os.path.basename(f) for f in files] == ["100.npz", "200.npz"]
     z = np.load(files[1])
     assert z["hitmap"].shape == (3, 250, 440) and list(z["fiducial"]) == [3.0, 4.0, 5.0]
+
+
+def test_opacity_and_doi_of_a_line():
+    """Inference2D.compute_opacity (:1011-1023) / compute_doi (:493-532) restated on the p5 / p95 summaries: a hand
+    example with 2 soundings x 5 depth cells."""
+    from geobipy_b200.dataset import opacity_and_doi
+    p5 = np.array([[1e-2, 1e-2, 1e-2, 1e-3, 1e-4], [1e-2, 1e-2, 1e-2, 1e-2, 1e-2]])
+    p95 = np.array([[2e-2, 2e-2, 1e-1, 1e-1, 1e0], [2e-2, 2e-2, 2e-2, 2e-2, np.nan]])
+    edges = np.arange(6) * 10.0
+    op, doi = opacity_and_doi(p5, p95, edges)
+    rng = np.abs(np.log10(p95) - np.log10(p5))              # decades: [0.301, 0.301, 1, 2, 4], [0.301 x4, nan]
+    t = (rng - np.log10(2.0)) / (4.0 - np.log10(2.0))       # normalised over the whole line
+    t[1, 4] = 1.0                                           # NaN -> fully transparent
+    assert np.allclose(op, 1.0 - t)
+    # sounding 0: opacity [1, 1, 0.811, 0.541, 0] -> deepest cell with opacity >= 0.67 is cell 2 (centre 25 m);
+    # sounding 1: cell 4 is transparent, cell 3 opaque -> 35 m
+    assert np.allclose(doi, [25.0, 35.0])
+    # nothing reaches the cut-off below the top: the search stops at the top cell (compute_doi's j >= 1 guard)
+    op2, doi2 = opacity_and_doi(np.array([[1e-3, 1e-4, 1e-4]]), np.array([[1e-3, 1e0, 1e0]]), np.arange(4) * 1.0, doi_percent=100.0)
+    assert np.allclose(op2, [[1.0, 0.0, 0.0]]) and doi2[0] == 0.5
+    # a line with one and the same credible range everywhere is fully opaque
+    op3, doi3 = opacity_and_doi(np.full((2, 3), 1e-2), np.full((2, 3), 1e-1), np.arange(4) * 2.0)
+    assert np.allclose(op3, 1.0) and np.allclose(doi3, 5.0)
+
+
+def test_inference3d_save_writes_line_products(tmp_path, golden_dir, built_lib):
+    """Inference3D.save on fabricated results (no GPU): one file per line with the per-line opacity / doi."""
+    from geobipy_b200 import _lib, dataset, ops
+    csvf, stm, g = _write_survey(tmp_path, golden_dir)
+    d = dataset.FdemData.read_csv(csvf, stm)
+    opt = ops.make_options()
+    nd = ops.n_depth(opt)
+    rng = np.random.default_rng(2)
+    sc = np.zeros((6, _lib.NSCALARS))
+    sc[:, _lib.S_HALFSPACE] = 0.02
+    res = dict(hitmap=rng.integers(0, 20, (6, opt.n_sigma_bins, nd)).astype(np.int32), scalars=sc,
+               edges_hist=rng.integers(0, 5, (6, nd)).astype(np.int32), index=np.arange(6))
+    res.update({"summary_" + k: v for k, v in dataset.summarise(res, opt).items()})
+    inv = dataset.Inference3D(d, seed=1)
+    inv.results, inv.options = res, opt
+    files = inv.save(str(tmp_path / "out"))
+    assert [os.path.basename(f) for f in files] == ["100.npz", "200.npz"]
+    z = np.load(files[0])
+    assert z["hitmap"].shape == (3, opt.n_sigma_bins, nd) and z["opacity"].shape == (3, nd) and z["doi"].shape == (3,)
+    assert z["opacity"].min() >= 0.0 and z["opacity"].max() <= 1.0 and z["opacity"].max() == 1.0
+    op, doi = dataset.opacity_and_doi(res["summary_p5"][:3], res["summary_p95"][:3], res["summary_depth_edges"])
+    assert np.array_equal(z["opacity"], op) and np.array_equal(z["doi"], doi)
