@@ -181,6 +181,49 @@ class Histogram:
     def median(self):
         return self.percentile(50.0)
 
+    def mode(self):
+        """Centre of the fullest value bin per depth cell (Mesh._mode, classes/mesh/Mesh.py:138-165)."""
+        c = self._xc()
+        out = c[np.argmax(self.counts, axis=0)]
+        out = np.exp(out) if self.log_x else out
+        return out if self.counts.ndim > 1 else float(out)
+
+    def credible_intervals(self, percent=90.0):
+        """(median, low, high) per depth cell (Mesh._credible_intervals, Mesh.py:30-55): the 50 %, (100 - percent) / 2
+        and 100 - (100 - percent) / 2 percentiles."""
+        p = 0.5 * min(percent, 100.0 - percent)
+        return self.percentile(50.0), self.percentile(p), self.percentile(100.0 - p)
+
+    def credible_range(self, percent=90.0):
+        """Width of the credible interval per depth cell (Mesh._credible_range, Mesh.py:58-78): in decades for the
+        conductivity axis of a hitmap (its mesh has log = 10, Model.py:677-679), linear otherwise."""
+        _, lo, hi = self.credible_intervals(percent)
+        if self.log_x:
+            return np.abs(np.log10(hi) - np.log10(lo))
+        return np.abs(np.asarray(hi) - np.asarray(lo))
+
+    def transparency(self, percent=95.0):
+        """Credible range normalised to [0, 1] over this histogram, NaN -> 1 (Histogram.transparency,
+        classes/statistics/Histogram.py:509-541)."""
+        out = np.asarray(self.credible_range(percent), dtype=np.float64)
+        mn, mx = np.nanmin(out), np.nanmax(out)
+        out = (out - mn) / (mx - mn) if (mx - mn) > 0.0 else out - mn
+        return np.where(np.isnan(out), 1.0, out)
+
+    def opacity(self, percent=95.0):
+        """1 - transparency (Histogram.opacity, Histogram.py:330-354)."""
+        return 1.0 - self.transparency(percent)
+
+    def opacity_level(self, percent=95.0):
+        """Depth-cell centre found from the bottom up where the transparency drops to percent / 100
+        (Histogram.opacity_level, Histogram.py:356-367; the reference's loop index may run to -1 = the last cell)."""
+        t = self.transparency(percent)
+        yc = 0.5 * (np.asarray(self.y_edges)[1:] + np.asarray(self.y_edges)[:-1])
+        i = t.size - 1
+        while t[i] > 0.01 * percent and i >= 0:
+            i -= 1
+        return yc[i]
+
 
 class FdemDataPoint:
     """One frequency-domain sounding (FdemDataPoint.py / EmDataPoint.py / DataPoint.py).

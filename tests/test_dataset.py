@@ -143,3 +143,38 @@ def test_inference3d_save_writes_line_products(tmp_path, golden_dir, built_lib):
     assert z["opacity"].min() >= 0.0 and z["opacity"].max() <= 1.0 and z["opacity"].max() == 1.0
     op, doi = dataset.opacity_and_doi(res["summary_p5"][:3], res["summary_p95"][:3], res["summary_depth_edges"])
     assert np.array_equal(z["opacity"], op) and np.array_equal(z["doi"], doi)
+
+
+def test_histogram_credible_range_opacity_mode(built_lib):
+    """The per-sounding summaries of the reference's Histogram class (mode, credible intervals / range, transparency,
+    opacity: Histogram.py:113-127, 308-367, 509-541; Mesh.py:30-78, 138-165) on the mirror, against direct numpy and
+    against the per-line opacity_and_doi when the line is that one sounding."""
+    from geobipy_b200 import api, dataset, ops
+    opt = ops.make_options()
+    nd = ops.n_depth(opt)
+    rng = np.random.default_rng(7)
+    # a posterior that widens with depth
+    hm = np.zeros((opt.n_sigma_bins, nd), np.int32)
+    for j in range(nd):
+        w = 2 + j // 8
+        hm[:, j] = np.bincount(np.clip(rng.normal(120, w, 400).astype(int), 0, opt.n_sigma_bins - 1), minlength=opt.n_sigma_bins)
+    g = ops.posterior_grids(opt, 0.03)
+    h = api.Histogram(hm, g["sigma_edges"], g["depth_edges"], log_x=True)
+    c = 0.5 * (np.log(g["sigma_edges"])[1:] + np.log(g["sigma_edges"])[:-1])
+    assert np.allclose(np.log(h.mode()), c[np.argmax(hm, axis=0)])
+    med, lo, hi = h.credible_intervals(90.0)
+    assert np.array_equal(med, h.median()) and np.array_equal(lo, h.percentile(5.0)) and np.array_equal(hi, h.percentile(95.0))
+    assert np.all(lo <= med) and np.all(med <= hi)
+    r = h.credible_range(90.0)
+    assert np.allclose(r, np.log10(hi / lo)) and r[-1] > r[0]
+    t, op = h.transparency(90.0), h.opacity(90.0)
+    assert t.min() == 0.0 and t.max() == 1.0 and np.allclose(op, 1.0 - t)
+    op_line, doi = dataset.opacity_and_doi(lo[None, :], hi[None, :], g["depth_edges"])
+    assert np.allclose(op_line[0], op)
+    yc = 0.5 * (g["depth_edges"][1:] + g["depth_edges"][:-1])
+    assert doi[0] == yc[np.flatnonzero(op >= 0.67).max()]
+    lvl = h.opacity_level(50.0)   # the reference uses `percent` for the interval AND for the threshold
+    assert lvl == yc[np.flatnonzero(h.transparency(50.0) <= 0.5).max()]
+    # 1-D histograms (error / height posteriors)
+    h1 = api.Histogram(np.array([0, 1, 5, 2, 0]), np.linspace(0.0, 5.0, 6))
+    assert h1.mode() == 2.5 and h1.credible_range(50.0) == 1.0
