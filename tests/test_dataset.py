@@ -177,4 +177,4 @@ def test_histogram_credible_range_opacity_mode(built_lib):
     assert lvl == yc[np.flatnonzero(h.transparency(50.0) <= 0.5).max()]
     # 1-D histograms (error / height posteriors)
     h1 = api.Histogram(np.array([0, 1, 5, 2, 0]), np.linspace(0.0, 5.0, 6))
-    assert h1.mode() == 2.5 and h1.credible_range(50.0) == 1.0
+    assert h1.mode() == 2.5 and h1.credible_range(50.0) == 0.0 and h1.credible_range(90.0) == 2.0
