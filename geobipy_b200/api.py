@@ -372,7 +372,9 @@ class Inference1D:
         if dp.n_active_channels == 0:
             return True
         struct = dp.c_struct if self._tdem else dp.system.c_struct
-        alt = dp.transmitter.z if self._tdem else dp.z
+        if not hasattr(dp, "z_input"):
+            dp.z_input = float(dp.transmitter.z if self._tdem else dp.z)   # a second infer() starts from the input height again
+        alt = dp.z_input
         r = ops.rjmcmc_run(struct, self.options, dp.data.reshape(1, -1), np.asarray([alt]), seed=self.seed,
                            first_index=self.sounding_index, max_iterations=max_iterations, precision=self.precision,
                            device=self.device)
@@ -423,9 +425,11 @@ class Inference1D:
             dp.additive_error = np.asarray([s[_lib.S_CUR_ADD]])
             self.best_relative_error, self.best_additive_error = float(s[_lib.S_BEST_REL]), float(s[_lib.S_BEST_ADD])
         if o.solve_height:  # solve_z: datapoint.z / best_datapoint.z and datapoint.z.posterior (Point.py:1013-1025)
-            z0 = float(dp.z)
-            self.height_posterior = Histogram(r["height_hist"][b], z0 + np.linspace(-o.max_height_change, o.max_height_change,
-                                                                                  o.n_err_bins + 1))
+            # the bins are relative to the centre of the height prior, which reset() re-centres on the sampled height
+            # (Inference1D.py:984-994): the kernel reports it (S_HEIGHT_REF); dp.z_input keeps the height handed in
+            z_ref = float(s[_lib.S_HEIGHT_REF])
+            self.height_posterior = Histogram(r["height_hist"][b], z_ref + np.linspace(-o.max_height_change, o.max_height_change,
+                                                                                     o.n_err_bins + 1))
             self.best_height = float(s[_lib.S_BEST_HEIGHT])
             dp.z = float(s[_lib.S_CUR_HEIGHT])
         dp.forward(self.model)

@@ -2,6 +2,7 @@
 // staging, launch configuration.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -19,9 +20,21 @@ namespace {
 
 thread_local std::string g_err;
 std::mutex g_mu;
-long long g_launches = 0;
-cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-bool g_ev_valid = false;
+std::atomic<long long> g_launches{0};
+constexpr int MAX_DEV = 64;
+
+// Per-device launch state.  Threading contract (include/geobipy_b200.h): entry points may be called from several
+// host threads, on several devices and streams at once - every launch takes its device's mutex for the (short,
+// asynchronous) launch sequence, the per-call scratch (Jacobian mirror, work counter) is allocated stream-ordered
+// per call, and the timing events form a per-device ring of the last TIMING_RING launches.
+constexpr int TIMING_RING = 32;
+struct DevState {
+    std::mutex mu;
+    cudaEvent_t ev0[TIMING_RING] = {nullptr}, ev1[TIMING_RING] = {nullptr};
+    long long n_timed = 0;
+    bool pool_ready = false;
+};
+DevState g_dev[MAX_DEV];
 
 int fail(const std::string& m)
 {
@@ -97,19 +110,43 @@ int get_tables(const gbp_fdem_system* sys, TableCache** out)
     return 0;
 }
 
-int time_begin(cudaStream_t st)
+int current_device(int* dev)
 {
-    if (!g_ev0) {
-        CK(cudaEventCreate(&g_ev0));
-        CK(cudaEventCreate(&g_ev1));
-    }
-    CK(cudaEventRecord(g_ev0, st));
+    CK(cudaGetDevice(dev));
+    if (*dev < 0 || *dev >= MAX_DEV) return fail("device index out of range");
     return 0;
 }
-int time_end(cudaStream_t st)
+// both called with g_dev[dev].mu held
+int time_begin(int dev, cudaStream_t st)
 {
-    CK(cudaEventRecord(g_ev1, st));
-    g_ev_valid = true;
+    DevState& D = g_dev[dev];
+    const int slot = (int)(D.n_timed % TIMING_RING);
+    if (!D.ev0[slot]) {
+        CK(cudaEventCreate(&D.ev0[slot]));
+        CK(cudaEventCreate(&D.ev1[slot]));
+    }
+    CK(cudaEventRecord(D.ev0[slot], st));
+    return 0;
+}
+int time_end(int dev, cudaStream_t st)
+{
+    DevState& D = g_dev[dev];
+    CK(cudaEventRecord(D.ev1[(int)(D.n_timed % TIMING_RING)], st));
+    D.n_timed++;
+    return 0;
+}
+// stream-ordered scratch of one call; the device's default memory pool keeps what it frees (no per-call cudaMalloc)
+int scratch_alloc(int dev, void** p, size_t bytes, cudaStream_t st)
+{
+    DevState& D = g_dev[dev];
+    if (!D.pool_ready) {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        D.pool_ready = true;
+    }
+    CK(cudaMallocAsync(p, bytes, st));
     return 0;
 }
 
@@ -142,11 +179,14 @@ int launch_fdem(TableCache* tc, int B, int l_stride, const int32_t* nl, const do
     const int need = (B + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if (time_begin(st)) return 1;
+    int dev;
+    if (current_device(&dev)) return 1;
+    std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+    if (time_begin(dev, st)) return 1;
     kern<<<grid, threads, smem, st>>>(tc->host.dev, tab_ptr<T>(tc), B, l_stride, nl, sig, thk, alt, out, J);
     g_launches++;
     CK(cudaGetLastError());
-    return time_end(st);
+    return time_end(dev, st);
 }
 
 // device copies of the time-domain window operator, cached per (device, survey)
@@ -212,27 +252,29 @@ int launch_tdem(TdCache* tc, int B, int l_stride, const int32_t* nl, const doubl
     const int need = (B + wpb - 1) / wpb;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if (time_begin(st)) return 1;
+    int dev;
+    if (current_device(&dev)) return 1;
+    std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+    if (time_begin(dev, st)) return 1;
     kern<<<grid, threads, smem, st>>>(tc->host.dev, td_ptr<T>(tc), B, l_stride, nl, sig, thk, alt, out, J, out_scale);
     g_launches++;
     CK(cudaGetLastError());
-    return time_end(st);
+    return time_end(dev, st);
 }
 
-unsigned long long* g_finish[64] = {nullptr};  // debug timeline (GBP_DEBUG_TIMELINE)
-size_t g_finish_cap[64] = {0};
-int g_finish_B[64] = {0};
-void* g_jstore[64] = {nullptr};
-size_t g_jstore_cap[64] = {0};
+unsigned long long* g_finish[MAX_DEV] = {nullptr};  // debug timeline (GBP_DEBUG_TIMELINE)
+size_t g_finish_cap[MAX_DEV] = {0};
+int g_finish_B[MAX_DEV] = {0};
 
 template <typename R, typename T, int NC, int WARPS, int KIND>
 int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, size_t tab_bytes_raw, const ChainParams& P,
                  cudaStream_t st)
 {
+    if (P.C > NC) return fail("datapoint has more channels than this sampler kernel holds");
     const size_t tab_bytes = (tab_bytes_raw + 127) & ~(size_t)127;
     const size_t per_warp = sizeof(WarpState<R, T, NC, KIND>);
     int dev = 0, max_smem = 0;
-    CK(cudaGetDevice(&dev));
+    if (current_device(&dev)) return 1;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t smem = tab_bytes + (size_t)WARPS * per_warp;
     auto kern = rjmcmc_kernel<R, T, NC, WARPS, KIND>;
@@ -240,16 +282,6 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
     CK(cudaFuncGetAttributes(&fa, kern));
     if (smem + fa.sharedSizeBytes + 1024 > (size_t)max_smem) return fail("rjmcmc kernel does not fit in shared memory on this device");
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // per-chain Jacobian mirror (L2 resident: 1.4 KB per chain in fp32)
-    const size_t jbytes = (size_t)P.B * NC * KS * sizeof(T);
-    if (dev < 0 || dev >= 64) return fail("device index out of range");
-    if (g_jstore_cap[dev] < jbytes) {
-        if (g_jstore[dev]) CK(cudaFree(g_jstore[dev]));
-        g_jstore[dev] = nullptr;
-        g_jstore_cap[dev] = 0;
-        CK(cudaMalloc(&g_jstore[dev], jbytes));
-        g_jstore_cap[dev] = jbytes;
-    }
     int grid = sm_count();
     if (grid > P.B) grid = P.B;
     ChainParams Q = P;
@@ -260,9 +292,15 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
         Q.spec_helpers = hmax < 0 ? 0 : (hmax > WARPS - 1 ? WARPS - 1 : hmax);
         const char* m = std::getenv("GBP_SPEC_MIN_REJECTIONS");
         Q.spec_min_rejections = m ? std::atoi(m) : 24;
-
     }
-    Q.jstore = g_jstore[dev];
+    std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+    // per-call scratch, stream ordered: [work counter (256 B)] [per-chain Jacobian mirror, L2 resident: 1.4 KB per
+    // chain in fp32].  Calls in flight on different streams never share it.
+    const size_t jbytes = (size_t)P.B * NC * KS * sizeof(T);
+    unsigned char* scratch = nullptr;
+    if (scratch_alloc(dev, (void**)&scratch, 256 + jbytes, st)) return 1;
+    Q.work_counter = (int*)scratch;
+    Q.jstore = scratch + 256;
     Q.finish_ns = nullptr;
     if (std::getenv("GBP_DEBUG_TIMELINE")) {
         const size_t need = (size_t)(P.B + 1) * sizeof(unsigned long long);
@@ -279,11 +317,13 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
     }
     // device-side work counter: chains beyond the first wave are claimed dynamically
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
-    if (time_begin(st)) return 1;
+    if (time_begin(dev, st)) return 1;
     kern<<<grid, WARPS * 32, smem, st>>>(sysdev, d_tab, Q);
     g_launches++;
     CK(cudaGetLastError());
-    return time_end(st);
+    if (time_end(dev, st)) return 1;
+    CK(cudaFreeAsync(scratch, st));
+    return 0;
 }
 
 // ---- microbenchmarks of the two pipes that bound this path (the roofline denominators for scalar
@@ -372,17 +412,6 @@ __global__ void __launch_bounds__(256) summarise_kernel(const int32_t* __restric
     }
 }
 
-int* g_counter[64] = {nullptr};
-int get_counter(int** out)
-{
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail("device index out of range");
-    if (!g_counter[dev]) CK(cudaMalloc(&g_counter[dev], 256));
-    *out = g_counter[dev];
-    return 0;
-}
-
 int check_options(const gbp_options* o)
 {
     if (o->max_layers < 1 || o->max_layers > GBP_MAXL) return fail("max_layers must be in [1, 30]");
@@ -438,13 +467,34 @@ double gbp_flops_per_forward(const gbp_fdem_system* sys, int L)
     return (double)gbp_filter_points(sys) * (75.0 * (double)L + 39.0);
 }
 
-int64_t gbp_launch_count(void) { return g_launches; }
+int64_t gbp_launch_count(void) { return g_launches.load(); }
 
 int gbp_last_kernel_ms(float* ms)
 {
-    if (!g_ev_valid) return fail("no kernel has been timed yet");
-    CK(cudaEventSynchronize(g_ev1));
-    CK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    int n = 0;
+    return gbp_kernel_ms_stats(1, ms, &n);
+}
+
+int gbp_kernel_ms_stats(int last_n, float* mean_ms, int* counted)
+{
+    int dev;
+    if (current_device(&dev)) return 1;
+    DevState& D = g_dev[dev];
+    std::lock_guard<std::mutex> lk(D.mu);
+    if (D.n_timed == 0) return fail("no kernel has been timed yet on this device");
+    long long n = last_n < 1 ? 1 : last_n;
+    if (n > D.n_timed) n = D.n_timed;
+    if (n > TIMING_RING) n = TIMING_RING;
+    double sum = 0.0;
+    for (long long i = D.n_timed - n; i < D.n_timed; ++i) {
+        const int slot = (int)(i % TIMING_RING);
+        float ms = 0.f;
+        CK(cudaEventSynchronize(D.ev1[slot]));
+        CK(cudaEventElapsedTime(&ms, D.ev0[slot], D.ev1[slot]));
+        sum += ms;
+    }
+    if (mean_ms) *mean_ms = (float)(sum / (double)n);
+    if (counted) *counted = (int)n;
     return 0;
 }
 
@@ -551,7 +601,6 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
     P.out = *d_buf;
     P.data_scale = 1.0;
     if (opt->n_systems > 1) return fail("an FDEM datapoint has one system (gbp_options.n_systems must be 0 or 1)");
-    if (get_counter(&P.work_counter)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     const bool small = P.C <= 12;
     const SysDev& sd = tc->host.dev;
@@ -591,8 +640,8 @@ struct HostArena {
     void* ptr[16];
     size_t cap[16];
 };
-static HostArena g_arena[64];
-static std::mutex g_host_mu;
+static HostArena g_arena[MAX_DEV];
+static std::mutex g_host_mu[MAX_DEV];
 static int arena_get(int dev, int slot, size_t bytes, void** out)
 {
     HostArena& a = g_arena[dev];
@@ -640,8 +689,8 @@ static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* 
         {(void* const*)&h->scalars, (void**)&d.scalars, (size_t)B * GBP_NSCALARS * sizeof(double)},
         {(void* const*)&h->height_hist, (void**)&d.height_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
     };
-    if (device < 0 || device >= 64) return fail("device index out of range");
-    std::lock_guard<std::mutex> lk(g_host_mu);  // the cached device buffers are shared by the callers of this process
+    if (device < 0 || device >= MAX_DEV) return fail("device index out of range");
+    std::lock_guard<std::mutex> lk(g_host_mu[device]);  // the cached device buffers of a device are shared by its callers
     double *d_data = nullptr, *d_alt = nullptr;
     int rc = 0, slot = 0;
     for (const Item& it : items) {
@@ -697,7 +746,10 @@ int gbp_summarise_hitmap(const int32_t* d_hitmap, int B, int n_sig, int n_depth,
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
-    if (time_begin(st)) return 1;
+    int dev;
+    if (current_device(&dev)) return 1;
+    std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+    if (time_begin(dev, st)) return 1;
     switch (n_pct) {
 #define GBP_SUMM_CASE(NP) case NP: summarise_kernel<NP><<<(int)blocks, 256, 0, st>>>(d_hitmap, d_sig_lo, P, d_mean, d_pct); break;
         GBP_SUMM_CASE(1) GBP_SUMM_CASE(2) GBP_SUMM_CASE(3) GBP_SUMM_CASE(4) GBP_SUMM_CASE(5) GBP_SUMM_CASE(6) GBP_SUMM_CASE(7)
@@ -707,13 +759,13 @@ int gbp_summarise_hitmap(const int32_t* d_hitmap, int B, int n_sig, int n_depth,
     }
     g_launches++;
     CK(cudaGetLastError());
-    return time_end(st);
+    return time_end(dev, st);
 }
 
 int gbp_release_host_buffers(void)
 {
-    std::lock_guard<std::mutex> lk(g_host_mu);
-    for (int dev = 0; dev < 64; ++dev)
+    for (int dev = 0; dev < MAX_DEV; ++dev) {
+        std::lock_guard<std::mutex> lk(g_host_mu[dev]);
         for (int s = 0; s < 16; ++s)
             if (g_arena[dev].ptr[s]) {
                 cudaSetDevice(dev);
@@ -721,6 +773,7 @@ int gbp_release_host_buffers(void)
                 g_arena[dev].ptr[s] = nullptr;
                 g_arena[dev].cap[s] = 0;
             }
+    }
     return 0;
 }
 
@@ -920,6 +973,10 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     if (!d_buf || !d_buf->scalars) return fail("gbp_chain_buffers.scalars is required");
     if ((opt->n_systems > 1 ? 2 : 1) != sv->n_systems)
         return fail("gbp_options.n_systems must equal the number of systems of the datapoint type");
+    // the sampler kernels hold GBP_TD_SAMPLER_MAXC channels per chain in shared memory (the forward / Jacobian
+    // operators take GBP_TD_MAXC); checked before any device work
+    if (gbp_tdem_n_channels(sv) > GBP_TD_SAMPLER_MAXC)
+        return fail("time-domain sampler: at most 48 data channels per datapoint (GBP_TD_SAMPLER_MAXC)");
     TdCache* tc;
     if (opt->solve_height) return fail("solve_height is not built for time-domain datapoints (the loop height enters the geometry weights)");
     if (get_td_tables(sv, &tc, true)) return 1;
@@ -936,7 +993,6 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     P.max_iterations = max_iterations;
     P.out = *d_buf;
     P.data_scale = 1.0;
-    if (get_counter(&P.work_counter)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     const TdDev& sd = tc->host.dev;
     if (precision == GBP_PRECISION_F32) {
@@ -950,10 +1006,10 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
         P.opt.add_max2 *= TD_F32_SCALE;
         // 12 chains per SM (to termination, scripts/gpu_tdem_warps.py: 4096 soundings 12: 3157 ms, 16: 3437, 8: 3656;
         // 8192 soundings 12: 5312 ms, 16: 5505, 8: 6243; 18 chains per SM at 113 registers spill and are slower still)
-        return launch_chain<float, float, 48, 12, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
+        return launch_chain<float, float, GBP_TD_SAMPLER_MAXC, 12, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
     }
     if (precision == GBP_PRECISION_F64)
-        return launch_chain<double, double, 48, 8, KIND_TDEM>(sd, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
+        return launch_chain<double, double, GBP_TD_SAMPLER_MAXC, 8, KIND_TDEM>(sd, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
     return fail("precision must be 32 or 64");
 }
 

@@ -1758,6 +1758,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_TOTAL_ITER] = (double)total;
         s[GBP_S_CUR_HEIGHT] = (KIND == KIND_FDEM_Z) ? (double)alt : P.altitude[chain];
         s[GBP_S_BEST_HEIGHT] = (KIND == KIND_FDEM_Z) ? (double)best_alt : P.altitude[chain];
+        s[GBP_S_HEIGHT_REF] = (KIND == KIND_FDEM_Z) ? (double)alt_ref : P.altitude[chain];
         if (spec_rounds > 0) {
             atomicAdd(&g_diag[8], (unsigned long long)w->ctr[CT_N_SPEC]);
             atomicAdd(&g_diag[9], (unsigned long long)spec_rounds);

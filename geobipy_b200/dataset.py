@@ -142,10 +142,14 @@ def summarise(result, opt):
     eh = np.asarray(result["edges_hist"]).astype(np.float64)
     out["interface_probability"] = eh / np.maximum(eh.sum(axis=1, keepdims=True), 1.0)
     out["depth_edges"] = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
-    if "height_hist" in result:   # sampled sensor height (solve_z): posterior mean of z - z0 per sounding [B]
+    if "height_hist" in result:
+        # sampled sensor height (solve_z).  The histogram bins z - z_ref, z_ref = the centre of the height prior: the
+        # input height, re-centred on the sampled height by every reset() (scalar slot S_HEIGHT_REF).  height_mean [B]
+        # is the posterior mean height itself; Inference3D.infer adds height_change_mean = height_mean - input height.
         hh = np.asarray(result["height_hist"]).astype(np.float64)
         c = -opt.max_height_change + (np.arange(hh.shape[1]) + 0.5) * (2.0 * opt.max_height_change / hh.shape[1])
-        out["height_change_mean"] = (hh * c[None, :]).sum(axis=1) / np.maximum(hh.sum(axis=1), 1.0)
+        out["height_mean"] = (np.asarray(result["scalars"])[:, _lib.S_HEIGHT_REF]
+                              + (hh * c[None, :]).sum(axis=1) / np.maximum(hh.sum(axis=1), 1.0))
     return out
 
 
@@ -221,6 +225,8 @@ class Inference3D:
             res = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
         res["index"] = sel
         res.update({"summary_" + k: v for k, v in summarise(res, opt).items()})
+        if "summary_height_mean" in res:
+            res["summary_height_change_mean"] = res["summary_height_mean"] - np.asarray(d.z, dtype=np.float64)[sel]
         self.results = res
         return res
 

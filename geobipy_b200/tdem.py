@@ -276,14 +276,28 @@ class TdemData:
             assert default is not None, ValueError("column %s missing from %s" % (names[0], data_filename))
             return np.full(len(df), default)
         n = sum(s.nTimes for s in system)
-        known = {"line_number", "line", "fiducial", "fid", "easting", "x", "northing", "y", "height", "z", "dtm", "elevation"}
-        known |= set(cls.GEOMETRY)
-        dcols = [c for c in df.columns if c.strip().lower() not in known and not c.strip().lower().startswith("off")]
-        assert len(dcols) >= n, ValueError("expected %d window columns, found %d" % (n, len(dcols)))
+        # TdemData._csv_channels (classes/data/dataset/TdemData.py:611-633): the data are the columns whose name contains
+        # off_time / x_time / y_time / z_time, those that also contain "err" are their standard deviations; on_time
+        # columns and the primary field (px, py, pz) are not data
+        dcols, ecols = [], []
+        for c in df.columns:
+            t = c.strip().lower()
+            if t in cls.GEOMETRY or "on_time" in t:
+                continue
+            if any(x in t for x in ("off_time", "x_time", "y_time", "z_time")):
+                (ecols if "err" in t else dcols).append(c)
+        assert len(dcols) == n, Exception("Number of off time columns {} in {} does not match total number of times {} in system files".format(
+            len(dcols), data_filename, n))
+        if ecols:
+            assert len(ecols) == len(dcols), Exception(
+                "Number of Off time standard deviation estimates does not match number of Off time data columns in file {}".format(data_filename))
         geometry = np.stack([col(g, default=(-13.0 if g == "txrx_dx" else 2.0 if g == "txrx_dz" else 0.0)) for g in cls.GEOMETRY], axis=1)
-        return cls(system, col("line_number", "line"), col("fiducial", "fid"), col("easting", "x"), col("northing", "y"),
+        self = cls(system, col("line_number", "line"), col("fiducial", "fid"), col("easting", "x"), col("northing", "y"),
                    col("height", "z"), col("elevation", "dtm", default=0.0), geometry,
-                   df[dcols[:n]].to_numpy(dtype=np.float64))
+                   df[dcols].to_numpy(dtype=np.float64))
+        # TdemData.read_csv :520-525: without error columns std = 0.1 * data
+        self.std = df[ecols].to_numpy(dtype=np.float64) if ecols else 0.1 * self.data
+        return self
 
     @property
     def nPoints(self):

@@ -25,6 +25,15 @@
  * (passed as void*) and are stream ordered.  All functions return 0 on success, non-zero
  * on error (message: gbp_last_error()).  There is no CPU fallback: without a CUDA device
  * every compute entry point fails.
+ *
+ * Threading contract.  Every entry point may be called concurrently from several host threads, on several devices
+ * and on several streams of one device: per-call scratch (the work counter and the per-chain Jacobian mirror of the
+ * samplers) is allocated stream-ordered per call, launch sequences are serialised per device by a mutex (they are
+ * asynchronous and short), the "_host" samplers serialise per device on their cached device buffers, and
+ * gbp_last_error() is thread local.  The kernel timings (gbp_last_kernel_ms / gbp_kernel_ms_stats) and
+ * gbp_debug_counters are per DEVICE, not per stream: with launches in flight on several streams of one device they
+ * describe whichever launches came last.  The device entry points use the CURRENT device of the calling thread, which
+ * must be the device the pointers and the stream belong to.
  */
 #ifndef GEOBIPY_B200_H
 #define GEOBIPY_B200_H
@@ -43,7 +52,9 @@ extern "C" {
 #define GBP_TD_NFREQ 32          /* spline nodes of the frequency-domain response (one per lane) */
 #define GBP_TD_MAXLAM 32         /* Hankel abscissae */
 #define GBP_TD_MAXWIN 32         /* receiver windows of one system */
-#define GBP_TD_MAXC 64           /* data channels of one time-domain datapoint */
+#define GBP_TD_MAXC 64           /* data channels of one time-domain datapoint (forward / Jacobian operators) */
+#define GBP_TD_SAMPLER_MAXC 48   /* data channels the time-domain SAMPLER holds per chain (gbp_tdem_rjmcmc_run*
+                                    reject datapoint types with more; SkyTEM dual moment has 45) */
 #define GBP_TD_MAXWAVE 64        /* vertices of the current waveform */
 #define GBP_TD_MAXFILT 4         /* receiver low-pass filters */
 
@@ -124,6 +135,8 @@ enum {
     GBP_S_TOTAL_ITER,   /* accept_reject+update pairs executed, including those before a reset() */
     GBP_S_CUR_REL2, GBP_S_CUR_ADD2, GBP_S_BEST_REL2, GBP_S_BEST_ADD2,  /* system 1 of a dual-moment datapoint */
     GBP_S_CUR_HEIGHT, GBP_S_BEST_HEIGHT,   /* datapoint.z / best_datapoint.z (the input height unless solve_height) */
+    GBP_S_HEIGHT_REF,   /* centre of the height prior and of the height_hist bins: the input height, re-centred on the
+                           sampled height by every reset() (Inference1D.py:984-994, Point.set_priors :959-961) */
     GBP_NSCALARS = 32
 };
 
@@ -175,6 +188,9 @@ int64_t gbp_launch_count(void);
 /* mean duration [ms] and launch count of the last gbp_rjmcmc_run / forward kernel, measured with CUDA
  * events on the launching stream (valid after the stream has been synchronised) */
 int gbp_last_kernel_ms(float *ms);
+/* mean duration [ms] of the last `last_n` (<= 32) kernels this library launched on the current device (*counted =
+ * how many were averaged); synchronises on their events.  bench.py's roofline.kernel_ms */
+int gbp_kernel_ms_stats(int last_n, float *mean_ms, int *counted);
 
 /* ---- FDEM forward / Jacobian, DEVICE pointers --------------------------------------------- */
 /* sigma, thickness: [B][l_stride] (thickness of the last layer is ignored = infinite half-space);

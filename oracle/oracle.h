@@ -93,6 +93,7 @@ enum {
     GBO_S_BEST_REL, GBO_S_BEST_ADD, GBO_S_N_RESETS, GBO_S_N_BIRTH, GBO_S_N_DEATH, GBO_S_N_MOVE, GBO_S_N_NONE, GBO_S_TOTAL_ITER,
     GBO_S_CUR_REL2, GBO_S_CUR_ADD2, GBO_S_BEST_REL2, GBO_S_BEST_ADD2,   /* system 1 of a dual-moment datapoint */
     GBO_S_CUR_HEIGHT, GBO_S_BEST_HEIGHT,                                /* sensor height (solve_height) */
+    GBO_S_HEIGHT_REF,                                                   /* centre of the height prior (re-centred by reset()) */
     GBO_NSCALARS = 32
 };
 

@@ -20,7 +20,7 @@ NSCALARS = 32
 S_ITER, S_BURNED_IN, S_BURNED_IN_ITER, S_BEST_ITER, S_BEST_K, S_CUR_K, S_HALFSPACE, S_FAILED, S_N_ACCEPT, \
     S_N_FORWARD, S_N_SENS, S_BEST_POSTERIOR, S_CUR_REL, S_CUR_ADD, S_CUR_MISFIT, S_CUR_PRIOR, S_CUR_LIKELIHOOD, \
     S_BEST_REL, S_BEST_ADD, S_N_RESETS, S_N_BIRTH, S_N_DEATH, S_N_MOVE, S_N_NONE, S_TOTAL_ITER, \
-    S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2, S_CUR_HEIGHT, S_BEST_HEIGHT = range(31)
+    S_CUR_REL2, S_CUR_ADD2, S_BEST_REL2, S_BEST_ADD2, S_CUR_HEIGHT, S_BEST_HEIGHT, S_HEIGHT_REF = range(32)
 
 
 class FdemSystemC(ctypes.Structure):

@@ -994,6 +994,7 @@ static int run_chain_impl(const survey_t *sv, const gbo_options *opt, const doub
     s[GBO_S_TOTAL_ITER] = (double)total;
     s[GBO_S_CUR_HEIGHT] = c->dp.z;
     s[GBO_S_BEST_HEIGHT] = c->best_z;
+    s[GBO_S_HEIGHT_REF] = c->z_ref;
     for (int i = 0; i < opt->max_layers; ++i) {
         out->best_sigma[i] = i < c->best_model.k ? c->best_model.sigma[i] : NAN;
         out->cur_sigma[i] = i < c->model.k ? c->model.sigma[i] : NAN;

@@ -4,6 +4,7 @@ Needs the read-only reference tree at /root/reference; imports the *unmodified* 
 through oracle/ref_shims.py and records its outputs.  The GPU box never runs this.
 
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
+    python tests/golden/make_golden.py fdem_tensor  # fdem_tensor_models.npz (tensor ids 3 / 7, vertical coil offsets)
     python tests/golden/make_golden.py tdem         # skytem_clean.npz
     python tests/golden/make_golden.py tdem_transitions   # tdem_transitions.npz (reference sampler + fake_gatdaem1d)
     python tests/golden/make_golden.py tdem_chain <i> [rep]   # ref_tdem_chain_<i>[_r<rep>].npz (minutes each)
@@ -134,6 +135,61 @@ def make_fdem():
     np.savez_compressed(os.path.join(HERE, "fdem_random_models.npz"), nlayers=Ls.astype(np.int32), sigma=sigma,
                         thickness=thk, height=height, forward=fwd, sensitivity=sens)
     print("fdem goldens written")
+
+
+# A frequency-domain system that exercises what RESOLVE does not: the mixed tensor components Hxz / Hzx
+# (tensor ids 3 and 7, fdem1d_numba.py:359-408) and coils offset vertically from the observation point
+# (fdem1d.py:31-32: transmitter_height = altitude + tz, receiver_height = -transmitter_height + rz).  rz >= 0 only: the
+# reference's primary-field sums use exp(-lambda * rz) (hSum = rHeight + tHeight = rz) and overflow to inf / NaN for a
+# receiver offset below the observation point.
+TENSOR_STM = """freq, tor, tmom, tx, ty, tzoff, ror, rmom, rx, ry, rzoff
+400, z, 1, 0, 0, 0.5, x, 1, 7.9, 0, 0.3
+1800, x, 1.5, 0, 0, -0.4, z, 1, 8.1, 0, 0.6
+3300, x, -1, 0, 0, 0.25, x, 2, 9.0, 0, 0.25
+8200, z, 1, 0.2, 0, 0, z, 1, 7.9, 0, 1.0
+40000, z, 2, 0, 0, -0.5, x, -1, 6.5, 0, 0.5
+130000, x, 1, 0, 0, 0.3, z, 1, 7.5, 0, 0.2
+"""
+
+
+def make_fdem_tensor():
+    """fdem_tensor_models.npz: fdem1dfwd / fdem1dsen of the live reference (fdem1d.py:10, :87 -> the Numba kernels)
+    through its own FdemSystem class for the system above, 96 random models."""
+    import tempfile
+    _geobipy()
+    from geobipy import FdemSystem
+    from geobipy.src.classes.forwardmodelling.Electromagnetic.FD.fdem1d import fdem1dfwd, fdem1dsen
+    with tempfile.NamedTemporaryFile("w", suffix=".stm", delete=False) as f:
+        f.write(TENSOR_STM)
+    s = FdemSystem.read(f.name)
+    assert list(s.tensor_id) == [3, 7, 1, 9, 3, 7], list(s.tensor_id)
+    rng = np.random.default_rng(20261018)
+    n = 96
+    Ls = np.r_[np.arange(1, 31), rng.integers(1, 31, n - 30)]
+    sigma = np.full((n, 30), np.nan)
+    thk = np.full((n, 30), np.nan)
+    height = rng.uniform(25.0, 45.0, n)
+    fwd = np.zeros((n, 12))
+    sens = np.full((n, 12, 30), np.nan)
+    for i in range(n):
+        L = int(Ls[i])
+        sg = 10.0 ** rng.uniform(-4.0, 1.0, L)
+        t = np.r_[np.exp(rng.uniform(np.log(1.0), np.log(60.0), L - 1)), np.inf]
+        sigma[i, :L] = sg
+        thk[i, :L] = t
+        mod = _model(np.r_[0.0, np.cumsum(t)], sg)
+        r = fdem1dfwd(s, mod, height[i])
+        fwd[i] = np.r_[r.real, r.imag]
+        J = fdem1dsen(s, mod, height[i])
+        sens[i, :, :L] = np.vstack([J.real, J.imag])
+    cols = {k: np.asarray(v) for k, v in dict(
+        freq=s.frequencies, tor=np.asarray(s.transmitter.orientation), tmom=s.transmitter.moment, tx=s.transmitter.x,
+        ty=s.transmitter.y, tz=s.transmitter.z, ror=np.asarray(s.receiver.orientation), rmom=s.receiver.moment,
+        rx=s.receiver.x, ry=s.receiver.y, rz=s.receiver.z).items()}
+    np.savez_compressed(os.path.join(HERE, "fdem_tensor_models.npz"), stm=TENSOR_STM, tensor_id=np.asarray(s.tensor_id),
+                        nlayers=Ls.astype(np.int32), sigma=sigma, thickness=thk, height=height, forward=fwd,
+                        sensitivity=sens, **{"sys_" + k: v for k, v in cols.items()})
+    print("fdem tensor goldens written; |d| range", np.abs(fwd).min(), np.abs(fwd).max())
 
 
 def make_tdem():
@@ -525,6 +581,8 @@ if __name__ == "__main__":
         make_tdem_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     if what == "tdem_height_chain":
         make_tdem_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0, height=True)
+    if what == "fdem_tensor":
+        make_fdem_tensor()
     if what == "fdem":
         make_fdem()
     elif what == "bins":

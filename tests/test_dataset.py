@@ -63,18 +63,21 @@ def test_summaries_match_histogram_class(built_lib):
         assert np.allclose(s["mean"][b], h.mean()) and np.allclose(s["p50"][b], h.median())
         assert np.allclose(s["p5"][b], h.percentile(5.0)) and np.allclose(s["p95"][b], h.percentile(95.0))
         assert abs(s["interface_probability"][b].sum() - 1.0) < 1e-12
-    assert "height_change_mean" not in s
-    # sampled sensor height (solve_z): posterior mean of z - z0 on the prior's bins (Point.set_z_posterior :1013-1020)
+    assert "height_mean" not in s
+    # sampled sensor height (solve_z): posterior mean height on the prior's bins (Point.set_z_posterior :1013-1020),
+    # which are centred on S_HEIGHT_REF (the input height, re-centred by every reset())
     optz = ops.make_options(solve_z=True, maximum_z_change=2.0, z_proposal_variance=0.01)
     hh = np.zeros((2, 99), np.int32)
     hh[0, 49] = 7                     # the centre bin: z = z0
     hh[1, 98], hh[1, 97] = 3, 1       # the two top bins
-    sz = dataset.summarise(dict(res, height_hist=hh), optz)
+    scz = sc.copy()
+    scz[:, _lib.S_HEIGHT_REF] = [30.0, 31.25]   # sounding 1 went through a reset(): prior re-centred 1.25 m higher
+    sz = dataset.summarise(dict(res, scalars=scz, height_hist=hh), optz)
     e = np.linspace(-2.0, 2.0, 100)
-    assert abs(sz["height_change_mean"][0]) < 1e-12
-    assert np.isclose(sz["height_change_mean"][1], (3 * 0.5 * (e[98] + e[99]) + 0.5 * (e[97] + e[98])) / 4)
-    hz = api.Histogram(hh[1], 30.0 + e)
-    assert np.isclose(hz.mean() - 30.0, sz["height_change_mean"][1])
+    assert abs(sz["height_mean"][0] - 30.0) < 1e-12
+    assert np.isclose(sz["height_mean"][1], 31.25 + (3 * 0.5 * (e[98] + e[99]) + 0.5 * (e[97] + e[98])) / 4)
+    hz = api.Histogram(hh[1], 31.25 + e)
+    assert np.isclose(hz.mean(), sz["height_mean"][1])
 
 
 @pytest.mark.gpu

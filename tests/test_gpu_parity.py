@@ -80,6 +80,24 @@ def test_forward_and_jacobian_random_models(gpu, systems, golden_dir, prec, tf, 
         assert not J[i, :, nl[i]:].any()
 
 
+@pytest.mark.parametrize("prec,tf,tj", [(64, F64_FWD, F64_J), (32, F32_FWD, (2e-4))])
+def test_mixed_tensor_components_and_coil_offsets(gpu, golden_dir, prec, tf, tj):
+    """Tensor ids 3 / 7 (Hxz, Hzx: fdem1d_numba.py:359-408) and non-zero vertical coil offsets (fdem1d.py:31-32)
+    against the live reference (make_golden.py fdem_tensor): fp64 <= 5e-8, fp32 <= 2e-4."""
+    g = np.load(os.path.join(golden_dir, "fdem_tensor_models.npz"))
+    sysc = gpu.make_system_struct(*(list(g["sys_" + k]) for k in ("freq", "tor", "tmom", "tx", "ty", "tz", "ror", "rmom", "rx", "ry", "rz")))
+    assert list(sysc.tid[:6]) == [3, 7, 1, 9, 3, 7]
+    nl = g["nlayers"]
+    sig = np.nan_to_num(g["sigma"], nan=1.0)
+    thk = np.nan_to_num(g["thickness"], nan=1.0, posinf=np.inf)
+    pred, J = gpu.fdem_forward(sysc, nl, sig, thk, g["height"], precision=prec, sensitivity=True)
+    assert fwd_ok(pred, g["forward"], tf), np.max(np.abs(pred - g["forward"]) / (np.abs(g["forward"]) + 1.0))
+    assert fwd_ok(gpu.fdem_forward(sysc, nl, sig, thk, g["height"], precision=prec), pred, tf)
+    refJ = np.nan_to_num(g["sensitivity"], nan=0.0)
+    err = np.abs(J - refJ).max(axis=(1, 2)) / np.abs(refJ).max(axis=(1, 2))
+    assert err.max() < tj, err.max()
+
+
 def test_forward_against_oracle_extremes(gpu, systems, oracle):
     """Conductive / resistive extremes, 1 and 30 layers, thin and thick layers, low and high sensors."""
     rng = np.random.default_rng(99)
@@ -257,6 +275,41 @@ def test_chain_fp32_statistics_match_oracle_ensemble(gpu, systems, oracle, golde
     m = med(res["hitmap"].sum(axis=0, dtype=np.int64))[:120]
     inside = (m >= ens.min(axis=0)[:120] - 2) & (m <= ens.max(axis=0)[:120] + 2)
     assert inside.mean() >= 0.9
+
+
+def _runs_from_result(res, oracle, n):
+    """per-chain dicts for tests/posterior_parity.py from a batched result"""
+    sc = res["scalars"]
+    runs = []
+    for b in range(n):
+        it = int(sc[b, oracle.S_ITER])
+        runs.append(dict(hitmap=res["hitmap"][b], edges_hist=res["edges_hist"][b], ncells_hist=res["ncells_hist"][b],
+                         misfit_trace=res["misfit_trace"][b], iterations=it, burned_in=bool(sc[b, oracle.S_BURNED_IN]),
+                         acceptance=sc[b, oracle.S_N_ACCEPT] / max(it, 1)))
+    return runs
+
+
+@pytest.mark.parametrize("sidx", [0, 1, 2, 3])
+def test_fp32_production_kernel_matches_live_reference_ensembles(gpu, systems, oracle, golden_dir, sidx):
+    """The kernel that earns the bench number - rjmcmc_kernel<float, float, 12, 16, FDEM> - against ensembles of chains of
+    the LIVE REFERENCE (Inference1D.infer loop, resolve_options, n_markov_chains = 10 000; 7 chains per sounding for
+    soundings 0, 2, 3 and 15 for sounding 1, tests/golden/make_golden.py chain) on the same observed data: 256 fp32 GPU chains
+    per sounding, the full SURVEY.md 8(d) list with the tolerances of tests/posterior_parity.py: 5 % / 50 % / 95 %
+    conductivity profiles above the depth of investigation within 2 bins of the reference envelope, interface peak within
+    2 depth cells, mean layer count +-0.5, acceptance +-5 points, misfit after burn-in and burned-in fraction."""
+    import posterior_parity as P
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_chain_%d" % sidx))
+    refs = [dict(np.load(os.path.join(golden_dir, f))) for f in files]
+    assert len(refs) >= 7
+    g = refs[0]
+    B = 256
+    opt = gpu.make_options(n_markov_chains=10000)
+    res = gpu.rjmcmc_run(systems[0], opt, np.tile(g["data"], (B, 1)), np.full(B, float(g["altitude"])), seed=4100 + sidx,
+                         first_index=0, precision=32, outputs=("hitmap", "edges_hist", "ncells_hist", "misfit_trace", "scalars"))
+    assert np.all(np.abs(res["scalars"][:, oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-6)
+    m = P.compare(refs, _runs_from_result(res, oracle, B))
+    print("sounding", sidx, m)
+    P.check(m)
 
 
 def test_chain_fp32_matches_fp64_ensemble(gpu, systems, oracle):

@@ -210,6 +210,47 @@ def test_chain_fp32_matches_fp64_ensemble(gpu, systems, oracle):
         assert d32[key] <= 2.5 * d64[key] + floor[key], (key, d32, d64)
 
 
+def test_fp32_production_kernel_matches_live_reference_ensemble(gpu, systems, oracle, golden_dir):
+    """rjmcmc_kernel<float, float, 48, 12, TDEM> (the production time-domain kernel) against the 6 chains of the LIVE
+    REFERENCE on sounding 2 (dual-moment TdemDataPoint, skytem_options at n_markov_chains = 10 000, through
+    tests/golden/fake_gatdaem1d.py): 128 fp32 GPU chains, the SURVEY.md 8(d) list of tests/posterior_parity.py (profiles
+    over the top 100 m inside the reference envelope +-2 bins - tails of a 6-chain ensemble are noisy, so 0.7 / 0.9 /
+    0.8 of the cells -, interface peak within 5 cells of 0.5 m, mean layer count +-0.75, acceptance +-5 points), the
+    post-burn-in misfit centred on the number of active channels (0.5-1.5 x 45, as the reference's own chains:
+    35-39), the same chain length (burn-in at 5001) and the posterior means of the four error parameters within 2 bins."""
+    import posterior_parity as P
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_tdem_chain_2"))
+    refs = [dict(np.load(os.path.join(golden_dir, f))) for f in files]
+    assert len(refs) >= 6
+    g = refs[0]
+    B = 128
+    opt = gpu.make_options(n_markov_chains=10000, **gpu.SKYTEM_OPTIONS)
+    res = gpu.rjmcmc_run(systems[0], opt, np.tile(g["data"], (B, 1)), np.full(B, float(g["altitude"])), seed=5200, precision=32,
+                         outputs=("hitmap", "edges_hist", "ncells_hist", "rel_hist", "add_hist", "misfit_trace", "scalars"))
+    sc = res["scalars"]
+    assert np.all(np.abs(sc[:, oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-6)
+    runs = []
+    for b in range(B):
+        it = int(sc[b, oracle.S_ITER])
+        runs.append(dict(hitmap=res["hitmap"][b], edges_hist=res["edges_hist"][b], ncells_hist=res["ncells_hist"][b],
+                         misfit_trace=res["misfit_trace"][b], iterations=it, burned_in=bool(sc[b, oracle.S_BURNED_IN]),
+                         acceptance=sc[b, oracle.S_N_ACCEPT] / max(it, 1)))
+    m = P.compare(refs, runs, top=200)
+    print("skytem sounding 2", m)
+    P.check(m, inside=(0.7, 0.9, 0.8), peak_cells=5, layers=0.75)
+    burned = sc[:, oracle.S_BURNED_IN] > 0
+    assert burned.mean() >= 0.9
+    assert np.median(sc[burned, oracle.S_BURNED_IN_ITER]) == int(g["burned_in_iteration"])       # 5001
+    for b in np.flatnonzero(burned)[:32]:
+        b0, it = int(sc[b, oracle.S_BURNED_IN_ITER]), int(sc[b, oracle.S_ITER])
+        assert 0.5 * 45 < res["misfit_trace"][b, b0:it].mean() < 1.5 * 45
+    k = np.arange(99)
+    for name in ("rel_hist", "add_hist"):
+        rr = sum(r[name].astype(np.int64) for r in refs)
+        oo = res[name].sum(axis=0, dtype=np.int64)
+        assert np.all(np.abs((rr * k).sum(axis=1) / rr.sum(axis=1) - (oo * k).sum(axis=1) / oo.sum(axis=1)) < 2.0), name
+
+
 def test_full_size_properties(gpu, systems):
     """A 4096-sounding batch (the bench's size) through size-independent invariants, device-pointer path."""
     import torch

@@ -53,6 +53,28 @@ def test_forward_and_jacobian_match_numba_reference(oracle, golden_dir):
         assert np.max(np.abs(J - refJ)) / np.max(np.abs(refJ)) < 1e-9
 
 
+def _tensor_system_dict(g):
+    return {k: list(g["sys_" + k]) for k in ("freq", "tor", "tmom", "tx", "ty", "tz", "ror", "rmom", "rx", "ry", "rz")}
+
+
+def test_mixed_tensor_components_and_coil_offsets_match_live_reference(oracle, golden_dir):
+    """Hxz / Hzx (tensor ids 3 and 7, fdem1d_numba.py:359-408) and vertical coil offsets (fdem1d.py:31-32): 96 models
+    through the reference's own FdemSystem + fdem1dfwd / fdem1dsen (tests/golden/make_golden.py fdem_tensor)."""
+    g = np.load(os.path.join(golden_dir, "fdem_tensor_models.npz"))
+    assert list(g["tensor_id"]) == [3, 7, 1, 9, 3, 7] and np.any(g["sys_tz"] != 0) and np.any(g["sys_rz"] != 0)
+    s = oracle.make_system(_tensor_system_dict(g))
+    assert list(s.tid[:6]) == [3, 7, 1, 9, 3, 7]
+    for i in range(len(g["nlayers"])):
+        L = int(g["nlayers"][i])
+        sig, thk = g["sigma"][i, :L], g["thickness"][i, :L]
+        f = oracle.fdem_forward(s, g["height"][i], sig, thk)
+        J = oracle.fdem_sensitivity(s, g["height"][i], sig, thk)
+        assert np.max(np.abs(f - g["forward"][i]) / (np.abs(g["forward"][i]) + 1.0)) < 5e-8, i
+        refJ = g["sensitivity"][i, :, :L]
+        # in-phase rows of the J1-only components carry the reference's own (H - H0)/H0 round-off (~1e-9 of max |J|)
+        assert np.max(np.abs(J - refJ)) / np.max(np.abs(refJ)) < 5e-9, i
+
+
 def test_jacobian_basement_column_is_derivative_of_forward(oracle):
     """Sanity of the Hankel/normalisation chain: the basement column of the Jacobian equals the finite
     difference of the forward.  NOTE (reference quirk, kept for parity): for layers of finite thickness
@@ -202,6 +224,26 @@ def test_chain_statistics_match_reference_chains(oracle, golden_dir):
     inside = (med >= ref_med.min(axis=0)[:120] - 2) & (med <= ref_med.max(axis=0)[:120] + 2)
     assert inside.mean() >= 0.9, med
     _extra_posterior_checks(refs, runs, 120, (0.85, 0.9))
+
+
+@pytest.mark.parametrize("sidx", [0, 2, 3])
+def test_chain_statistics_match_reference_ensembles_more_soundings(oracle, golden_dir, sidx):
+    """The same parity list (tests/posterior_parity.py) on three more soundings, 7 live-reference chains each: a
+    sounding that never burns in (0), one that burns in about half of the time (2), and one whose reference chains
+    scatter between 0.15 and 0.47 in acceptance rate (3)."""
+    import posterior_parity as P
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_chain_%d" % sidx))
+    refs = [dict(np.load(os.path.join(golden_dir, f))) for f in files]
+    assert len(refs) >= 7
+    g = refs[0]
+    s, o = oracle.make_system(), oracle.resolve_options(n_markov_chains=10000)
+    runs = _chains(oracle, s, o, g["data"], float(g["altitude"]), [900 + j for j in range(8)], sidx)
+    for r in runs:
+        sc = r["scalars"]
+        r["iterations"], r["burned_in"] = sc[oracle.S_ITER], sc[oracle.S_BURNED_IN]
+        r["acceptance"] = sc[oracle.S_N_ACCEPT] / sc[oracle.S_ITER]
+    assert abs(runs[0]["scalars"][oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-12
+    P.check(P.compare(refs, runs))
 
 
 # ------------------------------------------------------------------------------------------ solve_z (sensor height)
