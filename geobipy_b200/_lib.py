@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgeobipy_b200.so")
+LIB_PATH = os.environ.get("GBP_LIB_PATH") or os.path.join(HERE, "libgeobipy_b200.so")   # GBP_LIB_PATH: A/B builds (scripts/)
 
 MAXF, MAXL = 16, 30
 MAXC = 2 * MAXF

@@ -99,11 +99,10 @@ int get_tables(const gbp_fdem_system* sys, TableCache** out)
         return fail(e);
     }
     const size_t n = c->host.tab.size();
-    std::vector<float> f32(n);
-    for (size_t i = 0; i < n; ++i) f32[i] = (float)c->host.tab[i];
-    CK(cudaMalloc(&c->d_f32, n * sizeof(float)));
+    const std::vector<float>& f32 = c->host.tab_f32;   // packed chunk layout (gbp_tables.h)
+    CK(cudaMalloc(&c->d_f32, f32.size() * sizeof(float)));
     CK(cudaMalloc(&c->d_f64, n * sizeof(double)));
-    CK(cudaMemcpy(c->d_f32, f32.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_f32, f32.data(), f32.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_f64, c->host.tab.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     g_cache.push_back(c);
     *out = c;
@@ -167,7 +166,7 @@ int launch_fdem(TableCache* tc, int B, int l_stride, const int32_t* nl, const do
                 const double* alt, double* out, double* J, cudaStream_t st)
 {
     const int threads = 256, wpb = threads / 32;
-    const size_t tab_bytes = ((size_t)TAB_ROWS * tc->host.dev.tab_stride * sizeof(T) + 127) & ~(size_t)127;
+    const size_t tab_bytes = ((size_t)fdem_table_bytes<T>(tc->host.dev) + 127) & ~(size_t)127;
     const size_t per_warp = (2 * KS + GBP_MAXC + (SENS ? GBP_MAXC * KS : 0)) * sizeof(T);
     const size_t smem = tab_bytes + wpb * per_warp;
     auto kern = fdem_kernel<T, SENS>;
@@ -607,14 +606,14 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
     if (opt->solve_height) {  // sampled sensor height: its own kernels (the fixed-height ones stay what they were)
         if (!small) return fail("solve_height: systems with more than 6 frequencies are not built");
         if (precision == GBP_PRECISION_F32)
-            return launch_chain<float, float, 12, 16, KIND_FDEM_Z>(sd, tc->d_f32, (size_t)TAB_ROWS * sd.tab_stride * sizeof(float), P, st);
+            return launch_chain<float, float, 12, 16, KIND_FDEM_Z>(sd, tc->d_f32, (size_t)fdem_table_bytes<float>(sd), P, st);
         if (precision == GBP_PRECISION_F64)
-            return launch_chain<double, double, 12, 8, KIND_FDEM_Z>(sd, tc->d_f64, (size_t)TAB_ROWS * sd.tab_stride * sizeof(double), P, st);
+            return launch_chain<double, double, 12, 8, KIND_FDEM_Z>(sd, tc->d_f64, (size_t)fdem_table_bytes<double>(sd), P, st);
         return fail("precision must be 32 or 64");
     }
     // fp32: 16 chains per SM; fp64: 8 per SM
     if (precision == GBP_PRECISION_F32) {
-        const size_t tb = (size_t)TAB_ROWS * sd.tab_stride * sizeof(float);
+        const size_t tb = (size_t)fdem_table_bytes<float>(sd);
         // resident chains per SM: 16 (128 registers).  The SM's throughput saturates at ~16 warps (full waves of
         // equal-length chains: 16 -> 34.7 M, 28 -> 36.6 M evals/s), and fewer, faster chains shorten the tail of real
         // batches: 4096 soundings to termination 16: 1936 ms, 20: 2019, 24: 2086, 28: 2163 (profiles/README.md);
@@ -625,7 +624,7 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
                      : launch_chain<float, float, GBP_MAXC, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
     }
     if (precision == GBP_PRECISION_F64) {
-        const size_t tb = (size_t)TAB_ROWS * sd.tab_stride * sizeof(double);
+        const size_t tb = (size_t)fdem_table_bytes<double>(sd);
         return small ? launch_chain<double, double, 12, 8, KIND_FDEM>(sd, tc->d_f64, tb, P, st)
                      : launch_chain<double, double, GBP_MAXC, 8, KIND_FDEM>(sd, tc->d_f64, tb, P, st);
     }

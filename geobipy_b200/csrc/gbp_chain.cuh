@@ -268,7 +268,7 @@ __device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const type
     if constexpr (KIND == KIND_TDEM)
         tdem_eval<T>(*S, tab, w->fx.lam, w->fx.wgt, kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
     else
-        fdem_eval<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
+        fdem_run<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
 }
 
 // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
@@ -1789,7 +1789,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     T* tab = reinterpret_cast<T*>(smem);
     uint32_t tab_bytes;
     if constexpr (KIND == KIND_TDEM) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
-    else tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
+    else tab_bytes = fdem_table_bytes<T>(S);
     if (threadIdx.x == 0) {
         make_consts<R>(P.opt, P.n_depth, P.C, consts);
         if constexpr (KIND == KIND_TDEM) {
@@ -1865,7 +1865,7 @@ __global__ void __launch_bounds__(256) fdem_kernel(const __grid_constant__ SysDe
     __shared__ uint64_t bar;
     __shared__ SysShared<T> sys_s;
     T* tab = reinterpret_cast<T*>(smem);
-    const uint32_t tab_bytes = (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(T));
+    const uint32_t tab_bytes = fdem_table_bytes<T>(S);
     if (threadIdx.x == 0) fill_sys_shared<T>(S, sys_s);
     tma_stage(tab, g_tab, tab_bytes, &bar);
     __syncthreads();
@@ -1886,7 +1886,7 @@ __global__ void __launch_bounds__(256) fdem_kernel(const __grid_constant__ SysDe
             mthk[lane] = (T)thickness[(size_t)b * l_stride + lane];
         }
         __syncwarp();
-        fdem_eval<T>(sys_s, tab, (T)altitude[b], L, msig, mthk, pred, SENS ? J : nullptr, SENS);
+        fdem_run<T>(sys_s, tab, (T)altitude[b], L, msig, mthk, pred, SENS ? J : nullptr, SENS);
         if (lane < C) out[(size_t)b * C + lane] = (double)pred[lane];
         if (SENS) {
 #pragma unroll 1

@@ -25,6 +25,11 @@ namespace gbp {
 constexpr int KS = GBP_MAXL;        // layer stride of per-warp arrays
 constexpr int TAB_ROWS = 7;         // lam, u0re, u0im, ere, eim, cre, cim
 constexpr int MAX_SEG = 2 * GBP_MAXF;
+// fp32 path: the abscissae of a system are cut into CHUNKS of 64 (two per lane, packed fp32x2); a chunk never spans
+// two frequencies.  120-point J0 filter: 2 chunks, 140-point J1 filter: 3 chunks -> at most 5 per frequency.
+constexpr int CHUNK = 64;
+constexpr int MAX_CHUNK = 5 * GBP_MAXF;
+constexpr int CHUNK_FLOATS = 4 * 32 * 4;   // 4 quads of one float4 per lane
 
 struct Seg {
     int start, count, freq, pad;
@@ -33,6 +38,8 @@ struct Seg {
 // Per-system constants, passed by value as a kernel parameter.
 struct SysDev {
     int n_freq, n_seg, n_items, tab_stride;  // tab_stride = n_items rounded up (16-byte rows)
+    int n_chunks, pad_[3];
+    unsigned char chunk_freq[MAX_CHUNK];     // frequency of chunk c (chunks are ordered by frequency)
     Seg seg[MAX_SEG];
     double omu[GBP_MAXF];   // omega * mu0
     double k2re[GBP_MAXF];  // -omega^2 * mu0 * eps0   (Re of y-hat*z-hat, same for every earth layer)
@@ -72,7 +79,8 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
 
 // Per-CTA copy of the per-frequency constants in the arithmetic type T (shared memory).
 template <typename T> struct SysShared {
-    int n_freq, n_seg, tab_stride, pad;
+    int n_freq, n_seg, tab_stride, n_chunks;
+    unsigned char chunk_freq[MAX_CHUNK];
     Seg seg[MAX_SEG];
     T omu[GBP_MAXF], k2re[GBP_MAXF], hd0[GBP_MAXF];
 };
@@ -81,12 +89,21 @@ template <typename T> __device__ __forceinline__ void fill_sys_shared(const SysD
     q.n_freq = S.n_freq;
     q.n_seg = S.n_seg;
     q.tab_stride = S.tab_stride;
+    q.n_chunks = S.n_chunks;
+    for (int i = 0; i < MAX_CHUNK; ++i) q.chunk_freq[i] = S.chunk_freq[i];
     for (int i = 0; i < MAX_SEG; ++i) q.seg[i] = S.seg[i];
     for (int i = 0; i < GBP_MAXF; ++i) {
         q.omu[i] = (T)S.omu[i];
         q.k2re[i] = (T)S.k2re[i];
         q.hd0[i] = (T)S.hd0[i];
     }
+}
+
+// bytes of the per-system table of arithmetic type T: fp64 = TAB_ROWS rows of tab_stride values; fp32 = the packed
+// chunk layout of gbp_fdem_f2.cuh
+template <typename T> __host__ __device__ inline uint32_t fdem_table_bytes(const SysDev& S)
+{
+    return sizeof(T) == 4 ? (uint32_t)(S.n_chunks * CHUNK_FLOATS * sizeof(float)) : (uint32_t)(TAB_ROWS * S.tab_stride * sizeof(double));
 }
 
 // ---------------------------------------------------------------- the operator

@@ -1,12 +1,25 @@
-// fp32 production instantiation of fdem_eval(): TWO filter abscissae per lane, packed fp32x2 arithmetic.
+// fp32 production instantiation of fdem_eval(): packed fp32x2 arithmetic, two (forward + Jacobian) or four (forward
+// only) filter abscissae per lane.
 //
-// Blackwell (sm_100) has two-wide fp32 instructions (FFMA2 / FMUL2 / FADD2 on 64-bit register pairs,
-// PTX fma.rn.f32x2 ...).  Each lane carries the admittance recursion of abscissae j and j+32 in the two
-// halves of float2 registers: the instruction count of the complex arithmetic halves, and the two
-// independent recursions give every warp instruction-level parallelism (the sampler is bound by
-// dependent-issue latency, not by any pipe: ncu profiles/).  Special functions (MUFU rcp/sqrt/ex2/sin/cos)
-// stay scalar, two per pair.  Same mathematics as the generic template in gbp_fdem.cuh (which remains the
-// fp64 validation path); results differ only by summation order.
+// Blackwell (sm_100) has two-wide fp32 instructions (FFMA2 / FMUL2 / FADD2 on 64-bit register pairs, with free
+// negation / absolute-value operand modifiers).  Each lane carries the admittance recursion of abscissae l and l + 32
+// of a 64-abscissa CHUNK in the two halves of float2 registers; the forward-only pass runs two chunks at once as two
+// independent dependency chains (the sampler is bound by dependent-issue latency, not by any pipe: profiles/).
+// Special functions (MUFU rsq / sqrt / rcp / ex2 / sin / cos) stay scalar, two per pair.
+//
+// Same mathematics as the generic template in gbp_fdem.cuh (the fp64 validation path), rearranged so that a layer
+// costs ONE complex reciprocal and no tanh: with e = exp(-2 u t), d = y - u (y = admittance of the stack below)
+//     y' = u (y + u tanh(ut)) / (u + y tanh(ut)) = u (2y + (e-1) d) / (2u - (e-1) d)
+// and, for the Jacobian (the reference's M1_1 form, fdem1d_numba.py:223-301, quirk (viii) of DESIGN.md included),
+//     dy'/dy      = 4 u^2 e / den^2,                                   den = 2u - (e-1) d
+//     dy'/dln(s)  = (i b / 2) [ s^2 - 4 u e d (1 + t s) + e^2 (4 u^2 - d^2) ] / (u den^2),   s = y + u
+// (obtained from the tanh expressions with tanh = (1-e)/(1+e); 1 - tanh^2 = 4e/(1+e)^2).  exp(-2ut) underflows to an
+// exact 0 beyond 2 Re(u) t = 87 (ex2.approx.ftz), where tanh = 1 to fp32 precision, and |Im(2ut)| <= Re(2ut), so the
+// phase needs no range reduction beyond the one MUFU.SIN/COS apply themselves (error <= x e^-x 2^-24 on the product).
+//
+// Table layout (gbp_tables.h): per chunk four float4 per lane, quad-major (conflict-free LDS.128):
+//   quad 0 = (lam_a, lam_b, u0r_a, u0r_b)  quad 1 = (u0i_a, u0i_b, er_a, er_b)
+//   quad 2 = (ei_a, ei_b, cr_a, cr_b)      quad 3 = (ci_a, ci_b, -, -)
 #pragma once
 #include "gbp_fdem.cuh"
 
@@ -26,6 +39,13 @@ __device__ __forceinline__ v2 sub(v2 a, v2 b) { return __fadd2_rn(a, neg(b)); }
 __device__ __forceinline__ v2 fma(v2 a, v2 b, v2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ v2 rcp(v2 a) { return V(rt<float>::rcp(a.x), rt<float>::rcp(a.y)); }
 __device__ __forceinline__ v2 sqrt(v2 a) { return V(rt<float>::sqrt(a.x), rt<float>::sqrt(a.y)); }
+__device__ __forceinline__ float rsqrt1(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ v2 rsqrt(v2 a) { return V(rsqrt1(a.x), rsqrt1(a.y)); }
 
 __device__ __forceinline__ c2 operator+(c2 a, c2 b) { return {add(a.re, b.re), add(a.im, b.im)}; }
 __device__ __forceinline__ c2 operator-(c2 a, c2 b) { return {sub(a.re, b.re), sub(a.im, b.im)}; }
@@ -34,47 +54,86 @@ __device__ __forceinline__ c2 operator*(c2 a, c2 b)
     return {fma(a.re, b.re, neg(mul(a.im, b.im))), fma(a.re, b.im, mul(a.im, b.re))};
 }
 __device__ __forceinline__ c2 operator*(c2 a, v2 s) { return {mul(a.re, s), mul(a.im, s)}; }
+__device__ __forceinline__ c2 csq(c2 a) { return {fma(a.re, a.re, neg(mul(a.im, a.im))), mul(add(a.re, a.re), a.im)}; }
 __device__ __forceinline__ c2 cinv(c2 a)
 {
     const v2 d = rcp(fma(a.re, a.re, mul(a.im, a.im)));
     return {mul(a.re, d), neg(mul(a.im, d))};
 }
-// sqrt of a + ib with b >= 0 (first-quadrant result), both halves
-__device__ __forceinline__ c2 csqrt_q1(v2 a, v2 b)
+// u = sqrt(a + ib), b > 0 (first quadrant), both halves; m = |u|^2 = |a + ib|.  2 MUFU per half:
+// with x = (m + |a|)/2:  sqrt(x) = x rsq(x),  b / (2 sqrt(x)) = (b/2) rsq(x)
+__device__ __forceinline__ c2 csqrt_q1(v2 a, float b, v2& m)
+{
+    m = sqrt(fma(a, a, S(b * b)));
+    const v2 x = mul(S(0.5f), add(m, V(fabsf(a.x), fabsf(a.y))));
+    const v2 r = rsqrt(x);
+    const v2 t = mul(x, r);
+    const v2 o = mul(S(0.5f * b), r);
+    c2 u;
+    u.re = V(a.x >= 0.f ? t.x : o.x, a.y >= 0.f ? t.y : o.y);
+    u.im = V(a.x >= 0.f ? o.x : t.x, a.y >= 0.f ? o.y : t.y);
+    return u;
+}
+__device__ __forceinline__ c2 csqrt_q1(v2 a, v2 b)   // per-half b (time-domain kernel: lane = frequency)
 {
     const v2 m = sqrt(fma(a, a, mul(b, b)));
-    const v2 t = sqrt(mul(S(0.5f), add(m, V(fabsf(a.x), fabsf(a.y)))));
-    const v2 o = mul(b, rcp(add(t, t)));
-    c2 r;
-    r.re = V(a.x >= 0.f ? t.x : o.x, a.y >= 0.f ? t.y : o.y);
-    r.im = V(a.x >= 0.f ? o.x : t.x, a.y >= 0.f ? o.y : t.y);
-    return r;
+    const v2 x = mul(S(0.5f), add(m, V(fabsf(a.x), fabsf(a.y))));
+    const v2 r = rsqrt(x);
+    const v2 t = mul(x, r);
+    const v2 o = mul(mul(S(0.5f), b), r);
+    c2 u;
+    u.re = V(a.x >= 0.f ? t.x : o.x, a.y >= 0.f ? t.y : o.y);
+    u.im = V(a.x >= 0.f ? o.x : t.x, a.y >= 0.f ? o.y : t.y);
+    return u;
 }
-// exp(z), |Im z| <= ~64
+// exp(z); the phase goes to MUFU.SIN / MUFU.COS as it is (callers: |Im z| <= |Re z| or tiny)
 __device__ __forceinline__ c2 cexp(c2 z)
 {
     const v2 l = mul(z.re, S(1.4426950408889634f));
-    v2 e;
+    v2 e, s, c;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(l.x));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(l.y));
-    const v2 q = mul(z.im, S(0.15915494309189535f));
-    const v2 n = V(rintf(q.x), rintf(q.y));
-    v2 r = fma(n, S(-6.2831854820251465f), z.im);
-    r = fma(n, S(1.7484556000744883e-07f), r);
-    v2 s, c;
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s.x) : "f"(r.x));
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s.y) : "f"(r.y));
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c.x) : "f"(r.x));
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c.y) : "f"(r.y));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s.x) : "f"(z.im.x));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s.y) : "f"(z.im.y));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c.x) : "f"(z.im.x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c.y) : "f"(z.im.y));
     return {mul(e, c), mul(e, s)};
+}
+
+// one finite layer, forward only: y <- admittance at the top of the layer (b = omega mu sigma, t2 = -2 thickness)
+__device__ __forceinline__ void layer_fwd(const v2 a, const float b, const float t2, c2& y)
+{
+    v2 m;
+    const c2 u = csqrt_q1(a, b, m);
+    const c2 e = cexp(c2{mul(S(t2), u.re), mul(S(t2), u.im)});
+    const c2 p = c2{add(e.re, S(-1.f)), e.im} * (y - u);                             // (e - 1)(y - u)
+    const c2 den = {fma(S(2.f), u.re, neg(p.re)), fma(S(2.f), u.im, neg(p.im))};     // (1+e) u + (1-e) y
+    const c2 num = {fma(S(2.f), y.re, p.re), fma(S(2.f), y.im, p.im)};               // (1+e) y + (1-e) u
+    y = (u * num) * cinv(den);
+}
+
+// the air-earth interface of one abscissa pair: rTE * c * exp(e_j hDiff); `is` = 1 / (u0 + y1) for the Jacobian
+struct TopOut {
+    c2 term, K, is, u0;
+};
+__device__ __forceinline__ TopOut top_term(const float4 q0, const float4 q1, const float4 q2, const float4 q3, const c2 y,
+                                           const float hd)
+{
+    TopOut o;
+    o.u0 = c2{V(q0.z, q0.w), V(q1.x, q1.y)};
+    o.is = cinv(o.u0 + y);
+    const c2 rte = (o.u0 - y) * o.is;
+    o.K = c2{V(q2.z, q2.w), V(q3.x, q3.y)} * cexp(c2{mul(V(q1.z, q1.w), S(hd)), mul(V(q2.x, q2.y), S(hd))});
+    o.term = rte * o.K;
+    return o;
 }
 
 }  // namespace f2
 
-template <>
-__device__ __noinline__ void fdem_eval<float>(const SysShared<float>& Q, const float* __restrict__ tab, float alt, int L,
-                                              const float* __restrict__ msig, const float* __restrict__ mthk,
-                                              float* __restrict__ pred, float* __restrict__ J, const bool sens)
+// ---------------------------------------------------------------- forward only: two chunks per pass
+__device__ __noinline__ void fdem_fwd_f2(const SysShared<float>& Q, const float* __restrict__ tab, float alt, int L,
+                                         const float* __restrict__ msig, const float* __restrict__ mthk,
+                                         float* __restrict__ pred)
 {
     using namespace f2;
     __builtin_assume(__isShared(&Q));
@@ -83,123 +142,184 @@ __device__ __noinline__ void fdem_eval<float>(const SysShared<float>& Q, const f
     __builtin_assume(__isShared(mthk));
     __builtin_assume(__isShared(pred));
     const int lane = threadIdx.x & 31;
-    const int F = Q.n_freq;
-    const int ts = Q.tab_stride;
-    const float* t_lam = tab;
-    const float* t_u0r = tab + ts;
-    const float* t_u0i = tab + 2 * ts;
-    const float* t_er = tab + 3 * ts;
-    const float* t_ei = tab + 4 * ts;
-    const float* t_cr = tab + 5 * ts;
-    const float* t_ci = tab + 6 * ts;
+    const int F = Q.n_freq, NCH = Q.n_chunks;
+    const float4* T4 = reinterpret_cast<const float4*>(tab) + lane;
+    const float sL = msig[L - 1];
+    int cur_f = Q.chunk_freq[0];
+    c2 acc = {S(0.f), S(0.f)};
+#pragma unroll 1
+    for (int c = 0; c < NCH; c += 2) {
+        const bool hasB = c + 1 < NCH;
+        const int cB = hasB ? c + 1 : c;
+        const int fA = Q.chunk_freq[c], fB = Q.chunk_freq[cB];
+        const float4 qa0 = T4[(c * 4 + 0) * 32], qb0 = T4[(cB * 4 + 0) * 32];
+        const float omuA = Q.omu[fA], omuB = Q.omu[fB];
+        const v2 lamA = V(qa0.x, qa0.y), lamB = V(qb0.x, qb0.y);
+        const v2 aA = fma(lamA, lamA, S(Q.k2re[fA])), aB = fma(lamB, lamB, S(Q.k2re[fB]));   // Re(u^2) of every earth layer
+        v2 mA, mB;
+        c2 yA = csqrt_q1(aA, omuA * sL, mA), yB = csqrt_q1(aB, omuB * sL, mB);               // basement: y_L = u_L
+#pragma unroll 1
+        for (int k = L - 2; k >= 0; --k) {
+            const float sg = msig[k], t2 = -2.f * mthk[k];
+            layer_fwd(aA, omuA * sg, t2, yA);
+            layer_fwd(aB, omuB * sg, t2, yB);
+        }
+        const TopOut tA = top_term(qa0, T4[(c * 4 + 1) * 32], T4[(c * 4 + 2) * 32], T4[(c * 4 + 3) * 32], yA,
+                                   Q.hd0[fA] - 2.f * alt);
+        const TopOut tB = top_term(qb0, T4[(cB * 4 + 1) * 32], T4[(cB * 4 + 2) * 32], T4[(cB * 4 + 3) * 32], yB,
+                                   Q.hd0[fB] - 2.f * alt);
+        // chunks are ordered by frequency: close a frequency when the next chunk belongs to another one
+        if (fA != cur_f) {
+            const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
+            if (lane == 0) {
+                pred[cur_f] = sr;
+                pred[F + cur_f] = si;
+            }
+            acc = c2{S(0.f), S(0.f)};
+            cur_f = fA;
+        }
+        acc = acc + tA.term;
+        if (hasB) {
+            if (fB != cur_f) {
+                const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
+                if (lane == 0) {
+                    pred[cur_f] = sr;
+                    pred[F + cur_f] = si;
+                }
+                acc = c2{S(0.f), S(0.f)};
+                cur_f = fB;
+            }
+            acc = acc + tB.term;
+        }
+    }
+    const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
+    if (lane == 0) {
+        pred[cur_f] = sr;
+        pred[F + cur_f] = si;
+    }
+    __syncwarp();
+}
 
-    // thread-local scratch of the chain-rule pass (sens only), one float2 (two abscissae) per layer
+// ---------------------------------------------------------------- forward + Jacobian: one chunk per pass
+__device__ __noinline__ void fdem_sens_f2(const SysShared<float>& Q, const float* __restrict__ tab, float alt, int L,
+                                          const float* __restrict__ msig, const float* __restrict__ mthk,
+                                          float* __restrict__ pred, float* __restrict__ J)
+{
+    using namespace f2;
+    __builtin_assume(__isShared(&Q));
+    __builtin_assume(__isShared(tab));
+    __builtin_assume(__isShared(msig));
+    __builtin_assume(__isShared(mthk));
+    __builtin_assume(__isShared(pred));
+    const int lane = threadIdx.x & 31;
+    const int F = Q.n_freq, NCH = Q.n_chunks;
+    const float4* T4 = reinterpret_cast<const float4*>(tab) + lane;
+
+    // thread-local scratch of the chain-rule pass, one float2 (two abscissae) per layer:
+    // D_k = dy_k/dy_{k+1}, l_k = dy_k/dln(sigma_k); jr/ji accumulate the Jacobian of the current frequency
     v2 Dr[KS], Di[KS], lr[KS], li[KS];
     v2 jr[KS], ji[KS];
 
-    int seg = 0;
+    int cur_f = -1;
+    c2 acc = {S(0.f), S(0.f)};
 #pragma unroll 1
-    for (int f = 0; f < F; ++f) {
-        const float omu = Q.omu[f];
-        const float k2 = Q.k2re[f];
-        const float hd = Q.hd0[f] - 2.f * alt;
-        c2 acc = {S(0.f), S(0.f)};
-        if (sens) {
+    for (int c = 0; c <= NCH; ++c) {
+        const int f = c < NCH ? (int)Q.chunk_freq[c] : -2;
+        if (f != cur_f) {
+            if (cur_f >= 0) {  // close frequency cur_f
+                const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
+                if (lane == 0) {
+                    pred[cur_f] = sr;
+                    pred[F + cur_f] = si;
+                }
+#pragma unroll 1
+                for (int k = 0; k < L; ++k) {
+                    const float a = warp_sum(jr[k].x + jr[k].y), b = warp_sum(ji[k].x + ji[k].y);
+                    if (lane == 0) {
+                        J[cur_f * KS + k] = a;
+                        J[(F + cur_f) * KS + k] = b;
+                    }
+                }
+            }
+            if (c >= NCH) break;
+            cur_f = f;
+            acc = c2{S(0.f), S(0.f)};
 #pragma unroll 1
             for (int k = 0; k < L; ++k) {
                 jr[k] = S(0.f);
                 ji[k] = S(0.f);
             }
         }
-#pragma unroll 1
-        for (; seg < Q.n_seg && Q.seg[seg].freq == f; ++seg) {
-            const int s0 = Q.seg[seg].start, cnt = Q.seg[seg].count;
-#pragma unroll 1
-            for (int j = lane; j < cnt; j += 64) {
-                // abscissae j and j + 32 (an out-of-range partner is computed on a valid index with weight 0)
-                const int jb = j + 32;
-                const bool vb = jb < cnt;
-                const int ia = s0 + j, ib = s0 + (vb ? jb : j);
-                const v2 lam = V(t_lam[ia], t_lam[ib]);
-                const v2 a = fma(lam, lam, S(k2));  // Re(u^2) of every earth layer
-                // basement: y_L = u_L
-                float b = omu * msig[L - 1];
-                c2 u = csqrt_q1(a, S(b));
-                c2 y = u;
-                if (sens) {  // i*b/(2u)
-                    const c2 iu = cinv(u);
-                    lr[L - 1] = mul(S(-0.5f * b), iu.im);
-                    li[L - 1] = mul(S(0.5f * b), iu.re);
-                }
-#pragma unroll 1
-                for (int k = L - 2; k >= 0; --k) {
-                    b = omu * msig[k];
-                    const float t = mthk[k];
-                    u = csqrt_q1(a, S(b));
-                    // tanh(u t) = (1 - e)/(1 + e), e = exp(-2ut); clamp as in the generic template
-                    const float two_t = 2.f * t;
-                    const v2 lim = mul(S(60.f), rcp(u.re));
-                    const v2 sc = V(fminf(two_t, lim.x), fminf(two_t, lim.y));
-                    c2 e = cexp(c2{neg(mul(sc, u.re)), neg(mul(sc, u.im))});
-                    const v2 ze = V(two_t * u.re.x > 60.f ? 0.f : 1.f, two_t * u.re.y > 60.f ? 0.f : 1.f);
-                    e = e * ze;
-                    const c2 th = c2{sub(S(1.f), e.re), neg(e.im)} * cinv(c2{add(S(1.f), e.re), e.im});
-                    const c2 den = u + y * th;
-                    const c2 num = y + u * th;
-                    const c2 inv = cinv(den);
-                    if (sens) {
-                        const c2 u2 = {a, S(b)};
-                        const c2 th2 = th * th;
-                        const c2 inv2 = inv * inv;
-                        const c2 w = y * y - u2;                               // y^2 - u^2
-                        const c2 one_m = {sub(S(1.f), th2.re), neg(th2.im)};   // 1 - tanh^2
-                        const c2 d = u2 * one_m * inv2;                        // accumulate[] of M1_1
-                        Dr[k] = d.re;
-                        Di[k] = d.im;
-                        // B = 2uy th^2 + (y^2-u^2) th + 2u^2 - t u (y^2-u^2)(1 - th^2)
-                        const c2 uy = u * y;
-                        const c2 B = (uy * th2) * S(2.f) + w * th + u2 * S(2.f) - ((u * w) * one_m) * S(t);
-                        const c2 q = B * inv2 * cinv(u);                       // B / (u den^2)
-                        lr[k] = mul(S(-0.5f * b), q.im);                        // * i*b/2
-                        li[k] = mul(S(0.5f * b), q.re);
-                    }
-                    y = u * num * inv;
-                }
-                const c2 u0 = {V(t_u0r[ia], t_u0r[ib]), V(t_u0i[ia], t_u0i[ib])};
-                const c2 is = cinv(u0 + y);
-                const c2 rte = (u0 - y) * is;
-                const c2 cw = {V(t_cr[ia], vb ? t_cr[ib] : 0.f), V(t_ci[ia], vb ? t_ci[ib] : 0.f)};
-                const c2 K = cw * cexp(c2{mul(V(t_er[ia], t_er[ib]), S(hd)), mul(V(t_ei[ia], t_ei[ib]), S(hd))});
-                acc = acc + rte * K;
-                if (sens) {
-                    c2 P = (u0 * is * is) * S(-2.f) * K;  // d rTE/dy1 * K
-#pragma unroll 1
-                    for (int k = 0; k < L; ++k) {
-                        const c2 v = P * c2{lr[k], li[k]};
-                        jr[k] = add(jr[k], v.re);
-                        ji[k] = add(ji[k], v.im);
-                        if (k < L - 1) P = P * c2{Dr[k], Di[k]};
-                    }
-                }
-            }
+        const float omu = Q.omu[f];
+        const float4 q0 = T4[(c * 4 + 0) * 32];
+        const v2 lam = V(q0.x, q0.y);
+        const v2 a = fma(lam, lam, S(Q.k2re[f]));  // Re(u^2) of every earth layer
+        // basement: y_L = u_L, dy_L/dln(sigma_L) = i b / (2 u_L)
+        float b = omu * msig[L - 1];
+        v2 m;
+        c2 u = csqrt_q1(a, b, m);
+        c2 y = u;
+        {
+            const v2 hb = mul(S(0.5f * b), rcp(m));    // (b/2) / |u|^2 ;  i (b/2) conj(u) / |u|^2
+            lr[L - 1] = mul(hb, u.im);
+            li[L - 1] = mul(hb, u.re);
         }
-        const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
-        if (lane == 0) {
-            pred[f] = sr;
-            pred[F + f] = si;
-        }
-        if (sens) {
 #pragma unroll 1
-            for (int k = 0; k < L; ++k) {
-                const float a = warp_sum(jr[k].x + jr[k].y), b = warp_sum(ji[k].x + ji[k].y);
-                if (lane == 0) {
-                    J[f * KS + k] = a;
-                    J[(F + f) * KS + k] = b;
-                }
-            }
+        for (int k = L - 2; k >= 0; --k) {
+            b = omu * msig[k];
+            const float t = mthk[k];
+            u = csqrt_q1(a, b, m);
+            const c2 e = cexp(c2{mul(S(-2.f * t), u.re), mul(S(-2.f * t), u.im)});
+            const c2 d = y - u, s = y + u;
+            const c2 p = c2{add(e.re, S(-1.f)), e.im} * d;                                   // (e - 1)(y - u)
+            const c2 den = {fma(S(2.f), u.re, neg(p.re)), fma(S(2.f), u.im, neg(p.im))};
+            const c2 num = {fma(S(2.f), y.re, p.re), fma(S(2.f), y.im, p.im)};
+            const c2 inv = cinv(den);
+            const c2 inv2 = csq(inv);
+            const c2 ue = u * e;
+            const c2 dk = ((u * ue) * inv2) * S(4.f);                                        // 4 u^2 e / den^2
+            Dr[k] = dk.re;
+            Di[k] = dk.im;
+            // N = s^2 - 4 u e d (1 + t s) + e^2 (4 u^2 - d^2)
+            const c2 d2 = csq(d);
+            const c2 g = (ue * d) * c2{fma(S(t), s.re, S(1.f)), mul(S(t), s.im)};
+            const c2 h = csq(e) * c2{fma(S(4.f), a, neg(d2.re)), add(S(4.f * b), neg(d2.im))};
+            const c2 s2 = csq(s);
+            const c2 N = {add(fma(S(-4.f), g.re, s2.re), h.re), add(fma(S(-4.f), g.im, s2.im), h.im)};
+            // q = N / (u den^2) = N inv2 conj(u) / |u|^2 ;  l = (i b / 2) q
+            const c2 q = (N * inv2) * c2{u.re, neg(u.im)};
+            const v2 hb = mul(S(0.5f * b), rcp(m));
+            lr[k] = neg(mul(hb, q.im));
+            li[k] = mul(hb, q.re);
+            y = (u * num) * inv;
+        }
+        const TopOut tp = top_term(q0, T4[(c * 4 + 1) * 32], T4[(c * 4 + 2) * 32], T4[(c * 4 + 3) * 32], y,
+                                   Q.hd0[f] - 2.f * alt);
+        acc = acc + tp.term;
+        c2 P = ((tp.u0 * csq(tp.is)) * S(-2.f)) * tp.K;  // d rTE/dy1 * K
+#pragma unroll 1
+        for (int k = 0; k < L; ++k) {
+            const c2 v = P * c2{lr[k], li[k]};
+            jr[k] = add(jr[k], v.re);
+            ji[k] = add(ji[k], v.im);
+            if (k < L - 1) P = P * c2{Dr[k], Di[k]};
         }
     }
     __syncwarp();
+}
+
+// dispatch on the arithmetic type: fp32 -> the packed bodies above, fp64 -> the generic template
+template <typename T>
+__device__ __forceinline__ void fdem_run(const SysShared<T>& Q, const T* __restrict__ tab, T alt, int L,
+                                         const T* __restrict__ msig, const T* __restrict__ mthk, T* __restrict__ pred,
+                                         T* __restrict__ J, const bool sens)
+{
+    if constexpr (sizeof(T) == 4) {
+        if (sens) fdem_sens_f2(Q, tab, alt, L, msig, mthk, pred, J);
+        else fdem_fwd_f2(Q, tab, alt, L, msig, mthk, pred);
+    } else {
+        fdem_eval<T>(Q, tab, alt, L, msig, mthk, pred, J, sens);
+    }
 }
 
 }  // namespace gbp

@@ -20,6 +20,7 @@ namespace gbp {
 struct SysHost {
     SysDev dev;
     std::vector<double> tab;  // TAB_ROWS x tab_stride, fp64
+    std::vector<float> tab_f32;  // packed chunk layout of the fp32 path (gbp_fdem_f2.cuh): n_chunks x CHUNK_FLOATS
     std::string error;
 };
 
@@ -128,6 +129,44 @@ inline bool build_system_tables(const gbp_fdem_system& sys, SysHost& out)
         out.tab[i] = 1.0;
         out.tab[(size_t)stride + i] = 1.0;
     }
+    // fp32 path: chunks of 64 abscissae of one (frequency, filter) segment; lane l of chunk c owns abscissae
+    // 64 c' + l and 64 c' + 32 + l of its segment (a missing partner: lam = u0 = 1, weight 0).  Four float4 per lane,
+    // stored quad-major so that the 32 lanes of one LDS.128 are contiguous (conflict free):
+    //   quad 0 = (lam_a, lam_b, u0r_a, u0r_b)  quad 1 = (u0i_a, u0i_b, er_a, er_b)
+    //   quad 2 = (ei_a, ei_b, cr_a, cr_b)      quad 3 = (ci_a, ci_b, 0, 0)
+    int nchunk = 0;
+    out.tab_f32.clear();
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+        const Seg& sg = out.dev.seg[sgi];
+        for (int c0 = 0; c0 < sg.count; c0 += CHUNK) {
+            if (nchunk >= MAX_CHUNK) {
+                out.error = "too many filter chunks";
+                return false;
+            }
+            out.dev.chunk_freq[nchunk] = (unsigned char)sg.freq;
+            const size_t base = out.tab_f32.size();
+            out.tab_f32.resize(base + CHUNK_FLOATS, 0.f);
+            for (int l = 0; l < 32; ++l) {
+                const int ja = c0 + l, jb = c0 + 32 + l;
+                const bool va = ja < sg.count, vb = jb < sg.count;
+                const int ia = sg.start + (va ? ja : 0), ib = sg.start + (vb ? jb : 0);
+                auto get = [&](const std::vector<double>& r, bool v, int i, double dflt) { return (float)(v ? r[i] : dflt); };
+                float* q0 = &out.tab_f32[base + (size_t)(0 * 32 + l) * 4];
+                float* q1 = &out.tab_f32[base + (size_t)(1 * 32 + l) * 4];
+                float* q2 = &out.tab_f32[base + (size_t)(2 * 32 + l) * 4];
+                float* q3 = &out.tab_f32[base + (size_t)(3 * 32 + l) * 4];
+                q0[0] = get(lam, va, ia, 1.0); q0[1] = get(lam, vb, ib, 1.0);
+                q0[2] = get(u0r, va, ia, 1.0); q0[3] = get(u0r, vb, ib, 1.0);
+                q1[0] = get(u0i, va, ia, 0.0); q1[1] = get(u0i, vb, ib, 0.0);
+                q1[2] = get(er, va, ia, 0.0);  q1[3] = get(er, vb, ib, 0.0);
+                q2[0] = get(ei, va, ia, 0.0);  q2[1] = get(ei, vb, ib, 0.0);
+                q2[2] = get(cr, va, ia, 0.0);  q2[3] = get(cr, vb, ib, 0.0);
+                q3[0] = get(ci, va, ia, 0.0);  q3[1] = get(ci, vb, ib, 0.0);
+            }
+            ++nchunk;
+        }
+    }
+    out.dev.n_chunks = nchunk;
     return true;
 }
 

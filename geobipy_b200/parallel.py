@@ -7,7 +7,7 @@ sampling; the only collective is one gather of the posterior arrays to rank 0 at
 """
 import numpy as np
 
-__all__ = ["shard_bounds", "gather_to_rank0", "summarise_hitmap", "run_sharded"]
+__all__ = ["shard_bounds", "Collator", "gather_to_rank0", "summarise_hitmap", "run_sharded"]
 
 
 def shard_bounds(n, rank, world):
@@ -18,35 +18,84 @@ def shard_bounds(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_to_rank0(local, n_total, group=None):
-    """Gather a dict of per-sounding tensors (leading dimension = local block) to rank 0.
+class Collator:
+    """The end-of-run collation: ONE collective for all result arrays of a rank.
 
-    Every rank passes its block; blocks are padded to the largest block so one fixed-size
-    ``dist.gather`` per array is enough.  Returns the dict of full arrays on rank 0, None elsewhere.
-    Works without torch.distributed initialised (single process): returns ``local``.
-    """
-    import torch
+    Every per-sounding array of the block is packed into one contiguous byte row per sounding ([block, row_bytes] uint8,
+    fields 8-byte aligned), the rows of all ranks land in one buffer preallocated on rank 0 ([world, max_block,
+    row_bytes]) with a single ``dist.gather`` (NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests), and rank 0
+    reads the arrays back as typed views of that buffer.  ``warm_up()`` runs the collective once on the real buffers so
+    that the lazily created NCCL point-to-point channels exist before anything is timed (the first gather of a process
+    otherwise pays ~0.2-1.4 s of channel set-up: SCALE_r01.json)."""
+
+    def __init__(self, example, n_total, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group, self.n_total = group, int(n_total)
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+        self.blocks = [shard_bounds(n_total, r, self.world) for r in range(self.world)]
+        self.max_block = max(hi - lo for lo, hi in self.blocks)
+        self.fields, off = [], 0
+        for name in sorted(example):
+            t = example[name]
+            nbytes = int(np.prod(t.shape[1:], dtype=np.int64)) * t.element_size()
+            self.fields.append((name, off, nbytes, t.dtype, tuple(t.shape[1:])))
+            off += (nbytes + 7) & ~7
+        self.row_bytes = off
+        dev = next(iter(example.values())).device
+        self.send = torch.zeros((self.max_block, self.row_bytes), dtype=torch.uint8, device=dev)
+        self.recv = (torch.zeros((self.world, self.max_block, self.row_bytes), dtype=torch.uint8, device=dev)
+                     if (self.active and self.rank == 0) else None)
+
+    @property
+    def bytes_per_rank(self):
+        return self.max_block * self.row_bytes
+
+    def _pack(self, local):
+        import torch
+        for name, off, nbytes, dtype, shape in self.fields:
+            t = local[name].contiguous()
+            n = t.shape[0]
+            self.send[:n, off:off + nbytes] = t.reshape(n, -1).view(torch.uint8)
+
+    def _collective(self):
+        import torch.distributed as dist
+        dist.gather(self.send, list(self.recv.unbind(0)) if self.rank == 0 else None, dst=0, group=self.group)
+
+    def warm_up(self):
+        if self.active:
+            self._collective()
+
+    def gather(self, local):
+        """Full arrays (typed views of the receive buffer, block order = sounding order) on rank 0, None elsewhere."""
+        import torch
+        if not self.active:
+            return local
+        self._pack(local)
+        self._collective()
+        if self.rank != 0:
+            return None
+        out = {}
+        even = all(hi - lo == self.max_block for lo, hi in self.blocks)
+        for name, off, nbytes, dtype, shape in self.fields:
+            if even:  # one strided view: [world * block, nbytes] -> typed
+                v = self.recv[:, :, off:off + nbytes].reshape(self.world * self.max_block, nbytes)
+            else:
+                v = torch.cat([self.recv[r, :hi - lo, off:off + nbytes] for r, (lo, hi) in enumerate(self.blocks)], dim=0)
+            out[name] = v.contiguous().view(dtype).reshape((v.shape[0],) + shape)
+        return out
+
+
+def gather_to_rank0(local, n_total, group=None):
+    """Gather a dict of per-sounding tensors (leading dimension = local block) to rank 0 with one collective
+    (``Collator``).  Returns the dict of full arrays on rank 0, None elsewhere.  Works without torch.distributed
+    initialised (single process): returns ``local``.  Callers that gather repeatedly keep a ``Collator``."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    max_block = max(shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world))
-    out = {} if rank == 0 else None
-    for name in sorted(local):
-        t = local[name]
-        pad = max_block - t.shape[0]
-        if pad:
-            t = torch.cat([t, torch.zeros((pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)], dim=0)
-        t = t.contiguous()
-        bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, bufs, dst=0, group=group)
-        if rank == 0:
-            parts = []
-            for r in range(world):
-                lo, hi = shard_bounds(n_total, r, world)
-                parts.append(bufs[r][: hi - lo])
-            out[name] = torch.cat(parts, dim=0)
-    return out
+    return Collator(local, n_total, group).gather(local)
 
 
 def summarise_hitmap(hitmap, sigma_edges_ln, percentiles=(5.0, 50.0, 95.0)):
