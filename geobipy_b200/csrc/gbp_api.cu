@@ -291,6 +291,15 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
         Q.spec_helpers = hmax < 0 ? 0 : (hmax > WARPS - 1 ? WARPS - 1 : hmax);
         const char* m = std::getenv("GBP_SPEC_MIN_REJECTIONS");
         Q.spec_min_rejections = m ? std::atoi(m) : 24;
+        // teams of warps share their forward evaluations (fp32 frequency-domain kernels; gbp_chain.cuh team_round).
+        // Measured (profiles/README.md round 2): 8 warps per team, members on different SM sub-partitions, work units of
+        // one frequency.  GBP_TEAM=1 switches it off (results are bit-identical either way).
+        const char* t = std::getenv("GBP_TEAM");
+        Q.team_size = t ? std::atoi(t) : 8;
+        const char* ts = std::getenv("GBP_TEAM_SPREAD");
+        Q.team_spread = ts ? std::atoi(ts) : 1;
+        const char* tu = std::getenv("GBP_TEAM_FREQ_UNITS");
+        Q.team_freq_units = tu ? std::atoi(tu) : 1;
     }
     std::lock_guard<std::mutex> lk(g_dev[dev].mu);
     // per-call scratch, stream ordered: [work counter (256 B)] [per-chain Jacobian mirror, L2 resident: 1.4 KB per
@@ -619,7 +628,6 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
         // batches: 4096 soundings to termination 16: 1936 ms, 20: 2019, 24: 2086, 28: 2163 (profiles/README.md);
         // 8192 and 16384 soundings: equal.  GBP_FDEM_WARPS=28 selects the 72-register build.
         const char* e = std::getenv("GBP_FDEM_WARPS");
-        if (small && e && std::atoi(e) == 28) return launch_chain<float, float, 12, 28, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
         return small ? launch_chain<float, float, 12, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st)
                      : launch_chain<float, float, GBP_MAXC, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
     }

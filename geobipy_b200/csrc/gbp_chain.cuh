@@ -89,6 +89,19 @@ template <typename R> struct ValBuf {
     R ls[GBP_MAXL];         // ln(conductivity)
 };
 
+// A TEAM of warps (2 or 4, on the same SM sub-partition) shares its forward evaluations: every member brings at most
+// one request per round, the requests are cut into work units of one frequency each (so the result does not depend on
+// who computes what) and the n_freq x team_size units are claimed dynamically, the longest first.  All members therefore
+// run the same phase of accept_reject at the same time - the sampler code between two rounds is fetched once per
+// team instead of once per warp (the kernel is bound by instruction fetch: profiles/README.md, round 2) - and a
+// member without a chain keeps evaluating forwards for its team mates.
+struct TeamShared {
+    volatile int alive;   // members that still own a chain
+    int unit;             // next work unit of the current round
+    int freq_units;
+    void* member[16];     // WarpState of member m
+};
+
 template <typename R, typename T, int NC, int KIND> struct __align__(16) WarpState {
     R A[NPACK];             // packed lower triangle: Gauss-Newton matrix, then its Cholesky factor
     MeshBuf<R> mesh[2];
@@ -105,6 +118,13 @@ template <typename R, typename T, int NC, int KIND> struct __align__(16) WarpSta
     void* outp[OP_N];       // this chain's output rows
     SpecOut<R, ns_of(KIND)> sout;  // written by a speculative step that ends in an acceptance
     FwdExtra<T, KIND> fx;
+    // team mode (nullptr: this warp evaluates its forwards alone) and this warp's request of the current round
+    TeamShared* team;
+    int tm_size, tm_bar;
+    int req_active, req_kk, req_sens;
+    T req_alt;
+    T* req_pred;
+    T* req_J;
 };
 
 // Option-derived constants, computed once per CTA in fp64 and shared by its warps.
@@ -138,6 +158,9 @@ struct ChainParams {
     gbp_chain_buffers out;
     double data_scale;       // observed data and additive errors are multiplied by this on the way in (fp32
                              // time-domain path: 2^40, so that squares of 1e-15 V/Am^4 stay normal numbers)
+    int team_size;           // warps per team (1 = every warp evaluates its own forwards; 2 or 4: team_round)
+    int team_spread;         // 1: the members of a team sit on different SM sub-partitions (warps t*T .. t*T + T - 1)
+    int team_freq_units;     // 1: work units of one frequency; 0: two halves per request
     int spec_helpers;        // max warps that evaluate future iterations of one chain speculatively (0 = off)
     int spec_min_rejections; // a chain speculates once it has rejected this many steps in a row
     int* work_counter;
@@ -247,6 +270,63 @@ template <typename R> __device__ __forceinline__ R warp_min(R v)
 }
 
 // ================================================================ shared, non-inlined helpers
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// One round of a team: every member arrives with its request (req_active = 0: none) in its WarpState.  Returns false
+// when no member owns a chain any more (the team dissolves; nothing is computed in that round).
+template <typename R, typename T, int NC, int KIND>
+__device__ __noinline__ bool team_round(WarpState<R, T, NC, KIND>* w, const typename SysOf<T, KIND>::shared* S, const T* tab)
+{
+    if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+        GBP_SHARED(w);
+        TeamShared* tm = w->team;
+        GBP_SHARED(tm);
+        const int lane = lane_id();
+        const int tsz = w->tm_size, nthreads = 32 * tsz, bar = w->tm_bar, fu = tm->freq_units;
+        const int tlog = 31 - __clz(tsz);   // team sizes are powers of two
+        const int n_units = (fu ? S->n_freq : 2) << tlog;
+        __syncwarp();
+        named_bar_sync(bar, nthreads);   // requests (and `alive`) of all members are visible
+        if (tm->alive <= 0) return false;
+#pragma unroll 1
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(&tm->unit, 1);
+            u = __shfl_sync(FULL, u, 0);
+            if (u >= n_units) break;
+            // unit u = (frequency rank u / T, request of member u % T): the frequencies with most chunks go first
+            WarpState<R, T, NC, KIND>* wi = (WarpState<R, T, NC, KIND>*)tm->member[u & (tsz - 1)];
+            GBP_SHARED(wi);
+            if (!wi->req_active) continue;
+            const int ur = u >> tlog;
+            const int c0 = fu ? (int)S->unit_begin[ur] : S->half_begin[ur];
+            const int c1 = fu ? c0 + (int)S->unit_count[ur] : S->half_begin[ur + 1];
+            if (wi->req_sens) fdem_sens_f2(*S, tab, wi->req_alt, wi->req_kk, wi->msig, wi->mthk, wi->req_pred, wi->req_J, c0, c1);
+            else fdem_fwd_f2(*S, tab, wi->req_alt, wi->req_kk, wi->msig, wi->mthk, wi->req_pred, c0, c1);
+        }
+        named_bar_sync(bar, nthreads);   // results are visible to their owners
+        if (lane == 0 && tm->member[0] == (void*)w) tm->unit = 0;   // ordered before the next round's first barrier
+        return true;
+    } else {
+        return false;
+    }
+}
+
+// a round without a request (keeps the members of a team in the same phase: every accept_reject step is two rounds)
+template <typename R, typename T, int NC, int KIND>
+__device__ __forceinline__ void ch_round_pad(WarpState<R, T, NC, KIND>* w, const typename SysOf<T, KIND>::shared* S, const T* tab)
+{
+    if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+        if (w->team) {
+            if (lane_id() == 0) w->req_active = 0;
+            team_round<R, T, NC, KIND>(w, S, tab);
+        }
+    }
+}
+
 // J == nullptr: forward only.  Otherwise forward + Jacobian in one pass (FdemDataPoint.fm_dlogc :535)
 template <typename R, typename T, int NC, int KIND>
 __device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const typename SysOf<T, KIND>::shared* S, const T* tab,
@@ -265,10 +345,25 @@ __device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const type
         if (J) w->ctr[CT_N_SENS]++;
     }
     __syncwarp();
-    if constexpr (KIND == KIND_TDEM)
+    if constexpr (KIND == KIND_TDEM) {
         tdem_eval<T>(*S, tab, w->fx.lam, w->fx.wgt, kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
-    else
+    } else {
+        if constexpr (sizeof(T) == 4) {
+            if (w->team) {   // the team evaluates it (and this warp its share of the team's other requests)
+                if (lane == 0) {
+                    w->req_active = 1;
+                    w->req_kk = kk;
+                    w->req_sens = J != nullptr;
+                    w->req_alt = alt;
+                    w->req_pred = pred;
+                    w->req_J = J;
+                }
+                team_round<R, T, NC, KIND>(w, S, tab);
+                return;
+            }
+        }
         fdem_run<T>(*S, tab, alt, kk, w->msig, w->mthk, pred, J, J != nullptr);
+    }
 }
 
 // DataPoint.std :268-282 -> 1/variance per active channel (EmDataPoint.active :44-56)
@@ -763,6 +858,7 @@ __device__ __noinline__ init_out<R> ch_initialize(WarpState<R, T, NC, KIND>* w, 
     }
     __syncwarp();
     ch_forward(w, S, tab, alt, 1, v.sig, m.edges, w->pred[0], w->J);
+    ch_round_pad(w, S, tab);   // 101 forwards: one more round, so that a team stays in phase (two rounds per step)
     if (!first) {  // reset(): posteriors and traces are re-created
         ch_zero_posteriors(w, K);
         const long long N2 = 2 * (long long)K->n_chains;
@@ -978,9 +1074,12 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
             // predicted-data update is commented out (TdemDataPoint.py:1031-1055), so a time-domain death / move
             // forms the Newton gradient with the CURRENT model's predicted data.
             if constexpr (KIND != KIND_TDEM) ph = pred_t;
-        } else if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
-            ch_copy16(w->J, jg, JBYTES);
-            j_valid = true;
+        } else {
+            if (!SPEC) ch_round_pad(w, S, tab);   // team mode: the round of the forward this step does not need
+            if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
+                ch_copy16(w->J, jg, JBYTES);
+                j_valid = true;
+            }
         }
         ch_set_ivar(w, K, C, err);
         const R ln_r = (lane < kn) ? w->ls_r[lane] : R(0);
@@ -988,6 +1087,7 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
         ch_assemble(w, K, kn, mesh_p.t2, Jh);
         if (!ch_cholesky(w->A, kn)) {
             chol_failed = true;
+            if (!SPEC) ch_round_pad(w, S, tab);
         } else {
             const R stepv = ch_solve_LT(w->A, kn, ch_solve_L(w->A, kn, g));  // H * dfk
             const R mean = ln_r - K->alpha * stepv;  // ln sigma + alpha * pk, pk = -H dfk
@@ -1271,6 +1371,8 @@ __device__ __noinline__ void tail_service(WarpState<R, T, NC, KIND>* w, TailCtx<
         const unsigned seq = __shfl_sync(FULL, (unsigned)rd->seq, 0);
         const long long c_wake = clock64();
         ch_copy16(w, rd->owner_ws, (int)sizeof(WarpState<R, T, NC, KIND>));
+        if (lane == 0) w->team = nullptr;   // a private copy: its forwards are this warp's alone
+        __syncwarp();
         const long long c_copied = clock64();
         if (lane == 0) {
             atomicAdd(&g_diag[0], 1ull);
@@ -1549,7 +1651,24 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         // hand-off is amortised), and a chain that accepts every other step gains nothing
         // (helpers are shared by the chains of a CTA: long rejection runs use them fully, a chain with acceptance rate a
         // commits about 1/a iterations per round whatever their number - lower thresholds were measured slower)
-        if (spec_left == 0 && spec_stop == STOP_NONE && tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && *tc.n_idle > 0) {
+        // Team mode: a chain that gets stuck (a long rejection run) while it is the last one of its team and finds fewer
+        // than 4 idle warps in the CTA DISSOLVES the team - its mates leave the round protocol and become speculation
+        // helpers, the chain goes on alone.
+        if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+            if (w->team != nullptr && tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && w->team->alive <= 1 && *tc.n_idle < 4) {
+                if (lane == 0) {
+                    w->team->alive = 0;
+                    w->req_active = 0;
+                }
+                team_round<R, T, NC, KIND>(w, S, tab);   // everybody sees alive == 0 and leaves
+                if (lane == 0) w->team = nullptr;
+                __syncwarp();
+            }
+        }
+        // (a chain that still has its team speculates with the warps of OTHER teams that are done; its mates keep serving
+        // its own steps)
+        if (spec_left == 0 && spec_stop == STOP_NONE && tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && *tc.n_idle > 0 &&
+            (w->team == nullptr || w->team->alive <= 1)) {
             // helpers asked for grow with the rejection run (a short run usually ends within a few steps); the owner
             // waits during a round, so a round needs at least 2 (stuck chain) to 4 helpers to pay
             int want = 4 + (rej_run >> 2);
@@ -1786,6 +1905,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     __shared__ SpecRound<R, T, ns_of(KIND)> rounds[WARPS];
     __shared__ int mailbox[WARPS];
     __shared__ int n_alive, n_idle;
+    __shared__ TeamShared teams[WARPS];
     T* tab = reinterpret_cast<T*>(smem);
     uint32_t tab_bytes;
     if constexpr (KIND == KIND_TDEM) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
@@ -1815,14 +1935,37 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
         n_alive = 0;
         n_idle = 0;
     }
+    // teams: T warps of the same SM sub-partition (warp ids congruent mod 4): team = (warp & 3) + 4 (warp / 4T),
+    // member = (warp / 4) mod T; named barrier 1 + team
+    int team_size = 1;
+    if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+        const bool pow2 = P.team_size >= 2 && P.team_size <= 16 && (P.team_size & (P.team_size - 1)) == 0;
+        if (pow2 && WARPS % (4 * P.team_size) == 0 && WARPS / P.team_size < 16) team_size = P.team_size;
+        if (pow2 && P.team_spread && WARPS % P.team_size == 0 && WARPS / P.team_size < 16) team_size = P.team_size;
+    }
+    const int team_id = P.team_spread ? warp / team_size : (warp & 3) + 4 * (warp / (4 * team_size));
+    const int team_member = P.team_spread ? warp % team_size : (warp >> 2) % team_size;
     if (lane == 0) {
         mailbox[warp] = MB_BUSY;
         for (int x = 0; x < 32; ++x) rounds[warp].midx[x] = 0;
         rounds[warp].seq = 0u;
         rounds[warp].released = 0u;
+        ws->team = team_size > 1 ? &teams[team_id] : nullptr;
+        ws->tm_size = team_size;
+        ws->tm_bar = 1 + team_id;
+        ws->req_active = 0;
+        teams[warp].alive = 0;
+        teams[warp].unit = 0;
+        teams[warp].freq_units = P.team_freq_units;
     }
     __syncthreads();
-    if (lane == 0 && c < P.B) atomicAdd(&n_alive, 1);
+    if (lane == 0) {
+        if (c < P.B) atomicAdd(&n_alive, 1);
+        if (team_size > 1) {
+            teams[team_id].member[team_member] = (void*)ws;
+            if (c < P.B) atomicAdd((int*)&teams[team_id].alive, 1);
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0 && P.finish_ns) {
         unsigned long long tnow;
@@ -1844,6 +1987,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(P.work_counter, 1);
         c = __shfl_sync(FULL, nxt, 0);
+    }
+    if (team_size > 1) {
+        // out of chains: keep evaluating forwards for the team mates until none of them owns a chain
+        if (ws->team != nullptr) {   // (nullptr: this warp dissolved its team and finished alone)
+            if (lane == 0) {
+                if (had_chain) atomicSub((int*)&teams[team_id].alive, 1);
+                ws->req_active = 0;
+            }
+            __syncwarp();
+#pragma unroll 1
+            while (team_round<R, T, NC, KIND>(ws, &sys_s, tab)) {
+            }
+            if (lane == 0) ws->team = nullptr;
+            __syncwarp();
+        }
     }
     if (P.spec_helpers > 0) {
         // out of chains: evaluate future iterations of the chains of this CTA that are still running

@@ -38,7 +38,10 @@ struct Seg {
 // Per-system constants, passed by value as a kernel parameter.
 struct SysDev {
     int n_freq, n_seg, n_items, tab_stride;  // tab_stride = n_items rounded up (16-byte rows)
-    int n_chunks, pad_[3];
+    int n_chunks, half_begin[3];             // chunks [half_begin[h], half_begin[h+1]) = half h of a forward
+    // work units of a team round (gbp_chain.cuh): unit r = the chunks [unit_begin[r], unit_begin[r] + unit_count[r]) of
+    // ONE frequency, frequencies with the most chunks first
+    unsigned char unit_begin[GBP_MAXF], unit_count[GBP_MAXF];
     unsigned char chunk_freq[MAX_CHUNK];     // frequency of chunk c (chunks are ordered by frequency)
     Seg seg[MAX_SEG];
     double omu[GBP_MAXF];   // omega * mu0
@@ -80,6 +83,8 @@ __device__ __forceinline__ void tma_stage(void* smem_dst, const void* gmem_src, 
 // Per-CTA copy of the per-frequency constants in the arithmetic type T (shared memory).
 template <typename T> struct SysShared {
     int n_freq, n_seg, tab_stride, n_chunks;
+    int half_begin[3], pad;
+    unsigned char unit_begin[GBP_MAXF], unit_count[GBP_MAXF];
     unsigned char chunk_freq[MAX_CHUNK];
     Seg seg[MAX_SEG];
     T omu[GBP_MAXF], k2re[GBP_MAXF], hd0[GBP_MAXF];
@@ -90,6 +95,11 @@ template <typename T> __device__ __forceinline__ void fill_sys_shared(const SysD
     q.n_seg = S.n_seg;
     q.tab_stride = S.tab_stride;
     q.n_chunks = S.n_chunks;
+    for (int i = 0; i < 3; ++i) q.half_begin[i] = S.half_begin[i];
+    for (int i = 0; i < GBP_MAXF; ++i) {
+        q.unit_begin[i] = S.unit_begin[i];
+        q.unit_count[i] = S.unit_count[i];
+    }
     for (int i = 0; i < MAX_CHUNK; ++i) q.chunk_freq[i] = S.chunk_freq[i];
     for (int i = 0; i < MAX_SEG; ++i) q.seg[i] = S.seg[i];
     for (int i = 0; i < GBP_MAXF; ++i) {

@@ -131,9 +131,10 @@ __device__ __forceinline__ TopOut top_term(const float4 q0, const float4 q1, con
 }  // namespace f2
 
 // ---------------------------------------------------------------- forward only: two chunks per pass
+// chunks [c0, c1) only (a whole forward: 0, Q.n_chunks; one half of it: Q.half_begin[h], Q.half_begin[h + 1])
 __device__ __noinline__ void fdem_fwd_f2(const SysShared<float>& Q, const float* __restrict__ tab, float alt, int L,
                                          const float* __restrict__ msig, const float* __restrict__ mthk,
-                                         float* __restrict__ pred)
+                                         float* __restrict__ pred, const int c0, const int c1)
 {
     using namespace f2;
     __builtin_assume(__isShared(&Q));
@@ -142,13 +143,14 @@ __device__ __noinline__ void fdem_fwd_f2(const SysShared<float>& Q, const float*
     __builtin_assume(__isShared(mthk));
     __builtin_assume(__isShared(pred));
     const int lane = threadIdx.x & 31;
-    const int F = Q.n_freq, NCH = Q.n_chunks;
+    const int F = Q.n_freq, NCH = c1;
+    if (c0 >= c1) return;
     const float4* T4 = reinterpret_cast<const float4*>(tab) + lane;
     const float sL = msig[L - 1];
-    int cur_f = Q.chunk_freq[0];
+    int cur_f = Q.chunk_freq[c0];
     c2 acc = {S(0.f), S(0.f)};
 #pragma unroll 1
-    for (int c = 0; c < NCH; c += 2) {
+    for (int c = c0; c < NCH; c += 2) {
         const bool hasB = c + 1 < NCH;
         const int cB = hasB ? c + 1 : c;
         const int fA = Q.chunk_freq[c], fB = Q.chunk_freq[cB];
@@ -203,7 +205,7 @@ __device__ __noinline__ void fdem_fwd_f2(const SysShared<float>& Q, const float*
 // ---------------------------------------------------------------- forward + Jacobian: one chunk per pass
 __device__ __noinline__ void fdem_sens_f2(const SysShared<float>& Q, const float* __restrict__ tab, float alt, int L,
                                           const float* __restrict__ msig, const float* __restrict__ mthk,
-                                          float* __restrict__ pred, float* __restrict__ J)
+                                          float* __restrict__ pred, float* __restrict__ J, const int c0, const int c1)
 {
     using namespace f2;
     __builtin_assume(__isShared(&Q));
@@ -212,7 +214,7 @@ __device__ __noinline__ void fdem_sens_f2(const SysShared<float>& Q, const float
     __builtin_assume(__isShared(mthk));
     __builtin_assume(__isShared(pred));
     const int lane = threadIdx.x & 31;
-    const int F = Q.n_freq, NCH = Q.n_chunks;
+    const int F = Q.n_freq, NCH = c1;
     const float4* T4 = reinterpret_cast<const float4*>(tab) + lane;
 
     // thread-local scratch of the chain-rule pass, one float2 (two abscissae) per layer:
@@ -223,7 +225,7 @@ __device__ __noinline__ void fdem_sens_f2(const SysShared<float>& Q, const float
     int cur_f = -1;
     c2 acc = {S(0.f), S(0.f)};
 #pragma unroll 1
-    for (int c = 0; c <= NCH; ++c) {
+    for (int c = c0; c <= NCH; ++c) {
         const int f = c < NCH ? (int)Q.chunk_freq[c] : -2;
         if (f != cur_f) {
             if (cur_f >= 0) {  // close frequency cur_f
@@ -315,8 +317,8 @@ __device__ __forceinline__ void fdem_run(const SysShared<T>& Q, const T* __restr
                                          T* __restrict__ J, const bool sens)
 {
     if constexpr (sizeof(T) == 4) {
-        if (sens) fdem_sens_f2(Q, tab, alt, L, msig, mthk, pred, J);
-        else fdem_fwd_f2(Q, tab, alt, L, msig, mthk, pred);
+        if (sens) fdem_sens_f2(Q, tab, alt, L, msig, mthk, pred, J, 0, Q.n_chunks);
+        else fdem_fwd_f2(Q, tab, alt, L, msig, mthk, pred, 0, Q.n_chunks);
     } else {
         fdem_eval<T>(Q, tab, alt, L, msig, mthk, pred, J, sens);
     }

@@ -134,36 +134,74 @@ inline bool build_system_tables(const gbp_fdem_system& sys, SysHost& out)
     // stored quad-major so that the 32 lanes of one LDS.128 are contiguous (conflict free):
     //   quad 0 = (lam_a, lam_b, u0r_a, u0r_b)  quad 1 = (u0i_a, u0i_b, er_a, er_b)
     //   quad 2 = (ei_a, ei_b, cr_a, cr_b)      quad 3 = (ci_a, ci_b, 0, 0)
+    // Chunk ORDER: the frequencies are dealt into two halves of (nearly) equal chunk count (longest first), the chunks
+    // of half 0 come first: a team of warps splits one forward at half_begin[1] (gbp_chain.cuh, team_round) and every
+    // frequency is still summed by one warp in the same order, so results do not depend on the split.
     int nchunk = 0;
     out.tab_f32.clear();
-    for (int sgi = 0; sgi < nseg; ++sgi) {
-        const Seg& sg = out.dev.seg[sgi];
-        for (int c0 = 0; c0 < sg.count; c0 += CHUNK) {
-            if (nchunk >= MAX_CHUNK) {
-                out.error = "too many filter chunks";
-                return false;
+    int cnt[GBP_MAXF] = {0}, half_of[GBP_MAXF] = {0}, load[2] = {0, 0};
+    for (int sgi = 0; sgi < nseg; ++sgi) cnt[out.dev.seg[sgi].freq] += (out.dev.seg[sgi].count + CHUNK - 1) / CHUNK;
+    {
+        bool done[GBP_MAXF] = {false};
+        for (int it = 0; it < F; ++it) {
+            int best = -1;
+            for (int f = 0; f < F; ++f)
+                if (!done[f] && (best < 0 || cnt[f] > cnt[best])) best = f;
+            done[best] = true;
+            const int h = load[1] < load[0] ? 1 : 0;
+            half_of[best] = h;
+            load[h] += cnt[best];
+        }
+    }
+    for (int h = 0; h < 2; ++h) {
+        out.dev.half_begin[h] = nchunk;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+            const Seg& sg = out.dev.seg[sgi];
+            if (half_of[sg.freq] != h) continue;
+            for (int c0 = 0; c0 < sg.count; c0 += CHUNK) {
+                if (nchunk >= MAX_CHUNK) {
+                    out.error = "too many filter chunks";
+                    return false;
+                }
+                out.dev.chunk_freq[nchunk] = (unsigned char)sg.freq;
+                const size_t base = out.tab_f32.size();
+                out.tab_f32.resize(base + CHUNK_FLOATS, 0.f);
+                for (int l = 0; l < 32; ++l) {
+                    const int ja = c0 + l, jb = c0 + 32 + l;
+                    const bool va = ja < sg.count, vb = jb < sg.count;
+                    const int ia = sg.start + (va ? ja : 0), ib = sg.start + (vb ? jb : 0);
+                    auto get = [&](const std::vector<double>& r, bool v, int i, double dflt) { return (float)(v ? r[i] : dflt); };
+                    float* q0 = &out.tab_f32[base + (size_t)(0 * 32 + l) * 4];
+                    float* q1 = &out.tab_f32[base + (size_t)(1 * 32 + l) * 4];
+                    float* q2 = &out.tab_f32[base + (size_t)(2 * 32 + l) * 4];
+                    float* q3 = &out.tab_f32[base + (size_t)(3 * 32 + l) * 4];
+                    q0[0] = get(lam, va, ia, 1.0); q0[1] = get(lam, vb, ib, 1.0);
+                    q0[2] = get(u0r, va, ia, 1.0); q0[3] = get(u0r, vb, ib, 1.0);
+                    q1[0] = get(u0i, va, ia, 0.0); q1[1] = get(u0i, vb, ib, 0.0);
+                    q1[2] = get(er, va, ia, 0.0);  q1[3] = get(er, vb, ib, 0.0);
+                    q2[0] = get(ei, va, ia, 0.0);  q2[1] = get(ei, vb, ib, 0.0);
+                    q2[2] = get(cr, va, ia, 0.0);  q2[3] = get(cr, vb, ib, 0.0);
+                    q3[0] = get(ci, va, ia, 0.0);  q3[1] = get(ci, vb, ib, 0.0);
+                }
+                ++nchunk;
             }
-            out.dev.chunk_freq[nchunk] = (unsigned char)sg.freq;
-            const size_t base = out.tab_f32.size();
-            out.tab_f32.resize(base + CHUNK_FLOATS, 0.f);
-            for (int l = 0; l < 32; ++l) {
-                const int ja = c0 + l, jb = c0 + 32 + l;
-                const bool va = ja < sg.count, vb = jb < sg.count;
-                const int ia = sg.start + (va ? ja : 0), ib = sg.start + (vb ? jb : 0);
-                auto get = [&](const std::vector<double>& r, bool v, int i, double dflt) { return (float)(v ? r[i] : dflt); };
-                float* q0 = &out.tab_f32[base + (size_t)(0 * 32 + l) * 4];
-                float* q1 = &out.tab_f32[base + (size_t)(1 * 32 + l) * 4];
-                float* q2 = &out.tab_f32[base + (size_t)(2 * 32 + l) * 4];
-                float* q3 = &out.tab_f32[base + (size_t)(3 * 32 + l) * 4];
-                q0[0] = get(lam, va, ia, 1.0); q0[1] = get(lam, vb, ib, 1.0);
-                q0[2] = get(u0r, va, ia, 1.0); q0[3] = get(u0r, vb, ib, 1.0);
-                q1[0] = get(u0i, va, ia, 0.0); q1[1] = get(u0i, vb, ib, 0.0);
-                q1[2] = get(er, va, ia, 0.0);  q1[3] = get(er, vb, ib, 0.0);
-                q2[0] = get(ei, va, ia, 0.0);  q2[1] = get(ei, vb, ib, 0.0);
-                q2[2] = get(cr, va, ia, 0.0);  q2[3] = get(cr, vb, ib, 0.0);
-                q3[0] = get(ci, va, ia, 0.0);  q3[1] = get(ci, vb, ib, 0.0);
-            }
-            ++nchunk;
+        }
+    }
+    out.dev.half_begin[2] = nchunk;
+    {   // per-frequency work units, most chunks first
+        int fb[GBP_MAXF], fc[GBP_MAXF] = {0};
+        for (int c = nchunk - 1; c >= 0; --c) {
+            fb[out.dev.chunk_freq[c]] = c;
+            fc[out.dev.chunk_freq[c]]++;
+        }
+        bool done[GBP_MAXF] = {false};
+        for (int r = 0; r < F; ++r) {
+            int best = -1;
+            for (int f = 0; f < F; ++f)
+                if (!done[f] && (best < 0 || fc[f] > fc[best])) best = f;
+            done[best] = true;
+            out.dev.unit_begin[r] = (unsigned char)fb[best];
+            out.dev.unit_count[r] = (unsigned char)fc[best];
         }
     }
     out.dev.n_chunks = nchunk;

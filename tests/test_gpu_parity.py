@@ -482,3 +482,26 @@ def test_ten_thousand_random_models_fp32_vs_fp64(gpu, systems, oracle, kind):
         ok = dJ <= 3e-2 * rowmax + 1e-3 * sn
         assert ok.all(), (float((dJ / (3e-2 * rowmax + 1e-3 * sn)).max()), int((~ok).sum()))
         assert np.median(dJ / rowmax) < 1e-4
+
+
+def test_team_mode_is_bit_identical(gpu, systems, oracle, monkeypatch):
+    """Teams of warps sharing their forward evaluations (gbp_chain.cuh team_round; the production default is 8 warps per
+    team) must not change a single bit of the results: every frequency of a forward is still summed by one warp in the
+    same order.  Team sizes 1 (off), 2, 4, 8 and both member mappings / unit granularities, on a batch that has more
+    chains than resident warps (chains are claimed dynamically and teams dissolve at the end) and one that has fewer."""
+    opt = gpu.make_options(n_markov_chains=10000)
+    for B, nit in ((2500, 200), (37, 900)):
+        data, alt = _observed(oracle, systems[1], min(B, 64))
+        reps = -(-B // data.shape[0])
+        data, alt = np.tile(data, (reps, 1))[:B], np.tile(alt, reps)[:B]
+        ref = None
+        for team, spread, fu in ((1, 1, 1), (2, 0, 0), (4, 0, 1), (4, 1, 0), (8, 1, 1)):
+            monkeypatch.setenv("GBP_TEAM", str(team))
+            monkeypatch.setenv("GBP_TEAM_SPREAD", str(spread))
+            monkeypatch.setenv("GBP_TEAM_FREQ_UNITS", str(fu))
+            r = gpu.rjmcmc_run(systems[0], opt, data, alt, seed=5, max_iterations=nit, precision=32)
+            if ref is None:
+                ref = r
+                continue
+            for k in ref:
+                assert np.array_equal(ref[k], r[k], equal_nan=True), (B, team, spread, fu, k)
