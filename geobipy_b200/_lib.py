@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("GBP_LIB_PATH") or os.path.join(HERE, "libgeobipy_b200
 MAXF, MAXL = 16, 30
 MAXC = 2 * MAXF
 TD_MAXSYS, TD_NFREQ, TD_MAXLAM, TD_MAXWIN, TD_MAXC, TD_MAXWAVE, TD_MAXFILT = 2, 32, 32, 32, 64, 64, 4
+TD_SAMPLER_MAXC = 48   # channels the time-domain SAMPLER holds per chain (GBP_TD_SAMPLER_MAXC)
 NSCALARS = 32
 PRECISION_F32, PRECISION_F64 = 32, 64
 
@@ -87,7 +88,7 @@ class ChainBuffersC(ctypes.Structure):
 # every symbol include/geobipy_b200.h declares
 EXPORTS = (
     "gbp_version", "gbp_last_error", "gbp_device_count", "gbp_n_depth", "gbp_flops_per_forward",
-    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times",
+    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_kernel_ms_stats", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times",
     "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host", "gbp_release_host_buffers", "gbp_summarise_hitmap",
@@ -126,6 +127,8 @@ def load():
     lib.gbp_launch_count.restype = i64
     lib.gbp_last_kernel_ms.restype = i32
     lib.gbp_last_kernel_ms.argtypes = [vp]
+    lib.gbp_kernel_ms_stats.restype = i32
+    lib.gbp_kernel_ms_stats.argtypes = [i32, vp, vp]
     lib.gbp_fdem_forward.restype = i32
     lib.gbp_fdem_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, vp]
     lib.gbp_fdem_sensitivity.restype = i32

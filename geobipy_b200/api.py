@@ -365,6 +365,12 @@ class Inference1D:
             datapoint.initialize(initial_relative_error=[o.rel_init, o.rel_init2], initial_additive_error=[o.add_init, o.add_init2])
         else:
             datapoint.initialize(initial_relative_error=o.rel_init, initial_additive_error=o.add_init)
+        hk = getattr(o, "height_key", None)
+        if o.solve_height and hk is not None:
+            # the reference reads solve_z for the datapoint's own height (Point.set_priors :959-961) and
+            # solve_transmitter_z for the transmitter loop of a time-domain datapoint (Loop_pair / EmLoop)
+            assert (hk == "solve_transmitter_z") == self._tdem, NotImplementedError(
+                "%s is not built for a %s datapoint" % (hk, "time-domain" if self._tdem else "frequency-domain"))
         self.iteration, self.burned_in, self.burned_in_iteration = 0, False, 0
 
     def infer(self, hdf_file_handle=None, max_iterations=0):
@@ -431,7 +437,12 @@ class Inference1D:
             self.height_posterior = Histogram(r["height_hist"][b], z_ref + np.linspace(-o.max_height_change, o.max_height_change,
                                                                                      o.n_err_bins + 1))
             self.best_height = float(s[_lib.S_BEST_HEIGHT])
-            dp.z = float(s[_lib.S_CUR_HEIGHT])
+            if self._tdem:   # the transmitter moves, the receiver keeps its offset (Loop_pair.Geometry, Loop_pair.py:62-78)
+                dz = float(s[_lib.S_CUR_HEIGHT]) - float(dp.transmitter.z)
+                dp.transmitter.z = float(dp.transmitter.z) + dz
+                dp.receiver.z = float(dp.receiver.z) + dz
+            else:
+                dp.z = float(s[_lib.S_CUR_HEIGHT])
         dp.forward(self.model)
 
     def interface_probability(self):

@@ -985,7 +985,6 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     if (gbp_tdem_n_channels(sv) > GBP_TD_SAMPLER_MAXC)
         return fail("time-domain sampler: at most 48 data channels per datapoint (GBP_TD_SAMPLER_MAXC)");
     TdCache* tc;
-    if (opt->solve_height) return fail("solve_height is not built for time-domain datapoints (the loop height enters the geometry weights)");
     if (get_td_tables(sv, &tc, true)) return 1;
     ChainParams P;
     std::memset(&P, 0, sizeof(P));
@@ -1013,10 +1012,16 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
         P.opt.add_max2 *= TD_F32_SCALE;
         // 12 chains per SM (to termination, scripts/gpu_tdem_warps.py: 4096 soundings 12: 3157 ms, 16: 3437, 8: 3656;
         // 8192 soundings 12: 5312 ms, 16: 5505, 8: 6243; 18 chains per SM at 113 registers spill and are slower still)
+        // solve_height (the options file's solve_transmitter_z): its own instantiation, the fixed-height kernel stays what it was
+        if (opt->solve_height)
+            return launch_chain<float, float, GBP_TD_SAMPLER_MAXC, 12, KIND_TDEM_Z>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
         return launch_chain<float, float, GBP_TD_SAMPLER_MAXC, 12, KIND_TDEM>(sd, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
     }
-    if (precision == GBP_PRECISION_F64)
+    if (precision == GBP_PRECISION_F64) {
+        if (opt->solve_height)
+            return launch_chain<double, double, GBP_TD_SAMPLER_MAXC, 8, KIND_TDEM_Z>(sd, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
         return launch_chain<double, double, GBP_TD_SAMPLER_MAXC, 8, KIND_TDEM>(sd, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
+    }
     return fail("precision must be 32 or 64");
 }
 

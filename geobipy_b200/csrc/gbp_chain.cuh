@@ -50,8 +50,13 @@ enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_REL2, BV_ADD2, BV_N = 8 };
 // domain (TdemDataPoint, one or two systems with per-system errors, TdemDataPoint.py:329-379)
 // KIND_FDEM_Z: a frequency-domain datapoint whose sensor height is sampled too (solve_z: Point.perturb :614-622,
 // Point.set_priors :959-961).  Its own instantiation, so that the fixed-height kernels are what they were.
-enum { KIND_FDEM = 0, KIND_TDEM = 1, KIND_FDEM_Z = 2 };
-__host__ __device__ constexpr int ns_of(int kind) { return kind == KIND_TDEM ? GBP_TD_MAXSYS : 1; }
+// KIND_TDEM_Z: a time-domain datapoint whose TRANSMITTER height is sampled (the options file's solve_transmitter_z:
+// TdemDataPoint.perturb :681-683 -> Loop_pair.perturb -> Point.perturb on the transmitter loop; prior added after the
+// error priors, TdemDataPoint.probability :950-951; fixed receiver offset).
+enum { KIND_FDEM = 0, KIND_TDEM = 1, KIND_FDEM_Z = 2, KIND_TDEM_Z = 3 };
+__host__ __device__ constexpr bool is_td(int kind) { return kind == KIND_TDEM || kind == KIND_TDEM_Z; }
+__host__ __device__ constexpr bool has_z(int kind) { return kind == KIND_FDEM_Z || kind == KIND_TDEM_Z; }
+__host__ __device__ constexpr int ns_of(int kind) { return is_td(kind) ? GBP_TD_MAXSYS : 1; }
 template <typename T, int KIND> struct SysOf {
     typedef SysShared<T> shared;
     typedef SysDev dev;
@@ -60,11 +65,25 @@ template <typename T> struct SysOf<T, KIND_TDEM> {
     typedef TdShared<T> shared;
     typedef TdDev dev;
 };
+template <typename T> struct SysOf<T, KIND_TDEM_Z> {
+    typedef TdShared<T> shared;
+    typedef TdDev dev;
+};
 // per-chain scratch of the forward operator
 template <typename T, int KIND> struct FwdExtra {};
 template <typename T> struct FwdExtra<T, KIND_TDEM> {
-    T lam[GBP_TD_MAXLAM], wgt[GBP_TD_MAXLAM];  // this sounding's Hankel abscissae and geometry weights
+    T lam[1][GBP_TD_MAXLAM], wgt[1][GBP_TD_MAXLAM];  // this sounding's Hankel abscissae and geometry weights
     T sbuf[TD_ROWS];
+    T alt[1];
+    int cur;
+};
+// sampled transmitter height: the abscissae / weights depend on it, so there are two sets - the current height's
+// (index cur) and the proposed height's, swapped on acceptance
+template <typename T> struct FwdExtra<T, KIND_TDEM_Z> {
+    T lam[2][GBP_TD_MAXLAM], wgt[2][GBP_TD_MAXLAM];
+    T sbuf[TD_ROWS];
+    T alt[2];   // height each set was computed for
+    int cur;
 };
 // relative / additive errors, one per system (registers)
 template <typename R, int NS> struct Errs {
@@ -168,7 +187,7 @@ struct ChainParams {
     unsigned long long* finish_ns;  // debug (GBP_DEBUG_TIMELINE): [B + 1] %globaltimer at the end of each chain, [B] = earliest start
 };
 
-template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c)
+template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c, const bool height_last)
 {
     c.cum0 = (R)o.p_birth;
     c.cum1 = (R)(o.p_birth + o.p_death);
@@ -189,7 +208,9 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
     c.half_log2pi = (R)(0.5 * l2pi);
     c.n_sys = o.n_systems > 1 ? 2 : 1;
     // Point.probability :160-196 comes first in DataPoint.probability: Uniform(z0 - dz, z0 + dz), always in bounds
-    double lp = o.solve_height ? -dlog_(2.0 * o.max_height_change) : 0.0;
+    // (a time-domain datapoint adds the height prior AFTER the error priors, TdemDataPoint.probability :950-951: the
+    // order only matters for the last bit of the fp64 sum, which the trajectory twin of the oracle shares)
+    double lp = (o.solve_height && !height_last) ? -dlog_(2.0 * o.max_height_change) : 0.0;
     c.z_sd = (R)::sqrt(o.height_prop_var);
     c.z_max = (R)o.max_height_change;
     c.z_dx = (R)(2.0 * o.max_height_change / (double)o.n_err_bins);
@@ -219,6 +240,7 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
         c.add_lnmin[1] = c.add_lnmin[0]; c.add_lnmax[1] = c.add_lnmax[0]; c.add_sd[1] = c.add_sd[0];
         c.add_ln0[1] = c.add_ln0[0]; c.add0[1] = c.add0[0]; c.add_dx[1] = c.add_dx[0];
     }
+    if (o.solve_height && height_last) lp += -dlog_(2.0 * o.max_height_change);
     c.err_lp = (R)lp;
     for (int i = 0; i < GBP_TD_MAXC; ++i) {
         c.tsc[i] = R(1);
@@ -280,7 +302,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 template <typename R, typename T, int NC, int KIND>
 __device__ __noinline__ bool team_round(WarpState<R, T, NC, KIND>* w, const typename SysOf<T, KIND>::shared* S, const T* tab)
 {
-    if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+    if constexpr (!is_td(KIND) && sizeof(T) == 4) {
         GBP_SHARED(w);
         TeamShared* tm = w->team;
         GBP_SHARED(tm);
@@ -319,7 +341,7 @@ __device__ __noinline__ bool team_round(WarpState<R, T, NC, KIND>* w, const type
 template <typename R, typename T, int NC, int KIND>
 __device__ __forceinline__ void ch_round_pad(WarpState<R, T, NC, KIND>* w, const typename SysOf<T, KIND>::shared* S, const T* tab)
 {
-    if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+    if constexpr (!is_td(KIND) && sizeof(T) == 4) {
         if (w->team) {
             if (lane_id() == 0) w->req_active = 0;
             team_round<R, T, NC, KIND>(w, S, tab);
@@ -345,8 +367,11 @@ __device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const type
         if (J) w->ctr[CT_N_SENS]++;
     }
     __syncwarp();
-    if constexpr (KIND == KIND_TDEM) {
-        tdem_eval<T>(*S, tab, w->fx.lam, w->fx.wgt, kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
+    if constexpr (is_td(KIND)) {
+        // the geometry set of the height this evaluation is for (KIND_TDEM_Z: current or proposed)
+        int g = 0;
+        if constexpr (KIND == KIND_TDEM_Z) g = (alt == w->fx.alt[w->fx.cur]) ? w->fx.cur : (w->fx.cur ^ 1);
+        tdem_eval<T>(*S, tab, w->fx.lam[g], w->fx.wgt[g], kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
     } else {
         if constexpr (sizeof(T) == 4) {
             if (w->team) {   // the team evaluates it (and this warp its share of the team's other requests)
@@ -380,7 +405,7 @@ __device__ __noinline__ void ch_set_ivar(WarpState<R, T, NC, KIND>* w, const Con
         if (c < C) {
             R d = w->data[c];
             R r = e.rel[0], a = e.add[0];
-            if constexpr (KIND == KIND_TDEM) {
+            if constexpr (is_td(KIND)) {
                 if (K->csys[c]) {
                     r = e.rel[ns_of(KIND) - 1];
                     a = e.add[ns_of(KIND) - 1];
@@ -1073,7 +1098,7 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
             // predicted data (FdemDataPoint.py:535-545); TdemDataPoint.fm_dlogc stores only the Jacobian, its
             // predicted-data update is commented out (TdemDataPoint.py:1031-1055), so a time-domain death / move
             // forms the Newton gradient with the CURRENT model's predicted data.
-            if constexpr (KIND != KIND_TDEM) ph = pred_t;
+            if constexpr (!is_td(KIND)) ph = pred_t;
         } else {
             if (!SPEC) ch_round_pad(w, S, tab);   // team mode: the round of the forward this step does not need
             if (!j_valid) {  // bring the current model's (possibly stale, as in the reference) Jacobian back
@@ -1143,6 +1168,20 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                 err_t.rel[s] = (ln_t_err.rel[s] == ln_err.rel[s]) ? err.rel[s] : rt<R>::exp(ln_t_err.rel[s]);
                 err_t.add[s] = (ln_t_err.add[s] == ln_err.add[s]) ? err.add[s] : rt<R>::exp(ln_t_err.add[s]);
             }
+            // a time-domain datapoint perturbs its loops AFTER the errors (TdemDataPoint.perturb :681-683): the
+            // transmitter height, and with it the Hankel abscissae / geometry weights of the candidate's forward
+            if constexpr (KIND == KIND_TDEM_Z) {
+                const prop_t<R> pz = ch_propose_height<R>(rng, (R)alt, K->z_sd, (R)alt_ref - K->z_max, (R)alt_ref + K->z_max);
+                alt_t = (T)pz.x;
+                rng.block = pz.block;
+                if (alt_t != alt) {
+                    const int g = w->fx.cur ^ 1;
+                    if constexpr (sizeof(T) == 4) td_geometry_f32(*S, alt_t, w->fx.lam[g], w->fx.wgt[g]);
+                    else td_geometry<T>(*S, (double)alt_t, w->fx.lam[g], w->fx.wgt[g]);
+                    if (lane == 0) w->fx.alt[g] = alt_t;
+                    __syncwarp();
+                }
+            }
 
             const bool jump = (action == ACT_BIRTH || action == ACT_DEATH);
             // forward at the candidate; for birth/death the Jacobian at the candidate is needed as well
@@ -1179,8 +1218,12 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                 accepted = rt<R>::exp(log_alpha) > u;
                 if (accepted && !SPEC) {  // a speculative evaluation only reports the outcome
                     ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
-                    if constexpr (KIND == KIND_FDEM_Z) {
+                    if constexpr (has_z(KIND)) {
                         ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
+                        if constexpr (KIND == KIND_TDEM_Z) {
+                            if (alt_t != alt && lane == 0) w->fx.cur ^= 1;   // the proposed height's geometry becomes current
+                            __syncwarp();
+                        }
                         alt = alt_t;
                     }
                     dwell = 0;
@@ -1209,7 +1252,7 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                         w->sout.likelihood = tml.b;
                         w->sout.err = err_t;
                         w->sout.ln_err = ln_t_err;
-                        if constexpr (KIND == KIND_FDEM_Z) w->sout.alt = (R)alt_t;
+                        if constexpr (has_z(KIND)) w->sout.alt = (R)alt_t;
                     }
                     __syncwarp();
                 }
@@ -1506,6 +1549,12 @@ __device__ __noinline__ int spec_round_end(WarpState<R, T, NC, KIND>* w, TailCtx
                 ch_copy4(&w->val[so.vp], &hw->val[so.vp], (int)sizeof(ValBuf<R>));
                 ch_copy4(w->pred[pc], hw->pred[pc], NC * (int)sizeof(T));
                 if (so.changed) ch_copy16(w->J, hw->J, NC * KS * (int)sizeof(T));
+                if constexpr (KIND == KIND_TDEM_Z) {   // the geometry set of the proposed transmitter height
+                    const int g = w->fx.cur ^ 1;
+                    ch_copy4(w->fx.lam[g], hw->fx.lam[g], GBP_TD_MAXLAM * (int)sizeof(T));
+                    ch_copy4(w->fx.wgt[g], hw->fx.wgt[g], GBP_TD_MAXLAM * (int)sizeof(T));
+                    if (lane == 0) w->fx.alt[g] = hw->fx.alt[g];
+                }
                 if (lane == 0) {
                     rd->win = so;
                     rd->win_byte = rd->res[fs - t0];
@@ -1583,7 +1632,14 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         }
     }
     const int n_active = warp_sum_i(act);
-    if constexpr (KIND == KIND_TDEM) td_geometry<T>(Sdev, P.altitude[chain], w->fx.lam, w->fx.wgt);
+    if constexpr (is_td(KIND)) {
+        td_geometry<T>(*S, P.altitude[chain], w->fx.lam[0], w->fx.wgt[0]);
+        if (lane == 0) {
+            w->fx.cur = 0;
+            w->fx.alt[0] = alt;
+        }
+        __syncwarp();
+    }
     const R nahl = (R)n_active * K->half_log2pi;
     if (lane == 0) {
         const gbp_chain_buffers& o = P.out;
@@ -1594,7 +1650,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         w->outp[OP_ADD] = o.add_hist ? o.add_hist + (size_t)chain * K->n_sys * K->n_err : nullptr;
         w->outp[OP_MISFIT] = o.misfit_trace ? o.misfit_trace + (size_t)chain * N2 : nullptr;
         w->outp[OP_ACCEPT] = o.accept_trace ? o.accept_trace + (size_t)chain * N2 : nullptr;
-        w->outp[OP_HEIGHT] = (KIND == KIND_FDEM_Z && o.height_hist) ? o.height_hist + (size_t)chain * K->n_err : nullptr;
+        w->outp[OP_HEIGHT] = (has_z(KIND) && o.height_hist) ? o.height_hist + (size_t)chain * K->n_err : nullptr;
         for (int i = 0; i < CT_N; ++i) w->ctr[i] = 0;
     }
     __syncwarp();
@@ -1654,7 +1710,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         // Team mode: a chain that gets stuck (a long rejection run) while it is the last one of its team and finds fewer
         // than 4 idle warps in the CTA DISSOLVES the team - its mates leave the round protocol and become speculation
         // helpers, the chain goes on alone.
-        if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+        if constexpr (!is_td(KIND) && sizeof(T) == 4) {
             if (w->team != nullptr && tc.max_helpers > 0 && rej_run >= P.spec_min_rejections && w->team->alive <= 1 && *tc.n_idle < 4) {
                 if (lane == 0) {
                     w->team->alive = 0;
@@ -1706,8 +1762,13 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
             const SpecOut<R, NS> so = tc.rounds[tc.warp].win;
             const int byte = tc.rounds[tc.warp].win_byte;
             ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);  // the outgoing model's visits
-            if constexpr (KIND == KIND_FDEM_Z) {
+            if constexpr (has_z(KIND)) {
                 ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
+                if constexpr (KIND == KIND_TDEM_Z) {
+                    // (spec_round_end copied the proposed height's geometry set into this warp's spare set)
+                    if ((T)so.alt != alt && lane == 0) w->fx.cur ^= 1;
+                    __syncwarp();
+                }
                 alt = (T)so.alt;
             }
             dwell = 0;
@@ -1828,7 +1889,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         if (P.max_iterations > 0 && total >= P.max_iterations) go = false;
     }
     ch_flush(w, K, k, mcur, vcur, ln_err, sig_lo, dwell);
-    if constexpr (KIND == KIND_FDEM_Z) ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
+    if constexpr (has_z(KIND)) ch_flush_height(w, K, (R)(alt - alt_ref), dwell);
 
     ch_write_model(w, ml, k, mcur, vcur, P.out.cur_sigma ? P.out.cur_sigma + (size_t)chain * ml : nullptr,
                    P.out.cur_edges ? P.out.cur_edges + (size_t)chain * (ml + 1) : nullptr);
@@ -1875,9 +1936,9 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_N_MOVE] = (double)w->ctr[CT_ACT2];
         s[GBP_S_N_NONE] = (double)w->ctr[CT_ACT3];
         s[GBP_S_TOTAL_ITER] = (double)total;
-        s[GBP_S_CUR_HEIGHT] = (KIND == KIND_FDEM_Z) ? (double)alt : P.altitude[chain];
-        s[GBP_S_BEST_HEIGHT] = (KIND == KIND_FDEM_Z) ? (double)best_alt : P.altitude[chain];
-        s[GBP_S_HEIGHT_REF] = (KIND == KIND_FDEM_Z) ? (double)alt_ref : P.altitude[chain];
+        s[GBP_S_CUR_HEIGHT] = has_z(KIND) ? (double)alt : P.altitude[chain];
+        s[GBP_S_BEST_HEIGHT] = has_z(KIND) ? (double)best_alt : P.altitude[chain];
+        s[GBP_S_HEIGHT_REF] = has_z(KIND) ? (double)alt_ref : P.altitude[chain];
         if (spec_rounds > 0) {
             atomicAdd(&g_diag[8], (unsigned long long)w->ctr[CT_N_SPEC]);
             atomicAdd(&g_diag[9], (unsigned long long)spec_rounds);
@@ -1908,11 +1969,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     __shared__ TeamShared teams[WARPS];
     T* tab = reinterpret_cast<T*>(smem);
     uint32_t tab_bytes;
-    if constexpr (KIND == KIND_TDEM) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
+    if constexpr (is_td(KIND)) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
     else tab_bytes = fdem_table_bytes<T>(S);
     if (threadIdx.x == 0) {
-        make_consts<R>(P.opt, P.n_depth, P.C, consts);
-        if constexpr (KIND == KIND_TDEM) {
+        make_consts<R>(P.opt, P.n_depth, P.C, consts, is_td(KIND));
+        if constexpr (is_td(KIND)) {
             fill_td_shared<T>(S, sys_s);
             for (int i = 0; i < GBP_TD_MAXC; ++i) {
                 consts.tsc[i] = (R)S.tsc[i];
@@ -1938,7 +1999,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     // teams: T warps of the same SM sub-partition (warp ids congruent mod 4): team = (warp & 3) + 4 (warp / 4T),
     // member = (warp / 4) mod T; named barrier 1 + team
     int team_size = 1;
-    if constexpr (KIND != KIND_TDEM && sizeof(T) == 4) {
+    if constexpr (!is_td(KIND) && sizeof(T) == 4) {
         const bool pow2 = P.team_size >= 2 && P.team_size <= 16 && (P.team_size & (P.team_size - 1)) == 0;
         if (pow2 && WARPS % (4 * P.team_size) == 0 && WARPS / P.team_size < 16) team_size = P.team_size;
         if (pow2 && P.team_spread && WARPS % P.team_size == 0 && WARPS / P.team_size < 16) team_size = P.team_size;

@@ -43,18 +43,28 @@ struct TdDev {
 template <typename T> struct TdShared {
     int n_lam, C;
     T omu[TD_NF];
+    double xi[GBP_TD_MAXLAM], tw[GBP_TD_MAXLAM];   // td_geometry (per sounding; per proposal when the height is sampled)
+    double rx_r, rx_dz, loop_radius;
 };
 template <typename T> __device__ __forceinline__ void fill_td_shared(const TdDev& S, TdShared<T>& q)
 {
     q.n_lam = S.n_lam;
     q.C = S.C;
     for (int i = 0; i < TD_NF; ++i) q.omu[i] = (T)S.omu[i];
+    for (int i = 0; i < GBP_TD_MAXLAM; ++i) {
+        q.xi[i] = S.xi[i];
+        q.tw[i] = S.tw[i];
+    }
+    q.rx_r = S.rx_r;
+    q.rx_dz = S.rx_dz;
+    q.loop_radius = S.loop_radius;
 }
 
 // Per-sounding Hankel abscissae and geometry weights (one warp; lane j = abscissa j), fp64 then cast:
 //   lambda_j = (2/ZH) exp(xi_j),  w_j = tw_j lambda_j^3 exp(-lambda_j ZH) J0(lambda_j r) 2 J1(lambda_j a)/(lambda_j a)
-template <typename T> __device__ __noinline__ void td_geometry(const TdDev& S, double altitude, T* lam, T* wgt)
+template <typename T> __device__ __noinline__ void td_geometry(const TdShared<T>& S, double altitude, T* lam, T* wgt)
 {
+    __builtin_assume(__isShared(&S));
     const int lane = threadIdx.x & 31;
     if (lane < S.n_lam) {
         const double ZH = 2.0 * altitude + S.rx_dz;
@@ -196,6 +206,61 @@ __device__ __noinline__ void tdem_eval(const TdShared<T>& Q, const T* __restrict
     __syncwarp();
 }
 
+// Compact single-precision Bessel functions J0, J1 (rational / asymptotic forms of Abramowitz & Stegun 9.4, the
+// classic bessj0 / bessj1 coefficients; ~1e-7 absolute in fp32).  Small on purpose: the per-step geometry update below
+// must not push the sampler's hot code out of the instruction cache (libdevice's j0f / j1f did: +16 % per step).
+__device__ __forceinline__ float bessel_j01_f32(const float x, const bool one)
+{
+    const float ax = fabsf(x);
+    if (ax < 8.f) {
+        const float y = x * x;
+        float n, d;
+        if (!one) {
+            n = 57568490574.0f + y * (-13362590354.0f + y * (651619640.7f + y * (-11214424.18f + y * (77392.33017f + y * (-184.9052456f)))));
+            d = 57568490411.0f + y * (1029532985.0f + y * (9494680.718f + y * (59272.64853f + y * (267.8532712f + y))));
+            return n / d;
+        }
+        n = x * (72362614232.0f + y * (-7895059235.0f + y * (242396853.1f + y * (-2972611.439f + y * (15704.48260f + y * (-30.16036606f))))));
+        d = 144725228442.0f + y * (2300535178.0f + y * (18583304.74f + y * (99447.43394f + y * (376.9991397f + y))));
+        return n / d;
+    }
+    const float z = 8.f / ax, y = z * z;
+    const float xx = ax - (one ? 2.356194491f : 0.785398164f);
+    float p, q;
+    if (!one) {
+        p = 1.f + y * (-0.1098628627e-2f + y * (0.2734510407e-4f + y * (-0.2073370639e-5f + y * 0.2093887211e-6f)));
+        q = -0.1562499995e-1f + y * (0.1430488765e-3f + y * (-0.6911147651e-5f + y * (0.7621095161e-6f - y * 0.934935152e-7f)));
+    } else {
+        p = 1.f + y * (0.183105e-2f + y * (-0.3516396496e-4f + y * (0.2457520174e-5f + y * (-0.240337019e-6f))));
+        q = 0.04687499995f + y * (-0.2002690873e-3f + y * (0.8449199096e-5f + y * (-0.88228987e-6f + y * 0.105787412e-6f)));
+    }
+    float sn, cs;
+    rt<float>::sincos(xx, &sn, &cs);
+    const float r = rt<float>::sqrt(0.636619772f / ax) * (cs * p - z * sn * q);
+    return (one && x < 0.f) ? -r : r;
+}
+
+// td_geometry in single precision (fp32 sampler with a sampled transmitter height: once per accept_reject step;
+// weights to ~1e-6 relative, the forward's fp32 tolerance is 2e-4).  lambda ZH = 2 exp(xi) does not depend on the height.
+__device__ __noinline__ void td_geometry_f32(const TdShared<float>& S, float altitude, float* lam, float* wgt)
+{
+    __builtin_assume(__isShared(&S));
+    const int lane = threadIdx.x & 31;
+    if (lane < S.n_lam) {
+        const float ZH = 2.f * altitude + (float)S.rx_dz;
+        const float lz = 2.f * rt<float>::exp((float)S.xi[lane]);   // lambda * ZH
+        const float l = lz / ZH;
+        float w = (float)S.tw[lane] * l * l * l * rt<float>::exp(-lz) * bessel_j01_f32(l * (float)S.rx_r, false);
+        if (S.loop_radius > 0.0) {
+            const float x = l * (float)S.loop_radius;
+            w *= 2.f * bessel_j01_f32(x, true) / x;
+        }
+        lam[lane] = l;
+        wgt[lane] = w;
+    }
+    __syncwarp();
+}
+
 // standalone operators: one warp per sounding, grid-stride over soundings
 template <typename T, bool SENS>
 __global__ void __launch_bounds__(256) tdem_kernel(const __grid_constant__ TdDev S, const T* __restrict__ g_Mt, int B,
@@ -230,7 +295,7 @@ __global__ void __launch_bounds__(256) tdem_kernel(const __grid_constant__ TdDev
             msig[lane] = (T)sigma[(size_t)b * l_stride + lane];
             mthk[lane] = (T)thickness[(size_t)b * l_stride + lane];
         }
-        td_geometry<T>(S, altitude[b], lam, wgt);
+        td_geometry<T>(sys_s, altitude[b], lam, wgt);
         tdem_eval<T>(sys_s, Mt, lam, wgt, L, msig, mthk, sbuf, pred, SENS ? J : nullptr, SENS);
 #pragma unroll 1
         for (int c = lane; c < C; c += 32) out[(size_t)b * C + c] = (double)pred[c] * out_scale;

@@ -136,7 +136,11 @@ _REFERENCE_KEYS = dict(
     relative_error_proposal_variance="rel_prop_var", initial_additive_error="add_init",
     minimum_additive_error="add_min", maximum_additive_error="add_max",
     additive_error_proposal_variance="add_prop_var",
-    solve_z="solve_height", maximum_z_change="max_height_change", z_proposal_variance="height_prop_var")
+    solve_z="solve_height", maximum_z_change="max_height_change", z_proposal_variance="height_prop_var",
+    # time-domain datapoints: the sampled height is the transmitter loop's (EmLoop.set_priors via Loop_pair, option keys
+    # prefixed "transmitter_"; TdemDataPoint.perturb :681-683)
+    solve_transmitter_z="solve_height", maximum_transmitter_z_change="max_height_change",
+    transmitter_z_proposal_variance="height_prop_var")
 
 
 def make_options(**kw):
@@ -165,6 +169,8 @@ def make_options(**kw):
         else:
             v = float(np.asarray(v).reshape(-1)[0])
         setattr(o, k, v)
+    # which unknown the height options were spelled for (Inference1D checks it against the datapoint type)
+    o.height_key = "solve_transmitter_z" if kw.get("solve_transmitter_z") else ("solve_z" if kw.get("solve_z") else None)
     return o
 
 
@@ -175,6 +181,7 @@ _DEAD_REFERENCE_KEYS = ("solve_height", "maximum_height_change", "height_proposa
 # unknowns of the reference that are not built here: asking for one is an error, not a silent no-op
 _UNBUILT_PREFIXES = ("solve_transmitter_", "solve_receiver_")
 _UNBUILT_KEYS = ("solve_x", "solve_y", "solve_calibration")
+_BUILT_KEYS = ("solve_transmitter_z",)   # time-domain datapoints: the transmitter height (KIND_TDEM_Z)
 
 
 def options_from_reference(**kw):
@@ -190,7 +197,7 @@ def options_from_reference(**kw):
     for k in _DEAD_REFERENCE_KEYS:
         kw.pop(k, None)
     for k, v in kw.items():
-        if (k in _UNBUILT_KEYS or k.startswith(_UNBUILT_PREFIXES)) and np.any(v):
+        if (k in _UNBUILT_KEYS or k.startswith(_UNBUILT_PREFIXES)) and k not in _BUILT_KEYS and np.any(v):
             raise NotImplementedError("%s: this unknown of the reference is not built in geobipy_b200 (DESIGN.md section 7)" % k)
     return make_options(**kw)
 
@@ -359,6 +366,13 @@ def last_kernel_ms():
     ms = ctypes.c_float(0.0)
     _lib.check(_lib.load().gbp_last_kernel_ms(ctypes.byref(ms)))
     return float(ms.value)
+
+
+def kernel_ms_stats(last_n):
+    """(mean duration [ms], number averaged) of the last `last_n` (<= 32) kernels launched on the current device."""
+    ms, n = ctypes.c_float(0.0), ctypes.c_int(0)
+    _lib.check(_lib.load().gbp_kernel_ms_stats(int(last_n), ctypes.byref(ms), ctypes.byref(n)))
+    return float(ms.value), int(n.value)
 
 
 def launch_count():

@@ -96,7 +96,9 @@ typedef struct {
     double add_init2, add_min2, add_max2, add_prop_var2;
     /* Sensor height as an unknown (the options file's solve_z / maximum_z_change / z_proposal_variance:
      * Point.set_priors pointcloud/Point.py:959-961, set_proposals :977-979, perturb :614-622).  Frequency-domain
-     * datapoints with <= 6 frequencies; the time-domain entry points reject it. */
+     * datapoints with <= 6 frequencies.  For the time-domain entry points it is the TRANSMITTER height
+     * (solve_transmitter_z / maximum_transmitter_z_change / transmitter_z_proposal_variance: TdemDataPoint.perturb
+     * :681-683, prior after the error priors :950-951; the receiver offset stays fixed). */
     int32_t solve_height;
     int32_t pad_h_;
     double max_height_change;           /* prior Uniform[z0 - max_height_change, z0 + max_height_change] */

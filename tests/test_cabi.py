@@ -61,6 +61,34 @@ def test_no_cpu_fallback_without_gpu(built_lib):
         ops.rjmcmc_run(s, ops.make_options(), np.ones((1, 12)), np.array([30.0]))
 
 
+def test_time_domain_sampler_rejects_more_channels_than_it_holds(built_lib):
+    """the sampler kernels hold GBP_TD_SAMPLER_MAXC = 48 channels per chain in shared memory while the
+    forward operators take up to GBP_TD_MAXC = 64 (2 x 32 windows).  A 2 x 26-window datapoint type must be refused
+    loudly - before any device work, so this runs without a GPU - instead of writing past the per-chain arrays."""
+    from geobipy_b200 import _lib, ops
+    defs = ops.skytem_definitions()
+    hm = dict(defs[0])
+    assert len(hm["window_start"]) == 26
+    sv = ops.make_tdem_survey_struct([hm, dict(hm)])
+    assert ops.n_channels(sv) == 52 and 48 == _lib.TD_SAMPLER_MAXC < ops.n_channels(sv) <= _lib.TD_MAXC
+    opt = ops.make_options(n_markov_chains=100, **ops.SKYTEM_OPTIONS)
+    cb = _lib.ChainBuffersC()
+    cb.scalars = 1   # non-NULL; never dereferenced: the channel check comes first
+    for fn in (built_lib.gbp_tdem_rjmcmc_run, ):
+        rc = fn(ctypes.addressof(sv), ctypes.addressof(opt), 1, None, None, 0, 0, 0, ctypes.addressof(cb), 32, None)
+        assert rc != 0 and b"48 data channels" in built_lib.gbp_last_error()
+    data, alt = np.full((1, 52), 1e-12), np.array([30.0])
+    h = _lib.ChainBuffersC()
+    sc = np.zeros((1, _lib.NSCALARS))
+    h.scalars = sc.ctypes.data
+    if built_lib.gbp_device_count() > 0:
+        rc = built_lib.gbp_tdem_rjmcmc_run_host(ctypes.addressof(sv), ctypes.addressof(opt), 1, data.ctypes.data, alt.ctypes.data,
+                                                0, 0, 0, ctypes.addressof(h), 32, 0)
+        assert rc != 0 and b"48 data channels" in built_lib.gbp_last_error()
+    # the SkyTEM dual-moment type (26 + 19 = 45 channels) is inside the limit
+    assert ops.n_channels(ops.skytem_survey_struct()) == 45
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "geobipy_b200")
     for dirpath, _, files in os.walk(pkg):
@@ -119,7 +147,7 @@ def test_solve_z_option_keys_and_buffers(built_lib):
     assert o.solve_height == 1 and o.max_height_change == 2.5 and o.height_prop_var == 0.04
     shp = ops.chain_buffer_shapes(o, 5)
     assert shp["height_hist"] == ((5, 99), np.int32)
-    assert _lib.S_CUR_HEIGHT == 29 and _lib.S_BEST_HEIGHT == 30 and _lib.NSCALARS == 32
+    assert _lib.S_CUR_HEIGHT == 29 and _lib.S_BEST_HEIGHT == 30 and _lib.S_HEIGHT_REF == 31 and _lib.NSCALARS == 32
     # the struct mirrors stay in step with the header (field order and size)
     import ctypes
     assert [n for n, _ in _lib.OptionsC._fields_][-4:] == ["solve_height", "pad_h_", "max_height_change", "height_prop_var"]
@@ -143,12 +171,21 @@ def test_options_from_a_reference_options_file(built_lib):
     assert o.solve_height == 0
     o = ops.options_from_reference(**dict(shipped, solve_z=True, maximum_z_change=0.5, z_proposal_variance=0.02))
     assert o.solve_height == 1 and o.max_height_change == 0.5 and o.height_prop_var == 0.02
-    for key in ("solve_transmitter_z", "solve_receiver_pitch", "solve_calibration", "solve_x"):
+    for key in ("solve_transmitter_pitch", "solve_receiver_pitch", "solve_receiver_z", "solve_calibration", "solve_x"):
         with pytest.raises(NotImplementedError, match=key):
             ops.options_from_reference(**dict(shipped, **{key: True}))
+    # the transmitter height of a time-domain datapoint IS built (KIND_TDEM_Z): same gbp_options fields as solve_z
+    o = ops.options_from_reference(**dict(shipped, solve_transmitter_z=True, maximum_transmitter_z_change=2.0,
+                                          transmitter_z_proposal_variance=0.04))
+    assert o.solve_height == 1 and o.max_height_change == 2.0 and o.height_prop_var == 0.04 and o.height_key == "solve_transmitter_z"
     # the object-level mirror goes through the same filter
     with pytest.warns(UserWarning, match="solve_height"):
         inf = api.Inference1D(prng=np.random.default_rng(0), **dict(shipped, solve_height=True))
     assert inf.options.solve_height == 0
     with pytest.raises(NotImplementedError):
-        api.Inference1D(prng=np.random.default_rng(0), **dict(shipped, solve_transmitter_z=True))
+        api.Inference1D(prng=np.random.default_rng(0), **dict(shipped, solve_receiver_z=True))
+    # ... and the transmitter height is only accepted for a time-domain datapoint
+    inf = api.Inference1D(prng=np.random.default_rng(0), **dict(shipped, solve_transmitter_z=True))
+    with pytest.raises(AssertionError):
+        inf.initialize(api.FdemDataPoint(z=30.0, system=api.FdemSystem([380.0], api.CircularLoop(["z"], [1.0], [0.0], [0.0], [0.0]),
+                                                                       api.CircularLoop(["z"], [1.0], [7.93], [0.0], [0.0]))))

@@ -377,7 +377,7 @@ def test_full_size_properties(gpu, systems):
     assert nd == 440
 
 
-@pytest.mark.parametrize("kind", ["fdem", "tdem", "fdem_solve_z"])
+@pytest.mark.parametrize("kind", ["fdem", "tdem", "fdem_solve_z", "tdem_solve_z"])
 def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, monkeypatch):
     """Idle warps evaluate future iterations of running chains speculatively (gbp_chain.cuh, "speculative evaluation").
     Per-iteration random sub-streams make that exact: every output of a batch that leaves most warps idle (so that
@@ -394,7 +394,8 @@ def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, mon
         alt = alt + 0.4
     else:
         from geobipy_b200.synthetic import synthetic_batch, skytem_noise_std
-        system, opt = gpu.skytem_survey_struct(), gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500, **gpu.SKYTEM_OPTIONS)
+        hk = dict(solve_height=1, max_height_change=1.0, height_prop_var=0.01) if kind == "tdem_solve_z" else {}
+        system, opt = gpu.skytem_survey_struct(), gpu.make_options(n_markov_chains=3000, update_plot_every=500, burn_in_min_iter=500, **gpu.SKYTEM_OPTIONS, **hk)
         tsys = oracle.make_tdem_system()
         b = synthetic_batch(0, 40, max_depth=400.0, n_channels=45)
         data = np.zeros((40, 45))
@@ -402,7 +403,7 @@ def test_speculative_evaluation_is_bit_identical(gpu, systems, oracle, kind, mon
             L = int(b["nlayers"][i])
             clean = oracle.tdem_forward(tsys, b["height"][i], b["sigma"][i, :L], b["thickness"][i, :L])
             data[i] = clean + b["noise"][i] * skytem_noise_std(clean, np.array(tsys.t_centre[:45]), (26, 19))
-        alt = b["height"]
+        alt = b["height"] + (0.4 if kind == "tdem_solve_z" else 0.0)   # the proposed height's geometry set comes back from the speculating warp
     out, nspec = {}, {}
     for helpers, minrej in (("0", "24"), ("12", "4"), ("27", "0")):
         monkeypatch.setenv("GBP_SPEC_HELPERS", helpers)
