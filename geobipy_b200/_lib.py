@@ -92,6 +92,7 @@ EXPORTS = (
     "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host", "gbp_release_host_buffers", "gbp_summarise_hitmap",
+    "gbp_summarise_posterior", "gbp_opacity_doi",
     "gbp_tdem_n_channels", "gbp_tdem_window_operator", "gbp_tdem_flops_per_forward",
     "gbp_tdem_forward", "gbp_tdem_sensitivity", "gbp_tdem_forward_host", "gbp_tdem_sensitivity_host",
     "gbp_tdem_rjmcmc_run", "gbp_tdem_rjmcmc_run_host",
@@ -147,6 +148,10 @@ def load():
     lib.gbp_tdem_mufu_per_forward.argtypes = [vp, i32]
     lib.gbp_summarise_hitmap.restype = i32
     lib.gbp_summarise_hitmap.argtypes = [vp, i32, i32, i32, vp, dbl, vp, i32, vp, vp, vp]
+    lib.gbp_summarise_posterior.restype = i32
+    lib.gbp_summarise_posterior.argtypes = [vp, i32, i32, i32, vp, dbl, vp, i32, dbl, vp, vp, vp, vp, vp]
+    lib.gbp_opacity_doi.restype = i32
+    lib.gbp_opacity_doi.argtypes = [vp, i32, i32, vp, i32, dbl, dbl, vp, vp, vp, vp, vp]
     lib.gbp_release_host_buffers.restype = i32
     lib.gbp_debug_finish_times.restype = i32
     lib.gbp_debug_finish_times.argtypes = [vp, i32]

@@ -172,8 +172,11 @@ class Histogram:
         c = self._xc()
         h = np.atleast_2d(self.counts.T).T if self.counts.ndim == 1 else self.counts
         cs = np.cumsum(h, axis=0).astype(np.float64)
-        tot = np.maximum(cs[-1], 1.0)
-        idx = np.minimum((cs < (percent / 100.0) * tot).sum(axis=0), c.size - 1)
+        tot = cs[-1]
+        # first bin whose cumulative fraction reaches percent * 0.01 - both in fp64, as the reference computes them
+        # (95.0 * 0.01 > 0.95: a fraction of exactly 0.95 goes to the next bin); an empty column -> the last bin
+        frac = np.divide(cs, tot, out=np.zeros_like(cs), where=tot > 0.0)
+        idx = np.minimum((frac < percent * 0.01).sum(axis=0), c.size - 1)
         out = c[idx]
         out = np.exp(out) if self.log_x else out
         return out if self.counts.ndim > 1 else out.item()

@@ -378,12 +378,27 @@ constexpr int SUMM_MAXP = 8;
 struct SummParams {
     int B, n_sig, n_depth, n_pct;
     double dx;
-    double pct[SUMM_MAXP];
+    double pct[SUMM_MAXP];      // percentiles; when a credible range is asked for, the last two are its bounds
+    int want_range;
 };
+// smallest integer count c with (double)c / (double)tot >= p, p = percent * 0.01 in fp64: exactly the reference's
+// rule (Mesh._percentile: searchsorted(cumsum / total, percent * 0.01), Mesh.py:196-208) including its round-off -
+// 95.0 * 0.01 = 0.9500000000000001 > 0.95, so a cumulative fraction of exactly 0.95 goes to the NEXT bin
+__device__ __forceinline__ long long percentile_threshold(double percent, long long tot)
+{
+    if (tot <= 0) return 1;   // empty column: every bin is "below" -> the last bin, as the reference's clip
+    const double p = percent * 0.01, t = (double)tot;
+    long long c = (long long)ceil(p * t);
+    if (c < 0) c = 0;
+    while (c > 0 && (double)(c - 1) / t >= p) --c;
+    while ((double)c / t < p) ++c;
+    return c;
+}
 template <int NP>
 __global__ void __launch_bounds__(256) summarise_kernel(const int32_t* __restrict__ hitmap, const double* __restrict__ sig_lo,
                                                          const __grid_constant__ SummParams P, double* __restrict__ mean,
-                                                         double* __restrict__ pct)
+                                                         double* __restrict__ pct, double* __restrict__ mode,
+                                                         int32_t* __restrict__ range_bins)
 {
     const long long n = (long long)P.B * P.n_depth;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -394,29 +409,96 @@ __global__ void __launch_bounds__(256) summarise_kernel(const int32_t* __restric
 #pragma unroll 10
         for (int s = 0; s < P.n_sig; ++s) tot += col[(size_t)s * P.n_depth];  // independent loads: 10 in flight per thread
         const double totd = tot > 0 ? (double)tot : 1.0, lo = sig_lo[b];
-        long long thr[NP];  // cs < target  <=>  cs < ceil(target) for integer cs
+        long long thr[NP];
         int idx[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            thr[q] = (long long)ceil((P.pct[q] / 100.0) * totd);
+            thr[q] = percentile_threshold(P.pct[q], tot);
             idx[q] = 0;
         }
         long long cs = 0, wsum = 0;
+        int vmax = -1, imax = 0;   // mode: the first fullest bin (Mesh._mode: argmax, Mesh.py:138-165)
 #pragma unroll 10
         for (int s = 0; s < P.n_sig; ++s) {
-            const long long v = col[(size_t)s * P.n_depth];
+            const int v32 = col[(size_t)s * P.n_depth];
+            const long long v = v32;
             cs += v;
             wsum += v * s;
+            if (v32 > vmax) {
+                vmax = v32;
+                imax = s;
+            }
 #pragma unroll
             for (int q = 0; q < NP; ++q) idx[q] += (cs < thr[q]) ? 1 : 0;
         }
         const double acc = (double)tot * (lo + 0.5 * P.dx) + (double)wsum * P.dx;
         mean[i] = acc / totd;
+        const int n_out = P.want_range ? NP - 2 : NP;
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const int k = idx[q] < P.n_sig - 1 ? idx[q] : P.n_sig - 1;
-            pct[(size_t)q * n + i] = lo + ((double)k + 0.5) * P.dx;
+            idx[q] = k;
+            if (q < n_out) pct[(size_t)q * n + i] = lo + ((double)k + 0.5) * P.dx;
         }
+        if (mode) mode[i] = lo + ((double)imax + 0.5) * P.dx;
+        // credible range in BINS (Mesh._credible_range, Mesh.py:58-78: |log10 hi - log10 lo| = bins * dx / ln 10)
+        if (P.want_range && range_bins) range_bins[i] = idx[NP - 1] - idx[NP - 2];
+    }
+}
+
+// Opacity, depth of investigation and opacity level from credible ranges (in bins) [B][n_depth]: one warp per sounding.
+// Histogram.transparency (Histogram.py:509-541): (range - min) / (max - min) over the group the sounding belongs to - the
+// sounding itself (Histogram.opacity of one hitmap) or its whole flight line (Inference2D.compute_opacity :1011-1023);
+// compute_doi (:493-532): from the bottom up, the first cell whose opacity reaches doi_p, never above cell 1's
+// predecessor test (j >= 1); Histogram.opacity_level (:356-367): from the bottom up while transparency > level_p.
+__global__ void __launch_bounds__(256) range_minmax_kernel(const int32_t* __restrict__ range_bins, const int32_t* __restrict__ group,
+                                                            int B, int n_depth, int32_t* __restrict__ gmin, int32_t* __restrict__ gmax)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    int mn = 0x7fffffff, mx = -0x7fffffff;
+    for (int j = lane; j < n_depth; j += 32) {
+        const int v = range_bins[(size_t)warp * n_depth + j];
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+    }
+    if (lane == 0) {
+        const int g = group ? group[warp] : warp;
+        atomicMin(&gmin[g], mn);
+        atomicMax(&gmax[g], mx);
+    }
+}
+__global__ void __launch_bounds__(256) opacity_doi_kernel(const int32_t* __restrict__ range_bins, const int32_t* __restrict__ group,
+                                                           int B, int n_depth, const int32_t* __restrict__ gmin,
+                                                           const int32_t* __restrict__ gmax, double doi_p, double level_p,
+                                                           double* __restrict__ opacity, int32_t* __restrict__ doi_cell,
+                                                           int32_t* __restrict__ level_cell)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int g = group ? group[warp] : warp;
+    const int mn = gmin[g], mx = gmax[g];
+    const double span = (double)(mx - mn);
+    int jd = 0, jl = -1;
+    for (int j = lane; j < n_depth; j += 32) {
+        const double r = (double)(range_bins[(size_t)warp * n_depth + j] - mn);
+        const double t = span > 0.0 ? r / span : r;   // transparency
+        const double op = 1.0 - t;
+        if (opacity) opacity[(size_t)warp * n_depth + j] = op;
+        if (op >= doi_p && j >= 1) jd = max(jd, j);   // loop of compute_doi: stops at the deepest cell with opacity >= p, or at 0
+        if (!(t > level_p)) jl = max(jl, j);           // opacity_level: stops at the deepest cell with transparency <= p, or at -1
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        jd = max(jd, __shfl_xor_sync(FULL, jd, o));
+        jl = max(jl, __shfl_xor_sync(FULL, jl, o));
+    }
+    if (lane == 0) {
+        if (doi_cell) doi_cell[warp] = jd;
+        if (level_cell) level_cell[warp] = jl < 0 ? n_depth - 1 : jl;   // index -1 = the last cell, as in the reference
     }
 }
 
@@ -735,19 +817,29 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                             });
 }
 
-int gbp_summarise_hitmap(const int32_t* d_hitmap, int B, int n_sig, int n_depth, const double* d_sig_lo, double dx,
-                         const double* percentiles, int n_pct, double* d_mean, double* d_pct, void* stream)
+static int summarise_impl(const int32_t* d_hitmap, int B, int n_sig, int n_depth, const double* d_sig_lo, double dx,
+                          const double* percentiles, int n_pct, double credible_percent, double* d_mean, double* d_pct,
+                          double* d_mode, int32_t* d_range_bins, void* stream)
 {
     if (B <= 0) return 0;
-    if (n_pct < 1 || n_pct > SUMM_MAXP) return fail("1 to 8 percentiles");
+    const int want_range = d_range_bins != nullptr;
+    const int np_total = n_pct + (want_range ? 2 : 0);
+    if (n_pct < (want_range ? 0 : 1) || np_total < 1 || np_total > SUMM_MAXP) return fail("1 to 8 percentiles (a credible range takes two of them)");
     if (n_sig < 1 || n_depth < 1) return fail("invalid hitmap shape");
+    if (want_range && !(credible_percent > 0.0 && credible_percent < 100.0)) return fail("credible_percent must be in (0, 100)");
     SummParams P;
     P.B = B;
     P.n_sig = n_sig;
     P.n_depth = n_depth;
     P.n_pct = n_pct;
     P.dx = dx;
+    P.want_range = want_range;
     for (int q = 0; q < SUMM_MAXP; ++q) P.pct[q] = q < n_pct ? percentiles[q] : 0.0;
+    if (want_range) {   // Mesh._credible_range :74-75: percent = 0.5 * min(percent, 100 - percent); bounds percent, 100 - percent
+        const double h = 0.5 * (credible_percent < 100.0 - credible_percent ? credible_percent : 100.0 - credible_percent);
+        P.pct[n_pct] = h;
+        P.pct[n_pct + 1] = 100.0 - h;
+    }
     const long long n = (long long)B * n_depth;
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
@@ -757,14 +849,54 @@ int gbp_summarise_hitmap(const int32_t* d_hitmap, int B, int n_sig, int n_depth,
     if (current_device(&dev)) return 1;
     std::lock_guard<std::mutex> lk(g_dev[dev].mu);
     if (time_begin(dev, st)) return 1;
-    switch (n_pct) {
-#define GBP_SUMM_CASE(NP) case NP: summarise_kernel<NP><<<(int)blocks, 256, 0, st>>>(d_hitmap, d_sig_lo, P, d_mean, d_pct); break;
+    switch (np_total) {
+#define GBP_SUMM_CASE(NP) case NP: summarise_kernel<NP><<<(int)blocks, 256, 0, st>>>(d_hitmap, d_sig_lo, P, d_mean, d_pct, d_mode, d_range_bins); break;
         GBP_SUMM_CASE(1) GBP_SUMM_CASE(2) GBP_SUMM_CASE(3) GBP_SUMM_CASE(4) GBP_SUMM_CASE(5) GBP_SUMM_CASE(6) GBP_SUMM_CASE(7)
         GBP_SUMM_CASE(8)
 #undef GBP_SUMM_CASE
-        default: summarise_kernel<1><<<(int)blocks, 256, 0, st>>>(d_hitmap, d_sig_lo, P, d_mean, nullptr); break;
+        default: break;
     }
     g_launches++;
+    CK(cudaGetLastError());
+    return time_end(dev, st);
+}
+
+int gbp_summarise_hitmap(const int32_t* d_hitmap, int B, int n_sig, int n_depth, const double* d_sig_lo, double dx,
+                         const double* percentiles, int n_pct, double* d_mean, double* d_pct, void* stream)
+{
+    return summarise_impl(d_hitmap, B, n_sig, n_depth, d_sig_lo, dx, percentiles, n_pct, 0.0, d_mean, d_pct, nullptr, nullptr, stream);
+}
+
+int gbp_summarise_posterior(const int32_t* d_hitmap, int B, int n_sig, int n_depth, const double* d_sig_lo, double dx,
+                            const double* percentiles, int n_pct, double credible_percent, double* d_mean, double* d_pct,
+                            double* d_mode, int32_t* d_range_bins, void* stream)
+{
+    return summarise_impl(d_hitmap, B, n_sig, n_depth, d_sig_lo, dx, percentiles, n_pct, credible_percent, d_mean, d_pct, d_mode,
+                          d_range_bins, stream);
+}
+
+int gbp_opacity_doi(const int32_t* d_range_bins, int B, int n_depth, const int32_t* d_group, int n_groups, double doi_percent,
+                    double level_percent, int32_t* d_group_minmax, double* d_opacity, int32_t* d_doi_cell, int32_t* d_level_cell,
+                    void* stream)
+{
+    if (B <= 0) return 0;
+    if (n_depth < 1) return fail("invalid shape");
+    if (!d_group_minmax) return fail("gbp_opacity_doi: d_group_minmax (2 x n_groups int32 of scratch) is required");
+    const int ng = d_group ? n_groups : B;
+    if (ng < 1) return fail("n_groups must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev;
+    if (current_device(&dev)) return 1;
+    std::lock_guard<std::mutex> lk(g_dev[dev].mu);
+    // min <- 0x7f7f7f7f, max <- 0x80808080 (byte fills): above / below every possible bin difference
+    CK(cudaMemsetAsync(d_group_minmax, 0x7f, (size_t)ng * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(d_group_minmax + ng, 0x80, (size_t)ng * sizeof(int32_t), st));
+    const int blocks = (B * 32 + 255) / 256;
+    if (time_begin(dev, st)) return 1;
+    range_minmax_kernel<<<blocks, 256, 0, st>>>(d_range_bins, d_group, B, n_depth, d_group_minmax, d_group_minmax + ng);
+    opacity_doi_kernel<<<blocks, 256, 0, st>>>(d_range_bins, d_group, B, n_depth, d_group_minmax, d_group_minmax + ng,
+                                               0.01 * doi_percent, 0.01 * level_percent, d_opacity, d_doi_cell, d_level_cell);
+    g_launches += 2;
     CK(cudaGetLastError());
     return time_end(dev, st);
 }

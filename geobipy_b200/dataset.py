@@ -121,13 +121,15 @@ class FdemData:
 def _percentile_bins(hitmap, percent):
     """First bin whose cumulative count reaches percent of the column total (Mesh._percentile)."""
     cs = np.cumsum(hitmap, axis=-2, dtype=np.float64)
-    tot = np.maximum(cs[..., -1:, :], 1.0)
-    return np.minimum((cs < (percent / 100.0) * tot).sum(axis=-2), hitmap.shape[-2] - 1)
+    tot = cs[..., -1:, :]
+    frac = np.divide(cs, tot, out=np.zeros_like(cs), where=tot > 0.0)   # the reference's rule, ties included (Mesh.py:196-208)
+    return np.minimum((frac < percent * 0.01).sum(axis=-2), hitmap.shape[-2] - 1)
 
 
-def summarise(result, opt):
-    """Posterior summaries per sounding from the raw arrays of `ops.rjmcmc_run`:
-    conductivity mean / p5 / p50 / p95 per depth cell [B, n_depth] and interface probability [B, n_depth]."""
+def summarise(result, opt, line_id=None, doi_percent=67.0, credible_percent=90.0):
+    """Host (numpy) statement of `summarise_device` - the checker of the device kernels in the tests, and what turns
+    host-resident result arrays into summaries: conductivity mean / p5 / p50 / p95 / mode per depth cell [B, n_depth],
+    credible range (decades), opacity and depth of investigation per flight line, interface probability."""
     hm = np.asarray(result["hitmap"])
     hs = np.asarray(result["scalars"])[:, _lib.S_HALFSPACE]
     s = np.log(1.0 + opt.factor) * opt.sigma_bins_nstd
@@ -139,6 +141,16 @@ def summarise(result, opt):
     for p in (5.0, 50.0, 95.0):
         idx = _percentile_bins(hm, p)
         out["p%g" % p] = np.exp(np.take_along_axis(centres, idx, axis=1))
+    out["mode"] = np.exp(np.take_along_axis(centres, np.argmax(hm, axis=1), axis=1))
+    hp = 0.5 * min(credible_percent, 100.0 - credible_percent)
+    dxl = (edges[:, 1] - edges[:, 0])[:, None]
+    out["credible_range"] = (_percentile_bins(hm, 100.0 - hp) - _percentile_bins(hm, hp)) * dxl / np.log(10.0)
+    depth_edges = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
+    out["opacity"], out["doi"] = np.zeros_like(out["credible_range"]), np.zeros(hm.shape[0])
+    lines = np.zeros(hm.shape[0]) if line_id is None else np.asarray(line_id)
+    for ln in np.unique(lines):
+        m = lines == ln
+        out["opacity"][m], out["doi"][m] = opacity_and_doi_from_range(out["credible_range"][m], depth_edges, doi_percent)
     eh = np.asarray(result["edges_hist"]).astype(np.float64)
     out["interface_probability"] = eh / np.maximum(eh.sum(axis=1, keepdims=True), 1.0)
     out["depth_edges"] = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
@@ -150,6 +162,40 @@ def summarise(result, opt):
         c = -opt.max_height_change + (np.arange(hh.shape[1]) + 0.5) * (2.0 * opt.max_height_change / hh.shape[1])
         out["height_mean"] = (np.asarray(result["scalars"])[:, _lib.S_HEIGHT_REF]
                               + (hh * c[None, :]).sum(axis=1) / np.maximum(hh.sum(axis=1), 1.0))
+    return out
+
+
+def summarise_device(result, opt, line_id=None, doi_percent=67.0, credible_percent=90.0):
+    """The posterior summaries of `summarise` plus mode, credible range, opacity and depth of investigation, computed ON
+    THE DEVICE from the torch CUDA result arrays of `ops.rjmcmc_run` (hand-written kernels gbp_summarise_posterior /
+    gbp_opacity_doi).  line_id [B] (integers): the flight line of every sounding - opacity is the
+    credible range normalised over the line (Inference2D.compute_opacity, Inference2D.py:1011-1023), the depth of
+    investigation its compute_doi (:493-532); None = one line.  Returns a dict of torch tensors (conductivities in S/m)."""
+    import torch
+    hm = result["hitmap"]
+    dev = hm.device
+    B, ns, nd = hm.shape
+    s = np.log(1.0 + opt.factor) * opt.sigma_bins_nstd
+    dx = 2.0 * s / opt.n_sigma_bins
+    lo = torch.log(result["scalars"][:, _lib.S_HALFSPACE].to(torch.float64)) - s
+    r = ops.summarise_posterior(hm.contiguous(), lo, dx, percentiles=(5.0, 50.0, 95.0), credible_percent=credible_percent)
+    if line_id is None:
+        grp, ng = torch.zeros(B, dtype=torch.int32, device=dev), 1
+    else:
+        u, inv = np.unique(np.asarray(line_id), return_inverse=True)
+        grp, ng = torch.as_tensor(inv.astype(np.int32), device=dev), int(u.size)
+    opacity, doi_cell, _ = ops.opacity_doi(r["range_bins"], group=grp, n_groups=ng, doi_percent=doi_percent)
+    depth_edges = np.arange(0.0, 1.1 * opt.max_edge, 0.5 * opt.min_width)
+    centres = torch.as_tensor(0.5 * (depth_edges[1:] + depth_edges[:-1]), device=dev)
+    eh = result["edges_hist"].to(torch.float64)
+    out = {"mean": torch.exp(r["mean"]), "p5": torch.exp(r["pct"][0]), "p50": torch.exp(r["pct"][1]), "p95": torch.exp(r["pct"][2]),
+           "mode": torch.exp(r["mode"]), "credible_range": r["credible_range"], "opacity": opacity,
+           "doi": centres[doi_cell.long()], "interface_probability": eh / eh.sum(dim=1, keepdim=True).clamp_min(1.0),
+           "depth_edges": torch.as_tensor(depth_edges, device=dev)}
+    if "height_hist" in result:
+        hh = result["height_hist"].to(torch.float64)
+        c = torch.as_tensor(-opt.max_height_change + (np.arange(hh.shape[1]) + 0.5) * (2.0 * opt.max_height_change / hh.shape[1]), device=dev)
+        out["height_mean"] = result["scalars"][:, _lib.S_HEIGHT_REF] + (hh * c[None, :]).sum(dim=1) / hh.sum(dim=1).clamp_min(1.0)
     return out
 
 
@@ -168,6 +214,12 @@ def opacity_and_doi(p_low, p_high, depth_edges, doi_percent=67.0):
     lo, hi = np.asarray(p_low, dtype=np.float64), np.asarray(p_high, dtype=np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         rng = np.abs(np.log10(hi) - np.log10(lo))
+    return opacity_and_doi_from_range(rng, depth_edges, doi_percent)
+
+
+def opacity_and_doi_from_range(credible_range, depth_edges, doi_percent=67.0):
+    """The same from the credible range itself [n_soundings, n_depth] (Mesh._credible_range of the counts)."""
+    rng = np.asarray(credible_range, dtype=np.float64)
     mn, mx = np.nanmin(rng), np.nanmax(rng)
     t = (rng - mn) / (mx - mn) if (mx - mn) > 0.0 else rng - mn
     t = np.where(np.isnan(t), 1.0, t)
@@ -209,22 +261,30 @@ class Inference3D:
         opt = ops.options_from_reference(**options)
         self.options = opt
         sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct   # time-domain surveys: systems + tx-rx offset
+        import torch
+        dev = torch.device("cuda", device)
+
+        def up(a):
+            return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+        lines = np.asarray(d.lineNumber)[sel]
         if sharded:
             from . import parallel
             res = parallel.run_sharded(sysc, opt, d.data[sel], d.z[sel], seed=self.seed, precision=precision,
                                        outputs=ops.DEFAULT_OUTPUTS, max_iterations=max_iterations)
             if res is None:
                 return None
-            res = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()}
         elif sel.size == d.nPoints:
-            res = ops.rjmcmc_run(sysc, opt, d.data, d.z, seed=self.seed, first_index=0, max_iterations=max_iterations,
-                                 precision=precision, device=device)
+            res = ops.rjmcmc_run(sysc, opt, up(d.data), up(d.z), seed=self.seed, first_index=0, max_iterations=max_iterations,
+                                 precision=precision)
         else:
-            parts = [ops.rjmcmc_run(sysc, opt, d.data[i:i + 1], d.z[i:i + 1], seed=self.seed, first_index=int(i),
-                                    max_iterations=max_iterations, precision=precision, device=device) for i in sel]
-            res = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+            parts = [ops.rjmcmc_run(sysc, opt, up(d.data[i:i + 1]), up(d.z[i:i + 1]), seed=self.seed, first_index=int(i),
+                                    max_iterations=max_iterations, precision=precision) for i in sel]
+            res = {k: torch.cat([p[k] for p in parts], dim=0) for k in parts[0]}
+        # posterior summaries on the device, then everything comes to the host once
+        summ = summarise_device(res, opt, line_id=lines)
+        res = {k: v.cpu().numpy() for k, v in res.items()}
         res["index"] = sel
-        res.update({"summary_" + k: v for k, v in summarise(res, opt).items()})
+        res.update({"summary_" + k: v.cpu().numpy() for k, v in summ.items()})
         if "summary_height_mean" in res:
             res["summary_height_change_mean"] = res["summary_height_mean"] - np.asarray(d.z, dtype=np.float64)[sel]
         self.results = res
@@ -241,8 +301,8 @@ class Inference3D:
             idx = r["index"][m]
             path = os.path.join(directory, "%s.npz" % (("%g" % ln)))
             line = {}
-            if "summary_p5" in r and "summary_p95" in r:   # per-line products of Inference2D (opacity, doi)
-                line["opacity"], line["doi"] = opacity_and_doi(r["summary_p5"][m], r["summary_p95"][m], r["summary_depth_edges"])
+            if "summary_opacity" in r:   # per-line products of Inference2D (opacity, doi)
+                line["opacity"], line["doi"] = r["summary_opacity"][m], r["summary_doi"][m]
             np.savez_compressed(
                 path, line_number=ln, fiducial=d.fiducial[idx], x=d.x[idx], y=d.y[idx], z=d.z[idx],
                 elevation=d.elevation[idx], data=d.data[idx], **line,

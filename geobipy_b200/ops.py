@@ -441,3 +441,51 @@ def summarise_hitmap(hitmap, sig_lo, dx, percentiles=(5.0, 50.0, 95.0)):
         _lib.check(lib.gbp_summarise_hitmap(hitmap.data_ptr(), B, ns, nd, sig_lo.data_ptr(), float(dx), p.ctypes.data, int(p.size),
                                             mean.data_ptr(), pct.data_ptr(), st))
     return mean, pct
+
+
+def summarise_posterior(hitmap, sig_lo, dx, percentiles=(5.0, 50.0, 95.0), credible_percent=90.0):
+    """All per-depth-cell summaries of hitmaps [B, n_sig, n_depth] (torch CUDA int32) in one pass of the hand-written
+    kernel (gbp_summarise_posterior): mean, percentiles and mode of ln(sigma), and the credible range of
+    `credible_percent` in bins.  Returns dict(mean [B, nd], pct [n_pct, B, nd], mode [B, nd], range_bins [B, nd] int32,
+    credible_range [B, nd] in decades = Mesh._credible_range with the hitmap's log = 10 axis)."""
+    import torch
+    lib = _lib.require_cuda()
+    assert hitmap.is_cuda and hitmap.dtype == torch.int32 and hitmap.is_contiguous()
+    B, ns, nd = hitmap.shape
+    sig_lo = sig_lo.to(torch.float64).contiguous()
+    p = np.ascontiguousarray(percentiles, dtype=np.float64)
+    dev = hitmap.device
+    mean = torch.empty((B, nd), dtype=torch.float64, device=dev)
+    pct = torch.empty((p.size, B, nd), dtype=torch.float64, device=dev)
+    mode = torch.empty((B, nd), dtype=torch.float64, device=dev)
+    rng = torch.empty((B, nd), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.gbp_summarise_posterior(hitmap.data_ptr(), B, ns, nd, sig_lo.data_ptr(), float(dx), p.ctypes.data, int(p.size),
+                                               float(credible_percent), mean.data_ptr(), pct.data_ptr(), mode.data_ptr(),
+                                               rng.data_ptr(), st))
+    return dict(mean=mean, pct=pct, mode=mode, range_bins=rng, credible_range=rng.to(torch.float64) * (float(dx) / np.log(10.0)))
+
+
+def opacity_doi(range_bins, group=None, n_groups=0, doi_percent=67.0, level_percent=95.0):
+    """Opacity [B, nd], depth-of-investigation cell [B] and opacity-level cell [B] from credible ranges in bins (torch CUDA
+    int32 [B, nd]) with gbp_opacity_doi.  group [B] int32 (torch CUDA) = the flight line of each sounding: the range is
+    normalised over the line (Inference2D.compute_opacity); None = per sounding (Histogram.opacity)."""
+    import torch
+    lib = _lib.require_cuda()
+    assert range_bins.is_cuda and range_bins.dtype == torch.int32 and range_bins.is_contiguous()
+    B, nd = range_bins.shape
+    dev = range_bins.device
+    ng = int(n_groups) if group is not None else B
+    if group is not None:
+        group = group.to(torch.int32).contiguous()
+    scratch = torch.empty((2, max(ng, 1)), dtype=torch.int32, device=dev)
+    opacity = torch.empty((B, nd), dtype=torch.float64, device=dev)
+    doi = torch.empty((B,), dtype=torch.int32, device=dev)
+    level = torch.empty((B,), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.gbp_opacity_doi(range_bins.data_ptr(), B, nd, group.data_ptr() if group is not None else None, ng,
+                                       float(doi_percent), float(level_percent), scratch.data_ptr(), opacity.data_ptr(),
+                                       doi.data_ptr(), level.data_ptr(), st))
+    return opacity, doi, level

@@ -126,12 +126,12 @@ def summarise_hitmap(hitmap, sigma_edges_ln, percentiles=(5.0, 50.0, 95.0)):
     centres = 0.5 * (sigma_edges_ln[..., 1:] + sigma_edges_ln[..., :-1])
     if centres.dim() == 1:
         centres = centres.unsqueeze(0).expand(h.shape[0], -1)
-    tot = h.sum(dim=1).clamp_min(1.0)
-    out = {"mean": (h * centres.unsqueeze(2)).sum(dim=1) / tot}
+    tot = h.sum(dim=1)
+    out = {"mean": (h * centres.unsqueeze(2)).sum(dim=1) / tot.clamp_min(1.0)}
     cs = torch.cumsum(h, dim=1)
-    for p in percentiles:
-        target = (p / 100.0) * tot
-        idx = (cs < target.unsqueeze(1)).sum(dim=1).clamp_max(h.shape[1] - 1)
+    frac = torch.where(tot.unsqueeze(1) > 0, cs / tot.unsqueeze(1).clamp_min(1.0), torch.zeros_like(cs))
+    for p in percentiles:   # first bin whose cumulative fraction reaches p * 0.01 (fp64 both: the reference's rule, ties included)
+        idx = (frac < p * 0.01).sum(dim=1).clamp_max(h.shape[1] - 1)
         out["p%g" % p] = torch.gather(centres, 1, idx)
     return out
 

@@ -234,6 +234,25 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system *sys, const gbp_options *opt, int 
  * of the column total, in ln(sigma).  DEVICE pointers, stream ordered; at most 8 percentiles. */
 int gbp_summarise_hitmap(const int32_t *d_hitmap, int B, int n_sig, int n_depth, const double *d_sig_lo, double dx,
                          const double *percentiles, int n_pct, double *d_mean, double *d_pct, void *stream);
+/* The same plus the remaining per-cell summaries of the reference: d_mode [B][n_depth] = centre of the first fullest
+ * bin (Mesh._mode, Mesh.py:138-165) and d_range_bins [B][n_depth] (int32) = the credible range of `credible_percent`
+ * (Mesh._credible_range, Mesh.py:58-78) in BINS: |log10 hi - log10 lo| = bins * dx / ln(10).  d_mode / d_range_bins may be
+ * NULL; a credible range uses two of the 8 percentile slots.  Percentile rule: first bin whose cumulative fraction
+ * (fp64) reaches percent * 0.01 (fp64) - the reference's rule including its round-off at exact ties. */
+int gbp_summarise_posterior(const int32_t *d_hitmap, int B, int n_sig, int n_depth, const double *d_sig_lo, double dx,
+                            const double *percentiles, int n_pct, double credible_percent, double *d_mean, double *d_pct,
+                            double *d_mode, int32_t *d_range_bins, void *stream);
+/* Opacity, depth of investigation and opacity level from credible ranges in bins (Histogram.transparency / opacity
+ * Histogram.py:330-354, :509-541; Inference2D.compute_doi Inference2D.py:493-532; Histogram.opacity_level :356-367).
+ * d_group [B] (int32, or NULL = every sounding its own group) names the set over which the range is normalised to
+ * [0, 1]: the sounding (Histogram.opacity of one hitmap) or its flight line (Inference2D.compute_opacity :1011-1023).
+ * d_group_minmax: 2 x n_groups int32 of scratch (n_groups = B when d_group is NULL).  d_opacity [B][n_depth];
+ * d_doi_cell [B] = depth cell of the depth of investigation (deepest cell, from the bottom up, whose opacity reaches
+ * doi_percent / 100, never below index 0); d_level_cell [B] = depth cell of Histogram.opacity_level(level_percent).
+ * Any output may be NULL.  DEVICE pointers, stream ordered. */
+int gbp_opacity_doi(const int32_t *d_range_bins, int B, int n_depth, const int32_t *d_group, int n_groups, double doi_percent,
+                    double level_percent, int32_t *d_group_minmax, double *d_opacity, int32_t *d_doi_cell,
+                    int32_t *d_level_cell, void *stream);
 /* The *_rjmcmc_run_host entry points keep their device buffers between calls (per device); this frees them. */
 int gbp_release_host_buffers(void);
 

@@ -540,6 +540,39 @@ def make_chain(sidx, rep=0, n_markov_chains=10000, height=False):
     print("chain", sidx, "iterations", it, "burned in", inf.burned_in, inf.burned_in_iteration, "s/it", dt / it)
 
 
+def make_summaries():
+    """posterior_summaries.npz: what the reference's OWN Histogram / Mesh methods return for recorded hitmaps (the 2-D
+    conductivity-depth posteriors of ref_chain_{1,2,3}): Histogram.mean / median / mode / percentile / credible_range /
+    transparency / opacity / opacity_level (classes/statistics/Histogram.py:262-401, :509-542 over Mesh._mean /
+    _percentile / _mode / _credible_range, classes/mesh/Mesh.py:30-217).  The Histogram object is the live one of an
+    initialised Inference1D (Model.set_posteriors, Model.py:666-684: conductivity axis log = 10, relative to the
+    half-space), its counts replaced by the recorded ones."""
+    _geobipy()
+    out = {}
+    for n, sidx in enumerate((1, 2, 3)):
+        g = np.load(os.path.join(HERE, "ref_chain_%d.npz" % sidx))
+        inf = _initialised_inference(g["data"], float(g["altitude"]), 100, 1)
+        H = inf.model.values.posterior
+        assert abs(float(inf.halfspace.item()) / float(g["halfspace"]) - 1.0) < 1e-12
+        assert tuple(H.counts.shape) == tuple(g["hitmap"].shape)
+        H.values = np.asarray(g["hitmap"], dtype=np.float64).copy()   # Histogram.values setter -> counts
+        assert np.array_equal(np.asarray(H.counts), g["hitmap"])
+        rec = dict(hitmap=g["hitmap"], halfspace=float(g["halfspace"]),
+                   x_edges=np.asarray(H.mesh.x.edges_absolute, dtype=np.float64), y_edges=np.asarray(H.mesh.y.edges, dtype=np.float64),
+                   mean=np.asarray(H.mean(axis=0).values), median=np.asarray(H.median(axis=0).values),
+                   mode=np.asarray(H.mode(axis=0).values), p5=np.asarray(H.percentile(5.0, axis=0).values),
+                   p95=np.asarray(H.percentile(95.0, axis=0).values),
+                   credible_range90=np.asarray(H.credible_range(percent=90.0, log=10, axis=0)),
+                   transparency90=np.asarray(H.transparency(percent=90.0, log=10, axis=0).values),
+                   opacity90=np.asarray(H.opacity(percent=90.0, log=10, axis=0).values),
+                   transparency95=np.asarray(H.transparency(percent=95.0, axis=0).values),
+                   opacity_level95=float(H.opacity_level(percent=95.0, axis=0)))
+        for k, v in rec.items():
+            out["s%d_%s" % (n, k)] = np.asarray(v, dtype=np.float64) if k != "hitmap" else v
+    np.savez_compressed(os.path.join(HERE, "posterior_summaries.npz"), soundings=np.array([1, 2, 3]), **out)
+    print("posterior summaries written", {k: np.shape(v) for k, v in out.items() if k.startswith("s0_")})
+
+
 def make_height_reset():
     """What Inference1D.reset() (:984-994) does to a sampled height: recorded from the live reference."""
     import io
@@ -587,6 +620,8 @@ if __name__ == "__main__":
         make_fdem()
     elif what == "bins":
         make_bins()
+    elif what == "summaries":
+        make_summaries()
     elif what == "transitions":
         make_transitions()
     elif what == "chain":

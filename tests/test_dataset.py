@@ -80,6 +80,38 @@ def test_summaries_match_histogram_class(built_lib):
     assert np.isclose(hz.mean(), sz["height_mean"][1])
 
 
+def test_histogram_mirror_matches_reference_histogram(golden_dir):
+    """api.Histogram against what the reference's own Histogram / Mesh methods return on recorded hitmaps
+    (tests/golden/posterior_summaries.npz, make_golden.py summaries): mean, median, mode, percentiles, credible range,
+    transparency, opacity, opacity level - including the reference's round-off at exact percentile ties (sounding 2 of the
+    file has 10 000 counts per column and cumulative fractions of exactly 0.95)."""
+    from geobipy_b200 import api
+    g = np.load(os.path.join(golden_dir, "posterior_summaries.npz"))
+    ties = 0
+    for n in range(3):
+        P = lambda k: g["s%d_%s" % (n, k)]   # noqa: E731
+        h = api.Histogram(P("hitmap"), P("x_edges"), P("y_edges"), log_x=True)
+        cs = np.cumsum(P("hitmap"), axis=0).astype(np.float64)
+        for name, mine in (("mean", h.mean()), ("median", h.median()), ("mode", h.mode())):
+            assert np.allclose(mine, P(name), rtol=1e-12, atol=0.0), (n, name)
+        # Histogram.percentile works on the pmf (counts / grand total, Histogram.py:43-49, :387): where a cumulative count
+        # hits percent x total EXACTLY its answer depends on the round-off of that normalisation (bin i or i + 1); median,
+        # credible range, transparency and opacity work on the counts and are reproduced exactly, ties included
+        for name, pc, mine in (("p5", 5.0, h.percentile(5.0)), ("p95", 95.0, h.percentile(95.0))):
+            tie = (np.abs(cs - pc * 0.01 * cs[-1]) < 1e-9 * np.maximum(cs[-1], 1.0)).any(axis=0)
+            assert np.allclose(mine[~tie], P(name)[~tie], rtol=1e-12, atol=0.0), (n, name)
+            bw = np.log(P("x_edges")[1] / P("x_edges")[0])
+            assert np.all(np.abs(np.log(mine[tie] / P(name)[tie])) <= bw * (1 + 1e-9)), (n, name)
+        assert np.allclose(h.credible_range(90.0), P("credible_range90"), rtol=0.0, atol=1e-12), n
+        assert np.allclose(h.transparency(90.0), P("transparency90"), rtol=0.0, atol=1e-12), n
+        assert np.allclose(h.opacity(90.0), P("opacity90"), rtol=0.0, atol=1e-12), n
+        assert np.allclose(h.transparency(95.0), P("transparency95"), rtol=0.0, atol=1e-12), n
+        assert h.opacity_level(95.0) == float(P("opacity_level95")), n
+        cs = np.cumsum(P("hitmap"), axis=0)
+        ties += int(((cs == 0.95 * cs[-1]) & (cs[-1] > 0)).any())
+    assert ties >= 1   # the tie rule is exercised
+
+
 @pytest.mark.gpu
 def test_inference3d_end_to_end(tmp_path, golden_dir, built_lib):
     from geobipy_b200 import _lib
@@ -91,6 +123,14 @@ def test_inference3d_end_to_end(tmp_path, golden_dir, built_lib):
     r = inv.infer(n_markov_chains=400, max_iterations=300)
     assert r["hitmap"].shape == (6, 250, 440) and (r["scalars"][:, _lib.S_ITER] == 300).all()
     assert r["summary_p50"].shape == (6, 440) and np.all(r["summary_p5"] <= r["summary_p95"])
+    # the summaries were computed on the device (gbp_summarise_posterior / gbp_opacity_doi): the host statement agrees
+    from geobipy_b200 import dataset
+    host = dataset.summarise(r, inv.options, line_id=d.lineNumber)
+    for k in ("mean", "p5", "p50", "p95", "mode", "interface_probability"):
+        assert np.allclose(r["summary_" + k], host[k], rtol=1e-12, atol=0.0), k
+    assert np.allclose(r["summary_credible_range"], host["credible_range"], rtol=0.0, atol=1e-12)
+    assert np.allclose(r["summary_opacity"], host["opacity"], rtol=0.0, atol=1e-12) and np.array_equal(r["summary_doi"], host["doi"])
+    assert r["summary_opacity"][:3].max() == 1.0 and r["summary_opacity"][3:].max() == 1.0   # normalised per flight line
     one = Inference3D(d, seed=5).infer(index=4, n_markov_chains=400, max_iterations=300)
     assert np.array_equal(one["hitmap"][0], r["hitmap"][4])       # (seed, sounding index) fixes the stream
     byfid = Inference3D(d, seed=5).infer(fiducial=4.0, line_number=200.0, n_markov_chains=400, max_iterations=300)
@@ -136,7 +176,7 @@ def test_inference3d_save_writes_line_products(tmp_path, golden_dir, built_lib):
     sc[:, _lib.S_HALFSPACE] = 0.02
     res = dict(hitmap=rng.integers(0, 20, (6, opt.n_sigma_bins, nd)).astype(np.int32), scalars=sc,
                edges_hist=rng.integers(0, 5, (6, nd)).astype(np.int32), index=np.arange(6))
-    res.update({"summary_" + k: v for k, v in dataset.summarise(res, opt).items()})
+    res.update({"summary_" + k: v for k, v in dataset.summarise(res, opt, line_id=d.lineNumber).items()})
     inv = dataset.Inference3D(d, seed=1)
     inv.results, inv.options = res, opt
     files = inv.save(str(tmp_path / "out"))
@@ -145,7 +185,7 @@ def test_inference3d_save_writes_line_products(tmp_path, golden_dir, built_lib):
     assert z["hitmap"].shape == (3, opt.n_sigma_bins, nd) and z["opacity"].shape == (3, nd) and z["doi"].shape == (3,)
     assert z["opacity"].min() >= 0.0 and z["opacity"].max() <= 1.0 and z["opacity"].max() == 1.0
     op, doi = dataset.opacity_and_doi(res["summary_p5"][:3], res["summary_p95"][:3], res["summary_depth_edges"])
-    assert np.array_equal(z["opacity"], op) and np.array_equal(z["doi"], doi)
+    assert np.allclose(z["opacity"], op, rtol=0.0, atol=1e-12) and np.array_equal(z["doi"], doi)
 
 
 def test_histogram_credible_range_opacity_mode(built_lib):

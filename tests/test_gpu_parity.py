@@ -506,3 +506,53 @@ def test_team_mode_is_bit_identical(gpu, systems, oracle, monkeypatch):
                 continue
             for k in ref:
                 assert np.array_equal(ref[k], r[k], equal_nan=True), (B, team, spread, fu, k)
+
+
+def test_device_summaries_match_reference_histogram(gpu, golden_dir):
+    """SURVEY.md 8(f) rank 2 on the device: gbp_summarise_posterior + gbp_opacity_doi against what the reference's OWN
+    Histogram / Mesh methods return on recorded hitmaps (tests/golden/posterior_summaries.npz): mean, median, mode, 5 % /
+    95 % percentiles (1e-12 relative), credible range in decades, transparency, opacity (1e-12 absolute), opacity level;
+    the depth of investigation and the per-line normalisation (Inference2D.compute_opacity / compute_doi, which need an
+    HDF5 file in the reference) against the host restatement dataset.opacity_and_doi."""
+    import torch
+    from geobipy_b200 import dataset
+    g = np.load(os.path.join(golden_dir, "posterior_summaries.npz"))
+    P = lambda n, k: g["s%d_%s" % (n, k)]   # noqa: E731
+    hm = torch.tensor(np.stack([P(n, "hitmap") for n in range(3)]).astype(np.int32), device="cuda")
+    ln_edges = np.stack([np.log(P(n, "x_edges")) for n in range(3)])
+    lo = torch.tensor(ln_edges[:, 0], device="cuda")
+    dx = float((ln_edges[0, -1] - ln_edges[0, 0]) / 250)
+    r = gpu.summarise_posterior(hm, lo, dx, percentiles=(5.0, 50.0, 95.0), credible_percent=90.0)
+    for n in range(3):
+        cs = np.cumsum(P(n, "hitmap"), axis=0).astype(np.float64)
+        for name, pc, mine in (("mean", None, r["mean"][n]), ("p5", 5.0, r["pct"][0, n]), ("median", None, r["pct"][1, n]),
+                               ("p95", 95.0, r["pct"][2, n]), ("mode", None, r["mode"][n])):
+            mine = np.exp(mine.cpu().numpy())
+            # Histogram.percentile normalises by the grand total first: at an EXACT tie of a cumulative count its bin
+            # depends on that round-off (tests/test_dataset.py); everything computed from the counts is exact
+            tie = np.zeros(mine.shape, bool) if pc is None else (np.abs(cs - pc * 0.01 * cs[-1]) < 1e-9 * np.maximum(cs[-1], 1.0)).any(axis=0)
+            assert np.allclose(mine[~tie], P(n, name)[~tie], rtol=1e-12, atol=0.0), (n, name)
+            assert np.all(np.abs(np.log(mine[tie] / P(n, name)[tie])) <= dx * (1 + 1e-9)), (n, name)
+        assert np.allclose(r["credible_range"][n].cpu().numpy(), P(n, "credible_range90"), rtol=0.0, atol=1e-12), n
+    # per sounding normalisation = Histogram.transparency / opacity of one hitmap
+    op, doi, _ = gpu.opacity_doi(r["range_bins"], doi_percent=67.0, level_percent=95.0)
+    for n in range(3):
+        assert np.allclose(op[n].cpu().numpy(), P(n, "opacity90"), rtol=0.0, atol=1e-12), n
+        assert np.allclose(1.0 - op[n].cpu().numpy(), P(n, "transparency90"), rtol=0.0, atol=1e-12), n
+    # opacity level of the 95 % credible range
+    r95 = gpu.summarise_posterior(hm, lo, dx, percentiles=(50.0,), credible_percent=95.0)
+    _, _, lvl = gpu.opacity_doi(r95["range_bins"], level_percent=95.0)
+    for n in range(3):
+        yc = 0.5 * (P(n, "y_edges")[1:] + P(n, "y_edges")[:-1])
+        assert yc[int(lvl[n])] == float(P(n, "opacity_level95")), n
+    # the flight line: the three soundings normalised together + depth of investigation
+    grp = torch.zeros(3, dtype=torch.int32, device="cuda")
+    op_l, doi_l, _ = gpu.opacity_doi(r["range_bins"], group=grp, n_groups=1, doi_percent=67.0)
+    ref_op, ref_doi = dataset.opacity_and_doi_from_range(np.stack([P(n, "credible_range90") for n in range(3)]), P(0, "y_edges"),
+                                                         doi_percent=67.0)
+    assert np.allclose(op_l.cpu().numpy(), ref_op, rtol=0.0, atol=1e-12)
+    yc = 0.5 * (P(0, "y_edges")[1:] + P(0, "y_edges")[:-1])
+    assert np.array_equal(yc[doi_l.cpu().numpy()], ref_doi)
+    # empty hitmap: every summary falls on the last bin, as the reference's clip
+    z = gpu.summarise_posterior(torch.zeros((1, 250, 440), dtype=torch.int32, device="cuda"), lo[:1], dx)
+    assert bool((z["range_bins"] == 0).all()) and np.allclose(z["pct"][1].cpu().numpy(), ln_edges[0, 0] + 249.5 * dx)
