@@ -18,10 +18,32 @@ import numpy as np
 
 from . import _lib, ops
 
-__all__ = ["CircularLoop", "FdemSystem", "RectilinearMesh1D", "Model", "FdemDataPoint", "Histogram",
+__all__ = ["CircularLoop", "FdemSystem", "RectilinearMesh1D", "Model", "FdemDataPoint", "Histogram", "StatArray",
            "Inference1D", "infer_batch"]
 
 _ORI = {"x": 0, "y": 1, "z": 2}
+
+
+class StatArray(np.ndarray):
+    """An array (or 0-d scalar) that carries its name, units and - after an inference - its `posterior` Histogram, like
+    the reference's StatArray (classes/core/StatArray.py): `model.values.posterior`, `model.mesh.nCells.posterior`,
+    `datapoint.relative_error.posterior` ... are the attribute paths Inference1D.writeHdf serialises (:1050-1090)."""
+
+    def __new__(cls, values, name=None, units=None, posterior=None):
+        obj = np.asarray(values).view(cls)
+        obj.name, obj.units, obj.posterior = name, units, posterior
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.name = getattr(obj, "name", None)
+        self.units = getattr(obj, "units", None)
+        self.posterior = getattr(obj, "posterior", None)
+
+    @property
+    def hasPosterior(self):
+        return self.posterior is not None
 
 
 class CircularLoop:
@@ -107,11 +129,13 @@ class RectilinearMesh1D:
     def __init__(self, edges=None, centres=None, widths=None, **kwargs):
         if edges is None and widths is not None:
             edges = np.r_[0.0, np.cumsum(widths)]
-        self.edges = np.asarray(edges, dtype=np.float64)
+        self.edges = StatArray(np.asarray(edges, dtype=np.float64), "Depth", "m")
+        self._nCells = StatArray(np.int32(self.edges.size - 1), "Number of layers")
 
     @property
     def nCells(self):
-        return self.edges.size - 1
+        """Number of layers: an integer-like 0-d StatArray (its `posterior` is the layer-count histogram)."""
+        return self._nCells
 
     @property
     def nEdges(self):
@@ -131,12 +155,21 @@ class Model:
 
     def __init__(self, mesh=None, values=None):
         self.mesh = mesh
-        self.values = np.asarray(values, dtype=np.float64) if values is not None else np.zeros(mesh.nCells)
-        self.posterior = None  # Histogram (hitmap) after an inference
+        self.values = StatArray(np.asarray(values, dtype=np.float64) if values is not None else np.zeros(int(mesh.nCells)),
+                                "Conductivity", "S/m")
+
+    @property
+    def posterior(self):
+        """The hitmap (alias of `values.posterior`, the reference's path)."""
+        return self.values.posterior
+
+    @posterior.setter
+    def posterior(self, h):
+        self.values.posterior = h
 
     @property
     def nCells(self):
-        return self.mesh.nCells
+        return int(self.mesh.nCells)
 
 
 class Histogram:
@@ -348,6 +381,8 @@ class Inference1D:
             seed = int(prng.integers(0, 2 ** 63 - 1)) if prng is not None else 0
         self.seed, self.sounding_index = int(seed) & (2 ** 64 - 1), int(sounding_index)
         self.n_markov_chains, self.update_plot_every = int(n_markov_chains), int(update_plot_every)
+        self.multiplier = np.float64(multiplier)   # carried and serialised, as in the reference (Inference1D.py:88, :1067)
+        self.interactive_plot, self.reciprocate_parameter, self.limits = bool(interactive_plot), False, None
         self.precision, self.device = precision, device
         self.options = ops.options_from_reference(
             covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains, update_plot_every=update_plot_every,
@@ -411,41 +446,59 @@ class Inference1D:
             return Model(RectilinearMesh1D(edges=edges[:k + 1]), sig[:k])
         self.model = model(s[_lib.S_CUR_K], r["cur_sigma"][b], r["cur_edges"][b])
         self.best_model = model(s[_lib.S_BEST_K], r["best_sigma"][b], r["best_edges"][b])
-        self.model.posterior = Histogram(r["hitmap"][b], g["sigma_edges"], g["depth_edges"], log_x=True)
-        self.hitmap = self.model.posterior
-        self.n_cells_posterior = Histogram(r["ncells_hist"][b], np.arange(-0.5, o.max_layers + 1.0))
-        self.edges_posterior = Histogram(r["edges_hist"][b], g["depth_edges"])
-        if o.n_systems > 1:  # one histogram per system, as DataPoint.set_relative_error_posterior builds them (:668-680)
-            self.relative_error_posterior = [Histogram(r["rel_hist"][b][i], g["rel_edges"][i], log_x=True) for i in range(2)]
-            self.additive_error_posterior = [Histogram(r["add_hist"][b][i], g["add_edges"][i], log_x=True) for i in range(2)]
-        else:
-            self.relative_error_posterior = Histogram(r["rel_hist"][b], g["rel_edges"], log_x=True)
-            self.additive_error_posterior = Histogram(r["add_hist"][b], g["add_edges"], log_x=True)
+        # the attribute paths Inference1D.writeHdf serialises (:1050-1090): model.values.posterior,
+        # model.mesh.nCells.posterior, model.mesh.edges.posterior, datapoint.relative_error / additive_error / z .posterior
+        self.model.values.posterior = Histogram(r["hitmap"][b], g["sigma_edges"], g["depth_edges"], log_x=True)
+        self.model.mesh.nCells.posterior = Histogram(r["ncells_hist"][b], np.arange(-0.5, o.max_layers + 1.0))
+        self.model.mesh.edges.posterior = Histogram(r["edges_hist"][b], g["depth_edges"])
+        self.hitmap = self.model.values.posterior
+        self.n_cells_posterior, self.edges_posterior = self.model.mesh.nCells.posterior, self.model.mesh.edges.posterior
         self.data_misfit_v = r["misfit_trace"][b]
         self.acceptance_v = r["accept_trace"][b]
         dp = self.datapoint
-        if o.n_systems > 1:
-            dp.relative_error = np.asarray([s[_lib.S_CUR_REL], s[_lib.S_CUR_REL2]])
-            dp.additive_error = np.asarray([s[_lib.S_CUR_ADD], s[_lib.S_CUR_ADD2]])
+        if o.n_systems > 1:  # one histogram per system, as DataPoint.set_relative_error_posterior builds them (:668-680)
+            rel_post = [Histogram(r["rel_hist"][b][i], g["rel_edges"][i], log_x=True) for i in range(2)]
+            add_post = [Histogram(r["add_hist"][b][i], g["add_edges"][i], log_x=True) for i in range(2)]
+            dp.relative_error = StatArray([s[_lib.S_CUR_REL], s[_lib.S_CUR_REL2]], "Relative error", posterior=rel_post)
+            dp.additive_error = StatArray([s[_lib.S_CUR_ADD], s[_lib.S_CUR_ADD2]], "Additive error", posterior=add_post)
             self.best_relative_error = np.asarray([s[_lib.S_BEST_REL], s[_lib.S_BEST_REL2]])
             self.best_additive_error = np.asarray([s[_lib.S_BEST_ADD], s[_lib.S_BEST_ADD2]])
         else:
-            dp.relative_error = np.asarray([s[_lib.S_CUR_REL]])
-            dp.additive_error = np.asarray([s[_lib.S_CUR_ADD]])
+            rel_post = Histogram(r["rel_hist"][b], g["rel_edges"], log_x=True)
+            add_post = Histogram(r["add_hist"][b], g["add_edges"], log_x=True)
+            dp.relative_error = StatArray([s[_lib.S_CUR_REL]], "Relative error", posterior=rel_post)
+            dp.additive_error = StatArray([s[_lib.S_CUR_ADD]], "Additive error", posterior=add_post)
             self.best_relative_error, self.best_additive_error = float(s[_lib.S_BEST_REL]), float(s[_lib.S_BEST_ADD])
+        self.relative_error_posterior, self.additive_error_posterior = rel_post, add_post
+        z_post = None
         if o.solve_height:  # solve_z: datapoint.z / best_datapoint.z and datapoint.z.posterior (Point.py:1013-1025)
             # the bins are relative to the centre of the height prior, which reset() re-centres on the sampled height
             # (Inference1D.py:984-994): the kernel reports it (S_HEIGHT_REF); dp.z_input keeps the height handed in
             z_ref = float(s[_lib.S_HEIGHT_REF])
-            self.height_posterior = Histogram(r["height_hist"][b], z_ref + np.linspace(-o.max_height_change, o.max_height_change,
-                                                                                     o.n_err_bins + 1))
+            z_post = Histogram(r["height_hist"][b], z_ref + np.linspace(-o.max_height_change, o.max_height_change, o.n_err_bins + 1))
+            self.height_posterior = z_post
             self.best_height = float(s[_lib.S_BEST_HEIGHT])
             if self._tdem:   # the transmitter moves, the receiver keeps its offset (Loop_pair.Geometry, Loop_pair.py:62-78)
                 dz = float(s[_lib.S_CUR_HEIGHT]) - float(dp.transmitter.z)
-                dp.transmitter.z = float(dp.transmitter.z) + dz
+                dp.transmitter.z = StatArray(float(dp.transmitter.z) + dz, "Height", "m", posterior=z_post)
                 dp.receiver.z = float(dp.receiver.z) + dz
             else:
-                dp.z = float(s[_lib.S_CUR_HEIGHT])
+                dp.z = StatArray(float(s[_lib.S_CUR_HEIGHT]), "Height", "m", posterior=z_post)
+        # best_datapoint: the datapoint at the highest-posterior state (errors, height, predicted data of best_model)
+        import copy
+        bdp = copy.copy(dp)
+        bdp.predictedData = dp.predictedData.copy()
+        bdp.relative_error = StatArray(np.atleast_1d(self.best_relative_error), "Relative error")
+        bdp.additive_error = StatArray(np.atleast_1d(self.best_additive_error), "Additive error")
+        if o.solve_height:
+            if self._tdem:
+                bdp.transmitter, bdp.receiver = copy.copy(dp.transmitter), copy.copy(dp.receiver)
+                dzb = self.best_height - float(dp.transmitter.z)
+                bdp.transmitter.z, bdp.receiver.z = self.best_height, float(dp.receiver.z) + dzb
+            else:
+                bdp.z = StatArray(self.best_height, "Height", "m")
+        bdp.forward(self.best_model)
+        self.best_datapoint = bdp
         dp.forward(self.model)
 
     def interface_probability(self):

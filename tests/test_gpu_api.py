@@ -129,3 +129,36 @@ def test_inference1d_solve_z(api, oracle):
     chk = api.FdemDataPoint(z=dp.z, system=system)
     chk.forward(inf.model)
     assert np.allclose(chk.predictedData, dp.predictedData)
+
+
+def test_inference1d_exposes_the_paths_writeHdf_serialises(api, oracle):
+    """Inference1D.writeHdf (inversion/Inference1D.py:1050-1090) walks model.values.posterior, model.mesh.nCells.posterior,
+    model.mesh.edges.posterior, datapoint.relative_error / additive_error / z .posterior, best_model, best_datapoint,
+    multiplier: the mirror exposes exactly those paths."""
+    system = _resolve(api)
+    true = api.Model(api.RectilinearMesh1D(edges=[0.0, 5.0, 7.5, np.inf]), [1e-2, 1e-1, 0.03333333])
+    dp = api.FdemDataPoint(z=30.0, system=system)
+    dp.forward(true)
+    dp.data[:] = dp.predictedData
+    inf = api.Inference1D(prng=np.random.default_rng(0), n_markov_chains=600, multiplier=1.5, solve_z=True,
+                          maximum_z_change=1.0, z_proposal_variance=0.01)
+    inf.initialize(dp)
+    inf.infer(None)
+    m = inf.model
+    assert m.values.hasPosterior and m.values.posterior.counts.shape == (250, 440)
+    assert m.values.posterior is inf.hitmap is m.posterior
+    assert int(m.mesh.nCells) == m.nCells == m.values.size
+    assert m.mesh.nCells.posterior.counts.sum() == 600 and m.mesh.nCells.posterior is inf.n_cells_posterior
+    assert m.mesh.edges.posterior.counts.shape == (440,)
+    d = inf.datapoint
+    assert d.relative_error.posterior.counts.sum() == 600 and d.additive_error.posterior.counts.sum() == 600
+    assert d.z.posterior.counts.sum() == 600 and d.z.posterior is inf.height_posterior
+    assert float(inf.multiplier) == 1.5
+    b = inf.best_datapoint
+    assert b is not d and float(b.z) == inf.best_height
+    assert np.allclose(b.relative_error, inf.best_relative_error) and np.allclose(b.additive_error, inf.best_additive_error)
+    chk = api.FdemDataPoint(z=float(b.z), system=system)
+    chk.forward(inf.best_model)
+    assert np.allclose(chk.predictedData, b.predictedData)
+    # slicing / arithmetic keep plain-array behaviour
+    assert np.all(np.asarray(m.values) * 2.0 == 2.0 * m.values) and (m.mesh.edges[1:] - m.mesh.edges[:-1]).shape == (m.nCells,)
