@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-forward-only", action="store_true", help="skip the forward-only operator throughput block")
+    ap.add_argument("--port", action="store_true", help="--impl reference: time the C restatement even when baseline/_ref is importable")
     return ap.parse_args()
 
 
@@ -148,42 +150,99 @@ def cpu_sample(chains, n_chains, max_it, pool, wname="resolve"):
     return float(sum(its)), time.perf_counter() - t0
 
 
+def _ref_live():
+    """oracle/ref_live.py when an importable copy of the reference exists on this machine (baseline/_ref), else None."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_live
+    except Exception:
+        return None
+    return ref_live if ref_live.reference_root() else None
+
+
+def _ref_chain(job):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_live
+    return ref_live.time_chain(job)
+
+
+def reference_sample(pool, n_chains, iters, seed=1):
+    """The UNMODIFIED reference (baseline/_ref: Inference1D.accept_reject + update, Inference1D.py:537, :705, its own
+    numba forward kernels) on soundings 0..n_chains-1 of the RESOLVE workload, `iters` iterations each, one process per
+    chain.  Returns (iterations, wall seconds of the pool.map, max of the per-chain loop times)."""
+    data, alt = _observed_cpu(n_chains, "resolve")
+    jobs = [(i, data[i], float(alt[i]), N_MARKOV_CHAINS, iters, seed) for i in range(n_chains)]
+    t0 = time.perf_counter()
+    out = pool.map(_ref_chain, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return float(sum(o[0] for o in out)), wall, max(o[1] for o in out)
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's algorithm on the host CPU.  The reference itself is pure Python
-    (NumPy/Numba) and cannot travel to the GPU box, so this arm times its plain-C restatement (oracle/,
-    kind "port") with one process per host core - an upper bound on the reference's own speed (the
-    Python reference measures ~115 evals/s/core in the build container)."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.
+
+    RESOLVE workload with baseline/_ref present (the offline `pip install --no-deps --target baseline/_ref` of the
+    reference; numba is in the image): the UNMODIFIED Python reference, one process per core, each step a bounded
+    sample of `cores` soundings x 400 iterations (kind "reference"; import + numba compilation happen in the warm-up).
+    Otherwise (time-domain workloads: the reference's gatdaem1d is absent; or no baseline/_ref): the plain-C
+    restatement (oracle/, kind "port") - ~18x faster per core than the Python reference, i.e. an upper bound."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        os.environ[k] = "1"   # one process per core already
     cores = os.cpu_count() or 1
     n_chains = cores
-    max_it = 4000  # bounded sample: first 4000 iterations of `cores` chains per step (~2-4 s per step)
     kinds = ("resolve", "skytem") if args.workload == "mixed" else (args.workload,)
     for k in kinds:
         _observed_cpu(1, k)
+    live = _ref_live() if args.workload == "resolve" and not args.port else None
+    port = None
     with mp.get_context("spawn").Pool(cores) as pool:
-        for _ in range(args.warmup):
+        if live is not None:
+            ref_iters = 400
+            try:
+                for w in range(max(args.warmup, 1)):   # the first one imports the reference and compiles its kernels
+                    reference_sample(pool, n_chains, 50)
+                its, secs = 0.0, 0.0
+                for _ in range(args.steps):
+                    i, wall, _ = reference_sample(pool, n_chains, ref_iters)
+                    its += i
+                    secs += wall
+                kind = "reference"
+                sample = ("%d soundings (0..%d of the workload) x first %d iterations per step, one process per core: the unmodified "
+                          "reference from baseline/_ref (Inference1D.accept_reject + update, numba forward kernels)" % (n_chains, n_chains - 1, ref_iters))
+            except Exception as e:   # the reference failed to import / run on this box: fall back to the port, say so
+                sys.stderr.write("reference arm: live reference failed (%r); timing the C port instead\n" % (e,))
+                live = None
+        # the C restatement: the arm itself when the reference cannot run, a side figure otherwise
+        max_it = 4000  # bounded sample: first 4000 iterations of `cores` chains per step (~2-4 s per step)
+        p_its, p_secs = 0.0, 0.0
+        for _ in range(args.warmup if live is None else 1):
             for k in kinds:
                 cpu_sample(args.chains, n_chains, 500, pool, k)
-        its, secs = 0.0, 0.0
-        for _ in range(args.steps):
+        for _ in range(args.steps if live is None else 1):
             for k in kinds:  # a mixed line: the same number of soundings of each kind
                 i, s = cpu_sample(args.chains, n_chains, max_it, pool, k)
-                its += i
-                secs += s
+                p_its += i
+                p_secs += s
+        port = {"value": p_its / p_secs, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d chains (soundings 0..%d of the workload) x first %d iterations per step, one process per core, C restatement (oracle/)" % (n_chains, n_chains - 1, max_it)}
+        if live is None:
+            its, secs, kind, sample = p_its, p_secs, "port", port["sample"]
     value = its / secs
-    sample = "%d chains (soundings 0..%d of the workload) x first %d iterations per step, one process per core" % (n_chains, n_chains - 1, max_it)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if kind == "reference":
+        line["cpu_port"] = port
     print(json.dumps(line))
 
 
@@ -237,11 +296,46 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def forward_only_block(ops, system, dev, precision, B=262144):
+    """Throughput of the standalone forward / forward+Jacobian operators (gbp_fdem_forward / gbp_fdem_sensitivity, or the
+    time-domain twins) at L = 3, 10, 30 layers: B soundings per launch resident in HBM, kernel time from the library's
+    CUDA events on the launching stream (best of 3 after one warm-up), with the SURVEY 8(d) flop and special-function
+    counts against the peaks measured on this device.  "10-layer RESOLVE" of the north-star target is the L = 10 row."""
+    import torch
+    rng = np.random.default_rng(99)
+    fp32_peak, mufu_peak = ops.measure_peaks()
+    out = {"soundings_per_launch": B, "precision": "fp%d" % precision, "rows": []}
+    sig = torch.tensor(10.0 ** rng.uniform(-3.0, 0.0, (B, 30)), device=dev)
+    thk = torch.tensor(np.exp(rng.uniform(np.log(1.0), np.log(20.0), (B, 30))), device=dev)
+    alt = torch.tensor(rng.uniform(25.0, 45.0, B), device=dev)
+    for L in (3, 10, 30):
+        nl = torch.full((B,), L, dtype=torch.int32, device=dev)
+        row = {"layers": L}
+        for sens in (False, True):
+            best = None
+            for rep in range(4):
+                ops.forward(system, nl, sig, thk, alt, precision=precision, sensitivity=sens)
+                torch.cuda.synchronize(dev)
+                if rep:
+                    best = ops.last_kernel_ms() if best is None else min(best, ops.last_kernel_ms())
+            key = "forward_jacobian" if sens else "forward"
+            per_s = B / (best * 1e-3)
+            row[key + "_per_s"] = per_s
+            row[key + "_ms"] = best
+            if not sens:
+                row["fp32_frac"] = ops.flops_per_forward(system, L) * per_s / 1e12 / fp32_peak
+                row["mufu_frac"] = ops.mufu_per_forward(system, L) * per_s / 1e9 / mufu_peak
+        out["rows"].append(row)
+    out["note"] = ("flops per forward = filter points x (75 L + 39) (SURVEY 8(d)); the sampler's chains hold 2-3 layers on these data "
+                   "(the reference's own chains: mean 2.1), so its evals/s sit between the L = 3 forward and forward+Jacobian rows")
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from geobipy_b200 import _lib, ops
-    from geobipy_b200.parallel import gather_to_rank0, summarise_hitmap
+    from geobipy_b200.parallel import Collator, summarise_hitmap
     from geobipy_b200.synthetic import synthetic_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,13 +368,39 @@ def run_b200_arm(args):
     tdt = {np.int32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}
     buffers = {n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]], device=dev) for n in outputs}
     iters_dev = torch.zeros((), dtype=torch.float64, device=dev)
-    kernel_ms = []
+    grids = ops.posterior_grids(opt, 1.0)
+    ln_edges = torch.tensor(np.log(grids["sigma_edges"]), device=dev)
+    k_ev, c_ev = [], []   # CUDA events on the launching stream: sampler kernel / collation of every timed step
+    collator = [None]
+
+    def collate(r):
+        """End-of-run collation of a step (BASELINE configs[2]): posterior summaries on the device
+        (gbp_summarise_hitmap), then ONE gather of the packed per-sounding rows to rank 0 over NCCL."""
+        summ = summarise_hitmap(r["hitmap"], ln_edges)
+        summ = {k: (v + torch.log(r["scalars"][:, _lib.S_HALFSPACE]).unsqueeze(1)) for k, v in summ.items()}
+        summ["edges_hist"] = r["edges_hist"]
+        summ["scalars"] = r["scalars"]
+        if world > 1:
+            if collator[0] is None:   # preallocated send / receive buffers; warm_up() creates the NCCL p2p channels
+                collator[0] = Collator(summ, world * B)
+                collator[0].warm_up()
+            return collator[0].gather(summ)
+        return summ
 
     def step(i, count=True):
+        if count:
+            k_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            c_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            k_ev[-1][0].record()
         r = ops.rjmcmc_run(system, opt, d_data, t_alt, seed=SEED + i, first_index=first, precision=args.precision,
                            outputs=outputs, buffers=buffers)
         if count:
+            k_ev[-1][1].record()
             iters_dev.add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+            c_ev[-1][0].record()
+        collate(r)
+        if count:
+            c_ev[-1][1].record()
         return r
 
     def barrier():
@@ -288,7 +408,7 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 1)):   # (the first collation also builds the Collator and warms its channels)
         step(1000 + i, count=False)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -306,9 +426,12 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     iters = iters_dev.clone().reshape(1)
-    last_kernel_ms = ops.last_kernel_ms()
+    # the dominant kernel: mean duration and mean units over the timed launches of this rank
+    mean_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    mean_iters = float(iters_dev.item()) / max(args.steps, 1)
+    collate_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in c_ev]))], dtype=torch.float64, device=dev)
     last_iters = float(res["scalars"][:, _lib.S_TOTAL_ITER].sum().item())
-    n_spec = float(ops.debug_counters()[8]) / max(args.steps + args.warmup, 1)  # per launch (all launches are alike)
+    n_spec = float(ops.debug_counters()[8]) / max(args.steps + max(args.warmup, 1), 1)  # per launch (all launches are alike)
     n_fwd = float(res["scalars"][:, _lib.S_N_FORWARD].sum().item())
     n_sens = float(res["scalars"][:, _lib.S_N_SENS].sum().item())
     mean_k = float((res["ncells_hist"].sum(dim=0).double() * torch.arange(opt.max_layers + 1, device=dev)).sum().item()
@@ -317,26 +440,17 @@ def run_b200_arm(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(iters, op=dist.ReduceOp.SUM)
+        dist.all_reduce(collate_ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     total_iters = float(iters.item())
     value = total_iters / (total_ms * 1e-3)
+    gather_ms = float(collate_ms.item())
+    gather_bytes = collator[0].bytes_per_rank if collator[0] is not None else 0
 
-    # end-of-run collation (BASELINE configs[2]): one gather of posterior summaries to rank 0 over NCCL
-    gather_ms = None
-    if world > 1:
-        grids = ops.posterior_grids(opt, 1.0)
-        ln_edges = torch.tensor(np.log(grids["sigma_edges"]), device=dev)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        summ = summarise_hitmap(res["hitmap"], ln_edges)
-        summ = {k: (v + torch.log(res["scalars"][:, _lib.S_HALFSPACE]).unsqueeze(1)) for k, v in summ.items()}
-        summ["edges_hist"] = res["edges_hist"]
-        summ["scalars"] = res["scalars"]
-        gather_to_rank0(summ, world * B)
-        g1.record()
-        barrier()
-        gather_ms = g0.elapsed_time(g1)
+    # forward-only operators ("report also raw kernel forwards/s for the forward-only op")
+    forward_only = None
+    if rank == 0 and not args.no_forward_only:
+        forward_only = forward_only_block(ops, system, dev, args.precision)
 
     # e2e: the public host-buffer API, pinned host memory, copies inside the timed region
     e2e = None
@@ -380,7 +494,7 @@ def run_b200_arm(args):
         # algorithmic HBM bytes per iteration = 8 N_z + 8 (L-1) + 8 (1 + 2 S) + 9, S = 1 system
         n_sys = 2 if wl.tdem else 1
         bytes_per_iter = 8.0 * nz + 8.0 * max(mean_k - 1.0, 0.0) + 8.0 * (1.0 + 2.0 * n_sys) + 9.0
-        achieved = bytes_per_iter * last_iters / (last_kernel_ms * 1e-3) / 1e9
+        achieved = bytes_per_iter * mean_iters / (mean_kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
@@ -402,14 +516,15 @@ def run_b200_arm(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "kernel": "gbp::rjmcmc_kernel<%s,%d,%s>" % ("float" if args.precision == 32 else "double", 48 if wl.tdem else 12, "TDEM" if wl.tdem else "FDEM"),
-                         "kernel_ms": last_kernel_ms, "units_per_launch": last_iters, "bytes_per_unit": bytes_per_iter,
+                         "kernel_ms": mean_kernel_ms, "units_per_launch": mean_iters, "bytes_per_unit": bytes_per_iter,
+                         "kernel_ms_is": "mean over the %d timed launches (CUDA events on the launching stream)" % args.steps,
                          "peak_source": peak_src,
                          "note": "BASELINE.json asks for the HBM fraction; this path is bound by scalar FP/SFU issue and latency, not by HBM (SURVEY.md 8(d))"},
-            "roofline_compute": {"bound": "fp32-issue", "achieved": flops / (last_kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "roofline_compute": {"bound": "fp32-issue", "achieved": flops * (mean_iters / last_iters) / (mean_kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                  "flops_per_forward": fpf, "forward_equivalents_per_launch": fwd_equiv,
                                  "peak": fp32_peak, "peak_source": "measured on this device: 8 independent FFMA chains per thread (gbp_measure_peaks); nominal 148 SM x 128 FMA/clk x 1965 MHz = 74.4",
-                                 "mufu_achieved_gops": mufu / (last_kernel_ms * 1e-3) / 1e9, "mufu_peak_gops": mufu_peak,
-                                 "mufu_frac": mufu / (last_kernel_ms * 1e-3) / 1e9 / mufu_peak},
+                                 "mufu_achieved_gops": mufu * (mean_iters / last_iters) / (mean_kernel_ms * 1e-3) / 1e9, "mufu_peak_gops": mufu_peak,
+                                 "mufu_frac": mufu * (mean_iters / last_iters) / (mean_kernel_ms * 1e-3) / 1e9 / mufu_peak},
             "speculation": {"helpers_per_chain_max": int(os.environ.get("GBP_SPEC_HELPERS", "12")),
                             "iterations_committed_from_speculation": n_spec / last_iters,
                             "note": "idle warps evaluate future iterations of running chains; results bit-identical with it off (tests)"},
@@ -417,16 +532,38 @@ def run_b200_arm(args):
                             "jacobians_per_iteration": n_sens / last_iters, "burned_in_fraction": burned / B},
         }
         line["roofline_compute"]["frac"] = line["roofline_compute"]["achieved"] / line["roofline_compute"]["peak"]
-        if gather_ms is not None:
+        line["collation"] = {"ms_per_step": gather_ms, "inside_timed_region": True, "bytes_per_rank": int(gather_bytes),
+                             "what": "gbp_summarise_hitmap (mean, p5/p50/p95 per depth cell) + edges histogram + scalars"
+                                     + (", packed and gathered to rank 0 with one NCCL collective (warm channels)" if world > 1 else "")}
+        if world > 1:
             line["gather_ms"] = gather_ms
+        if forward_only is not None:
+            line["forward_only"] = forward_only
         if world == 1 and not args.no_cpu_baseline:
             import multiprocessing as mp
+            for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+                os.environ[k] = "1"
             cores = os.cpu_count() or 1
             with mp.get_context("spawn").Pool(cores) as pool:
                 cpu_sample(args.chains, cores, 200, pool, args.workload)
                 its, secs = cpu_sample(args.chains, cores, 0 if not wl.tdem else 4000, pool, args.workload)
-            line["cpu_baseline"] = {"value": its / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d chains (soundings 0..%d of the workload) %s, one process per core, C restatement of the reference (oracle/)" % (cores, cores - 1, "run to termination" if not wl.tdem else "x first 4000 iterations")}
+                line["cpu_baseline"] = {"value": its / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": "%d chains (soundings 0..%d of the workload) %s, one process per core, C restatement of the reference (oracle/)" % (cores, cores - 1, "run to termination" if not wl.tdem else "x first 4000 iterations")}
+                # the reference's OWN NumPy/Numba path on this box's host cores, in the same run
+                if _ref_live() is not None and not wl.tdem:
+                    try:
+                        reference_sample(pool, cores, 30)                 # import + numba compilation in every worker
+                        i1, _, t1 = reference_sample(pool, 1, 1500)       # one core
+                        ia, wa, _ = reference_sample(pool, cores, 400)    # all cores
+                        line["cpu_baseline_reference"] = {
+                            "kind": "reference", "unit": UNIT, "one_core": i1 / t1, "all_cores": ia / wa, "cores": cores,
+                            "sample": "unmodified reference from baseline/_ref (Inference1D.accept_reject + update, numba kernels): "
+                                      "sounding 0 x 1500 iterations on one core; %d soundings x 400 iterations, one process per core" % cores}
+                    except Exception as e:
+                        line["cpu_baseline_reference"] = {"unavailable": repr(e)[:200]}
+                else:
+                    line["cpu_baseline_reference"] = {"unavailable": "time-domain forward of the reference (gatdaem1d) is absent" if wl.tdem
+                                                      else "baseline/_ref is not importable on this machine"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -1,9 +1,11 @@
 #!/bin/bash
-# round-2 GPU check: -m gpu suite, smoke, one short bench line.  Logs under gpurun_out/.
+# round-2 GPU check: -m gpu suite, smoke, the bench line of both arms.  Logs under gpurun_out/.
 mkdir -p gpurun_out
 TAG=${1:-r02a}
 python -m pytest tests -m gpu -x -q -s > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
 tail -5 gpurun_out/${TAG}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
-cat gpurun_out/${TAG}_bench.json | head -c 1200
+python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json | head -c 1500
+python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"
+cat gpurun_out/${TAG}_bench_ref.json | head -c 600

@@ -1,5 +1,6 @@
-"""CPU checks of bench.py's contract: the reference arm (the C restatement on the host cores) runs without a GPU and
-prints one JSON line with the keys the driver reads."""
+"""CPU checks of bench.py's contract: the reference arm (the unmodified reference from baseline/_ref when it is
+importable, else the C restatement, on the host cores) runs without a GPU and prints one JSON line with the keys the
+driver reads."""
 import json
 import os
 import subprocess
@@ -12,10 +13,10 @@ REQUIRED = ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
             "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e")
 
 
-@pytest.mark.parametrize("workload", ["resolve", "skytem"])
-def test_reference_arm_json_line(workload):
+@pytest.mark.parametrize("workload,extra", [("resolve", ["--port"]), ("skytem", [])])
+def test_reference_arm_json_line(workload, extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
-                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--steps", "1", "--warmup", "1"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -33,3 +34,19 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_runs_the_unmodified_reference_when_installed():
+    """With baseline/_ref present (the offline pip --target install of the reference) the arm times
+    the reference's own Inference1D loop; without it the same command falls back to the C port."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")][0])
+    for k in REQUIRED:
+        assert k in d, k
+    have = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "geobipy", "src")) or os.path.isdir("/root/reference/geobipy/src")
+    assert d["cpu_baseline"]["kind"] == ("reference" if have else "port")
+    if have:   # the Python reference runs ~100-130 iterations per second per core; the port rides along
+        assert 20.0 < d["value"] / d["cpu_baseline"]["cores"] < 2000.0 and d["cpu_port"]["kind"] == "port"
+        assert d["cpu_port"]["value"] > d["value"]
