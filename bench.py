@@ -369,7 +369,7 @@ def run_b200_arm(args):
     buffers = {n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]], device=dev) for n in outputs}
     iters_dev = torch.zeros((), dtype=torch.float64, device=dev)
     grids = ops.posterior_grids(opt, 1.0)
-    ln_edges = torch.tensor(np.log(grids["sigma_edges"]), device=dev)
+    ln_edges = np.log(grids["sigma_edges"])   # host edges: the collation never synchronises the stream
     k_ev, c_ev = [], []   # CUDA events on the launching stream: sampler kernel / collation of every timed step
     collator = [None]
 
@@ -428,6 +428,10 @@ def run_b200_arm(args):
     iters = iters_dev.clone().reshape(1)
     # the dominant kernel: mean duration and mean units over the timed launches of this rank
     mean_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    if os.environ.get("GBP_BENCH_TRACE"):   # where the step's time goes, on the stream's own clock
+        tl = [("k%d" % i, ev0.elapsed_time(a), ev0.elapsed_time(b)) for i, (a, b) in enumerate(k_ev)]
+        tl += [("c%d" % i, ev0.elapsed_time(a), ev0.elapsed_time(b)) for i, (a, b) in enumerate(c_ev)]
+        sys.stderr.write("trace rank %d: %s total %.1f\n" % (rank, sorted(tl, key=lambda x: x[1]), ev0.elapsed_time(ev1)))
     mean_iters = float(iters_dev.item()) / max(args.steps, 1)
     collate_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in c_ev]))], dtype=torch.float64, device=dev)
     last_iters = float(res["scalars"][:, _lib.S_TOTAL_ITER].sum().item())

@@ -487,7 +487,10 @@ class Inference1D:
         # best_datapoint: the datapoint at the highest-posterior state (errors, height, predicted data of best_model)
         import copy
         bdp = copy.copy(dp)
-        bdp.predictedData = dp.predictedData.copy()
+        if self._tdem:
+            bdp.predicted_secondary_field = dp.predicted_secondary_field.copy()
+        else:
+            bdp.predictedData = dp.predictedData.copy()
         bdp.relative_error = StatArray(np.atleast_1d(self.best_relative_error), "Relative error")
         bdp.additive_error = StatArray(np.atleast_1d(self.best_additive_error), "Additive error")
         if o.solve_height:

@@ -113,16 +113,22 @@ def summarise_hitmap(hitmap, sigma_edges_ln, percentiles=(5.0, 50.0, 95.0)):
         from . import ops
         # sigma_edges_ln: [n_sig + 1] (shared) or [B, n_sig + 1] (per sounding: the bins are centred on each sounding's
         # best half-space); uniform bins of one common width either way (Model.set_posteriors, Model.py:666-684)
-        e = sigma_edges_ln.to(hitmap.device, torch.float64)
-        lo = e[..., 0] if e.dim() == 2 else e[0].expand(hitmap.shape[0])
-        dx = float((e[..., -1] - e[..., 0]).reshape(-1)[0]) / (e.shape[-1] - 1)
+        if isinstance(sigma_edges_ln, np.ndarray):   # host edges: no device round trip (the caller's stream keeps running)
+            eh = np.asarray(sigma_edges_ln, dtype=np.float64)
+            dx = float((eh[..., -1] - eh[..., 0]).reshape(-1)[0]) / (eh.shape[-1] - 1)
+            lo = torch.as_tensor(np.ascontiguousarray(eh[..., 0]).reshape(-1), device=hitmap.device)
+            lo = lo if eh.ndim == 2 else lo.expand(hitmap.shape[0])
+        else:
+            e = sigma_edges_ln.to(hitmap.device, torch.float64)
+            lo = e[..., 0] if e.dim() == 2 else e[0].expand(hitmap.shape[0])
+            dx = float((e[..., -1] - e[..., 0]).reshape(-1)[0]) / (e.shape[-1] - 1)
         mean, pct = ops.summarise_hitmap(hitmap.to(torch.int32).contiguous(), lo.contiguous(), dx, percentiles)
         out = {"mean": mean}
         for i, p in enumerate(percentiles):
             out["p%g" % p] = pct[i]
         return out
     h = hitmap.to(torch.float64)
-    sigma_edges_ln = sigma_edges_ln.to(torch.float64)
+    sigma_edges_ln = torch.as_tensor(sigma_edges_ln).to(torch.float64)
     centres = 0.5 * (sigma_edges_ln[..., 1:] + sigma_edges_ln[..., :-1])
     if centres.dim() == 1:
         centres = centres.unsqueeze(0).expand(h.shape[0], -1)
