@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem", "mixed"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="streams consecutive steps alternate over (1 = one batch at a time)")
     ap.add_argument("--no-forward-only", action="store_true", help="skip the forward-only operator throughput block")
     ap.add_argument("--port", action="store_true", help="--impl reference: time the C restatement even when baseline/_ref is importable")
     return ap.parse_args()
@@ -100,6 +101,9 @@ def workload_config(args, world):
             "forward_precision": "fp%d" % args.precision,
             "l2": "no flush needed: each step rewrites %.1f GB of posterior arrays per GPU (> 126 MB L2)"
                   % (args.soundings * (250 * nd * 4 + 2 * args.chains * 9) / 1e9),
+            "pipelining": ("consecutive steps (independent batches) alternate over %d CUDA streams with separate result buffers: "
+                           "a batch's tail of long chains overlaps the start of the next batch" % args.streams) if args.streams > 1
+                          else "one batch at a time",
         }
     return {
         "workload": "BASELINE configs[1]: %d synthetic RESOLVE FDEM soundings per GPU (6 freq, 12 channels), "
@@ -109,6 +113,9 @@ def workload_config(args, world):
         "forward_precision": "fp%d" % args.precision,
         "l2": "no flush needed: each step rewrites %.1f GB of posterior arrays per GPU (> 126 MB L2)"
               % (args.soundings * (250 * 440 * 4 + 2 * args.chains * 9) / 1e9),
+        "pipelining": ("consecutive steps (independent batches) alternate over %d CUDA streams with separate result buffers: "
+                       "a batch's tail of long chains overlaps the start of the next batch" % args.streams) if args.streams > 1
+                      else "one batch at a time",
     }
 
 
@@ -252,7 +259,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.first = gpu_index, None, [], 0
+
+    def mark(self):
+        """The timed region starts here: only samples taken from now on count.  (nvidia-smi is started BEFORE the warm-up:
+        its start-up holds a driver lock for a second or two, which stalled the first timed launch when it ran inside.)"""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -278,7 +290,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -335,7 +347,7 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from geobipy_b200 import _lib, ops
-    from geobipy_b200.parallel import Collator, summarise_hitmap
+    from geobipy_b200.parallel import Collator
     from geobipy_b200.synthetic import synthetic_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -366,41 +378,53 @@ def run_b200_arm(args):
     outputs = ops.DEFAULT_OUTPUTS
     shapes = ops.chain_buffer_shapes(opt, B)
     tdt = {np.int32: torch.int32, np.float64: torch.float64, np.uint8: torch.uint8}
-    buffers = {n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]], device=dev) for n in outputs}
-    iters_dev = torch.zeros((), dtype=torch.float64, device=dev)
+    # Consecutive steps (independent batches, as the flight lines of a survey are) go to alternating streams, each with
+    # its own result buffers: the persistent kernel of step i+1 gets the SMs one by one as the CTAs of step i run out of
+    # chains, so the tail of a batch - a few long chains on a few SMs - overlaps the bulk of the next.  --streams 1 =
+    # strictly one batch at a time.
+    ns = max(1, args.streams)
+    main = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(ns)] if ns > 1 else [main]
+    bufsets = [{n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]], device=dev) for n in outputs} for _ in range(ns)]
+    iters_part = [torch.zeros((), dtype=torch.float64, device=dev) for _ in range(ns)]
     grids = ops.posterior_grids(opt, 1.0)
-    ln_edges = np.log(grids["sigma_edges"])   # host edges: the collation never synchronises the stream
+    ln_edges = np.log(grids["sigma_edges"])
+    sig_lo = torch.full((B,), float(ln_edges[0]), dtype=torch.float64, device=dev)   # bins relative to each sounding's half-space
+    sig_dx = float(ln_edges[-1] - ln_edges[0]) / (ln_edges.size - 1)
     k_ev, c_ev = [], []   # CUDA events on the launching stream: sampler kernel / collation of every timed step
-    collator = [None]
+    collators = [None] * ns
 
-    def collate(r):
+    def collate(r, j):
         """End-of-run collation of a step (BASELINE configs[2]): posterior summaries on the device
         (gbp_summarise_hitmap), then ONE gather of the packed per-sounding rows to rank 0 over NCCL."""
-        summ = summarise_hitmap(r["hitmap"], ln_edges)
-        summ = {k: (v + torch.log(r["scalars"][:, _lib.S_HALFSPACE]).unsqueeze(1)) for k, v in summ.items()}
+        # (bin edges resident on the device: nothing here copies from the host or waits for the stream)
+        mean, pct = ops.summarise_hitmap(r["hitmap"], sig_lo, sig_dx, (5.0, 50.0, 95.0))
+        ln_ref = torch.log(r["scalars"][:, _lib.S_HALFSPACE]).unsqueeze(1)
+        summ = {"mean": mean + ln_ref, "p5": pct[0] + ln_ref, "p50": pct[1] + ln_ref, "p95": pct[2] + ln_ref}
         summ["edges_hist"] = r["edges_hist"]
         summ["scalars"] = r["scalars"]
         if world > 1:
-            if collator[0] is None:   # preallocated send / receive buffers; warm_up() creates the NCCL p2p channels
-                collator[0] = Collator(summ, world * B)
-                collator[0].warm_up()
-            return collator[0].gather(summ)
+            if collators[j] is None:   # preallocated send / receive buffers; warm_up() creates the NCCL p2p channels
+                collators[j] = Collator(summ, world * B)
+                collators[j].warm_up()
+            return collators[j].gather(summ)
         return summ
 
-    def step(i, count=True):
-        if count:
-            k_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
-            c_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
-            k_ev[-1][0].record()
-        r = ops.rjmcmc_run(system, opt, d_data, t_alt, seed=SEED + i, first_index=first, precision=args.precision,
-                           outputs=outputs, buffers=buffers)
-        if count:
-            k_ev[-1][1].record()
-            iters_dev.add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
-            c_ev[-1][0].record()
-        collate(r)
-        if count:
-            c_ev[-1][1].record()
+    def step(i, count=True, j=0):
+        with torch.cuda.stream(streams[j]):
+            if count:
+                k_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                c_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                k_ev[-1][0].record()
+            r = ops.rjmcmc_run(system, opt, d_data, t_alt, seed=SEED + i, first_index=first, precision=args.precision,
+                               outputs=outputs, buffers=bufsets[j])
+            if count:
+                k_ev[-1][1].record()
+                iters_part[j].add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+                c_ev[-1][0].record()
+            collate(r, j)
+            if count:
+                c_ev[-1][1].record()
         return r
 
     def barrier():
@@ -408,34 +432,62 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 1)):   # (the first collation also builds the Collator and warms its channels)
-        step(1000 + i, count=False)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # warm-up: one batch at a time (also builds the Collators and warms their channels); its launches, timed alone with
+    # events on their stream, give the duration of ONE launch that does not share the machine (roofline.kernel_ms_alone)
+    alone_ev = []
+    for i in range(max(args.warmup, ns)):
+        j = i % ns
+        torch.cuda.synchronize()
+        with torch.cuda.stream(streams[j]):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+        # (exactly the code path of a timed step: a kernel used for the first time inside the timed region is loaded
+        # lazily, and loading waits for the running persistent kernel to finish - that serialised the first two launches)
+        r = step(1000 + i, count=True, j=j)
+        with torch.cuda.stream(streams[j]):
+            a1.record()
+        alone_ev.append((a0, a1, r))
+    torch.cuda.synchronize()
+    k_ev.clear()
+    c_ev.clear()
+    for x in iters_part:
+        x.zero_()
+    alone_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in alone_ev[-2:]]))
+    barrier()
     launches0 = ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
+    sampler.mark()
+    ev0.record(main)
+    for st in streams:
+        st.wait_event(ev0)
+    host_t = [time.perf_counter()]
     for i in range(args.steps):
-        res = step(i)
-    ev1.record()
+        res = step(i, j=i % ns)
+        host_t.append(time.perf_counter())
+    for st in streams:
+        main.wait_stream(st)
+    ev1.record(main)
     barrier()
     launches = ops.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    iters_dev = torch.stack(iters_part).sum()
     iters = iters_dev.clone().reshape(1)
-    # the dominant kernel: mean duration and mean units over the timed launches of this rank
-    mean_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
-    if os.environ.get("GBP_BENCH_TRACE"):   # where the step's time goes, on the stream's own clock
+    # the dominant kernel: timed region / launches (launches overlap when ns > 1) and mean units over the timed launches
+    mean_kernel_ms = float(ms.item()) / max(args.steps, 1) if ns > 1 else float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    if os.environ.get("GBP_BENCH_TRACE"):   # where the step's time goes, on the streams' own clocks
         tl = [("k%d" % i, ev0.elapsed_time(a), ev0.elapsed_time(b)) for i, (a, b) in enumerate(k_ev)]
         tl += [("c%d" % i, ev0.elapsed_time(a), ev0.elapsed_time(b)) for i, (a, b) in enumerate(c_ev)]
-        sys.stderr.write("trace rank %d: %s total %.1f\n" % (rank, sorted(tl, key=lambda x: x[1]), ev0.elapsed_time(ev1)))
+        sys.stderr.write("trace rank %d: %s total %.1f host enqueue done at %s ms\n" % (
+            rank, sorted(tl, key=lambda x: x[1]), ev0.elapsed_time(ev1), [round(1e3 * (x - host_t[0]), 1) for x in host_t[1:]]))
     mean_iters = float(iters_dev.item()) / max(args.steps, 1)
     collate_ms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in c_ev]))], dtype=torch.float64, device=dev)
     last_iters = float(res["scalars"][:, _lib.S_TOTAL_ITER].sum().item())
-    n_spec = float(ops.debug_counters()[8]) / max(args.steps + max(args.warmup, 1), 1)  # per launch (all launches are alike)
+    n_spec = float(ops.debug_counters()[8]) / max(args.steps + max(args.warmup, ns), 1)  # per launch (all launches are alike)
     n_fwd = float(res["scalars"][:, _lib.S_N_FORWARD].sum().item())
     n_sens = float(res["scalars"][:, _lib.S_N_SENS].sum().item())
     mean_k = float((res["ncells_hist"].sum(dim=0).double() * torch.arange(opt.max_layers + 1, device=dev)).sum().item()
@@ -449,7 +501,7 @@ def run_b200_arm(args):
     total_iters = float(iters.item())
     value = total_iters / (total_ms * 1e-3)
     gather_ms = float(collate_ms.item())
-    gather_bytes = collator[0].bytes_per_rank if collator[0] is not None else 0
+    gather_bytes = collators[0].bytes_per_rank if collators[0] is not None else 0
 
     # forward-only operators ("report also raw kernel forwards/s for the forward-only op")
     forward_only = None
@@ -461,21 +513,35 @@ def run_b200_arm(args):
     if not args.no_e2e:
         h_data = d_data.cpu().numpy()
         h_alt = t_alt.cpu().numpy()
-        hb = {n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]]).pin_memory().numpy() for n in outputs}
+        ne = max(1, min(ns, 2))   # calls in flight: the library keeps two sets of device buffers, each with its own stream
+        hbs = [{n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]]).pin_memory().numpy() for n in outputs} for _ in range(ne)]
         h2d = h_data.nbytes + h_alt.nbytes
-        d2h = sum(v.nbytes for v in hb.values())
-        for b in buffers.values():
-            b.resize_(0)  # free the device-resident result buffers: the host path allocates its own
-        del buffers, res
+        d2h = sum(v.nbytes for v in hbs[0].values())
+        for bs in bufsets:
+            for b in bs.values():
+                b.resize_(0)  # free the device-resident result buffers: the host path allocates its own
+        del bufsets, res, alone_ev, r
         torch.cuda.empty_cache()
-        n_e2e = max(1, min(args.steps, 2))
+        n_e2e = max(ne, min(args.steps, 4))
+
+        def host_step(i):
+            rr = ops.rjmcmc_run(system, opt, h_data, h_alt, seed=SEED + i, first_index=first, precision=args.precision,
+                                device=local_rank, outputs=outputs, buffers=hbs[i % ne])
+            return float(rr["scalars"][:, _lib.S_TOTAL_ITER].sum())
+        from concurrent.futures import ThreadPoolExecutor
         barrier()
         t0 = time.perf_counter()
-        e_iters = 0.0
-        for i in range(n_e2e):
-            r = ops.rjmcmc_run(system, opt, h_data, h_alt, seed=SEED + i, first_index=first, precision=args.precision,
-                               device=local_rank, outputs=outputs, buffers=hb)
-            e_iters += float(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+        if ne > 1:   # two host threads, as a survey driver feeding consecutive flight lines would: ctypes drops the GIL
+            with ThreadPoolExecutor(ne) as ex:
+                # step i reuses the host buffers of step i - ne: submit it only when that one is done
+                futs = []
+                for i in range(n_e2e):
+                    if i >= ne:
+                        futs[i - ne].result()
+                    futs.append(ex.submit(host_step, i))
+                e_iters = sum(f.result() for f in futs)
+        else:
+            e_iters = sum(host_step(i) for i in range(n_e2e))
         torch.cuda.synchronize()
         el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         ei = torch.tensor([e_iters], dtype=torch.float64, device=dev)
@@ -483,8 +549,9 @@ def run_b200_arm(args):
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
             dist.all_reduce(ei, op=dist.ReduceOp.SUM)
         e2e = {"value": float(ei.item()) / float(el.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "api": "geobipy_b200.ops.rjmcmc_run(numpy) -> gbp_rjmcmc_run_host (pinned host buffers)"}
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e, "calls_in_flight": ne,
+               "api": "geobipy_b200.ops.rjmcmc_run(numpy) -> gbp_rjmcmc_run_host (pinned host buffers)"
+                      + (", consecutive steps issued from %d host threads" % ne if ne > 1 else "")}
 
     if rank == 0:
         peaks = {}
@@ -521,7 +588,9 @@ def run_b200_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "kernel": "gbp::rjmcmc_kernel<%s,%d,%s>" % ("float" if args.precision == 32 else "double", 48 if wl.tdem else 12, "TDEM" if wl.tdem else "FDEM"),
                          "kernel_ms": mean_kernel_ms, "units_per_launch": mean_iters, "bytes_per_unit": bytes_per_iter,
-                         "kernel_ms_is": "mean over the %d timed launches (CUDA events on the launching stream)" % args.steps,
+                         "kernel_ms_is": ("timed region / %d launches (CUDA events; consecutive launches overlap on %d streams)" % (args.steps, ns)) if ns > 1
+                                         else "mean over the %d timed launches (CUDA events on the launching stream)" % args.steps,
+                         "kernel_ms_alone": alone_ms,
                          "peak_source": peak_src,
                          "note": "BASELINE.json asks for the HBM fraction; this path is bound by scalar FP/SFU issue and latency, not by HBM (SURVEY.md 8(d))"},
             "roofline_compute": {"bound": "fp32-issue", "achieved": flops * (mean_iters / last_iters) / (mean_kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",

@@ -88,7 +88,7 @@ class ChainBuffersC(ctypes.Structure):
 # every symbol include/geobipy_b200.h declares
 EXPORTS = (
     "gbp_version", "gbp_last_error", "gbp_device_count", "gbp_n_depth", "gbp_flops_per_forward",
-    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_kernel_ms_stats", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times",
+    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_kernel_ms_stats", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times", "gbp_debug_progress_times",
     "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host", "gbp_release_host_buffers", "gbp_summarise_hitmap",
@@ -155,6 +155,8 @@ def load():
     lib.gbp_release_host_buffers.restype = i32
     lib.gbp_debug_finish_times.restype = i32
     lib.gbp_debug_finish_times.argtypes = [vp, i32]
+    lib.gbp_debug_progress_times.restype = i32
+    lib.gbp_debug_progress_times.argtypes = [vp, i32]
     lib.gbp_debug_counters.restype = i32
     lib.gbp_debug_counters.argtypes = [vp, i32]
     lib.gbp_measure_peaks.restype = i32

@@ -311,7 +311,7 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
     Q.jstore = scratch + 256;
     Q.finish_ns = nullptr;
     if (std::getenv("GBP_DEBUG_TIMELINE")) {
-        const size_t need = (size_t)(P.B + 1) * sizeof(unsigned long long);
+        const size_t need = ((size_t)(P.B + 1) + (size_t)P.B * 32) * sizeof(unsigned long long);   // + 32 progress stamps per chain
         if (g_finish_cap[dev] < need) {
             if (g_finish[dev]) CK(cudaFree(g_finish[dev]));
             g_finish[dev] = nullptr;
@@ -324,7 +324,11 @@ int launch_chain(const typename SysOf<T, KIND>::dev& sysdev, const T* d_tab, siz
         Q.finish_ns = g_finish[dev];
     }
     // device-side work counter: chains beyond the first wave are claimed dynamically
+#ifdef GBP_STATIC_FIRST_WAVE
     CK(cudaMemcpyAsync(Q.work_counter, &Q.n_warps_total, sizeof(int), cudaMemcpyHostToDevice, st));
+#else
+    CK(cudaMemsetAsync(Q.work_counter, 0, sizeof(int), st));
+#endif
     if (time_begin(dev, st)) return 1;
     kern<<<grid, WARPS * 32, smem, st>>>(sysdev, d_tab, Q);
     g_launches++;
@@ -724,16 +728,19 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
 }  // extern "C"
 
 // Device buffers of the host-pointer sampler entry points are kept between calls (per device, one slot per result
-// array): allocating and freeing 2.5 GB of posterior arrays cost more per call than copying them.
+// array): allocating and freeing 2.5 GB of posterior arrays cost more per call than copying them.  Two arenas per device,
+// each with its own stream: two host threads can have a call in flight at once, and the second call's chains start on
+// the SMs the first call's tail has already left while the first call's results are still on their way to the host.
 struct HostArena {
     void* ptr[16];
     size_t cap[16];
+    cudaStream_t stream;
+    std::mutex mu;
 };
-static HostArena g_arena[MAX_DEV];
-static std::mutex g_host_mu[MAX_DEV];
-static int arena_get(int dev, int slot, size_t bytes, void** out)
+constexpr int N_ARENAS = 2;
+static HostArena g_arena[MAX_DEV][N_ARENAS];
+static int arena_get(HostArena& a, int slot, size_t bytes, void** out)
 {
-    HostArena& a = g_arena[dev];
     if (a.cap[slot] < bytes) {
         if (a.ptr[slot]) cudaFree(a.ptr[slot]);
         a.ptr[slot] = nullptr;
@@ -779,28 +786,38 @@ static int rjmcmc_host_impl(int C, const gbp_options* opt, int B, const double* 
         {(void* const*)&h->height_hist, (void**)&d.height_hist, (size_t)B * opt->n_err_bins * sizeof(int32_t)},
     };
     if (device < 0 || device >= MAX_DEV) return fail("device index out of range");
-    std::lock_guard<std::mutex> lk(g_host_mu[device]);  // the cached device buffers of a device are shared by its callers
+    // the first free arena of the device (a third concurrent caller waits for the second one)
+    HostArena* A = &g_arena[device][0];
+    std::unique_lock<std::mutex> lk(A->mu, std::try_to_lock);
+    if (!lk.owns_lock()) {
+        A = &g_arena[device][1];
+        lk = std::unique_lock<std::mutex>(A->mu);
+    }
+    if (!A->stream) CK(cudaStreamCreateWithFlags(&A->stream, cudaStreamNonBlocking));
+    cudaStream_t st = A->stream;
     double *d_data = nullptr, *d_alt = nullptr;
     int rc = 0, slot = 0;
     for (const Item& it : items) {
         if (*it.host) {
-            if (arena_get(device, slot, it.bytes, it.dev)) return 1;
-            CK(cudaMemsetAsync(*it.dev, 0, it.bytes, nullptr));
+            if (arena_get(*A, slot, it.bytes, it.dev)) return 1;
+            CK(cudaMemsetAsync(*it.dev, 0, it.bytes, st));
         }
         ++slot;
     }
-    if (arena_get(device, 14, (size_t)B * C * sizeof(double), (void**)&d_data)) return 1;
-    if (arena_get(device, 15, (size_t)B * sizeof(double), (void**)&d_alt)) return 1;
-    CK(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    CK(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, nullptr));
-    rc = run(d_data, d_alt, &d);
+    if (arena_get(*A, 14, (size_t)B * C * sizeof(double), (void**)&d_data)) return 1;
+    if (arena_get(*A, 15, (size_t)B * sizeof(double), (void**)&d_alt)) return 1;
+    CK(cudaMemcpyAsync(d_data, data, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_alt, altitude, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = run(d_data, d_alt, &d, (void*)st);
     if (!rc) {
-        cudaError_t e = cudaDeviceSynchronize();
+        cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail(std::string("kernel: ") + cudaGetErrorString(e));
     }
-    if (!rc)
+    if (!rc) {
         for (const Item& it : items)
-            if (*it.host) CK(cudaMemcpy(*it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost));
+            if (*it.host) CK(cudaMemcpyAsync(*it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return rc;
 }
 
@@ -811,9 +828,9 @@ int gbp_rjmcmc_run_host(const gbp_fdem_system* sys, const gbp_options* opt, int 
                         const gbp_chain_buffers* h, int precision, int device)
 {
     return rjmcmc_host_impl(2 * sys->n_freq, opt, B, data, altitude, h, device,
-                            [&](const double* d_data, const double* d_alt, const gbp_chain_buffers* d) {
+                            [&](const double* d_data, const double* d_alt, const gbp_chain_buffers* d, void* st) {
                                 return gbp_rjmcmc_run(sys, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
-                                                      precision, nullptr);
+                                                      precision, st);
                             });
 }
 
@@ -903,16 +920,18 @@ int gbp_opacity_doi(const int32_t* d_range_bins, int B, int n_depth, const int32
 
 int gbp_release_host_buffers(void)
 {
-    for (int dev = 0; dev < MAX_DEV; ++dev) {
-        std::lock_guard<std::mutex> lk(g_host_mu[dev]);
-        for (int s = 0; s < 16; ++s)
-            if (g_arena[dev].ptr[s]) {
-                cudaSetDevice(dev);
-                cudaFree(g_arena[dev].ptr[s]);
-                g_arena[dev].ptr[s] = nullptr;
-                g_arena[dev].cap[s] = 0;
-            }
-    }
+    for (int dev = 0; dev < MAX_DEV; ++dev)
+        for (int a = 0; a < N_ARENAS; ++a) {
+            HostArena& A = g_arena[dev][a];
+            std::lock_guard<std::mutex> lk(A.mu);
+            for (int s = 0; s < 16; ++s)
+                if (A.ptr[s]) {
+                    cudaSetDevice(dev);
+                    cudaFree(A.ptr[s]);
+                    A.ptr[s] = nullptr;
+                    A.cap[s] = 0;
+                }
+        }
     return 0;
 }
 
@@ -925,6 +944,22 @@ int gbp_debug_finish_times(double* out_ms, int n)
     CK(cudaMemcpy(h.data(), g_finish[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     const unsigned long long t0 = h[g_finish_B[dev]];
     for (int i = 0; i < n; ++i) out_ms[i] = (double)(h[i] - t0) * 1e-6;
+    return 0;
+}
+
+int gbp_debug_progress_times(double* out_ms, int n)
+{
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!g_finish[dev] || n > g_finish_B[dev]) return fail("no timeline recorded (set GBP_DEBUG_TIMELINE before the run)");
+    const size_t B = (size_t)g_finish_B[dev];
+    std::vector<unsigned long long> h(B + 1 + 32 * B);
+    CK(cudaMemcpy(h.data(), g_finish[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const unsigned long long t0 = h[B];
+    for (size_t i = 0; i < (size_t)n * 32; ++i) {
+        const unsigned long long v = h[B + 1 + i];
+        out_ms[i] = (v == ~0ull) ? -1.0 : (double)(v - t0) * 1e-6;
+    }
     return 0;
 }
 
@@ -1164,9 +1199,9 @@ int gbp_tdem_rjmcmc_run_host(const gbp_tdem_survey* sv, const gbp_options* opt, 
     for (int b = 0; b < B; ++b)
         if (!(altitude[b] > 0.0)) return fail("Sensor altitude must be above the top of the model");
     return rjmcmc_host_impl(gbp_tdem_n_channels(sv), opt, B, data, altitude, h, device,
-                            [&](const double* d_data, const double* d_alt, const gbp_chain_buffers* d) {
+                            [&](const double* d_data, const double* d_alt, const gbp_chain_buffers* d, void* st) {
                                 return gbp_tdem_rjmcmc_run(sv, opt, B, d_data, d_alt, seed, first_index, max_iterations, d,
-                                                           precision, nullptr);
+                                                           precision, st);
                             });
 }
 

@@ -1854,6 +1854,11 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         if (!do_reset) dwell++;
 
         // ==================================================== Inference1D.infer :650-677 (loop control)
+        if (P.finish_ns && (total & 2047) == 0 && lane == 0) {   // debug timeline: a stamp every 2048 iterations
+            unsigned long long tnow;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+            P.finish_ns[(size_t)P.B + 1 + (size_t)chain * 32 + min(31, total >> 11)] = tnow;
+        }
         total++;
         if (do_reset) {
             int nr = w->ctr[CT_N_RESETS] + 1;
@@ -1988,10 +1993,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     const uint32_t tab_pad = (tab_bytes + 127u) & ~127u;
     const int warp = threadIdx.x >> 5;
     WarpState<R, T, NC, KIND>* ws = reinterpret_cast<WarpState<R, T, NC, KIND>*>(smem + tab_pad) + warp;
-    // persistent: the first wave is dealt round-robin over the CTAs (one CTA per SM) so that a batch smaller
-    // than the machine still spreads evenly; later chains are claimed from a device-side counter
-    int c = warp * gridDim.x + blockIdx.x;
+    // persistent: every chain is claimed from a device-side counter.  Which WARPS take part in the first wave is static
+    // (round-robin over the CTAs, one CTA per SM, so that a batch smaller than the machine still spreads evenly), which
+    // chain each of them gets is not: when this launch overlaps the tail of the previous one on another stream, its CTAs
+    // start one by one as SMs come free, and a CTA that starts late must not sit on chains the others could have run.
     const int lane = threadIdx.x & 31;
+    int c = P.B;
+#ifdef GBP_STATIC_FIRST_WAVE   // A/B build: the first wave dealt statically (chain = warp * grid + CTA), as in round 1
+    c = warp * (int)gridDim.x + (int)blockIdx.x;
+#else
+    if (warp * (int)gridDim.x + (int)blockIdx.x < P.B) {
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(P.work_counter, 1);
+        c = __shfl_sync(FULL, nxt, 0);
+    }
+#endif
     if (threadIdx.x == 0) {
         n_alive = 0;
         n_idle = 0;

@@ -185,6 +185,9 @@ int gbp_debug_counters(unsigned long long *out16, int reset);
 /* with the environment variable GBP_DEBUG_TIMELINE set, the sampler records when each chain of the last launch
  * on the current device finished; out_ms[i] = milliseconds after the start of the kernel (synchronises) */
 int gbp_debug_finish_times(double *out_ms, int n);
+/* the same run's progress stamps: out_ms[i][j] = milliseconds after the start of the kernel at which chain i had done
+ * 2048 j iterations (j = 0 is its start; -1 where it never got there; j = 31 absorbs everything beyond) */
+int gbp_debug_progress_times(double *out_ms, int n);
 /* kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t gbp_launch_count(void);
 /* mean duration [ms] and launch count of the last gbp_rjmcmc_run / forward kernel, measured with CUDA
