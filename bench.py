@@ -437,25 +437,17 @@ def run_b200_arm(args):
         sampler.start()
     # warm-up: one batch at a time (also builds the Collators and warms their channels); its launches, timed alone with
     # events on their stream, give the duration of ONE launch that does not share the machine (roofline.kernel_ms_alone)
-    alone_ev = []
     for i in range(max(args.warmup, ns)):
-        j = i % ns
         torch.cuda.synchronize()
-        with torch.cuda.stream(streams[j]):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
         # (exactly the code path of a timed step: a kernel used for the first time inside the timed region is loaded
         # lazily, and loading waits for the running persistent kernel to finish - that serialised the first two launches)
-        r = step(1000 + i, count=True, j=j)
-        with torch.cuda.stream(streams[j]):
-            a1.record()
-        alone_ev.append((a0, a1, r))
+        r = step(1000 + i, count=True, j=i % ns)
     torch.cuda.synchronize()
+    alone_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev[-2:]]))
     k_ev.clear()
     c_ev.clear()
     for x in iters_part:
         x.zero_()
-    alone_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in alone_ev[-2:]]))
     barrier()
     launches0 = ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -520,7 +512,7 @@ def run_b200_arm(args):
         for bs in bufsets:
             for b in bs.values():
                 b.resize_(0)  # free the device-resident result buffers: the host path allocates its own
-        del bufsets, res, alone_ev, r
+        del bufsets, res, r
         torch.cuda.empty_cache()
         n_e2e = max(ne, min(args.steps, 4))
 

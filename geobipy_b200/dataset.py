@@ -113,6 +113,13 @@ class FdemData:
     def line(self, line_number):
         return np.flatnonzero(self.lineNumber == line_number)
 
+    def subset(self, idx):
+        """The soundings `idx` as a data set of their own (Data.__getitem__ of the reference)."""
+        out = FdemData(self.system)
+        for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data", "std"):
+            setattr(out, k, np.asarray(getattr(self, k))[idx])
+        return out
+
     @property
     def lines(self):
         return np.unique(self.lineNumber)
@@ -290,12 +297,35 @@ class Inference3D:
         self.results = res
         return res
 
-    def save(self, directory):
-        """One `<line>.npz` per flight line (the reference writes one `<line>.h5` per line)."""
+    def save(self, directory, format="h5", precision=_lib.PRECISION_F64, device=0):
+        """One result file per flight line, `<line>.h5` in the reference's HDF5 layout (what `Inference3D.create_hdf5`
+        + every sounding's `Inference1D.writeHdf` leave behind, inversion/Inference3D.py:276-340; `geobipy_b200.hdf`): the
+        file `Inference2D` / `Inference3D` of the reference open for their sections and maps.  The predicted data of every
+        sounding's best model come from ONE call of the forward operator.  `format="npz"` keeps round 1's flat archive
+        (plus the per-line summaries the device computed)."""
         assert self.results is not None, "run infer() first"
         os.makedirs(directory, exist_ok=True)
         r, d = self.results, self.data
         files = []
+        if format in ("h5", "hdf5"):
+            from . import hdf
+            from .tdem import TdemData
+            opt = self.options
+            sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct
+            idx_all = r["index"]
+            k = r["scalars"][:, _lib.S_BEST_K].astype(np.int32)
+            sig = np.where(np.isnan(r["best_sigma"]), 1.0, r["best_sigma"])
+            thk = np.diff(np.where(np.isfinite(r["best_edges"]), r["best_edges"], 0.0), axis=1)
+            thk[thk <= 0.0] = 1.0   # the half-space and the padding: ignored by the operator
+            alt = r["scalars"][:, _lib.S_BEST_HEIGHT] if opt.solve_height else np.asarray(d.z, dtype=np.float64)[idx_all]
+            predicted = ops.forward(sysc, k, sig, thk, alt, precision=precision, device=device)
+            for ln in np.unique(np.asarray(d.lineNumber)[idx_all]):
+                m = np.asarray(d.lineNumber)[idx_all] == ln
+                sub = d.subset(idx_all[m])
+                res = {key: v[m] for key, v in r.items() if isinstance(v, np.ndarray) and v.shape[:1] == m.shape and not key.startswith("summary_")}
+                files.append(hdf.save_line(os.path.join(directory, "%g.h5" % ln), res, opt, sub, predicted[m]))
+            return files
+        assert format == "npz", ValueError("format must be 'h5' or 'npz'")
         for ln in np.unique(d.lineNumber[r["index"]]):
             m = d.lineNumber[r["index"]] == ln
             idx = r["index"][m]

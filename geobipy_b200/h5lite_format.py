@@ -182,14 +182,16 @@ class _Heap:
 def _attr_payload(value, heap):
     """-> (datatype body, dataspace body, data bytes or ('vlen', heap item index))."""
     if isinstance(value, (str, np.str_)):
-        return encode_datatype(_VLEN_STR), encode_dataspace(()), ("vlen", heap.add(str(value).encode("utf-8")))
+        return encode_datatype(_VLEN_STR), encode_dataspace(()), ("vlen", [heap.add(str(value).encode("utf-8"))])
     if isinstance(value, (bytes, np.bytes_)):
         a = np.asarray(value, dtype="S%d" % max(len(value), 1))
     else:
         a = np.asarray(value)
-        if a.dtype.kind == "U":
-            a = np.char.encode(a, "utf-8")
-        elif a.dtype == object:
+        if a.dtype.kind == "U" or (a.dtype == object and all(isinstance(x, str) for x in a.reshape(-1))):
+            # a list / array of str: an array of variable-length UTF-8 strings (what h5py writes; TdemSystem's .stm lines)
+            idx = [heap.add(str(x).encode("utf-8")) for x in a.reshape(-1)]
+            return encode_datatype(_VLEN_STR), encode_dataspace(a.shape), ("vlen", idx)
+        if a.dtype == object:
             raise TypeError("h5lite cannot store attribute value %r" % (value,))
     if a.dtype.byteorder == ">":
         a = a.astype(a.dtype.newbyteorder("<"))
@@ -210,7 +212,7 @@ class _Plan:
         self.children = [] if self.is_dataset else [(k, _Plan(c, heap)) for k, c in node._children.items()]
         n = 0
         for k, (dt, ds, data) in self.attrs:
-            n += 4 + 9 + len(k.encode("utf-8")) + 1 + len(dt) + len(ds) + (16 if isinstance(data, tuple) else len(data))
+            n += 4 + 9 + len(k.encode("utf-8")) + 1 + len(dt) + len(ds) + (16 * len(data[1]) if isinstance(data, tuple) else len(data))
         if self.is_dataset:
             a = node._a
             self.dt, self.ds = encode_datatype(a.dtype), encode_dataspace(a.shape)
@@ -250,8 +252,7 @@ class _Plan:
         for k, (dt, ds, data) in self.attrs:
             kb = k.encode("utf-8") + b"\x00"
             if isinstance(data, tuple):
-                caddr, idx = heap.where[data[1]]
-                data = struct.pack("<IQI", len(heap.items[data[1]]), caddr, idx)
+                data = b"".join(struct.pack("<IQI", len(heap.items[i]), *heap.where[i]) for i in data[1])
             body += _msg(0x0C, struct.pack("<BBHHHB", 3, 0, len(kb), len(dt), len(ds), 0 if kb.isascii() else 1) + kb + dt + ds + data)
         assert len(body) == self.msg_bytes, (len(body), self.msg_bytes)
         head = b"OHDR" + struct.pack("<BBI", 2, 0x02, len(body)) + bytes(body)

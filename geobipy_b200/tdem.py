@@ -59,6 +59,30 @@ def read_stm(filename):
         n_abscissae=int(float(d.get("NumberOfAbsiccaInHankelTransformEvaluation", 21))))
 
 
+def format_stm(d):
+    """A GA-AEM .stm text (list of lines) for a parsed description: `read_stm` of it gives the description back."""
+    L = ["System Begin\n", "\tName = %s\n" % d.get("name", ""), "\tType = Time Domain\n", "\tTransmitter Begin\n",
+         "\t\tNumberOfTurns = %g\n" % d.get("n_turns", 1), "\t\tPeakCurrent   = %g\n" % d.get("peak_current", 1),
+         "\t\tLoopArea      = %g\n" % d.get("loop_area", 1), "\t\tBaseFrequency = %r\n" % float(d["base_frequency"]),
+         "\t\tWaveformDigitisingFrequency = %r\n" % float(d["digitising_frequency"]), "\t\tWaveFormCurrent Begin\n"]
+    L += ["%r\t%r\n" % (float(t), float(c)) for t, c in zip(d["waveform_time"], d["waveform_current"])]
+    L += ["\t\tWaveFormCurrent End\n", "\tTransmitter End\n", "\tReceiver Begin\n",
+          "\t\tNumberOfWindows = %d\n" % len(d["window_start"]), "\t\tWindowWeightingScheme = AreaUnderCurve\n",
+          "\t\tWindowTimes Begin\n"]
+    L += ["%r\t%r\n" % (float(a), float(b)) for a, b in zip(d["window_start"], d["window_end"])]
+    L += ["\t\tWindowTimes End\n"]
+    if len(d.get("filter_cutoff", [])):
+        L += ["\t\tLowPassFilter Begin\n", "\t\t\tCutOffFrequency = %s\n" % " ".join("%r" % float(x) for x in d["filter_cutoff"]),
+              "\t\t\tOrder           = %s\n" % " ".join("%d" % int(x) for x in d["filter_order"]), "\t\tLowPassFilter End\n"]
+    L += ["\tReceiver End\n", "\tForwardModelling Begin\n", "\t\tModellingLoopRadius = %r\n" % float(d.get("loop_radius", 0.0)),
+          "\t\tOutputType = %s\n" % d.get("output_type", "dB/dt"), "\t\tXOutputScaling = %g\n" % d.get("x_scaling", 0),
+          "\t\tYOutputScaling = %g\n" % d.get("y_scaling", 0), "\t\tZOutputScaling = %g\n" % d.get("z_scaling", 1),
+          "\t\tSecondaryFieldNormalisation  =  none\n", "\t\tFrequenciesPerDecade = %d\n" % d.get("frequencies_per_decade", 5),
+          "\t\tNumberOfAbsiccaInHankelTransformEvaluation = %d\n" % d.get("n_abscissae", 21), "\tForwardModelling End\n",
+          "System End\n"]
+    return L
+
+
 class TdemSystem:
     """One time-domain system (TdemSystem_GAAEM): built from an .stm file or a parsed description."""
 
@@ -70,6 +94,10 @@ class TdemSystem:
             definition = read_stm(system_filename)
         self.definition = definition
         self.filename = system_filename
+        self._lines = None
+        if system_filename is not None:
+            with open(system_filename) as f:
+                self._lines = f.readlines()
         self.off_time = 0.5 * (np.asarray(definition["window_start"]) + np.asarray(definition["window_end"]))
         assert np.min(np.diff(self.off_time)) > 0.0 if self.off_time.size > 1 else True, ValueError(
             "Receiver window times must monotonically increase for system " + str(system_filename))
@@ -78,6 +106,12 @@ class TdemSystem:
     @classmethod
     def read(cls, system_filename):
         return cls(system_filename)
+
+    @property
+    def stm_lines(self):
+        """The .stm file line by line - what the reference keeps as `TdemSystem_GAAEM.string` and stores in its result
+        files (`toHdf`, TdemSystem_GAAEM.py:114-118).  A system built from a parsed description is written out again."""
+        return self._lines if self._lines is not None else format_stm(self.definition)
 
     @property
     def nTimes(self):
@@ -307,10 +341,36 @@ class TdemData:
     def nChannels(self):
         return self.data.shape[1]
 
+    def subset(self, idx):
+        """The soundings `idx` as a data set of their own (Data.__getitem__ of the reference)."""
+        out = TdemData(self.system, self.line_number[idx], self.fiducial[idx], self.x[idx], self.y[idx], self.height[idx],
+                       np.asarray(self.elevation)[idx], self.geometry[idx], self.data[idx])
+        if getattr(self, "std", None) is not None:
+            out.std = np.asarray(self.std)[idx]
+        return out
+
     # names the survey driver (dataset.Inference3D) shares with FdemData
     @property
     def z(self):
         return self.height
+
+    def _loop(self, dx, dy, dz, att):
+        n = self.nPoints
+        r = float(self.system[0].definition.get("loop_radius", 0.0))
+        return dict(x=self.x + dx, y=self.y + dy, z=self.height + dz, elevation=np.asarray(self.elevation, dtype=np.float64),
+                    pitch=self.geometry[:, att], roll=self.geometry[:, att + 1], yaw=self.geometry[:, att + 2],
+                    moment=np.ones(n), orientation=np.full(n, 2, dtype=np.int32), radius=np.full(n, r))
+
+    @property
+    def transmitter(self):
+        """Per-sounding transmitter loops as arrays (TdemData.loop_pair.transmitter, a CircularLoops): position = the
+        sounding's, attitude from the tx_* columns, radius = the systems' ModellingLoopRadius, z-directed unit moment."""
+        return self._loop(0.0, 0.0, 0.0, 0)
+
+    @property
+    def receiver(self):
+        g = self.geometry
+        return self._loop(g[:, 3], g[:, 4], g[:, 5], 6)
 
     @property
     def lineNumber(self):

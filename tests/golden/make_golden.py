@@ -11,6 +11,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py bins         # posterior_bins.npz
     python tests/golden/make_golden.py transitions  # transitions.npz
     python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
+    python tests/golden/make_golden.py hdf fdem|fdem_height|tdem   # hdf_layout_<kind>.npz: the reference's own HDF5 result tree
 
 Files written
   resolve_clean.npz       the reference's own known-answer vectors
@@ -602,8 +603,128 @@ def make_height_reset():
     print(rec)
 
 
+def _h5lite_as_h5py():
+    """The reference writes its result files through h5py, which this image lacks: hand it geobipy_b200.h5lite (the same
+    calls over an in-memory tree) under that name, BEFORE the reference is imported."""
+    import types
+    from geobipy_b200 import h5lite
+    m = types.ModuleType("h5py")
+    m.File, m.Group, m.Dataset, m._hl = h5lite.File, h5lite.Group, h5lite.Dataset, h5lite._hl
+    sys.modules["h5py"] = m
+    return h5lite
+
+
+def _dump_tree(f, h5lite):
+    """{path: array} + {path: {kind, dtype, shape, attrs}} of an h5lite tree."""
+    arrays, meta = {}, {}
+
+    def visit(name, obj):
+        attrs = {k: (v if isinstance(v, str) else np.asarray(v).tolist()) for k, v in obj.attrs.items()}
+        if isinstance(obj, h5lite.Dataset):
+            a = np.asarray(obj)
+            meta[name] = dict(kind="dataset", dtype=a.dtype.str, shape=list(a.shape), attrs=attrs)
+            arrays[name] = a
+        else:
+            meta[name] = dict(kind="group", attrs=attrs)
+    f.visititems(visit)
+    return arrays, meta
+
+
+def make_hdf(kind="fdem", n_iter=1200, n_points=3, index=1):
+    """hdf_layout_<kind>.npz: the tree the reference's OWN Inference2D.createHdf / Inference1D.writeHdf code builds
+    (inversion/Inference2D.py:2001-2016, Inference1D.py:1002-1090) for a line of `n_points` soundings with one sounding
+    written at `index`, recorded through h5lite, together with the state of that reference chain in the form of the
+    product's result arrays - what geobipy_b200.hdf must turn into the same tree."""
+    import io
+    import json
+    import contextlib
+    h5lite = _h5lite_as_h5py()
+    height = kind == "fdem_height"
+    if kind == "tdem":
+        kw = _tdem_setup()
+        from geobipy import Inference1D, get_prng
+        from geobipy_b200.synthetic import skytem_noise_std
+        import oracle_py as O
+        tsys = O.make_tdem_system()
+        tc = np.array(tsys.t_centre[:45])
+        edges, sigma, z, noise = synthetic_sounding(2, 400.0, 45)
+        clean = O.tdem_forward(tsys, z, sigma, np.r_[np.diff(edges)[:-1], 1.0])
+        data = clean + noise * skytem_noise_std(clean, tc, (26, 19))
+        kw["n_markov_chains"] = 10000
+        kw["prng"] = get_prng(seed=4242)
+        inf = Inference1D(**kw)
+        dp = _tdem_datapoint(data, z)
+        with contextlib.redirect_stdout(io.StringIO()):
+            inf.initialize(dp)
+    else:
+        _geobipy()
+        data, z, edges, sigma = _observed(1)
+        if height:
+            z = z + HEIGHT_BIAS
+        inf = _initialised_inference(data, z, 10000, 4242, **(HEIGHT_KW if height else {}))
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(n_iter):
+            inf.accept_reject()
+            inf.update()
+    from geobipy import StatArray
+    fid = np.arange(n_points, dtype=np.float64) * 10.0 + 10.0
+    inf.datapoint.fiducial = StatArray(fid[index], "fiducial")
+    inf.datapoint.lineNumber = StatArray(100.0, "Line number")
+    inf.best_datapoint.fiducial = StatArray(fid[index], "fiducial")
+    inf.best_datapoint.lineNumber = StatArray(100.0, "Line number")
+    f = h5lite.File(os.path.join("/tmp", "hdf_layout_%s.h5" % kind), "w")
+    with contextlib.redirect_stdout(io.StringIO()):
+        inf.createHdf(f, add_axis=StatArray(fid, "fiducial"))        # what Inference2D.createHdf does (:2006-2014)
+        StatArray(np.full(n_points, 100.0), "Line number").writeHdf(f, "data/line_number")
+        StatArray(fid, "fiducial").writeHdf(f, "data/fiducial")
+        inf.writeHdf(f, index=index)
+    arrays, meta = _dump_tree(f, h5lite)
+    f.close()
+
+    # the same chain as the product's result arrays (include/geobipy_b200.h gbp_chain_buffers)
+    m, bm, d, bd = inf.model, inf.best_model, inf.datapoint, inf.best_datapoint
+    ml = 30
+    N2 = 2 * inf.n_markov_chains
+
+    def padded(a, n, fill=np.nan):
+        out = np.full(n, fill)
+        a = np.asarray(a, dtype=np.float64).reshape(-1)
+        out[:a.size] = a
+        return out
+    ns = 2 if kind == "tdem" else 1
+    rel_hist = np.stack([np.asarray(d.relative_error.posterior[i].counts if ns > 1 else d.relative_error.posterior.counts, dtype=np.int32) for i in range(ns)])
+    add_hist = np.stack([np.asarray(d.additive_error.posterior[i].counts if ns > 1 else d.additive_error.posterior.counts, dtype=np.int32) for i in range(ns)])
+    state = dict(
+        hitmap=np.asarray(m.values.posterior.counts, dtype=np.int32), edges_hist=np.asarray(m.mesh.edges.posterior.counts, dtype=np.int32),
+        ncells_hist=np.asarray(m.mesh.nCells.posterior.counts, dtype=np.int32), rel_hist=rel_hist if ns > 1 else rel_hist[0],
+        add_hist=add_hist if ns > 1 else add_hist[0],
+        misfit_trace=padded(np.asarray(inf.data_misfit_v), N2, 0.0), accept_trace=padded(np.asarray(inf.acceptance_v), N2, 0.0).astype(np.uint8),
+        best_sigma=padded(bm.values, ml), best_edges=padded(bm.mesh.edges, ml + 1),
+        cur_sigma=padded(m.values, ml), cur_edges=padded(m.mesh.edges, ml + 1),
+        iteration=int(inf.iteration), burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
+        best_iteration=int(inf.best_iteration), best_k=int(bm.nCells.item()), cur_k=int(m.nCells.item()),
+        halfspace=float(inf.halfspace.item()), multiplier=float(inf.multiplier),
+        cur_rel=np.asarray(d.relative_error, dtype=np.float64), cur_add=np.asarray(d.additive_error, dtype=np.float64),
+        best_rel=np.asarray(bd.relative_error, dtype=np.float64), best_add=np.asarray(bd.additive_error, dtype=np.float64),
+        data=np.asarray(d.data, dtype=np.float64), std_best=np.asarray(bd.std, dtype=np.float64),
+        predicted_best=np.asarray(bd.predictedData, dtype=np.float64), z_input=float(z),
+        x=float(d.x), y=float(d.y), elevation=float(d.elevation), fiducial=fid, line_number=100.0, index=index, n_points=n_points)
+    if kind == "tdem":
+        state.update(tx_z=float(np.asarray(bd.transmitter.z).item()), rx_z=float(np.asarray(bd.receiver.z).item()))
+    if height:
+        state.update(height_hist=np.asarray(d.z.posterior.counts, dtype=np.int32), cur_height=float(np.asarray(d.z).item()),
+                     best_height=float(np.asarray(bd.z).item()),
+                     height_edges=np.asarray(d.z.posterior.mesh.edges, dtype=np.float64))
+    out = {"tree/" + k: v for k, v in arrays.items()}
+    out.update({"state/" + k: np.asarray(v) for k, v in state.items()})
+    np.savez_compressed(os.path.join(HERE, "hdf_layout_%s.npz" % kind), meta=json.dumps(meta), **out)
+    print(kind, "tree entries", len(meta), "datasets", len(arrays), "iteration", inf.iteration, "k", state["cur_k"], state["best_k"])
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "hdf":
+        make_hdf(sys.argv[2] if len(sys.argv) > 2 else "fdem")
     if what == "tdem":
         make_tdem()
     if what == "tdem_transitions":

@@ -135,10 +135,26 @@ def test_inference3d_end_to_end(tmp_path, golden_dir, built_lib):
     assert np.array_equal(one["hitmap"][0], r["hitmap"][4])       # (seed, sounding index) fixes the stream
     byfid = Inference3D(d, seed=5).infer(fiducial=4.0, line_number=200.0, n_markov_chains=400, max_iterations=300)
     assert np.array_equal(byfid["scalars"], one["scalars"])
-    files = inv.save(str(tmp_path / "out"))
+    files = inv.save(str(tmp_path / "out"), format="npz")
     assert [os.path.basename(f) for f in files] == ["100.npz", "200.npz"]
     z = np.load(files[1])
     assert z["hitmap"].shape == (3, 250, 440) and list(z["fiducial"]) == [3.0, 4.0, 5.0]
+    # the reference's own output: one HDF5 file per line in the layout of Inference2D.createHdf / Inference1D.writeHdf
+    # (tests/test_hdf.py pins the layout on the reference's own writer and readers)
+    from geobipy_b200 import api, h5lite
+    files = inv.save(str(tmp_path / "out"))
+    assert [os.path.basename(f) for f in files] == ["100.h5", "200.h5"]
+    f = h5lite.File(files[1], "r")
+    assert f["model/values/posterior/values/data"].shape == (3, 250, 440) and list(f["data/fiducial/data"][()]) == [3.0, 4.0, 5.0]
+    assert np.array_equal(f["model/values/posterior/values/data"][()], r["hitmap"][3:]) and f.attrs == {} and f["data"].attrs["repr"] == "FdemData"
+    assert np.array_equal(f["iteration"][()], r["scalars"][3:, _lib.S_ITER]) and f["model/mesh/nCells/data"][1] == r["scalars"][4, _lib.S_BEST_K]
+    assert np.array_equal(f["phids/data"][()], r["misfit_trace"][3:]) and f["acceptance_rate/data"].dtype == np.uint8
+    kb = int(r["scalars"][4, _lib.S_BEST_K])
+    best = api.Model(api.RectilinearMesh1D(edges=r["best_edges"][4, :kb + 1]), r["best_sigma"][4, :kb])
+    dp = d.datapoint(4)
+    dp.forward(best)     # predicted data of the best model, as best_datapoint.writeHdf leaves them
+    assert np.allclose(f["data/predicted_data/data"][1], dp.predictedData, rtol=1e-10)
+    assert np.allclose(f["data/std/data"][1], np.sqrt((r["scalars"][4, _lib.S_BEST_REL] * d.data[4]) ** 2 + r["scalars"][4, _lib.S_BEST_ADD] ** 2))
 
 
 def test_opacity_and_doi_of_a_line():
@@ -179,7 +195,7 @@ def test_inference3d_save_writes_line_products(tmp_path, golden_dir, built_lib):
     res.update({"summary_" + k: v for k, v in dataset.summarise(res, opt, line_id=d.lineNumber).items()})
     inv = dataset.Inference3D(d, seed=1)
     inv.results, inv.options = res, opt
-    files = inv.save(str(tmp_path / "out"))
+    files = inv.save(str(tmp_path / "out"), format="npz")
     assert [os.path.basename(f) for f in files] == ["100.npz", "200.npz"]
     z = np.load(files[0])
     assert z["hitmap"].shape == (3, opt.n_sigma_bins, nd) and z["opacity"].shape == (3, nd) and z["doi"].shape == (3,)

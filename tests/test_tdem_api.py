@@ -175,5 +175,24 @@ def test_inference3d_time_domain_survey(stm_files, tmp_path, golden_dir, built_l
     assert r["rel_hist"].shape == (4, 2, 99) and r["summary_p50"].shape == (4, 1209)
     one = Inference3D(ds, seed=3).infer(index=2, n_markov_chains=400, max_iterations=200, **{k: v for k, v in ops.SKYTEM_OPTIONS.items()})
     assert np.array_equal(one["hitmap"][0], r["hitmap"][2])        # (seed, sounding index) fixes the stream
-    files = inv.save(str(tmp_path / "out"))
+    files = inv.save(str(tmp_path / "out"), format="npz")
     assert [os.path.basename(x) for x in files] == ["100.npz", "101.npz"]
+    # HDF5 in the reference's layout (TdemDataPoint.createHdf :603-626: systems as .stm text, loop pair, per-system error
+    # posteriors); the reference reads the .stm text back with its own parser (TdemSystem_GAAEM.fromHdf :120-129)
+    from geobipy_b200 import h5lite
+    files = inv.save(str(tmp_path / "out"))
+    assert [os.path.basename(x) for x in files] == ["100.h5", "101.h5"]
+    h = h5lite.File(files[1], "r")
+    assert h["data"].attrs["repr"] == "TdemData" and h["data/nSystems"][()] == 2 and h["nsystems"][()] == 2
+    assert np.array_equal(h["model/values/posterior/values/data"][()], r["hitmap"][2:])
+    assert np.array_equal(h["data/relative_error/posterior1/values/data"][()], r["rel_hist"][2:, 1])
+    assert h["data/loop_pair/receiver/x/data"][0] == ds.x[2] - 13.0 and h["data/loop_pair/transmitter/z/data"][1] == 30.0
+    lines = list(h["data/System0"].attrs["data"])
+    p_stm = tmp_path / "back.stm"
+    p_stm.write_text("".join(lines))
+    assert tdem.read_stm(str(p_stm)) == ds.system[0].definition
+    dp = ds.datapoint(3)
+    kb = int(r["scalars"][3, _lib.S_BEST_K])
+    from geobipy_b200 import api
+    dp.forward(api.Model(api.RectilinearMesh1D(edges=r["best_edges"][3, :kb + 1]), r["best_sigma"][3, :kb]))
+    assert np.allclose(h["data/predicted_secondary_field/data"][1], dp.predictedData, rtol=1e-10)
