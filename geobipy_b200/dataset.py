@@ -65,7 +65,25 @@ class FdemData:
             system = api.FdemSystem.read(system)
         self.system = system
         self.lineNumber = self.fiducial = self.x = self.y = self.z = self.elevation = None
-        self.data = self.std = None
+        self.data = self._std = None
+        self.relative_error, self.additive_error = 0.01, 0.0     # Data.__init__ :94-95
+
+    @property
+    def std(self):
+        """sqrt((relative_error data)^2 + additive_error^2), recomputed on every access with the data set's relative error
+        (1 % unless set) and additive error (0) - the reference's getter (Data.std, classes/data/dataset/Data.py:376-384),
+        which also overrides standard deviations read from `*err*` columns; those stay available as `std_from_file`."""
+        if self.data is None:
+            return None
+        return np.sqrt((self.relative_error * self.data) ** 2 + self.additive_error ** 2)
+
+    @std.setter
+    def std(self, values):
+        self._std = values
+
+    @property
+    def std_from_file(self):
+        return self._std
 
     @property
     def nPoints(self):
@@ -80,21 +98,23 @@ class FdemData:
         """Read a data file whose header names Line, Fiducial, Easting, Northing, Height[, Elevation] and one
         in-phase + one quadrature column per frequency (any order; `*err*` columns are uncertainties)."""
         self = cls(system=system)
-        with open(dataFilename, newline="") as f:
+        # numbers are parsed as the reference parses them (pandas.read_csv with its default float parser, comma or
+        # whitespace separated: FdemData.read_csv :555-559), so that a file gives bit-identical arrays in both
+        import pandas as pd
+        with open(dataFilename) as f:
             sample = f.readline()
-            f.seek(0)
-            delim = "," if "," in sample else None
-            if delim:
-                rows = list(csv.reader(f, skipinitialspace=True))
-            else:
-                rows = [ln.split() for ln in f if ln.strip()]
-        header, body = [h.strip() for h in rows[0]], [r for r in rows[1:] if len(r)]
+        if "," in sample:
+            df = pd.read_csv(dataFilename, index_col=False, skipinitialspace=True)
+        else:
+            df = pd.read_csv(dataFilename, index_col=False, sep=r"\s+", skipinitialspace=True)
+        df = df.replace("NaN", np.nan)
+        header = [str(h).strip() for h in df.columns]
+        df.columns = header
         roles = _csv_channels(header)
-        col = {h: i for i, h in enumerate(header)}
 
         def num(name):
-            j = col[name]
-            return np.asarray([np.nan if r[j].strip().lower() == "nan" else float(r[j]) for r in body], dtype=np.float64)
+            return df[name].to_numpy(dtype=np.float64)
+        body = df
         self.lineNumber, self.fiducial = num(roles["line"]), num(roles["fid"])
         self.x, self.y, self.z = num(roles["x"]), num(roles["y"]), num(roles["z"])
         self.elevation = num(roles["elev"]) if roles["elev"] else np.zeros(len(body))
@@ -116,8 +136,10 @@ class FdemData:
     def subset(self, idx):
         """The soundings `idx` as a data set of their own (Data.__getitem__ of the reference)."""
         out = FdemData(self.system)
-        for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data", "std"):
+        for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data"):
             setattr(out, k, np.asarray(getattr(self, k))[idx])
+        out.std = None if self._std is None else np.asarray(self._std)[idx]
+        out.relative_error, out.additive_error = self.relative_error, self.additive_error
         return out
 
     @property

@@ -290,6 +290,9 @@ class TdemData:
         self.system = system
         self.line_number, self.fiducial, self.x, self.y = line_number, fiducial, x, y
         self.height, self.elevation, self.geometry, self.data = height, elevation, geometry, data
+        n, ns = np.shape(data)[0], len(system)
+        self.relative_error, self.additive_error = np.full((n, ns), 0.01), np.zeros((n, ns))     # Data.__init__ :94-95
+        self._std = None
 
     @classmethod
     def read_csv(cls, data_filename, system):
@@ -300,7 +303,7 @@ class TdemData:
         if isinstance(system, (str, TdemSystem)):
             system = [system]
         system = [s if isinstance(s, TdemSystem) else TdemSystem(s) for s in system]
-        df = pd.read_csv(data_filename, skipinitialspace=True, float_precision="round_trip")
+        df = pd.read_csv(data_filename, index_col=False, skipinitialspace=True)   # the reference's parser settings (TdemData.read_csv)
         low = {c.strip().lower(): c for c in df.columns}
 
         def col(*names, default=None):
@@ -329,9 +332,30 @@ class TdemData:
         self = cls(system, col("line_number", "line"), col("fiducial", "fid"), col("easting", "x"), col("northing", "y"),
                    col("height", "z"), col("elevation", "dtm", default=0.0), geometry,
                    df[dcols].to_numpy(dtype=np.float64))
-        # TdemData.read_csv :520-525: without error columns std = 0.1 * data
+        # TdemData.read_csv :520-525: without error columns std = 0.1 * data (kept as std_from_file: the `std` getter
+        # recomputes from the per-system errors, as the reference's does)
         self.std = df[ecols].to_numpy(dtype=np.float64) if ecols else 0.1 * self.data
         return self
+
+    @property
+    def std(self):
+        """TdemData.std (classes/data/dataset/TdemData.py:269-278): recomputed on every access from the per-system
+        relative errors (1 % unless set) and additive errors (0); what the file gave stays in `std_from_file`."""
+        out = np.empty_like(self.data)
+        o = 0
+        for i, s_ in enumerate(self.system):
+            j = slice(o, o + s_.nTimes)
+            out[:, j] = np.sqrt((self.relative_error[:, i][:, None] * self.data[:, j]) ** 2 + (self.additive_error[:, i] ** 2)[:, None])
+            o += s_.nTimes
+        return out
+
+    @std.setter
+    def std(self, values):
+        self._std = values
+
+    @property
+    def std_from_file(self):
+        return getattr(self, "_std", None)
 
     @property
     def nPoints(self):
@@ -345,8 +369,9 @@ class TdemData:
         """The soundings `idx` as a data set of their own (Data.__getitem__ of the reference)."""
         out = TdemData(self.system, self.line_number[idx], self.fiducial[idx], self.x[idx], self.y[idx], self.height[idx],
                        np.asarray(self.elevation)[idx], self.geometry[idx], self.data[idx])
-        if getattr(self, "std", None) is not None:
-            out.std = np.asarray(self.std)[idx]
+        if self._std is not None:
+            out.std = np.asarray(self._std)[idx]
+        out.relative_error, out.additive_error = self.relative_error[idx], self.additive_error[idx]
         return out
 
     # names the survey driver (dataset.Inference3D) shares with FdemData

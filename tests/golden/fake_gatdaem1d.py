@@ -52,10 +52,12 @@ class TDAEMSystem:
     CONDUCTIVITYDERIVATIVE = 1
 
     def __init__(self, stmfile):
-        base = None
+        base, self._radius = None, 0.0
         for line in open(stmfile):
             if "BaseFrequency" in line:
                 base = float(line.split("=")[1])
+            if "ModellingLoopRadius" in line and not line.strip().startswith("//"):
+                self._radius = float(line.split("=")[1])
         tsys, defs = _dual()
         self._index = [i for i, d in enumerate(defs) if d["base_frequency"] == base][0]
         d = defs[self._index]
@@ -64,6 +66,9 @@ class TDAEMSystem:
         self.windows = types.SimpleNamespace(centre=0.5 * (np.asarray(d["window_start"]) + np.asarray(d["window_end"])))
         self.waveform = types.SimpleNamespace()
         self._last = None
+
+    def loopRadius(self):
+        return self._radius
 
     def _thk(self, E):
         return np.r_[E.thickness, 1.0]

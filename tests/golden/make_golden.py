@@ -11,6 +11,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py bins         # posterior_bins.npz
     python tests/golden/make_golden.py transitions  # transitions.npz
     python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
+    python tests/golden/make_golden.py readers      # reader_files/ (heads of the reference's shipped data files) + readers.npz
     python tests/golden/make_golden.py hdf fdem|fdem_height|tdem   # hdf_layout_<kind>.npz: the reference's own HDF5 result tree
 
 Files written
@@ -721,8 +722,53 @@ def make_hdf(kind="fdem", n_iter=1200, n_points=3, index=1):
     print(kind, "tree entries", len(meta), "datasets", len(arrays), "iteration", inf.iteration, "k", state["cur_k"], state["best_k"])
 
 
+def make_readers():
+    """reader_files/ + readers.npz: heads of the data files the reference ships (documentation_source/source/
+    supplementary/data: a comma-separated RESOLVE file, a whitespace-separated field file with other column names, a
+    SkyTEM dual-moment file) and what the reference's OWN readers make of exactly those heads
+    (FdemData.read_csv classes/data/dataset/FdemData.py:520-610, TdemData.read_csv classes/data/dataset/TdemData.py:
+    401-560)."""
+    import fake_gatdaem1d
+    fake_gatdaem1d.install()
+    _geobipy()
+    from geobipy import FdemData, TdemData
+    out_dir = os.path.join(HERE, "reader_files")
+    os.makedirs(out_dir, exist_ok=True)
+    data_dir = os.path.join(SUP, "data")
+    rec = {}
+    for name, rows in (("resolve_glacial.csv", 12), ("Resolve_small.txt", 40), ("Resolve_single.txt", 2), ("skytem_glacial.csv", 7)):
+        with open(os.path.join(data_dir, name)) as f:
+            head = [next(f) for _ in range(rows)] if rows else f.readlines()
+        with open(os.path.join(out_dir, name), "w") as f:
+            f.writelines(head)
+    for name in ("resolve.stm", "FdemSystem1.stm", "SkytemHM.stm", "SkytemLM.stm"):
+        with open(os.path.join(data_dir, name)) as f, open(os.path.join(out_dir, name), "w") as g:
+            g.write(f.read())
+    for name, stm in (("resolve_glacial.csv", "resolve.stm"), ("Resolve_small.txt", "FdemSystem1.stm"), ("Resolve_single.txt", "FdemSystem1.stm")):
+        d = FdemData.read_csv(os.path.join(out_dir, name), os.path.join(out_dir, stm))
+        key = name.split(".")[0]
+        for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data", "std"):
+            rec[key + "/" + k] = np.asarray(getattr(d, k), dtype=np.float64)
+        rec[key + "/frequencies"] = np.asarray(d.system[0].frequencies, dtype=np.float64)
+        rec[key + "/loop_separation"] = np.asarray(d.system[0].loop_separation, dtype=np.float64)
+        print(name, d.nPoints, "points", rec[key + "/data"].shape)
+    d = TdemData.read_csv(os.path.join(out_dir, "skytem_glacial.csv"), [os.path.join(out_dir, "SkytemHM.stm"), os.path.join(out_dir, "SkytemLM.stm")])
+    for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data", "std"):
+        rec["skytem_glacial/" + k] = np.asarray(getattr(d, k), dtype=np.float64)
+    for who in ("transmitter", "receiver"):
+        lp = getattr(d.loop_pair, who)
+        for k in ("x", "y", "z", "pitch", "roll", "yaw", "radius"):
+            rec["skytem_glacial/%s_%s" % (who, k)] = np.asarray(getattr(lp, k), dtype=np.float64)
+    rec["skytem_glacial/off_time0"] = np.asarray(d.system[0].off_time, dtype=np.float64)
+    rec["skytem_glacial/off_time1"] = np.asarray(d.system[1].off_time, dtype=np.float64)
+    print("skytem", d.nPoints, "points", rec["skytem_glacial/data"].shape)
+    np.savez_compressed(os.path.join(HERE, "readers.npz"), **rec)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "readers":
+        make_readers()
     if what == "hdf":
         make_hdf(sys.argv[2] if len(sys.argv) > 2 else "fdem")
     if what == "tdem":
