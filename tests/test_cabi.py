@@ -189,3 +189,17 @@ def test_options_from_a_reference_options_file(built_lib):
     with pytest.raises(AssertionError):
         inf.initialize(api.FdemDataPoint(z=30.0, system=api.FdemSystem([380.0], api.CircularLoop(["z"], [1.0], [0.0], [0.0], [0.0]),
                                                                        api.CircularLoop(["z"], [1.0], [7.93], [0.0], [0.0]))))
+
+
+def test_torch_ops_are_registered():
+    """the three operators exist under torch.ops.geobipy_b200 with tensor-in / tensor-out schemas (the CUDA
+    implementations call the C-ABI; without a device only the registration can be checked)."""
+    import torch
+    from geobipy_b200 import torch_ops  # noqa: F401
+    for name in ("fdem_forward", "fdem_sensitivity", "rjmcmc_run"):
+        op = getattr(torch.ops.geobipy_b200, name)
+        assert "Tensor system" in str(op.default._schema)
+    assert str(torch.ops.geobipy_b200.rjmcmc_run.default._schema).endswith("-> Tensor[]")
+    with pytest.raises((NotImplementedError, RuntimeError)):   # no CPU implementation: the dispatcher refuses CPU tensors
+        z = torch.zeros(1)
+        torch.ops.geobipy_b200.fdem_forward(z.to(torch.uint8), z.to(torch.int32), z.double().reshape(1, 1), z.double().reshape(1, 1), z.double(), 32)

@@ -162,3 +162,30 @@ def test_inference1d_exposes_the_paths_writeHdf_serialises(api, oracle):
     assert np.allclose(chk.predictedData, b.predictedData)
     # slicing / arithmetic keep plain-array behaviour
     assert np.all(np.asarray(m.values) * 2.0 == 2.0 * m.values) and (m.mesh.edges[1:] - m.mesh.edges[:-1]).shape == (m.nCells,)
+
+
+def test_torch_ops_match_the_python_entry_points(api, oracle):
+    """torch.ops.geobipy_b200.*  run the same C-ABI calls as geobipy_b200.ops."""
+    import torch
+    from geobipy_b200 import _lib, ops, torch_ops
+    from geobipy_b200.synthetic import synthetic_batch
+    dev = torch.device("cuda")
+    sysc = ops.resolve_system_struct()
+    b = synthetic_batch(0, 16)
+    t = {k: torch.tensor(v, device=dev) for k, v in b.items()}
+    S = torch_ops.pod(sysc)
+    pred = torch.ops.geobipy_b200.fdem_forward(S, t["nlayers"], t["sigma"], t["thickness"], t["height"], 64)
+    assert torch.equal(pred, ops.fdem_forward(sysc, t["nlayers"], t["sigma"], t["thickness"], t["height"], precision=64))
+    p2, J = torch.ops.geobipy_b200.fdem_sensitivity(S, t["nlayers"], t["sigma"], t["thickness"], t["height"], 32)
+    q2, K = ops.fdem_forward(sysc, t["nlayers"], t["sigma"], t["thickness"], t["height"], precision=32, sensitivity=True)
+    assert torch.equal(p2, q2) and torch.equal(J, K) and J.shape == (16, 12, 30)
+    opt = ops.make_options(n_markov_chains=400)
+    data = (pred + t["noise"] * torch.sqrt((0.05 * pred) ** 2 + 25.0)).contiguous()
+    out = torch.ops.geobipy_b200.rjmcmc_run(S, torch_ops.pod(opt), data, t["height"], 7, 0, 150, 32)
+    ref = ops.rjmcmc_run(sysc, opt, data, t["height"], seed=7, max_iterations=150, precision=32)
+    got = dict(zip(torch_ops.RJMCMC_OUTPUTS, out))
+    for k, v in ref.items():
+        assert torch.equal(got[k], v, ) or (v.dtype.is_floating_point and torch.allclose(got[k], v, equal_nan=True)), k
+    assert got["height_hist"].numel() == 0 and got["hitmap"].shape == (16, 250, 440)
+    with pytest.raises(RuntimeError):
+        torch.ops.geobipy_b200.fdem_forward(S[:-1], t["nlayers"], t["sigma"], t["thickness"], t["height"], 64)
