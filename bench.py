@@ -444,6 +444,7 @@ def run_b200_arm(args):
         r = step(1000 + i, count=True, j=i % ns)
     torch.cuda.synchronize()
     alone_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev[-2:]]))
+    collate_alone = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in c_ev[-2:]]))], dtype=torch.float64, device=dev)
     k_ev.clear()
     c_ev.clear()
     for x in iters_part:
@@ -489,10 +490,13 @@ def run_b200_arm(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(iters, op=dist.ReduceOp.SUM)
         dist.all_reduce(collate_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(collate_alone, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     total_iters = float(iters.item())
     value = total_iters / (total_ms * 1e-3)
-    gather_ms = float(collate_ms.item())
+    gather_ms = float(collate_alone.item())          # the collation's own duration (summaries + pack + one gather), warm
+    gather_span_ms = float(collate_ms.item())       # first to last event of it inside the timed region: with steps overlapping,
+                                                    # its small kernels wait for SMs the next batch's persistent kernel holds
     gather_bytes = collators[0].bytes_per_rank if collators[0] is not None else 0
 
     # forward-only operators ("report also raw kernel forwards/s for the forward-only op")
@@ -597,7 +601,8 @@ def run_b200_arm(args):
                             "jacobians_per_iteration": n_sens / last_iters, "burned_in_fraction": burned / B},
         }
         line["roofline_compute"]["frac"] = line["roofline_compute"]["achieved"] / line["roofline_compute"]["peak"]
-        line["collation"] = {"ms_per_step": gather_ms, "inside_timed_region": True, "bytes_per_rank": int(gather_bytes),
+        line["collation"] = {"ms_per_step": gather_ms, "ms_is": "duration of one collation on an otherwise idle GPU (max over ranks, warm channels)",
+                             "span_in_timed_region_ms": gather_span_ms, "inside_timed_region": True, "bytes_per_rank": int(gather_bytes),
                              "what": "gbp_summarise_hitmap (mean, p5/p50/p95 per depth cell) + edges histogram + scalars"
                                      + (", packed and gathered to rank 0 with one NCCL collective (warm channels)" if world > 1 else "")}
         if world > 1:
