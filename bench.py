@@ -444,7 +444,19 @@ def run_b200_arm(args):
         r = step(1000 + i, count=True, j=i % ns)
     torch.cuda.synchronize()
     alone_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev[-2:]]))
-    collate_alone = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in c_ev[-2:]]))], dtype=torch.float64, device=dev)
+    # the collation on its own: every rank's results ready (barrier), buffers and channels warm.  Inside the timed region
+    # a rank's gather also waits for the slowest rank's batch to end - that skew is in ms_per_step, not in the collective.
+    jl = (max(args.warmup, ns) - 1) % ns
+    ce = []
+    for _ in range(3):
+        barrier()
+        with torch.cuda.stream(streams[jl]):
+            ce.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            ce[-1][0].record()
+            collate(r, jl)
+            ce[-1][1].record()
+    torch.cuda.synchronize()
+    collate_alone = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ce[1:]]))], dtype=torch.float64, device=dev)
     k_ev.clear()
     c_ev.clear()
     for x in iters_part:
@@ -601,7 +613,7 @@ def run_b200_arm(args):
                             "jacobians_per_iteration": n_sens / last_iters, "burned_in_fraction": burned / B},
         }
         line["roofline_compute"]["frac"] = line["roofline_compute"]["achieved"] / line["roofline_compute"]["peak"]
-        line["collation"] = {"ms_per_step": gather_ms, "ms_is": "duration of one collation on an otherwise idle GPU (max over ranks, warm channels)",
+        line["collation"] = {"ms_per_step": gather_ms, "ms_is": "duration of one collation with every rank ready (barrier before it; max over ranks, warm channels)",
                              "span_in_timed_region_ms": gather_span_ms, "inside_timed_region": True, "bytes_per_rank": int(gather_bytes),
                              "what": "gbp_summarise_hitmap (mean, p5/p50/p95 per depth cell) + edges histogram + scalars"
                                      + (", packed and gathered to rank 0 with one NCCL collective (warm channels)" if world > 1 else "")}

@@ -704,6 +704,13 @@ __device__ __noinline__ void ch_flush_height(WarpState<R, T, NC, KIND>* w, const
     __syncwarp();
 }
 
+// fire-and-forget integer add to GLOBAL memory (SASS REDG): the output rows come through void* slots, so a plain
+// atomicAdd compiles to the generic-address ATOM
+__device__ __forceinline__ void red_add_global(int32_t* p, int v)
+{
+    asm volatile("red.global.add.s32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+
 // add `count` visits of the current model / errors to every histogram
 template <typename R, typename T, int NC, int KIND>
 __device__ __noinline__ void ch_flush(WarpState<R, T, NC, KIND>* w, const Consts<R>* K, int k, int mcur, int vcur,
@@ -738,7 +745,7 @@ __device__ __noinline__ void ch_flush(WarpState<R, T, NC, KIND>* w, const Consts
         const R dl = v.ls[lane] - v.ls[lane - 1];
         const R d = m.edges[lane];
         if ((dl <= K->ln_half || dl >= K->ln_3half) && d >= R(0) && d < K->depth_max)
-            atomicAdd(&edges_hist[uniform_bin<R>(d, R(0), K->depth_step, nd)], count);
+            red_add_global(&edges_hist[uniform_bin<R>(d, R(0), K->depth_step, nd)], count);
     }
     __syncwarp();
     // hitmap (Model.update_parameter_posterior :819-847; staircase interp RectilinearMesh1D.py:1148-1158)
@@ -762,7 +769,7 @@ __device__ __noinline__ void ch_flush(WarpState<R, T, NC, KIND>* w, const Consts
                     break;
                 }
             }
-            atomicAdd(&hitmap[(size_t)b * nd + j], count);  // RED.ADD, coalesced along depth
+            red_add_global(&hitmap[(size_t)b * nd + j], count);  // REDG.ADD, coalesced along depth
         }
     }
     __syncwarp();
