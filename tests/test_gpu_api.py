@@ -189,3 +189,56 @@ def test_torch_ops_match_the_python_entry_points(api, oracle):
     assert got["height_hist"].numel() == 0 and got["hitmap"].shape == (16, 250, 440)
     with pytest.raises(RuntimeError):
         torch.ops.geobipy_b200.fdem_forward(S[:-1], t["nlayers"], t["sigma"], t["thickness"], t["height"], 64)
+
+
+def test_integration_adapter_at_the_numba_seam(api, golden_dir):
+    """`nbFdem1dfwd / nbFdem1dsen` with the reference's positional signature over the C-ABI,
+    called with the arguments fdem1d.py:39-56 / :116-133 builds, against the live Numba kernels' outputs
+    (tests/golden/fdem_random_models.npz)."""
+    from geobipy_b200 import _lib, ops
+
+    def _system(tid, frequencies, tHeight, rHeight, moments, rx, separation, scale, altitude):
+        F = len(frequencies)
+        tor, ror = (np.asarray(tid) - 1) % 3, (np.asarray(tid) - 1) // 3
+        tz = np.asarray(tHeight) - altitude
+        rz = np.asarray(rHeight) + np.asarray(tHeight)
+        ry = np.sqrt(np.maximum(np.asarray(separation) ** 2 - np.asarray(rx) ** 2 - (rz - tz) ** 2, 0.0))
+        rmom = np.asarray(scale) / np.asarray(moments)
+        return ops.make_system_struct(frequencies, tor, moments, np.zeros(F), np.zeros(F), tz, ror, rmom, rx, ry, rz)
+
+    def nbFdem1dfwd(tid, frequencies, tHeight, rHeight, moments, rx, separation, w0, lamda0, lamda02, w1, lamda1,
+                    lamda12, scale, conductivity, susceptibility, permeability, thickness, altitude=None):
+        altitude = tHeight[0] if altitude is None else altitude
+        s = _system(tid, frequencies, tHeight, rHeight, moments, rx, separation, scale, altitude)
+        L, F = len(conductivity), len(frequencies)
+        out = ops.fdem_forward(s, np.int32([L]), np.float64(conductivity)[None], np.float64(thickness)[None],
+                               np.float64([altitude]), precision=_lib.PRECISION_F64)[0]
+        return out[:F] + 1j * out[F:]
+
+    def nbFdem1dsen(tid, frequencies, tHeight, rHeight, moments, rx, separation, w0, lamda0, lamda02, w1, lamda1,
+                    lamda12, scale, conductivity, susceptibility, permeability, thickness, altitude=None):
+        altitude = tHeight[0] if altitude is None else altitude
+        s = _system(tid, frequencies, tHeight, rHeight, moments, rx, separation, scale, altitude)
+        L, F = len(conductivity), len(frequencies)
+        _, J = ops.fdem_forward(s, np.int32([L]), np.float64(conductivity)[None], np.float64(thickness)[None],
+                                np.float64([altitude]), precision=_lib.PRECISION_F64, sensitivity=True)
+        J = J[0, :, :L]
+        return J[:F] + 1j * J[F:]
+
+    g = np.load(os.path.join(golden_dir, "fdem_random_models.npz"))
+    sysm = _resolve(api)
+    tmom, rmom = np.asarray(sysm.transmitter.moment, float), np.asarray(sysm.receiver.moment, float)
+    for i in (0, 17, 101, 255):
+        L = int(g["nlayers"][i])
+        alt = float(g["height"][i])
+        tH = alt + np.asarray(sysm.transmitter.z, float)           # fdem1d.py:31-34
+        rH = -tH + np.asarray(sysm.receiver.z, float)
+        args = (sysm.tensor_id, sysm.frequencies, tH, rH, tmom, np.asarray(sysm.receiver.x, float) - np.asarray(sysm.transmitter.x, float),
+                sysm.loop_separation, None, None, None, None, None, None, tmom * rmom, g["sigma"][i, :L], np.zeros(L), np.zeros(L),
+                g["thickness"][i, :L])
+        f = nbFdem1dfwd(*args)
+        ref = g["forward"][i]
+        assert np.max(np.abs(np.r_[f.real, f.imag] - ref) / (np.abs(ref) + 1.0)) < 5e-8
+        J = nbFdem1dsen(*args)
+        refJ = g["sensitivity"][i, :, :L]
+        assert J.shape == (6, L) and np.max(np.abs(np.vstack([J.real, J.imag]) - refJ)) / np.max(np.abs(refJ)) < 1e-8
