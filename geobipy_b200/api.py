@@ -411,7 +411,10 @@ class Inference1D:
                 "%s is not built for a %s datapoint" % (hk, "time-domain" if self._tdem else "frequency-domain"))
         self.iteration, self.burned_in, self.burned_in_iteration = 0, False, 0
 
-    def infer(self, hdf_file_handle=None, max_iterations=0):
+    def infer(self, hdf_file_handle=None, max_iterations=0, index=None):
+        """Run the chain to the reference's termination rule.  With a file handle (any h5py-shaped group laid out by
+        `createHdf` / `Inference2D.createHdf`) the result is written into it at the end, as the reference does
+        (Inference1D.infer :679-688 -> writeHdf)."""
         dp = self.datapoint
         if dp.n_active_channels == 0:
             return True
@@ -423,7 +426,54 @@ class Inference1D:
                            first_index=self.sounding_index, max_iterations=max_iterations, precision=self.precision,
                            device=self.device)
         self._fill(r, 0)
+        self._result = r
+        if hdf_file_handle is not None:
+            self.writeHdf(hdf_file_handle, index=index)
         return self.failed
+
+    # -- HDF5 (Inference1D.createHdf :1002-1048, writeHdf :1050-1090) through geobipy_b200.hdf
+    def _as_dataset(self, dp=None):
+        """The datapoint as a one-sounding data set (what geobipy_b200.hdf lays files out from)."""
+        dp = self.datapoint if dp is None else dp
+        one = lambda v: np.asarray([float(v)])
+        if self._tdem:
+            from .tdem import TdemData
+            tx, rx = dp.transmitter, dp.receiver
+            z_in = getattr(dp, "z_input", float(tx.z))
+            geometry = np.asarray([[tx.pitch, tx.roll, tx.yaw, rx.x - tx.x, rx.y - tx.y, float(rx.z) - float(tx.z), rx.pitch, rx.roll, rx.yaw]], dtype=np.float64)
+            return TdemData(dp.system, one(dp.lineNumber), one(dp.fiducial), one(dp.x), one(dp.y), one(z_in), one(dp.elevation), geometry,
+                            np.asarray(dp.data, dtype=np.float64)[None])
+        from .dataset import FdemData
+        d = FdemData(dp.system)
+        d.lineNumber, d.fiducial, d.x, d.y, d.elevation = one(dp.lineNumber), one(dp.fiducial), one(dp.x), one(dp.y), one(dp.elevation)
+        d.z, d.data = one(getattr(dp, "z_input", dp.z)), np.asarray(dp.data, dtype=np.float64)[None]
+        return d
+
+    def createHdf(self, parent, add_axis=None):
+        """Lay out `parent` for a line of soundings (`add_axis`: their number, or their fiducials as Inference2D.createHdf
+        passes them): every group, dataset and attribute of the reference's file (geobipy_b200.hdf.create_line)."""
+        from . import hdf
+        assert self.datapoint is not None, ValueError("Inference needs a datapoint before creating HDF5 files.")
+        if add_axis is None:
+            raise NotImplementedError("createHdf without add_axis (a file for one sounding, no line axis) is not built: "
+                                      "pass add_axis=1 for a one-sounding line")
+        n = int(add_axis) if np.ndim(add_axis) == 0 else int(np.size(add_axis))
+        hdf.create_line(parent, n, self.options, self._as_dataset(), n_markov_chains=self.n_markov_chains,
+                        update_plot_every=self.update_plot_every, interactive_plot=self.interactive_plot,
+                        reciprocate_parameter=True)
+        return parent
+
+    def writeHdf(self, parent, index=None):
+        """Write this sounding's row (geobipy_b200.hdf.write_line): the chain's posteriors, then the best model / best
+        datapoint over the same datasets, as the reference's writeHdf does.  `index` defaults to the position of the
+        datapoint's fiducial among the file's sorted fiducials (:1054-1056)."""
+        from . import hdf
+        assert getattr(self, "_result", None) is not None, "run infer() first"
+        if index is None:
+            index = int(np.searchsorted(np.asarray(parent["data/fiducial/data"][()]), float(self.datapoint.fiducial)))
+        hdf.write_line(parent, self._result, self.options, self._as_dataset(), np.asarray(self.best_datapoint.predictedData)[None],
+                       rows=[int(index)], multiplier=float(self.multiplier))
+        return parent
 
     def _fill(self, r, b):
         o, s = self.options, r["scalars"][b]

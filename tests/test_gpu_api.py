@@ -242,3 +242,31 @@ def test_integration_adapter_at_the_numba_seam(api, golden_dir):
         J = nbFdem1dsen(*args)
         refJ = g["sensitivity"][i, :, :L]
         assert J.shape == (6, L) and np.max(np.abs(np.vstack([J.real, J.imag]) - refJ)) / np.max(np.abs(refJ)) < 1e-8
+
+
+def test_inference1d_writes_the_reference_hdf_layout(api, oracle, tmp_path):
+    """`Inference1D.createHdf(parent, add_axis)` + `.infer(hdf_file_handle)` as the reference's survey driver calls them
+    (Inference3D._create_HDF5_dataset :312-340, infer_serial :488-492): the sounding lands in its row (found by fiducial)
+    of a file in the reference's layout (tests/test_hdf.py pins the layout itself on the reference's own writer)."""
+    from geobipy_b200 import _lib, h5lite
+    system = _resolve(api)
+    true = api.Model(api.RectilinearMesh1D(edges=[0.0, 5.0, 7.5, np.inf]), [1e-2, 1e-1, 0.03333333])
+    dp = api.FdemDataPoint(z=30.0, system=system, fiducial=20.0, lineNumber=7.0)
+    dp.forward(true)
+    dp.data[:] = dp.predictedData
+    inf = api.Inference1D(prng=np.random.default_rng(0), n_markov_chains=500)
+    inf.initialize(dp)
+    path = str(tmp_path / "7.h5")
+    with h5lite.File(path, "w") as f:
+        inf.createHdf(f, add_axis=np.asarray([10.0, 20.0, 30.0]))
+        f["data/fiducial/data"][:] = [10.0, 20.0, 30.0]          # Inference2D.createHdf :2011-2012
+        inf.infer(f)
+    f = h5lite.File(path, "r")
+    assert f["iteration"][1] == 500 and f["iteration"][0] == 0 and np.isnan(f["halfspace/data"][0])
+    assert np.isclose(f["halfspace/data"][1], inf.halfspace) and f["n_markov_chains"][()] == 500
+    assert np.array_equal(f["model/values/posterior/values/data"][1], inf.hitmap.counts)
+    k = inf.best_model.nCells
+    assert f["model/mesh/nCells/data"][1] == k and np.allclose(f["model/values/data"][1, :k], inf.best_model.values)
+    assert np.allclose(f["data/predicted_data/data"][1], inf.best_datapoint.predictedData)
+    assert np.array_equal(f["data/relative_error/posterior/values/data"][1], inf.datapoint.relative_error.posterior.counts)
+    assert f["data/line_number/data"][1] == 7.0 and f["data"].attrs["repr"] == "FdemData" and f["model"].attrs["repr"] == "Model"
