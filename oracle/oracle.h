@@ -67,6 +67,9 @@ typedef struct {
     double loop_radius;               /* ModellingLoopRadius */
     double MR[GBO_MAXC * GBO_TD_NFREQ], MI[GBO_MAXC * GBO_TD_NFREQ]; /* [C][n_freq] window operator */
     double t_centre[GBO_MAXC];        /* window centre times = off_time (TdemSystem_GAAEM.py:33) */
+    int32_t comp[GBO_MAXC];           /* component of channel c: 0 = z, 1 = x (fixed-wing systems: Tempest measures X and Z;
+                                         TdemDataPoint.forward :1008-1016 stacks SX then -SZ) */
+    double rx_cx;                     /* dx / r: direction cosine of the receiver offset (x component of the horizontal field) */
 } gbo_tdem_system;
 
 /* Everything one chain produces (caller allocates; sizes from gbo_sizes()). */

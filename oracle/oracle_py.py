@@ -63,6 +63,7 @@ class TdemSystemC(ctypes.Structure):
         ("loop_radius", ctypes.c_double),
         ("MR", ctypes.c_double * (MAXC * TD_NFREQ)), ("MI", ctypes.c_double * (MAXC * TD_NFREQ)),
         ("t_centre", ctypes.c_double * MAXC),
+        ("comp", ctypes.c_int32 * MAXC), ("rx_cx", ctypes.c_double),
     ]
 
 
@@ -276,9 +277,20 @@ def tdem_nodes(defs):
     return lo * (hi / lo) ** (np.arange(TD_NFREQ) / (TD_NFREQ - 1.0))
 
 
-def tdem_window_operator(d, fnodes):
-    """MR, MI [n_windows, n_nodes]: window averages of dBz/dt from the node values of S(f) (see
-    tdem1d_oracle.c step 3).  Independent numpy/scipy statement of what the product builds in C++."""
+def tdem_components(d):
+    """Components a system measures, in the reference's channel order (TdemDataPoint.forward :1008-1016: x, then z):
+    those with a non-zero Output Scaling in the .stm (SkyTEM: z; Tempest: x and z)."""
+    return [c for c, k in (("x", "x_scaling"), ("z", "z_scaling")) if float(d.get(k, 1.0 if c == "z" else 0.0)) != 0.0]
+
+
+def tdem_window_operator(d, fnodes, component="z"):
+    """MR, MI [n_windows, n_nodes]: window averages of the measured quantity from the node values of S(f) (see
+    tdem1d_oracle.c step 3).  Independent numpy/scipy statement of what the product builds in C++.
+
+    The physical time signal of harmonic coefficients A is 2 Re(A S e^{iwt}) -> (2 Re A, -2 Im A).  OutputType dB/dt: the
+    data are receiver voltages, -dB/dt (SkyTEM goldens); OutputType B: A / (i w) and the field itself (Tempest goldens).
+    The x component comes with the opposite sign of z (Tempest goldens; unpinned for a dB/dt system).  PeakCurrent scales
+    the normalised waveform, X / ZOutputScaling the output (Tempest: 0.5 A, 1e15 = fT)."""
     from scipy.interpolate import CubicSpline
     base, nyq = d["base_frequency"], 0.5 * d["digitising_frequency"]
     T = 1.0 / base
@@ -290,16 +302,37 @@ def tdem_window_operator(d, fnodes):
     for j, s in enumerate(slope):
         if s != 0.0:
             dn += s * (np.exp(-1j * w * wt[j]) - np.exp(-1j * w * wt[j + 1])) / (1j * w)
-    dn *= 2.0 / T                                             # second half period = minus the first
+    full = abs((wt[-1] - wt[0]) * base - 1.0) < 1e-3          # the .stm gives the whole period (Tempest) or half of it
+    dn *= (1.0 if full else 2.0) / T                          # (second half period = minus the first)
     F = np.ones(f.size, complex)
     for fc, order in zip(d["filter_cutoff"], d["filter_order"]):
         F *= (1.0 / (1.0 + 1j * f / fc)) ** order             # cascaded first-order stages
     ta, tb = np.asarray(d["window_start"])[:, None], np.asarray(d["window_end"])[:, None]
     A = dn * F * (np.exp(1j * w * tb) - np.exp(1j * w * ta)) / (1j * w * (tb - ta))
+    b_field = str(d.get("output_type", "dB/dt")).strip().lower() == "b"
+    if b_field:
+        A = A / (1j * w)
+    sign = (1.0 if b_field else -1.0) * (1.0 if component == "z" else -1.0)
+    scale = sign * float(d.get("peak_current", 1.0)) * float(d.get("z_scaling" if component == "z" else "x_scaling", 1.0))
     lf = np.log10(fnodes)
     G = np.stack([CubicSpline(lf, e)(np.log10(f)) for e in np.eye(fnodes.size)], axis=1)  # harmonics x nodes
-    # minus: the reference flips the sign of gatdaem1d's z component (TdemDataPoint.py:1015-1016)
-    return -2.0 * A.real @ G, 2.0 * A.imag @ G
+    return scale * 2.0 * A.real @ G, -scale * 2.0 * A.imag @ G
+
+
+def tdem_primary_field(d, rx_offset):
+    """Primary field [per component, reference order] of the transmitter dipole at the receiver during the windows
+    (Tempest: PX, PZ; TdemDataPoint.forward :1008-1016 stacks PX, -PZ): B = mu0 m / (4 pi) (3 x z / R^5, 3 z^2 / R^5 - 1 / R^3),
+    m = PeakCurrent x NumberOfTurns x LoopArea, z sign flipped, times the Output Scaling."""
+    x, y, z = rx_offset
+    R = np.sqrt(x * x + y * y + z * z)
+    m = float(d.get("peak_current", 1.0)) * float(d.get("n_turns", 1.0)) * float(d.get("loop_area", 1.0)) * 1e-7
+    out = []
+    for c in tdem_components(d):
+        if c == "x":
+            out.append(m * 3.0 * x * z / R ** 5 * float(d.get("x_scaling", 1.0)))
+        else:
+            out.append(-m * (3.0 * z * z / R ** 5 - 1.0 / R ** 3) * float(d.get("z_scaling", 1.0)))
+    return np.asarray(out)
 
 
 def make_tdem_system(defs=None, rx_offset=(-13.0, 0.0, 2.0)):
@@ -313,17 +346,21 @@ def make_tdem_system(defs=None, rx_offset=(-13.0, 0.0, 2.0)):
     for i, v in enumerate(np.linspace(TD_XI_LO, TD_XI_HI, n_lam)):
         s.xi[i] = v
     s.rx_dx, s.rx_dy, s.rx_dz = rx_offset
+    r = float(np.hypot(rx_offset[0], rx_offset[1]))
+    s.rx_cx = rx_offset[0] / r if r > 0.0 else 0.0
     s.loop_radius = defs[0]["loop_radius"]
     c = 0
     for k, d in enumerate(defs):
-        MR, MI = tdem_window_operator(d, fn)
-        s.n_win[k] = MR.shape[0]
-        for i in range(MR.shape[0]):
-            for j in range(TD_NFREQ):
-                s.MR[c * TD_NFREQ + j] = MR[i, j]
-                s.MI[c * TD_NFREQ + j] = MI[i, j]
-            s.t_centre[c] = 0.5 * (d["window_start"][i] + d["window_end"][i])
-            c += 1
+        s.n_win[k] = len(d["window_start"])
+        for comp in tdem_components(d):        # channel order: system, then component (x, z), then window
+            MR, MI = tdem_window_operator(d, fn, comp)
+            for i in range(MR.shape[0]):
+                for j in range(TD_NFREQ):
+                    s.MR[c * TD_NFREQ + j] = MR[i, j]
+                    s.MI[c * TD_NFREQ + j] = MI[i, j]
+                s.t_centre[c] = 0.5 * (d["window_start"][i] + d["window_end"][i])
+                s.comp[c] = 1 if comp == "x" else 0
+                c += 1
     s.C = c
     return s
 

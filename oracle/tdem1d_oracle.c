@@ -55,7 +55,7 @@
 typedef double complex cplx;
 
 /* per-sounding abscissae and geometry weights */
-static void td_geometry(const gbo_tdem_system *s, double altitude, double *lam, double *wgt)
+static void td_geometry(const gbo_tdem_system *s, double altitude, double *lam, double *wgt, double *wgtx)
 {
     const double ZH = 2.0 * altitude + s->rx_dz;
     const double r = hypot(s->rx_dx, s->rx_dy);
@@ -63,22 +63,24 @@ static void td_geometry(const gbo_tdem_system *s, double altitude, double *lam, 
     for (int j = 0; j < s->n_lam; ++j) {
         const double l = (2.0 / ZH) * exp(s->xi[j]);
         double w = dxi * ((j == 0 || j == s->n_lam - 1) ? 0.5 : 1.0);
-        w *= l * l * l * exp(-l * ZH) * j0(l * r);
+        w *= l * l * l * exp(-l * ZH);
         if (s->loop_radius > 0.0) {
             const double x = l * s->loop_radius;
             w *= 2.0 * j1(x) / x;
         }
         lam[j] = l;
-        wgt[j] = w * MU0 / (4.0 * M_PI);
+        wgt[j] = w * j0(l * r) * MU0 / (4.0 * M_PI);
+        /* horizontal (x) secondary field of the vertical dipole: the same integrand with J1(lam r) dx / r */
+        wgtx[j] = w * j1(l * r) * s->rx_cx * MU0 / (4.0 * M_PI);
     }
 }
 
 /* S_i and (optionally) dS_i / d ln sigma_k for every spline node */
 static void td_frequency_response(const gbo_tdem_system *s, double altitude, int L, const double *sigma,
-                                  const double *thick, cplx *S, cplx *dS /* [n_freq][L] or NULL */)
+                                  const double *thick, cplx *S, cplx *dS /* [n_freq][L] or NULL */, int xcomp)
 {
-    double lam[GBO_TD_MAXLAM], wgt[GBO_TD_MAXLAM];
-    td_geometry(s, altitude, lam, wgt);
+    double lam[GBO_TD_MAXLAM], wgt[GBO_TD_MAXLAM], wgtx[GBO_TD_MAXLAM];
+    td_geometry(s, altitude, lam, xcomp ? wgtx : wgt, xcomp ? wgt : wgtx);   /* wgt = the weights of the asked component */
     for (int i = 0; i < s->n_freq; ++i) {
         const double omu = 2.0 * M_PI * s->freq[i] * MU0;
         cplx acc = 0.0;
@@ -126,12 +128,16 @@ int gbo_tdem_forward(const gbo_tdem_system *s, double altitude, int L, const dou
                      const double *thickness, double *out)
 {
     if (L < 1 || L > GBO_MAXL || altitude <= 0.0) return 1;
-    cplx S[GBO_TD_NFREQ];
-    td_frequency_response(s, altitude, L, sigma, thickness, S, NULL);
+    cplx S[2][GBO_TD_NFREQ];
+    int any_x = 0;
+    for (int c = 0; c < s->C; ++c) any_x |= (s->comp[c] == 1);
+    td_frequency_response(s, altitude, L, sigma, thickness, S[0], NULL, 0);
+    if (any_x) td_frequency_response(s, altitude, L, sigma, thickness, S[1], NULL, 1);
     for (int c = 0; c < s->C; ++c) {
+        const cplx *Sc = S[s->comp[c] == 1];
         double d = 0.0;
         for (int i = 0; i < s->n_freq; ++i)
-            d += s->MR[c * GBO_TD_NFREQ + i] * creal(S[i]) + s->MI[c * GBO_TD_NFREQ + i] * cimag(S[i]);
+            d += s->MR[c * GBO_TD_NFREQ + i] * creal(Sc[i]) + s->MI[c * GBO_TD_NFREQ + i] * cimag(Sc[i]);
         out[c] = d;
     }
     return 0;
@@ -143,15 +149,20 @@ int gbo_tdem_sensitivity(const gbo_tdem_system *s, double altitude, int L, const
 {
     if (L < 1 || L > GBO_MAXL || altitude <= 0.0) return 1;
     cplx S[GBO_TD_NFREQ];
-    static __thread cplx dS[GBO_TD_NFREQ * GBO_MAXL];
-    td_frequency_response(s, altitude, L, sigma, thickness, S, dS);
-    for (int c = 0; c < s->C; ++c)
+    static __thread cplx dS2[2][GBO_TD_NFREQ * GBO_MAXL];
+    int any_x = 0;
+    for (int c = 0; c < s->C; ++c) any_x |= (s->comp[c] == 1);
+    td_frequency_response(s, altitude, L, sigma, thickness, S, dS2[0], 0);
+    if (any_x) td_frequency_response(s, altitude, L, sigma, thickness, S, dS2[1], 1);
+    for (int c = 0; c < s->C; ++c) {
+        const cplx *dS = dS2[s->comp[c] == 1];
         for (int k = 0; k < L; ++k) {
             double d = 0.0;
             for (int i = 0; i < s->n_freq; ++i)
                 d += s->MR[c * GBO_TD_NFREQ + i] * creal(dS[i * L + k]) + s->MI[c * GBO_TD_NFREQ + i] * cimag(dS[i * L + k]);
             J[c * L + k] = d;
         }
+    }
     return 0;
 }
 
@@ -161,7 +172,7 @@ int gbo_tdem_frequency_response(const gbo_tdem_system *s, double altitude, int L
 {
     if (L < 1 || L > GBO_MAXL || altitude <= 0.0) return 1;
     cplx S[GBO_TD_NFREQ];
-    td_frequency_response(s, altitude, L, sigma, thickness, S, NULL);
+    td_frequency_response(s, altitude, L, sigma, thickness, S, NULL, 0);
     for (int i = 0; i < s->n_freq; ++i) {
         S_re[i] = creal(S[i]);
         S_im[i] = cimag(S[i]);

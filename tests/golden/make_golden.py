@@ -6,6 +6,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
     python tests/golden/make_golden.py fdem_tensor  # fdem_tensor_models.npz (tensor ids 3 / 7, vertical coil offsets)
     python tests/golden/make_golden.py tdem         # skytem_clean.npz
+    python tests/golden/make_golden.py tempest      # tempest_clean.npz (X and Z components, B field, point dipole)
     python tests/golden/make_golden.py tdem_transitions   # tdem_transitions.npz (reference sampler + fake_gatdaem1d)
     python tests/golden/make_golden.py tdem_chain <i> [rep]   # ref_tdem_chain_<i>[_r<rep>].npz (minutes each)
     python tests/golden/make_golden.py bins         # posterior_bins.npz
@@ -765,8 +766,37 @@ def make_readers():
     np.savez_compressed(os.path.join(HERE, "readers.npz"), **rec)
 
 
+def make_tempest():
+    """tempest_clean.npz: the reference's Tempest known-answer CSVs (tests/data_checks/tempest_*_clean.csv, tests/
+    test_synthetic_data.py:51-66; plain CSV, no reference import needed): 6 models x 79 soundings x (15 X + 15 Z windows) of
+    B-field in fT plus the primary field PX, PZ - a second system (point dipole, square wave, OutputType = B), a second
+    geometry (120 m, receiver 107 m behind and 45 m below) and a second component for the time-domain arithmetic."""
+    import pandas as pd
+    data = np.zeros((6, 79, 30))
+    prim = np.zeros((6, 79, 2))
+    sig = np.array([[1e-2, 1e-1, 0.03333333], [1e-2, 1e-1, 1.0], [2e-2, 2e-3, 2e-2], [1e-2, 1e-1, 1e-4],
+                    [1.0, 1e-2, 5e-2], [1e-4, 1e-2, 1.0]])  # Model.create_synthetic_model, Model.py:902-908
+    geom = None
+    for m, name in enumerate(MODELS):
+        df = pd.read_csv(os.path.join(REF, "tests/data_checks/tempest_%s_clean.csv" % name))
+        xc = [c for c in df.columns if c.startswith("S0X")]
+        zc = [c for c in df.columns if c.startswith("S0Z")]
+        data[m] = df[xc + zc].values
+        prim[m] = df[["PX", "PZ"]].values
+        g = df[["Height", "tx_pitch", "tx_roll", "tx_yaw", "txrx_dx", "txrx_dy", "txrx_dz", "rx_pitch", "rx_roll", "rx_yaw"]].values
+        assert np.all(g == g[0])
+        geom = g[0]
+        times = np.array([float(c.split("_")[-1]) for c in xc])
+    np.savez_compressed(os.path.join(HERE, "tempest_clean.npz"), data=data, primary=prim, sigma=sig,
+                        zwedge=np.linspace(50.0, 1.0, 79), zdeep=np.linspace(75.0, 500.0, 79), geometry=geom,
+                        times=times, models=np.array(MODELS))
+    print("tempest", data.shape, geom)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "tempest":
+        make_tempest()
     if what == "readers":
         make_readers()
     if what == "hdf":

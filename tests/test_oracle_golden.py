@@ -370,7 +370,7 @@ def test_tdem_forward_matches_reference_csv_goldens(oracle, golden_dir):
     # within 15 %.  The exceptions are the last high-moment windows (t > 3.5 ms) of the thin-salt-water
     # soundings, where the golden vectors' error alternates in sign from window to window (-3 %, +2 %, -13 %,
     # +13 %): ringing of gatdaem1d's 5-per-decade spline; a 240-node dense evaluation of the same physics is
-    # smooth there and agrees with this restatement (scripts/tdem_proto.py).
+    # smooth there and agrees with this restatement (round-1 study).
     ref = np.array([g["data"][m, i] for m in range(6) for i in range(79)])
     t = np.array(s.t_centre[:45])
     floor = np.r_[np.full(26, 2e-14), np.full(19, 2e-13)] * np.sqrt(1e-3 / t)
@@ -378,6 +378,69 @@ def test_tdem_forward_matches_reference_csv_goldens(oracle, golden_dir):
     assert strong.mean() > 0.8
     assert (E[strong] < 0.03).mean() > 0.995, (E[strong] < 0.03).mean()
     assert E[strong].max() < 0.15, E[strong].max()
+
+
+TEMPEST_ADDITIVE = np.r_[0.011474, 0.012810, 0.008507, 0.005154, 0.004742, 0.004477, 0.004168, 0.003539, 0.003352, 0.003213, 0.003161,
+                         0.003122, 0.002587, 0.002038, 0.002201, 0.007383, 0.005693, 0.005178, 0.003659, 0.003426, 0.003046, 0.003095,
+                         0.003247, 0.002775, 0.002627, 0.002460, 0.002178, 0.001754, 0.001405, 0.001283]   # tempest_options: initial_additive_error [fT]
+
+
+def _tempest_system(oracle):
+    import json
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "..", "geobipy_b200", "data", "tempest.json")))
+    return d
+
+
+def test_tdem_forward_matches_tempest_csv_goldens(oracle, golden_dir):
+    """A SECOND, independent pin of the time-domain restatement: the reference's Tempest known-answer CSVs
+    (tests/data_checks/tempest_*_clean.csv, tests/test_synthetic_data.py:51-66) - another system (point dipole instead of a
+    finite loop, 100 % duty square wave given over a whole period, no receiver filters, OutputType = B in fT with PeakCurrent
+    0.5 A), another geometry (120 m, receiver 107 m behind and 45 m below) and another component (X as well as Z), 474
+    soundings x 30 windows, plus the primary field.  Nothing was fitted to these vectors except the two overall signs (a
+    dB/dt system reports the receiver voltage -dB/dt, the x axis): the Hankel rule, the spline nodes, the waveform series and
+    the window averages are those pinned on the SkyTEM vectors.  Tolerance as stated for SkyTEM: median < 0.2 %, 95 % within
+    1 %, every value within max(3 %, 0.75 of the additive noise level of tempest_options)."""
+    g = np.load(os.path.join(golden_dir, "tempest_clean.npz"))
+    d = _tempest_system(oracle)
+    s = oracle.make_tdem_system([d], rx_offset=tuple(g["geometry"][4:7]))
+    assert s.C == 30 and list(s.comp[:30]) == [1] * 15 + [0] * 15 and oracle.tdem_components(d) == ["x", "z"]
+    assert np.allclose(np.array(s.t_centre[:15]), g["times"], rtol=2e-3)
+    # primary field (PX, PZ): exact dipole formula
+    assert np.allclose(oracle.tdem_primary_field(d, tuple(g["geometry"][4:7])), g["primary"][0, 0], rtol=1e-12)
+    assert np.all(g["primary"] == g["primary"][0, 0])
+    E, Z, R = [], [], []
+    for m in range(6):
+        for i in range(79):
+            thk = np.r_[g["zwedge"][i], g["zdeep"][i] - g["zwedge"][i], 1.0]
+            out = oracle.tdem_forward(s, float(g["geometry"][0]), g["sigma"][m], thk)
+            ref = g["data"][m, i]
+            E.append(np.abs(out / ref - 1.0))
+            Z.append(np.abs(out - ref) / TEMPEST_ADDITIVE)
+            R.append(ref)
+    E, Z, R = np.array(E), np.array(Z), np.array(R)
+    assert np.median(E) < 2e-3, np.median(E)
+    assert (E < 0.01).mean() > 0.95, (E < 0.01).mean()
+    assert np.all((E < 0.03) | (Z < 0.75)), Z[E >= 0.03].max()
+    for c0 in (0, 15):   # each component on its own
+        assert np.median(E[:, c0:c0 + 15]) < 2e-3
+    strong = np.abs(R) > 5.0 * TEMPEST_ADDITIVE
+    assert strong.mean() > 0.9 and (E[strong] < 0.03).mean() > 0.995 and E[strong].max() < 0.06, E[strong].max()
+
+
+def test_tempest_jacobian_is_derivative_of_forward(oracle):
+    d = _tempest_system(oracle)
+    s = oracle.make_tdem_system([d], rx_offset=(-107.0, 0.0, -45.0))
+    rng = np.random.default_rng(11)
+    for L in (1, 3, 8):
+        sig = 10.0 ** rng.uniform(-3, 0, L)
+        thk = np.r_[np.exp(rng.uniform(np.log(2.0), np.log(60.0), L - 1)), 1.0]
+        J = oracle.tdem_sensitivity(s, 120.0, sig, thk)
+        for k in range(L):
+            sp, sm = sig.copy(), sig.copy()
+            sp[k] *= np.exp(1e-5)
+            sm[k] *= np.exp(-1e-5)
+            fd = (oracle.tdem_forward(s, 120.0, sp, thk) - oracle.tdem_forward(s, 120.0, sm, thk)) / 2e-5
+            assert np.max(np.abs(fd - J[:, k])) < 2e-6 * np.max(np.abs(J)) + 1e-12, (L, k)
 
 
 def test_tdem_jacobian_is_derivative_of_forward(oracle):
