@@ -67,6 +67,8 @@ class TdemSystemC(ctypes.Structure):
         ("wave_time", ctypes.c_double * TD_MAXWAVE), ("wave_current", ctypes.c_double * TD_MAXWAVE),
         ("window_start", ctypes.c_double * TD_MAXWIN), ("window_end", ctypes.c_double * TD_MAXWIN),
         ("filter_cutoff", ctypes.c_double * TD_MAXFILT), ("filter_order", ctypes.c_int32 * TD_MAXFILT),
+        ("output_type", ctypes.c_int32), ("pad2_", ctypes.c_int32), ("peak_current", ctypes.c_double),
+        ("x_scaling", ctypes.c_double), ("z_scaling", ctypes.c_double),
     ]
 
 
@@ -88,7 +90,7 @@ class ChainBuffersC(ctypes.Structure):
 # every symbol include/geobipy_b200.h declares
 EXPORTS = (
     "gbp_version", "gbp_last_error", "gbp_device_count", "gbp_n_depth", "gbp_flops_per_forward",
-    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_kernel_ms_stats", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times", "gbp_debug_progress_times",
+    "gbp_filter_points", "gbp_launch_count", "gbp_last_kernel_ms", "gbp_kernel_ms_stats", "gbp_mufu_per_forward", "gbp_measure_peaks", "gbp_debug_counters", "gbp_debug_finish_times", "gbp_debug_progress_times", "gbp_tdem_primary_field",
     "gbp_tdem_mufu_per_forward",
     "gbp_fdem_forward", "gbp_fdem_sensitivity", "gbp_fdem_forward_host", "gbp_fdem_sensitivity_host",
     "gbp_rjmcmc_run", "gbp_rjmcmc_run_host", "gbp_release_host_buffers", "gbp_summarise_hitmap",
@@ -157,6 +159,8 @@ def load():
     lib.gbp_debug_finish_times.argtypes = [vp, i32]
     lib.gbp_debug_progress_times.restype = i32
     lib.gbp_debug_progress_times.argtypes = [vp, i32]
+    lib.gbp_tdem_primary_field.restype = i32
+    lib.gbp_tdem_primary_field.argtypes = [vp, vp]
     lib.gbp_debug_counters.restype = i32
     lib.gbp_debug_counters.argtypes = [vp, i32]
     lib.gbp_measure_peaks.restype = i32

@@ -1025,9 +1025,28 @@ double gbp_tdem_mufu_per_forward(const gbp_tdem_survey* sv, int L)
 // ------------------------------------------------------------------------------------------ time domain
 int gbp_tdem_n_channels(const gbp_tdem_survey* sv)
 {
-    int c = 0;
-    for (int s = 0; s < sv->n_systems && s < GBP_TD_MAXSYS; ++s) c += sv->sys[s].n_windows;
-    return c;
+    return td_n_channels(*sv);
+}
+
+int gbp_tdem_primary_field(const gbp_tdem_survey* sv, double* out)
+{
+    // B of a vertical dipole of moment m = PeakCurrent x (turns x area = 1) at the receiver, z up:
+    //   Bx = mu0 m / (4 pi) 3 x z / R^5,  Bz = mu0 m / (4 pi) (3 z^2 / R^5 - 1 / R^3); the reference stacks PX, -PZ
+    if (!sv || !out) return -1;
+    const double x = sv->rx_dx, y = sv->rx_dy, z = sv->rx_dz, R = std::sqrt(x * x + y * y + z * z);
+    if (!(R > 0.0)) {
+        fail("primary field: the receiver sits on the transmitter");
+        return -1;
+    }
+    int n = 0;
+    for (int s = 0; s < sv->n_systems && s < GBP_TD_MAXSYS; ++s) {
+        const TdOutput o = td_output(sv->sys[s]);
+        const double sx = sv->sys[s].x_scaling, sz = (sv->sys[s].x_scaling == 0.0 && sv->sys[s].z_scaling == 0.0) ? 1.0 : sv->sys[s].z_scaling;
+        for (int q = 0; q < o.n_comp; ++q)
+            out[n++] = o.comp[q] == 1 ? 1e-7 * o.peak * 3.0 * x * z / std::pow(R, 5) * sx
+                                      : -1e-7 * o.peak * (3.0 * z * z / std::pow(R, 5) - 1.0 / std::pow(R, 3)) * sz;
+    }
+    return n;
 }
 
 int gbp_tdem_window_operator(const gbp_tdem_survey* sv, double* freq, double* MR, double* MI, double* t_centre)
@@ -1151,6 +1170,12 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     // operators take GBP_TD_MAXC); checked before any device work
     if (gbp_tdem_n_channels(sv) > GBP_TD_SAMPLER_MAXC)
         return fail("time-domain sampler: at most 48 data channels per datapoint (GBP_TD_SAMPLER_MAXC)");
+    for (int s = 0; s < sv->n_systems && s < GBP_TD_MAXSYS; ++s) {
+        const TdOutput o = td_output(sv->sys[s]);
+        if (o.n_comp != 1 || o.comp[0] != 0 || o.b_field)
+            return fail("time-domain sampler: Z-component dB/dt systems only (the error model of a Tempest datapoint, "
+                        "Tempest_datapoint.std :141-176, is not built; the forward / Jacobian operators take X and B systems)");
+    }
     TdCache* tc;
     if (get_td_tables(sv, &tc, true)) return 1;
     ChainParams P;

@@ -38,16 +38,22 @@ struct TdDev {
     double rx_r, rx_dz, loop_radius;
     double tsc[GBP_TD_MAXC];      // sqrt(1 ms / t_c): additive-error scaling of channel c (TdemDataPoint.py:369)
     int csys[GBP_TD_MAXC];        // system of channel c
+    int ccomp[GBP_TD_MAXC];       // component of channel c: 0 = z, 1 = x
+    int has_x, pad2;              // some channel measures the x component (fixed-wing systems: Tempest)
+    double rx_cx;                 // dx / r: direction cosine of the receiver offset
 };
 
 template <typename T> struct TdShared {
     int n_lam, C;
     T omu[TD_NF];
     double xi[GBP_TD_MAXLAM], tw[GBP_TD_MAXLAM];   // td_geometry (per sounding; per proposal when the height is sampled)
-    double rx_r, rx_dz, loop_radius;
+    double rx_r, rx_dz, loop_radius, rx_cx;
+    signed char ccomp[GBP_TD_MAXC];
 };
 template <typename T> __device__ __forceinline__ void fill_td_shared(const TdDev& S, TdShared<T>& q)
 {
+    q.rx_cx = S.rx_cx;
+    for (int i = 0; i < GBP_TD_MAXC; ++i) q.ccomp[i] = (signed char)S.ccomp[i];
     q.n_lam = S.n_lam;
     q.C = S.C;
     for (int i = 0; i < TD_NF; ++i) q.omu[i] = (T)S.omu[i];
@@ -62,14 +68,16 @@ template <typename T> __device__ __forceinline__ void fill_td_shared(const TdDev
 
 // Per-sounding Hankel abscissae and geometry weights (one warp; lane j = abscissa j), fp64 then cast:
 //   lambda_j = (2/ZH) exp(xi_j),  w_j = tw_j lambda_j^3 exp(-lambda_j ZH) J0(lambda_j r) 2 J1(lambda_j a)/(lambda_j a)
-template <typename T> __device__ __noinline__ void td_geometry(const TdShared<T>& S, double altitude, T* lam, T* wgt)
+// xcomp: the weights of the horizontal (x) secondary field instead - J1(lambda_j r) dx / r in place of J0(lambda_j r)
+template <typename T>
+__device__ __noinline__ void td_geometry(const TdShared<T>& S, double altitude, T* lam, T* wgt, const bool xcomp = false)
 {
     __builtin_assume(__isShared(&S));
     const int lane = threadIdx.x & 31;
     if (lane < S.n_lam) {
         const double ZH = 2.0 * altitude + S.rx_dz;
         const double l = (2.0 / ZH) * ::exp(S.xi[lane]);
-        double w = S.tw[lane] * l * l * l * ::exp(-l * ZH) * ::j0(l * S.rx_r);
+        double w = S.tw[lane] * l * l * l * ::exp(-l * ZH) * (xcomp ? ::j1(l * S.rx_r) * S.rx_cx : ::j0(l * S.rx_r));
         if (S.loop_radius > 0.0) {
             const double x = l * S.loop_radius;
             w *= 2.0 * ::j1(x) / x;
@@ -295,18 +303,24 @@ __global__ void __launch_bounds__(256) tdem_kernel(const __grid_constant__ TdDev
             msig[lane] = (T)sigma[(size_t)b * l_stride + lane];
             mthk[lane] = (T)thickness[(size_t)b * l_stride + lane];
         }
-        td_geometry<T>(sys_s, altitude[b], lam, wgt);
-        tdem_eval<T>(sys_s, Mt, lam, wgt, L, msig, mthk, sbuf, pred, SENS ? J : nullptr, SENS);
+        // one pass per measured component: the x channels see the same admittance recursion through other Hankel weights
+        // (J1 instead of J0), so a pass evaluates every window and keeps the channels of its component
 #pragma unroll 1
-        for (int c = lane; c < C; c += 32) out[(size_t)b * C + c] = (double)pred[c] * out_scale;
-        if (SENS) {
+        for (int pass = 0; pass <= (S.has_x ? 1 : 0); ++pass) {
+            td_geometry<T>(sys_s, altitude[b], lam, wgt, pass == 1);
+            tdem_eval<T>(sys_s, Mt, lam, wgt, L, msig, mthk, sbuf, pred, SENS ? J : nullptr, SENS);
 #pragma unroll 1
-            for (int i = lane; i < C * l_stride; i += 32) {
-                const int c = i / l_stride, kk = i % l_stride;
-                Jout[(size_t)b * C * l_stride + i] = (kk < L) ? (double)J[c * KS + kk] * out_scale : 0.0;
+            for (int c = lane; c < C; c += 32)
+                if (sys_s.ccomp[c] == pass) out[(size_t)b * C + c] = (double)pred[c] * out_scale;
+            if (SENS) {
+#pragma unroll 1
+                for (int i = lane; i < C * l_stride; i += 32) {
+                    const int c = i / l_stride, kk = i % l_stride;
+                    if (sys_s.ccomp[c] == pass) Jout[(size_t)b * C * l_stride + i] = (kk < L) ? (double)J[c * KS + kk] * out_scale : 0.0;
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 

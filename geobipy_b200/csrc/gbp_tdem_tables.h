@@ -64,6 +64,43 @@ inline bool td_solve(int n, int m, std::vector<double>& A, std::vector<double>& 
     return true;
 }
 
+// what a system measures: components (x, z) with their output scalings, PeakCurrent, B or dB/dt.  An all-zero tail of the
+// struct (a caller built against the round-1 header) means Z only, scaling 1, 1 A, dB/dt.
+struct TdOutput {
+    int n_comp;
+    int comp[2];        // 1 = x, 0 = z, in channel order (x first: TdemDataPoint.forward :1008-1016)
+    double scale[2];    // sign x PeakCurrent x Output Scaling
+    bool b_field;
+    double peak;
+};
+inline TdOutput td_output(const gbp_tdem_system& y)
+{
+    TdOutput o;
+    o.b_field = y.output_type == 1;
+    o.peak = y.peak_current != 0.0 ? y.peak_current : 1.0;
+    double sx = y.x_scaling, sz = y.z_scaling;
+    if (sx == 0.0 && sz == 0.0) sz = 1.0;
+    // signs, pinned by the reference's known-answer vectors: a dB/dt system reports the receiver voltage -dB/dt (SkyTEM,
+    // z), a B system the field itself (Tempest, z); the x component has the opposite sign of z (Tempest; unpinned for dB/dt)
+    const double sgn_z = o.b_field ? 1.0 : -1.0;
+    o.n_comp = 0;
+    if (sx != 0.0) {
+        o.comp[o.n_comp] = 1;
+        o.scale[o.n_comp++] = -sgn_z * o.peak * sx;
+    }
+    if (sz != 0.0) {
+        o.comp[o.n_comp] = 0;
+        o.scale[o.n_comp++] = sgn_z * o.peak * sz;
+    }
+    return o;
+}
+inline int td_n_channels(const gbp_tdem_survey& sv)
+{
+    int c = 0;
+    for (int s = 0; s < sv.n_systems && s < GBP_TD_MAXSYS; ++s) c += sv.sys[s].n_windows * td_output(sv.sys[s]).n_comp;
+    return c;
+}
+
 inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
 {
     typedef std::complex<double> cd;
@@ -84,9 +121,9 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
             out.error = "invalid time-domain system description";
             return false;
         }
-        const double half = y.wave_time[y.n_wave - 1] - y.wave_time[0];
-        if (std::fabs(half * 2.0 * y.base_frequency - 1.0) > 1e-3) {
-            out.error = "the current waveform must span half a period of the base frequency";
+        const double span = y.wave_time[y.n_wave - 1] - y.wave_time[0];
+        if (std::fabs(span * 2.0 * y.base_frequency - 1.0) > 1e-3 && std::fabs(span * y.base_frequency - 1.0) > 1e-3) {
+            out.error = "the current waveform must span half a period or one period of the base frequency";
             return false;
         }
         for (int i = 0; i < y.n_windows; ++i)
@@ -101,7 +138,7 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
             out.error = "systems of one datapoint type must share ModellingLoopRadius";
             return false;
         }
-        C += y.n_windows;
+        C += y.n_windows * td_output(y).n_comp;
     }
     if (C > GBP_TD_MAXC) {
         out.error = "too many windows";
@@ -115,6 +152,7 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
     d.n_lam = n_lam;
     d.C = C;
     d.rx_r = std::hypot(sv.rx_dx, sv.rx_dy);
+    d.rx_cx = d.rx_r > 0.0 ? sv.rx_dx / d.rx_r : 0.0;
     d.rx_dz = sv.rx_dz;
     d.loop_radius = sv.sys[0].loop_radius;
     const double dxi = (TD_XI_HI - TD_XI_LO) / (double)(n_lam - 1);
@@ -157,6 +195,7 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
         const gbp_tdem_system& y = sv.sys[s];
         d.n_win[s] = y.n_windows;
         const double T = 1.0 / y.base_frequency;
+        const TdOutput o = td_output(y);
         const int nharm = (int)(0.5 * y.digitising_frequency / y.base_frequency);
         std::vector<double> g(n);
         for (int hn = 1; hn <= nharm; hn += 2) {
@@ -167,7 +206,8 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
                 const double slope = (y.wave_current[j + 1] - y.wave_current[j]) / dt;
                 if (slope != 0.0) dn += slope * (std::exp(-I * (w * y.wave_time[j])) - std::exp(-I * (w * y.wave_time[j + 1]))) / (I * w);
             }
-            dn *= 2.0 / T;
+            const double span = y.wave_time[y.n_wave - 1] - y.wave_time[0];
+            dn *= (std::fabs(span * y.base_frequency - 1.0) <= 1e-3 ? 1.0 : 2.0) / T;   // whole period given, or half of it
             cd F = 1.0;
             for (int k = 0; k < y.n_filters; ++k) {
                 const cd stage = 1.0 / (1.0 + I * (f / y.filter_cutoff[k]));
@@ -184,20 +224,28 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
             g[iv + 1] += b / hh;
             for (int i = 0; i < y.n_windows; ++i) {
                 const double ta = y.window_start[i], tb = y.window_end[i];
-                const cd Aw = dn * F * (std::exp(I * (w * tb)) - std::exp(I * (w * ta))) / (I * w * (tb - ta));
-                const int c = c0 + i;
-                for (int k = 0; k < n; ++k) {
-                    out.Mt[(size_t)k * TD_CP + c] += -2.0 * Aw.real() * g[k];
-                    out.Mt[(size_t)(TD_NF + k) * TD_CP + c] += 2.0 * Aw.imag() * g[k];
+                cd Aw = dn * F * (std::exp(I * (w * tb)) - std::exp(I * (w * ta))) / (I * w * (tb - ta));
+                if (o.b_field) Aw /= I * w;   // B = the integral of dB/dt
+                // the time signal of harmonic coefficient A is 2 Re(A S e^{iwt}): (2 Re A) Re S - (2 Im A) Im S
+                for (int q = 0; q < o.n_comp; ++q) {
+                    const int c = c0 + q * y.n_windows + i;
+                    for (int k = 0; k < n; ++k) {
+                        out.Mt[(size_t)k * TD_CP + c] += o.scale[q] * 2.0 * Aw.real() * g[k];
+                        out.Mt[(size_t)(TD_NF + k) * TD_CP + c] += -o.scale[q] * 2.0 * Aw.imag() * g[k];
+                    }
                 }
             }
         }
-        for (int i = 0; i < y.n_windows; ++i) {
-            const double tc = 0.5 * (y.window_start[i] + y.window_end[i]);  // off_time = window centre
-            d.tsc[c0 + i] = std::exp(-0.5 * (std::log(tc) - std::log(1e-3)));
-            d.csys[c0 + i] = s;
-        }
-        c0 += y.n_windows;
+        for (int q = 0; q < o.n_comp; ++q)
+            for (int i = 0; i < y.n_windows; ++i) {
+                const int c = c0 + q * y.n_windows + i;
+                const double tc = 0.5 * (y.window_start[i] + y.window_end[i]);  // off_time = window centre
+                d.tsc[c] = std::exp(-0.5 * (std::log(tc) - std::log(1e-3)));
+                d.csys[c] = s;
+                d.ccomp[c] = o.comp[q];
+                if (o.comp[q] == 1) d.has_x = 1;
+            }
+        c0 += y.n_windows * o.n_comp;
     }
     return true;
 }

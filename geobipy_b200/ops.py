@@ -6,6 +6,7 @@ Two calling conventions, as in include/geobipy_b200.h:
 PyTorch is used for device memory / streams only.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -45,10 +46,16 @@ def make_tdem_system_struct(d):
     nw, nwin, nf = len(d["waveform_time"]), len(d["window_start"]), len(d["filter_cutoff"])
     if nw > _lib.TD_MAXWAVE or nwin > _lib.TD_MAXWIN or nf > _lib.TD_MAXFILT:
         raise ValueError("time-domain system too large for the C-ABI limits")
-    if d.get("x_scaling", 0.0) != 0.0 or d.get("y_scaling", 0.0) != 0.0 or d.get("z_scaling", 1.0) == 0.0:
-        raise ValueError("only Z-component systems are supported")
-    if str(d.get("output_type", "dB/dt")).strip().lower() != "db/dt":
-        raise ValueError("only dB/dt output is supported")
+    if d.get("y_scaling", 0.0) != 0.0:
+        raise ValueError("the Y component is not supported (X and Z are)")
+    ot = str(d.get("output_type", "dB/dt")).strip().lower()
+    if ot not in ("db/dt", "b"):
+        raise ValueError("OutputType must be dB/dt or B")
+    s.output_type = 1 if ot == "b" else 0
+    s.peak_current = float(d.get("peak_current", 1.0))
+    s.x_scaling, s.z_scaling = float(d.get("x_scaling", 0.0)), float(d.get("z_scaling", 1.0))
+    if s.x_scaling == 0.0 and s.z_scaling == 0.0:
+        raise ValueError("a system must measure X or Z")
     s.n_wave, s.n_windows, s.n_filters, s.n_abscissae = nw, nwin, nf, int(d["n_abscissae"])
     s.base_frequency, s.digitising_frequency = float(d["base_frequency"]), float(d["digitising_frequency"])
     s.loop_radius = float(d.get("loop_radius", 0.0))
@@ -79,6 +86,26 @@ def skytem_definitions():
     import os
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
     return [json.load(open(os.path.join(d, n))) for n in ("skytem_hm.json", "skytem_lm.json")]
+
+
+def tempest_definition():
+    """The Tempest fixed-wing system of the reference (documentation_source/source/supplementary/data/tempest.stm): point
+    dipole, square wave, 15 windows of X and Z B-field in fT."""
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tempest.json")))
+
+
+def tempest_survey_struct(rx_offset=(-107.0, 0.0, -45.0)):
+    return make_tdem_survey_struct([tempest_definition()], rx_offset)
+
+
+def tdem_primary_field(survey):
+    """Primary field per system and measured component, in channel order (gbp_tdem_primary_field)."""
+    out = np.zeros(2 * _lib.TD_MAXSYS)
+    n = _lib.load().gbp_tdem_primary_field(ctypes.addressof(survey), out.ctypes.data)
+    if n < 0:
+        raise _lib.GeobipyB200Error(_lib.load().gbp_last_error().decode())
+    return out[:n]
 
 
 def skytem_survey_struct(rx_offset=(-13.0, 0.0, 2.0)):

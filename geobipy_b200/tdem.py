@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib, ops
 from .api import Model
 
-__all__ = ["read_stm", "TdemSystem", "TdemLoop", "TdemDataPoint", "TdemData"]
+__all__ = ["read_stm", "TdemSystem", "TdemLoop", "TdemDataPoint", "Tempest_datapoint", "TdemData"]
 
 
 def read_stm(filename):
@@ -101,7 +101,8 @@ class TdemSystem:
         self.off_time = 0.5 * (np.asarray(definition["window_start"]) + np.asarray(definition["window_end"]))
         assert np.min(np.diff(self.off_time)) > 0.0 if self.off_time.size > 1 else True, ValueError(
             "Receiver window times must monotonically increase for system " + str(system_filename))
-        self.components = ['z']
+        # the components with a non-zero Output Scaling, x before z (TdemSystem_GAAEM / TdemDataPoint.forward :1008-1016)
+        self.components = [c for c, k, dflt in (('x', "x_scaling", 0.0), ('z', "z_scaling", 1.0)) if float(definition.get(k, dflt)) != 0.0]
 
     @classmethod
     def read(cls, system_filename):
@@ -119,7 +120,7 @@ class TdemSystem:
 
     @property
     def n_components(self):
-        return 1
+        return len(self.components)
 
     @property
     def isGA(self):
@@ -183,18 +184,27 @@ class TdemDataPoint:
 
     @property
     def nChannels(self):
-        return int(self.nTimes.sum())
+        return int((self.nTimes * self.n_components).sum())
 
     @property
     def components(self):
-        return ['z']
+        return list(self.system[0].components)
+
+    @property
+    def n_components(self):
+        return len(self.components)
 
     def off_time(self, system=0):
         return self.system[system].off_time
 
     def _systemIndices(self, system=0):
-        o = np.r_[0, np.cumsum(self.nTimes)]
+        o = np.r_[0, np.cumsum(self.nTimes * self.n_components)]
         return np.s_[o[system]:o[system + 1]]
+
+    def _component_indices(self, component=0, system=0):
+        """Channels of component `component` (position in `components`) of a system (TdemDataPoint._component_indices)."""
+        o = np.r_[0, np.cumsum(self.nTimes * self.n_components)][system] + component * self.nTimes[system]
+        return np.s_[o:o + self.nTimes[system]]
 
     @property
     def data(self):
@@ -252,9 +262,11 @@ class TdemDataPoint:
                 mod.mesh.widths.reshape(1, L).astype(np.float64), np.asarray([alt]))
 
     def forward(self, mod):
-        """Fill predicted_secondary_field from a 1-D layered model (TdemDataPoint.forward :997)."""
+        """Fill predicted_secondary_field (and predicted_primary_field: one value per system and component) from a 1-D
+        layered model (TdemDataPoint.forward :997-1022)."""
         nl, s, t, a = self._model_arrays(mod)
         self.predicted_secondary_field[:] = ops.forward(self.c_struct, nl, s, t, a, precision=self.precision)[0]
+        self.predicted_primary_field = ops.tdem_primary_field(self.c_struct)
 
     def sensitivity(self, mod, ix=None, model_changed=False):
         """d(predicted)/d ln(sigma) [nChannels, nCells] (TdemDataPoint.sensitivity :1024, gaTdem1dsen's sigma scaling)."""
@@ -279,6 +291,50 @@ class TdemDataPoint:
         var = self.std[a] ** 2
         ll = -0.5 * a.sum() * np.log(2.0 * np.pi) - 0.5 * np.sum(np.log(var)) - 0.5 * np.sum(self.deltaD[a] ** 2 / var)
         return float(ll) if log else float(np.exp(ll))
+
+
+class Tempest_datapoint(TdemDataPoint):
+    """A fixed-wing Tempest sounding (classes/data/datapoint/Tempest_datapoint.py): X and Z components of the B field in fT;
+    `data` / `predictedData` are secondary + primary field per component (:107-127), the error model has one relative
+    error per component and an additive error per channel (:141-176).  Forward and Jacobian run on the GPU; the sampler
+    for this datapoint type (its error model, the pitch / offset unknowns of tempest_options) is not built."""
+
+    def __init__(self, *args, primary_field=None, additive_error_multiplier=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        n = self.nSystems * self.n_components
+        self.primary_field = np.zeros(n) if primary_field is None else np.asarray(primary_field, np.float64).reshape(n)
+        self.predicted_primary_field = np.zeros(n)
+        self.relative_error = np.full(n, 0.01)
+        self.additive_error = np.zeros(self.nChannels)
+        self.additive_error_multiplier = np.ones(n) if additive_error_multiplier is None else np.asarray(additive_error_multiplier, np.float64).reshape(n)
+
+    @property
+    def data(self):
+        out = self.secondary_field.copy()
+        for i in range(self.n_components):
+            ic = self._component_indices(i, 0)
+            out[ic] = self.secondary_field[ic] + self.primary_field[i]
+        return out
+
+    @property
+    def predictedData(self):
+        out = self.predicted_secondary_field.copy()
+        for i in range(self.n_components):
+            ic = self._component_indices(i, 0)
+            out[ic] = self.predicted_secondary_field[ic] + self.predicted_primary_field[i]
+        return out
+
+    @property
+    def std(self):
+        assert np.all(self.relative_error > 0.0), ValueError('relative_error must be > 0.0')
+        d, out = self.data, np.empty(self.nChannels)
+        for j in range(self.n_components):
+            ic = self._component_indices(j, 0)
+            out[ic] = np.sqrt((self.relative_error[j] * d[ic]) ** 2 + (self.additive_error_multiplier[j] * self.additive_error[ic]) ** 2)
+        return out
+
+    def initialize(self, **kwargs):
+        raise NotImplementedError("the sampler for Tempest datapoints is not built (DESIGN.md section 7): forward / sensitivity only")
 
 
 class TdemData:

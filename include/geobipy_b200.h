@@ -106,8 +106,10 @@ typedef struct {
 } gbp_options;
 
 /* One time-domain acquisition system = the contents of a GA-AEM .stm file as gatdaem1d's TDAEMSystem reads
- * it (classes/system/TdemSystem_GAAEM.py:26-40; e.g. documentation_source/.../data/SkytemHM.stm).
- * Vertical-axis transmitter loop, Z-component dB/dt receiver, unit moment, no secondary-field normalisation. */
+ * it (classes/system/TdemSystem_GAAEM.py:26-40; e.g. documentation_source/.../data/SkytemHM.stm, tempest.stm).
+ * Vertical-axis transmitter (finite loop or point dipole), zero attitudes, no secondary-field normalisation; receiver
+ * components Z and / or X; OutputType dB/dt (the receiver voltage, -dB/dt) or B.  Channel order of a system, as
+ * TdemDataPoint.forward stacks them (TdemDataPoint.py:1008-1016): the X windows (if measured), then the Z windows. */
 typedef struct {
     int32_t n_wave, n_windows, n_filters;
     int32_t n_abscissae;                /* NumberOfAbsiccaInHankelTransformEvaluation */
@@ -118,6 +120,13 @@ typedef struct {
     double window_start[GBP_TD_MAXWIN], window_end[GBP_TD_MAXWIN];   /* WindowTimes [s] */
     double filter_cutoff[GBP_TD_MAXFILT];                            /* LowPassFilter CutOffFrequency [Hz] */
     int32_t filter_order[GBP_TD_MAXFILT];                            /* LowPassFilter Order */
+    /* (appended in round 2; an all-zero tail means the SkyTEM-type defaults: dB/dt, 1 A, Z only with scaling 1) */
+    int32_t output_type;                /* OutputType: 0 = dB/dt, 1 = B */
+    int32_t pad2_;
+    double peak_current;                /* PeakCurrent [A]: scales the normalised waveform; 0 is read as 1 */
+    double x_scaling, z_scaling;        /* X / ZOutputScaling: a component is measured where its scaling is non-zero (Tempest:
+                                           1e15 = fT); (0, 0) is read as Z only, scaling 1.  The waveform may cover half a period
+                                           (the second half is its negative) or the whole period. */
 } gbp_tdem_system;
 
 /* A time-domain datapoint type: its systems and the transmitter->receiver offset (Loop_pair.Geometry,
@@ -260,7 +269,7 @@ int gbp_opacity_doi(const int32_t *d_range_bins, int B, int n_depth, const int32
 int gbp_release_host_buffers(void);
 
 /* ---- time domain (SkyTEM-type systems) ---------------------------------------------------------- */
-/* total number of data channels = windows of every system, system 0 first (TdemDataPoint channel order) */
+/* total number of data channels = (measured components) x windows of every system, system 0 first (TdemDataPoint channel order) */
 int gbp_tdem_n_channels(const gbp_tdem_survey *sv);
 /* The model-independent tables the kernels use (tests / inspection): freq [GBP_TD_NFREQ] spline-node
  * frequencies; MR, MI [C][GBP_TD_NFREQ] window operator d_c = sum_i MR[c][i] Re S_i + MI[c][i] Im S_i;
@@ -271,8 +280,10 @@ int gbp_tdem_window_operator(const gbp_tdem_survey *sv, double *freq, double *MR
 double gbp_tdem_flops_per_forward(const gbp_tdem_survey *sv, int n_layers);
 double gbp_tdem_mufu_per_forward(const gbp_tdem_survey *sv, int n_layers);
 
-/* out: [B][C] dBz/dt window averages (V/(A m^4) for unit moment), J: [B][C][l_stride] = d out / d ln(sigma).
- * altitude = transmitter height above ground [B].  DEVICE pointers, stream ordered. */
+/* out: [B][C] window averages of the SECONDARY field (dB/dt systems: V/(A m^4) for unit moment; B systems: the output
+ * scaling's unit), J: [B][C][l_stride] = d out / d ln(sigma).  altitude = transmitter height above ground [B].  DEVICE
+ * pointers, stream ordered.  Pinned on the reference's SkyTEM (Z, dB/dt, finite loop) and Tempest (X + Z, B, point dipole)
+ * known-answer vectors. */
 int gbp_tdem_forward(const gbp_tdem_survey *sv, int B, int l_stride, const int32_t *d_nlayers,
                      const double *d_sigma, const double *d_thickness, const double *d_altitude,
                      double *d_out, int precision, void *stream);
@@ -286,8 +297,13 @@ int gbp_tdem_forward_host(const gbp_tdem_survey *sv, int B, int l_stride, const 
 int gbp_tdem_sensitivity_host(const gbp_tdem_survey *sv, int B, int l_stride, const int32_t *nlayers,
                               const double *sigma, const double *thickness, const double *altitude,
                               double *out, double *J, int precision, int device);
+/* primary field of the transmitter dipole at the receiver during the windows, per system and measured component in channel
+ * order ([n_systems x components]: Tempest PX, PZ; TdemDataPoint.forward :1008-1016 stacks PX, -PZ), in the output
+ * scaling's unit.  Host only.  Returns the number of values written. */
+int gbp_tdem_primary_field(const gbp_tdem_survey *sv, double *out);
 /* rjMCMC for time-domain datapoints: data [B][C]; errors per system (gbp_options.n_systems must equal
- * sv->n_systems); additive error of channel c scaled by (t_c / 1 ms)^-0.5 (TdemDataPoint.std :329-379). */
+ * sv->n_systems); additive error of channel c scaled by (t_c / 1 ms)^-0.5 (TdemDataPoint.std :329-379).  Z-component
+ * dB/dt systems only: the error model of a Tempest datapoint (Tempest_datapoint.std :141-176) is not built. */
 int gbp_tdem_rjmcmc_run(const gbp_tdem_survey *sv, const gbp_options *opt, int B, const double *d_data,
                         const double *d_altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
                         const gbp_chain_buffers *d_buf, int precision, void *stream);

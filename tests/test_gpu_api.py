@@ -211,8 +211,8 @@ def test_integration_adapter_at_the_numba_seam(api, golden_dir):
         altitude = tHeight[0] if altitude is None else altitude
         s = _system(tid, frequencies, tHeight, rHeight, moments, rx, separation, scale, altitude)
         L, F = len(conductivity), len(frequencies)
-        out = ops.fdem_forward(s, np.int32([L]), np.float64(conductivity)[None], np.float64(thickness)[None],
-                               np.float64([altitude]), precision=_lib.PRECISION_F64)[0]
+        out = ops.fdem_forward(s, np.int32([L]), np.asarray(conductivity, float)[None], np.asarray(thickness, float)[None],
+                               np.asarray([altitude], float), precision=_lib.PRECISION_F64)[0]
         return out[:F] + 1j * out[F:]
 
     def nbFdem1dsen(tid, frequencies, tHeight, rHeight, moments, rx, separation, w0, lamda0, lamda02, w1, lamda1,
@@ -220,8 +220,8 @@ def test_integration_adapter_at_the_numba_seam(api, golden_dir):
         altitude = tHeight[0] if altitude is None else altitude
         s = _system(tid, frequencies, tHeight, rHeight, moments, rx, separation, scale, altitude)
         L, F = len(conductivity), len(frequencies)
-        _, J = ops.fdem_forward(s, np.int32([L]), np.float64(conductivity)[None], np.float64(thickness)[None],
-                                np.float64([altitude]), precision=_lib.PRECISION_F64, sensitivity=True)
+        _, J = ops.fdem_forward(s, np.int32([L]), np.asarray(conductivity, float)[None], np.asarray(thickness, float)[None],
+                                np.asarray([altitude], float), precision=_lib.PRECISION_F64, sensitivity=True)
         J = J[0, :, :L]
         return J[:F] + 1j * J[F:]
 

@@ -322,3 +322,90 @@ def test_single_moment_datapoint_twin(gpu, oracle):
     assert same >= B - 1, same
     r32 = gpu.rjmcmc_run(sv, opt, data, alt, seed=5, max_iterations=NIT, precision=32, outputs=("scalars",))
     assert (r32["scalars"][:, 0] == NIT).all()
+
+
+# ------------------------------------------------------------------------------------------ Tempest: X + Z components, B field
+TEMPEST_ADDITIVE = np.r_[0.011474, 0.012810, 0.008507, 0.005154, 0.004742, 0.004477, 0.004168, 0.003539, 0.003352, 0.003213, 0.003161,
+                         0.003122, 0.002587, 0.002038, 0.002201, 0.007383, 0.005693, 0.005178, 0.003659, 0.003426, 0.003046, 0.003095,
+                         0.003247, 0.002775, 0.002627, 0.002460, 0.002178, 0.001754, 0.001405, 0.001283]   # tempest_options [fT]
+
+
+@pytest.fixture(scope="module")
+def tempest(gpu, oracle):
+    return gpu.tempest_survey_struct(), oracle.make_tdem_system([gpu.tempest_definition()], rx_offset=(-107.0, 0.0, -45.0))
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_tempest_forward_reference_csv_goldens(gpu, tempest, golden_dir, prec):
+    """The reference's Tempest known-answer vectors (X and Z components of the B field of a point dipole, 474 soundings x 30
+    windows + the primary field) through the forward operator: the stated tolerance of the oracle's own pin
+    (tests/test_oracle_golden.py::test_tdem_forward_matches_tempest_csv_goldens)."""
+    g = np.load(os.path.join(golden_dir, "tempest_clean.npz"))
+    sv = gpu.make_tdem_survey_struct([gpu.tempest_definition()], tuple(g["geometry"][4:7]))
+    assert gpu.n_channels(sv) == 30
+    assert np.allclose(gpu.tdem_primary_field(sv), g["primary"][0, 0], rtol=1e-12)
+    sig = np.repeat(g["sigma"][:, None, :], 79, axis=1).reshape(-1, 3)
+    thk = np.tile(np.stack([g["zwedge"], g["zdeep"] - g["zwedge"], np.full(79, np.inf)], axis=1), (6, 1))
+    out = gpu.forward(sv, np.full(474, 3, np.int32), sig, thk, np.full(474, float(g["geometry"][0])), precision=prec)
+    ref = g["data"].reshape(-1, 30)
+    E = np.abs(out / ref - 1.0)
+    Z = np.abs(out - ref) / TEMPEST_ADDITIVE
+    assert np.median(E) < 2e-3 and np.median(E[:, :15]) < 2e-3 and np.median(E[:, 15:]) < 2e-3
+    assert (E < 0.01).mean() > 0.95
+    assert np.all((E < 0.03) | (Z < 0.75))
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_tempest_forward_and_jacobian_against_oracle(gpu, tempest, oracle, prec):
+    rng = np.random.default_rng(8)
+    B = 96
+    nl = rng.integers(1, 31, B).astype(np.int32)
+    nl[:6] = [1, 2, 3, 5, 30, 30]
+    sig = 10.0 ** rng.uniform(-3.5, 0.5, (B, 30))
+    thk = rng.uniform(1.0, 40.0, (B, 30))
+    alt = rng.uniform(90.0, 150.0, B)
+    ref, refJ = np.zeros((B, 30)), np.zeros((B, 30, 30))
+    for b in range(B):
+        L = nl[b]
+        ref[b] = oracle.tdem_forward(tempest[1], alt[b], sig[b, :L], thk[b, :L])
+        refJ[b, :, :L] = oracle.tdem_sensitivity(tempest[1], alt[b], sig[b, :L], thk[b, :L])
+    pred, J = gpu.forward(tempest[0], nl, sig, thk, alt, precision=prec, sensitivity=True)
+    pred2 = gpu.forward(tempest[0], nl, sig, thk, alt, precision=prec)
+    assert np.array_equal(pred, pred2) or np.allclose(pred, pred2, rtol=1e-6)
+    rowmax = np.abs(refJ).max(axis=2)
+    if prec == 64:
+        assert np.max(np.abs(pred - ref) / (np.abs(ref) + 1e-9)) < 5e-9
+        assert np.max(np.abs(J - refJ).max(axis=2) / rowmax) < 1e-8
+    else:   # fp32: 2e-4 |d| + 1 % of the additive noise level of tempest_options
+        assert np.all(np.abs(pred - ref) <= 2e-4 * np.abs(ref) + 0.01 * TEMPEST_ADDITIVE)
+        assert np.max(np.abs(J - refJ).max(axis=2) / rowmax) < 2e-2
+    for b in range(B):   # layers beyond the model's are zero columns
+        assert np.all(J[b, :, nl[b]:] == 0.0)
+
+
+def test_tempest_datapoint_and_sampler_refusal(gpu, tempest, golden_dir):
+    """Tempest_datapoint mirror (data = secondary + primary per component, Tempest_datapoint.py:107-127) and the loud refusal of
+    the sampler for this datapoint type."""
+    from geobipy_b200 import _lib, api, tdem
+    g = np.load(os.path.join(golden_dir, "tempest_clean.npz"))
+    system = tdem.TdemSystem(definition=gpu.tempest_definition())
+    assert system.components == ['x', 'z'] and system.nTimes == 15
+    tx = tdem.TdemLoop(x=0.0, y=0.0, z=120.0)
+    rx = tdem.TdemLoop(x=-107.0, y=0.0, z=75.0)
+    dp = tdem.Tempest_datapoint(x=0.0, y=0.0, z=120.0, elevation=0.0, system=[system], transmitter_loop=tx, receiver_loop=rx,
+                                secondary_field=g["data"][0, 10], primary_field=g["primary"][0, 10])
+    assert dp.nChannels == 30 and dp.components == ['x', 'z']
+    mod = api.Model(api.RectilinearMesh1D(edges=np.r_[0.0, g["zwedge"][10], g["zdeep"][10], np.inf]), g["sigma"][0])
+    dp.forward(mod)
+    assert np.allclose(dp.predicted_primary_field, g["primary"][0, 10], rtol=1e-12)
+    assert np.median(np.abs(dp.predicted_secondary_field / g["data"][0, 10] - 1.0)) < 2e-3
+    assert np.allclose(dp.predictedData[:15], dp.predicted_secondary_field[:15] + g["primary"][0, 10, 0])
+    assert np.allclose(dp.data[15:], g["data"][0, 10, 15:] + g["primary"][0, 10, 1])
+    J = dp.sensitivity(mod)
+    assert J.shape == (30, 3)
+    dp.additive_error = TEMPEST_ADDITIVE
+    assert np.allclose(dp.std[:15], np.sqrt((0.01 * dp.data[:15]) ** 2 + TEMPEST_ADDITIVE[:15] ** 2))
+    with pytest.raises(_lib.GeobipyB200Error, match="Z-component dB/dt systems only"):
+        gpu.rjmcmc_run(tempest[0], gpu.make_options(n_markov_chains=100), g["data"][0, :2], np.full(2, 120.0), max_iterations=10)
+    with pytest.raises(NotImplementedError):
+        dp.initialize(initial_relative_error=[0.001, 0.001], initial_additive_error=TEMPEST_ADDITIVE)
