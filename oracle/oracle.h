@@ -70,6 +70,12 @@ typedef struct {
     int32_t comp[GBO_MAXC];           /* component of channel c: 0 = z, 1 = x (fixed-wing systems: Tempest measures X and Z;
                                          TdemDataPoint.forward :1008-1016 stacks SX then -SZ) */
     double rx_cx;                     /* dx / r: direction cosine of the receiver offset (x component of the horizontal field) */
+    /* Tempest_datapoint (classes/data/datapoint/Tempest_datapoint.py): data = secondary + primary field per component
+     * (:107-127); std_c = sqrt((rel[component] data_c)^2 + (multiplier[component] additive_c)^2) with a FIXED additive level
+     * per channel (:141-176); the unknowns are the relative errors and the multipliers, one per component (:478-510) */
+    int32_t tempest, pad_t;
+    double add_level[GBO_MAXC];       /* additive error of channel c (the options file's initial_additive_error vector) */
+    double primary[GBO_MAXC];         /* predicted primary field of channel c's component, added to the forward response */
 } gbo_tdem_system;
 
 /* Everything one chain produces (caller allocates; sizes from gbo_sizes()). */

@@ -64,6 +64,8 @@ class TdemSystemC(ctypes.Structure):
         ("MR", ctypes.c_double * (MAXC * TD_NFREQ)), ("MI", ctypes.c_double * (MAXC * TD_NFREQ)),
         ("t_centre", ctypes.c_double * MAXC),
         ("comp", ctypes.c_int32 * MAXC), ("rx_cx", ctypes.c_double),
+        ("tempest", ctypes.c_int32), ("pad_t", ctypes.c_int32),
+        ("add_level", ctypes.c_double * MAXC), ("primary", ctypes.c_double * MAXC),
     ]
 
 
@@ -206,7 +208,7 @@ def run_chain(sys, opt, data, altitude, seed, sounding_index, max_iterations=0):
     nd = lib().gbo_n_depth(ctypes.byref(opt))
     N2 = 2 * opt.n_markov_chains
     tdem = isinstance(sys, TdemSystemC)
-    eshape = (sys.n_sys, opt.n_err_bins) if tdem else (opt.n_err_bins,)
+    eshape = (max(int(opt.n_systems), 1), opt.n_err_bins) if tdem else (opt.n_err_bins,)   # (Tempest: one entry per component)
     r = dict(
         hitmap=np.zeros((opt.n_sigma_bins, nd), np.int32), edges_hist=np.zeros(nd, np.int32),
         ncells_hist=np.zeros(opt.max_layers + 1, np.int32), rel_hist=np.zeros(eshape, np.int32),
@@ -363,6 +365,50 @@ def make_tdem_system(defs=None, rx_offset=(-13.0, 0.0, 2.0)):
                 c += 1
     s.C = c
     return s
+
+
+TEMPEST_ADDITIVE = np.r_[0.011474, 0.012810, 0.008507, 0.005154, 0.004742, 0.004477, 0.004168, 0.003539, 0.003352, 0.003213, 0.003161,
+                         0.003122, 0.002587, 0.002038, 0.002201, 0.007383, 0.005693, 0.005178, 0.003659, 0.003426, 0.003046, 0.003095,
+                         0.003247, 0.002775, 0.002627, 0.002460, 0.002178, 0.001754, 0.001405, 0.001283]   # tempest_options: initial_additive_error [fT]
+
+
+def tempest_definition():
+    import json
+    return json.load(open(os.path.join(HERE, "..", "geobipy_b200", "data", "tempest.json")))
+
+
+def make_tempest_system(d=None, rx_offset=(-107.0, 0.0, -45.0), additive_level=TEMPEST_ADDITIVE):
+    """A Tempest datapoint type for the SAMPLER oracle: the forward tables of make_tdem_system plus the fixed additive level
+    of every channel and the predicted primary field of its component (Tempest_datapoint.py:107-127, :141-176)."""
+    d = tempest_definition() if d is None else d
+    s = make_tdem_system([d], rx_offset=rx_offset)
+    s.tempest = 1
+    comps = tdem_components(d)
+    prim = tdem_primary_field(d, rx_offset)
+    nw = len(d["window_start"])
+    for q in range(len(comps)):
+        for i in range(nw):
+            s.primary[q * nw + i] = prim[q]
+            s.add_level[q * nw + i] = float(additive_level[q * nw + i])
+    return s
+
+
+def tempest_options(**over):
+    """tempest_options (documentation_source/source/supplementary/options_files/tempest_options): errors per component (x,
+    z); the "additive error" unknown is the multiplier of the fixed additive levels (initially 1, prior bounds
+    minimum / maximum_additive_error)."""
+    o = resolve_options()
+    o.min_edge, o.max_edge, o.min_width = 1.0, 550.0, 1.0   # minimum_thickness None -> 1.0 (RectilinearMesh1D.py:358)
+    o.covariance_scaling, o.gradient_std = 0.5, 5.0
+    o.n_markov_chains = 1000
+    o.n_systems = 2
+    o.rel_init, o.rel_min, o.rel_max, o.rel_prop_var = 0.001, 0.0001, 0.01, 1e-6
+    o.rel_init2, o.rel_min2, o.rel_max2, o.rel_prop_var2 = 0.001, 0.0001, 0.01, 1e-6
+    o.add_init, o.add_min, o.add_max, o.add_prop_var = 1.0, 0.001, 100.0, 1e-6
+    o.add_init2, o.add_min2, o.add_max2, o.add_prop_var2 = 1.0, 0.001, 100.0, 1e-6
+    for k, v in over.items():
+        setattr(o, k, v)
+    return o
 
 
 def tdem_forward(sys, altitude, sigma, thickness):

@@ -207,6 +207,17 @@ static void survey_tdem(survey_t *v, const gbo_tdem_system *sys)
     v->tdem = sys;
     v->C = sys->C;
     v->n_sys = sys->n_sys;
+    if (sys->tempest) {
+        /* one system, errors per COMPONENT in channel order (x, then z): Tempest_datapoint.relative_error :129-139 */
+        int has_x = 0;
+        for (int c = 0; c < sys->C; ++c) has_x |= (sys->comp[c] == 1);
+        v->n_sys = has_x ? 2 : 1;
+        for (int c = 0; c < sys->C; ++c) {
+            v->sys_of[c] = (sys->comp[c] == 1) ? 0 : has_x;
+            v->log_t[c] = log(sys->t_centre[c]);
+        }
+        return;
+    }
     int c = 0;
     for (int s = 0; s < sys->n_sys; ++s)
         for (int i = 0; i < sys->n_win[s]; ++i, ++c) {
@@ -231,7 +242,13 @@ static double o_add_var(const gbo_options *o, int s) { return s ? o->add_prop_va
 static void data_variance(const survey_t *v, const double *data, const double *rel, const double *add, double *var)
 {
     for (int i = 0; i < v->C; ++i) {
-        if (v->tdem) {
+        if (v->tdem && v->tdem->tempest) {
+            /* Tempest_datapoint.std :170-173: (rel_j d)^2 + (multiplier_j additive_c)^2 */
+            const int s = v->sys_of[i];
+            double a = rel[s] * data[i];
+            double b = add[s] * v->tdem->add_level[i];
+            var[i] = a * a + b * b;
+        } else if (v->tdem) {
             const int s = v->sys_of[i];
             double a = rel[s] * data[i];
             double b = exp(log(add[s]) - 0.5 * (v->log_t[i] - log(1e-3)));
@@ -290,13 +307,17 @@ static double height_logprior(const gbo_options *o, double dz)
  * errors (DataPoint.probability :352-389).  height_last = 1 (time domain, solve_transmitter_z): the sampled height is the
  * transmitter loop's and its prior is added after the errors (TdemDataPoint.probability :950-951 =
  * DataPoint.probability + Loop_pair.probability, Loop_pair.py:294-295). */
-static double datapoint_probability(const gbo_options *o, int n_sys, const double *rel, const double *add, double dz, int height_last)
+static double datapoint_probability(const gbo_options *o, const survey_t *v, const double *rel, const double *add, double dz)
 {
+    const int n_sys = v->n_sys, height_last = v->tdem != NULL;
+    /* Tempest: the additive-error multiplier carries a prior only for its histogram bins; DataPoint.probability :385-389
+     * never sees it (additive_error itself has none, Tempest_datapoint.set_priors :478-488) */
+    const int add_prior = !(v->tdem && v->tdem->tempest);
     double p = 0.0;
     if (o->solve_height && !height_last) p += height_logprior(o, dz);
     for (int s = 0; s < n_sys; ++s) {
         if (o->solve_relative_error) p += log_uniform_logpdf(rel[s], o_rel_min(o, s), o_rel_max(o, s));
-        if (o->solve_additive_error) p += log_uniform_logpdf(add[s], o_add_min(o, s), o_add_max(o, s));
+        if (o->solve_additive_error && add_prior) p += log_uniform_logpdf(add[s], o_add_min(o, s), o_add_max(o, s));
     }
     if (o->solve_height && height_last) p += height_logprior(o, dz);
     return p;
@@ -672,8 +693,11 @@ static void forward(chain_t *c, const model_t *m, double z, double *pred)
 {
     double thk[GBO_MAXL];
     model_thickness(m, thk);
-    if (c->sv.tdem) gbo_tdem_forward(c->sv.tdem, z, m->k, m->sigma, thk, pred);
-    else gbo_fdem_forward(c->sv.fdem, z, m->k, m->sigma, thk, pred);
+    if (c->sv.tdem) {
+        gbo_tdem_forward(c->sv.tdem, z, m->k, m->sigma, thk, pred);
+        if (c->sv.tdem->tempest)   /* predictedData = predicted secondary + predicted primary field (:120-127) */
+            for (int i = 0; i < c->sv.C; ++i) pred[i] += c->sv.tdem->primary[i];
+    } else gbo_fdem_forward(c->sv.fdem, z, m->k, m->sigma, thk, pred);
     c->n_forward++;
 }
 static void sensitivity(chain_t *c, const model_t *m, dpoint_t *dp)
@@ -733,7 +757,7 @@ static void chain_init(chain_t *c, gbo_chain_out *out)
     double var[GBO_MAXC];
     data_variance(&c->sv, c->data, c->dp.rel, c->dp.add, var);
     c->misfit = data_misfit(c->C, c->data, c->dp.pred, var);
-    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, c->sv.n_sys, c->dp.rel, c->dp.add, 0.0, c->sv.tdem != NULL);
+    c->prior = model_probability(o, &c->model, c->sigma_ref) + datapoint_probability(o, &c->sv, c->dp.rel, c->dp.add, 0.0);
     c->likelihood = data_likelihood(c->C, c->data, c->dp.pred, var);
     c->posterior = c->likelihood + c->prior;
     c->burned_in = 0;
@@ -802,7 +826,17 @@ static int chain_step(chain_t *c)
         const double rv[2] = {o_rel_var(o, 0), o_rel_var(o, 1)}, rmn[2] = {o_rel_min(o, 0), o_rel_min(o, 1)}, rmx[2] = {o_rel_max(o, 0), o_rel_max(o, 1)};
         const double av[2] = {o_add_var(o, 0), o_add_var(o, 1)}, amn[2] = {o_add_min(o, 0), o_add_min(o, 1)}, amx[2] = {o_add_max(o, 0), o_add_max(o, 1)};
         if (o->solve_relative_error) propose_error2(&c->rng, tdp.rel, rv, rmn, rmx);
-        if (o->solve_additive_error) propose_error2(&c->rng, tdp.add, av, amn, amx);
+        if (o->solve_additive_error) {
+            if (c->sv.tdem && c->sv.tdem->tempest) {
+                /* Tempest_datapoint.perturb :339-341: additive_error_multiplier.perturb() with the defaults - no prior imposed,
+                 * and the proposal's mean is never moved (DataPoint.perturb :561-573 moves only those of the two errors): every
+                 * step draws exp(N(ln initial, var)) around the INITIAL multiplier */
+                double z0, z1;
+                rng_normal2(&c->rng, &z0, &z1);
+                tdp.add[0] = exp(log(o_add_init(o, 0)) + sqrt(av[0]) * z0);
+                tdp.add[1] = exp(log(o_add_init(o, 1)) + sqrt(av[1]) * z1);
+            } else propose_error2(&c->rng, tdp.add, av, amn, amx);
+        }
     }
     if (o->solve_height && c->sv.tdem)
         tdp.z = propose_height(&c->rng, tdp.z, o->height_prop_var, c->z_ref - o->max_height_change, c->z_ref + o->max_height_change);
@@ -810,7 +844,7 @@ static int chain_step(chain_t *c)
     forward(c, &test, tdp.z, tdp.pred);
     data_variance(&c->sv, c->data, tdp.rel, tdp.add, var);
     double t_misfit = data_misfit(C, c->data, tdp.pred, var);
-    double t_prior = datapoint_probability(o, c->sv.n_sys, tdp.rel, tdp.add, tdp.z - c->z_ref, c->sv.tdem != NULL);
+    double t_prior = datapoint_probability(o, &c->sv, tdp.rel, tdp.add, tdp.z - c->z_ref);
     if (t_prior == -INFINITY) return 0;
     t_prior += model_probability(o, &test, c->sigma_ref);
     if (t_prior == -INFINITY) return 0;
@@ -1029,8 +1063,11 @@ int gbo_run_chain_tdem(const gbo_tdem_system *sys, const gbo_options *opt, const
 /* ------------------------------------------------------------------ term-level pin */
 static void sv_forward(const survey_t *sv, double alt, int k, const double *sig, const double *thk, double *pred)
 {
-    if (sv->tdem) gbo_tdem_forward(sv->tdem, alt, k, sig, thk, pred);
-    else gbo_fdem_forward(sv->fdem, alt, k, sig, thk, pred);
+    if (sv->tdem) {
+        gbo_tdem_forward(sv->tdem, alt, k, sig, thk, pred);
+        if (sv->tdem->tempest)
+            for (int i = 0; i < sv->C; ++i) pred[i] += sv->tdem->primary[i];
+    } else gbo_fdem_forward(sv->fdem, alt, k, sig, thk, pred);
 }
 static void sv_sensitivity(const survey_t *sv, double alt, int k, const double *sig, const double *thk, double *J)
 {
@@ -1084,7 +1121,7 @@ static int eval_transition_impl(const survey_t *sv, const gbo_options *o, gbo_tr
     sv_forward(sv, z_test, k, test.sigma, thk, t->pred_test);
     data_variance(sv, t->data, t->rel_test, t->add_test, var);
     t->misfit_test = data_misfit(C, t->data, t->pred_test, var);
-    t->prior_test = datapoint_probability(o, sv->n_sys, t->rel_test, t->add_test, o->solve_height ? z_test - t->altitude_ref : 0.0, sv->tdem != NULL) +
+    t->prior_test = datapoint_probability(o, sv, t->rel_test, t->add_test, o->solve_height ? z_test - t->altitude_ref : 0.0) +
                     model_probability(o, &test, t->sigma_ref);
     t->likelihood_test = data_likelihood(C, t->data, t->pred_test, var);
     t->proposal = 1.0;

@@ -37,8 +37,8 @@ class Earth:
 class Geometry:
     def __init__(self, tx_height, tx_roll, tx_pitch, tx_yaw, txrx_dx, txrx_dy, txrx_dz, rx_roll, rx_pitch, rx_yaw):
         assert tx_roll == tx_pitch == tx_yaw == rx_roll == rx_pitch == rx_yaw == 0.0
-        assert (txrx_dx, txrx_dy, txrx_dz) == (-13.0, 0.0, 2.0)
         self.tx_height = float(tx_height)
+        self.offset = (float(txrx_dx), float(txrx_dy), float(txrx_dz))
 
 
 class _Response:
@@ -48,10 +48,86 @@ class _Response:
         self.SX, self.SY, self.SZ = z, z, sz
 
 
+class _Components:
+    pass
+
+
+class _GenericSystem:
+    """Any single system that is not one of the two SkyTEM moments (the fixed-wing Tempest system: X and Z components of
+    the B field, primary field): the oracle's generalised restatement, one oracle system per receiver offset."""
+    CONDUCTIVITYDERIVATIVE = 1
+
+    def __init__(self, stmfile):
+        sys.path.insert(0, os.path.join(HERE, "..", ".."))
+        from geobipy_b200 import tdem
+        self.d = tdem.read_stm(stmfile)
+        self.comps = O.tdem_components(self.d)
+        self.nw = len(self.d["window_start"])
+        self.windows = types.SimpleNamespace(centre=0.5 * (np.asarray(self.d["window_start"]) + np.asarray(self.d["window_end"])))
+        self.waveform = types.SimpleNamespace()
+        self._cache, self._last = {}, None
+
+    def loopRadius(self):
+        return float(self.d.get("loop_radius", 0.0))
+
+    def _sys(self, G):
+        if G.offset not in self._cache:
+            self._cache[G.offset] = O.make_tdem_system([self.d], rx_offset=G.offset)
+        return self._cache[G.offset]
+
+    def _split(self, v, G=None):
+        """our channel order (x windows, z windows; z up) -> gatdaem1d's SX / SY / SZ (z down: the reference negates it)"""
+        r = _Components()
+        zero = np.zeros((self.nw,) + np.shape(v)[1:])
+        r.SX, r.SY, r.SZ = zero, zero, zero
+        o = 0
+        for c in self.comps:
+            if c == "x":
+                r.SX = v[o:o + self.nw]
+            else:
+                r.SZ = -v[o:o + self.nw]
+            o += self.nw
+        if G is not None:
+            p = O.tdem_primary_field(self.d, G.offset)
+            r.PX = r.PY = r.PZ = 0.0
+            for c, val in zip(self.comps, p):
+                if c == "x":
+                    r.PX = val
+                else:
+                    r.PZ = -val
+        return r
+
+    def _thk(self, E):
+        return np.r_[E.thickness, 1.0]
+
+    def forwardmodel(self, G, E):
+        self._last = (G, E)
+        return self._split(O.tdem_forward(self._sys(G), G.tx_height, E.conductivity, self._thk(E)), G)
+
+    def fm_dlogc(self, G, E):
+        self._last = (G, E)
+        out = O.tdem_forward(self._sys(G), G.tx_height, E.conductivity, self._thk(E))
+        J = self._split(O.tdem_sensitivity(self._sys(G), G.tx_height, E.conductivity, self._thk(E)))
+        return self._split(out, G), J.SX.T, np.zeros_like(J.SX.T), J.SZ.T
+
+    def derivative(self, dtype, layer):
+        G, E = self._last
+        J = O.tdem_sensitivity(self._sys(G), G.tx_height, E.conductivity, self._thk(E))
+        return self._split(J[:, layer - 1] / E.conductivity[layer - 1])   # d/d sigma: the reference re-multiplies by sigma
+
+
 class TDAEMSystem:
     CONDUCTIVITYDERIVATIVE = 1
 
     def __init__(self, stmfile):
+        text = open(stmfile).read()
+        first = [ln.split("=")[1].strip().lower() for ln in text.splitlines() if ln.strip().startswith("OutputType")]
+        self._generic = None
+        if first and first[0] == "b":     # not a SkyTEM moment: the generalised restatement (Tempest)
+            g = self._generic = _GenericSystem(stmfile)
+            self.windows, self.waveform = g.windows, g.waveform
+            self.loopRadius, self.forwardmodel, self.fm_dlogc, self.derivative = g.loopRadius, g.forwardmodel, g.fm_dlogc, g.derivative
+            return
         base, self._radius = None, 0.0
         for line in open(stmfile):
             if "BaseFrequency" in line:
@@ -75,6 +151,7 @@ class TDAEMSystem:
 
     def forwardmodel(self, G, E):
         tsys, _ = _dual()
+        assert G.offset == (-13.0, 0.0, 2.0)
         self._last = (G, E)
         out = O.tdem_forward(tsys, G.tx_height, E.conductivity, self._thk(E))
         return _Response(-out[self._slice])          # the reference negates the z component

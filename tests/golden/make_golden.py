@@ -6,6 +6,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py fdem         # resolve_clean.npz, fdem_random_models.npz
     python tests/golden/make_golden.py fdem_tensor  # fdem_tensor_models.npz (tensor ids 3 / 7, vertical coil offsets)
     python tests/golden/make_golden.py tdem         # skytem_clean.npz
+    python tests/golden/make_golden.py tempest_transitions   # tempest_transitions.npz (reference sampler with a Tempest_datapoint)
     python tests/golden/make_golden.py tempest      # tempest_clean.npz (X and Z components, B field, point dipole)
     python tests/golden/make_golden.py tdem_transitions   # tdem_transitions.npz (reference sampler + fake_gatdaem1d)
     python tests/golden/make_golden.py tdem_chain <i> [rep]   # ref_tdem_chain_<i>[_r<rep>].npz (minutes each)
@@ -793,8 +794,156 @@ def make_tempest():
     print("tempest", data.shape, geom)
 
 
+def _tempest_setup():
+    import fake_gatdaem1d
+    fake_gatdaem1d.install()
+    _geobipy()
+    from geobipy import user_parameters
+    kw = dict(user_parameters.read(os.path.join(SUP, "options_files/tempest_options")))
+    kw["interactive_plot"] = False
+    kw["save_hdf5"] = True
+    for k in ("data_type", "data_filename", "system_filename", "data_directory", "seed"):
+        kw.pop(k, None)
+    return kw
+
+
+def _tempest_datapoint(secondary, primary, z=120.0):
+    from geobipy import Tempest_datapoint, CircularLoop
+    tx = CircularLoop(x=0.0, y=0.0, z=z, pitch=0.0, roll=0.0, yaw=0.0, radius=1.0)
+    rx = CircularLoop(x=-107.0, y=0.0, z=z - 45.0, pitch=0.0, roll=0.0, yaw=0.0, radius=1.0)
+    return Tempest_datapoint(x=0.0, y=0.0, z=z, elevation=0.0, secondary_field=secondary, primary_field=primary,
+                             system=[os.path.join(SUP, "data/tempest.stm")], transmitter_loop=tx, receiver_loop=rx)
+
+
+def _tempest_observed(sidx, O, tsys):
+    """Synthetic Tempest sounding `sidx`: the shared true-model generator, 120 m, noise = tempest_options' error model."""
+    edges, sigma, _, noise = synthetic_sounding(sidx, 400.0, 30)
+    clean = O.tdem_forward(tsys, 120.0, sigma, np.r_[np.diff(edges)[:-1], 1.0])
+    prim = np.repeat(O.tdem_primary_field(O.tempest_definition(), (-107.0, 0.0, -45.0)), 15)
+    std = np.sqrt((0.001 * (clean + prim)) ** 2 + O.TEMPEST_ADDITIVE ** 2)
+    return clean + noise * std, prim[[0, 15]]
+
+
+def make_tempest_transitions(n_soundings=4, n_iter=200):
+    """tempest_transitions.npz: per-term records of the reference's Inference1D.accept_reject with a Tempest_datapoint and
+    tempest_options (errors per component, additive-error multiplier, data = secondary + primary field), the external
+    gatdaem1d replaced by tests/golden/fake_gatdaem1d.py over the oracle's forward."""
+    kw0 = _tempest_setup()
+    from geobipy import Inference1D, get_prng
+    import oracle_py as O
+    from numpy import inf as npinf
+    import io
+    import contextlib
+    tsys = O.make_tdem_system([O.tempest_definition()], rx_offset=(-107.0, 0.0, -45.0))
+    recs = []
+    for sidx in range(n_soundings):
+        sec, prim = _tempest_observed(sidx, O, tsys)
+        kw = dict(kw0)
+        kw["prng"] = get_prng(seed=6000 + sidx)
+        inf = Inference1D(**kw)
+        dp = _tempest_datapoint(sec, prim)
+        with contextlib.redirect_stdout(io.StringIO()):
+            inf.initialize(dp)
+        hs = float(inf.halfspace.item())
+        init = dict(prior=float(inf.prior), likelihood=float(inf.likelihood), misfit=float(inf.data_misfit))
+        for it in range(n_iter):
+            dp0, m0 = inf.datapoint, inf.model
+            J_in = np.asarray(dp0.sensitivity_matrix).copy()
+            pred_in = np.asarray(dp0.predictedData).copy()
+            rel_cur = np.asarray(dp0.relative_error).copy()
+            add_cur = np.asarray(dp0.additive_error_multiplier).copy()
+            tdp = deepcopy(dp0)
+            remapped, test = m0.perturb(tdp, -npinf, npinf, alpha=inf.covariance_scaling)
+            action = ACT[remapped.mesh.action[0]]
+            k = int(remapped.nCells.item())
+            grad = np.asarray(remapped.local_gradient(observation=tdp)).copy()
+            H = np.asarray(test.values.proposal.variance).copy()
+            mean = np.asarray(test.values.proposal.mean).copy()
+            tdp.perturb()
+            tdp.forward(test)
+            misfit = float(tdp.data_misfit())
+            prior = float(tdp.probability) + float(test.probability(inf.solve_parameter, inf.solve_gradient))
+            like = float(tdp.likelihood(log=True))
+            prop, prop1 = test.proposal_probabilities(remapped, tdp, alpha=inf.covariance_scaling)
+            recs.append(dict(sounding=sidx, altitude=120.0, sigma_ref=hs, data=np.asarray(dp0.data).copy(), k=k, action=action,
+                             edges=np.asarray(remapped.mesh.edges).copy(), sigma_remap=np.asarray(remapped.values).copy(),
+                             sigma_test=np.asarray(test.values).copy(), rel_cur=rel_cur, add_cur=add_cur,
+                             rel_test=np.asarray(tdp.relative_error).copy(), add_test=np.asarray(tdp.additive_error_multiplier).copy(),
+                             J_in=J_in, pred_in=pred_in, H=H, gradient=grad, newton_mean=mean,
+                             pred_test=np.asarray(tdp.predictedData).copy(), std_test=np.asarray(tdp.std).copy(),
+                             misfit_test=misfit, prior_test=prior, likelihood_test=like, proposal=float(prop),
+                             proposal1=float(prop1), init_prior=init["prior"], init_likelihood=init["likelihood"],
+                             init_misfit=init["misfit"], alpha=float(inf.covariance_scaling)))
+            log_alpha = (prior - inf.prior) + (like - inf.likelihood) + (prop - prop1)
+            if np.exp(log_alpha) > inf.prng.uniform():
+                inf.data_misfit, inf.prior, inf.likelihood = misfit, prior, like
+                inf.model, inf.datapoint = test, tdp
+        print("tempest sounding", sidx, "k now", inf.model.nCells.item(), "halfspace", hs, flush=True)
+    n = len(recs)
+    out = {}
+    for key in recs[0]:
+        vals = [r[key] for r in recs]
+        if np.ndim(vals[0]) == 0:
+            out[key] = np.asarray(vals)
+        else:
+            obj = np.empty(n, dtype=object)
+            for i, v in enumerate(vals):
+                obj[i] = np.asarray(v)
+            out[key] = obj
+    np.savez_compressed(os.path.join(HERE, "tempest_transitions.npz"), **out)
+    print("tempest transitions written:", n, "actions", np.bincount(out["action"], minlength=4))
+
+
+def make_tempest_chain(sidx, rep=0, n_markov_chains=10000):
+    """A full chain of the live reference with a Tempest_datapoint (tempest_options with n_markov_chains raised to 10 000),
+    driven through fake_gatdaem1d (oracle forward).  Posterior arrays -> ref_tempest_chain_<i>[_r<rep>].npz."""
+    kw = _tempest_setup()
+    from geobipy import Inference1D, get_prng
+    import oracle_py as O
+    import io
+    import contextlib
+    tsys = O.make_tdem_system([O.tempest_definition()], rx_offset=(-107.0, 0.0, -45.0))
+    sec, prim = _tempest_observed(sidx, O, tsys)
+    kw["n_markov_chains"] = n_markov_chains
+    kw["prng"] = get_prng(seed=8000 + sidx + 100 * rep)
+    inf = Inference1D(**kw)
+    dp = _tempest_datapoint(sec, prim)
+    t0 = time.time()
+    go, failed = True, False
+    with contextlib.redirect_stdout(io.StringIO()):
+        inf.initialize(dp)
+        while go:  # Inference1D.infer :650-677 without the HDF5 write
+            failed = inf.accept_reject()
+            inf.update()
+            go = (not failed) and (inf.iteration <= inf.n_markov_chains + inf.burned_in_iteration)
+            if (not failed) and (not inf.burned_in):
+                go = inf.iteration < inf.n_markov_chains
+                if not go:
+                    failed = True
+    dt = time.time() - t0
+    it = int(inf.iteration)
+    d = inf.datapoint
+    np.savez_compressed(
+        os.path.join(HERE, "ref_tempest_chain_%d%s.npz" % (sidx, "" if rep == 0 else "_r%d" % rep)),
+        sounding=sidx, data=np.asarray(d.data, dtype=np.float64), secondary=sec, primary=prim, altitude=120.0,
+        halfspace=float(inf.halfspace.item()), iterations=it, failed=bool(failed), burned_in=bool(inf.burned_in),
+        burned_in_iteration=int(inf.burned_in_iteration),
+        hitmap=np.asarray(inf.model.values.posterior.counts, dtype=np.int32),
+        edges_hist=np.asarray(inf.model.mesh.edges.posterior.counts, dtype=np.int32),
+        ncells_hist=np.asarray(inf.model.mesh.nCells.posterior.counts, dtype=np.int32),
+        rel_hist=np.stack([np.asarray(p.counts, dtype=np.int32) for p in d.relative_error.posterior]),
+        add_hist=np.stack([np.asarray(p.counts, dtype=np.int32) for p in d.additive_error_multiplier.posterior]),
+        misfit_trace=np.asarray(inf.data_misfit_v[:it], dtype=np.float32),
+        accept_trace=np.asarray(inf.acceptance_v[:it + 1], dtype=np.uint8), seconds=dt, n_markov_chains=n_markov_chains)
+    print("tempest chain", sidx, rep, "iterations", it, "burned in", inf.burned_in, inf.burned_in_iteration, "s/it", dt / it)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "tempest_chain":
+        make_tempest_chain(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    if what == "tempest_transitions":
+        make_tempest_transitions()
     if what == "tempest":
         make_tempest()
     if what == "readers":

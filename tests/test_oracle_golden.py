@@ -515,6 +515,44 @@ def test_tdem_transition_terms_match_live_reference(oracle, golden_dir):
     assert changed_errors > 0.45 * n   # the per-system error proposals really moved (every second record is checked)
 
 
+def test_tempest_transition_terms_match_live_reference(oracle, golden_dir):
+    """800 transitions of the reference's own Inference1D.accept_reject with a Tempest_datapoint and tempest_options
+    (tests/golden/fake_gatdaem1d.py over the oracle's forward).  Pins the Tempest datapoint's model around the forward:
+    data = secondary + primary field per component (Tempest_datapoint.py:107-127), std from one relative error and one
+    additive-error multiplier per component over fixed per-channel additive levels (:141-176), a prior that counts the
+    relative errors only (:478-488, DataPoint.probability :385-389), gradient_standard_deviation 5, the 30-channel
+    Gauss-Newton matrix, misfit, likelihood and both proposal densities."""
+    g = np.load(os.path.join(golden_dir, "tempest_transitions.npz"), allow_pickle=True)
+    s, o = oracle.make_tempest_system(), oracle.tempest_options()
+    n = len(g["k"])
+    assert n >= 800 and set(np.unique(g["action"])) == {0, 1, 2, 3}
+    assert np.all(g["alpha"] == o.covariance_scaling)
+    moved = 0
+    for i in range(n):
+        kw = {k: g[k][i] for k in g.files}
+        rc, r = oracle.eval_transition(s, o, **kw)
+        assert rc == 0
+        k = int(kw["k"])
+        Href = np.asarray(kw["H"], dtype=np.float64).reshape(k, k)
+        assert np.max(np.abs(np.linalg.inv(r["hessian"]) - Href)) <= 1e-6 * np.max(np.abs(Href)), i
+        gref = np.asarray(kw["gradient"], dtype=np.float64)
+        assert np.max(np.abs(r["gradient"] - gref)) <= 1e-6 * (np.max(np.abs(gref)) + 1e-12), i
+        assert np.max(np.abs(r["newton_mean"] / np.asarray(kw["newton_mean"], dtype=np.float64) - 1)) < 1e-6, i
+        assert np.allclose(r["pred_test"], np.asarray(kw["pred_test"], dtype=np.float64), rtol=1e-12, atol=0.0)
+        for name in ("misfit_test", "prior_test", "likelihood_test", "proposal", "proposal1"):
+            a, b = r[name], float(kw[name])
+            if np.isfinite(b):
+                assert abs(a - b) <= 1e-7 * (abs(b) + 1.0), (i, name, a, b)
+            else:
+                assert (a == b) or (np.isnan(a) and np.isnan(b)), (i, name, a, b)
+        moved += int(np.any(np.asarray(kw["add_test"]) != np.asarray(kw["add_cur"])))
+    assert moved > 0.9 * n
+    # the multiplier is re-drawn around its INITIAL value every step (its proposal's mean is never moved, and no prior is
+    # imposed: Tempest_datapoint.perturb :339-341): it never drifts
+    m = np.array([np.asarray(a, dtype=np.float64) for a in g["add_test"]])
+    assert np.all(np.abs(np.log(m)) < 6e-3) and np.std(np.log(m)) < 1.5e-3
+
+
 def test_tdem_initial_state_matches_live_reference(oracle, golden_dir):
     """Best half-space, initial misfit / likelihood / prior of the reference's Inference1D.initialize with a
     TdemDataPoint."""
