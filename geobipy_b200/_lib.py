@@ -74,8 +74,9 @@ class TdemSystemC(ctypes.Structure):
 
 class TdemSurveyC(ctypes.Structure):
     """gbp_tdem_survey"""
-    _fields_ = [("n_systems", ctypes.c_int32), ("pad_", ctypes.c_int32), ("sys", TdemSystemC * TD_MAXSYS),
-                ("rx_dx", ctypes.c_double), ("rx_dy", ctypes.c_double), ("rx_dz", ctypes.c_double)]
+    _fields_ = [("n_systems", ctypes.c_int32), ("error_model", ctypes.c_int32), ("sys", TdemSystemC * TD_MAXSYS),
+                ("rx_dx", ctypes.c_double), ("rx_dy", ctypes.c_double), ("rx_dz", ctypes.c_double),
+                ("additive_level", ctypes.c_double * TD_MAXC)]
 
 
 BUFFER_FIELDS = ("hitmap", "edges_hist", "ncells_hist", "rel_hist", "add_hist", "misfit_trace", "accept_trace",

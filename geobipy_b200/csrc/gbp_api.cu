@@ -1164,7 +1164,8 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     if (B <= 0) return 0;
     if (check_options(opt)) return 1;
     if (!d_buf || !d_buf->scalars) return fail("gbp_chain_buffers.scalars is required");
-    if ((opt->n_systems > 1 ? 2 : 1) != sv->n_systems)
+    const bool tempest = sv->error_model == 1;
+    if (!tempest && (opt->n_systems > 1 ? 2 : 1) != sv->n_systems)
         return fail("gbp_options.n_systems must equal the number of systems of the datapoint type");
     // the sampler kernels hold GBP_TD_SAMPLER_MAXC channels per chain in shared memory (the forward / Jacobian
     // operators take GBP_TD_MAXC); checked before any device work
@@ -1172,10 +1173,13 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
         return fail("time-domain sampler: at most 48 data channels per datapoint (GBP_TD_SAMPLER_MAXC)");
     for (int s = 0; s < sv->n_systems && s < GBP_TD_MAXSYS; ++s) {
         const TdOutput o = td_output(sv->sys[s]);
-        if (o.n_comp != 1 || o.comp[0] != 0 || o.b_field)
-            return fail("time-domain sampler: Z-component dB/dt systems only (the error model of a Tempest datapoint, "
-                        "Tempest_datapoint.std :141-176, is not built; the forward / Jacobian operators take X and B systems)");
+        if (!tempest && (o.n_comp != 1 || o.comp[0] != 0 || o.b_field))
+            return fail("time-domain sampler: a system that measures X or reports B needs the Tempest error model "
+                        "(gbp_tdem_survey.error_model = 1 with the additive level of every channel)");
+        if (tempest && (opt->n_systems > 1 ? 2 : 1) != o.n_comp)
+            return fail("Tempest error model: gbp_options.n_systems must equal the number of measured components");
     }
+    if (tempest && opt->solve_height) return fail("Tempest error model: the transmitter height is not sampled (solve_height)");
     TdCache* tc;
     if (get_td_tables(sv, &tc, true)) return 1;
     ChainParams P;
@@ -1193,6 +1197,22 @@ int gbp_tdem_rjmcmc_run(const gbp_tdem_survey* sv, const gbp_options* opt, int B
     P.data_scale = 1.0;
     cudaStream_t st = (cudaStream_t)stream;
     const TdDev& sd = tc->host.dev;
+    if (tempest) {
+        // the additive-error unknowns are dimensionless multipliers: in the scaled data units of the fp32 kernel it is the
+        // additive LEVELS and the primary field that scale with the data
+        TdDev sq = sd;
+        if (precision == GBP_PRECISION_F32) {
+            P.data_scale = TD_F32_SCALE;
+            for (int c = 0; c < GBP_TD_MAXC; ++c) {
+                sq.tsc[c] *= TD_F32_SCALE;
+                sq.poff[c] *= TD_F32_SCALE;
+            }
+            return launch_chain<float, float, GBP_TD_SAMPLER_MAXC, 12, KIND_TEMPEST>(sq, tc->d_f32, (size_t)TD_ROWS * TD_CP * sizeof(float), P, st);
+        }
+        if (precision == GBP_PRECISION_F64)
+            return launch_chain<double, double, GBP_TD_SAMPLER_MAXC, 8, KIND_TEMPEST>(sq, tc->d_f64, (size_t)TD_ROWS * TD_CP * sizeof(double), P, st);
+        return fail("precision must be GBP_PRECISION_F32 or GBP_PRECISION_F64");
+    }
     if (precision == GBP_PRECISION_F32) {
         // scaled data units: additive errors scale with the data
         P.data_scale = TD_F32_SCALE;

@@ -53,8 +53,13 @@ enum { BV_POSTERIOR = 0, BV_REL, BV_ADD, BV_REL2, BV_ADD2, BV_N = 8 };
 // KIND_TDEM_Z: a time-domain datapoint whose TRANSMITTER height is sampled (the options file's solve_transmitter_z:
 // TdemDataPoint.perturb :681-683 -> Loop_pair.perturb -> Point.perturb on the transmitter loop; prior added after the
 // error priors, TdemDataPoint.probability :950-951; fixed receiver offset).
-enum { KIND_FDEM = 0, KIND_TDEM = 1, KIND_FDEM_Z = 2, KIND_TDEM_Z = 3 };
-__host__ __device__ constexpr bool is_td(int kind) { return kind == KIND_TDEM || kind == KIND_TDEM_Z; }
+// KIND_TEMPEST: a fixed-wing Tempest_datapoint (classes/data/datapoint/Tempest_datapoint.py): X and Z components (two
+// passes of tdem_eval, J1 / J0 Hankel weights), data = secondary + primary field (:107-127), one relative error and one
+// additive-error multiplier per COMPONENT over fixed per-channel additive levels (:141-176) - the two-"system" error arrays
+// of KIND_TDEM indexed by component, the per-channel scale table holding the additive levels - a prior that counts the
+// relative errors only (:478-488), and a multiplier re-drawn around its INITIAL value every step (:339-341).
+enum { KIND_FDEM = 0, KIND_TDEM = 1, KIND_FDEM_Z = 2, KIND_TDEM_Z = 3, KIND_TEMPEST = 4 };
+__host__ __device__ constexpr bool is_td(int kind) { return kind == KIND_TDEM || kind == KIND_TDEM_Z || kind == KIND_TEMPEST; }
 __host__ __device__ constexpr bool has_z(int kind) { return kind == KIND_FDEM_Z || kind == KIND_TDEM_Z; }
 __host__ __device__ constexpr int ns_of(int kind) { return is_td(kind) ? GBP_TD_MAXSYS : 1; }
 template <typename T, int KIND> struct SysOf {
@@ -66,6 +71,10 @@ template <typename T> struct SysOf<T, KIND_TDEM> {
     typedef TdDev dev;
 };
 template <typename T> struct SysOf<T, KIND_TDEM_Z> {
+    typedef TdShared<T> shared;
+    typedef TdDev dev;
+};
+template <typename T> struct SysOf<T, KIND_TEMPEST> {
     typedef TdShared<T> shared;
     typedef TdDev dev;
 };
@@ -83,6 +92,13 @@ template <typename T> struct FwdExtra<T, KIND_TDEM_Z> {
     T lam[2][GBP_TD_MAXLAM], wgt[2][GBP_TD_MAXLAM];
     T sbuf[TD_ROWS];
     T alt[2];   // height each set was computed for
+    int cur;
+};
+// X and Z components: the same abscissae under two weight sets (wgt[0]: J0, the z channels; wgt[1]: J1 dx / r, the x channels)
+template <typename T> struct FwdExtra<T, KIND_TEMPEST> {
+    T lam[1][GBP_TD_MAXLAM], wgt[2][GBP_TD_MAXLAM];
+    T sbuf[TD_ROWS];
+    T alt[1];
     int cur;
 };
 // relative / additive errors, one per system (registers)
@@ -187,7 +203,8 @@ struct ChainParams {
     unsigned long long* finish_ns;  // debug (GBP_DEBUG_TIMELINE): [B + 1] %globaltimer at the end of each chain, [B] = earliest start
 };
 
-template <typename R> __device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c, const bool height_last)
+template <typename R>
+__device__ __noinline__ void make_consts(const gbp_options& o, int n_depth, int C, Consts<R>& c, const bool height_last, const bool add_prior = true)
 {
     c.cum0 = (R)o.p_birth;
     c.cum1 = (R)(o.p_birth + o.p_death);
@@ -232,7 +249,8 @@ template <typename R> __device__ __noinline__ void make_consts(const gbp_options
         // Uniform(log=True) priors: the proposals are forced inside their bounds (or fall back to the current
         // values), so DataPoint.probability (:351-395) is this constant
         if (o.solve_relative_error) lp += -dlog_(dlog_(rmax) - dlog_(rmin));
-        if (o.solve_additive_error) lp += -dlog_(dlog_(amax) - dlog_(amin));
+        // (Tempest: the additive-error multiplier's prior only gives its histogram its bins, DataPoint.probability never sees it)
+        if (o.solve_additive_error && add_prior) lp += -dlog_(dlog_(amax) - dlog_(amin));
     }
     if (c.n_sys == 1) {
         c.rel_lnmin[1] = c.rel_lnmin[0]; c.rel_lnmax[1] = c.rel_lnmax[0]; c.rel_sd[1] = c.rel_sd[0];
@@ -371,7 +389,17 @@ __device__ __noinline__ void ch_forward(WarpState<R, T, NC, KIND>* w, const type
         // the geometry set of the height this evaluation is for (KIND_TDEM_Z: current or proposed)
         int g = 0;
         if constexpr (KIND == KIND_TDEM_Z) g = (alt == w->fx.alt[w->fx.cur]) ? w->fx.cur : (w->fx.cur ^ 1);
-        tdem_eval<T>(*S, tab, w->fx.lam[g], w->fx.wgt[g], kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
+        if constexpr (KIND == KIND_TEMPEST) {
+            // one pass per component (each writes the channels of its component), then the predicted primary field:
+            // predictedData = predicted secondary + primary (Tempest_datapoint.py:120-127)
+            tdem_eval<T>(*S, tab, w->fx.lam[0], w->fx.wgt[0], kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr, S->ccomp, 0);
+            tdem_eval<T>(*S, tab, w->fx.lam[0], w->fx.wgt[1], kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr, S->ccomp, 1);
+#pragma unroll 1
+            for (int c = lane; c < S->C; c += 32) pred[c] += S->poff[c];
+            __syncwarp();
+        } else {
+            tdem_eval<T>(*S, tab, w->fx.lam[g], w->fx.wgt[g], kk, w->msig, w->mthk, w->fx.sbuf, pred, J, J != nullptr);
+        }
     } else {
         if constexpr (sizeof(T) == 4) {
             if (w->team) {   // the team evaluates it (and this warp its share of the team's other requests)
@@ -1164,10 +1192,18 @@ __device__ __forceinline__ void ar_step(WarpState<R, T, NC, KIND>* w, const Cons
                     rng.block = pr.block;
                 }
                 if (K->solve_add) {
-                    const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.add[0], ln_err.add[NS - 1], K->add_sd, K->add_lnmin, K->add_lnmax);
-                    ln_t_err.add[0] = pr.x0;
-                    ln_t_err.add[NS - 1] = pr.x1;
-                    rng.block = pr.block;
+                    if constexpr (KIND == KIND_TEMPEST) {
+                        // additive_error_multiplier.perturb() with the defaults (Tempest_datapoint.perturb :339-341): no prior
+                        // imposed, and the proposal's mean is never moved - every step draws around the INITIAL multiplier
+                        const pair_t<R> z = normal2_at<R>(rng.block++, rng.iter, rng.snd_lo, rng.snd_hi, rng.seed_lo, rng.seed_hi);
+                        ln_t_err.add[0] = K->add_ln0[0] + K->add_sd[0] * z.a;
+                        ln_t_err.add[NS - 1] = K->add_ln0[1] + K->add_sd[1] * z.b;
+                    } else {
+                        const prop2_t<R> pr = ch_propose_ln_error2<R>(rng, ln_err.add[0], ln_err.add[NS - 1], K->add_sd, K->add_lnmin, K->add_lnmax);
+                        ln_t_err.add[0] = pr.x0;
+                        ln_t_err.add[NS - 1] = pr.x1;
+                        rng.block = pr.block;
+                    }
                 }
             }
 #pragma unroll
@@ -1641,6 +1677,7 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
     const int n_active = warp_sum_i(act);
     if constexpr (is_td(KIND)) {
         td_geometry<T>(*S, P.altitude[chain], w->fx.lam[0], w->fx.wgt[0]);
+        if constexpr (KIND == KIND_TEMPEST) td_geometry<T>(*S, P.altitude[chain], w->fx.lam[0], w->fx.wgt[1], true);
         if (lane == 0) {
             w->fx.cur = 0;
             w->fx.alt[0] = alt;
@@ -1926,7 +1963,8 @@ __device__ __forceinline__ void run_chain(WarpState<R, T, NC, KIND>* w, const Co
         s[GBP_S_N_FORWARD] = (double)w->ctr[CT_N_FWD];
         s[GBP_S_N_SENS] = (double)w->ctr[CT_N_SENS];
         // undo the data scaling: variances scale by data_scale^2, so the log-likelihood shifts by n ln(scale)
-        const double inv_sc = 1.0 / P.data_scale;
+        // (Tempest: the additive unknowns are dimensionless multipliers - the scaling went into the additive levels)
+        const double inv_sc = (KIND == KIND_TEMPEST) ? 1.0 : 1.0 / P.data_scale;
         const double lik_shift = (P.data_scale != 1.0) ? (double)n_active * dlog_(P.data_scale) : 0.0;
         s[GBP_S_BEST_POSTERIOR] = (double)w->bestv[BV_POSTERIOR] + lik_shift;
         s[GBP_S_CUR_REL] = (double)err.rel[0];
@@ -1984,7 +2022,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     if constexpr (is_td(KIND)) tab_bytes = (uint32_t)(TD_ROWS * TD_CP * sizeof(T));
     else tab_bytes = fdem_table_bytes<T>(S);
     if (threadIdx.x == 0) {
-        make_consts<R>(P.opt, P.n_depth, P.C, consts, is_td(KIND));
+        make_consts<R>(P.opt, P.n_depth, P.C, consts, is_td(KIND), KIND != KIND_TEMPEST);
         if constexpr (is_td(KIND)) {
             fill_td_shared<T>(S, sys_s);
             for (int i = 0; i < GBP_TD_MAXC; ++i) {

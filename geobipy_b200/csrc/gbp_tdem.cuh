@@ -39,8 +39,9 @@ struct TdDev {
     double tsc[GBP_TD_MAXC];      // sqrt(1 ms / t_c): additive-error scaling of channel c (TdemDataPoint.py:369)
     int csys[GBP_TD_MAXC];        // system of channel c
     int ccomp[GBP_TD_MAXC];       // component of channel c: 0 = z, 1 = x
-    int has_x, pad2;              // some channel measures the x component (fixed-wing systems: Tempest)
+    int has_x, tempest;           // some channel measures the x component; the Tempest datapoint's error model (sampler)
     double rx_cx;                 // dx / r: direction cosine of the receiver offset
+    double poff[GBP_TD_MAXC];     // Tempest: predicted primary field of channel c's component (added to the response)
 };
 
 template <typename T> struct TdShared {
@@ -49,11 +50,15 @@ template <typename T> struct TdShared {
     double xi[GBP_TD_MAXLAM], tw[GBP_TD_MAXLAM];   // td_geometry (per sounding; per proposal when the height is sampled)
     double rx_r, rx_dz, loop_radius, rx_cx;
     signed char ccomp[GBP_TD_MAXC];
+    T poff[GBP_TD_MAXC];
 };
 template <typename T> __device__ __forceinline__ void fill_td_shared(const TdDev& S, TdShared<T>& q)
 {
     q.rx_cx = S.rx_cx;
-    for (int i = 0; i < GBP_TD_MAXC; ++i) q.ccomp[i] = (signed char)S.ccomp[i];
+    for (int i = 0; i < GBP_TD_MAXC; ++i) {
+        q.ccomp[i] = (signed char)S.ccomp[i];
+        q.poff[i] = (T)S.poff[i];
+    }
     q.n_lam = S.n_lam;
     q.C = S.C;
     for (int i = 0; i < TD_NF; ++i) q.omu[i] = (T)S.omu[i];
@@ -95,8 +100,8 @@ template <typename T>
 __device__ __noinline__ void tdem_eval(const TdShared<T>& Q, const T* __restrict__ Mt, const T* __restrict__ lam,
                                        const T* __restrict__ wgt, int L, const T* __restrict__ msig,
                                        const T* __restrict__ mthk, T* __restrict__ sbuf, T* __restrict__ pred,
-                                       T* __restrict__ J, const bool sens)
-{
+                                       T* __restrict__ J, const bool sens, const signed char* ccomp = nullptr, const int comp = 0)
+{   // ccomp != nullptr: only the channels c with ccomp[c] == comp are written (one call per measured component)
     __builtin_assume(__isShared(&Q));
     __builtin_assume(__isShared(Mt));
     __builtin_assume(__isShared(lam));
@@ -190,6 +195,7 @@ __device__ __noinline__ void tdem_eval(const TdShared<T>& Q, const T* __restrict
     __syncwarp();
 #pragma unroll 1
     for (int c = lane; c < C; c += 32) {
+        if (ccomp != nullptr && ccomp[c] != comp) continue;
         T d = T(0);
 #pragma unroll 8
         for (int i = 0; i < TD_ROWS; ++i) d += Mt[i * TD_CP + c] * sbuf[i];
@@ -204,6 +210,7 @@ __device__ __noinline__ void tdem_eval(const TdShared<T>& Q, const T* __restrict
             __syncwarp();
 #pragma unroll 1
             for (int c = lane; c < C; c += 32) {
+                if (ccomp != nullptr && ccomp[c] != comp) continue;
                 T d = T(0);
 #pragma unroll 8
                 for (int i = 0; i < TD_ROWS; ++i) d += Mt[i * TD_CP + c] * sbuf[i];

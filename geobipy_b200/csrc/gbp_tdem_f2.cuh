@@ -14,7 +14,7 @@ __device__ __noinline__ void tdem_eval<float>(const TdShared<float>& Q, const fl
                                               const float* __restrict__ lam, const float* __restrict__ wgt, int L,
                                               const float* __restrict__ msig, const float* __restrict__ mthk,
                                               float* __restrict__ sbuf, float* __restrict__ pred, float* __restrict__ J,
-                                              const bool sens)
+                                              const bool sens, const signed char* ccomp, const int comp)
 {
     using namespace f2;
     __builtin_assume(__isShared(&Q));
@@ -110,6 +110,7 @@ __device__ __noinline__ void tdem_eval<float>(const TdShared<float>& Q, const fl
     __syncwarp();
 #pragma unroll 1
     for (int c = lane; c < C; c += 32) {
+        if (ccomp != nullptr && ccomp[c] != comp) continue;
         float d = 0.f;
 #pragma unroll 8
         for (int i = 0; i < TD_ROWS; ++i) d = fmaf(Mt[i * TD_CP + c], sbuf[i], d);
@@ -124,6 +125,7 @@ __device__ __noinline__ void tdem_eval<float>(const TdShared<float>& Q, const fl
             __syncwarp();
 #pragma unroll 1
             for (int c = lane; c < C; c += 32) {
+                if (ccomp != nullptr && ccomp[c] != comp) continue;
                 float d = 0.f;
 #pragma unroll 8
                 for (int i = 0; i < TD_ROWS; ++i) d = fmaf(Mt[i * TD_CP + c], sbuf[i], d);

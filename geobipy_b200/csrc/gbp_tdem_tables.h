@@ -247,6 +247,28 @@ inline bool build_tdem_tables(const gbp_tdem_survey& sv, TdHost& out)
             }
         c0 += y.n_windows * o.n_comp;
     }
+    if (sv.error_model == 1) {
+        // Tempest_datapoint: errors per COMPONENT in channel order (x, then z), a fixed additive level per channel in place
+        // of the t^-1/2 scale, and the predicted primary field of the channel's component added to the response
+        if (sv.n_systems != 1) {
+            out.error = "the Tempest error model takes one system";
+            return false;
+        }
+        d.tempest = 1;
+        const TdOutput o = td_output(sv.sys[0]);
+        const double x = sv.rx_dx, yy = sv.rx_dy, z = sv.rx_dz, R = std::sqrt(x * x + yy * yy + z * z);
+        const double sx = sv.sys[0].x_scaling, sz = (sx == 0.0 && sv.sys[0].z_scaling == 0.0) ? 1.0 : sv.sys[0].z_scaling;
+        for (int c = 0; c < C; ++c) {
+            if (!(sv.additive_level[c] > 0.0)) {
+                out.error = "the Tempest error model needs a positive additive level for every channel";
+                return false;
+            }
+            d.tsc[c] = sv.additive_level[c];
+            d.csys[c] = (d.ccomp[c] == 1) ? 0 : (d.has_x ? 1 : 0);
+            d.poff[c] = d.ccomp[c] == 1 ? 1e-7 * o.peak * 3.0 * x * z / std::pow(R, 5) * sx
+                                        : -1e-7 * o.peak * (3.0 * z * z / std::pow(R, 5) - 1.0 / std::pow(R, 3)) * sz;
+        }
+    }
     return true;
 }
 

@@ -68,8 +68,10 @@ def make_tdem_system_struct(d):
     return s
 
 
-def make_tdem_survey_struct(definitions, rx_offset=(-13.0, 0.0, 2.0)):
-    """gbp_tdem_survey: the systems of one time-domain datapoint type + the transmitter->receiver offset."""
+def make_tdem_survey_struct(definitions, rx_offset=(-13.0, 0.0, 2.0), additive_level=None):
+    """gbp_tdem_survey: the systems of one time-domain datapoint type + the transmitter->receiver offset.
+    `additive_level` [C] selects the Tempest datapoint's error model for the sampler (the options file's
+    initial_additive_error vector: a fixed additive error per channel, the unknowns being one multiplier per component)."""
     if not 1 <= len(definitions) <= _lib.TD_MAXSYS:
         raise ValueError("a time-domain datapoint has 1..%d systems" % _lib.TD_MAXSYS)
     sv = TdemSurveyC()
@@ -77,6 +79,13 @@ def make_tdem_survey_struct(definitions, rx_offset=(-13.0, 0.0, 2.0)):
     for i, d in enumerate(definitions):
         sv.sys[i] = make_tdem_system_struct(d)
     sv.rx_dx, sv.rx_dy, sv.rx_dz = (float(v) for v in rx_offset)
+    if additive_level is not None:
+        a = np.asarray(additive_level, dtype=np.float64).reshape(-1)
+        if len(definitions) != 1 or a.size != n_channels(sv) or not np.all(a > 0.0):
+            raise ValueError("the Tempest error model takes one system and one positive additive level per channel")
+        sv.error_model = 1
+        for i, v in enumerate(a):
+            sv.additive_level[i] = float(v)
     return sv
 
 
@@ -95,8 +104,23 @@ def tempest_definition():
     return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tempest.json")))
 
 
-def tempest_survey_struct(rx_offset=(-107.0, 0.0, -45.0)):
-    return make_tdem_survey_struct([tempest_definition()], rx_offset)
+# tempest_options (documentation_source/source/supplementary/options_files/tempest_options): the additive error of every
+# channel [fT] ...
+TEMPEST_ADDITIVE = (0.011474, 0.012810, 0.008507, 0.005154, 0.004742, 0.004477, 0.004168, 0.003539, 0.003352, 0.003213, 0.003161,
+                    0.003122, 0.002587, 0.002038, 0.002201, 0.007383, 0.005693, 0.005178, 0.003659, 0.003426, 0.003046, 0.003095,
+                    0.003247, 0.002775, 0.002627, 0.002460, 0.002178, 0.001754, 0.001405, 0.001283)
+# ... and the sampler options: errors per component (x, z); the "additive error" unknown is the multiplier of those levels
+# (initially 1; minimum / maximum_additive_error bound its histogram); minimum_thickness None -> 1.0
+TEMPEST_OPTIONS = dict(
+    n_markov_chains=1000, min_edge=1.0, max_edge=550.0, min_width=1.0, covariance_scaling=0.5, gradient_std=5.0, n_systems=2,
+    rel_init=0.001, rel_min=0.0001, rel_max=0.01, rel_prop_var=1e-6, add_init=1.0, add_min=0.001, add_max=100.0, add_prop_var=1e-6,
+    rel_init2=0.001, rel_min2=0.0001, rel_max2=0.01, rel_prop_var2=1e-6, add_init2=1.0, add_min2=0.001, add_max2=100.0,
+    add_prop_var2=1e-6)
+
+
+def tempest_survey_struct(rx_offset=(-107.0, 0.0, -45.0), additive_level=None):
+    """The Tempest datapoint type; with `additive_level` (e.g. TEMPEST_ADDITIVE) also for the sampler."""
+    return make_tdem_survey_struct([tempest_definition()], rx_offset, additive_level)
 
 
 def tdem_primary_field(survey):

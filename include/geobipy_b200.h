@@ -130,11 +130,17 @@ typedef struct {
 } gbp_tdem_system;
 
 /* A time-domain datapoint type: its systems and the transmitter->receiver offset (Loop_pair.Geometry,
- * classes/system/Loop_pair.py:62-78; z up, zero pitch/roll/yaw). */
+ * classes/system/Loop_pair.py:62-78; z up, zero pitch/roll/yaw).
+ * error_model (sampler only): 0 = TdemDataPoint (TdemDataPoint.std :329-379: relative and additive error per SYSTEM, the
+ * additive error scaled by (t / 1 ms)^-1/2); 1 = Tempest_datapoint (Tempest_datapoint.py:107-176, :478-510): ONE system,
+ * the data handed to the sampler are secondary + primary field, the errors are per COMPONENT in channel order (x, z):
+ * gbp_options.rel_* / rel_*2 the relative errors, gbp_options.add_* / add_*2 the additive-error MULTIPLIERS over the fixed
+ * additive_level of every channel (the options file's initial_additive_error vector). */
 typedef struct {
-    int32_t n_systems, pad_;
+    int32_t n_systems, error_model;
     gbp_tdem_system sys[GBP_TD_MAXSYS];
     double rx_dx, rx_dy, rx_dz;
+    double additive_level[GBP_TD_MAXC];   /* error_model 1: additive error of channel c, in the output scaling's unit */
 } gbp_tdem_survey;
 
 /* Per-chain scalar slots of gbp_chain_buffers.scalars ([B][GBP_NSCALARS] doubles). */
@@ -301,9 +307,10 @@ int gbp_tdem_sensitivity_host(const gbp_tdem_survey *sv, int B, int l_stride, co
  * order ([n_systems x components]: Tempest PX, PZ; TdemDataPoint.forward :1008-1016 stacks PX, -PZ), in the output
  * scaling's unit.  Host only.  Returns the number of values written. */
 int gbp_tdem_primary_field(const gbp_tdem_survey *sv, double *out);
-/* rjMCMC for time-domain datapoints: data [B][C]; errors per system (gbp_options.n_systems must equal
- * sv->n_systems); additive error of channel c scaled by (t_c / 1 ms)^-0.5 (TdemDataPoint.std :329-379).  Z-component
- * dB/dt systems only: the error model of a Tempest datapoint (Tempest_datapoint.std :141-176) is not built. */
+/* rjMCMC for time-domain datapoints: data [B][C].  error_model 0: errors per system (gbp_options.n_systems must equal
+ * sv->n_systems), additive error of channel c scaled by (t_c / 1 ms)^-0.5 (TdemDataPoint.std :329-379), Z-component dB/dt
+ * systems.  error_model 1 (Tempest): data = secondary + primary field, gbp_options.n_systems = the number of measured
+ * components; the transmitter height is not sampled for this datapoint type. */
 int gbp_tdem_rjmcmc_run(const gbp_tdem_survey *sv, const gbp_options *opt, int B, const double *d_data,
                         const double *d_altitude, uint64_t seed, uint64_t first_index, int64_t max_iterations,
                         const gbp_chain_buffers *d_buf, int precision, void *stream);

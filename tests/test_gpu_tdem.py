@@ -384,8 +384,8 @@ def test_tempest_forward_and_jacobian_against_oracle(gpu, tempest, oracle, prec)
 
 
 def test_tempest_datapoint_and_sampler_refusal(gpu, tempest, golden_dir):
-    """Tempest_datapoint mirror (data = secondary + primary per component, Tempest_datapoint.py:107-127) and the loud refusal of
-    the sampler for this datapoint type."""
+    """Tempest_datapoint mirror (data = secondary + primary per component, Tempest_datapoint.py:107-127); the sampler refuses an
+    X / B-field system that comes without the Tempest error model."""
     from geobipy_b200 import _lib, api, tdem
     g = np.load(os.path.join(golden_dir, "tempest_clean.npz"))
     system = tdem.TdemSystem(definition=gpu.tempest_definition())
@@ -405,7 +405,117 @@ def test_tempest_datapoint_and_sampler_refusal(gpu, tempest, golden_dir):
     assert J.shape == (30, 3)
     dp.additive_error = TEMPEST_ADDITIVE
     assert np.allclose(dp.std[:15], np.sqrt((0.01 * dp.data[:15]) ** 2 + TEMPEST_ADDITIVE[:15] ** 2))
-    with pytest.raises(_lib.GeobipyB200Error, match="Z-component dB/dt systems only"):
+    with pytest.raises(_lib.GeobipyB200Error, match="needs the Tempest error model"):     # X / B system without its error model
         gpu.rjmcmc_run(tempest[0], gpu.make_options(n_markov_chains=100), g["data"][0, :2], np.full(2, 120.0), max_iterations=10)
-    with pytest.raises(NotImplementedError):
-        dp.initialize(initial_relative_error=[0.001, 0.001], initial_additive_error=TEMPEST_ADDITIVE)
+
+
+# ------------------------------------------------------------------------------------------ the sampler for Tempest datapoints
+def _tempest_observed(gpu, oracle, tempest, B, first=0):
+    """Synthetic Tempest soundings: the shared true-model generator at 120 m, noise = tempest_options' error model; the
+    data handed to the sampler are secondary + primary field (Tempest_datapoint.py:107-118)."""
+    from geobipy_b200.synthetic import synthetic_batch
+    b = synthetic_batch(first, B, max_depth=400.0, n_channels=30)
+    prim = np.repeat(oracle.tdem_primary_field(oracle.tempest_definition(), (-107.0, 0.0, -45.0)), 15)
+    data = np.zeros((B, 30))
+    for i in range(B):
+        L = int(b["nlayers"][i])
+        clean = oracle.tdem_forward(tempest[1], 120.0, b["sigma"][i, :L], b["thickness"][i, :L])
+        data[i] = clean + prim + b["noise"][i] * np.sqrt((0.001 * (clean + prim)) ** 2 + TEMPEST_ADDITIVE ** 2)
+    return data, np.full(B, 120.0)
+
+
+def test_tempest_chain_fp64_is_trajectory_twin_of_oracle(gpu, tempest, oracle):
+    """KIND_TEMPEST in fp64 against the oracle (pinned on 800 live-reference transitions, tests/test_oracle_golden.py::
+    test_tempest_transition_terms_match_live_reference): same Philox stream, same arithmetic -> identical hitmaps, traces and
+    per-component error histograms."""
+    B, NIT = 10, 400
+    data, alt = _tempest_observed(gpu, oracle, tempest, B)
+    sv = gpu.tempest_survey_struct(additive_level=gpu.TEMPEST_ADDITIVE)
+    osys = oracle.make_tempest_system()
+    opt = gpu.make_options(**dict(gpu.TEMPEST_OPTIONS, n_markov_chains=2000))
+    oo = oracle.tempest_options(n_markov_chains=2000)
+    res = gpu.rjmcmc_run(sv, opt, data, alt, seed=33, max_iterations=NIT, precision=64)
+    assert res["rel_hist"].shape == (B, 2, 99) and res["hitmap"].shape == (B, 250, 1209)
+    same = 0
+    for b in range(B):
+        r = oracle.run_chain(osys, oo, data[b], alt[b], 33, b, max_iterations=NIT)
+        s, q = res["scalars"][b], r["scalars"]
+        assert abs(s[oracle.S_HALFSPACE] - q[oracle.S_HALFSPACE]) <= 1e-12 * q[oracle.S_HALFSPACE]
+        assert res["hitmap"][b].sum() == r["hitmap"].sum() == NIT * 1209
+        ok = (np.array_equal(res["hitmap"][b], r["hitmap"]) and np.array_equal(res["accept_trace"][b], r["accept_trace"])
+              and np.array_equal(res["rel_hist"][b], r["rel_hist"]) and np.array_equal(res["add_hist"][b], r["add_hist"])
+              and np.array_equal(res["ncells_hist"][b], r["ncells_hist"]) and np.array_equal(res["edges_hist"][b], r["edges_hist"]))
+        if ok:
+            for k in (oracle.S_CUR_REL, oracle.S_CUR_ADD, oracle.S_CUR_REL2, oracle.S_CUR_ADD2, oracle.S_CUR_MISFIT,
+                      oracle.S_CUR_LIKELIHOOD, oracle.S_CUR_PRIOR, oracle.S_BEST_POSTERIOR):
+                assert abs(s[k] - q[k]) <= 1e-8 * abs(q[k]) + 1e-300, (b, k)
+            assert np.allclose(res["misfit_trace"][b], r["misfit_trace"], rtol=1e-8)
+        same += ok
+    assert same >= B - 1, same
+    # the multiplier never drifts from its initial value (it is re-drawn around it every step: the reference's behaviour)
+    assert np.all(np.abs(np.log(res["scalars"][:, [oracle.S_CUR_ADD, oracle.S_CUR_ADD2]])) < 6e-3)
+
+
+def test_tempest_fp32_production_kernel_against_reference_chains(gpu, tempest, oracle, golden_dir):
+    """The fp32 KIND_TEMPEST kernel against full chains of the live reference (Inference1D with a Tempest_datapoint,
+    tempest_options at n_markov_chains = 10 000, gatdaem1d replaced by tests/golden/fake_gatdaem1d.py) on the same observed
+    data: acceptance +-5 points, mean layer count +-0.75, post-burn-in misfit centred like the reference's, the pooled median
+    profile inside the reference envelope +-2 bins for >= 90 % of the top 100 m."""
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_tempest_chain_1"))
+    refs = [np.load(os.path.join(golden_dir, f)) for f in files]
+    assert len(refs) >= 5
+    g = refs[0]
+    sv = gpu.tempest_survey_struct(additive_level=gpu.TEMPEST_ADDITIVE)
+    opt = gpu.make_options(**dict(gpu.TEMPEST_OPTIONS, n_markov_chains=10000))
+    n = 128
+    data = np.tile(g["data"], (n, 1))
+    res = gpu.rjmcmc_run(sv, opt, data, np.full(n, 120.0), seed=77, precision=32,
+                         outputs=("hitmap", "ncells_hist", "accept_trace", "misfit_trace", "rel_hist", "add_hist", "scalars"))
+    s = res["scalars"]
+    assert np.allclose(s[:, 6], float(g["halfspace"]), rtol=1e-5)                      # same best half-space
+    ref_acc = np.mean([r["accept_trace"].mean() for r in refs])
+    acc = (s[:, 8] / s[:, 24]).mean()
+    kref = np.mean([(r["ncells_hist"] * np.arange(r["ncells_hist"].size)).sum() / r["ncells_hist"].sum() for r in refs])
+    kk = ((res["ncells_hist"] * np.arange(res["ncells_hist"].shape[1])).sum(axis=1) / res["ncells_hist"].sum(axis=1)).mean()
+    ref_burn = np.mean([bool(r["burned_in"]) for r in refs])
+    burn = s[:, 1].mean()
+    print("tempest sounding 1", dict(acceptance_ref=ref_acc, acceptance=acc, kbar_ref=kref, kbar=kk, burned_in_ref=ref_burn, burned_in=burn,
+                                     n_ref=len(refs), n=n))
+    assert abs(acc - ref_acc) < 0.05 and abs(kk - kref) < 0.75
+    assert abs(burn - ref_burn) < 0.45            # 5 reference chains: 2 of them burn in
+    # final misfit of the chains that burned in: around the number of active channels, as the reference's
+    mis = np.array([res["misfit_trace"][b, int(s[b, 0]) - 1] for b in range(n) if s[b, 1]])
+    mref = [float(r["misfit_trace"][-1]) for r in refs if bool(r["burned_in"])]
+    assert mis.size > 0 and 10.0 < np.median(mis) < 60.0 and all(10.0 < m < 80.0 for m in mref)
+    # pooled median profile (top 100 m = 200 depth cells) against the envelope of the reference chains
+    def med(h):
+        c = np.cumsum(h, axis=0)
+        return (c < 0.5 * c[-1]).sum(axis=0)
+    pooled = med(res["hitmap"].sum(axis=0))[:200]
+    rm = np.array([med(r["hitmap"])[:200] for r in refs])
+    inside = (pooled >= rm.min(axis=0) - 2) & (pooled <= rm.max(axis=0) + 2)
+    assert inside.mean() > 0.9, inside.mean()
+
+
+def test_tempest_speculation_and_precision_consistency(gpu, tempest, oracle, monkeypatch):
+    """Speculative evaluation is bit-identical for KIND_TEMPEST too, and fp32 agrees with fp64 over a short run."""
+    B, NIT = 24, 300
+    data, alt = _tempest_observed(gpu, oracle, tempest, B, first=50)
+    sv = gpu.tempest_survey_struct(additive_level=gpu.TEMPEST_ADDITIVE)
+    opt = gpu.make_options(**dict(gpu.TEMPEST_OPTIONS, n_markov_chains=2000))
+    r32 = gpu.rjmcmc_run(sv, opt, data, alt, seed=4, max_iterations=NIT, precision=32)
+    monkeypatch.setenv("GBP_SPEC_MIN_REJECTIONS", "0")
+    q32 = gpu.rjmcmc_run(sv, opt, data, alt, seed=4, max_iterations=NIT, precision=32)
+    monkeypatch.setenv("GBP_SPEC_HELPERS", "0")
+    p32 = gpu.rjmcmc_run(sv, opt, data, alt, seed=4, max_iterations=NIT, precision=32)
+    for k in ("hitmap", "accept_trace", "rel_hist", "add_hist", "ncells_hist", "edges_hist"):
+        assert np.array_equal(r32[k], q32[k]) and np.array_equal(r32[k], p32[k]), k
+    monkeypatch.delenv("GBP_SPEC_HELPERS")
+    monkeypatch.delenv("GBP_SPEC_MIN_REJECTIONS")
+    r64 = gpu.rjmcmc_run(sv, opt, data, alt, seed=4, max_iterations=NIT, precision=64)
+    a64, a32 = r64["scalars"][:, 8], r32["scalars"][:, 8]
+    assert (r32["scalars"][:, 0] == NIT).all() and not r32["scalars"][:, 7].any()
+    assert abs(a64.mean() - a32.mean()) < 0.15 * a64.mean() + 5
+    assert np.allclose(r32["scalars"][:, 6], r64["scalars"][:, 6], rtol=1e-6)
+    # errors come back unscaled: relative errors inside their prior, multipliers near 1
+    assert np.all((r32["scalars"][:, 12] >= 1e-4) & (r32["scalars"][:, 12] <= 1e-2)) and np.all(np.abs(np.log(r32["scalars"][:, 13])) < 6e-3)
