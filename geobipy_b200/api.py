@@ -384,18 +384,32 @@ class Inference1D:
         self.multiplier = np.float64(multiplier)   # carried and serialised, as in the reference (Inference1D.py:88, :1067)
         self.interactive_plot, self.reciprocate_parameter, self.limits = bool(interactive_plot), False, None
         self.precision, self.device = precision, device
-        self.options = ops.options_from_reference(
-            covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains, update_plot_every=update_plot_every,
-            solve_gradient=int(bool(solve_gradient)), solve_parameter=int(bool(solve_parameter)), **kwargs)
+        self._raw_options = dict(kwargs, covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains,
+                                 update_plot_every=update_plot_every, solve_gradient=int(bool(solve_gradient)),
+                                 solve_parameter=int(bool(solve_parameter)))
+        self.options = ops.options_from_reference(**self._raw_options)
         self.user_options = kwargs
         self.datapoint = None
 
     def initialize(self, datapoint):
-        from .tdem import TdemDataPoint
+        from .tdem import TdemDataPoint, Tempest_datapoint
         assert isinstance(datapoint, (FdemDataPoint, TdemDataPoint)), TypeError("datapoint must be a FdemDataPoint or TdemDataPoint")
         self.datapoint = datapoint
-        o = self.options
         self._tdem = isinstance(datapoint, TdemDataPoint)
+        self._tempest = isinstance(datapoint, Tempest_datapoint)
+        if self._tempest:
+            # tempest_options: initial_additive_error is the additive level of every CHANNEL; the sampled "additive error"
+            # is one multiplier per component, starting at 1 (Tempest_datapoint.set_priors / set_proposals :478-510)
+            kw = dict(self._raw_options)
+            level = np.asarray(kw["initial_additive_error"], dtype=np.float64).reshape(-1)
+            nc = datapoint.nSystems * datapoint.n_components
+            kw["initial_additive_error"] = [1.0] * nc if nc > 1 else 1.0
+            self.options = ops.options_from_reference(**kw)
+            datapoint.initialize(initial_relative_error=self._raw_options["initial_relative_error"], initial_additive_error=level)
+            assert (2 if self.options.n_systems > 1 else 1) == nc, ValueError("the error options must have one entry per component ({})".format(nc))
+            self.iteration, self.burned_in, self.burned_in_iteration = 0, False, 0
+            return
+        o = self.options
         ns = datapoint.nSystems if self._tdem else 1
         assert (2 if o.n_systems > 1 else 1) == ns, ValueError(
             "the error options must be lists with one entry per system ({})".format(ns))
@@ -418,7 +432,7 @@ class Inference1D:
         dp = self.datapoint
         if dp.n_active_channels == 0:
             return True
-        struct = dp.c_struct if self._tdem else dp.system.c_struct
+        struct = dp.survey_struct() if self._tempest else (dp.c_struct if self._tdem else dp.system.c_struct)
         if not hasattr(dp, "z_input"):
             dp.z_input = float(dp.transmitter.z if self._tdem else dp.z)   # a second infer() starts from the input height again
         alt = dp.z_input
@@ -454,6 +468,8 @@ class Inference1D:
         passes them): every group, dataset and attribute of the reference's file (geobipy_b200.hdf.create_line)."""
         from . import hdf
         assert self.datapoint is not None, ValueError("Inference needs a datapoint before creating HDF5 files.")
+        if getattr(self, "_tempest", False):
+            raise NotImplementedError("the HDF5 layout of a Tempest_datapoint (Tempest_datapoint.createHdf :566-586) is not built")
         if add_axis is None:
             raise NotImplementedError("createHdf without add_axis (a file for one sounding, no line axis) is not built: "
                                       "pass add_axis=1 for a one-sounding line")
@@ -510,7 +526,10 @@ class Inference1D:
             rel_post = [Histogram(r["rel_hist"][b][i], g["rel_edges"][i], log_x=True) for i in range(2)]
             add_post = [Histogram(r["add_hist"][b][i], g["add_edges"][i], log_x=True) for i in range(2)]
             dp.relative_error = StatArray([s[_lib.S_CUR_REL], s[_lib.S_CUR_REL2]], "Relative error", posterior=rel_post)
-            dp.additive_error = StatArray([s[_lib.S_CUR_ADD], s[_lib.S_CUR_ADD2]], "Additive error", posterior=add_post)
+            if self._tempest:   # the sampled quantity is the multiplier of the fixed additive levels (one per component)
+                dp.additive_error_multiplier = StatArray([s[_lib.S_CUR_ADD], s[_lib.S_CUR_ADD2]], "Multiplier", posterior=add_post)
+            else:
+                dp.additive_error = StatArray([s[_lib.S_CUR_ADD], s[_lib.S_CUR_ADD2]], "Additive error", posterior=add_post)
             self.best_relative_error = np.asarray([s[_lib.S_BEST_REL], s[_lib.S_BEST_REL2]])
             self.best_additive_error = np.asarray([s[_lib.S_BEST_ADD], s[_lib.S_BEST_ADD2]])
         else:
@@ -542,7 +561,10 @@ class Inference1D:
         else:
             bdp.predictedData = dp.predictedData.copy()
         bdp.relative_error = StatArray(np.atleast_1d(self.best_relative_error), "Relative error")
-        bdp.additive_error = StatArray(np.atleast_1d(self.best_additive_error), "Additive error")
+        if self._tempest:
+            bdp.additive_error_multiplier = StatArray(np.atleast_1d(self.best_additive_error), "Multiplier")
+        else:
+            bdp.additive_error = StatArray(np.atleast_1d(self.best_additive_error), "Additive error")
         if o.solve_height:
             if self._tdem:
                 bdp.transmitter, bdp.receiver = copy.copy(dp.transmitter), copy.copy(dp.receiver)

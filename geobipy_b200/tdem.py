@@ -334,7 +334,19 @@ class Tempest_datapoint(TdemDataPoint):
         return out
 
     def initialize(self, **kwargs):
-        raise NotImplementedError("the sampler for Tempest datapoints is not built (DESIGN.md section 7): forward / sensitivity only")
+        """Tempest_datapoint.initialize :274-278 -> DataPoint.initialize :530-532: one relative error per component, the
+        additive error of every channel (the options file's initial_additive_error vector), multipliers of 1."""
+        n = self.nSystems * self.n_components
+        self.relative_error = np.asarray(kwargs['initial_relative_error'], np.float64).reshape(n)
+        self.additive_error = np.asarray(kwargs['initial_additive_error'], np.float64).reshape(self.nChannels)
+        self.additive_error_multiplier = np.ones(n)
+
+    def survey_struct(self, with_errors=True):
+        """gbp_tdem_survey of this datapoint type; with the additive level of every channel it selects the Tempest error
+        model of the sampler (include/geobipy_b200.h gbp_tdem_survey.error_model)."""
+        off = (self.receiver.x - self.transmitter.x, self.receiver.y - self.transmitter.y, float(self.receiver.z) - float(self.transmitter.z))
+        return ops.make_tdem_survey_struct([s.definition for s in self.system], off,
+                                           additive_level=self.additive_error if with_errors else None)
 
 
 class TdemData:

@@ -612,6 +612,39 @@ def test_tdem_chain_statistics_match_reference_chains(oracle, golden_dir):
         assert np.all(np.abs((rr * b).sum(axis=1) / rr.sum(axis=1) - (oo * b).sum(axis=1) / oo.sum(axis=1)) < 2.0), name
 
 
+def test_tempest_chain_statistics_match_reference_chains(oracle, golden_dir):
+    """Oracle chains vs 6 full chains of the live reference with a Tempest_datapoint (tempest_options at n_markov_chains =
+    10 000, gatdaem1d replaced by tests/golden/fake_gatdaem1d.py) on the same observed data, different random streams:
+    acceptance +-5 points, mean layer count +-0.75, the error posteriors in the same bins (the relative errors move by
+    ~0.1 % per step, the multiplier is re-drawn around 1: both stay within two bins of where they start), and the same two
+    kinds of chain as the reference produces - never burned in (exactly 10 000 iterations) or burned in after b > 5000."""
+    files = sorted(f for f in os.listdir(golden_dir) if f.startswith("ref_tempest_chain_1"))
+    refs = [np.load(os.path.join(golden_dir, f)) for f in files]
+    assert len(refs) >= 6
+    g = refs[0]
+    s, o = oracle.make_tempest_system(), oracle.tempest_options(n_markov_chains=10000)
+    runs = _chains(oracle, s, o, g["data"], 120.0, [300 + j for j in range(8)], 1)
+    assert abs(runs[0]["scalars"][oracle.S_HALFSPACE] / float(g["halfspace"]) - 1) < 1e-12
+    for r in list(refs):
+        it, b = int(r["iterations"]), int(r["burned_in_iteration"])
+        assert (not bool(r["burned_in"]) and it == 10000) or (bool(r["burned_in"]) and b > 5000 and it == 10000 + b + 1)
+    for r in runs:
+        it, b = int(r["scalars"][oracle.S_ITER]), int(r["scalars"][oracle.S_BURNED_IN_ITER])
+        assert (not r["scalars"][oracle.S_BURNED_IN] and it == 10000) or (r["scalars"][oracle.S_BURNED_IN] and b > 5000 and it == 10000 + b + 1)
+    ref_acc = np.mean([r["accept_trace"].mean() for r in refs])
+    acc = np.mean([r["scalars"][oracle.S_N_ACCEPT] / r["scalars"][oracle.S_ITER] for r in runs])
+    assert abs(acc - ref_acc) < 0.05, (acc, ref_acc)
+    ref_nc = sum(r["ncells_hist"].astype(np.int64) for r in refs)
+    nc = sum(r["ncells_hist"].astype(np.int64) for r in runs)
+    k = np.arange(nc.size)
+    assert abs((nc * k).sum() / nc.sum() - (ref_nc * k).sum() / ref_nc.sum()) < 0.75
+    b = np.arange(99)
+    for name in ("rel_hist", "add_hist"):
+        rr = sum(r[name].astype(np.int64) for r in refs)
+        oo = sum(r[name].astype(np.int64) for r in runs)
+        assert np.all(np.abs((rr * b).sum(axis=1) / rr.sum(axis=1) - (oo * b).sum(axis=1) / oo.sum(axis=1)) < 2.0), name
+
+
 def test_tdem_chain_invariants(oracle, golden_dir):
     """Book-keeping identities of a time-domain oracle chain (dual moment, per-system error histograms)."""
     g = np.load(os.path.join(golden_dir, "ref_tdem_chain_2.npz"))

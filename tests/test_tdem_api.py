@@ -198,3 +198,42 @@ def test_inference3d_time_domain_survey(stm_files, tmp_path, golden_dir, built_l
     from geobipy_b200 import api
     dp.forward(api.Model(api.RectilinearMesh1D(edges=r["best_edges"][3, :kb + 1]), r["best_sigma"][3, :kb]))
     assert np.allclose(h["data/predicted_secondary_field/data"][1], dp.predictedData, rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_inference1d_with_tempest_datapoint(golden_dir, built_lib):
+    """The reference's calling sequence with a Tempest_datapoint and the keys of tempest_options: `initial_additive_error` is
+    the additive level of every channel, the sampled errors are one relative error and one multiplier per component."""
+    from geobipy_b200 import _lib, api, ops, tdem
+    _lib.require_cuda()
+    g = np.load(os.path.join(golden_dir, "ref_tempest_chain_1.npz"))
+    system = tdem.TdemSystem(definition=ops.tempest_definition())
+    dp = tdem.Tempest_datapoint(x=0.0, y=0.0, z=120.0, elevation=0.0, system=[system], transmitter_loop=tdem.TdemLoop(z=120.0),
+                                receiver_loop=tdem.TdemLoop(x=-107.0, z=75.0), secondary_field=g["secondary"], primary_field=g["primary"])
+    assert np.allclose(dp.data, g["data"], rtol=1e-13)
+    options = dict(n_markov_chains=600, solve_relative_error=True, initial_relative_error=[0.001, 0.001], minimum_relative_error=[0.0001, 0.0001],
+                   maximum_relative_error=[0.01, 0.01], relative_error_proposal_variance=[1e-6, 1e-6], solve_additive_error=True,
+                   initial_additive_error=np.asarray(ops.TEMPEST_ADDITIVE), additive_error_proposal_variance=1e-6,
+                   minimum_additive_error=[0.001, 0.001], maximum_additive_error=[100.0, 100.0], solve_transmitter_z=False,
+                   solve_receiver_pitch=False, maximum_number_of_layers=30, minimum_depth=1.0, maximum_depth=550.0, minimum_thickness=None,
+                   probability_of_birth=1 / 6, probability_of_death=1 / 6, probability_of_perturb=1 / 6, probability_of_no_change=0.5,
+                   gradient_standard_deviation=5, covariance_scaling=0.5, interactive_plot=False, save_hdf5=True)
+    inf = api.Inference1D(seed=5, precision=64, **options)
+    inf.initialize(dp)
+    assert inf.options.gradient_std == 5.0 and inf.options.add_init == 1.0 and inf.options.n_systems == 2
+    inf.infer(None)
+    assert inf.iteration == 600 and abs(inf.halfspace / float(g["halfspace"]) - 1.0) < 1e-9
+    assert len(inf.relative_error_posterior) == 2 and inf.relative_error_posterior[1].counts.sum() == 600
+    assert np.allclose(dp.additive_error, ops.TEMPEST_ADDITIVE) and np.all(np.abs(np.log(dp.additive_error_multiplier)) < 6e-3)
+    assert dp.additive_error_multiplier.posterior[0].counts.sum() == 600
+    # the same chain through the operator level
+    sv = dp.survey_struct()
+    r = ops.rjmcmc_run(sv, inf.options, dp.data[None], np.asarray([120.0]), seed=5, precision=64)
+    assert np.array_equal(r["hitmap"][0], inf.hitmap.counts)
+    # predicted data of the final model: secondary + primary
+    chk = tdem.Tempest_datapoint(x=0.0, y=0.0, z=120.0, elevation=0.0, system=[system], transmitter_loop=tdem.TdemLoop(z=120.0),
+                                 receiver_loop=tdem.TdemLoop(x=-107.0, z=75.0))
+    chk.forward(inf.model)
+    assert np.allclose(chk.predictedData, dp.predictedData) and inf.data_misfit < 18415.0
+    with pytest.raises(NotImplementedError):
+        inf.createHdf(None, add_axis=2)
