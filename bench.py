@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--soundings", type=int, default=SOUNDINGS_PER_GPU, help="soundings per GPU")
     ap.add_argument("--chains", type=int, default=N_MARKOV_CHAINS, help="n_markov_chains")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
-    ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem", "mixed"])
+    ap.add_argument("--workload", default="resolve", choices=["resolve", "skytem", "mixed", "tempest"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="streams consecutive steps alternate over (1 = one batch at a time)")
@@ -56,12 +56,33 @@ class Workload:
 
     def __init__(self, name):
         self.name = name
-        self.tdem = name == "skytem"
-        self.C = 45 if self.tdem else 12
-        self.synth = dict(max_depth=400.0, n_channels=45) if self.tdem else {}
+        self.tempest = name == "tempest"
+        self.tdem = name in ("skytem", "tempest")
+        self.C = 30 if self.tempest else (45 if self.tdem else 12)
+        self.synth = dict(max_depth=400.0, n_channels=self.C) if self.tdem else {}
+
+    def altitude(self, h, xp=np):
+        """Sensor / transmitter height of the synthetic soundings: the generator's 25-45 m, a fixed-wing Tempest at 120 m."""
+        return h if not self.tempest else (xp.full_like(h, 120.0))
+
+    def observe(self, clean, noise, xp):
+        """Observed data from the clean response: + noise; a Tempest datapoint's data are secondary + primary field
+        (Tempest_datapoint.py:107-118), noise = tempest_options' error model (0.1 %, the per-channel additive levels)."""
+        if not self.tempest:
+            return clean + noise * self.noise_std(clean, xp)
+        from geobipy_b200 import ops
+        prim = np.repeat(ops.tdem_primary_field(ops.tempest_survey_struct()), 15)
+        add = np.asarray(ops.TEMPEST_ADDITIVE)
+        if xp is not np:
+            prim, add = xp.tensor(prim, device=clean.device), xp.tensor(add, device=clean.device)
+        total = clean + prim
+        return total + noise * xp.sqrt((0.001 * total) ** 2 + add ** 2)
 
     def product(self, chains):
         from geobipy_b200 import ops
+        if self.tempest:
+            return (ops.tempest_survey_struct(additive_level=ops.TEMPEST_ADDITIVE),
+                    ops.make_options(**dict(ops.TEMPEST_OPTIONS, n_markov_chains=chains)))
         if self.tdem:
             return ops.skytem_survey_struct(), ops.make_options(n_markov_chains=chains, **ops.SKYTEM_OPTIONS)
         return ops.resolve_system_struct(), ops.make_options(n_markov_chains=chains)
@@ -80,6 +101,8 @@ class Workload:
     def oracle(self, chains):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py as O
+        if self.tempest:
+            return O, O.make_tempest_system(), O.tempest_options(n_markov_chains=chains), O.tdem_forward
         if self.tdem:
             return O, O.make_tdem_system(), O.skytem_options(n_markov_chains=chains), O.tdem_forward
         return O, O.make_system(), O.resolve_options(n_markov_chains=chains), O.fdem_forward
@@ -91,6 +114,15 @@ def workload_config(args, world):
                             "n_markov_chains=%d" % (args.soundings, args.chains), "soundings_per_gpu": args.soundings,
                 "soundings_total": args.soundings * world, "n_markov_chains": args.chains,
                 "options": "resolve_options / skytem_options", "parallelism": "shard%d" % world}
+    if args.workload == "tempest":
+        return {
+            "workload": "Tempest fixed-wing soundings (tempest_options; not in BASELINE.json): %d synthetic soundings per GPU, 15 X + 15 Z "
+                        "windows of B field + primary field, <=30 layers, n_markov_chains=%d, chains run to the reference's termination rule"
+                        % (args.soundings, args.chains),
+            "soundings_per_gpu": args.soundings, "soundings_total": args.soundings * world, "n_markov_chains": args.chains,
+            "options": "tempest_options", "parallelism": "shard%d" % world, "forward_precision": "fp%d" % args.precision,
+            "l2": "no flush needed: each step rewrites GBs of posterior arrays per GPU (> 126 MB L2)",
+            "pipelining": ("consecutive steps alternate over %d CUDA streams" % args.streams) if args.streams > 1 else "one batch at a time"}
     if args.workload == "skytem":
         nd = 1209
         return {
@@ -143,9 +175,13 @@ def _observed_cpu(n, wname="resolve"):
     data = np.zeros((n, wl.C))
     for i in range(n):
         L = int(b["nlayers"][i])
-        clean = fwd(osys, b["height"][i], b["sigma"][i, :L], b["thickness"][i, :L])
-        data[i] = clean + b["noise"][i] * wl.noise_std(clean, np)
-    return data, b["height"]
+        h = float(wl.altitude(b["height"][i:i + 1])[0])
+        if wl.tempest:   # the forward tables only (the sampler system adds the primary field itself)
+            clean = fwd(O.make_tdem_system([O.tempest_definition()], rx_offset=(-107.0, 0.0, -45.0)), h, b["sigma"][i, :L], b["thickness"][i, :L])
+        else:
+            clean = fwd(osys, h, b["sigma"][i, :L], b["thickness"][i, :L])
+        data[i] = wl.observe(clean, b["noise"][i], np)
+    return data, wl.altitude(b["height"])
 
 
 def cpu_sample(chains, n_chains, max_it, pool, wname="resolve"):
@@ -369,10 +405,10 @@ def run_b200_arm(args):
     t_sig = torch.tensor(sb["sigma"], device=dev)
     t_thk = torch.tensor(sb["thickness"], device=dev)
     t_nl = torch.tensor(sb["nlayers"], device=dev)
-    t_alt = torch.tensor(sb["height"], device=dev)
+    t_alt = wl.altitude(torch.tensor(sb["height"], device=dev), torch)
     clean = ops.forward(system, t_nl, t_sig, t_thk, t_alt, precision=64)
     noise = torch.tensor(sb["noise"], device=dev)
-    d_data = (clean + noise * wl.noise_std(clean, torch)).contiguous()
+    d_data = wl.observe(clean, noise, torch).contiguous()
     torch.cuda.synchronize()
 
     outputs = ops.DEFAULT_OUTPUTS
@@ -577,7 +613,7 @@ def run_b200_arm(args):
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "dram_bytes_per_launch" if not wl.tdem else "dram_bytes_per_launch_skytem")
+                "dram_bytes_per_launch" if not wl.tdem else ("dram_bytes_per_launch_skytem" if not wl.tempest else "dram_bytes_per_launch_tempest"))
         except Exception:
             pass
         # secondary (the binding one): scalar fp32 issue.  flops per unit from gbp_flops_per_forward at the mean
@@ -594,7 +630,7 @@ def run_b200_arm(args):
             "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "kernel": "gbp::rjmcmc_kernel<%s,%d,%s>" % ("float" if args.precision == 32 else "double", 48 if wl.tdem else 12, "TDEM" if wl.tdem else "FDEM"),
+                         "traffic": traffic, "kernel": "gbp::rjmcmc_kernel<%s,%d,%s>" % ("float" if args.precision == 32 else "double", 48 if wl.tdem else 12, "TEMPEST" if wl.tempest else ("TDEM" if wl.tdem else "FDEM")),
                          "kernel_ms": mean_kernel_ms, "units_per_launch": mean_iters, "bytes_per_unit": bytes_per_iter,
                          "kernel_ms_is": ("timed region / %d launches (CUDA events; consecutive launches overlap on %d streams)" % (args.steps, ns)) if ns > 1
                                          else "mean over the %d timed launches (CUDA events on the launching stream)" % args.steps,

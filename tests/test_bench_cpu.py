@@ -13,7 +13,7 @@ REQUIRED = ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
             "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e")
 
 
-@pytest.mark.parametrize("workload,extra", [("resolve", ["--port"]), ("skytem", [])])
+@pytest.mark.parametrize("workload,extra", [("resolve", ["--port"]), ("skytem", []), ("tempest", [])])
 def test_reference_arm_json_line(workload, extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
                           "--steps", "1", "--warmup", "1"] + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
