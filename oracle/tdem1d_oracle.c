@@ -62,16 +62,19 @@ static void td_geometry(const gbo_tdem_system *s, double altitude, double *lam, 
     const double dxi = s->xi[1] - s->xi[0];
     for (int j = 0; j < s->n_lam; ++j) {
         const double l = (2.0 / ZH) * exp(s->xi[j]);
-        double w = dxi * ((j == 0 || j == s->n_lam - 1) ? 0.5 : 1.0);
-        w *= l * l * l * exp(-l * ZH);
+        const double t = dxi * ((j == 0 || j == s->n_lam - 1) ? 0.5 : 1.0);
+        double w = t, wx = t;
+        w *= l * l * l * exp(-l * ZH) * j0(l * r);
+        /* horizontal (x) secondary field of the vertical dipole: the same integrand with J1(lam r) dx / r */
+        wx *= l * l * l * exp(-l * ZH) * (j1(l * r) * s->rx_cx);
         if (s->loop_radius > 0.0) {
             const double x = l * s->loop_radius;
             w *= 2.0 * j1(x) / x;
+            wx *= 2.0 * j1(x) / x;
         }
         lam[j] = l;
-        wgt[j] = w * j0(l * r) * MU0 / (4.0 * M_PI);
-        /* horizontal (x) secondary field of the vertical dipole: the same integrand with J1(lam r) dx / r */
-        wgtx[j] = w * j1(l * r) * s->rx_cx * MU0 / (4.0 * M_PI);
+        wgt[j] = w * MU0 / (4.0 * M_PI);
+        wgtx[j] = wx * MU0 / (4.0 * M_PI);
     }
 }
 
