@@ -128,6 +128,13 @@ __device__ __forceinline__ TopOut top_term(const float4 q0, const float4 q1, con
     return o;
 }
 
+// the Hankel sum of one frequency is complete: both warp sums in one folded reduction (same bits as two warp_sum calls)
+__device__ __forceinline__ void close_frequency(const c2& acc, float* __restrict__ pred, const int F, const int f, const int lane)
+{
+    const float v = warp_sum2(acc.re.x + acc.re.y, acc.im.x + acc.im.y, lane);
+    if ((lane & 15) == 0) pred[(lane >> 4) * F + f] = v;
+}
+
 }  // namespace f2
 
 // ---------------------------------------------------------------- forward only: two chunks per pass
@@ -172,33 +179,21 @@ __device__ __noinline__ void fdem_fwd_f2(const SysShared<float>& Q, const float*
                                    Q.hd0[fB] - 2.f * alt);
         // chunks are ordered by frequency: close a frequency when the next chunk belongs to another one
         if (fA != cur_f) {
-            const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
-            if (lane == 0) {
-                pred[cur_f] = sr;
-                pred[F + cur_f] = si;
-            }
+            close_frequency(acc, pred, F, cur_f, lane);
             acc = c2{S(0.f), S(0.f)};
             cur_f = fA;
         }
         acc = acc + tA.term;
         if (hasB) {
             if (fB != cur_f) {
-                const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
-                if (lane == 0) {
-                    pred[cur_f] = sr;
-                    pred[F + cur_f] = si;
-                }
+                close_frequency(acc, pred, F, cur_f, lane);
                 acc = c2{S(0.f), S(0.f)};
                 cur_f = fB;
             }
             acc = acc + tB.term;
         }
     }
-    const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
-    if (lane == 0) {
-        pred[cur_f] = sr;
-        pred[F + cur_f] = si;
-    }
+    close_frequency(acc, pred, F, cur_f, lane);
     __syncwarp();
 }
 
@@ -228,19 +223,31 @@ __device__ __noinline__ void fdem_sens_f2(const SysShared<float>& Q, const float
     for (int c = c0; c <= NCH; ++c) {
         const int f = c < NCH ? (int)Q.chunk_freq[c] : -2;
         if (f != cur_f) {
-            if (cur_f >= 0) {  // close frequency cur_f
-                const float sr = warp_sum(acc.re.x + acc.re.y), si = warp_sum(acc.im.x + acc.im.y);
-                if (lane == 0) {
-                    pred[cur_f] = sr;
-                    pred[F + cur_f] = si;
+            if (cur_f >= 0) {  // close frequency cur_f: 8 warp sums per folded reduction (same bits as warp_sum), the
+                // response and the first three layers in the first one, then four layers at a time; value i = 2 j + part
+                // (j = 0: response, j >= 1: layer k0 + j - 1) lands in lane vl, which stores it
+                const int vi = ((lane >> 4) & 1) | ((lane >> 2) & 2) | (lane & 4), part = vi & 1, slot = vi >> 1;
+                const bool writer = (lane & 3) == 0;
+                {
+                    const v2 z = S(0.f);
+                    const v2 a0 = L > 0 ? jr[0] : z, b0 = L > 0 ? ji[0] : z, a1 = L > 1 ? jr[1] : z, b1 = L > 1 ? ji[1] : z;
+                    const v2 a2 = L > 2 ? jr[2] : z, b2 = L > 2 ? ji[2] : z;
+                    const float v = warp_sum8(acc.re.x + acc.re.y, acc.im.x + acc.im.y, a0.x + a0.y, b0.x + b0.y, a1.x + a1.y,
+                                              b1.x + b1.y, a2.x + a2.y, b2.x + b2.y, lane);
+                    if (writer) {
+                        if (slot == 0) pred[part * F + cur_f] = v;
+                        else if (slot <= L) J[(part * F + cur_f) * KS + slot - 1] = v;
+                    }
                 }
 #pragma unroll 1
-                for (int k = 0; k < L; ++k) {
-                    const float a = warp_sum(jr[k].x + jr[k].y), b = warp_sum(ji[k].x + ji[k].y);
-                    if (lane == 0) {
-                        J[cur_f * KS + k] = a;
-                        J[(F + cur_f) * KS + k] = b;
-                    }
+                for (int k0 = 3; k0 < L; k0 += 4) {
+                    const v2 z = S(0.f);
+                    const v2 a0 = jr[k0], b0 = ji[k0], a1 = k0 + 1 < L ? jr[k0 + 1] : z, b1 = k0 + 1 < L ? ji[k0 + 1] : z;
+                    const v2 a2 = k0 + 2 < L ? jr[k0 + 2] : z, b2 = k0 + 2 < L ? ji[k0 + 2] : z;
+                    const v2 a3 = k0 + 3 < L ? jr[k0 + 3] : z, b3 = k0 + 3 < L ? ji[k0 + 3] : z;
+                    const float v = warp_sum8(a0.x + a0.y, b0.x + b0.y, a1.x + a1.y, b1.x + b1.y, a2.x + a2.y, b2.x + b2.y,
+                                              a3.x + a3.y, b3.x + b3.y, lane);
+                    if (writer && k0 + slot < L) J[(part * F + cur_f) * KS + k0 + slot] = v;
                 }
             }
             if (c >= NCH) break;
