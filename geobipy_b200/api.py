@@ -382,7 +382,8 @@ class Inference1D:
         self.seed, self.sounding_index = int(seed) & (2 ** 64 - 1), int(sounding_index)
         self.n_markov_chains, self.update_plot_every = int(n_markov_chains), int(update_plot_every)
         self.multiplier = np.float64(multiplier)   # carried and serialised, as in the reference (Inference1D.py:88, :1067)
-        self.interactive_plot, self.reciprocate_parameter, self.limits = bool(interactive_plot), False, None
+        # carried and serialised (Inference1D.py:88, :114, :1031): the options files of the reference set it
+        self.interactive_plot, self.reciprocate_parameter, self.limits = bool(interactive_plot), bool(kwargs.get("reciprocate_parameters", False)), None
         self.precision, self.device = precision, device
         self._raw_options = dict(kwargs, covariance_scaling=covariance_scaling, n_markov_chains=n_markov_chains,
                                  update_plot_every=update_plot_every, solve_gradient=int(bool(solve_gradient)),
@@ -451,10 +452,15 @@ class Inference1D:
         dp = self.datapoint if dp is None else dp
         one = lambda v: np.asarray([float(v)])
         if self._tdem:
-            from .tdem import TdemData
+            from .tdem import TdemData, TempestData
             tx, rx = dp.transmitter, dp.receiver
             z_in = getattr(dp, "z_input", float(tx.z))
             geometry = np.asarray([[tx.pitch, tx.roll, tx.yaw, rx.x - tx.x, rx.y - tx.y, float(rx.z) - float(tx.z), rx.pitch, rx.roll, rx.yaw]], dtype=np.float64)
+            if self._tempest:
+                d = TempestData(dp.system, one(dp.lineNumber), one(dp.fiducial), one(dp.x), one(dp.y), one(z_in), one(dp.elevation), geometry,
+                                np.asarray(dp.secondary_field, dtype=np.float64)[None], np.asarray(dp.primary_field, dtype=np.float64)[None])
+                d.additive_error = np.asarray(dp.additive_error, dtype=np.float64)[None]
+                return d
             return TdemData(dp.system, one(dp.lineNumber), one(dp.fiducial), one(dp.x), one(dp.y), one(z_in), one(dp.elevation), geometry,
                             np.asarray(dp.data, dtype=np.float64)[None])
         from .dataset import FdemData
@@ -468,15 +474,13 @@ class Inference1D:
         passes them): every group, dataset and attribute of the reference's file (geobipy_b200.hdf.create_line)."""
         from . import hdf
         assert self.datapoint is not None, ValueError("Inference needs a datapoint before creating HDF5 files.")
-        if getattr(self, "_tempest", False):
-            raise NotImplementedError("the HDF5 layout of a Tempest_datapoint (Tempest_datapoint.createHdf :566-586) is not built")
         if add_axis is None:
             raise NotImplementedError("createHdf without add_axis (a file for one sounding, no line axis) is not built: "
                                       "pass add_axis=1 for a one-sounding line")
         n = int(add_axis) if np.ndim(add_axis) == 0 else int(np.size(add_axis))
         hdf.create_line(parent, n, self.options, self._as_dataset(), n_markov_chains=self.n_markov_chains,
                         update_plot_every=self.update_plot_every, interactive_plot=self.interactive_plot,
-                        reciprocate_parameter=True)
+                        reciprocate_parameter=self.reciprocate_parameter)
         return parent
 
     def writeHdf(self, parent, index=None):
@@ -487,7 +491,9 @@ class Inference1D:
         assert getattr(self, "_result", None) is not None, "run infer() first"
         if index is None:
             index = int(np.searchsorted(np.asarray(parent["data/fiducial/data"][()]), float(self.datapoint.fiducial)))
-        hdf.write_line(parent, self._result, self.options, self._as_dataset(), np.asarray(self.best_datapoint.predictedData)[None],
+        bdp = self.best_datapoint   # (a Tempest line takes the predicted SECONDARY field and adds the primary field itself)
+        predicted = bdp.predicted_secondary_field if self._tempest else bdp.predictedData
+        hdf.write_line(parent, self._result, self.options, self._as_dataset(), np.asarray(predicted)[None],
                        rows=[int(index)], multiplier=float(self.multiplier))
         return parent
 

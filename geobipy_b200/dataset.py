@@ -287,9 +287,21 @@ class Inference3D:
         if index is None and fiducial is not None:
             index = int(np.flatnonzero((d.fiducial == fiducial) & ((d.lineNumber == line_number) if line_number is not None else True))[0])
         sel = np.arange(d.nPoints) if index is None else np.atleast_1d(index)
+        from .tdem import TempestData
+        if isinstance(d, TempestData):
+            # tempest_options: initial_additive_error is the additive level of every CHANNEL; what is sampled is one
+            # multiplier per component, starting at 1 (Tempest_datapoint.set_priors / set_proposals :478-510)
+            level = np.asarray(options["initial_additive_error"], dtype=np.float64).reshape(-1)
+            assert level.size == d.nChannels, ValueError("initial_additive_error must hold the additive level of every channel ({})".format(d.nChannels))
+            nc = d.n_components
+            options = dict(options, initial_additive_error=[1.0] * nc if nc > 1 else 1.0)
+            d.additive_error = np.tile(level, (d.nPoints, 1))
+            sysc = d.survey_struct(additive_level=level)
+        else:
+            sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct   # time-domain surveys: systems + tx-rx offset
         opt = ops.options_from_reference(**options)
         self.options = opt
-        sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct   # time-domain surveys: systems + tx-rx offset
+        self._struct = sysc
         import torch
         dev = torch.device("cuda", device)
 
@@ -333,7 +345,7 @@ class Inference3D:
             from . import hdf
             from .tdem import TdemData
             opt = self.options
-            sysc = d.c_struct if hasattr(d, "c_struct") else d.system.c_struct
+            sysc = self._struct
             idx_all = r["index"]
             k = r["scalars"][:, _lib.S_BEST_K].astype(np.int32)
             sig = np.where(np.isnan(r["best_sigma"]), 1.0, r["best_sigma"])

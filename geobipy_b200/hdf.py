@@ -113,6 +113,8 @@ def _grids(opt):
         e = np.atleast_2d(np.asarray(g[key], dtype=np.float64))
         # relative_to = 0.5 (max - min) of the bins (DataPoint.set_relative_error_posterior :673), a log10 mesh
         out[key] = [(np.log10(b) - np.log10(0.5 * (b.max() - b.min())), np.log10(0.5 * (b.max() - b.min()))) for b in e]
+        # the same bins on a mesh without log (Tempest_datapoint.set_additive_error_posterior :535-547)
+        out[key + "_linear"] = [(b - 0.5 * (b.max() - b.min()), 0.5 * (b.max() - b.min())) for b in e]
     return out
 
 
@@ -121,15 +123,17 @@ def create_line(parent, n, opt, data, n_markov_chains=None, update_plot_every=No
                 reciprocate_parameter=True):
     """`Inference2D.createHdf(parent, inference1d)` for a line of `n` soundings: every group, dataset, attribute and fill
     value of the reference's file.  `data` is the line's FdemData / TdemData (systems, channel count)."""
-    from .tdem import TdemData
+    from .tdem import TdemData, TempestData
     tdem = isinstance(data, TdemData)
-    nsys = 2 if opt.n_systems > 1 else 1
+    tempest = isinstance(data, TempestData)   # errors per component, additive levels per channel, data in fT
+    nsys = 2 if opt.n_systems > 1 else 1      # entries of the error arrays (systems; components of a Tempest datapoint)
     G = _grids(opt)
     C = int(data.nChannels)
-    d_units = _VM2 if tdem else "ppm"
+    d_units = "fT" if tempest else (_VM2 if tdem else "ppm")
+    tz = tdem and opt.solve_height            # solve_transmitter_z: the transmitter loop's z carries the posterior
 
     # ---- data (DataPoint.createHdf + Point.createHdf)
-    d = _group(parent, "data", "TdemData" if tdem else "FdemData")
+    d = _group(parent, "data", "TempestData" if tempest else ("TdemData" if tdem else "FdemData"))
     for key, label in (("x", "Easting"), ("y", "Northing"), ("z", "Height"), ("elevation", "Elevation")):
         if key == "z" and opt.solve_height and not tdem:    # a sampled height is a StatArray with its posterior (Point.py:1013-1020)
             z = _data_array(d, "z", n, label=label, units="m", repr_="StatArray")
@@ -140,31 +144,46 @@ def create_line(parent, n, opt, data, n_markov_chains=None, update_plot_every=No
             _data_array(d, key, n, label=label, units="m")
     _data_array(d, "fiducial", n, label="fiducial")
     _data_array(d, "line_number", n, label="Line number")
-    _data_array(d, "data", (n, C), label="Secondary field" if tdem else "Frequency domain data", units=d_units)
+    _data_array(d, "data", (n, C), label="Data" if tempest else ("Secondary field" if tdem else "Frequency domain data"), units=d_units)
     _data_array(d, "std", (n, C), label="Standard deviation", units=d_units)
-    _data_array(d, "predicted_data", (n, C), label="Predicted secondary field" if tdem else "Predicted Data", units=d_units)
-    for key, label, units, gkey in (("relative_error", "$\\epsilon_{Relative}x10^{2}$", "%", "rel_edges"),
-                                    ("additive_error", "$\\epsilon_{Additive}$", d_units, "add_edges")):
+    _data_array(d, "predicted_data", (n, C), label="Predicted Data" if (tempest or not tdem) else "Predicted secondary field",
+                units=d_units)
+    errs = [("relative_error", "$\\epsilon_{Relative}$" if tempest else "$\\epsilon_{Relative}x10^{2}$", "%", "rel_edges", 10)]
+    if tempest:
+        # Tempest_datapoint.createHdf :566-575: the additive level of every channel is a plain array, the sampled
+        # multiplier (one per component) carries the posteriors - log-spaced bins kept on a LINEAR mesh (:535-547)
+        _data_array(d, "additive_error", (n, C), label="$\\epsilon_{additive}$", units=d_units)
+        errs.append(("additive_error_multiplier", "Multiplier", None, "add_edges_linear", None))
+    else:
+        errs.append(("additive_error", "$\\epsilon_{Additive}$", d_units, "add_edges", 10))
+    for key, label, units, gkey, log in errs:
         e = _data_array(d, key, (n, nsys) if nsys > 1 else n, label=label, units=units, repr_="StatArray")
         e.create_dataset("n_posteriors", data=np.int64(nsys))
         for i in range(nsys):
             edges, _ = G[gkey][i]
-            _histogram(e, "posterior%d" % i if nsys > 1 else "posterior", n, edges, label, units, log=10, relative=True)
+            _histogram(e, "posterior%d" % i if nsys > 1 else "posterior", n, edges, label, units, log=log, relative=True)
     if tdem:
-        d.create_dataset("nSystems", data=np.int64(nsys))
+        d.create_dataset("nSystems", data=np.int64(len(data.system)))
         for i, s in enumerate(data.system):
             g = _group(d, "System%d" % i, "TdemSystem")
             g.attrs["data"] = list(s.stm_lines)          # the .stm file, line by line (TdemSystem_GAAEM.toHdf)
-        d.create_dataset("components", data=np.asarray([2], dtype=np.int32))      # 'z'
+        d.create_dataset("components", data=np.asarray([_ORI[c] for c in data.system[0].components], dtype=np.int32))
         lp = _group(d, "loop_pair", "Loop_pair")
         for key, label in (("x", "Easting"), ("y", "Northing"), ("z", "Height"), ("elevation", "Elevation")):
             _data_array(lp, key, n, label=label, units="m")
-        _loop(lp, "transmitter", n, "CircularLoops")
+        t = _loop(lp, "transmitter", n, "CircularLoops")
+        if tz:   # a sampled transmitter height: StatArray with its posterior (EmLoop.createHdf -> Point.createHdf :1403-1427)
+            z = t["z"]
+            z.attrs["repr"] = "StatArray"
+            z.create_dataset("n_posteriors", data=np.int64(1))
+            dz = opt.max_height_change
+            _histogram(z, "posterior", n, np.linspace(-dz, dz, opt.n_err_bins + 1), "Height", "m", relative=True)
         _loop(lp, "receiver", n, "CircularLoops")
-        _data_array(d, "primary_field", n, label="Primary field", units=_VM2)
-        _data_array(d, "secondary_field", (n, C), label="Secondary field", units=_VM2)
-        _data_array(d, "predicted_primary_field", n, label="Predicted primary field", units=_VM2)
-        _data_array(d, "predicted_secondary_field", (n, C), label="Predicted secondary field", units=_VM2)
+        pshape = (n, data.system[0].n_components) if tempest else n
+        _data_array(d, "primary_field", pshape, label="Primary field", units=d_units)
+        _data_array(d, "secondary_field", (n, C), label="Secondary field", units=d_units)
+        _data_array(d, "predicted_primary_field", pshape, label="Predicted primary field", units=d_units)
+        _data_array(d, "predicted_secondary_field", (n, C), label="Predicted secondary field", units=d_units)
     else:
         s = data.system
         g = _group(d, "sys", "FdemSystem")
@@ -181,7 +200,7 @@ def create_line(parent, n, opt, data, n_markov_chains=None, update_plot_every=No
     parent.create_dataset("interactive_plot", data=np.bool_(interactive_plot))
     parent.create_dataset("reciprocate_parameter", data=np.bool_(reciprocate_parameter))
     parent.create_dataset("n_markov_chains", data=np.int64(N))
-    parent.create_dataset("nsystems", data=np.int64(nsys))
+    parent.create_dataset("nsystems", data=np.int64(len(data.system) if tdem else 1))
     for key in ("iteration", "burned_in_iteration", "best_iteration"):
         parent.create_dataset(key, (n,), dtype=np.int64, fillvalue=0)
     parent.create_dataset("burned_in", (n,), dtype=np.bool_, fillvalue=0)
@@ -241,11 +260,12 @@ def write_line(parent, res, opt, data, predicted_best, rows=None, multiplier=1.0
     """`Inference1D.writeHdf` for every sounding of a block at once.
 
     res: the arrays `ops.rjmcmc_run` returned for the block (numpy, leading dimension m); data: the block's FdemData /
-    TdemData (m soundings); predicted_best [m, C]: forward response of each sounding's best model (the caller runs the
-    forward operator once for the block); rows: where the block's soundings sit in the file (default 0 .. m-1 - the
+    TdemData / TempestData (m soundings); predicted_best [m, C]: forward response of each sounding's best model (the caller
+    runs the forward operator once for the block; the secondary field - a Tempest line adds the primary field here); rows: where the block's soundings sit in the file (default 0 .. m-1 - the
     reference sorts a line by fiducial, Inference2D.createHdf :2011-2012)."""
-    from .tdem import TdemData
+    from .tdem import TdemData, TempestData
     tdem = isinstance(data, TdemData)
+    tempest = isinstance(data, TempestData)
     s = np.asarray(res["scalars"], dtype=np.float64)
     m = s.shape[0]
     rows = np.arange(m) if rows is None else np.asarray(rows)
@@ -270,28 +290,49 @@ def write_line(parent, res, opt, data, predicted_best, rows=None, multiplier=1.0
     rel = s[:, [L.S_BEST_REL, L.S_BEST_REL2][:nsys]]
     add = s[:, [L.S_BEST_ADD, L.S_BEST_ADD2][:nsys]]
     put(d + "relative_error/data", rel if nsys > 1 else rel[:, 0])
-    put(d + "additive_error/data", add if nsys > 1 else add[:, 0])
     off = [sy.off_time for sy in data.system] if tdem else None
-    put(d + "std/data", _std(tdem, obs, rel, add, off))
-    put(d + "predicted_data/data", predicted_best)
+    if tempest:   # the sampled "additive error" is the multiplier of the channels' additive levels, one per component
+        nt = data.system[0].nTimes
+        level = np.asarray(data.additive_error, dtype=np.float64)
+        put(d + "additive_error/data", level)
+        put(d + "additive_error_multiplier/data", add)
+        put(d + "std/data", np.sqrt((np.repeat(rel, nt, axis=1) * obs) ** 2 + (np.repeat(add, nt, axis=1) * level) ** 2))
+    else:
+        put(d + "additive_error/data", add if nsys > 1 else add[:, 0])
+        put(d + "std/data", _std(tdem, obs, rel, add, off))
+    if tempest:   # predicted data = predicted secondary + predicted primary field, which follows from the geometry alone
+        pprim = np.tile(ops.tdem_primary_field(data.survey_struct()), (m, 1))
+        put(d + "predicted_data/data", np.asarray(predicted_best) + np.repeat(pprim, nt, axis=1))
+    else:
+        put(d + "predicted_data/data", predicted_best)
     z_in = np.asarray(data.z, dtype=np.float64)
     z_best = s[:, L.S_BEST_HEIGHT] if opt.solve_height else z_in
-    for key, hkey in (("relative_error", "rel_hist"), ("additive_error", "add_hist")):
+    for key, hkey, gkey in (("relative_error", "rel_hist", "rel_edges"),
+                            ("additive_error_multiplier" if tempest else "additive_error", "add_hist",
+                             "add_edges_linear" if tempest else "add_edges")):
         hist = np.asarray(res[hkey]).reshape(m, nsys, -1)
         for i in range(nsys):
             p = d + key + ("/posterior%d" % i if nsys > 1 else "/posterior")
             put(p + "/values/data", hist[:, i])
             # (the reference hands every system's histogram the relative_to of the first one, StatArray.writeHdf)
-            put(p + "/mesh/y/relative_to/data", np.full(m, G["rel_edges" if key == "relative_error" else "add_edges"][0][1]))
+            put(p + "/mesh/y/relative_to/data", np.full(m, G[gkey][0][1]))
     if tdem:
         put(d + "z/data", z_in)
-        put(d + "secondary_field/data", obs)
-        put(d + "predicted_secondary_field/data", predicted_best)
-        put(d + "primary_field/data", np.zeros(m))
-        put(d + "predicted_primary_field/data", np.zeros(m))
+        if tempest:   # data = secondary + primary per component
+            put(d + "secondary_field/data", data.secondary_field)
+            put(d + "predicted_secondary_field/data", predicted_best)
+            put(d + "primary_field/data", data.primary_field)
+            put(d + "predicted_primary_field/data", pprim)
+        else:
+            put(d + "secondary_field/data", obs)
+            put(d + "predicted_secondary_field/data", predicted_best)
+            put(d + "primary_field/data", np.zeros(m))
+            put(d + "predicted_primary_field/data", np.zeros(m))
         tx, rx = data.transmitter, data.receiver
         lp = d + "loop_pair/"
-        dz = z_best - z_in                               # a sampled transmitter height moves both loops (Loop_pair.py:62-78)
+        # a sampled transmitter height: the forward sees both loops move (Loop_pair.Geometry hands gatdaem1d the height
+        # and the OFFSET, Loop_pair.py:62-78), the stored receiver loop keeps the z it was given
+        dz = z_best - z_in
         put(lp + "x/data", rx["x"] - tx["x"])
         put(lp + "y/data", rx["y"] - tx["y"])
         put(lp + "z/data", rx["z"] - tx["z"])
@@ -299,8 +340,11 @@ def write_line(parent, res, opt, data, predicted_best, rows=None, multiplier=1.0
         for name, q in (("transmitter", tx), ("receiver", rx)):
             for key in ("x", "y", "elevation", "pitch", "roll", "yaw", "moment", "radius"):
                 put(lp + name + "/" + key + "/data", q[key])
-            put(lp + name + "/z/data", q["z"] + dz)
+            put(lp + name + "/z/data", q["z"] + (dz if name == "transmitter" else 0.0))
             put(lp + name + "/orientation/data", q["orientation"])
+        if opt.solve_height:
+            put(lp + "transmitter/z/posterior/values/data", res["height_hist"])
+            put(lp + "transmitter/z/posterior/mesh/y/relative_to/data", s[:, L.S_HEIGHT_REF])
     else:
         put(d + "z/data", z_best)
         if opt.solve_height:

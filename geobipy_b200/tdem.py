@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib, ops
 from .api import Model
 
-__all__ = ["read_stm", "TdemSystem", "TdemLoop", "TdemDataPoint", "Tempest_datapoint", "TdemData"]
+__all__ = ["read_stm", "TdemSystem", "TdemLoop", "TdemDataPoint", "Tempest_datapoint", "TdemData", "TempestData"]
 
 
 def read_stm(filename):
@@ -380,7 +380,7 @@ class TdemData:
                     return df[low[n]].to_numpy(dtype=np.float64)
             assert default is not None, ValueError("column %s missing from %s" % (names[0], data_filename))
             return np.full(len(df), default)
-        n = sum(s.nTimes for s in system)
+        n = sum(s.nTimes * s.n_components for s in system)
         # TdemData._csv_channels (classes/data/dataset/TdemData.py:611-633): the data are the columns whose name contains
         # off_time / x_time / y_time / z_time, those that also contain "err" are their standard deviations; on_time
         # columns and the primary field (px, py, pz) are not data
@@ -400,10 +400,19 @@ class TdemData:
         self = cls(system, col("line_number", "line"), col("fiducial", "fid"), col("easting", "x"), col("northing", "y"),
                    col("height", "z"), col("elevation", "dtm", default=0.0), geometry,
                    df[dcols].to_numpy(dtype=np.float64))
+        # the primary field of every component (columns px / py / pz, sorted by name: TdemData._csv_channels :631-633)
+        pcols = sorted(c for c in df.columns if c.strip().lower() in ("px", "py", "pz"))
+        self._read_primary(df[pcols].to_numpy(dtype=np.float64) if pcols else None)
         # TdemData.read_csv :520-525: without error columns std = 0.1 * data (kept as std_from_file: the `std` getter
         # recomputes from the per-system errors, as the reference's does)
-        self.std = df[ecols].to_numpy(dtype=np.float64) if ecols else 0.1 * self.data
+        self.std = df[ecols].to_numpy(dtype=np.float64) if ecols else self._std_without_columns()
         return self
+
+    def _read_primary(self, primary):
+        pass   # a TdemData keeps the secondary field only (TdemData.read_csv :520-525); TempestData overrides
+
+    def _std_without_columns(self):
+        return 0.1 * self.data
 
     @property
     def std(self):
@@ -488,3 +497,94 @@ class TdemData:
         return TdemDataPoint(self.x[i], self.y[i], self.height[i], self.elevation[i], secondary_field=self.data[i],
                              system=self.system, transmitter_loop=tx, receiver_loop=rx, lineNumber=self.line_number[i],
                              fiducial=self.fiducial[i])
+
+
+class TempestData(TdemData):
+    """A fixed-wing Tempest survey (classes/data/dataset/TempestData.py): one system, X and Z components of the B field in
+    fT.  `secondary_field` [n, C] is what the file's S0X_time* / S0Z_time* columns hold, `primary_field` [n, components]
+    its PX / PZ columns (:251-252); `data` = secondary + primary per component (what a Tempest_datapoint inverts,
+    Tempest_datapoint.py:107-127).  Errors per COMPONENT: `relative_error` [n, components], `additive_error` [n, C] (the
+    additive level of every channel) times `additive_error_multiplier` [n, components] (TempestData.py:68-123)."""
+
+    def __init__(self, system, line_number, fiducial, x, y, height, elevation, geometry, secondary_field, primary_field=None):
+        super().__init__(system, line_number, fiducial, x, y, height, elevation, geometry, secondary_field)
+        assert len(self.system) == 1, NotImplementedError("a Tempest data set has one system")
+        n, nc = self._secondary.shape[0], self.n_components
+        self.primary_field = np.zeros((n, nc)) if primary_field is None else np.asarray(primary_field, np.float64).reshape(n, nc)
+        # what the reference's reader leaves behind (TempestData.__init__ :59-65 as read_csv returns it): all zero until the
+        # inversion's options set them
+        self.relative_error = np.zeros((n, nc))
+        self.additive_error = np.zeros((n, self.secondary_field.shape[1]))
+        self.additive_error_multiplier = np.zeros((n, nc))
+        self._std = np.zeros((n, self.secondary_field.shape[1]))
+
+    def _std_without_columns(self):
+        return np.zeros_like(self._secondary)   # TempestData.read_csv :255-258 assigns std only when the file has error columns
+
+    def _read_primary(self, primary):
+        if primary is not None:
+            assert primary.shape[1] == self.n_components, Exception("one primary-field column (PX / PY / PZ) per component")
+            self.primary_field = primary
+
+    @property
+    def n_components(self):
+        return self.system[0].n_components
+
+    @property
+    def secondary_field(self):
+        return self._secondary
+
+    @property
+    def nPoints(self):
+        return self._secondary.shape[0]
+
+    # TdemData keeps its channels in `data`; here that name is secondary + primary (TempestData / Tempest_datapoint.data)
+    @property
+    def data(self):
+        nt = self.system[0].nTimes
+        return self._secondary + np.repeat(self.primary_field, nt, axis=1)
+
+    @data.setter
+    def data(self, values):
+        self._secondary = np.asarray(values, dtype=np.float64)
+
+    @property
+    def std(self):
+        """The data set's std is the getter TempestData inherits from TdemData (classes/data/dataset/TdemData.py:269-278):
+        once a relative error is set, every channel of the one system takes the FIRST component's relative error and the
+        FIRST channel's additive level; before that, what the file gave (zeros without error columns).  The error model
+        the inversion uses is the datapoint's (`datapoint(i).std`, Tempest_datapoint.py:141-176)."""
+        if self.relative_error.max() > 0.0:
+            self._std = np.sqrt((self.relative_error[:, :1] * self.data) ** 2 + self.additive_error[:, :1] ** 2)
+        return self._std
+
+    @std.setter
+    def std(self, values):
+        self._std = values
+
+    def subset(self, idx):
+        out = TempestData(self.system, self.line_number[idx], self.fiducial[idx], self.x[idx], self.y[idx], self.height[idx],
+                          np.asarray(self.elevation)[idx], self.geometry[idx], self._secondary[idx], self.primary_field[idx])
+        out.std = np.asarray(self._std)[idx]
+        out.relative_error, out.additive_error = self.relative_error[idx], self.additive_error[idx]
+        out.additive_error_multiplier = self.additive_error_multiplier[idx]
+        return out
+
+    def survey_struct(self, additive_level=None):
+        """gbp_tdem_survey of the file; with the additive level of every channel (tempest_options' initial_additive_error)
+        it selects the Tempest error model of the sampler."""
+        g = self.geometry
+        assert np.all(g[:, [0, 1, 2, 6, 7, 8]] == 0.0), NotImplementedError("loop pitch / roll / yaw are not supported on the GPU path")
+        assert np.all(g[:, 3:6] == g[0, 3:6]), NotImplementedError("the transmitter-receiver offset must be constant over the file")
+        return ops.make_tdem_survey_struct([s.definition for s in self.system], tuple(g[0, 3:6]), additive_level=additive_level)
+
+    def datapoint(self, i):
+        g = self.geometry[i]
+        tx = TdemLoop(x=self.x[i], y=self.y[i], z=self.height[i])
+        rx = TdemLoop(x=self.x[i] + g[3], y=self.y[i] + g[4], z=self.height[i] + g[5])
+        dp = Tempest_datapoint(self.x[i], self.y[i], self.height[i], self.elevation[i], secondary_field=self._secondary[i],
+                               primary_field=self.primary_field[i], system=self.system, transmitter_loop=tx, receiver_loop=rx,
+                               lineNumber=self.line_number[i], fiducial=self.fiducial[i])
+        if self.relative_error[i].max() > 0.0:    # errors the data set carries go with the datapoint (TdemData.datapoint)
+            dp.relative_error, dp.additive_error = self.relative_error[i].copy(), self.additive_error[i].copy()
+        return dp

@@ -14,7 +14,7 @@ through oracle/ref_shims.py and records its outputs.  The GPU box never runs thi
     python tests/golden/make_golden.py transitions  # transitions.npz
     python tests/golden/make_golden.py chain <i> [rep]   # ref_chain_<i>[_r<rep>].npz (minutes each)
     python tests/golden/make_golden.py readers      # reader_files/ (heads of the reference's shipped data files) + readers.npz
-    python tests/golden/make_golden.py hdf fdem|fdem_height|tdem   # hdf_layout_<kind>.npz: the reference's own HDF5 result tree
+    python tests/golden/make_golden.py hdf fdem|fdem_height|tdem|tdem_height|tempest   # hdf_layout_<kind>.npz: the reference's own HDF5 result tree
 
 Files written
   resolve_clean.npz       the reference's own known-answer vectors
@@ -643,8 +643,23 @@ def make_hdf(kind="fdem", n_iter=1200, n_points=3, index=1):
     import contextlib
     h5lite = _h5lite_as_h5py()
     height = kind == "fdem_height"
-    if kind == "tdem":
+    if kind == "tempest":
+        kw = _tempest_setup()
+        from geobipy import Inference1D, get_prng
+        import oracle_py as O
+        tsys = O.make_tdem_system([O.tempest_definition()], rx_offset=(-107.0, 0.0, -45.0))
+        sec, prim = _tempest_observed(1, O, tsys)
+        z = 120.0
+        kw["n_markov_chains"] = 10000
+        kw["prng"] = get_prng(seed=4242)
+        inf = Inference1D(**kw)
+        dp = _tempest_datapoint(sec, prim)
+        with contextlib.redirect_stdout(io.StringIO()):
+            inf.initialize(dp)
+    elif kind in ("tdem", "tdem_height"):
         kw = _tdem_setup()
+        if kind == "tdem_height":
+            kw.update(TX_HEIGHT_KW)
         from geobipy import Inference1D, get_prng
         from geobipy_b200.synthetic import skytem_noise_std
         import oracle_py as O
@@ -694,9 +709,11 @@ def make_hdf(kind="fdem", n_iter=1200, n_points=3, index=1):
         a = np.asarray(a, dtype=np.float64).reshape(-1)
         out[:a.size] = a
         return out
-    ns = 2 if kind == "tdem" else 1
+    ns = 2 if kind in ("tdem", "tdem_height", "tempest") else 1
+    # a Tempest datapoint samples the multiplier of fixed per-channel additive levels (Tempest_datapoint.py:85-105)
+    add_of = (lambda q: q.additive_error_multiplier) if kind == "tempest" else (lambda q: q.additive_error)
     rel_hist = np.stack([np.asarray(d.relative_error.posterior[i].counts if ns > 1 else d.relative_error.posterior.counts, dtype=np.int32) for i in range(ns)])
-    add_hist = np.stack([np.asarray(d.additive_error.posterior[i].counts if ns > 1 else d.additive_error.posterior.counts, dtype=np.int32) for i in range(ns)])
+    add_hist = np.stack([np.asarray(add_of(d).posterior[i].counts if ns > 1 else add_of(d).posterior.counts, dtype=np.int32) for i in range(ns)])
     state = dict(
         hitmap=np.asarray(m.values.posterior.counts, dtype=np.int32), edges_hist=np.asarray(m.mesh.edges.posterior.counts, dtype=np.int32),
         ncells_hist=np.asarray(m.mesh.nCells.posterior.counts, dtype=np.int32), rel_hist=rel_hist if ns > 1 else rel_hist[0],
@@ -707,13 +724,23 @@ def make_hdf(kind="fdem", n_iter=1200, n_points=3, index=1):
         iteration=int(inf.iteration), burned_in=bool(inf.burned_in), burned_in_iteration=int(inf.burned_in_iteration),
         best_iteration=int(inf.best_iteration), best_k=int(bm.nCells.item()), cur_k=int(m.nCells.item()),
         halfspace=float(inf.halfspace.item()), multiplier=float(inf.multiplier),
-        cur_rel=np.asarray(d.relative_error, dtype=np.float64), cur_add=np.asarray(d.additive_error, dtype=np.float64),
-        best_rel=np.asarray(bd.relative_error, dtype=np.float64), best_add=np.asarray(bd.additive_error, dtype=np.float64),
+        cur_rel=np.asarray(d.relative_error, dtype=np.float64), cur_add=np.asarray(add_of(d), dtype=np.float64),
+        best_rel=np.asarray(bd.relative_error, dtype=np.float64), best_add=np.asarray(add_of(bd), dtype=np.float64),
         data=np.asarray(d.data, dtype=np.float64), std_best=np.asarray(bd.std, dtype=np.float64),
         predicted_best=np.asarray(bd.predictedData, dtype=np.float64), z_input=float(z),
         x=float(d.x), y=float(d.y), elevation=float(d.elevation), fiducial=fid, line_number=100.0, index=index, n_points=n_points)
-    if kind == "tdem":
+    if kind in ("tdem", "tdem_height", "tempest"):
         state.update(tx_z=float(np.asarray(bd.transmitter.z).item()), rx_z=float(np.asarray(bd.receiver.z).item()))
+    if kind == "tempest":
+        state.update(secondary=sec, primary=prim, additive_levels=np.asarray(bd.additive_error, dtype=np.float64),
+                     predicted_primary_best=np.asarray(bd.predicted_primary_field, dtype=np.float64),
+                     predicted_secondary_best=np.asarray(bd.predicted_secondary_field, dtype=np.float64))
+    if kind == "tdem_height":
+        tz = d.transmitter.z
+        state.update(height_hist=np.asarray(tz.posterior.counts, dtype=np.int32), cur_height=float(np.asarray(tz).item()),
+                     best_height=float(np.asarray(bd.transmitter.z).item()),
+                     height_edges=np.asarray(tz.posterior.mesh.edges, dtype=np.float64),
+                     height_relative_to=float(np.asarray(tz.posterior.mesh.relative_to).item()))
     if height:
         state.update(height_hist=np.asarray(d.z.posterior.counts, dtype=np.int32), cur_height=float(np.asarray(d.z).item()),
                      best_height=float(np.asarray(bd.z).item()),
@@ -765,6 +792,41 @@ def make_readers():
     rec["skytem_glacial/off_time1"] = np.asarray(d.system[1].off_time, dtype=np.float64)
     print("skytem", d.nPoints, "points", rec["skytem_glacial/data"].shape)
     np.savez_compressed(os.path.join(HERE, "readers.npz"), **rec)
+
+
+def make_readers_tempest():
+    """reader_files/tempest_glacial.csv + tempest.stm and readers_tempest.npz: the head of the Tempest file the reference
+    ships and what the reference's OWN TempestData.read_csv (classes/data/dataset/TempestData.py:140-273) makes of it."""
+    import fake_gatdaem1d
+    fake_gatdaem1d.install()
+    _geobipy()
+    from geobipy import TempestData
+    out_dir = os.path.join(HERE, "reader_files")
+    data_dir = os.path.join(SUP, "data")
+    with open(os.path.join(data_dir, "tempest_glacial.csv")) as f:
+        head = [next(f) for _ in range(7)]
+    with open(os.path.join(out_dir, "tempest_glacial.csv"), "w") as f:
+        f.writelines(head)
+    with open(os.path.join(data_dir, "tempest.stm")) as f, open(os.path.join(out_dir, "tempest.stm"), "w") as g:
+        g.write(f.read())
+    d = TempestData.read_csv(os.path.join(out_dir, "tempest_glacial.csv"), os.path.join(out_dir, "tempest.stm"))
+    rec = {}
+    for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data", "std", "primary_field", "secondary_field", "relative_error",
+              "additive_error", "additive_error_multiplier"):
+        rec[k] = np.array(getattr(d, k), dtype=np.float64, copy=True)
+    for who in ("transmitter", "receiver"):
+        lp = getattr(d.loop_pair, who)
+        for k in ("x", "y", "z", "pitch", "roll", "yaw", "radius"):
+            rec["%s_%s" % (who, k)] = np.asarray(getattr(lp, k), dtype=np.float64)
+    rec["off_time0"] = np.asarray(d.system[0].off_time, dtype=np.float64)
+    rec["components"] = np.asarray(d.components)
+    d.relative_error = np.tile([0.001, 0.002], (d.nPoints, 1))     # (the file gives none: 0, which a datapoint refuses)
+    d.additive_error = np.tile(np.linspace(0.01, 0.02, 30), (d.nPoints, 1))
+    dp = d.datapoint(2)
+    rec["dp2_data"], rec["dp2_std"] = np.asarray(dp.data, dtype=np.float64), np.asarray(dp.std, dtype=np.float64)
+    rec["std_with_errors"] = np.asarray(d.std, dtype=np.float64)
+    print("tempest", d.nPoints, "points", rec["data"].shape, rec["primary_field"].shape, rec["additive_error"].shape, rec["components"])
+    np.savez_compressed(os.path.join(HERE, "readers_tempest.npz"), **rec)
 
 
 def make_tempest():
@@ -948,6 +1010,8 @@ if __name__ == "__main__":
         make_tempest()
     if what == "readers":
         make_readers()
+    if what == "readers_tempest":
+        make_readers_tempest()
     if what == "hdf":
         make_hdf(sys.argv[2] if len(sys.argv) > 2 else "fdem")
     if what == "tdem":

@@ -32,8 +32,12 @@ def _inputs(kind, st):
     """The product's inputs for the golden's one written sounding: result arrays (as ops.rjmcmc_run returns them), the
     options and a one-sounding data set."""
     from geobipy_b200 import _lib, api, ops, tdem
-    tdem_kind = kind == "tdem"
-    if tdem_kind:
+    tdem_kind = kind in ("tdem", "tdem_height")
+    if kind == "tempest":
+        opt = ops.make_options(**dict(ops.TEMPEST_OPTIONS, n_markov_chains=10000))
+    elif kind == "tdem_height":   # solve_transmitter_z (make_golden.TX_HEIGHT_KW)
+        opt = ops.make_options(n_markov_chains=10000, solve_height=1, max_height_change=1.0, height_prop_var=0.01, **ops.SKYTEM_OPTIONS)
+    elif tdem_kind:
         opt = ops.make_options(n_markov_chains=10000, **ops.SKYTEM_OPTIONS)
     elif kind == "fdem_height":
         opt = ops.make_options(n_markov_chains=10000, solve_height=1, max_height_change=1.0, height_prop_var=0.01)
@@ -56,7 +60,13 @@ def _inputs(kind, st):
         res["height_hist"] = st["height_hist"][None]
     i = int(st["index"])
     one = lambda v: np.asarray([float(v)])
-    if tdem_kind:
+    if kind == "tempest":
+        system = [tdem.TdemSystem(definition=ops.tempest_definition())]
+        geometry = np.asarray([[0, 0, 0, -107.0, 0.0, -45.0, 0, 0, 0]], dtype=np.float64)
+        data = tdem.TempestData(system, one(st["line_number"]), st["fiducial"][i:i + 1], one(st["x"]), one(st["y"]), one(st["z_input"]),
+                                one(st["elevation"]), geometry, st["secondary"][None], st["primary"][None])
+        data.additive_error = st["additive_levels"][None]
+    elif tdem_kind:
         system = [tdem.TdemSystem(definition=d) for d in ops.skytem_definitions()]
         geometry = np.asarray([[0, 0, 0, -13.0, 0.0, 2.0, 0, 0, 0]], dtype=np.float64)
         data = tdem.TdemData(system, one(st["line_number"]), st["fiducial"][i:i + 1], one(st["x"]), one(st["y"]), one(st["z_input"]),
@@ -86,9 +96,12 @@ _SKIP_VALUES = {
     "data/loop_pair/transmitter/moment/data", "data/loop_pair/receiver/moment/data",
     "data/loop_pair/transmitter/orientation/data", "data/loop_pair/receiver/orientation/data",
 }
+# make_golden.py gave the Tempest datapoint loops of radius 1; a TempestData takes the radius from the .stm file (tempest.stm
+# has no ModellingLoopRadius: 0, as the reference's reader returns, tests/test_readers.py) - an input as well
+_SKIP_TEMPEST = {"data/loop_pair/transmitter/radius/data", "data/loop_pair/receiver/radius/data"}
 
 
-@pytest.mark.parametrize("kind", ["fdem", "fdem_height", "tdem"])
+@pytest.mark.parametrize("kind", ["fdem", "fdem_height", "tdem", "tdem_height", "tempest"])
 def test_line_file_matches_the_reference_tree(kind, tmp_path):
     from geobipy_b200 import h5lite, hdf
     meta, tree, st = _state(kind)
@@ -96,11 +109,12 @@ def test_line_file_matches_the_reference_tree(kind, tmp_path):
     n, i = int(st["n_points"]), int(st["index"])
     path = str(tmp_path / "line.h5")
     with h5lite.File(path, "w") as f:
-        hdf.create_line(f, n, opt, data)
+        hdf.create_line(f, n, opt, data, reciprocate_parameter=kind != "tempest")   # the options files' reciprocate_parameters
         # Inference2D.createHdf writes every sounding's line number and the sorted fiducials up front (:2008-2012)
         f["data/line_number/data"][:] = st["line_number"]
         f["data/fiducial/data"][:] = st["fiducial"]
-        hdf.write_line(f, res, opt, data, st["predicted_best"][None], rows=[i], multiplier=float(st["multiplier"]))
+        predicted = st["predicted_secondary_best" if kind == "tempest" else "predicted_best"]   # the forward operator's output
+        hdf.write_line(f, res, opt, data, predicted[None], rows=[i], multiplier=float(st["multiplier"]))
     f = h5lite.File(path, "r")      # through the file: what is compared went through the HDF5 encoder and decoder
     got = _walk(f)
     assert set(got) == set(meta), (sorted(set(meta) - set(got))[:10], sorted(set(got) - set(meta))[:10])
@@ -121,7 +135,7 @@ def test_line_file_matches_the_reference_tree(kind, tmp_path):
             continue
         a, ref = np.asarray(obj), tree[name]
         assert a.dtype.str == m["dtype"] and list(a.shape) == m["shape"], (name, a.dtype.str, a.shape, m["dtype"], m["shape"])
-        if name in _SKIP_VALUES:
+        if name in _SKIP_VALUES or (kind == "tempest" and name in _SKIP_TEMPEST):
             continue
         if a.dtype.kind == "f":
             assert np.allclose(a, ref, rtol=1e-12, atol=0.0, equal_nan=True), (name, a.reshape(-1)[:6], ref.reshape(-1)[:6])
@@ -223,7 +237,7 @@ def _rebuild(meta, tree, path):
     return path
 
 
-def _reference_reads(path, index, tdem):
+def _reference_reads(path, index, tdem, kind="fdem"):
     """What the reference's OWN readers (base/HDF/hdfRead.py read_item -> Model.fromHdf, Histogram.fromHdf,
     StatArray.fromHdf, FdemDataPoint.fromHdf ...) make of the line file at `path`, as plain arrays."""
     from geobipy_b200 import h5lite
@@ -243,7 +257,16 @@ def _reference_reads(path, index, tdem):
     out["hitmap.median"] = np.asarray(hm.median(axis=0).values, dtype=np.float64)
     out["hitmap.x_edges"] = np.asarray(hm.mesh.x.edges_absolute if hasattr(hm.mesh.x, "edges_absolute") else hm.mesh.x.edges, dtype=np.float64)
     out["hitmap.y_edges"] = np.asarray(hm.mesh.y.edges, dtype=np.float64)
-    for key in ("relative_error", "additive_error"):
+    if kind == "tempest":     # the levels are a plain array, the sampled multiplier carries the posteriors
+        out["additive_levels"] = np.asarray(hdfRead.read_item(f["data/additive_error"], index=index), dtype=np.float64)
+        for key in ("primary_field", "secondary_field", "predicted_primary_field", "predicted_secondary_field", "predicted_data", "std"):
+            out[key] = np.asarray(hdfRead.read_item(f["data/" + key], index=index), dtype=np.float64)
+    if kind == "tdem_height":   # the sampled transmitter height and its posterior
+        z = hdfRead.read_item(f["data/loop_pair/transmitter/z"], index=index)
+        out["tx_z"] = np.asarray(z, dtype=np.float64)
+        out["tx_z.posterior"] = np.asarray(z.posterior.counts)
+        out["tx_z.posterior.edges"] = np.asarray(z.posterior.mesh.edges_absolute, dtype=np.float64)
+    for key in ("relative_error", "additive_error_multiplier" if kind == "tempest" else "additive_error"):
         e = hdfRead.read_item(f["data/" + key], index=index)
         out[key] = np.asarray(e, dtype=np.float64)
         post = e.posterior if isinstance(e.posterior, list) else [e.posterior]
@@ -265,7 +288,7 @@ def _reference_reads(path, index, tdem):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/geobipy/src"), reason="the reference tree is only present in the build container")
-@pytest.mark.parametrize("kind", ["fdem", "fdem_height", "tdem"])
+@pytest.mark.parametrize("kind", ["fdem", "fdem_height", "tdem", "tdem_height", "tempest"])
 def test_the_reference_reads_a_file_the_product_wrote(kind, tmp_path):
     """The reference's OWN readers (base/HDF/hdfRead.py read_item and the fromHdf of Model, RectilinearMesh1D, Histogram,
     StatArray, FdemDataPoint, FdemSystem, CircularLoop) return the same objects from a line file geobipy_b200.hdf wrote as
@@ -278,7 +301,8 @@ def test_the_reference_reads_a_file_the_product_wrote(kind, tmp_path):
     had = sys.modules.get("h5py")
     sys.modules["h5py"] = m
     try:
-        if kind == "tdem":
+        td = kind in ("tdem", "tdem_height", "tempest")
+        if td:
             sys.path.insert(0, GOLDEN)
             import fake_gatdaem1d
             fake_gatdaem1d.install()
@@ -289,12 +313,13 @@ def test_the_reference_reads_a_file_the_product_wrote(kind, tmp_path):
         n, i = int(st["n_points"]), int(st["index"])
         ours = str(tmp_path / "ours.h5")
         with h5lite.File(ours, "w") as f:
-            hdf.create_line(f, n, opt, data)
+            hdf.create_line(f, n, opt, data, reciprocate_parameter=kind != "tempest")   # the options files' reciprocate_parameters
             f["data/line_number/data"][:] = st["line_number"]
             f["data/fiducial/data"][:] = st["fiducial"]
-            hdf.write_line(f, res, opt, data, st["predicted_best"][None], rows=[i], multiplier=float(st["multiplier"]))
+            predicted = st["predicted_secondary_best" if kind == "tempest" else "predicted_best"]   # the forward operator's output
+            hdf.write_line(f, res, opt, data, predicted[None], rows=[i], multiplier=float(st["multiplier"]))
         theirs = _rebuild(meta, tree, str(tmp_path / "theirs.h5"))
-        a, b = _reference_reads(ours, i, kind == "tdem"), _reference_reads(theirs, i, kind == "tdem")
+        a, b = _reference_reads(ours, i, td, kind), _reference_reads(theirs, i, td, kind)
         assert set(a) == set(b) and len(a) >= 20
         for k in b:
             assert a[k].shape == b[k].shape and np.allclose(a[k], b[k], rtol=1e-12, atol=0.0, equal_nan=True), k

@@ -46,3 +46,28 @@ def test_tdem_reader_on_the_reference_file(ref):
         for k in ("x", "y", "z", "pitch", "roll", "yaw", "radius"):
             assert np.array_equal(np.asarray(lp[k], dtype=np.float64), ref[key + who + "_" + k]), (who, k)
     assert np.allclose(d.system[0].off_time, ref[key + "off_time0"], rtol=1e-15) and np.allclose(d.system[1].off_time, ref[key + "off_time1"], rtol=1e-15)
+
+
+def test_tempest_reader_on_the_reference_file():
+    """TempestData.read_csv on the head of the Tempest file the reference ships, against the reference's own TempestData.read_csv
+    (classes/data/dataset/TempestData.py:140-273; tests/golden/make_golden.py readers_tempest): secondary field per component,
+    primary field PX / PZ, data = secondary + primary, the loops, and the reader's all-zero error arrays."""
+    from geobipy_b200.tdem import TempestData, Tempest_datapoint
+    ref = np.load(os.path.join(HERE, "golden", "readers_tempest.npz"))
+    d = TempestData.read_csv(os.path.join(FILES, "tempest_glacial.csv"), os.path.join(FILES, "tempest.stm"))
+    assert d.nPoints == 6 and d.nChannels == 30 and list(d.system[0].components) == list(ref["components"])
+    for k in ("lineNumber", "fiducial", "x", "y", "z", "elevation", "data", "std", "primary_field", "secondary_field", "relative_error",
+              "additive_error", "additive_error_multiplier"):
+        got = np.asarray(getattr(d, k), dtype=np.float64)
+        assert got.shape == ref[k].shape and np.array_equal(got, ref[k], equal_nan=True), k
+    for who in ("transmitter", "receiver"):
+        lp = getattr(d, who)
+        for k in ("x", "y", "z", "pitch", "roll", "yaw", "radius"):
+            assert np.array_equal(np.asarray(lp[k], dtype=np.float64), ref[who + "_" + k]), (who, k)
+    assert np.allclose(d.system[0].off_time, ref["off_time0"], rtol=1e-15)
+    # errors set on the data set: its own std (the getter inherited from TdemData) and the datapoint's (Tempest_datapoint.std)
+    d.relative_error = np.tile([0.001, 0.002], (6, 1))
+    d.additive_error = np.tile(np.linspace(0.01, 0.02, 30), (6, 1))
+    assert np.allclose(d.std, ref["std_with_errors"], rtol=1e-14)
+    dp = d.datapoint(2)
+    assert isinstance(dp, Tempest_datapoint) and np.array_equal(dp.data, ref["dp2_data"]) and np.allclose(dp.std, ref["dp2_std"], rtol=1e-14)

@@ -201,7 +201,7 @@ def test_inference3d_time_domain_survey(stm_files, tmp_path, golden_dir, built_l
 
 
 @pytest.mark.gpu
-def test_inference1d_with_tempest_datapoint(golden_dir, built_lib):
+def test_inference1d_with_tempest_datapoint(golden_dir, built_lib, tmp_path):
     """The reference's calling sequence with a Tempest_datapoint and the keys of tempest_options: `initial_additive_error` is
     the additive level of every channel, the sampled errors are one relative error and one multiplier per component."""
     from geobipy_b200 import _lib, api, ops, tdem
@@ -235,5 +235,98 @@ def test_inference1d_with_tempest_datapoint(golden_dir, built_lib):
                                  receiver_loop=tdem.TdemLoop(x=-107.0, z=75.0))
     chk.forward(inf.model)
     assert np.allclose(chk.predictedData, dp.predictedData) and inf.data_misfit < 18415.0
-    with pytest.raises(NotImplementedError):
-        inf.createHdf(None, add_axis=2)
+    # the result file of a Tempest line (Tempest_datapoint.createHdf / writeHdf :566-586: errors per component, the additive
+    # level of every channel, the sampled multiplier with its posteriors, data = secondary + primary)
+    from geobipy_b200 import h5lite
+    dp.fiducial = 20.0
+    with h5lite.File(str(tmp_path / "tempest.h5"), "w") as f:
+        inf.createHdf(f, add_axis=np.asarray([10.0, 20.0, 30.0]))
+        f["data/fiducial/data"][:] = [10.0, 20.0, 30.0]
+        inf.writeHdf(f)
+    h = h5lite.File(str(tmp_path / "tempest.h5"), "r")
+    assert h["data"].attrs["repr"] == "TempestData" and h["data/components"][()].tolist() == [0, 2]
+    assert np.allclose(h["data/additive_error/data"][1], ops.TEMPEST_ADDITIVE) and np.isnan(h["data/additive_error/data"][0]).all()
+    assert h["data/additive_error_multiplier/posterior1/values/data"][1].sum() == 600
+    assert np.allclose(h["data/additive_error_multiplier/data"][1], inf.best_additive_error)
+    assert np.allclose(h["data/data/data"][1], g["data"], rtol=1e-13) and np.allclose(h["data/secondary_field/data"][1], g["secondary"])
+    assert np.allclose(h["data/predicted_data/data"][1], inf.best_datapoint.predictedData, rtol=1e-12)
+    assert np.allclose(h["data/primary_field/data"][1], g["primary"]) and np.allclose(h["data/predicted_primary_field/data"][1], g["primary"], rtol=1e-9)
+    assert h["reciprocate_parameter"][()] == False and h["nsystems"][()] == 1
+
+
+def _tempest_csv(path, golden_dir, n=4):
+    """A Tempest survey file in the reference's layout (tests/data_checks/tempest_*_clean.csv: PX / PZ primary-field columns,
+    S0X_time_* / S0Z_time_* secondary-field columns) from the reference's known-answer vectors."""
+    g = np.load(os.path.join(golden_dir, "tempest_clean.npz"))
+    hdr = ("Line_number,Fiducial,Easting,Northing,Height,Elevation,tx_pitch,tx_roll,tx_yaw,txrx_dx,txrx_dy,txrx_dz,rx_pitch,rx_roll,rx_yaw,PX,PZ,"
+           + ",".join("S0X_time_%.3e" % t for t in g["times"]) + "," + ",".join("S0Z_time_%.3e" % t for t in g["times"]))
+    rows = [hdr]
+    for i in range(n):
+        rows.append(",".join(repr(float(v)) for v in [100.0 + (i // 2), i, float(i), 0.0, 120.0, 0.0, 0, 0, 0, -107.0, 0.0, -45.0, 0, 0, 0]
+                             + list(g["primary"][0, 10 * i]) + list(g["data"][0, 10 * i])))
+    with open(path, "w") as f:
+        f.write("\n".join(rows) + "\n")
+    return g
+
+
+def test_tempest_data_reader(tmp_path, golden_dir):
+    """TempestData.read_csv (classes/data/dataset/TempestData.py:140-273): the x_time / z_time columns are the secondary field, PX /
+    PZ the primary field of each component; `data` = secondary + primary (Tempest_datapoint.data :107-115)."""
+    from geobipy_b200 import ops, tdem
+    g = _tempest_csv(str(tmp_path / "tempest.csv"), golden_dir)
+    ds = tdem.TempestData.read_csv(str(tmp_path / "tempest.csv"), [tdem.TdemSystem(definition=ops.tempest_definition())])
+    assert ds.nPoints == 4 and ds.nChannels == 30 and ds.n_components == 2
+    assert np.array_equal(ds.secondary_field[1], g["data"][0, 10]) and np.array_equal(ds.primary_field[1], g["primary"][0, 10])
+    assert np.allclose(ds.data[1, :15], g["data"][0, 10, :15] + g["primary"][0, 10, 0], rtol=0, atol=0)
+    assert np.allclose(ds.data[1, 15:], g["data"][0, 10, 15:] + g["primary"][0, 10, 1], rtol=0, atol=0)
+    dp = ds.datapoint(1)
+    assert isinstance(dp, tdem.Tempest_datapoint) and np.array_equal(dp.data, ds.data[1])
+    sub = ds.subset(np.asarray([2, 3]))
+    assert sub.nPoints == 2 and np.array_equal(sub.primary_field, ds.primary_field[2:]) and np.array_equal(sub.lineNumber, [101.0, 101.0])
+    if os.path.isdir("/root/reference/tests/data_checks"):     # the reference's own file (build container)
+        ref = tdem.TempestData.read_csv("/root/reference/tests/data_checks/tempest_glacial_clean.csv", [tdem.TdemSystem(definition=ops.tempest_definition())])
+        assert ref.nPoints == 79 and np.array_equal(ref.secondary_field, g["data"][0]) and np.array_equal(ref.primary_field, g["primary"][0])
+
+
+@pytest.mark.gpu
+def test_inference3d_tempest_survey(tmp_path, golden_dir, built_lib):
+    """The survey driver on a Tempest CSV with the keys of tempest_options: per-channel additive levels, errors per component;
+    one `<line>.h5` per flight line in the layout of Tempest_datapoint.createHdf (:566-586)."""
+    from geobipy_b200 import _lib, api, h5lite, ops, tdem
+    from geobipy_b200.dataset import Inference3D
+    _lib.require_cuda()
+    _tempest_csv(str(tmp_path / "tempest.csv"), golden_dir)
+    ds = tdem.TempestData.read_csv(str(tmp_path / "tempest.csv"), [tdem.TdemSystem(definition=ops.tempest_definition())])
+    options = dict(n_markov_chains=400, solve_relative_error=True, initial_relative_error=[0.001, 0.001], minimum_relative_error=[0.0001, 0.0001],
+                   maximum_relative_error=[0.01, 0.01], relative_error_proposal_variance=[1e-6, 1e-6], solve_additive_error=True,
+                   initial_additive_error=np.asarray(ops.TEMPEST_ADDITIVE), additive_error_proposal_variance=1e-6,
+                   minimum_additive_error=[0.001, 0.001], maximum_additive_error=[100.0, 100.0], maximum_number_of_layers=30,
+                   minimum_depth=1.0, maximum_depth=550.0, minimum_thickness=None, probability_of_birth=1 / 6, probability_of_death=1 / 6,
+                   probability_of_perturb=1 / 6, probability_of_no_change=0.5, gradient_standard_deviation=5, covariance_scaling=0.5)
+    inv = Inference3D(ds, seed=3)
+    r = inv.infer(max_iterations=200, precision=64, **options)
+    assert (r["scalars"][:, _lib.S_ITER] == 200).all() and r["rel_hist"].shape == (4, 2, 99)
+    # the same chains through the one-sounding interface (Inference1D with a Tempest_datapoint)
+    inf = api.Inference1D(seed=3, precision=64, sounding_index=2, interactive_plot=False, save_hdf5=True, **options)
+    inf.initialize(ds.datapoint(2))
+    inf.infer(None, max_iterations=200)
+    assert np.array_equal(inf.hitmap.counts, r["hitmap"][2])
+    files = inv.save(str(tmp_path / "out"))
+    assert [os.path.basename(x) for x in files] == ["100.h5", "101.h5"]
+    h = h5lite.File(files[1], "r")
+    assert h["data"].attrs["repr"] == "TempestData" and h["data/nSystems"][()] == 1 and h["data/components"][()].tolist() == [0, 2]
+    assert np.array_equal(h["model/values/posterior/values/data"][()], r["hitmap"][2:])
+    assert np.array_equal(h["data/additive_error_multiplier/posterior1/values/data"][()], r["add_hist"][2:, 1])
+    assert np.allclose(h["data/additive_error/data"][()], np.tile(ops.TEMPEST_ADDITIVE, (2, 1)))
+    assert np.array_equal(h["data/secondary_field/data"][()], ds.secondary_field[2:]) and np.array_equal(h["data/primary_field/data"][()], ds.primary_field[2:])
+    assert np.allclose(h["data/data/data"][()], ds.data[2:], rtol=1e-15)
+    # predicted data of the best model of sounding 3 = predicted secondary + primary field of the geometry
+    dp = ds.datapoint(3)
+    kb = int(r["scalars"][3, _lib.S_BEST_K])
+    dp.forward(api.Model(api.RectilinearMesh1D(edges=r["best_edges"][3, :kb + 1]), r["best_sigma"][3, :kb]))
+    assert np.allclose(h["data/predicted_data/data"][1], dp.predictedData, rtol=1e-10)
+    assert np.allclose(h["data/predicted_secondary_field/data"][1], dp.predicted_secondary_field, rtol=1e-10)
+    best_rel = r["scalars"][3][[_lib.S_BEST_REL, _lib.S_BEST_REL2]]
+    best_mul = r["scalars"][3][[_lib.S_BEST_ADD, _lib.S_BEST_ADD2]]
+    std = np.sqrt((np.repeat(best_rel, 15) * ds.data[3]) ** 2 + (np.repeat(best_mul, 15) * np.asarray(ops.TEMPEST_ADDITIVE)) ** 2)
+    assert np.allclose(h["data/std/data"][1], std, rtol=1e-12)
