@@ -712,8 +712,7 @@ int gbp_rjmcmc_run(const gbp_fdem_system* sys, const gbp_options* opt, int B, co
         // resident chains per SM: 16 (128 registers).  The SM's throughput saturates at ~16 warps (full waves of
         // equal-length chains: 16 -> 34.7 M, 28 -> 36.6 M evals/s), and fewer, faster chains shorten the tail of real
         // batches: 4096 soundings to termination 16: 1936 ms, 20: 2019, 24: 2086, 28: 2163 (profiles/README.md);
-        // 8192 and 16384 soundings: equal.  GBP_FDEM_WARPS=28 selects the 72-register build.
-        const char* e = std::getenv("GBP_FDEM_WARPS");
+        // 8192 and 16384 soundings: equal (measured with the 20 / 24 / 28-warp builds of round 1, since removed).
         return small ? launch_chain<float, float, 12, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st)
                      : launch_chain<float, float, GBP_MAXC, 16, KIND_FDEM>(sd, tc->d_f32, tb, P, st);
     }

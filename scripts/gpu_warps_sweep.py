@@ -1,4 +1,6 @@
-"""Resident chains per SM (frequency-domain fp32 kernel): full waves and the bench-size batch (run under gpurun)."""
+"""Resident chains per SM (frequency-domain fp32 kernel): full waves and the bench-size batch (run under gpurun).
+Historical: needs the 20 / 24 / 28-warp instantiations of round 1 behind GBP_FDEM_WARPS (commit 43c46c2 .. 795c10d); the
+current library builds the 16-warp kernel only and ignores the variable."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
