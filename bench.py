@@ -722,19 +722,25 @@ def run_mixed_arm(args):
         shapes = ops.chain_buffer_shapes(opt, len(idx))
         bufs = {n: torch.zeros(shapes[n][0], dtype=tdt[shapes[n][1]], device=dev) for n in outputs}
         parts.append(dict(wl=wl, system=system, opt=opt, data=data, alt=t["height"], bufs=bufs, n=len(idx), first=int(idx[0])))
-    iters_dev = torch.zeros((), dtype=torch.float64, device=dev)
+    # the two datapoint kinds are independent launches of two persistent kernels: each on its own stream (--streams 1: one
+    # after the other), so that the tail of one kind's chains runs under the other kind's bulk (DESIGN.md "Batches overlap")
+    ns = 1 if args.streams == 1 else 2
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(ns)] if ns > 1 else [main, main]
+    iters_part = [torch.zeros((), dtype=torch.float64, device=dev) for _ in parts]
 
     def step(i, count=True):
         out = []
-        for p in parts:
-            # sounding index of the random stream: position within this kind's list (streams stay sharding independent)
-            r = ops.rjmcmc_run(p["system"], p["opt"], p["data"], p["alt"], seed=SEED + i, first_index=p["first"] // 2,
-                               precision=args.precision, outputs=outputs, buffers=p["bufs"])
-            if count:
-                iters_dev.add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
-            # interface probability per sounding (Inference2D.interface_probability)
-            e = r["edges_hist"].to(torch.float64)
-            out.append((r, e / e.sum(dim=1, keepdim=True).clamp_min(1.0)))
+        for j, p in enumerate(parts):
+            with torch.cuda.stream(streams[j % len(streams)]):
+                # sounding index of the random stream: position within this kind's list (streams stay sharding independent)
+                r = ops.rjmcmc_run(p["system"], p["opt"], p["data"], p["alt"], seed=SEED + i, first_index=p["first"] // 2,
+                                   precision=args.precision, outputs=outputs, buffers=p["bufs"])
+                if count:
+                    iters_part[j].add_(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+                # interface probability per sounding (Inference2D.interface_probability)
+                e = r["edges_hist"].to(torch.float64)
+                out.append((r, e / e.sum(dim=1, keepdim=True).clamp_min(1.0)))
         return out
 
     def barrier():
@@ -751,15 +757,21 @@ def run_mixed_arm(args):
     launches0 = ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
+    ev0.record(main)
+    if ns > 1:
+        for st in streams:
+            st.wait_event(ev0)
     for i in range(args.steps):
         res = step(i)
-    ev1.record()
+    if ns > 1:
+        for st in streams:
+            main.wait_stream(st)
+    ev1.record(main)
     barrier()
     launches = ops.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    iters = iters_dev.clone().reshape(1)
+    iters = torch.stack(iters_part).sum().reshape(1)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(iters, op=dist.ReduceOp.SUM)
@@ -772,13 +784,29 @@ def run_mixed_arm(args):
     del res
     torch.cuda.empty_cache()
     barrier()
+
+    n_e2e = 2   # host calls per kind, back to back on that kind's thread
+
+    def host_call(px, n=n_e2e):
+        p, x = px
+        its, nbytes = 0.0, 0
+        for i in range(n):
+            r = ops.rjmcmc_run(p["system"], p["opt"], x["data"], x["alt"], seed=SEED + i, first_index=p["first"] // 2,
+                               precision=args.precision, device=local_rank, outputs=outputs)
+            its += float(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
+            nbytes = sum(v.nbytes for v in r.values())
+        return its, nbytes
+    for px in zip(parts, h):   # untimed: the library's host-path buffers are allocated on first use
+        host_call(px, 1)
+    barrier()
     t0 = time.perf_counter()
-    e_iters, d2h = 0.0, 0
-    for p, x in zip(parts, h):
-        r = ops.rjmcmc_run(p["system"], p["opt"], x["data"], x["alt"], seed=SEED, first_index=p["first"] // 2,
-                           precision=args.precision, device=local_rank, outputs=outputs)
-        e_iters += float(r["scalars"][:, _lib.S_TOTAL_ITER].sum())
-        d2h += sum(v.nbytes for v in r.values())
+    if ns > 1:   # one host thread per kind (the library keeps two sets of device buffers with their own streams; ctypes drops the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(2) as ex:
+            got = list(ex.map(host_call, zip(parts, h)))
+    else:
+        got = [host_call(px) for px in zip(parts, h)]
+    e_iters, d2h = sum(g[0] for g in got), sum(g[1] for g in got)
     torch.cuda.synchronize()
     el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     ei = torch.tensor([e_iters], dtype=torch.float64, device=dev)
@@ -795,10 +823,13 @@ def run_mixed_arm(args):
                                    "n_markov_chains=%d, posterior hitmaps + interface probabilities" % (B, args.chains),
                        "soundings_per_gpu": B, "soundings_total": B * world, "n_markov_chains": args.chains,
                        "options": "resolve_options / skytem_options", "parallelism": "shard%d" % world,
-                       "l2": "no flush needed: each step rewrites GBs of posterior arrays per GPU (> 126 MB L2)"},
+                       "l2": "no flush needed: each step rewrites GBs of posterior arrays per GPU (> 126 MB L2)",
+                       "pipelining": ("the two kinds run on two CUDA streams (two persistent kernels, separate result buffers): the tail of one "
+                                      "kind's chains overlaps the other kind's bulk" if ns > 1 else "one kind after the other on one stream")},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": float(ei.item()) / float(el.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": 1, "api": "geobipy_b200.ops.rjmcmc_run(numpy), one call per datapoint kind"},
+                    "steps": n_e2e, "calls_in_flight": 2 if ns > 1 else 1,
+                    "api": "geobipy_b200.ops.rjmcmc_run(numpy), one call per datapoint kind" + (", one host thread per kind" if ns > 1 else "")},
         }
         print(json.dumps(line))
     if world > 1:
