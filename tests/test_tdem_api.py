@@ -330,3 +330,35 @@ def test_inference3d_tempest_survey(tmp_path, golden_dir, built_lib):
     best_mul = r["scalars"][3][[_lib.S_BEST_ADD, _lib.S_BEST_ADD2]]
     std = np.sqrt((np.repeat(best_rel, 15) * ds.data[3]) ** 2 + (np.repeat(best_mul, 15) * np.asarray(ops.TEMPEST_ADDITIVE)) ** 2)
     assert np.allclose(h["data/std/data"][1], std, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_inference3d_time_domain_survey_with_sampled_transmitter_height(stm_files, tmp_path, golden_dir, built_lib):
+    """solve_transmitter_z through the survey driver: the transmitter loop's z of the line file is a StatArray with its posterior
+    (EmLoop.createHdf -> Point.createHdf :1403-1427), the stored receiver loop keeps the z it was given (golden:
+    tests/golden/hdf_layout_tdem_height.npz, recorded from the reference's own writer)."""
+    from geobipy_b200 import _lib, h5lite, ops, tdem
+    from geobipy_b200.dataset import Inference3D
+    _lib.require_cuda()
+    g = np.load(os.path.join(golden_dir, "skytem_clean.npz"))
+    hdr = ("Line_number,Fiducial,Easting,Northing,Height,Elevation,tx_pitch,tx_roll,tx_yaw,txrx_dx,txrx_dy,txrx_dz,rx_pitch,rx_roll,rx_yaw,"
+           + ",".join("S0Z_time_%.3e" % t for t in g["times"][:26]) + "," + ",".join("S1Z_time_%.3e" % t for t in g["times"][26:]))
+    rows = [hdr]
+    for i in range(3):
+        rows.append(",".join(repr(float(v)) for v in [100.0, i, float(i), 0.0, 30.0, 0.0, 0, 0, 0, -13.0, 0.0, 2.0, 0, 0, 0] + list(g["data"][0, 10 * i])))
+    f = tmp_path / "skytem.csv"
+    f.write_text("\n".join(rows) + "\n")
+    ds = tdem.TdemData.read_csv(str(f), [p for p, _ in stm_files])
+    inv = Inference3D(ds, seed=5)
+    r = inv.infer(n_markov_chains=400, max_iterations=300, solve_transmitter_z=True, maximum_transmitter_z_change=1.0,
+                  transmitter_z_proposal_variance=0.01, **{k: v for k, v in ops.SKYTEM_OPTIONS.items()})
+    assert r["height_hist"].shape == (3, 99) and (r["height_hist"].sum(axis=1) == 300).all()
+    files = inv.save(str(tmp_path / "out"))
+    h = h5lite.File(files[0], "r")
+    z = h["data/loop_pair/transmitter/z"]
+    assert z.attrs["repr"] == "StatArray" and z["n_posteriors"][()] == 1
+    assert np.array_equal(z["posterior/values/data"][()], r["height_hist"])
+    assert np.allclose(z["posterior/mesh/y/relative_to/data"][()], r["scalars"][:, _lib.S_HEIGHT_REF])
+    assert np.allclose(z["posterior/mesh/y/edges/data"][()], np.linspace(-1.0, 1.0, 100))
+    assert np.allclose(z["data"][()], r["scalars"][:, _lib.S_BEST_HEIGHT]) and np.all(np.abs(z["data"][()] - 30.0) <= 1.0)
+    assert np.allclose(h["data/loop_pair/receiver/z/data"][()], 32.0) and np.allclose(h["data/z/data"][()], 30.0)
