@@ -566,7 +566,8 @@ def run_b200_arm(args):
                 b.resize_(0)  # free the device-resident result buffers: the host path allocates its own
         del bufsets, res, r
         torch.cuda.empty_cache()
-        n_e2e = max(ne, min(args.steps, 4)) if ne == 1 else 4   # two calls in flight: 4 steps, so that the pipeline is not all ramp
+        # two calls in flight: at least 4 steps, so that the pipeline is not all ramp (as many as the device-timed region, up to 8)
+        n_e2e = max(ne, min(args.steps, 4)) if ne == 1 else max(4, min(args.steps, 8))
 
         def host_step(i):
             rr = ops.rjmcmc_run(system, opt, h_data, h_alt, seed=SEED + i, first_index=first, precision=args.precision,
