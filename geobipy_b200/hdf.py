@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib, ops
 
-__all__ = ["h5", "create_line", "write_line", "save_line"]
+__all__ = ["h5", "create_line", "write_line", "save_line", "read_line"]
 
 _SIEMENS = "$\\frac{S}{m}$"
 _VM2 = "$\\frac{V}{m^{2}}$"
@@ -379,3 +379,55 @@ def save_line(filename, res, opt, data, predicted_best, **kwargs):
         create_line(f, order.size, opt, data, **{k: v for k, v in kwargs.items() if k != "multiplier"})
         write_line(f, res, opt, data, predicted_best, rows=rows, multiplier=kwargs.get("multiplier", 1.0))
     return filename
+
+
+def read_line(filename_or_group):
+    """The arrays of a line file back in the form `ops.rjmcmc_run` returns them (what `write_line` took): posterior histograms,
+    traces, best models and the scalar columns that the file holds (best errors, heights, iterations, burn-in, half-space),
+    plus `fiducial`, `line_number`, `x`, `y`, `z`, `elevation`, `data`, `predicted_data`, `std` and the bin `edges` of every
+    posterior - enough for `dataset.summarise_device` and the per-line products without the reference installed.  Works on the
+    files of the reference's own writer as well (same layout)."""
+    f = h5().File(filename_or_group, "r") if isinstance(filename_or_group, str) else filename_or_group
+    L = _lib
+
+    def get(path):
+        return np.asarray(f[path][()])
+    n = int(get("data/fiducial/data").size)
+    out = dict(hitmap=get("model/values/posterior/values/data"), edges_hist=get("model/mesh/y/edges/posterior/values/data"),
+               ncells_hist=get("model/mesh/nCells/posterior/values/data"), misfit_trace=get("phids/data"),
+               accept_trace=get("acceptance_rate/data"), best_sigma=get("model/values/data"), best_edges=get("model/mesh/y/edges/data"))
+    for key in ("fiducial", "line_number", "x", "y", "z", "elevation", "data", "predicted_data", "std"):
+        out[key] = get("data/%s/data" % key)
+    s = np.zeros((n, L.NSCALARS))
+    s[:, L.S_ITER], s[:, L.S_BURNED_IN_ITER], s[:, L.S_BEST_ITER] = get("iteration"), get("burned_in_iteration"), get("best_iteration")
+    s[:, L.S_BURNED_IN], s[:, L.S_HALFSPACE], s[:, L.S_BEST_K] = get("burned_in"), get("halfspace/data"), get("model/mesh/nCells/data")
+    s[:, L.S_BEST_HEIGHT] = s[:, L.S_HEIGHT_REF] = out["z"]
+    tempest = "data/additive_error_multiplier" in f
+    rel = get("data/relative_error/data").reshape(n, -1)
+    add = get("data/additive_error_multiplier/data" if tempest else "data/additive_error/data").reshape(n, -1)
+    s[:, L.S_BEST_REL], s[:, L.S_BEST_ADD] = rel[:, 0], add[:, 0]
+    nsys = rel.shape[1]
+    if nsys > 1:
+        s[:, L.S_BEST_REL2], s[:, L.S_BEST_ADD2] = rel[:, 1], add[:, 1]
+    hists = {}
+    for key, name in (("relative_error", "rel_hist"), ("additive_error_multiplier" if tempest else "additive_error", "add_hist")):
+        posts = ["data/%s/posterior%s" % (key, ("%d" % i) if nsys > 1 else "") for i in range(nsys)]
+        hists[name] = np.stack([get(p_ + "/values/data") for p_ in posts], axis=1)
+        out[name + "_edges"] = np.stack([get(p_ + "/mesh/y/edges/data") for p_ in posts])
+    out["rel_hist"], out["add_hist"] = (hists["rel_hist"], hists["add_hist"]) if nsys > 1 else (hists["rel_hist"][:, 0], hists["add_hist"][:, 0])
+    for zpath in ("data/z", "data/loop_pair/transmitter/z"):     # a sampled (transmitter) height and its posterior
+        if zpath + "/posterior" in f:
+            out["height_hist"] = get(zpath + "/posterior/values/data")
+            s[:, L.S_BEST_HEIGHT] = get(zpath + "/data")
+            s[:, L.S_HEIGHT_REF] = get(zpath + "/posterior/mesh/y/relative_to/data")
+            out["height_edges"] = get(zpath + "/posterior/mesh/y/edges/data")
+    out["scalars"] = s
+    # the posteriors' bins as stored: conductivity bins are log10 and relative to each sounding's half-space value
+    out["sigma_edges_log10_relative"] = get("model/values/posterior/mesh/y/edges/data")
+    out["sigma_relative_to_log10"] = get("model/values/posterior/mesh/y/relative_to/data")
+    out["depth_edges"] = get("model/values/posterior/mesh/z/edges/data")
+    if tempest:
+        out["additive_level"] = get("data/additive_error/data")
+        for key in ("primary_field", "secondary_field", "predicted_primary_field", "predicted_secondary_field"):
+            out[key] = get("data/%s/data" % key)
+    return out

@@ -330,3 +330,37 @@ def test_the_reference_reads_a_file_the_product_wrote(kind, tmp_path):
             sys.modules["h5py"] = had
         else:
             sys.modules.pop("h5py", None)
+
+
+@pytest.mark.parametrize("kind", ["fdem", "fdem_height", "tdem", "tdem_height", "tempest"])
+def test_read_line_returns_what_write_line_took(kind, tmp_path):
+    """hdf.read_line gives a line file back in the form of the sampler's result arrays - from a file the product wrote and from
+    the tree the reference's own writer produced (same layout)."""
+    from geobipy_b200 import _lib, h5lite, hdf
+    meta, tree, st = _state(kind)
+    opt, res, data = _inputs(kind, st)
+    n, i = int(st["n_points"]), int(st["index"])
+    path = str(tmp_path / "line.h5")
+    with h5lite.File(path, "w") as f:
+        hdf.create_line(f, n, opt, data, reciprocate_parameter=kind != "tempest")
+        f["data/line_number/data"][:] = st["line_number"]
+        f["data/fiducial/data"][:] = st["fiducial"]
+        predicted = st["predicted_secondary_best" if kind == "tempest" else "predicted_best"]
+        hdf.write_line(f, res, opt, data, predicted[None], rows=[i], multiplier=float(st["multiplier"]))
+    theirs = _rebuild(meta, tree, str(tmp_path / "theirs.h5"))
+    for p in (path, theirs):
+        r = hdf.read_line(p)
+        for key in ("hitmap", "edges_hist", "ncells_hist", "rel_hist", "add_hist", "misfit_trace", "accept_trace"):
+            assert np.array_equal(r[key][i], res[key][0]), (p, key)
+        k = int(st["best_k"])
+        assert np.allclose(r["best_sigma"][i, :k], st["best_sigma"][:k], rtol=1e-15) and np.allclose(r["best_edges"][i, :k], st["best_edges"][:k], rtol=1e-15)
+        s, s0 = r["scalars"][i], res["scalars"][0]
+        for col in (_lib.S_ITER, _lib.S_BURNED_IN, _lib.S_BURNED_IN_ITER, _lib.S_BEST_ITER, _lib.S_BEST_K, _lib.S_HALFSPACE, _lib.S_BEST_REL,
+                    _lib.S_BEST_ADD, _lib.S_BEST_HEIGHT):
+            assert np.isclose(s[col], s0[col], rtol=1e-14), (p, col, s[col], s0[col])
+        if "height_hist" in res:
+            assert np.array_equal(r["height_hist"][i], res["height_hist"][0]) and np.isclose(s[_lib.S_HEIGHT_REF], s0[_lib.S_HEIGHT_REF])
+        assert r["fiducial"].shape == (n,) and np.allclose(r["data"][i], st["data"], rtol=1e-15)
+        assert r["depth_edges"].size == r["hitmap"].shape[2] + 1 and r["sigma_edges_log10_relative"].size == r["hitmap"].shape[1] + 1
+        if kind == "tempest":
+            assert np.allclose(r["additive_level"][i], st["additive_levels"]) and np.allclose(r["primary_field"][i], st["primary"])
